@@ -1,0 +1,273 @@
+/*
+ * semk.h -- C ABI of libsemk, the sm_100a spectral-element operator engine.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * nchisholm/SpectralElementMethod that this repository accelerates:
+ *
+ *     per-element geometric factors -> matrix-free Poisson stiffness apply ->
+ *     global assembly over the local-to-global (L2G) node map with Dirichlet
+ *     masking -> Jacobi-preconditioned conjugate gradients.
+ *
+ * The reference has no FFI of its own (it is pure Python); each entry point
+ * below names the reference code it replaces (path:line under the reference
+ * tree).  The Python binding a maintainer would add is in INTEGRATION.md and
+ * is what spectralelementmethod_b200/_lib.py implements with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.
+ *   - every function returns an int status: 0 = ok, <0 = error
+ *     (semk_last_error() gives the message for the calling thread).
+ *   - "device" pointers are caller-owned device memory (torch tensors'
+ *     data_ptr()), contiguous, 16-byte aligned.  The library allocates no
+ *     device memory except inside the *_host convenience entry points.
+ *   - stream is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - element fields are C-ordered [m][n] = (xi0 index, xi1 index), n1 = p+1
+ *     points per direction, NN = n1*n1; node ids are uint32 like the
+ *     reference's node maps (sem/discrete.py:1044).
+ */
+#ifndef SEMK_H
+#define SEMK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEMK_VERSION 100          /* 0.1.0 */
+#define SEMK_MAX_N1 17            /* orders 1..16 */
+
+/* status codes */
+#define SEMK_OK 0
+#define SEMK_ERR_INVALID (-1)     /* bad argument (ValueError in the Python mirror) */
+#define SEMK_ERR_CUDA (-2)        /* CUDA runtime error */
+#define SEMK_ERR_JACOBIAN (-3)    /* non-positive Jacobian (AssertionError, sem/mapping.py:117) */
+#define SEMK_ERR_BREAKDOWN (-4)   /* PCG breakdown: pAp <= 0 or non-finite (SolverFailure) */
+#define SEMK_ERR_UNSUPPORTED (-5) /* order / size outside the compiled range (NotImplementedError) */
+
+/* node-table flag bits (upper bits of the uint32 entries of plan tables) */
+#define SEMK_NODE_ID_MASK 0x3fffffffu
+#define SEMK_NODE_SHARED 0x40000000u
+#define SEMK_NODE_DIRICHLET 0x80000000u
+
+/* apply flags */
+#define SEMK_MASK_IN 1            /* treat Dirichlet entries of the input as zero      */
+#define SEMK_MASK_OUT 2           /* zero the Dirichlet rows of the result              */
+#define SEMK_DIRICHLET_IDENTITY 4 /* with MASK_OUT: y_D = u_D instead of 0 (SPD system) */
+
+int semk_version(void);
+const char *semk_last_error(void);
+/* 1 if a CUDA device is usable from this process, else 0 (never an error). */
+int semk_device_available(void);
+
+/* ------------------------------------------------------------------------
+ * Host-side plan: groups elements into patches (one CTA each), builds the
+ * patch node tables, the per-element patch-local index table, the in-patch
+ * colouring and the deterministic interface reduction lists.  Pure host
+ * code, no CUDA call -- usable (and tested) without a GPU.
+ *
+ * Replaces the bookkeeping of the reference's assembly loop
+ * (sem/discrete.py:478-500: per-element meshgrid of global DOF ids, COO
+ * triplets, `grhs[inds_ext] += ...`) with static tables.
+ * ------------------------------------------------------------------------ */
+typedef struct semk_hostplan semk_hostplan;
+
+enum semk_plan_array {
+  SEMK_PA_PATCH_NODE_PTR = 0, /* int32  [n_patch+1]   offsets into PNODE                    */
+  SEMK_PA_PNODE = 1,          /* uint32 [n_pnode]     global id | flags; private nodes first */
+  SEMK_PA_PATCH_NPRIV = 2,    /* int32  [n_patch]     number of private nodes of the patch   */
+  SEMK_PA_PATCH_SLOT_BASE = 3,/* int32  [n_patch]     first interface slot of the patch      */
+  SEMK_PA_ELOC = 4,           /* uint16 [n_slot_elems][NN] patch-local index of each node    */
+  SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
+  SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
+  SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
+  SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
+  SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node    */
+  SEMK_PA_COUNT = 10
+};
+
+enum semk_plan_scalar {
+  SEMK_PS_N_PATCH = 0,
+  SEMK_PS_N_PNODE = 1,
+  SEMK_PS_N_SLOTS = 2,
+  SEMK_PS_N_SHARED = 3,
+  SEMK_PS_MAX_PATCH_NODES = 4,
+  SEMK_PS_MAX_COLORS = 5,
+  SEMK_PS_N_SLOT_ELEMS = 6,   /* n_patch * elems_per_patch (last patch padded) */
+  SEMK_PS_COUNT = 7
+};
+
+/* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
+ *      sem/discrete.py:810-812, stacked).  elem_order: host int64 [n_elem]
+ *      permutation, slot -> element (NULL = identity); consecutive runs of
+ *      elems_per_patch slots form one patch.  dirichlet: host uint8 [n_nodes]
+ *      (1 = essential-BC node, the reference's on_ebc polarity,
+ *      sem/discrete.py:505) or NULL. */
+int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
+                         const int64_t *elem_order, int elems_per_patch,
+                         const uint8_t *dirichlet, semk_hostplan **out);
+int64_t semk_hostplan_scalar(const semk_hostplan *plan, int which);
+const void *semk_hostplan_array(const semk_hostplan *plan, int which, int64_t *n_bytes);
+void semk_hostplan_destroy(semk_hostplan *plan);
+
+/* ------------------------------------------------------------------------
+ * Device tables of one operator (all device pointers; filled by the caller
+ * from a host plan).
+ * ------------------------------------------------------------------------ */
+typedef struct semk_op {
+  int32_t n1;               /* points per direction */
+  int32_t elems_per_patch;
+  int64_t n_elem;
+  int64_t n_nodes;
+  int64_t n_patch;
+  int32_t max_patch_nodes;
+  int32_t max_colors;
+  int64_t g_stride;         /* doubles between consecutive element slots of G (even) */
+  const double *G;          /* [n_slot_elems][g_stride]: G00[NN], G01[NN], G11[NN] per slot */
+  const int32_t *patch_node_ptr;
+  const uint32_t *pnode;
+  const int32_t *patch_npriv;
+  const int32_t *patch_slot_base;
+  const uint16_t *eloc;
+  const uint8_t *elem_color;
+  int64_t n_slots;
+  double *slot_buf;         /* [n_slots] interface partial sums (scratch)  */
+  int64_t n_shared;
+  const uint32_t *shared_node;
+  const int32_t *shared_ptr;
+  const int32_t *shared_slot;
+  double *partials;         /* [semk_partials_len()] dot-product scratch    */
+  const double *D_host;     /* HOST pointer, [NN] differentiation matrix    */
+} semk_op;
+
+/* number of doubles the `partials` scratch of an operator must hold */
+int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
+
+/* ------------------------------------------------------------------------
+ * K1: geometric factors.  Replaces, per element, Mapping._compute_x_phys /
+ * _compute_jacobian (sem/mapping.py:98-119: compute_coeffs_grid_eq LU solves,
+ * sem/basis_functions.py:599-624; tensor gradient, :626-650), det_inv_2x2
+ * (sem/linalg.py:105-115), FiniteElement.detJxW (sem/discrete.py:594-597 with
+ * TensorQuadratureRule.xweight, sem/quadratures.py:268-275) and the
+ * G = JxW * invJ invJ^T contraction implicit in examples/poisson.py:166-193.
+ *
+ * nodes_x/nodes_y: device [n_nodes] (rows of the reference's mesh.nodes);
+ * l2g: device uint32 [n_elem][NN]; Einv, D: device [NN]; w: device [n1].
+ * elem_of_slot: device int64 [n_elem] or NULL (identity).  Outputs are
+ * optional (NULL = skip): G in engine slot order with stride g_stride;
+ * JxW [n_elem][NN], x_phys [n_elem][2][NN], J / invJ [n_elem][2][2][NN],
+ * detJ [n_elem][NN] in the reference's element order and layouts.
+ * bad_flag: device int32, set to 1 if any detJ <= 0 (caller zeroes it).
+ * ------------------------------------------------------------------------ */
+int semk_geom_factors_f64(int n1, int64_t n_elem, const double *nodes_x, const double *nodes_y,
+                          const uint32_t *l2g, const double *Einv, const double *D,
+                          const double *w, const int64_t *elem_of_slot, double *G,
+                          int64_t g_stride, double *JxW, double *x_phys, double *J,
+                          double *invJ, double *detJ, int32_t *bad_flag, void *stream);
+
+/* G (engine slot layout) from externally supplied factors in the reference's
+ * layouts: invJ [n_elem][2][2][NN] (fe.invJ) and JxW [n_elem][NN]
+ * (fe.detJxW).  Parity tier T1. */
+int semk_gfactors_from_invj_f64(int n1, int64_t n_elem, const double *invJ, const double *JxW,
+                                const int64_t *elem_of_slot, double *G, int64_t g_stride,
+                                void *stream);
+
+/* ------------------------------------------------------------------------
+ * K2: y = A u, the assembled Poisson stiffness operator, matrix-free.
+ * Replaces the dense local apply np.einsum('pqrs,rs', L, u[L2G])
+ * (examples/squirmer-axisymmetric.py:268-270,284-295) with L from
+ * examples/poisson.py:166-193, the scatter-add of sem/discrete.py:491-499
+ * and the Dirichlet row/column elimination of sem/discrete.py:505-510.
+ * u, y: device [n_nodes], distinct buffers.  dot_out: device double or NULL;
+ * receives sum_k u_k y_k over the (masked) input and the result.
+ * Deterministic: no floating-point atomics.
+ * ------------------------------------------------------------------------ */
+int semk_poisson_apply_f64(const semk_op *op, const double *u, double *y, int flags,
+                           double *dot_out, void *stream);
+
+/* Same operator, simple one-element-per-thread-group kernel with
+ * red.global.add.f64 scatter on a zeroed y (not deterministic in the last
+ * bit).  Kept as the independent cross-check of the patch kernel.
+ * l2g: device uint32 [n_elem][NN]; dirichlet: device uint8 [n_nodes] or NULL. */
+int semk_poisson_apply_atomic_f64(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
+                                  const int64_t *elem_of_slot, const double *G, int64_t g_stride,
+                                  const double *D_host, const uint8_t *dirichlet,
+                                  const double *u, double *y, int flags, void *stream);
+
+/* Host-buffer convenience call (the e2e path of bench.py): copies u from
+ * host, applies, copies y back; all on `stream`, synchronises before return.
+ * d_u, d_y: device scratch [n_nodes]. */
+int semk_poisson_apply_host_f64(const semk_op *op, const double *u_host, double *y_host,
+                                double *d_u, double *d_y, int flags, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K3: generic assembly  out[g] = sum over element-local entries mapped to g
+ * of loc[slot][k]  (the reference's `grhs[inds] += local` pattern,
+ * sem/discrete.py:499, for any element-local field).  loc: device
+ * [n_slot_elems][NN] in engine slot order.  flags: SEMK_MASK_OUT zeroes
+ * Dirichlet rows (fill_dirichlet is written there instead).
+ * ------------------------------------------------------------------------ */
+int semk_assemble_f64(const semk_op *op, const double *loc, double *out, int flags,
+                      double fill_dirichlet, void *stream);
+
+/* K5: element-local diagonal of the stiffness matrix, diag[p,q] = L[p,q,p,q]
+ * (SURVEY.md appendix C closed form), written to loc [n_slot_elems][NN] in
+ * engine slot order; assemble with semk_assemble_f64. */
+int semk_poisson_local_diag_f64(const semk_op *op, double *loc, void *stream);
+
+/* RHS/mass: loc[slot][k] = JxW[elem][k] * f[l2g[elem][k]]  (f NULL = 1, the
+ * reference's rhs = JxW, examples/poisson.py:200).  JxW in reference element
+ * order, l2g device uint32 [n_elem][NN], elem_of_slot device or NULL. */
+int semk_weighted_local_f64(int n1, int64_t n_elem, int64_t n_slot_elems, const double *JxW,
+                            const uint32_t *l2g, const int64_t *elem_of_slot, const double *f,
+                            double *loc, void *stream);
+
+/* ------------------------------------------------------------------------
+ * K4: fused vector kernels of Jacobi-PCG (replaces sparse.linalg.spsolve,
+ * sem/discrete.py:511, on the path).  Scalars live on the device:
+ *   sc[0]=rz  sc[1]=pAp  sc[2]=rz_new  sc[3]=rr  sc[4]=bb
+ *   sc[5]=iterations done  sc[6]=converged flag  sc[7]=breakdown flag.
+ * Once sc[6] or sc[7] is set the update kernels return without touching
+ * x, r, p (the iterate is frozen at the converged iteration).
+ * n = vector length, n_dot = leading entries that enter dot products
+ * (multi-GPU: owned nodes first, duplicates last).
+ * partials: device scratch of semk_vec_partials_len(n) doubles, zeroed once
+ * by the caller before first use (holds an arrival counter).
+ * ------------------------------------------------------------------------ */
+int64_t semk_vec_partials_len(int64_t n);
+/* r = b - Ax (Ax given);  z = dinv*r;  p = z;  sc[0] = r.z, sc[3] = r.r, sc[4] = b.b */
+int semk_pcg_init_f64(int64_t n, int64_t n_dot, const double *b, const double *Ax,
+                      const double *dinv, double *r, double *p, double *sc, double *partials,
+                      void *stream);
+/* alpha = sc[0]/sc[1];  x += alpha p;  r -= alpha Ap;  sc[2] = r.(dinv r), sc[3] = r.r,
+ * sc[5] += 1; sc[7] = 1 on breakdown (pAp <= 0 or NaN; x, r are then left unchanged) */
+int semk_pcg_update_xr_f64(int64_t n, int64_t n_dot, const double *p, const double *Ap,
+                           const double *dinv, double *x, double *r, double *sc,
+                           double *partials, void *stream);
+/* beta = sc[2]/sc[0];  p = dinv*r + beta p;  then sc[0] = sc[2] */
+int semk_pcg_update_p_f64(int64_t n, const double *r, const double *dinv, double *p, double *sc,
+                          double *partials, void *stream);
+/* out[0] = sum_{k<n} a_k b_k (deterministic two-stage reduction) */
+int semk_dot_f64(int64_t n, const double *a, const double *b, double *out, double *partials,
+                 void *stream);
+
+typedef struct semk_pcg_info {
+  int32_t iterations;
+  int32_t status;          /* 0 converged, 1 maxiter reached, SEMK_ERR_BREAKDOWN */
+  double rel_residual;     /* recursive ||r|| / ||b|| at exit */
+  double bnorm;
+} semk_pcg_info;
+
+/* Native single-GPU PCG driver on Ahat = M A M + (I - M): solves
+ * Ahat x = b from the initial guess in x.  work: device [4*n] (r, p, Ap,
+ * spare); sc: device [8]; vec_partials as above.  Convergence
+ * ||r|| <= rtol*||b|| is polled every check_every iterations (one 32-byte
+ * D2H copy); no other host synchronisation. */
+int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x, const double *dinv,
+                       double *work, double *sc, double *vec_partials, double rtol,
+                       int maxiter, int check_every, semk_pcg_info *info, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMK_H */

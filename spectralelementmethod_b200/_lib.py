@@ -1,0 +1,178 @@
+"""ctypes binding of libsemk.so (the C ABI declared in include/semk.h).
+
+This is the stub a maintainer of the reference would add.
+There is deliberately NO fallback: if the shared library is missing or a CUDA
+device is required and absent, the call raises -- the product never routes
+through a CPU implementation.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsemk.so")
+
+# status codes / flags (mirror include/semk.h)
+OK, ERR_INVALID, ERR_CUDA, ERR_JACOBIAN, ERR_BREAKDOWN, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+NODE_ID_MASK, NODE_SHARED, NODE_DIRICHLET = 0x3FFFFFFF, 0x40000000, 0x80000000
+MASK_IN, MASK_OUT, DIRICHLET_IDENTITY = 1, 2, 4
+MAX_N1 = 17
+
+(PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
+ PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT) = range(10)
+(PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
+ PS_N_SLOT_ELEMS) = range(7)
+
+PLAN_ARRAY_DTYPES = {
+    PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
+    PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16, PA_ELEM_COLOR: np.uint8,
+    PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
+    PA_SHARED_SLOT: np.int32,
+}
+
+
+class SemkError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libsemk error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SolverFailure(Exception):
+    """PCG breakdown (the reference's solver-failure convention,
+    sem/rootfind.py:15-19)."""
+
+
+class semk_op(C.Structure):
+    _fields_ = [
+        ("n1", C.c_int32), ("elems_per_patch", C.c_int32),
+        ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
+        ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
+        ("g_stride", C.c_int64), ("G", C.c_void_p),
+        ("patch_node_ptr", C.c_void_p), ("pnode", C.c_void_p), ("patch_npriv", C.c_void_p),
+        ("patch_slot_base", C.c_void_p), ("eloc", C.c_void_p), ("elem_color", C.c_void_p),
+        ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
+        ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
+        ("shared_slot", C.c_void_p),
+        ("partials", C.c_void_p), ("D_host", C.c_void_p),
+    ]
+
+
+class semk_pcg_info(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("status", C.c_int32),
+                ("rel_residual", C.c_double), ("bnorm", C.c_double)]
+
+
+_P, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+# name -> (restype, argtypes); every symbol include/semk.h declares
+SIGNATURES = {
+    "semk_version": (_I, []),
+    "semk_last_error": (C.c_char_p, []),
+    "semk_device_available": (_I, []),
+    "semk_hostplan_create": (_I, [_I, _L, _L, _P, _P, _I, _P, C.POINTER(_P)]),
+    "semk_hostplan_scalar": (_L, [_P, _I]),
+    "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
+    "semk_hostplan_destroy": (None, [_P]),
+    "semk_partials_len": (_L, [_L, _L]),
+    "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P,
+                                   _P, _P, _P]),
+    "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _P]),
+    "semk_poisson_apply_f64": (_I, [C.POINTER(semk_op), _P, _P, _I, _P, _P]),
+    "semk_poisson_apply_atomic_f64": (_I, [_I, _L, _L, _P, _P, _P, _L, _P, _P, _P, _P, _I, _P]),
+    "semk_poisson_apply_host_f64": (_I, [C.POINTER(semk_op), _P, _P, _P, _P, _I, _P]),
+    "semk_assemble_f64": (_I, [C.POINTER(semk_op), _P, _P, _I, _D, _P]),
+    "semk_poisson_local_diag_f64": (_I, [C.POINTER(semk_op), _P, _P]),
+    "semk_weighted_local_f64": (_I, [_I, _L, _L, _P, _P, _P, _P, _P, _P]),
+    "semk_vec_partials_len": (_L, [_L]),
+    "semk_pcg_init_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "semk_pcg_update_xr_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "semk_pcg_update_p_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
+    "semk_dot_f64": (_I, [_L, _P, _P, _P, _P, _P]),
+    "semk_pcg_solve_f64": (_I, [C.POINTER(semk_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
+                                C.POINTER(semk_pcg_info), _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsemk.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libsemk.so not found at %s -- build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                "spectralelementmethod_b200/csrc/build.sh.  There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().semk_last_error().decode("utf-8", "replace")
+
+
+def check(code):
+    """Map a libsemk status to the reference's exception conventions
+    (SURVEY.md 8b 'Error conventions')."""
+    if code == OK:
+        return
+    msg = last_error()
+    if code == ERR_INVALID:
+        raise ValueError(msg)
+    if code == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if code == ERR_JACOBIAN:
+        raise AssertionError(msg)
+    if code == ERR_BREAKDOWN:
+        raise SolverFailure(msg)
+    raise SemkError(code, msg)
+
+
+def require_device():
+    """Fail loudly when no CUDA device is usable (no CPU fallback)."""
+    if not load().semk_device_available():
+        raise RuntimeError("spectralelementmethod_b200: no CUDA device available; "
+                           "the operator engine has no CPU fallback")
+
+
+def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None):
+    """Run the host plan builder; returns (scalars dict, arrays dict of numpy copies)."""
+    lib = load()
+    l2g = np.ascontiguousarray(l2g, dtype=np.uint32).reshape(-1, n1 * n1)
+    n_elem = l2g.shape[0]
+    order_p = None
+    if elem_order is not None:
+        elem_order = np.ascontiguousarray(elem_order, dtype=np.int64)
+        if elem_order.shape != (n_elem,):
+            raise ValueError("elem_order must have one entry per element")
+        order_p = elem_order.ctypes.data
+    dir_p = None
+    if dirichlet is not None:
+        dirichlet = np.ascontiguousarray(dirichlet).astype(np.uint8, copy=False)
+        if dirichlet.shape != (n_nodes,):
+            raise ValueError("dirichlet mask must have one entry per node")
+        dir_p = dirichlet.ctypes.data
+    handle = _P()
+    check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p,
+                                   int(elems_per_patch), dir_p, C.byref(handle)))
+    try:
+        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(7)}
+        arrays = {}
+        for k, dt in PLAN_ARRAY_DTYPES.items():
+            nb = _L(0)
+            ptr = lib.semk_hostplan_array(handle, k, C.byref(nb))
+            if nb.value:
+                buf = (C.c_char * nb.value).from_address(ptr)
+                arrays[k] = np.frombuffer(buf, dtype=dt).copy()
+            else:
+                arrays[k] = np.zeros(0, dtype=dt)
+    finally:
+        lib.semk_hostplan_destroy(handle)
+    return scalars, arrays

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Build libsemk.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3"
+OBJS=""
+for f in semk_api.cu semk_geom.cu semk_apply.cu semk_vec.cu; do
+  o="${f%.cu}.o"
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ semk_common.cuh -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
+    $NVCC $FLAGS ${SEMK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
+  fi
+  OBJS="$OBJS $o"
+done
+o=semk_hostplan.o
+if [ ! -f "$o" ] || [ semk_hostplan.cpp -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
+  g++ -O3 -std=c++17 -fPIC -c semk_hostplan.cpp -o "$o" &
+fi
+wait
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libsemk.so $OBJS semk_hostplan.o
+echo "built $(pwd)/libsemk.so"

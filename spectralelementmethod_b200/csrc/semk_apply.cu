@@ -1,0 +1,595 @@
+// semk_apply.cu -- K2/K3/K5: matrix-free Poisson apply, assembly, diagonal.
+//
+// Reference being replaced (per element, in a Python loop):
+//   Lse[p,q,r,s] from four O(N^5) einsums            examples/poisson.py:181-193
+//   u_loc = u[L2G];  y_loc = einsum('pqrs,rs', L, u_loc)
+//                                    examples/squirmer-axisymmetric.py:268-295
+//   scatter-add through the L2G map                  sem/discrete.py:491-499
+//   Dirichlet row/column elimination                 sem/discrete.py:505-510
+//
+// Here the dense Lse is never formed.  With the symmetric geometric factors
+// G (semk_geom.cu) the local operator is
+//   ur = D u,  us = u D^T,  w0 = G00.ur + G01.us,  w1 = G01.ur + G11.us,
+//   y  = D^T w0 + w1 D.
+//
+// Kernel layout (patch kernel, the production path):
+//   * one CTA per patch of PE element slots, N threads per element; thread t
+//     of an element owns column t (nodes [m][t], m = 0..N-1) in registers.
+//   * contractions along the in-thread axis are N*N DFMAs whose D operand is
+//     a compile-time-indexed __constant__ entry (folded into the DFMA as a
+//     constant-bank operand: no shared-memory traffic, no registers);
+//     the other axis is reached by transposing through shared memory.
+//   * the patch's geometric factors (59% of all HBM traffic) arrive by one
+//     TMA bulk copy (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier,
+//     issued before the nodal gather so the two overlap.
+//   * nodal values are gathered once per patch into shared memory through the
+//     patch node table (coalesced for locality-preserving numberings), with
+//     the Dirichlet mask carried in the table's flag bits.
+//   * assembly inside the patch is by colour (no atomics); private nodes are
+//     stored straight to y, shared nodes go to interface slots that the tiny
+//     `shared_nodes_kernel` sums in a fixed order => bit-reproducible.
+#include "semk_common.cuh"
+
+#include <cstring>
+
+namespace {
+
+// Differentiation matrix of the order currently in use, row-major [N][N].
+__constant__ double cD[SEMK_MAX_N1 * SEMK_MAX_N1];
+double g_hostD[SEMK_MAX_N1 * SEMK_MAX_N1];
+int g_hostD_n1 = 0;
+
+int upload_D(int n1, const double *D_host, cudaStream_t st) {
+  const size_t bytes = sizeof(double) * n1 * n1;
+  if (g_hostD_n1 == n1 && std::memcmp(g_hostD, D_host, bytes) == 0) return SEMK_OK;
+  std::memcpy(g_hostD, D_host, bytes);
+  g_hostD_n1 = n1;
+  // stream-ordered: kernels already queued keep the old table
+  SEMK_CUDA_CHECK(cudaMemcpyToSymbolAsync(cD, g_hostD, bytes, 0, cudaMemcpyHostToDevice, st));
+  return SEMK_OK;
+}
+
+// out[i] = sum_k D[i][k] v[k]      (derivative along the in-thread axis)
+template <int N>
+__device__ __forceinline__ void apply_D(const double (&v)[N], double (&out)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc = fma(cD[i * N + k], v[k], acc);
+    out[i] = acc;
+  }
+}
+// out[i] = sum_k D[k][i] v[k]      (transpose: the weak-form "test" side)
+template <int N>
+__device__ __forceinline__ void apply_Dt(const double (&v)[N], double (&out)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc = fma(cD[k * N + i], v[k], acc);
+    out[i] = acc;
+  }
+}
+
+// The element-local operator for one column-owning thread.
+//   ucol[m] = u[m][t] on entry;  ycol[m] = y[m][t] on exit.
+//   A, B: this element's two N*N shared scratch arrays.
+//   g: this element's G block in shared or global memory (G00, G01, G11);
+//   g_ready: mbarrier guarding a TMA-staged g (nullptr when g is in global).
+// Contains four __syncthreads(); every thread of the CTA must call it.
+template <int N>
+__device__ __forceinline__ void local_poisson(int t, bool active, const double (&ucol)[N],
+                                              double (&ycol)[N], double *__restrict__ A,
+                                              double *__restrict__ B,
+                                              const double *__restrict__ g,
+                                              uint64_t *g_ready = nullptr) {
+  constexpr int NN = N * N;
+  double ur[N], tmp[N], us[N];
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < N; ++m) A[m * N + t] = ucol[m];
+  }
+  __syncthreads();
+  if (active) {
+    apply_D<N>(ucol, ur);  // ur[m][t] = sum_r D[m][r] u[r][t]
+#pragma unroll
+    for (int s = 0; s < N; ++s) tmp[s] = A[t * N + s];  // row t of u
+    apply_D<N>(tmp, us);                                // us[t][n] = sum_s D[n][s] u[t][s]
+#pragma unroll
+    for (int n = 0; n < N; ++n) B[t * N + n] = us[n];
+  }
+  __syncthreads();
+  // G staged by TMA: every thread observes the mbarrier phase itself (acquire)
+  if (g_ready) semk_mbar_wait(g_ready, 0);
+  double w1[N];
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const double usc = B[m * N + t];  // us[m][t]
+      const double g00 = g[m * N + t], g01 = g[NN + m * N + t], g11 = g[2 * NN + m * N + t];
+      tmp[m] = g00 * ur[m] + g01 * usc;  // w0[m][t]
+      w1[m] = g01 * ur[m] + g11 * usc;   // w1[m][t]
+    }
+    apply_Dt<N>(tmp, ycol);  // y0[p][t] = sum_m D[m][p] w0[m][t]
+#pragma unroll
+    for (int m = 0; m < N; ++m) A[m * N + t] = w1[m];
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) tmp[n] = A[t * N + n];  // row t of w1
+    apply_Dt<N>(tmp, us);                               // y1[t][q] = sum_n w1[t][n] D[n][q]
+#pragma unroll
+    for (int q = 0; q < N; ++q) B[t * N + q] = us[q];
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < N; ++m) ycol[m] += B[m * N + t];
+  }
+}
+
+template <int N, int PE>
+struct PatchCfg {
+  static constexpr int NN = N * N;
+  static constexpr int kThreads = ((N * PE + 31) / 32) * 32;
+};
+
+enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
+
+// MODE_APPLY:    y = A u (masked per flags), optional dot partials.
+// MODE_ASSEMBLE: y = assembly of the element-local field `loc` (slot order).
+template <int N, int PE, int MODE>
+__global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
+    patch_kernel(semk_op op, const double *__restrict__ u, const double *__restrict__ loc,
+                 double *__restrict__ y, int flags, double fill_dirichlet,
+                 double *__restrict__ dot_partials) {
+  constexpr int NN = N * N;
+  constexpr int kThreads = PatchCfg<N, PE>::kThreads;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [mbar 16 B][Gs PE*g_stride][up mpn][yp mpn][A PE*NN][B PE*NN][red 32]
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
+  double *Gs = reinterpret_cast<double *>(smem_raw + 16);
+  const int gs_len = (MODE == MODE_APPLY) ? PE * (int)op.g_stride : 0;
+  double *up = Gs + gs_len;
+  double *yp = up + op.max_patch_nodes;
+  double *As = yp + op.max_patch_nodes;
+  double *Bs = As + ((MODE == MODE_APPLY) ? PE * NN : 0);
+  double *red = Bs + ((MODE == MODE_APPLY) ? PE * NN : 0);
+
+  const int tid = threadIdx.x;
+  const int64_t patch = blockIdx.x;
+  const int64_t slot0 = patch * PE;
+  const int le = tid / N, t = tid - le * N;
+  const bool active = (le < PE) && (slot0 + le < op.n_elem);
+  const int64_t slot = slot0 + (le < PE ? le : 0);
+
+  if (MODE == MODE_APPLY) {
+    if (tid == 0) {
+      semk_mbar_init(mbar, 1);
+      semk_fence_mbar_init();
+      const uint32_t bytes = (uint32_t)(PE * op.g_stride * sizeof(double));
+      semk_mbar_expect_tx(mbar, bytes);
+      semk_bulk_g2s(Gs, op.G + slot0 * op.g_stride, bytes, mbar);
+    }
+  }
+
+  // ---- gather the patch's nodal values --------------------------------------
+  const int n0 = op.patch_node_ptr[patch];
+  const int npn = op.patch_node_ptr[patch + 1] - n0;
+  const int npriv = op.patch_npriv[patch];
+  for (int k = tid; k < npn; k += kThreads) {
+    if (MODE == MODE_APPLY) {
+      const uint32_t pn = op.pnode[n0 + k];
+      double v = u[pn & SEMK_NODE_ID_MASK];
+      if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) v = 0.0;
+      up[k] = v;
+    }
+    yp[k] = 0.0;
+  }
+  // element-local index column
+  uint16_t idx[N];
+  uint8_t color = 255;
+  if (active) {
+    const uint16_t *er = op.eloc + slot * NN;
+#pragma unroll
+    for (int m = 0; m < N; ++m) idx[m] = er[m * N + t];
+    color = op.elem_color[slot];
+  }
+  __syncthreads();
+
+  double ycol[N];
+  if (MODE == MODE_APPLY) {
+    double ucol[N];
+    if (active) {
+#pragma unroll
+      for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
+    }
+    local_poisson<N>(t, active, ucol, ycol, As + (le < PE ? le : 0) * NN,
+                     Bs + (le < PE ? le : 0) * NN, Gs + (le < PE ? le : 0) * op.g_stride, mbar);
+  } else {
+    if (active) {
+      const double *lr = loc + slot * NN;
+#pragma unroll
+      for (int m = 0; m < N; ++m) ycol[m] = lr[m * N + t];
+    }
+  }
+
+  // ---- assemble inside the patch, colour by colour (no atomics) -------------
+  for (int c = 0; c < op.max_colors; ++c) {
+    if (active && color == c) {
+#pragma unroll
+      for (int m = 0; m < N; ++m) yp[idx[m]] += ycol[m];
+    }
+    __syncthreads();
+  }
+
+  // ---- write out: private nodes -> y, shared nodes -> interface slots --------
+  double dot = 0.0;
+  const int slot_base = op.patch_slot_base[patch];
+  for (int k = tid; k < npn; k += kThreads) {
+    const uint32_t pn = op.pnode[n0 + k];
+    double v = yp[k];
+    if (k < npriv) {
+      const uint32_t g = pn & SEMK_NODE_ID_MASK;
+      double uin = (MODE == MODE_APPLY) ? up[k] : 0.0;
+      if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_OUT)) {
+        if (MODE == MODE_APPLY) {
+          v = (flags & SEMK_DIRICHLET_IDENTITY) ? u[g] : 0.0;
+          uin = v;
+        } else {
+          v = fill_dirichlet;
+        }
+      }
+      y[g] = v;
+      dot = fma(uin, v, dot);
+    } else {
+      op.slot_buf[slot_base + (k - npriv)] = v;
+    }
+  }
+  if (MODE == MODE_APPLY && dot_partials) {
+    const double s = semk_block_sum(dot, red);
+    if (tid == 0) dot_partials[patch] = s;
+  }
+}
+
+// Sum the interface slots of every shared node in a fixed order.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    shared_nodes_kernel(semk_op op, const double *__restrict__ u, double *__restrict__ y,
+                        int flags, double fill_dirichlet, double *__restrict__ dot_partials,
+                        int64_t partial_offset) {
+  __shared__ double red[32];
+  double dot = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < op.n_shared;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t pn = op.shared_node[i];
+    const uint32_t g = pn & SEMK_NODE_ID_MASK;
+    const int j0 = op.shared_ptr[i], j1 = op.shared_ptr[i + 1];
+    double v = 0.0;
+    for (int j = j0; j < j1; ++j) v += op.slot_buf[op.shared_slot[j]];
+    double uin = 0.0;
+    if (MODE == MODE_APPLY) {
+      uin = u[g];
+      if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) uin = 0.0;
+    }
+    if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_OUT)) {
+      if (MODE == MODE_APPLY) {
+        v = (flags & SEMK_DIRICHLET_IDENTITY) ? u[g] : 0.0;
+        uin = v;
+      } else {
+        v = fill_dirichlet;
+      }
+    }
+    y[g] = v;
+    dot = fma(uin, v, dot);
+  }
+  if (MODE == MODE_APPLY && dot_partials) {
+    const double s = semk_block_sum(dot, red);
+    if (threadIdx.x == 0) dot_partials[partial_offset + blockIdx.x] = s;
+  }
+}
+
+// Final, fixed-order sum of the per-CTA partials (single CTA).
+__global__ void __launch_bounds__(1024)
+    reduce_partials_kernel(const double *__restrict__ partials, int64_t n,
+                           double *__restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  s = semk_block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+constexpr int kSharedBlocks = 148 * 4;
+
+// ---- simple atomic-scatter kernel (independent cross-check) -------------------
+template <int N, int PE>
+__global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
+    atomic_kernel(int64_t n_elem, const uint32_t *__restrict__ l2g,
+                  const int64_t *__restrict__ elem_of_slot, const double *__restrict__ G,
+                  int64_t g_stride, const uint8_t *__restrict__ dirichlet,
+                  const double *__restrict__ u, double *__restrict__ y, int flags) {
+  constexpr int NN = N * N;
+  __shared__ double As[PE * NN], Bs[PE * NN];
+  const int tid = threadIdx.x;
+  const int le = tid / N, t = tid - le * N;
+  const int64_t slot = (int64_t)blockIdx.x * PE + le;
+  const bool active = (le < PE) && (slot < n_elem);
+  double ucol[N], ycol[N];
+  uint32_t gid[N];
+  if (active) {
+    const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
+    const uint32_t *row = l2g + e * NN;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      gid[m] = row[m * N + t];
+      double v = u[gid[m]];
+      if (dirichlet && (flags & SEMK_MASK_IN) && dirichlet[gid[m]]) v = 0.0;
+      ucol[m] = v;
+    }
+  }
+  const int lec = le < PE ? le : 0;
+  local_poisson<N>(t, active, ucol, ycol, As + lec * NN, Bs + lec * NN,
+                   G + (active ? slot : 0) * g_stride);
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < N; ++m) atomicAdd(y + gid[m], ycol[m]);
+  }
+}
+
+__global__ void dirichlet_fix_kernel(int64_t n, const uint8_t *__restrict__ dirichlet,
+                                     const double *__restrict__ u, double *__restrict__ y,
+                                     int flags) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    if (dirichlet[i]) y[i] = (flags & SEMK_DIRICHLET_IDENTITY) ? u[i] : 0.0;
+}
+
+// ---- K5: element-local diagonal ------------------------------------------------
+// diag[p][q] = sum_m G00[m][q] D[m][p]^2 + 2 G01[p][q] D[p][p] D[q][q]
+//            + sum_n G11[p][n] D[n][q]^2
+__global__ void local_diag_kernel(int n1, int64_t n_slot_elems, const double *__restrict__ G,
+                                  int64_t g_stride, double *__restrict__ loc) {
+  const int NN = n1 * n1;
+  const int64_t total = n_slot_elems * NN;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t slot = i / NN;
+    const int k = (int)(i - slot * NN);
+    const int p = k / n1, q = k - p * n1;
+    const double *g = G + slot * g_stride;
+    double acc = 2.0 * g[NN + k] * cD[p * n1 + p] * cD[q * n1 + q];
+    for (int m = 0; m < n1; ++m) {
+      const double d0 = cD[m * n1 + p], d1 = cD[m * n1 + q];
+      acc = fma(g[m * n1 + q], d0 * d0, acc);
+      acc = fma(g[2 * NN + p * n1 + m], d1 * d1, acc);
+    }
+    loc[i] = acc;
+  }
+}
+
+__global__ void weighted_local_kernel(int NN, int64_t n_elem, const double *__restrict__ JxW,
+                                      const uint32_t *__restrict__ l2g,
+                                      const int64_t *__restrict__ elem_of_slot,
+                                      const double *__restrict__ f, double *__restrict__ loc) {
+  const int64_t total = n_elem * NN;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t slot = i / NN;
+    const int k = (int)(i - slot * NN);
+    const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
+    double v = JxW[e * NN + k];
+    if (f) v *= f[l2g[e * NN + k]];
+    loc[i] = v;
+  }
+}
+
+template <int PE, int MODE>
+struct PatchLaunch {
+  template <int N>
+  static int run(const semk_op &op, const double *u, const double *loc, double *y, int flags,
+                 double fill, double *partials, cudaStream_t st) {
+    constexpr int NN = N * N;
+    size_t smem = 16 + sizeof(double) * (2 * (size_t)op.max_patch_nodes + 32);
+    if (MODE == MODE_APPLY) smem += sizeof(double) * ((size_t)PE * op.g_stride + 2 * PE * NN);
+    auto kern = patch_kernel<N, PE, MODE>;
+    if (smem > 227 * 1024) {
+      semk_set_error("patch kernel: shared memory request exceeds 227 KB");
+      return SEMK_ERR_UNSUPPORTED;
+    }
+    static size_t configured = 0;  // per instantiation; one device per process
+    if (smem > configured) {
+      SEMK_CUDA_CHECK(
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    kern<<<(unsigned)op.n_patch, PatchCfg<N, PE>::kThreads, smem, st>>>(op, u, loc, y, flags, fill,
+                                                                      partials);
+    SEMK_LAUNCH_CHECK("patch_kernel");
+    return SEMK_OK;
+  }
+};
+
+// elements per patch supported by the compiled kernels, per order
+inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16; }
+
+template <int MODE>
+int launch_patch(const semk_op &op, const double *u, const double *loc, double *y, int flags,
+                 double fill, double *partials, cudaStream_t st) {
+#define SEMK_CALL(NV)                                                                         \
+  do {                                                                                        \
+    int rc;                                                                                   \
+    if (op.elems_per_patch == 16)                                                             \
+      rc = PatchLaunch<16, MODE>::template run<NV>(op, u, loc, y, flags, fill, partials, st); \
+    else if (op.elems_per_patch == 8)                                                         \
+      rc = PatchLaunch<8, MODE>::template run<NV>(op, u, loc, y, flags, fill, partials, st);  \
+    else                                                                                      \
+      rc = PatchLaunch<4, MODE>::template run<NV>(op, u, loc, y, flags, fill, partials, st);  \
+    if (rc != SEMK_OK) return rc;                                                             \
+  } while (0)
+  SEMK_DISPATCH_N1(op.n1, SEMK_CALL)
+#undef SEMK_CALL
+  return SEMK_OK;
+}
+
+int check_op(const semk_op *op, const char *who) {
+  if (!op) {
+    semk_set_error(std::string(who) + ": null operator");
+    return SEMK_ERR_INVALID;
+  }
+  if (op->n1 < 2 || op->n1 > SEMK_MAX_N1) {
+    semk_set_error(std::string(who) + ": n1 outside [2, 17]");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  if (!pe_supported(op->elems_per_patch)) {
+    semk_set_error(std::string(who) + ": elems_per_patch must be 4, 8 or 16");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  if (!op->patch_node_ptr || !op->pnode || !op->patch_npriv || !op->patch_slot_base ||
+      !op->eloc || !op->elem_color || (op->n_slots > 0 && !op->slot_buf) ||
+      (op->n_shared > 0 && (!op->shared_node || !op->shared_ptr || !op->shared_slot))) {
+    semk_set_error(std::string(who) + ": operator tables incomplete");
+    return SEMK_ERR_INVALID;
+  }
+  if ((op->g_stride & 1) != 0) {
+    semk_set_error(std::string(who) + ": g_stride must be even (16-byte TMA granularity)");
+    return SEMK_ERR_INVALID;
+  }
+  return SEMK_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
+  (void)n_shared;
+  return n_patch + kSharedBlocks + 8;
+}
+
+extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double *y, int flags,
+                                      double *dot_out, void *stream) {
+  int rc = check_op(op, "semk_poisson_apply_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(u && y && u != y, "semk_poisson_apply_f64: u and y must be distinct buffers");
+  SEMK_REQUIRE(op->G && op->D_host, "semk_poisson_apply_f64: missing G or D");
+  SEMK_REQUIRE(!dot_out || op->partials, "semk_poisson_apply_f64: dot_out needs op->partials");
+  cudaStream_t st = semk_stream(stream);
+  rc = upload_D(op->n1, op->D_host, st);
+  if (rc != SEMK_OK) return rc;
+  double *partials = dot_out ? op->partials : nullptr;
+  rc = launch_patch<MODE_APPLY>(*op, u, nullptr, y, flags, 0.0, partials, st);
+  if (rc != SEMK_OK) return rc;
+  int shared_blocks = 0;
+  if (op->n_shared > 0) {
+    const int64_t want = (op->n_shared + 255) / 256;
+    shared_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
+    shared_nodes_kernel<MODE_APPLY><<<shared_blocks, 256, 0, st>>>(*op, u, y, flags, 0.0, partials,
+                                                                  op->n_patch);
+    SEMK_LAUNCH_CHECK("shared_nodes_kernel");
+  }
+  if (dot_out) {
+    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, op->n_patch + shared_blocks, dot_out);
+    SEMK_LAUNCH_CHECK("reduce_partials_kernel");
+  }
+  return SEMK_OK;
+}
+
+extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *out, int flags,
+                                 double fill_dirichlet, void *stream) {
+  int rc = check_op(op, "semk_assemble_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(loc && out, "semk_assemble_f64: null pointer");
+  cudaStream_t st = semk_stream(stream);
+  rc = launch_patch<MODE_ASSEMBLE>(*op, nullptr, loc, out, flags, fill_dirichlet, nullptr, st);
+  if (rc != SEMK_OK) return rc;
+  if (op->n_shared > 0) {
+    const int64_t want = (op->n_shared + 255) / 256;
+    const int blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
+    shared_nodes_kernel<MODE_ASSEMBLE><<<blocks, 256, 0, st>>>(*op, nullptr, out, flags,
+                                                              fill_dirichlet, nullptr, 0);
+    SEMK_LAUNCH_CHECK("shared_nodes_kernel");
+  }
+  return SEMK_OK;
+}
+
+extern "C" int semk_poisson_local_diag_f64(const semk_op *op, double *loc, void *stream) {
+  int rc = check_op(op, "semk_poisson_local_diag_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(loc && op->G && op->D_host, "semk_poisson_local_diag_f64: null pointer");
+  cudaStream_t st = semk_stream(stream);
+  rc = upload_D(op->n1, op->D_host, st);
+  if (rc != SEMK_OK) return rc;
+  const int64_t n_slot_elems = op->n_patch * op->elems_per_patch;
+  const int64_t total = n_slot_elems * op->n1 * op->n1;
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  local_diag_kernel<<<grid, 256, 0, st>>>(op->n1, n_slot_elems, op->G, op->g_stride, loc);
+  SEMK_LAUNCH_CHECK("local_diag_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_weighted_local_f64(int n1, int64_t n_elem, int64_t n_slot_elems,
+                                       const double *JxW, const uint32_t *l2g,
+                                       const int64_t *elem_of_slot, const double *f, double *loc,
+                                       void *stream) {
+  SEMK_REQUIRE(n1 >= 2 && n1 <= SEMK_MAX_N1, "semk_weighted_local_f64: bad n1");
+  SEMK_REQUIRE(JxW && loc && (!f || l2g), "semk_weighted_local_f64: null pointer");
+  SEMK_REQUIRE(n_slot_elems >= n_elem, "semk_weighted_local_f64: n_slot_elems < n_elem");
+  cudaStream_t st = semk_stream(stream);
+  const int NN = n1 * n1;
+  if (n_slot_elems > n_elem)
+    SEMK_CUDA_CHECK(cudaMemsetAsync(loc + n_elem * NN, 0,
+                                    sizeof(double) * (n_slot_elems - n_elem) * NN, st));
+  if (n_elem <= 0) return SEMK_OK;
+  const int64_t total = n_elem * NN;
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  weighted_local_kernel<<<grid, 256, 0, st>>>(NN, n_elem, JxW, l2g, elem_of_slot, f, loc);
+  SEMK_LAUNCH_CHECK("weighted_local_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_poisson_apply_atomic_f64(int n1, int64_t n_elem, int64_t n_nodes,
+                                             const uint32_t *l2g, const int64_t *elem_of_slot,
+                                             const double *G, int64_t g_stride,
+                                             const double *D_host, const uint8_t *dirichlet,
+                                             const double *u, double *y, int flags,
+                                             void *stream) {
+  SEMK_REQUIRE(l2g && G && D_host && u && y && u != y,
+               "semk_poisson_apply_atomic_f64: null or aliased pointer");
+  SEMK_REQUIRE(n_elem > 0 && n_nodes > 0, "semk_poisson_apply_atomic_f64: empty problem");
+  cudaStream_t st = semk_stream(stream);
+  int rc = upload_D(n1, D_host, st);
+  if (rc != SEMK_OK) return rc;
+  SEMK_CUDA_CHECK(cudaMemsetAsync(y, 0, sizeof(double) * n_nodes, st));
+  constexpr int PE = 8;
+  const unsigned grid = (unsigned)((n_elem + PE - 1) / PE);
+#define SEMK_CALL(NV)                                                                       \
+  atomic_kernel<NV, PE><<<grid, PatchCfg<NV, PE>::kThreads, 0, st>>>(                       \
+      n_elem, l2g, elem_of_slot, G, g_stride, dirichlet, u, y, flags)
+  SEMK_DISPATCH_N1(n1, SEMK_CALL)
+#undef SEMK_CALL
+  SEMK_LAUNCH_CHECK("atomic_kernel");
+  if (dirichlet && (flags & SEMK_MASK_OUT)) {
+    const int64_t want = (n_nodes + 255) / 256;
+    const unsigned g2 = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    dirichlet_fix_kernel<<<g2, 256, 0, st>>>(n_nodes, dirichlet, u, y, flags);
+    SEMK_LAUNCH_CHECK("dirichlet_fix_kernel");
+  }
+  return SEMK_OK;
+}
+
+extern "C" int semk_poisson_apply_host_f64(const semk_op *op, const double *u_host,
+                                           double *y_host, double *d_u, double *d_y, int flags,
+                                           void *stream) {
+  SEMK_REQUIRE(op && u_host && y_host && d_u && d_y, "semk_poisson_apply_host_f64: null pointer");
+  cudaStream_t st = semk_stream(stream);
+  const size_t bytes = sizeof(double) * (size_t)op->n_nodes;
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(d_u, u_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = semk_poisson_apply_f64(op, d_u, d_y, flags, nullptr, st);
+  if (rc != SEMK_OK) return rc;
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(y_host, d_y, bytes, cudaMemcpyDeviceToHost, st));
+  SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SEMK_OK;
+}

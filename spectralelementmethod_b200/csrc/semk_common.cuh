@@ -1,0 +1,127 @@
+// semk_common.cuh -- shared helpers for the libsemk translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/semk.h"
+
+void semk_set_error(const std::string &msg);
+
+#define SEMK_CUDA_CHECK(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      semk_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+      return SEMK_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define SEMK_LAUNCH_CHECK(name)                                                      \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      semk_set_error(std::string(name) + " launch: " + cudaGetErrorString(_e));      \
+      return SEMK_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define SEMK_REQUIRE(cond, msg)                                                      \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      semk_set_error(msg);                                                           \
+      return SEMK_ERR_INVALID;                                                       \
+    }                                                                                \
+  } while (0)
+
+// Expand `CALL(N)` for the run-time value n1 in [2, 17].
+#define SEMK_DISPATCH_N1(n1, CALL)                                                   \
+  switch (n1) {                                                                      \
+    case 2: CALL(2); break;                                                          \
+    case 3: CALL(3); break;                                                          \
+    case 4: CALL(4); break;                                                          \
+    case 5: CALL(5); break;                                                          \
+    case 6: CALL(6); break;                                                          \
+    case 7: CALL(7); break;                                                          \
+    case 8: CALL(8); break;                                                          \
+    case 9: CALL(9); break;                                                          \
+    case 10: CALL(10); break;                                                        \
+    case 11: CALL(11); break;                                                        \
+    case 12: CALL(12); break;                                                        \
+    case 13: CALL(13); break;                                                        \
+    case 14: CALL(14); break;                                                        \
+    case 15: CALL(15); break;                                                        \
+    case 16: CALL(16); break;                                                        \
+    case 17: CALL(17); break;                                                        \
+    default:                                                                         \
+      semk_set_error("n1 outside [2, 17]");                                          \
+      return SEMK_ERR_UNSUPPORTED;                                                   \
+  }
+
+static inline cudaStream_t semk_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#ifdef __CUDACC__
+// ---- async-proxy (TMA bulk copy) + mbarrier PTX wrappers (sm_90+/sm_100a) ----
+__device__ __forceinline__ uint32_t semk_smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void semk_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(semk_smem_u32(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void semk_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void semk_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(semk_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool semk_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(semk_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void semk_mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!semk_mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP);
+// completion is signalled on `bar` as `bytes` transaction bytes.
+__device__ __forceinline__ void semk_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                              uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(semk_smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(semk_smem_u32(bar))
+      : "memory");
+}
+
+// Deterministic block reduction of one double (blockDim.x a multiple of 32, <= 1024).
+// Result valid in thread 0.
+__device__ __forceinline__ double semk_block_sum(double v, double *smem_scratch /*[32]*/) {
+  const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) smem_scratch[wid] = v;
+  __syncthreads();
+  const unsigned nw = (blockDim.x + 31u) >> 5;
+  double t = 0.0;
+  if (wid == 0) {
+    t = (lane < nw) ? smem_scratch[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;
+}
+#endif

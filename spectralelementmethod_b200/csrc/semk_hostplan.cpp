@@ -1,0 +1,267 @@
+// semk_hostplan.cpp -- host-side patch plan builder (no CUDA calls).
+//
+// The reference assembles by looping over elements and scatter-adding through
+// the L2G map (sem/discrete.py:478-500).  The engine instead groups element
+// slots into patches (one CTA each).  Per patch we tabulate the distinct
+// global nodes it touches, split into
+//   private nodes -- every element containing the node lies in this patch:
+//                    the CTA owns the final value and stores it directly;
+//   shared nodes  -- touched by more than one patch: the CTA writes its
+//                    partial sum to an interface slot and a second, tiny
+//                    kernel sums the slots of each shared node in a fixed
+//                    order (deterministic, no floating-point atomics).
+// Within a patch, elements are greedily coloured so that elements of one
+// colour share no node; the CTA accumulates colour by colour into shared
+// memory without atomics.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/semk.h"
+
+extern void semk_set_error(const std::string &msg);  // semk_api.cu
+
+struct semk_hostplan {
+  int n1 = 0;
+  int pe = 0;
+  int64_t n_elem = 0, n_nodes = 0;
+  int64_t scalars[SEMK_PS_COUNT] = {0};
+  std::vector<int32_t> patch_node_ptr, patch_npriv, patch_slot_base, shared_ptr, shared_slot;
+  std::vector<uint32_t> pnode, shared_node;
+  std::vector<uint16_t> eloc;
+  std::vector<uint8_t> elem_color;
+  std::vector<int64_t> elem_of_slot;
+};
+
+extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
+                                    const int64_t *elem_order, int elems_per_patch,
+                                    const uint8_t *dirichlet, semk_hostplan **out) {
+  if (!out) return SEMK_ERR_INVALID;
+  *out = nullptr;
+  if (n1 < 2 || n1 > SEMK_MAX_N1) {
+    semk_set_error("semk_hostplan_create: n1 must be in [2, 17]");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  if (n_elem < 1 || n_nodes < 1 || !l2g || elems_per_patch < 1) {
+    semk_set_error("semk_hostplan_create: bad sizes or null l2g");
+    return SEMK_ERR_INVALID;
+  }
+  if (n_nodes > (int64_t)SEMK_NODE_ID_MASK) {
+    semk_set_error("semk_hostplan_create: more than 2^30-1 nodes per rank");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  const int NN = n1 * n1;
+  const int PE = elems_per_patch;
+  if ((int64_t)PE * NN > 65535) {
+    semk_set_error("semk_hostplan_create: patch too large for 16-bit local indices");
+    return SEMK_ERR_INVALID;
+  }
+  semk_hostplan *P = new (std::nothrow) semk_hostplan();
+  if (!P) return SEMK_ERR_INVALID;
+  try {
+    P->n1 = n1;
+    P->pe = PE;
+    P->n_elem = n_elem;
+    P->n_nodes = n_nodes;
+    const int64_t n_patch = (n_elem + PE - 1) / PE;
+    const int64_t n_slot_elems = n_patch * PE;
+
+    // slot -> element
+    P->elem_of_slot.resize(n_elem);
+    {
+      std::vector<uint8_t> seen(n_elem, 0);
+      for (int64_t s = 0; s < n_elem; ++s) {
+        int64_t e = elem_order ? elem_order[s] : s;
+        if (e < 0 || e >= n_elem || seen[e]) {
+          delete P;
+          semk_set_error("semk_hostplan_create: elem_order is not a permutation");
+          return SEMK_ERR_INVALID;
+        }
+        seen[e] = 1;
+        P->elem_of_slot[s] = e;
+      }
+    }
+    for (int64_t i = 0; i < n_elem * NN; ++i) {
+      if (l2g[i] >= (uint64_t)n_nodes) {
+        delete P;
+        semk_set_error("semk_hostplan_create: l2g entry out of range");
+        return SEMK_ERR_INVALID;
+      }
+    }
+
+    // pass 1: which nodes are touched by more than one patch
+    std::vector<int32_t> first_patch(n_nodes, -1);
+    std::vector<uint8_t> multi(n_nodes, 0);
+    for (int64_t p = 0; p < n_patch; ++p) {
+      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
+      for (int64_t s = s0; s < s1; ++s) {
+        const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
+        for (int k = 0; k < NN; ++k) {
+          const uint32_t g = row[k];
+          if (first_patch[g] < 0)
+            first_patch[g] = (int32_t)p;
+          else if (first_patch[g] != (int32_t)p)
+            multi[g] = 1;
+        }
+      }
+    }
+
+    // shared node list (ascending id) and slot counts
+    std::vector<int32_t> shared_index(n_nodes, -1);
+    for (int64_t g = 0; g < n_nodes; ++g)
+      if (multi[g]) {
+        shared_index[g] = (int32_t)P->shared_node.size();
+        uint32_t v = (uint32_t)g | SEMK_NODE_SHARED;
+        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
+        P->shared_node.push_back(v);
+      }
+    const int64_t n_shared = (int64_t)P->shared_node.size();
+    P->shared_ptr.assign(n_shared + 1, 0);
+
+    // pass 2: per-patch tables
+    P->patch_node_ptr.assign(n_patch + 1, 0);
+    P->patch_npriv.assign(n_patch, 0);
+    P->patch_slot_base.assign(n_patch, 0);
+    P->eloc.assign((size_t)n_slot_elems * NN, 0);
+    P->elem_color.assign(n_slot_elems, 0);
+    std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
+    std::vector<uint32_t> priv, shar, colmask;
+    std::vector<std::pair<int32_t, int32_t>> slot_pairs;  // (shared index, slot)
+    int64_t max_patch_nodes = 0, n_slots = 0;
+    int max_colors = 1;
+    for (int64_t p = 0; p < n_patch; ++p) {
+      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
+      priv.clear();
+      shar.clear();
+      for (int64_t s = s0; s < s1; ++s) {
+        const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
+        for (int k = 0; k < NN; ++k) {
+          const uint32_t g = row[k];
+          if (local_of[g] == -1) {
+            local_of[g] = -2;  // mark as collected
+            (multi[g] ? shar : priv).push_back(g);
+          }
+        }
+      }
+      std::sort(priv.begin(), priv.end());
+      std::sort(shar.begin(), shar.end());
+      const int32_t np = (int32_t)priv.size(), ns = (int32_t)shar.size();
+      P->patch_npriv[p] = np;
+      P->patch_slot_base[p] = (int32_t)n_slots;
+      for (int32_t k = 0; k < np; ++k) {
+        const uint32_t g = priv[k];
+        local_of[g] = k;
+        uint32_t v = g;
+        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
+        P->pnode.push_back(v);
+      }
+      for (int32_t k = 0; k < ns; ++k) {
+        const uint32_t g = shar[k];
+        local_of[g] = np + k;
+        uint32_t v = g | SEMK_NODE_SHARED;
+        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
+        P->pnode.push_back(v);
+        slot_pairs.emplace_back(shared_index[g], (int32_t)(n_slots + k));
+        P->shared_ptr[shared_index[g] + 1] += 1;
+      }
+      n_slots += ns;
+      if (n_slots > INT32_MAX) {
+        delete P;
+        semk_set_error("semk_hostplan_create: interface slot count overflows int32");
+        return SEMK_ERR_UNSUPPORTED;
+      }
+      P->patch_node_ptr[p + 1] = (int32_t)P->pnode.size();
+      max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
+
+      // element-local index table + greedy colouring
+      colmask.assign(np + ns, 0u);
+      for (int64_t s = s0; s < s1; ++s) {
+        const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
+        uint16_t *er = P->eloc.data() + (size_t)s * NN;
+        uint32_t forbidden = 0;
+        for (int k = 0; k < NN; ++k) {
+          const int32_t loc = local_of[row[k]];
+          er[k] = (uint16_t)loc;
+          forbidden |= colmask[loc];
+        }
+        int c = 0;
+        while (c < 31 && (forbidden >> c) & 1u) ++c;
+        if (c >= 31) {
+          delete P;
+          semk_set_error("semk_hostplan_create: more than 31 colours needed in a patch");
+          return SEMK_ERR_UNSUPPORTED;
+        }
+        for (int k = 0; k < NN; ++k) colmask[er[k]] |= (1u << c);
+        P->elem_color[s] = (uint8_t)c;
+        max_colors = std::max(max_colors, c + 1);
+      }
+      // padded slots of a ragged last patch: colour 255 = never active
+      for (int64_t s = s1; s < s0 + PE; ++s) P->elem_color[s] = 255;
+      // reset scratch
+      for (uint32_t g : priv) local_of[g] = -1;
+      for (uint32_t g : shar) local_of[g] = -1;
+    }
+    if ((int64_t)P->pnode.size() > INT32_MAX) {
+      delete P;
+      semk_set_error("semk_hostplan_create: patch node table overflows int32");
+      return SEMK_ERR_UNSUPPORTED;
+    }
+
+    // CSR of interface slots per shared node (slots in ascending patch order)
+    for (int64_t i = 0; i < n_shared; ++i) P->shared_ptr[i + 1] += P->shared_ptr[i];
+    P->shared_slot.assign(n_slots, 0);
+    {
+      std::vector<int32_t> fill(P->shared_ptr.begin(), P->shared_ptr.end() - 1);
+      for (const auto &pr : slot_pairs) P->shared_slot[fill[pr.first]++] = pr.second;
+    }
+
+    P->scalars[SEMK_PS_N_PATCH] = n_patch;
+    P->scalars[SEMK_PS_N_PNODE] = (int64_t)P->pnode.size();
+    P->scalars[SEMK_PS_N_SLOTS] = n_slots;
+    P->scalars[SEMK_PS_N_SHARED] = n_shared;
+    P->scalars[SEMK_PS_MAX_PATCH_NODES] = max_patch_nodes;
+    P->scalars[SEMK_PS_MAX_COLORS] = max_colors;
+    P->scalars[SEMK_PS_N_SLOT_ELEMS] = n_slot_elems;
+  } catch (const std::bad_alloc &) {
+    delete P;
+    semk_set_error("semk_hostplan_create: out of host memory");
+    return SEMK_ERR_INVALID;
+  }
+  *out = P;
+  return SEMK_OK;
+}
+
+extern "C" int64_t semk_hostplan_scalar(const semk_hostplan *plan, int which) {
+  if (!plan || which < 0 || which >= SEMK_PS_COUNT) return -1;
+  return plan->scalars[which];
+}
+
+template <class T>
+static const void *vec_ptr(const std::vector<T> &v, int64_t *n_bytes) {
+  if (n_bytes) *n_bytes = (int64_t)(v.size() * sizeof(T));
+  return v.data();
+}
+
+extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
+                                           int64_t *n_bytes) {
+  if (n_bytes) *n_bytes = 0;
+  if (!plan) return nullptr;
+  switch (which) {
+    case SEMK_PA_PATCH_NODE_PTR: return vec_ptr(plan->patch_node_ptr, n_bytes);
+    case SEMK_PA_PNODE: return vec_ptr(plan->pnode, n_bytes);
+    case SEMK_PA_PATCH_NPRIV: return vec_ptr(plan->patch_npriv, n_bytes);
+    case SEMK_PA_PATCH_SLOT_BASE: return vec_ptr(plan->patch_slot_base, n_bytes);
+    case SEMK_PA_ELOC: return vec_ptr(plan->eloc, n_bytes);
+    case SEMK_PA_ELEM_COLOR: return vec_ptr(plan->elem_color, n_bytes);
+    case SEMK_PA_ELEM_OF_SLOT: return vec_ptr(plan->elem_of_slot, n_bytes);
+    case SEMK_PA_SHARED_NODE: return vec_ptr(plan->shared_node, n_bytes);
+    case SEMK_PA_SHARED_PTR: return vec_ptr(plan->shared_ptr, n_bytes);
+    case SEMK_PA_SHARED_SLOT: return vec_ptr(plan->shared_slot, n_bytes);
+    default: return nullptr;
+  }
+}
+
+extern "C" void semk_hostplan_destroy(semk_hostplan *plan) { delete plan; }

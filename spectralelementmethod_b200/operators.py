@@ -1,0 +1,401 @@
+"""The device-resident Poisson operator (additive API).
+
+The reference has no operator object: examples/poisson.py:145-259 builds a
+dense 4-index local stiffness per element, assembles a COO Schur system and
+calls SuperLU.  ``PoissonOperator`` is the matrix-free replacement of that
+whole path on one GPU:
+
+    op = dof_mngr.poisson_operator(dirichlet=on_ebc)
+    y  = op.apply(u)                      # y = Ahat u, Ahat = M A M + (I - M)
+    d  = op.diagonal()                    # diag(Ahat)
+    b  = op.rhs(f=1.0)                    # assembled load vector  Q^T (JxW f)
+    x, info = op.solve_pcg(op.lift(b, g)) # Jacobi-PCG, Dirichlet data g lifted
+
+Vectors are ``torch.float64`` CUDA tensors of length ``n_nodes`` in the
+reference's global node order (whatever numbering the DOF manager produced:
+lexicographic, exterior-first, RCM).  Every number is computed by the CUDA
+kernels behind the C ABI (include/semk.h); nothing here falls back to NumPy.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, device
+from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
+
+__all__ = ["PoissonOperator", "PCGInfo", "default_element_order", "choose_elems_per_patch"]
+
+_TILES = {16: (4, 4), 8: (2, 4), 4: (2, 2)}
+_SMEM_TARGET = 76 * 1024     # <= this keeps >= 3 CTAs per SM
+_SMEM_LIMIT = 227 * 1024
+
+
+def g_stride_of(n1):
+    nn3 = 3 * n1 * n1
+    return nn3 + (nn3 & 1)          # even => 16-byte multiples for the TMA bulk copy
+
+
+def patch_smem_bytes(n1, pe, max_patch_nodes):
+    nn = n1 * n1
+    return 16 + 8 * (pe * g_stride_of(n1) + 2 * max_patch_nodes + 2 * pe * nn + 32)
+
+
+def choose_elems_per_patch(n1):
+    """Largest patch (16, 8 or 4 elements) whose shared-memory footprint still
+    lets three CTAs share an SM; else the largest that fits at all."""
+    p = n1 - 1
+
+    def est(pe):
+        bx, by = _TILES[pe]
+        return patch_smem_bytes(n1, pe, (bx * p + 1) * (by * p + 1))
+    for pe in (16, 8, 4):
+        if est(pe) <= _SMEM_TARGET:
+            return pe
+    for pe in (16, 8, 4):
+        if est(pe) <= _SMEM_LIMIT:
+            return pe
+    raise NotImplementedError("no patch size fits shared memory for n1=%d" % n1)
+
+
+def _morton_order(cx, cy):
+    def spread(v):
+        v = v.astype(np.uint64)
+        v = (v | (v << 16)) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << 8)) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << 4)) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << 2)) & np.uint64(0x3333333333333333)
+        v = (v | (v << 1)) & np.uint64(0x5555555555555555)
+        return v
+
+    def quant(c):
+        lo, hi = c.min(), c.max()
+        scale = 65535.0 / (hi - lo) if hi > lo else 0.0
+        return np.floor((c - lo) * scale).astype(np.uint32)
+    key = spread(quant(cx)) | (spread(quant(cy)) << np.uint64(1))
+    return np.argsort(key, kind="stable").astype(np.int64)
+
+
+def default_element_order(mesh, elems_per_patch):
+    """Engine slot order (slot -> element) that makes consecutive runs of
+    ``elems_per_patch`` elements compact patches: tiles of a structured grid
+    when the mesh builder recorded one, else a Morton curve through the cell
+    centroids."""
+    shape = getattr(mesh, "_structured_shape", None)
+    if shape is not None and shape[0] * shape[1] == mesh.n_cells:
+        nx, ny = shape
+        bx, by = _TILES[elems_per_patch]
+        ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
+        key = ((ex // bx) * ((ny + by - 1) // by) + ey // by) * (bx * by) + (ex % bx) * by + ey % by
+        return np.argsort(key, kind="stable").astype(np.int64)
+    if not hasattr(mesh, "_centroids"):
+        mesh._compute_cell_centroids()
+    return _morton_order(mesh._centroids[:, 0], mesh._centroids[:, 1])
+
+
+class PCGInfo(object):
+    __slots__ = ("iterations", "status", "rel_residual", "bnorm", "converged")
+
+    def __init__(self, iterations, status, rel_residual, bnorm):
+        self.iterations = int(iterations)
+        self.status = int(status)
+        self.rel_residual = float(rel_residual)
+        self.bnorm = float(bnorm)
+        self.converged = self.status == 0
+
+    def __repr__(self):
+        return ("PCGInfo(iterations=%d, status=%d, rel_residual=%.3e, bnorm=%.6e)"
+                % (self.iterations, self.status, self.rel_residual, self.bnorm))
+
+
+class PoissonOperator(object):
+    def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
+                 elem_order=None, keep_l2g=True):
+        _lib.require_device()
+        self._lib = _lib.load()
+        mesh = dof_mngr.mesh
+        self.dof_mngr = dof_mngr
+        self.tab = device.basis_tables(dof_mngr._basis)
+        n1 = self.n1 = self.tab.n1
+        NN = n1 * n1
+        l2g = mesh.node_map_array().reshape(-1, NN)
+        self.n_elem = int(l2g.shape[0])
+        self.n_nodes = int(mesh.n_nodes)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+
+        if dirichlet is not None:
+            dirichlet = np.asarray(dirichlet)
+            if dirichlet.dtype != np.bool_ or dirichlet.shape != (self.n_nodes,):
+                raise ValueError("dirichlet must be bool[n_nodes] (True = essential-BC node)")
+        self.dirichlet_host = dirichlet
+        self.has_dirichlet = dirichlet is not None and bool(dirichlet.any())
+
+        pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
+        if elem_order is None:
+            elem_order = default_element_order(mesh, pe)
+        sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
+        self.plan_scalars = sc
+        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES])
+        if smem > _SMEM_LIMIT:
+            raise NotImplementedError(
+                "patch of %d elements needs %d B of shared memory (> 227 KB); pass a smaller "
+                "elems_per_patch or a more local elem_order" % (pe, smem))
+        self.smem_bytes = smem
+
+        t = {}
+        for k in (_lib.PA_PATCH_NODE_PTR, _lib.PA_PATCH_NPRIV, _lib.PA_PATCH_SLOT_BASE,
+                  _lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT):
+            t[k] = torch.from_numpy(ar[k]).to(self.dev)
+        for k in (_lib.PA_PNODE, _lib.PA_SHARED_NODE):
+            t[k] = device.as_i32_bits(ar[k], self.dev)
+        t[_lib.PA_ELOC] = torch.from_numpy(ar[_lib.PA_ELOC].view(np.int16)).to(self.dev)
+        t[_lib.PA_ELEM_COLOR] = torch.from_numpy(ar[_lib.PA_ELEM_COLOR]).to(self.dev)
+        t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
+        self._tables = t
+        self.elem_of_slot_host = ar[_lib.PA_ELEM_OF_SLOT]
+        self.n_slot_elems = sc[_lib.PS_N_SLOT_ELEMS]
+        self.n_patch = sc[_lib.PS_N_PATCH]
+        self.n_shared = sc[_lib.PS_N_SHARED]
+        self.n_slots = sc[_lib.PS_N_SLOTS]
+
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.g_stride = g_stride_of(n1)
+        self.G = torch.zeros((self.n_slot_elems, self.g_stride), **f64)
+        self.JxW = torch.empty((self.n_elem, NN), **f64)
+        self.l2g_dev = device.as_i32_bits(l2g, self.dev)
+        if geometric_factors is None:
+            nodes_dev = torch.from_numpy(np.ascontiguousarray(mesh.nodes, dtype=np.float64)).to(self.dev)
+            if nodes_dev.shape[0] != 2:
+                raise NotImplementedError("Only supporting 2D elements right now")
+            device.geom_factors(self.tab, nodes_dev, self.l2g_dev, self.n_elem,
+                                elem_of_slot=t[_lib.PA_ELEM_OF_SLOT], G=self.G,
+                                g_stride=self.g_stride, JxW=self.JxW)
+            del nodes_dev
+        else:
+            invJ, jxw = geometric_factors
+            invJ = device._f64(np.asarray(invJ).reshape(self.n_elem, 4, NN), self.dev)
+            self.JxW.copy_(device._f64(np.asarray(jxw).reshape(self.n_elem, NN), self.dev))
+            _lib.check(self._lib.semk_gfactors_from_invj_f64(
+                n1, self.n_elem, device.ptr(invJ), device.ptr(self.JxW),
+                device.ptr(t[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G), self.g_stride,
+                device.stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+            del invJ
+        if not keep_l2g:
+            self.l2g_dev = None
+
+        self.slot_buf = torch.zeros(max(self.n_slots, 1), **f64)
+        self.partials = torch.zeros(
+            int(self._lib.semk_partials_len(self.n_patch, self.n_shared)), **f64)
+        self.vec_partials = torch.zeros(int(self._lib.semk_vec_partials_len(self.n_nodes)), **f64)
+        self.dirichlet_dev = (torch.from_numpy(dirichlet.astype(np.uint8)).to(self.dev)
+                              if dirichlet is not None else None)
+
+        op = _lib.semk_op()
+        op.n1, op.elems_per_patch = n1, pe
+        op.n_elem, op.n_nodes, op.n_patch = self.n_elem, self.n_nodes, self.n_patch
+        op.max_patch_nodes = sc[_lib.PS_MAX_PATCH_NODES]
+        op.max_colors = sc[_lib.PS_MAX_COLORS]
+        op.g_stride = self.g_stride
+        op.G = self.G.data_ptr()
+        op.patch_node_ptr = t[_lib.PA_PATCH_NODE_PTR].data_ptr()
+        op.pnode = t[_lib.PA_PNODE].data_ptr()
+        op.patch_npriv = t[_lib.PA_PATCH_NPRIV].data_ptr()
+        op.patch_slot_base = t[_lib.PA_PATCH_SLOT_BASE].data_ptr()
+        op.eloc = t[_lib.PA_ELOC].data_ptr()
+        op.elem_color = t[_lib.PA_ELEM_COLOR].data_ptr()
+        op.n_slots = self.n_slots
+        op.slot_buf = self.slot_buf.data_ptr()
+        op.n_shared = self.n_shared
+        op.shared_node = t[_lib.PA_SHARED_NODE].data_ptr() if self.n_shared else None
+        op.shared_ptr = t[_lib.PA_SHARED_PTR].data_ptr() if self.n_shared else None
+        op.shared_slot = t[_lib.PA_SHARED_SLOT].data_ptr() if self.n_shared else None
+        op.partials = self.partials.data_ptr()
+        op.D_host = self.tab.D_host.ctypes.data
+        self._op = op
+        self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
+        self._dinv = None
+
+    # -- helpers ---------------------------------------------------------------------
+    def _vec(self, v, name="vector"):
+        if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float64
+                and v.is_contiguous() and v.numel() == self.n_nodes):
+            raise ValueError("%s must be a contiguous float64 CUDA tensor of length n_nodes" % name)
+        return v
+
+    def new_vector(self, fill=None):
+        if fill is None:
+            return torch.empty(self.n_nodes, dtype=torch.float64, device=self.dev)
+        return torch.full((self.n_nodes,), float(fill), dtype=torch.float64, device=self.dev)
+
+    def from_host(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+
+    @property
+    def algorithmic_bytes_per_apply(self):
+        """read u, write y, 3 geometric factors + one uint32
+        L2G entry per element-local node."""
+        return 16 * self.n_nodes + 28 * self.n_elem * self.n1 * self.n1
+
+    # -- operator --------------------------------------------------------------------
+    def apply(self, u, out=None, flags=None, dot_out=None):
+        """y = Ahat u with Ahat = M A M + (I - M) (A if no Dirichlet mask).
+        ``flags`` overrides the masking (bit-or of MASK_IN, MASK_OUT,
+        DIRICHLET_IDENTITY; 0 = the pure Neumann operator A).  ``dot_out``:
+        optional 1-element device tensor receiving u.y."""
+        self._vec(u, "u")
+        y = self.new_vector() if out is None else self._vec(out, "out")
+        if flags is None:
+            flags = self._masked_flags
+        _lib.check(self._lib.semk_poisson_apply_f64(
+            C.byref(self._op), device.ptr(u), device.ptr(y), int(flags), device.ptr(dot_out),
+            device.stream_ptr()))
+        return y
+
+    def apply_unmasked(self, u, out=None):
+        """y = A u: the reference's assembled stiffness matrix, no BCs."""
+        return self.apply(u, out=out, flags=0)
+
+    def apply_atomic(self, u, out=None, flags=None):
+        """Same operator through the independent atomic-scatter kernel."""
+        if self.l2g_dev is None:
+            raise RuntimeError("operator was built with keep_l2g=False")
+        self._vec(u, "u")
+        y = self.new_vector() if out is None else self._vec(out, "out")
+        if flags is None:
+            flags = self._masked_flags
+        _lib.check(self._lib.semk_poisson_apply_atomic_f64(
+            self.n1, self.n_elem, self.n_nodes, device.ptr(self.l2g_dev),
+            device.ptr(self._tables[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G), self.g_stride,
+            device.ptr(self.tab.D_host), device.ptr(self.dirichlet_dev), device.ptr(u),
+            device.ptr(y), int(flags), device.stream_ptr()))
+        return y
+
+    def apply_host(self, u_host, y_host, scratch=None):
+        """End-to-end call on HOST buffers (numpy float64 or pinned torch CPU
+        tensors): H2D copy, apply, D2H copy, synchronised on return."""
+        if scratch is None:
+            scratch = (self.new_vector(), self.new_vector())
+        _lib.check(self._lib.semk_poisson_apply_host_f64(
+            C.byref(self._op), device.ptr(u_host), device.ptr(y_host), device.ptr(scratch[0]),
+            device.ptr(scratch[1]), int(self._masked_flags), device.stream_ptr()))
+        return y_host
+
+    def assemble(self, loc, out=None, mask=False, fill_dirichlet=0.0):
+        """Assemble an element-local field ``loc[n_slot_elems, NN]`` (engine
+        slot order) into a global vector (the reference's ``grhs[inds] +=``)."""
+        y = self.new_vector() if out is None else self._vec(out, "out")
+        _lib.check(self._lib.semk_assemble_f64(
+            C.byref(self._op), device.ptr(loc), device.ptr(y), MASK_OUT if mask else 0,
+            float(fill_dirichlet), device.stream_ptr()))
+        return y
+
+    def diagonal(self, masked=True):
+        """diag(Ahat) (masked: 1 on Dirichlet rows) or diag(A)."""
+        loc = torch.empty((self.n_slot_elems, self.n1 * self.n1), dtype=torch.float64,
+                          device=self.dev)
+        _lib.check(self._lib.semk_poisson_local_diag_f64(C.byref(self._op), device.ptr(loc),
+                                                         device.stream_ptr()))
+        return self.assemble(loc, mask=masked and self.has_dirichlet, fill_dirichlet=1.0)
+
+    def rhs(self, f=1.0):
+        """Load vector b = Q^T (JxW . f); ``f`` a scalar or nodal values
+        (examples/poisson.py:200 uses f = 1).  No boundary treatment."""
+        fv = None
+        scale = 1.0
+        if isinstance(f, torch.Tensor):
+            fv = self._vec(f, "f")
+        elif np.ndim(f) == 0:
+            scale = float(f)
+        else:
+            fv = self.from_host(f)
+        if fv is not None and self.l2g_dev is None:
+            raise RuntimeError("operator was built with keep_l2g=False")
+        loc = torch.empty((self.n_slot_elems, self.n1 * self.n1), dtype=torch.float64,
+                          device=self.dev)
+        _lib.check(self._lib.semk_weighted_local_f64(
+            self.n1, self.n_elem, self.n_slot_elems, device.ptr(self.JxW),
+            device.ptr(self.l2g_dev), device.ptr(self._tables[_lib.PA_ELEM_OF_SLOT]),
+            device.ptr(fv), device.ptr(loc), device.stream_ptr()))
+        b = self.assemble(loc)
+        if scale != 1.0:
+            b *= scale
+        return b
+
+    def mass_diagonal(self):
+        """Diagonal (lumped = exact for GLL collocation) mass matrix."""
+        return self.rhs(1.0)
+
+    def lift(self, b, dirichlet_values=None):
+        """RHS of the SPD system Ahat x = bhat: free rows b_f - A_fe g_e,
+        Dirichlet rows g_e (sem/discrete.py:505-509)."""
+        self._vec(b, "b")
+        if not self.has_dirichlet:
+            return b.clone()
+        mask = self.dirichlet_dev.bool()
+        g = torch.zeros_like(b)
+        if dirichlet_values is not None:
+            gv = dirichlet_values if isinstance(dirichlet_values, torch.Tensor) \
+                else self.from_host(dirichlet_values)
+            g[mask] = gv[mask]
+        t = self.apply(g, flags=MASK_OUT)      # A (I-M) g on the free rows
+        out = b - t
+        out[mask] = g[mask]
+        return out
+
+    # -- solver ----------------------------------------------------------------------
+    def jacobi_inverse(self):
+        if self._dinv is None:
+            self._dinv = 1.0 / self.diagonal(masked=True)
+        return self._dinv
+
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
+        """Jacobi-preconditioned CG on Ahat x = b (b already lifted).  Returns
+        (x, PCGInfo).  The loop runs on the device (native driver,
+        csrc/semk_vec.cu); the host polls 64 bytes every ``check_every``
+        iterations."""
+        self._vec(b, "b")
+        if x0 is None:
+            x = torch.zeros_like(b)
+            if self.has_dirichlet:
+                m = self.dirichlet_dev.bool()
+                x[m] = b[m]
+        else:
+            x = self._vec(x0, "x0").clone()
+        dinv = self.jacobi_inverse()
+        work = torch.empty(4 * self.n_nodes, dtype=torch.float64, device=self.dev)
+        sc = torch.zeros(8, dtype=torch.float64, device=self.dev)
+        info = _lib.semk_pcg_info()
+        rc = self._lib.semk_pcg_solve_f64(
+            C.byref(self._op), device.ptr(b), device.ptr(x), device.ptr(dinv), device.ptr(work),
+            device.ptr(sc), device.ptr(self.vec_partials), float(rtol), int(maxiter),
+            int(check_every), C.byref(info), device.stream_ptr())
+        _lib.check(rc)
+        return x, PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
+
+    def solve(self, f=1.0, dirichlet_values=None, **pcg_kwargs):
+        """Poisson solve in one call: assemble the load, lift the Dirichlet
+        data, run PCG.  Returns (u, PCGInfo)."""
+        b = self.lift(self.rhs(f), dirichlet_values)
+        return self.solve_pcg(b, **pcg_kwargs)
+
+    # -- small-mesh test helper ----------------------------------------------------------
+    def to_scipy_csr(self, masked=False, tol=0.0):
+        """Assembled matrix by applying the operator to unit vectors (tests,
+        small meshes only)."""
+        from scipy import sparse
+        n = self.n_nodes
+        if n > 20000:
+            raise ValueError("to_scipy_csr is meant for small meshes")
+        cols = []
+        e = self.new_vector(0.0)
+        y = self.new_vector()
+        flags = None if masked else 0
+        for j in range(n):
+            e[j] = 1.0
+            self.apply(e, out=y, flags=flags)
+            e[j] = 0.0
+            c = y.cpu().numpy()
+            c[np.abs(c) <= tol] = 0.0
+            cols.append(sparse.csc_matrix(c.reshape(-1, 1)))
+        return sparse.hstack(cols).tocsr()
