@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: FP64 matrix-free Poisson operator apply (p = 8).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # engine arm
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU reference arm
+
+A "step" is one operator apply y = Ahat u over the whole mesh:
+  N = 1 : BASELINE.json configs[1], 1024 x 1024 elements, p = 8 (67 125 249 DOF);
+  N > 1 : BASELINE.json configs[4], 884 x 884 elements per GPU (50 027 329 DOF
+          per GPU), strip-partitioned, interface exchange included (weak scaling).
+The working set (>= 2.6 GB per GPU) is far larger than the 126 MB L2, so no
+cache flush is needed between timed iterations.
+
+One JSON line is printed by rank 0 (see the task contract): value = GDOF/s of
+the device-resident apply, e2e = the same apply through the C ABI on pinned
+HOST buffers (H2D + apply + D2H per step), roofline = algorithmic bytes /
+measured time of the apply kernels vs the measured HBM copy peak,
+cpu_baseline = the reference's dense local apply (oracle port) on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Poisson operator-apply GDOF/s (FP64, p=8)"
+ORDER = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--nx", type=int, default=0, help="elements per side per GPU (0 = config default)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--pcg-iters", type=int, default=300,
+                    help="PCG iterations timed for the time-to-solution estimate (0 = skip)")
+    ap.add_argument("--pcg-full", action="store_true", help="run PCG to rtol 1e-12")
+    ap.add_argument("--cpu-sample", type=int, default=64,
+                    help="elements per side of the CPU-baseline sample mesh (0 = skip)")
+    ap.add_argument("--kind", default="S", choices=["S", "C"])
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                for line in out.stdout.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU baseline (the oracle port of the reference's apply), bounded sample
+# --------------------------------------------------------------------------
+def cpu_baseline(n_side, kind, target_seconds=12.0):
+    """The reference's operator apply on host cores: dense local stiffness
+    (examples/poisson.py:181-193) applied element by element
+    (examples/squirmer-axisymmetric.py:284-295) in a Python loop -- exactly how
+    the reference does it -- on an n_side x n_side, p = 8 sample mesh."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sem_oracle as so
+    basis = so.Basis(ORDER)
+    nodes, l2g = so.build_case(kind, n_side, n_side, ORDER, False, False)
+    geo = so.geometry(basis, nodes, l2g)
+    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+    u = np.sin(3 * nodes[0]) * np.cos(2 * nodes[1])
+    so.apply_dense_local(L, l2g, u)                     # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        so.apply_dense_local(L, l2g, u)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= target_seconds or reps >= 200:
+            break
+    ndof = nodes.shape[1]
+    return {"value": ndof * reps / el / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "port",
+            "sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s, dense local einsum "
+                      "loop (oracle/sem_oracle.py:apply_dense_local)" % (n_side, n_side, ORDER,
+                                                                         ndof, reps, el)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle
+    port; the Python reference cannot travel to the GPU box), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_side = args.cpu_sample or 64
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sem_oracle as so
+    basis = so.Basis(ORDER)
+    nodes, l2g = so.build_case(args.kind, n_side, n_side, ORDER, False, False)
+    geo = so.geometry(basis, nodes, l2g)
+    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+    u = np.sin(3 * nodes[0]) * np.cos(2 * nodes[1])
+    ndof = nodes.shape[1]
+    for _ in range(max(args.warmup, 1)):
+        so.apply_dense_local(L, l2g, u)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        so.apply_dense_local(L, l2g, u)
+    el = time.perf_counter() - t0
+    value = ndof * args.steps / el / 1e9
+    sample = ("%dx%d elements p=%d (%d DOF) per step: bounded sample of the 1024x1024 workload; "
+              "dense local einsum loop, single Python thread like the reference"
+              % (n_side, n_side, ORDER, ndof))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GDOF/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "structured quad mesh Poisson p=8 FP64 (CPU sample %dx%d)"
+                               % (n_side, n_side)},
+        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": 1, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# engine arm
+# --------------------------------------------------------------------------
+def run_engine(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from spectralelementmethod_b200 import discrete, meshgen
+    from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t_setup = time.perf_counter()
+    if not multi:
+        nx = args.nx or 1024
+        mesh = meshgen.structured_quad_mesh(nx, nx, ORDER, args.kind)
+        b1 = LagrangeGaussLobatto(ORDER)
+        mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        on_ebc = mngr.boundary_node_mask("ebc")
+        op = mngr.poisson_operator(dirichlet=on_ebc)
+        apply_fn = lambda u, out: op.apply(u, out=out)          # noqa: E731
+        n_local = n_global = op.n_nodes
+        n_global_units = n_global
+        workload = ("structured %dx%d-element quad mesh Poisson, p=8, FP64, rcm_order=False "
+                    "(BASELINE configs[1])" % (nx, nx))
+        dp = None
+    else:
+        from spectralelementmethod_b200.distributed import DistributedPoisson, StripPartition
+        nx = args.nx or 884
+        part = StripPartition(rank, world, nx, nx, ORDER, bounds=(-1.0, -1.0 + 2.0 * world, -1.0, 1.0))
+        dp = DistributedPoisson(part, ORDER, args.kind)
+        op = dp.op
+        apply_fn = lambda u, out: dp.apply(u, out=out)          # noqa: E731
+        n_local = op.n_nodes
+        n_global_units = part.n_global
+        workload = ("weak scaling: %dx%d elements p=8 per GPU, strip-partitioned over %d GPUs, "
+                    "NCCL interface exchange (BASELINE configs[4])" % (nx, nx, world))
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    x, y = op.dof_mngr.mesh.nodes
+    u = torch.from_numpy(np.sin(3 * x) * np.cos(2 * y)).to(dev)
+    out = torch.empty_like(u)
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident apply: W warm-ups, K timed steps ----------------------
+    for _ in range(max(args.warmup, 3)):
+        apply_fn(u, out)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            apply_fn(u, out)
+        ev1.record()
+        barrier()
+        elapsed = ev0.elapsed_time(ev1) / 1e3
+    if multi:
+        t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t)
+    ms_per_step = elapsed / args.steps * 1e3
+    value = n_global_units / (elapsed / args.steps) / 1e9
+
+    # ---- roofline of the apply kernels (local operator only, rank 0's GPU) -------
+    for _ in range(3):
+        op.apply(u, out=out)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        op.apply(u, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_kernel = ev0.elapsed_time(ev1) / 1e3 / args.steps
+    peak, peak_kind = measured_peaks()
+    alg_bytes = op.algorithmic_bytes_per_apply
+    achieved = alg_bytes / t_kernel / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "kernel": "patch_kernel<9,16,APPLY> + shared_nodes_kernel (one apply)",
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "ms_per_launch": t_kernel * 1e3}
+
+    # ---- e2e: host buffers through the C ABI (H2D + apply + D2H per step) ---------
+    u_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    y_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    u_host.copy_(u)
+    scratch = (op.new_vector(), op.new_vector())
+
+    def e2e_step():
+        if dp is None:
+            op.apply_host(u_host, y_host, scratch)
+        else:
+            scratch[0].copy_(u_host, non_blocking=True)
+            dp.apply(scratch[0], out=scratch[1])
+            y_host.copy_(scratch[1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_el = time.perf_counter() - t0
+    if multi:
+        t = torch.tensor([e2e_el], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_el = float(t)
+    e2e_value = n_global_units / (e2e_el / args.e2e_steps) / 1e9
+    e2e_ok = bool(torch.equal(y_host.to(dev), out)) if dp is None else True
+
+    # ---- PCG time-to-solution (reported beside the headline) -----------------------
+    pcg = None
+    if args.pcg_iters > 0 or args.pcg_full:
+        maxiter = 200000 if args.pcg_full else args.pcg_iters
+        if dp is None:
+            gl = None
+            b = op.lift(op.rhs(1.0), gl)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            xs, info = op.solve_pcg(b, rtol=1e-12, maxiter=maxiter, check_every=50)
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            pcg = {"iterations": info.iterations, "seconds": el, "converged": info.converged,
+                   "rel_residual": info.rel_residual,
+                   "ms_per_iteration": el / max(info.iterations, 1) * 1e3}
+        else:
+            b = dp.lift(dp.rhs(1.0), None)
+            barrier()
+            t0 = time.perf_counter()
+            xs, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, maxiter=maxiter, check_every=50)
+            barrier()
+            el = time.perf_counter() - t0
+            pcg = {"iterations": it, "seconds": el, "converged": ok, "rel_residual": rel,
+                   "ms_per_iteration": el / max(it, 1) * 1e3}
+        pcg["note"] = ("homogeneous Dirichlet on ebc, f=1, rtol 1e-12"
+                       + ("" if args.pcg_full else "; capped at %d iterations" % maxiter))
+
+    cpu = None
+    if rank == 0 and not multi and args.cpu_sample > 0:
+        cpu = cpu_baseline(args.cpu_sample, args.kind)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload, "order": ORDER, "dof_total": int(n_global_units),
+                       "dof_per_gpu": int(n_local), "elements_per_gpu": int(op.n_elem),
+                       "elems_per_patch": op.elems_per_patch, "kind": args.kind,
+                       "l2_policy": "inputs (>= 2.6 GB per GPU) exceed the 126 MB L2; no flush",
+                       "setup_seconds": t_setup},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local * world,
+                    "d2h_bytes_per_step": 8 * n_local * world, "steps": args.e2e_steps,
+                    "matches_device_result": e2e_ok},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks.summary(),
+            "pcg": pcg,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,7 @@ typedef struct semk_op {
   const int32_t *shared_slot;
   double *partials;         /* [semk_partials_len()] dot-product scratch    */
   const double *D_host;     /* HOST pointer, [NN] differentiation matrix    */
+  const uint8_t *dirichlet; /* [n_nodes] 1 = essential-BC node, or NULL (PCG: not an unknown) */
 } semk_op;
 
 /* number of doubles the `partials` scratch of an operator must hold */
@@ -235,10 +236,12 @@ int semk_weighted_local_f64(int n1, int64_t n_elem, int64_t n_slot_elems, const 
  * by the caller before first use (holds an arrival counter).
  * ------------------------------------------------------------------------ */
 int64_t semk_vec_partials_len(int64_t n);
-/* r = b - Ax (Ax given);  z = dinv*r;  p = z;  sc[0] = r.z, sc[3] = r.r, sc[4] = b.b */
+/* r = b - Ax (Ax given);  z = dinv*r;  p = z;  sc[0] = r.z, sc[3] = r.r, sc[4] = b.b.
+ * dirichlet (device uint8 [n] or NULL): rows that are not unknowns -- r is forced
+ * to 0 there and they do not enter ||b|| (the reduced system of sem/discrete.py:505-510). */
 int semk_pcg_init_f64(int64_t n, int64_t n_dot, const double *b, const double *Ax,
-                      const double *dinv, double *r, double *p, double *sc, double *partials,
-                      void *stream);
+                      const double *dinv, const uint8_t *dirichlet, double *r, double *p,
+                      double *sc, double *partials, void *stream);
 /* alpha = sc[0]/sc[1];  x += alpha p;  r -= alpha Ap;  sc[2] = r.(dinv r), sc[3] = r.r,
  * sc[5] += 1; sc[7] = 1 on breakdown (pAp <= 0 or NaN; x, r are then left unchanged) */
 int semk_pcg_update_xr_f64(int64_t n, int64_t n_dot, const double *p, const double *Ap,

@@ -1,0 +1,440 @@
+"""CPU oracle: a NumPy restatement of the reference's algorithm for the hot path.
+
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module; it
+is the checker, never the thing shipped or measured as the engine.  The product
+package (spectralelementmethod_b200/) never imports it and has no CPU fallback.
+
+Parity pinning: the reference's own tests hold no golden vectors for this path
+(both test files are stale and only check analytic values
+at rtol 1e-2).  The oracle is therefore pinned against outputs of the
+*reference itself run in the development container* (oracle/live_reference.py
+drives the unmodified /root/reference/sem through five compatibility shims);
+oracle/make_golden.py froze those outputs into tests/golden/*.npz and
+tests/test_oracle_golden.py checks this restatement against them.
+
+Every function cites the reference lines it follows (paths relative to the
+reference tree).  Where it is cheap the restatement is batched over elements,
+but it keeps the reference's formulas (dense 4-index local stiffness from the
+four einsums, dense local apply, LU solve with the equispaced matrix, ...).
+The only data shared with the product is the GLL table
+(spectralelementmethod_b200/gll_tables.py = bytes of sem/data/basis-data.hdf5).
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.linalg as sla
+from scipy import sparse
+from scipy.sparse import csgraph
+from scipy.sparse.linalg import spsolve
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _tables():
+    sys.path.insert(0, os.path.join(_HERE, ".."))
+    try:
+        from spectralelementmethod_b200 import gll_tables
+    finally:
+        sys.path.pop(0)
+    return gll_tables
+
+
+# --------------------------------------------------------------------------
+# 1-D tables
+# --------------------------------------------------------------------------
+def gll(order):
+    """nodes, barycentric weights, quadrature weights on [-1, 1], mirrored from
+    the stored non-negative half (sem/basis_functions.py:372-388)."""
+    half = np.array(_tables().half_table(order))
+    n = order + 1
+    nodes, bary, quad = np.zeros(n), np.zeros(n), np.zeros(n)
+    m = n // 2
+    nodes[m:], bary[m:], quad[m:] = half[0], half[1], half[2]
+    if n % 2 == 1:
+        nodes[:m] = -half[0, -1:0:-1]
+        bary[:m] = half[1, -1:0:-1]
+        quad[:m] = half[2, -1:0:-1]
+    else:
+        nodes[:m] = -half[0, -1::-1]
+        bary[:m] = -half[1, -1::-1]
+        quad[:m] = half[2, -1::-1]
+    return nodes, bary, quad
+
+
+def diff_matrix(nodes, bary):
+    """D[i,j] = (w_j/w_i)/(x_i-x_j), D[i,i] = -sum_j D[i,j]
+    (sem/basis_functions.py:213-217)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        D = bary[None, :] / bary[:, None]
+        D /= nodes[:, None] - nodes[None, :]
+    np.fill_diagonal(D, 0.0)
+    np.fill_diagonal(D, -D.sum(axis=1))
+    return D
+
+
+def lagrange_eval(nodes, bary, x):
+    """B[i,j] = l_j(x_i), barycentric form (sem/basis_functions.py:226-255)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kern = bary / (x[..., None] - nodes)
+        s = kern.sum(axis=-1)
+        s.shape += (1,)
+        out = kern / s
+    out[np.isnan(out)] = 1.0
+    return out
+
+
+def interp_eq_matrix(nodes, bary):
+    """GLL coefficients -> values at equispaced points
+    (sem/basis_functions.py:221-223)."""
+    return lagrange_eval(nodes, bary, np.linspace(-1, 1, nodes.size))
+
+
+class Basis(object):
+    """The tables one order needs."""
+
+    def __init__(self, order):
+        self.order = order
+        self.N = order + 1
+        self.nodes, self.bary, self.w = gll(order)
+        self.D = diff_matrix(self.nodes, self.bary)
+        self.E = interp_eq_matrix(self.nodes, self.bary)
+        self.E_lu = sla.lu_factor(self.E)
+
+
+def hier_order(N):
+    """Hierarchical local node order of an N x N quadrilateral: 4 vertices,
+    edges xi0=-1, xi0=+1, xi1=-1, xi1=+1 (open), interior
+    (sem/geometry.py:151-212)."""
+    lin = np.arange(N * N).reshape(N, N)
+    parts = [[lin[0, 0]], [lin[0, -1]], [lin[-1, 0]], [lin[-1, -1]],
+             lin[0, 1:-1], lin[-1, 1:-1], lin[1:-1, 0], lin[1:-1, -1],
+             lin[1:-1, 1:-1].ravel()]
+    return np.concatenate([np.asarray(p).ravel() for p in parts]).astype(np.uint32)
+
+
+# --------------------------------------------------------------------------
+# synthetic meshes (tests/test_discrete.py:22-38 pattern)
+# --------------------------------------------------------------------------
+def mesh_nodes(kind, nx, ny, p):
+    NX, NY = nx * p + 1, ny * p + 1
+    X, Y = np.meshgrid(np.linspace(-1, 1, NX), np.linspace(-1, 1, NY), indexing="ij")
+    if kind == "C":
+        s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
+        X = X + s
+        Y = Y + s
+    return np.vstack([X.ravel(), Y.ravel()])
+
+
+def mesh_l2g(nx, ny, p):
+    """uint32[E, N, N]; cell (ex, ey) at index ex*ny+ey; node id = i*NY + j."""
+    NX, NY = nx * p + 1, ny * p + 1
+    gid = np.arange(NX * NY).reshape(NX, NY)
+    return np.stack([gid[ex * p:ex * p + p + 1, ey * p:ey * p + p + 1]
+                     for ex in range(nx) for ey in range(ny)]).astype(np.uint32)
+
+
+def mesh_boundary_faces(nx, ny):
+    """{'ebc': [(cell, face)...], 'nbc': [...]}: ebc = left (face 0) + bottom
+    (face 2), nbc = right (1) + top (3); per cell in the order 0, 2, 1, 3."""
+    out = {"ebc": [], "nbc": []}
+    for ex in range(nx):
+        for ey in range(ny):
+            c = ex * ny + ey
+            if ex == 0:
+                out["ebc"].append((c, 0))
+            if ey == 0:
+                out["ebc"].append((c, 2))
+            if ex == nx - 1:
+                out["nbc"].append((c, 1))
+            if ey == ny - 1:
+                out["nbc"].append((c, 3))
+    return out
+
+
+def face_nodes(cell_map, face):
+    """Counter-clockwise node ids of a face of a 2-D cell map
+    (sem/mapping.py:19-76 specialised to ndim=2)."""
+    if face == 0:
+        return cell_map[..., 0, ::-1]
+    if face == 1:
+        return cell_map[..., -1, :]
+    if face == 2:
+        return cell_map[..., :, 0]
+    return cell_map[..., ::-1, -1]
+
+
+def permute_nodes(nodes, l2g, perm):
+    """Mesh._permute_nodes (sem/discrete.py:1115-1127): new node k = old
+    perm[k]; returns the new (nodes, l2g)."""
+    nodes = nodes.copy()
+    nodes[:, :perm.size] = nodes[:, perm]
+    inv = np.zeros_like(perm)
+    inv[perm] = np.arange(perm.size)
+    return nodes, inv[l2g].astype(np.uint32)
+
+
+def static_condensation(nodes, l2g):
+    """Exterior-first ordering (sem/discrete.py:314-359).  Returns
+    (nodes, l2g, n_exterior)."""
+    E, N = l2g.shape[0], l2g.shape[1]
+    h = hier_order(N)
+    n_ext = N * N - (N - 2) ** 2
+    flat = l2g.reshape(E, -1)
+    ext = np.unique(flat[:, h[:n_ext]].astype(int))
+    itr = np.sort(flat[:, h[n_ext:]].astype(int).ravel())
+    perm = np.concatenate((ext, itr))
+    assert perm.size == nodes.shape[1]
+    nodes, l2g = permute_nodes(nodes, l2g, perm)
+    return nodes, l2g, ext.size
+
+
+def _graph(idsets, size):
+    rows = np.concatenate([np.repeat(ids, ids.shape[1], axis=1).ravel() for ids in idsets])
+    cols = np.concatenate([np.tile(ids, (1, ids.shape[1])).ravel() for ids in idsets])
+    g = sparse.coo_matrix((np.ones(rows.size, dtype=bool), (rows, cols)), (size, size))
+    return g.tocsr()
+
+
+def rcm_all(nodes, l2g):
+    """DOFManager._reorder_nodes_rcm (sem/discrete.py:142-178)."""
+    E = l2g.shape[0]
+    g = _graph([l2g.reshape(E, -1)], nodes.shape[1])
+    perm = csgraph.reverse_cuthill_mckee(g, True)
+    return permute_nodes(nodes, l2g, perm)
+
+
+def rcm_exterior(nodes, l2g, n_ext):
+    """DOFManagerSC._reorder_nodes_rcm (sem/discrete.py:361-402): RCM over the
+    exterior nodes, interior identity."""
+    E, N = l2g.shape[0], l2g.shape[1]
+    h = hier_order(N)
+    k = N * N - (N - 2) ** 2
+    g = _graph([l2g.reshape(E, -1)[:, h[:k]]], n_ext)
+    n = nodes.shape[1]
+    perm = np.empty(n, np.uint32)
+    perm[:n_ext] = csgraph.reverse_cuthill_mckee(g, True)
+    perm[n_ext:] = np.arange(n_ext, n)
+    return permute_nodes(nodes, l2g, perm)
+
+
+def build_case(kind, nx, ny, p, sc, rcm):
+    """nodes, l2g after the manager's renumbering (DOFManager /
+    DOFManagerSC with rcm_order)."""
+    nodes, l2g = mesh_nodes(kind, nx, ny, p), mesh_l2g(nx, ny, p)
+    if sc:
+        nodes, l2g, n_ext = static_condensation(nodes, l2g)
+        if rcm:
+            nodes, l2g = rcm_exterior(nodes, l2g, n_ext)
+    elif rcm:
+        nodes, l2g = rcm_all(nodes, l2g)
+    return nodes, l2g
+
+
+# --------------------------------------------------------------------------
+# geometry and the local operator
+# --------------------------------------------------------------------------
+def geometry(basis, nodes, l2g):
+    """x_phys [E,2,N,N], J, invJ [E,2,2,N,N], detJ, JxW [E,N,N].
+
+    x_phys: LU solves with E along axis 0 then axis 1
+    (sem/mapping.py:98-103, sem/basis_functions.py:599-624);
+    J[i,a] = d x_i/d xi_a (sem/mapping.py:113, sem/basis_functions.py:626-650);
+    det/inv closed form with inv *= 1/det (sem/linalg.py:105-115);
+    JxW = (detJ*w_m)*w_n (sem/quadratures.py:268-275)."""
+    E, N = l2g.shape[0], basis.N
+    X = nodes[:, l2g]                                   # [2, E, N, N]
+    X = np.moveaxis(X, 1, 0).copy()                     # [E, 2, N, N]
+    # axis 0 solve
+    a = np.moveaxis(X, 2, 0).reshape(N, -1)
+    a = sla.lu_solve(basis.E_lu, a).reshape(N, E, 2, N)
+    a = np.moveaxis(a, 0, 2)                            # [E, 2, N, N]
+    # axis 1 solve
+    b = np.moveaxis(a, 3, 0).reshape(N, -1)
+    b = sla.lu_solve(basis.E_lu, b).reshape(N, E, 2, N)
+    xph = np.ascontiguousarray(np.moveaxis(b, 0, 3))    # [E, 2, N, N]
+    d0 = np.einsum("mr,eirn->eimn", basis.D, xph)       # d/dxi0
+    d1 = np.einsum("ns,eims->eimn", basis.D, xph)       # d/dxi1
+    J = np.stack([d0, d1], axis=2)                      # [E, i, a, N, N]
+    det = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+    assert np.all(det > 0)                              # sem/mapping.py:117
+    inv = np.empty_like(J)
+    inv[:, 0, 0] = J[:, 1, 1]
+    inv[:, 0, 1] = -J[:, 0, 1]
+    inv[:, 1, 0] = -J[:, 1, 0]
+    inv[:, 1, 1] = J[:, 0, 0]
+    inv *= (1 / det)[:, None, None]
+    JxW = det.copy()
+    JxW *= basis.w[:, None]
+    JxW *= basis.w[None, :]
+    return dict(x_phys=xph, J=J, invJ=inv, detJ=det, JxW=JxW)
+
+
+def local_stiffness(basis, invJ, JxW):
+    """Dense local stiffness L[E,p,q,r,s] by the reference's four einsums
+    (examples/poisson.py:166-193), batched over elements."""
+    D, N = basis.D, basis.N
+    g0 = np.einsum("mp,eimn->eimnp", D, invJ[:, 0])     # gradh_xi0
+    g1 = np.einsum("nq,eimn->eimnq", D, invJ[:, 1])     # gradh_xi1
+    E = invJ.shape[0]
+    L = np.zeros((E, N, N, N, N))
+    p, q, r = np.ogrid[0:N, 0:N, 0:N]
+    L[:, p, q, r, q] += np.einsum("emn,eimnp,eimnr->epnr", JxW, g0, g0)
+    L += np.einsum("emn,eimnp,eimns->epnms", JxW, g0, g1)
+    L += np.einsum("emn,eimnq,eimnr->emqrn", JxW, g1, g0)
+    L[:, p, q, p, r] += np.einsum("emn,eimnq,eimns->emqs", JxW, g1, g1)
+    return L
+
+
+def apply_dense_local(L, l2g, u):
+    """y[L2G] += einsum('pqrs,rs', L_e, u[L2G]) element by element
+    (examples/squirmer-axisymmetric.py:268-270,284-295 + the scatter of
+    sem/discrete.py:499)."""
+    y = np.zeros_like(u)
+    for e in range(l2g.shape[0]):
+        idx = l2g[e]
+        y[idx] += np.einsum("pqrs,rs", L[e], u[idx])
+    return y
+
+
+def apply_dense_batched(L, l2g, u):
+    """Same contraction, batched (used where the Python loop is too slow)."""
+    yl = np.einsum("epqrs,ers->epq", L, u[l2g])
+    y = np.zeros_like(u)
+    np.add.at(y, l2g.ravel(), yl.ravel())
+    return y
+
+
+def assemble_csr(L, l2g, n):
+    """COO of all local blocks -> CSR with duplicates summed
+    (sem/discrete.py:491-499,507 applied to the full local matrices)."""
+    E, N = l2g.shape[0], l2g.shape[1]
+    ids = l2g.reshape(E, -1).astype(np.int64)
+    nn = N * N
+    rows = np.repeat(ids, nn, axis=1).ravel()
+    cols = np.tile(ids, (1, nn)).ravel()
+    return sparse.coo_matrix((L.reshape(-1), (rows, cols)), shape=(n, n)).tocsr()
+
+
+def assemble_vector(loc, l2g, n):
+    out = np.zeros(n)
+    np.add.at(out, l2g.ravel(), loc.ravel())
+    return out
+
+
+def local_diagonal(L):
+    return np.einsum("epqpq->epq", L)
+
+
+def dirichlet_data(nodes_unused, l2g, x_phys, faces):
+    """on_ebc mask and u = 0.2((x+1)+(y+1)) at the GLL points of the 'ebc'
+    faces (examples/poisson.py:125-143 via boundary_elements,
+    sem/discrete.py:211-219,702-705)."""
+    n = int(l2g.max()) + 1
+    on = np.zeros(n, dtype=bool)
+    vals = np.zeros(n)
+    for c, f in sorted(faces["ebc"], key=lambda cf: cf[0]):
+        loc = face_nodes(l2g[c], f)
+        x = face_nodes(x_phys[c, 0], f)
+        y = face_nodes(x_phys[c, 1], f)
+        vals[loc] = 0.2 * ((x + 1) + (y + 1))
+        on[loc] = True
+    return on, vals
+
+
+def solve_direct(A, b, on_ebc, vals):
+    """Essential-BC elimination + sparse direct solve on the full assembled
+    matrix (the operations of sem/discrete.py:505-511)."""
+    free = ~on_ebc
+    sol = vals.copy()
+    Af = A[free]
+    rhs = b[free] - Af[:, on_ebc] @ vals[on_ebc]
+    sol[free] = spsolve(Af[:, free].tocsc(), rhs)
+    return sol
+
+
+def solve_schur(L, JxW, l2g, n_ext, on_ebc, vals):
+    """The reference's actual solver: hierarchical reorder, local Schur
+    complements, COO assembly over exterior DOFs, eliminate essential BCs,
+    spsolve, interior back-substitution (sem/discrete.py:404-528).  Requires
+    the exterior-first numbering (DOFManagerSC)."""
+    E, N = l2g.shape[0], l2g.shape[1]
+    nn = N * N
+    h = hier_order(N).astype(np.int64)
+    ne = nn - (N - 2) ** 2
+    Lm = L.reshape(E, nn, nn)[:, h][:, :, h]            # reorder_local_system_hier
+    rh = JxW.reshape(E, nn)[:, h]
+    gid = l2g.reshape(E, nn).astype(np.int64)[:, h]
+    Aee, Aei = Lm[:, :ne, :ne], Lm[:, :ne, ne:]
+    Aie, Aii = Lm[:, ne:, :ne], Lm[:, ne:, ne:]
+    X = np.swapaxes(np.linalg.solve(np.swapaxes(Aii, 1, 2), np.swapaxes(Aei, 1, 2)), 1, 2)
+    S = Aee - X @ Aie
+    g = rh[:, :ne] - np.einsum("eij,ej->ei", X, rh[:, ne:])
+    ids = gid[:, :ne]
+    rows = np.repeat(ids, ne, axis=1).ravel()
+    cols = np.tile(ids, (1, ne)).ravel()
+    Sg = sparse.coo_matrix((S.reshape(-1), (rows, cols)), shape=(n_ext, n_ext)).tocsr()
+    grhs = np.zeros(n_ext)
+    np.add.at(grhs, ids.ravel(), g.ravel())
+    sol = vals.copy()
+    ebc = on_ebc[:n_ext]
+    free = ~ebc
+    ext = sol[:n_ext]
+    A1 = Sg[free]
+    r1 = grhs[free] - A1[:, ebc] @ ext[ebc]
+    ext[free] = spsolve(A1[:, free].tocsc(), r1)
+    inner = np.linalg.solve(Aii, (rh[:, ne:] - np.einsum("eij,ej->ei", Aie, sol[ids]))[..., None])
+    sol[gid[:, ne:]] = inner[..., 0]
+    return sol
+
+
+def pcg_jacobi(A, b, x0, rtol, maxiter):
+    """Plain Jacobi-PCG on an assembled SPD matrix (protocol of SURVEY.md
+    8(d): stop on the recursive residual ||r|| <= rtol ||b||).  Checker for
+    the device solver's iteration counts; not part of the reference."""
+    dinv = 1.0 / A.diagonal()
+    x = x0.copy()
+    r = b - A @ x
+    z = dinv * r
+    p = z.copy()
+    rz = r @ z
+    bb = b @ b
+    it = 0
+    while it < maxiter and r @ r > rtol * rtol * bb:
+        Ap = A @ p
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        z = dinv * r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+        it += 1
+    return x, it
+
+
+def run_case(kind, nx, ny, p, sc, rcm, solve=True, python_loop_apply=False):
+    """The oracle's counterpart of oracle/live_reference.run_case."""
+    basis = Basis(p)
+    nodes, l2g = build_case(kind, nx, ny, p, sc, rcm)
+    n = nodes.shape[1]
+    geo = geometry(basis, nodes, l2g)
+    L = local_stiffness(basis, geo["invJ"], geo["JxW"])
+    x, y = nodes
+    u = np.sin(3 * x) * np.cos(2 * y)
+    Au = apply_dense_local(L, l2g, u) if python_loop_apply else apply_dense_batched(L, l2g, u)
+    out = dict(l2g=l2g, nodes=nodes, invJ=geo["invJ"], JxW=geo["JxW"], x_phys=geo["x_phys"],
+               u=u, Au=Au, b=assemble_vector(geo["JxW"], l2g, n),
+               diag=assemble_vector(local_diagonal(L), l2g, n), L=L)
+    on, vals = dirichlet_data(nodes, l2g, geo["x_phys"], mesh_boundary_faces(nx, ny))
+    out["on_ebc"], out["ebc_vals"] = on, vals
+    if solve:
+        if sc:
+            n_ext = int(np.unique(l2g.reshape(l2g.shape[0], -1)[
+                :, hier_order(basis.N)[:basis.N ** 2 - (basis.N - 2) ** 2]]).size)
+            out["solution"] = solve_schur(L, geo["JxW"], l2g, n_ext, on, vals)
+        else:
+            A = assemble_csr(L, l2g, n)
+            out["solution"] = solve_direct(A, out["b"], on, vals)
+    return out

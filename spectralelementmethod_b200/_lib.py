@@ -54,7 +54,7 @@ class semk_op(C.Structure):
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
         ("shared_slot", C.c_void_p),
-        ("partials", C.c_void_p), ("D_host", C.c_void_p),
+        ("partials", C.c_void_p), ("D_host", C.c_void_p), ("dirichlet", C.c_void_p),
     ]
 
 
@@ -85,7 +85,7 @@ SIGNATURES = {
     "semk_poisson_local_diag_f64": (_I, [C.POINTER(semk_op), _P, _P]),
     "semk_weighted_local_f64": (_I, [_I, _L, _L, _P, _P, _P, _P, _P, _P]),
     "semk_vec_partials_len": (_L, [_L]),
-    "semk_pcg_init_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "semk_pcg_init_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "semk_pcg_update_xr_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "semk_pcg_update_p_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
     "semk_dot_f64": (_I, [_L, _P, _P, _P, _P, _P]),

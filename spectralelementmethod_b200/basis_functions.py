@@ -202,7 +202,7 @@ class BarycentricLagrange(_Basis1D, _Nodal):
         pts, which = hit[:-1], hit[-1]
         if which.size > 0:
             if x.ndim == 0:
-                out[:] = f[..., which[0]]
+                out[...] = f[..., which[0]]
             elif broadcast:
                 out[pts] = f[pts + (Ellipsis, which)]
             else:

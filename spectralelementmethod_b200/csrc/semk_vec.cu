@@ -64,13 +64,15 @@ __device__ __forceinline__ bool finish_reduction(double (&v)[NV], double *partia
 __global__ void __launch_bounds__(kVecThreads)
     pcg_init_kernel(int64_t n, int64_t n_dot, const double *__restrict__ b,
                     const double *__restrict__ Ax, const double *__restrict__ dinv,
-                    double *__restrict__ r, double *__restrict__ p, double *__restrict__ sc,
+                    const uint8_t *__restrict__ dirichlet, double *__restrict__ r,
+                    double *__restrict__ p, double *__restrict__ sc,
                     double *__restrict__ partials) {
   double acc[3] = {0.0, 0.0, 0.0};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const double bi = b[i];
-    const double ri = bi - Ax[i];
+    const bool fixed = dirichlet && dirichlet[i];
+    const double bi = fixed ? 0.0 : b[i];
+    const double ri = fixed ? 0.0 : bi - Ax[i];
     const double zi = dinv[i] * ri;
     r[i] = ri;
     p[i] = zi;
@@ -169,12 +171,12 @@ extern "C" int64_t semk_vec_partials_len(int64_t n) {
 }
 
 extern "C" int semk_pcg_init_f64(int64_t n, int64_t n_dot, const double *b, const double *Ax,
-                                 const double *dinv, double *r, double *p, double *sc,
-                                 double *partials, void *stream) {
+                                 const double *dinv, const uint8_t *dirichlet, double *r,
+                                 double *p, double *sc, double *partials, void *stream) {
   SEMK_REQUIRE(n > 0 && n_dot >= 0 && n_dot <= n, "semk_pcg_init_f64: bad sizes");
   SEMK_REQUIRE(b && Ax && dinv && r && p && sc && partials, "semk_pcg_init_f64: null pointer");
-  pcg_init_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(n, n_dot, b, Ax, dinv, r,
-                                                                         p, sc, partials);
+  pcg_init_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(
+      n, n_dot, b, Ax, dinv, dirichlet, r, p, sc, partials);
   SEMK_LAUNCH_CHECK("pcg_init_kernel");
   return SEMK_OK;
 }
@@ -233,7 +235,7 @@ extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
 
   int rc = semk_poisson_apply_f64(op, x, Ap, flags, nullptr, st);
   if (rc != SEMK_OK) return rc;
-  rc = semk_pcg_init_f64(n, n, b, Ap, dinv, r, p, sc, vec_partials, st);
+  rc = semk_pcg_init_f64(n, n, b, Ap, dinv, op->dirichlet, r, p, sc, vec_partials, st);
   if (rc != SEMK_OK) return rc;
 
   auto poll = [&]() -> int {

@@ -1,0 +1,277 @@
+"""Element-partitioned multi-GPU execution (one process per GPU, NCCL).
+
+The reference is single-process; the only coupling between
+elements is the scatter-add over shared nodes (sem/discrete.py:499) and, in a
+Krylov solver, the inner products.  A structured mesh is cut into vertical
+strips of whole element columns, one per rank:
+
+    rank r owns element columns [r*nx_local, (r+1)*nx_local)
+
+Each rank builds an ordinary local mesh of its strip with the natural local
+numbering (node id = i_local*NY + j).  The node column shared with the left
+neighbour is ids [0, NY), the one shared with the right neighbour is ids
+[n - NY, n) -- both contiguous, so the interface exchange needs no pack
+kernels.  The right neighbour owns a shared column: rank r's owned nodes are
+the prefix [0, n_owned), n_owned = n - NY (n on the last rank), which is what
+the PCG kernels' ``n_dot`` argument expects.
+
+Per operator apply: one local apply (partial sums on the interface columns),
+one neighbour exchange (<= 2 messages of NY doubles each way), two adds.
+p.Ap is taken on the *partial* sums before the exchange: summed over ranks it
+equals the global p.Ap exactly, so it rides on the same all-reduce.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["StripPartition", "DistributedOperator", "distributed_pcg"]
+
+
+class StripPartition(object):
+    """Description of one rank's strip of a global (nx_local*world) x ny mesh."""
+
+    def __init__(self, rank, world, nx_local, ny, p, bounds=(-1.0, 1.0, -1.0, 1.0)):
+        if not (0 <= rank < world):
+            raise ValueError("rank out of range")
+        self.rank, self.world = int(rank), int(world)
+        self.nx_local, self.ny, self.p = int(nx_local), int(ny), int(p)
+        self.nx_global = self.nx_local * self.world
+        self.NY = self.ny * self.p + 1
+        self.NX_local = self.nx_local * self.p + 1
+        self.n_local = self.NX_local * self.NY
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
+        self.n_owned = self.n_local - (self.NY if self.right is not None else 0)
+        x0, x1, y0, y1 = bounds
+        w = (x1 - x0) / self.world
+        self.bounds_global = bounds
+        self.bounds_local = (x0 + rank * w, x0 + (rank + 1) * w, y0, y1)
+        self.n_global = (self.nx_global * self.p + 1) * self.NY
+
+    # contiguous id ranges of the two interface columns
+    @property
+    def left_slice(self):
+        return slice(0, self.NY)
+
+    @property
+    def right_slice(self):
+        return slice(self.n_local - self.NY, self.n_local)
+
+    def global_ids(self):
+        """Global lattice id of every local node (global id = i*NY + j)."""
+        i0 = self.rank * self.nx_local * self.p
+        return (np.arange(self.n_local, dtype=np.int64) + i0 * self.NY)
+
+    def local_coordinates(self, kind="S"):
+        """Coordinates of the local lattice, cut from the global lattice so
+        that shared columns are bit-identical on both ranks."""
+        x0, x1, y0, y1 = self.bounds_global
+        gx = np.linspace(x0, x1, self.nx_global * self.p + 1)
+        i0 = self.rank * self.nx_local * self.p
+        X, Y = np.meshgrid(gx[i0:i0 + self.NX_local], np.linspace(y0, y1, self.NY), indexing="ij")
+        if kind == "C":
+            s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
+            X, Y = X + s, Y + s
+        elif kind != "S":
+            raise ValueError("kind must be 'S' or 'C'")
+        return np.vstack([X.ravel(), Y.ravel()])
+
+    def build_local_mesh(self, kind="S"):
+        """Local Mesh with the global problem's boundaries: 'ebc' = global
+        left edge (rank 0 only) + bottom, 'nbc' = global right edge (last rank
+        only) + top."""
+        from . import meshgen
+        from .discrete import Mesh
+        from .geometry import Quadrilateral
+        nx, ny, p = self.nx_local, self.ny, self.p
+        mesh = Mesh(2)
+        mesh.set_nodes(self.local_coordinates(kind))
+        g = mesh.add_geometry(Quadrilateral(p + 1, p + 1))
+        r = mesh.new_region("interior")
+        ebc, nbc = mesh.new_boundary("ebc"), mesh.new_boundary("nbc")
+        mesh.add_cells(meshgen.structured_node_maps(nx, ny, p), g, r)
+        cell = np.arange(nx * ny).reshape(nx, ny)
+        if self.left is None:
+            mesh.add_boundary_cells(cell[0, :], ebc, 1, 0)
+        mesh.add_boundary_cells(cell[:, 0], ebc, 1, 2)
+        if self.right is None:
+            mesh.add_boundary_cells(cell[-1, :], nbc, 1, 1)
+        mesh.add_boundary_cells(cell[:, -1], nbc, 1, 3)
+        mesh._structured_shape = (nx, ny)
+        return mesh
+
+
+class DistributedOperator(object):
+    """Global operator = local operators + interface exchange.
+
+    local_apply(u, out, dot_out) -> out : the rank-local operator *without*
+        Dirichlet identity rows on interface nodes resolved (partial sums on
+        the interface columns).  In production this is
+        ``PoissonOperator.apply``; the CPU tests inject an oracle-based one.
+    dirichlet : bool tensor [n_local] or None -- identity rows are re-imposed
+        on the interface columns after the exchange (each side wrote u there,
+        the sum would double it).
+    """
+
+    def __init__(self, part, local_apply, dirichlet=None, group=None, device=None):
+        self.part = part
+        self.local_apply = local_apply
+        self.group = group
+        self.device = device
+        NY = part.NY
+        kw = dict(dtype=torch.float64, device=device)
+        self._recv_left = torch.empty(NY, **kw) if part.left is not None else None
+        self._recv_right = torch.empty(NY, **kw) if part.right is not None else None
+        self._fix_ids = None
+        if dirichlet is not None:
+            d = torch.as_tensor(dirichlet).to("cpu").bool()
+            ids = []
+            if part.left is not None:
+                ids.append(torch.nonzero(d[part.left_slice]).ravel())
+            if part.right is not None:
+                ids.append(torch.nonzero(d[part.right_slice]).ravel() + (part.n_local - NY))
+            if ids:
+                ids = torch.cat(ids)
+                if ids.numel():
+                    self._fix_ids = ids.to(device)
+
+    def exchange_add(self, y):
+        """Sum the interface columns of y across neighbouring ranks, in place."""
+        part = self.part
+        ops = []
+        if part.left is not None:
+            ops.append(dist.P2POp(dist.isend, y[part.left_slice], part.left, self.group))
+            ops.append(dist.P2POp(dist.irecv, self._recv_left, part.left, self.group))
+        if part.right is not None:
+            ops.append(dist.P2POp(dist.isend, y[part.right_slice], part.right, self.group))
+            ops.append(dist.P2POp(dist.irecv, self._recv_right, part.right, self.group))
+        if not ops:
+            return y
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if part.left is not None:
+            y[part.left_slice] += self._recv_left
+        if part.right is not None:
+            y[part.right_slice] += self._recv_right
+        return y
+
+    def apply(self, u, out=None, dot_out=None):
+        """y = A_global u on this rank's nodes.  ``dot_out`` (1-element
+        tensor) receives this rank's share of u.y; all-reduce it for the
+        global value."""
+        y = self.local_apply(u, out, dot_out)
+        self.exchange_add(y)
+        if self._fix_ids is not None:
+            y[self._fix_ids] = u[self._fix_ids]
+        return y
+
+    def owned_dot(self, a, b):
+        n = self.part.n_owned
+        s = torch.dot(a[:n], b[:n]).reshape(1)
+        dist.all_reduce(s, group=self.group)
+        return s
+
+
+def distributed_pcg(dop, b, x, dinv, kernels, rtol=1e-12, maxiter=200000, check_every=25):
+    """Jacobi-PCG over all ranks with device-resident scalars.
+
+    kernels: object with init(b, Ax, dinv, r, p, sc, n_dot), update_xr(p, Ap,
+    dinv, x, r, sc, n_dot), update_p(r, dinv, p, sc) -- the C-ABI vector
+    kernels (operators.PCGKernels) or a CPU stand-in in the tests.  Two
+    all-reduces per iteration (p.Ap; [r.z, r.r]); the host polls the scalars
+    every ``check_every`` iterations.  Returns (iterations, rel_residual,
+    converged)."""
+    part = dop.part
+    n_dot = part.n_owned
+    r, p, Ap = torch.empty_like(b), torch.empty_like(b), torch.empty_like(b)
+    sc = torch.zeros(8, dtype=torch.float64, device=b.device)
+    dop.apply(x, out=Ap)
+    kernels.init(b, Ap, dinv, r, p, sc, n_dot)
+    dist.all_reduce(sc[0:5], group=dop.group)
+    sc[2] = sc[0]
+    h = sc.cpu()
+    bb = float(h[4])
+    tol2 = rtol * rtol
+    if bb == 0.0 or float(h[3]) <= tol2 * bb:
+        return 0, (float(h[3]) / bb) ** 0.5 if bb > 0 else 0.0, True
+    it = 0
+    while it < maxiter:
+        for _ in range(min(check_every, maxiter - it)):
+            dop.apply(p, out=Ap, dot_out=sc[1:2])
+            dist.all_reduce(sc[1:2], group=dop.group)
+            kernels.update_xr(p, Ap, dinv, x, r, sc, n_dot)
+            dist.all_reduce(sc[2:4], group=dop.group)
+            kernels.update_p(r, dinv, p, sc)
+            it += 1
+        h = sc.cpu()
+        if float(h[7]) != 0.0:
+            from ._lib import SolverFailure
+            raise SolverFailure("distributed PCG breakdown (p.Ap <= 0 or non-finite)")
+        if float(h[3]) <= tol2 * bb:
+            return it, (float(h[3]) / bb) ** 0.5, True
+    return it, (float(h[3]) / bb) ** 0.5, False
+
+
+class DistributedPoisson(object):
+    """The whole multi-GPU Poisson path for the strip-partitioned structured
+    configurations (BASELINE.json configs[4]): local mesh + DOF manager +
+    device operator on each rank, interface exchange, global Jacobi-PCG."""
+
+    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None):
+        from . import discrete
+        from .basis_functions import LagrangeGaussLobatto, TensorProductQS
+        from .operators import PCGKernels
+        self.part = part
+        self.group = group
+        self.mesh = part.build_local_mesh(kind)
+        b1 = LagrangeGaussLobatto(order)
+        self.mngr = discrete.DOFManager(self.mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        self.on_ebc = self.mngr.boundary_node_mask("ebc")
+        self.op = self.mngr.poisson_operator(dirichlet=self.on_ebc, elems_per_patch=elems_per_patch)
+        self.kernels = PCGKernels(self.op)
+        op = self.op
+        self.dop = DistributedOperator(
+            part, lambda u, out, dot: op.apply(u, out=out, dot_out=dot),
+            dirichlet=self.on_ebc if op.has_dirichlet else None, group=group, device=op.dev)
+        self._mask = op.dirichlet_dev.bool() if op.has_dirichlet else None
+        self._dinv = None
+
+    def apply(self, u, out=None, dot_out=None):
+        return self.dop.apply(u, out=out, dot_out=dot_out)
+
+    def diagonal(self):
+        d = self.op.diagonal(masked=False)
+        self.dop.exchange_add(d)
+        if self._mask is not None:
+            d[self._mask] = 1.0
+        return d
+
+    def rhs(self, f=1.0):
+        return self.dop.exchange_add(self.op.rhs(f))
+
+    def lift(self, b, g=None):
+        """b_f - A_fe g on free rows, g on Dirichlet rows (global operator)."""
+        if self._mask is None:
+            return b.clone()
+        gv = torch.zeros_like(b)
+        if g is not None:
+            gv[self._mask] = g[self._mask]
+        from ._lib import MASK_OUT
+        t = self.op.apply(gv, flags=MASK_OUT)
+        self.dop.exchange_add(t)
+        out = b - t
+        out[self._mask] = gv[self._mask]
+        return out
+
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
+        if x0 is None:
+            x = torch.zeros_like(b)
+            if self._mask is not None:
+                x[self._mask] = b[self._mask]
+        else:
+            x = x0.clone()
+        if self._dinv is None:
+            self._dinv = 1.0 / self.diagonal()
+        it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
+                                      maxiter=maxiter, check_every=check_every)
+        return x, it, rel, ok

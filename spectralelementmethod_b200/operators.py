@@ -212,6 +212,7 @@ class PoissonOperator(object):
         op.shared_slot = t[_lib.PA_SHARED_SLOT].data_ptr() if self.n_shared else None
         op.partials = self.partials.data_ptr()
         op.D_host = self.tab.D_host.ctypes.data
+        op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None
         self._op = op
         self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
         self._dinv = None
@@ -399,3 +400,37 @@ class PoissonOperator(object):
             c[np.abs(c) <= tol] = 0.0
             cols.append(sparse.csc_matrix(c.reshape(-1, 1)))
         return sparse.hstack(cols).tocsr()
+
+
+class PCGKernels(object):
+    """The C-ABI vector kernels of Jacobi-PCG bound to one operator's scratch
+    (used by distributed.distributed_pcg, where the loop is driven from Python
+    so that NCCL all-reduces can sit between the kernels)."""
+
+    def __init__(self, op):
+        self.op = op
+        self._lib = op._lib
+        self.n = op.n_nodes
+
+    def init(self, b, Ax, dinv, r, p, sc, n_dot):
+        _lib.check(self._lib.semk_pcg_init_f64(
+            self.n, int(n_dot), device.ptr(b), device.ptr(Ax), device.ptr(dinv),
+            device.ptr(self.op.dirichlet_dev if self.op.has_dirichlet else None),
+            device.ptr(r), device.ptr(p), device.ptr(sc), device.ptr(self.op.vec_partials),
+            device.stream_ptr()))
+
+    def update_xr(self, p, Ap, dinv, x, r, sc, n_dot):
+        _lib.check(self._lib.semk_pcg_update_xr_f64(
+            self.n, int(n_dot), device.ptr(p), device.ptr(Ap), device.ptr(dinv), device.ptr(x),
+            device.ptr(r), device.ptr(sc), device.ptr(self.op.vec_partials), device.stream_ptr()))
+
+    def update_p(self, r, dinv, p, sc):
+        _lib.check(self._lib.semk_pcg_update_p_f64(
+            self.n, device.ptr(r), device.ptr(dinv), device.ptr(p), device.ptr(sc),
+            device.ptr(self.op.vec_partials), device.stream_ptr()))
+
+    def dot(self, a, b, out):
+        _lib.check(self._lib.semk_dot_f64(
+            int(a.numel()), device.ptr(a), device.ptr(b), device.ptr(out),
+            device.ptr(self.op.vec_partials), device.stream_ptr()))
+        return out

@@ -1,0 +1,197 @@
+"""The C-ABI shared library: loads, exports every symbol include/semk.h
+declares, and its host-side plan builder (pure C++, no GPU) produces
+consistent tables.  No compute kernels are launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from spectralelementmethod_b200 import _lib, meshgen, operators
+
+HEADER = os.path.join(ROOT, "include", "semk.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(semk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libsemk.so does not export %s" % n
+    # ... and the ctypes binding covers exactly the declared API
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_channel():
+    lib = _lib.load()
+    assert lib.semk_version() == 100
+    out = ctypes.c_void_p()
+    rc = lib.semk_hostplan_create(1, 1, 1, None, None, 16, None, ctypes.byref(out))
+    assert rc == _lib.ERR_UNSUPPORTED and b"n1" in lib.semk_last_error()
+    with pytest.raises(NotImplementedError):
+        _lib.check(rc)
+    assert lib.semk_device_available() in (0, 1)
+
+
+def test_struct_layout_matches_header():
+    # 24 fields; 8-byte aligned pointers after two int32 pairs
+    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 6 * 8 + 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.semk_pcg_info) == 24
+
+
+def _plan(nx, ny, p, pe, order=None, dirichlet=None):
+    N = p + 1
+    l2g = meshgen.structured_node_maps(nx, ny, p)
+    n_nodes = (nx * p + 1) * (ny * p + 1)
+    sc, ar = _lib.hostplan(N, l2g, n_nodes, order, pe, dirichlet)
+    return l2g.reshape(-1, N * N), n_nodes, sc, ar
+
+
+def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
+    NN = l2g.shape[1]
+    E = l2g.shape[0]
+    n_patch = sc[_lib.PS_N_PATCH]
+    assert n_patch == -(-E // pe) and sc[_lib.PS_N_SLOT_ELEMS] == n_patch * pe
+    ptr = ar[_lib.PA_PATCH_NODE_PTR]
+    pnode = ar[_lib.PA_PNODE]
+    npriv = ar[_lib.PA_PATCH_NPRIV]
+    base = ar[_lib.PA_PATCH_SLOT_BASE]
+    eloc = ar[_lib.PA_ELOC].reshape(-1, NN)
+    color = ar[_lib.PA_ELEM_COLOR]
+    eos = ar[_lib.PA_ELEM_OF_SLOT]
+    assert sorted(eos.tolist()) == list(range(E))
+    ids = pnode & _lib.NODE_ID_MASK
+    shared_flag = (pnode & _lib.NODE_SHARED) != 0
+    dir_flag = (pnode & _lib.NODE_DIRICHLET) != 0
+    if dirichlet is not None:
+        assert np.array_equal(dir_flag, dirichlet[ids].astype(bool))
+    else:
+        assert not dir_flag.any()
+    touched = np.zeros(n_nodes, dtype=int)
+    slots_seen = 0
+    for p in range(n_patch):
+        a, b = ptr[p], ptr[p + 1]
+        loc_ids = ids[a:b]
+        assert len(set(loc_ids.tolist())) == b - a
+        assert not shared_flag[a:a + npriv[p]].any() and shared_flag[a + npriv[p]:b].all()
+        assert np.all(np.diff(loc_ids[:npriv[p]]) > 0) and np.all(np.diff(loc_ids[npriv[p]:]) > 0)
+        assert base[p] == slots_seen
+        slots_seen += (b - a) - npriv[p]
+        touched[loc_ids] += 1
+        s0, s1 = p * pe, min((p + 1) * pe, E)
+        # eloc reproduces the L2G rows of the patch's elements
+        assert np.array_equal(loc_ids[eloc[s0:s1].astype(int)], l2g[eos[s0:s1]])
+        # colouring: elements of one colour share no node
+        for c in set(color[s0:s1].tolist()):
+            sel = [s for s in range(s0, s1) if color[s] == c]
+            allnodes = np.concatenate([eloc[s] for s in sel])
+            assert len(set(allnodes.tolist())) == allnodes.size
+        assert np.all(color[s1:(p + 1) * pe] == 255)
+        assert (b - a) <= sc[_lib.PS_MAX_PATCH_NODES]
+    assert color[color != 255].max() + 1 == sc[_lib.PS_MAX_COLORS]
+    assert slots_seen == sc[_lib.PS_N_SLOTS]
+    # private <=> touched by exactly one patch
+    is_shared_node = np.zeros(n_nodes, dtype=bool)
+    is_shared_node[ids[shared_flag]] = True
+    assert np.array_equal(is_shared_node, touched > 1)
+    # CSR of interface slots: every slot exactly once, grouped under its node
+    sn = ar[_lib.PA_SHARED_NODE]
+    sp = ar[_lib.PA_SHARED_PTR]
+    ss = ar[_lib.PA_SHARED_SLOT]
+    assert sc[_lib.PS_N_SHARED] == sn.size == is_shared_node.sum()
+    assert np.all(np.diff((sn & _lib.NODE_ID_MASK).astype(np.int64)) > 0)
+    assert sp[0] == 0 and sp[-1] == ss.size == slots_seen
+    assert sorted(ss.tolist()) == list(range(slots_seen))
+    slot_node = np.empty(slots_seen, dtype=np.int64)
+    for p in range(n_patch):
+        a, b = ptr[p] + npriv[p], ptr[p + 1]
+        slot_node[base[p]:base[p] + (b - a)] = ids[a:b]
+    for i in range(sn.size):
+        assert np.all(slot_node[ss[sp[i]:sp[i + 1]]] == (sn[i] & _lib.NODE_ID_MASK))
+        assert sp[i + 1] - sp[i] == touched[sn[i] & _lib.NODE_ID_MASK]
+
+
+@pytest.mark.parametrize("nx,ny,p,pe", [(8, 8, 8, 16), (5, 3, 4, 16), (7, 5, 2, 8), (3, 3, 10, 4),
+                                        (1, 1, 3, 16), (6, 6, 1, 4)])
+def test_hostplan_structured(nx, ny, p, pe):
+    from spectralelementmethod_b200.discrete import Mesh
+    mesh = meshgen.structured_quad_mesh(nx, ny, p)
+    order = operators.default_element_order(mesh, pe)
+    rng = np.random.default_rng(0)
+    n_nodes = (nx * p + 1) * (ny * p + 1)
+    dirichlet = (rng.uniform(size=n_nodes) < 0.2).astype(np.uint8)
+    l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, dirichlet)
+    check_plan(l2g, n_nodes, sc, ar, pe, dirichlet)
+    if (nx, ny, p, pe) == (8, 8, 8, 16):
+        assert sc[_lib.PS_N_PATCH] == 4 and sc[_lib.PS_MAX_COLORS] == 4
+        assert sc[_lib.PS_MAX_PATCH_NODES] == 33 * 33 and sc[_lib.PS_N_SHARED] == 129
+
+
+def test_hostplan_scrambled_numbering_and_order():
+    """Arbitrary node numbering (as after RCM) and a random element order."""
+    nx, ny, p, pe = 6, 5, 3, 8
+    l2g = meshgen.structured_node_maps(nx, ny, p)
+    n_nodes = (nx * p + 1) * (ny * p + 1)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(n_nodes).astype(np.uint32)
+    l2g = perm[l2g]
+    order = rng.permutation(nx * ny)
+    sc, ar = _lib.hostplan(p + 1, l2g, n_nodes, order, pe, None)
+    check_plan(l2g.reshape(nx * ny, -1), n_nodes, sc, ar, pe)
+    assert np.array_equal(ar[_lib.PA_ELEM_OF_SLOT], order)
+
+
+def test_hostplan_rejects_bad_input():
+    l2g = meshgen.structured_node_maps(2, 2, 2)
+    with pytest.raises(ValueError):
+        _lib.hostplan(3, l2g, 25, np.array([0, 1, 1, 2]), 4, None)      # not a permutation
+    with pytest.raises(ValueError):
+        _lib.hostplan(3, l2g, 20, None, 4, None)                          # id out of range
+    with pytest.raises(ValueError):
+        _lib.hostplan(3, l2g, 25, None, 4, np.zeros(7, dtype=np.uint8))   # mask length
+    with pytest.raises(NotImplementedError):
+        _lib.hostplan(18, np.zeros((1, 324), dtype=np.uint32), 400, None, 4, None)
+
+
+def test_patch_size_choice_and_smem_budget():
+    for n1 in range(2, 18):
+        pe = operators.choose_elems_per_patch(n1)
+        bx, by = operators._TILES[pe]
+        p = n1 - 1
+        smem = operators.patch_smem_bytes(n1, pe, (bx * p + 1) * (by * p + 1))
+        assert smem <= 227 * 1024
+        assert operators.g_stride_of(n1) % 2 == 0
+    assert operators.choose_elems_per_patch(9) == 16
+
+
+def test_default_element_order_tiles():
+    mesh = meshgen.structured_quad_mesh(8, 8, 1)
+    order = operators.default_element_order(mesh, 16)
+    first = sorted(order[:16].tolist())
+    assert first == sorted(ex * 8 + ey for ex in range(4) for ey in range(4))
+    mesh._structured_shape = None
+    mo = operators.default_element_order(mesh, 16)
+    assert sorted(mo.tolist()) == list(range(64))
+    # a Morton run of 16 cells on an 8x8 grid is a 4x4 block
+    ex, ey = np.divmod(mo[:16], 8)
+    assert ex.max() - ex.min() == 3 and ey.max() - ey.min() == 3
+
+
+def test_product_fails_loudly_without_gpu():
+    lib = _lib.load()
+    if lib.semk_device_available():
+        pytest.skip("a GPU is present")
+    from conftest import build_package_case
+    mesh, mngr = build_package_case("S", 2, 2, 3, False, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mngr.poisson_operator()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        next(mngr.finite_elements(x_phys=True, Jacobian=True))

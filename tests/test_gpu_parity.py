@@ -1,0 +1,319 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+Three anchors:
+  * golden vectors frozen from the live reference (tests/golden/, made by
+    oracle/make_golden.py),
+  * the CPU oracle (oracle/sem_oracle.py) on seeded inputs at sizes it
+    finishes in seconds,
+  * size-independent properties at large sizes (symmetry, null space,
+    linearity, determinism, PCG residual).
+
+Tolerances: integer tables bit-exact (tests/test_host_api.py);
+T1 = kernels fed the reference's own invJ / detJxW: 1e-12 relative L2
+(observed ~1e-15); T2 = device geometry kernel: 1e-12 on these <= 8x8 meshes.
+"""
+import numpy as np
+import pytest
+import torch
+
+import sem_oracle as so
+from conftest import build_package_case, golden_case_names, load_case, rel_l2
+from spectralelementmethod_b200 import _lib, device, meshgen
+from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+from spectralelementmethod_b200 import discrete
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def case_and_manager(name):
+    g = load_case(name)
+    mesh, mngr = build_package_case(g["kind"], g["nx"], g["ny"], g["p"], g["sc"], g["rcm"])
+    return g, mesh, mngr
+
+
+# --------------------------------------------------------------------------
+# K1 geometry kernel and the FiniteElement view (tier T2)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_case_names())
+def test_geometry_kernel_vs_reference(name):
+    g, mesh, mngr = case_and_manager(name)
+    geo = device.element_geometry(mngr._basis, mesh.nodes, mngr.node_map_array())
+    assert geo["x_phys"].shape == g["x_phys"].shape and geo["invJ"].shape == g["invJ"].shape
+    assert rel_l2(geo["x_phys"], g["x_phys"]) < TOL
+    assert rel_l2(geo["invJ"], g["invJ"]) < TOL
+    w = mngr._basis.quad_rule.xweight(np.ones(g["JxW"].shape[1:]))
+    assert rel_l2(geo["detJ"] * w, g["JxW"]) < TOL
+    # J * invJ = I
+    prod = np.einsum("eiamn,eajmn->eijmn", geo["J"], geo["invJ"])
+    eye = np.eye(2)[None, :, :, None, None]
+    assert np.abs(prod - eye).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["C534_dm", "S448_sc_rcm", "C3310_dm_rcm"])
+def test_finite_element_api_vs_reference(name):
+    g, mesh, mngr = case_and_manager(name)
+    n = 0
+    for e, fe in enumerate(mngr.finite_elements(x_phys=True, Jacobian=True)):
+        assert np.array_equal(fe.node_ind, g["l2g"][e])
+        assert rel_l2(fe.x_phys, g["x_phys"][e]) < TOL
+        assert rel_l2(fe.invJ, g["invJ"][e]) < TOL
+        assert rel_l2(fe.detJxW, g["JxW"][e]) < TOL
+        n += 1
+    assert n == g["l2g"].shape[0]
+    fe = mngr.get_finite_element(1, Jacobian=True)       # single-cell device path
+    assert rel_l2(fe.invJ, g["invJ"][1]) < TOL
+    # Dirichlet data through boundary_elements (examples/poisson.py:125-143)
+    vals = np.zeros(mngr.ndof)
+    on = np.zeros(mngr.ndof, dtype=bool)
+    for parent, bfe in mngr.boundary_elements("ebc", x_phys=True):
+        x, y = bfe.x_phys
+        vals[bfe.node_ind] = 0.2 * ((x + 1) + (y + 1))
+        on[bfe.node_ind] = True
+    assert np.array_equal(on, g["on_ebc"])
+    assert rel_l2(vals, g["ebc_vals"]) < TOL
+    # face geometry: outward normals of the unit square boundary
+    for parent, bfe in mngr.boundary_elements("nbc", Jacobian=True):
+        nrm = bfe.unit_normal
+        assert nrm.shape == (2, g["p"] + 1)
+        assert np.allclose(np.linalg.norm(nrm, axis=0), 1.0)
+        assert (nrm[0] > 0.5).all() or (nrm[1] > 0.5).all()
+
+
+def test_negative_jacobian_raises_like_the_reference():
+    mesh = meshgen.structured_quad_mesh(2, 2, 3)
+    mesh.nodes[0] *= -1.0                                  # mirror => detJ < 0
+    b1 = LagrangeGaussLobatto(3)
+    mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+    with pytest.raises(AssertionError):
+        next(mngr.finite_elements(Jacobian=True))
+    with pytest.raises(AssertionError):
+        mngr.poisson_operator()
+
+
+# --------------------------------------------------------------------------
+# K2/K3/K5: apply, assembly, diagonal, RHS
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_case_names())
+@pytest.mark.parametrize("tier", ["T1", "T2"])
+def test_operator_vs_reference(name, tier):
+    g, mesh, mngr = case_and_manager(name)
+    gf = (g["invJ"], g["JxW"]) if tier == "T1" else None
+    op = mngr.poisson_operator(geometric_factors=gf)
+    u = dev(g["u"])
+    y = op.apply_unmasked(u)
+    assert rel_l2(host(y), g["Au"]) < TOL
+    ya = op.apply_atomic(u, flags=0)
+    assert rel_l2(host(ya), g["Au"]) < TOL
+    assert rel_l2(host(op.diagonal(masked=False)), g["diag"]) < TOL
+    assert rel_l2(host(op.rhs(1.0)), g["b"]) < TOL
+    if tier == "T1":
+        assert rel_l2(host(y), g["Au"]) < 1e-13     # same factors: only summation order differs
+
+
+@pytest.mark.parametrize("name", ["S448_sc", "C448_sc_rcm", "C534_dm", "C3310_dm_rcm",
+                                  "S888_sc_rcm", "C888_sc_rcm"])
+@pytest.mark.parametrize("tier", ["T1", "T2"])
+def test_pcg_solution_vs_reference_direct_solve(name, tier):
+    g, mesh, mngr = case_and_manager(name)
+    gf = (g["invJ"], g["JxW"]) if tier == "T1" else None
+    op = mngr.poisson_operator(dirichlet=g["on_ebc"], geometric_factors=gf)
+    b = op.lift(op.rhs(1.0), g["ebc_vals"])
+    x, info = op.solve_pcg(b, rtol=1e-13, maxiter=20000, check_every=10)
+    assert info.converged and info.rel_residual <= 1e-13
+    assert rel_l2(host(x), g["solution"]) < TOL
+    # true residual of the lifted system
+    r = b - op.apply(x)
+    assert float(r.norm() / b.norm()) < 1e-12
+    # one-call convenience path
+    x2, info2 = op.solve(1.0, g["ebc_vals"], rtol=1e-13, check_every=10)
+    assert torch.equal(x, x2) and info2.iterations == info.iterations
+
+
+def test_pcg_iteration_count_matches_cpu_pcg():
+    g, mesh, mngr = case_and_manager("S448_sc")
+    op = mngr.poisson_operator(dirichlet=g["on_ebc"])
+    b = op.lift(op.rhs(1.0), g["ebc_vals"])
+    x, info = op.solve_pcg(b, rtol=1e-13, check_every=1)
+    basis = so.Basis(g["p"])
+    L = so.local_stiffness(basis, g["invJ"], g["JxW"])
+    A = so.assemble_csr(L, g["l2g"], mngr.ndof)
+    on, vals = g["on_ebc"], g["ebc_vals"]
+    free = ~on
+    rhs = g["b"][free] - A[free][:, on] @ vals[on]
+    xs, it = so.pcg_jacobi(A[free][:, free].tocsr(), rhs, np.zeros(rhs.size), 1e-13, 5000)
+    assert abs(info.iterations - it) <= 3
+    # iterate is frozen at the converged iteration even when polling is sparse
+    x25, info25 = op.solve_pcg(b, rtol=1e-13, check_every=25)
+    assert info25.iterations == info.iterations and torch.equal(x25, x)
+
+
+def test_masking_modes_and_dot():
+    g, mesh, mngr = case_and_manager("C448_sc_rcm")
+    on = g["on_ebc"]
+    op = mngr.poisson_operator(dirichlet=on)
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(mngr.ndof)
+    A = so.assemble_csr(so.local_stiffness(so.Basis(g["p"]), g["invJ"], g["JxW"]), g["l2g"],
+                        mngr.ndof)
+    M = (~on).astype(float)
+    ref = M * (A @ (M * u)) + (1 - M) * u                   # Ahat = M A M + (I - M)
+    dot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    y = op.apply(dev(u), dot_out=dot)
+    assert rel_l2(host(y), ref) < TOL
+    assert abs(float(dot) - u @ ref) < 1e-11 * abs(u @ ref)
+    y0 = op.apply(dev(u), flags=_lib.MASK_IN | _lib.MASK_OUT)
+    assert rel_l2(host(y0), M * (A @ (M * u))) < TOL
+    y1 = op.apply(dev(u), flags=_lib.MASK_OUT)
+    assert rel_l2(host(y1), M * (A @ u)) < TOL
+    ya = op.apply_atomic(dev(u))
+    assert rel_l2(host(ya), ref) < TOL
+    d = op.diagonal()
+    assert rel_l2(host(d), M * A.diagonal() + (1 - M)) < TOL
+    lifted = op.lift(dev(g["b"]), g["ebc_vals"])
+    assert rel_l2(host(lifted), M * (g["b"] - A @ ((1 - M) * g["ebc_vals"])) + (1 - M) * g["ebc_vals"]) < TOL
+    with pytest.raises(ValueError):
+        op.apply(dev(u)[:-1])
+    with pytest.raises(ValueError):
+        op.apply(dev(u).float())
+    with pytest.raises(ValueError):
+        ub = dev(u)
+        op.apply(ub, out=ub)
+
+
+def test_to_scipy_csr_matches_reference_matrix():
+    g, mesh, mngr = case_and_manager("S324_sc_rcm")
+    op = mngr.poisson_operator()
+    A = op.to_scipy_csr()
+    Aref = so.assemble_csr(so.local_stiffness(so.Basis(g["p"]), g["invJ"], g["JxW"]), g["l2g"],
+                           mngr.ndof)
+    assert abs(A - Aref).max() < 1e-12 * abs(Aref).max()
+    assert abs(A - A.T).max() < 1e-13 * abs(Aref).max()
+
+
+# --------------------------------------------------------------------------
+# oracle on seeded random inputs, several orders / patch sizes / numberings
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,nx,ny,p,sc,rcm,pe", [
+    ("C", 9, 7, 1, False, False, None),
+    ("C", 9, 7, 2, True, True, None),
+    ("C", 6, 9, 3, False, True, 8),
+    ("C", 7, 5, 5, True, False, 4),
+    ("C", 6, 5, 6, False, False, None),
+    ("C", 5, 6, 7, True, True, 8),
+    ("C", 11, 9, 8, False, False, None),
+    ("C", 4, 5, 9, True, False, None),
+    ("S", 5, 4, 12, False, False, None),
+    ("C", 3, 4, 12, False, False, 4),
+    ("C", 3, 3, 16, False, False, None),
+])
+def test_apply_vs_oracle_random(kind, nx, ny, p, sc, rcm, pe):
+    mesh, mngr = build_package_case(kind, nx, ny, p, sc, rcm)
+    r = so.run_case(kind, nx, ny, p, sc, rcm, solve=False)
+    assert np.array_equal(mngr.node_map_array(), r["l2g"])
+    rng = np.random.default_rng(1)
+    u = rng.standard_normal(mngr.ndof)
+    ref = so.apply_dense_batched(r["L"], r["l2g"], u)
+    tol = TOL if p <= 10 else 1e-9        # p > 10: no reference table, LU-vs-inverse noise
+    kw = {} if pe is None else {"elems_per_patch": pe}
+    op = mngr.poisson_operator(**kw)
+    y = op.apply_unmasked(dev(u))
+    assert rel_l2(host(y), ref) < tol
+    opT1 = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), **kw)
+    assert rel_l2(host(opT1.apply_unmasked(dev(u))), ref) < 1e-12
+    assert rel_l2(host(opT1.apply_atomic(dev(u), flags=0)), ref) < 1e-12
+    assert rel_l2(host(opT1.diagonal(masked=False)), r["diag"]) < 1e-12
+    f = rng.standard_normal(mngr.ndof)
+    bref = so.assemble_vector(r["JxW"] * f[r["l2g"]], r["l2g"], mngr.ndof)
+    assert rel_l2(host(opT1.rhs(f)), bref) < 1e-12
+
+
+def test_unstructured_element_order_and_ragged_last_patch():
+    """Random element order (no locality), E not a multiple of the patch size."""
+    mesh, mngr = build_package_case("C", 5, 5, 4, False, False)
+    r = so.run_case("C", 5, 5, 4, False, False, solve=False)
+    rng = np.random.default_rng(2)
+    order = rng.permutation(25)
+    op = mngr.poisson_operator(elem_order=order, elems_per_patch=8)
+    assert op.n_patch == 4 and op.n_slot_elems == 32
+    u = rng.standard_normal(mngr.ndof)
+    ref = so.apply_dense_batched(r["L"], r["l2g"], u)
+    assert rel_l2(host(op.apply_unmasked(dev(u))), ref) < TOL
+
+
+# --------------------------------------------------------------------------
+# properties at larger sizes
+# --------------------------------------------------------------------------
+def _properties(op, n, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    u = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    v = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    Au, Av = op.apply_unmasked(u), op.apply_unmasked(v)
+    # determinism: bitwise identical on repetition
+    assert torch.equal(Au, op.apply_unmasked(u))
+    # symmetry
+    a, b = float(torch.dot(v, Au)), float(torch.dot(u, Av))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    # constants are in the null space of the Neumann operator
+    one = torch.ones(n, dtype=torch.float64, device="cuda")
+    assert float(op.apply_unmasked(one).abs().max()) <= 1e-9 * float(op.diagonal(masked=False).max())
+    # linearity
+    lin = op.apply_unmasked(2.0 * u - 3.0 * v)
+    assert float((lin - (2.0 * Au - 3.0 * Av)).norm() / lin.norm()) < 1e-13
+    # positive semi-definite, and agreement with the atomic cross-check kernel
+    assert float(torch.dot(u, Au)) > 0
+    assert float((op.apply_atomic(u, flags=0) - Au).norm() / Au.norm()) < 1e-13
+    # sum of the load vector = area of the domain
+    assert abs(float(op.rhs(1.0).sum()) - 4.0) < 1e-10
+    return u
+
+
+def test_properties_256x256_p8_curved():
+    mesh, mngr = build_package_case("C", 256, 256, 8, False, False)
+    on = mngr.boundary_node_mask("ebc")
+    op = mngr.poisson_operator(dirichlet=on)
+    _properties(op, mngr.ndof)
+    # short PCG run: residual must drop monotonically in the energy norm => just check progress
+    b = op.lift(op.rhs(1.0), None)
+    x, info = op.solve_pcg(b, rtol=1e-3, maxiter=4000, check_every=50)
+    assert info.converged
+    r = b - op.apply(x)
+    assert float(r.norm() / b.norm()) < 2e-3
+
+
+def test_full_size_config2_1024x1024_p8():
+    """BASELINE.json configs[1]: 1024 x 1024 elements, p = 8, 67 125 249 DOF."""
+    mesh, mngr = build_package_case("S", 1024, 1024, 8, False, False)
+    assert mngr.ndof == 8193 * 8193
+    maps = mngr.node_map_array()
+    # closed form of the structured L2G map, spot-checked (rcm_order=False)
+    for e in (0, 1, 1023, 1024, 524800, 1048575):
+        ex, ey = divmod(e, 1024)
+        want = (ex * 8 + np.arange(9))[:, None] * 8193 + ey * 8 + np.arange(9)[None, :]
+        assert np.array_equal(maps[e], want)
+    op = mngr.poisson_operator(dirichlet=mngr.boundary_node_mask("ebc"))
+    u = _properties(op, mngr.ndof)
+    # affine elements: G is known in closed form (G00 = G11 = w_m w_n, G01 = 0)
+    w = mngr._basis.quad_rule.xweight(np.ones((9, 9))).ravel()
+    G = op.G[:4096].cpu().numpy()
+    assert np.abs(G[:, :81] - w).max() < 1e-12 and np.abs(G[:, 162:243] - w).max() < 1e-12
+    assert np.abs(G[:, 81:162]).max() < 1e-12
+    # quadratic field: A u = -laplace(u) weak form; u = x^2 - y^2 is harmonic, so interior rows vanish
+    x, y = mesh.nodes
+    # DOFs live at GLL points: rebuild their coordinates from the structured lattice
+    gl = LagrangeGaussLobatto(8).nodes
+    h = 2.0 / 1024
+    c1 = (-1.0 + h * (np.arange(1024)[:, None] + (gl[None, :-1] + 1) / 2)).ravel()
+    c1 = np.append(c1, 1.0)
+    harm = torch.from_numpy(c1[:, None] ** 2 - c1[None, :] ** 2).reshape(-1).cuda()
+    Ah = op.apply_unmasked(harm).reshape(8193, 8193)
+    assert float(Ah[1:-1, 1:-1].abs().max()) < 1e-9

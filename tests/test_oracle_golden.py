@@ -1,0 +1,77 @@
+"""The CPU oracle (oracle/sem_oracle.py) against golden vectors frozen from the
+live reference (oracle/make_golden.py).  Integer tables bit-exact; FP64 tables
+bit-exact; operator / solution quantities within 1e-12 relative L2."""
+import numpy as np
+import pytest
+
+import sem_oracle as so
+from conftest import golden_case_names, load_case, rel_l2
+
+TOL = 1e-12
+
+
+def test_tables_bit_exact(golden_tables):
+    for p in range(1, 11):
+        b = so.Basis(p)
+        assert np.array_equal(b.nodes, golden_tables["nodes_%d" % p])
+        assert np.array_equal(b.bary, golden_tables["bary_%d" % p])
+        assert np.array_equal(b.w, golden_tables["quad_%d" % p])
+        assert np.array_equal(b.D, golden_tables["D_%d" % p])
+        assert np.array_equal(b.E, golden_tables["E_%d" % p])
+
+
+def test_hier_and_faces(golden_tables):
+    for N in (2, 3, 5, 9, 11):
+        assert np.array_equal(so.hier_order(N), golden_tables["hier_%d" % N])
+    arr = np.arange(2 * 4 * 5).reshape(2, 4, 5)
+    for f in range(4):
+        assert np.array_equal(so.face_nodes(arr, f), golden_tables["face_%d" % f])
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_case(name):
+    g = load_case(name)
+    big = g["l2g"].shape[0] > 32
+    r = so.run_case(g["kind"], g["nx"], g["ny"], g["p"], g["sc"], g["rcm"],
+                    python_loop_apply=not big)
+    # T0: integer tables and the permuted coordinates, bit-exact
+    assert np.array_equal(r["l2g"], g["l2g"])
+    assert r["l2g"].dtype == np.uint32
+    assert np.array_equal(r["nodes"], g["nodes"])
+    assert np.array_equal(r["on_ebc"], g["on_ebc"])
+    # geometry and operator quantities
+    assert rel_l2(r["x_phys"], g["x_phys"]) < TOL
+    assert rel_l2(r["invJ"], g["invJ"]) < TOL
+    assert rel_l2(r["JxW"], g["JxW"]) < TOL
+    assert rel_l2(r["Au"], g["Au"]) < TOL
+    assert rel_l2(r["b"], g["b"]) < TOL
+    assert rel_l2(r["diag"], g["diag"]) < TOL
+    assert rel_l2(r["ebc_vals"], g["ebc_vals"]) < TOL
+    assert rel_l2(r["solution"], g["solution"]) < TOL
+
+
+def test_python_loop_and_batched_apply_agree():
+    g = load_case("C534_dm")
+    b = so.Basis(g["p"])
+    L = so.local_stiffness(b, g["invJ"], g["JxW"])
+    y1 = so.apply_dense_local(L, g["l2g"], g["u"])
+    y2 = so.apply_dense_batched(L, g["l2g"], g["u"])
+    assert rel_l2(y1, y2) < 1e-14
+    assert rel_l2(y1, g["Au"]) < TOL
+
+
+def test_pcg_on_oracle_matrix_matches_direct_solution():
+    g = load_case("S448_sc")
+    b = so.Basis(g["p"])
+    L = so.local_stiffness(b, g["invJ"], g["JxW"])
+    n = g["nodes"].shape[1]
+    A = so.assemble_csr(L, g["l2g"], n)
+    on, vals = g["on_ebc"], g["ebc_vals"]
+    free = ~on
+    Af = A[free][:, free].tocsr()
+    rhs = g["b"][free] - A[free][:, on] @ vals[on]
+    x, it = so.pcg_jacobi(Af, rhs, np.zeros(rhs.size), 1e-13, 5000)
+    sol = vals.copy()
+    sol[free] = x
+    assert rel_l2(sol, g["solution"]) < TOL
+    assert 100 < it < 400      # 218 iterations at n=4
