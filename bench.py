@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=64,
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
     ap.add_argument("--kind", default="S", choices=["S", "C"])
+    ap.add_argument("--pe", type=int, default=0, help="elements per patch (0 = automatic)")
     return ap.parse_args()
 
 
@@ -208,7 +209,7 @@ def run_engine(args):
         b1 = LagrangeGaussLobatto(ORDER)
         mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
         on_ebc = mngr.boundary_node_mask("ebc")
-        op = mngr.poisson_operator(dirichlet=on_ebc)
+        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None)
         apply_fn = lambda u, out: op.apply(u, out=out)          # noqa: E731
         n_local = n_global = op.n_nodes
         n_global_units = n_global
@@ -219,7 +220,7 @@ def run_engine(args):
         from spectralelementmethod_b200.distributed import DistributedPoisson, StripPartition
         nx = args.nx or 884
         part = StripPartition(rank, world, nx, nx, ORDER, bounds=(-1.0, -1.0 + 2.0 * world, -1.0, 1.0))
-        dp = DistributedPoisson(part, ORDER, args.kind)
+        dp = DistributedPoisson(part, ORDER, args.kind, elems_per_patch=args.pe or None)
         op = dp.op
         apply_fn = lambda u, out: dp.apply(u, out=out)          # noqa: E731
         n_local = op.n_nodes

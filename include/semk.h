@@ -73,17 +73,19 @@ int semk_device_available(void);
 typedef struct semk_hostplan semk_hostplan;
 
 enum semk_plan_array {
-  SEMK_PA_PATCH_NODE_PTR = 0, /* int32  [n_patch+1]   offsets into PNODE                    */
-  SEMK_PA_PNODE = 1,          /* uint32 [n_pnode]     global id | flags; private nodes first */
+  SEMK_PA_PATCH_NODE_PTR = 0, /* int32  [n_patch+1]   offsets into PNODE (multiples of 4)    */
+  SEMK_PA_PNODE = 1,          /* uint32 [n_pnode]     global id | flags; private nodes first;
+                                 each patch padded with 0xffffffff to a multiple of 4       */
   SEMK_PA_PATCH_NPRIV = 2,    /* int32  [n_patch]     number of private nodes of the patch   */
   SEMK_PA_PATCH_SLOT_BASE = 3,/* int32  [n_patch]     first interface slot of the patch      */
-  SEMK_PA_ELOC = 4,           /* uint16 [n_slot_elems][NN] patch-local index of each node    */
+  SEMK_PA_ELOC = 4,           /* uint16 [n_slot_elems][eloc_stride] patch-local node indices */
   SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
   SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
   SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
   SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
   SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node    */
-  SEMK_PA_COUNT = 10
+  SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
+  SEMK_PA_COUNT = 11
 };
 
 enum semk_plan_scalar {
@@ -94,7 +96,8 @@ enum semk_plan_scalar {
   SEMK_PS_MAX_PATCH_NODES = 4,
   SEMK_PS_MAX_COLORS = 5,
   SEMK_PS_N_SLOT_ELEMS = 6,   /* n_patch * elems_per_patch (last patch padded) */
-  SEMK_PS_COUNT = 7
+  SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per row of ELOC: NN rounded up to 8 */
+  SEMK_PS_COUNT = 8
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
@@ -127,8 +130,10 @@ typedef struct semk_op {
   const int32_t *patch_node_ptr;
   const uint32_t *pnode;
   const int32_t *patch_npriv;
+  const int32_t *patch_nnodes;
   const int32_t *patch_slot_base;
   const uint16_t *eloc;
+  int64_t eloc_stride;      /* uint16 entries per element row of eloc (multiple of 8) */
   const uint8_t *elem_color;
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums (scratch)  */
@@ -143,6 +148,9 @@ typedef struct semk_op {
 
 /* number of doubles the `partials` scratch of an operator must hold */
 int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
+/* dynamic shared memory (bytes) one CTA of the apply kernel needs */
+int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_stride, int64_t eloc_stride,
+                              int max_patch_nodes);
 
 /* ------------------------------------------------------------------------
  * K1: geometric factors.  Replaces, per element, Mapping._compute_x_phys /

@@ -20,15 +20,15 @@ MASK_IN, MASK_OUT, DIRICHLET_IDENTITY = 1, 2, 4
 MAX_N1 = 17
 
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
- PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT) = range(10)
+ PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES) = range(11)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
- PS_N_SLOT_ELEMS) = range(7)
+ PS_N_SLOT_ELEMS, PS_ELOC_STRIDE) = range(8)
 
 PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
     PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16, PA_ELEM_COLOR: np.uint8,
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
-    PA_SHARED_SLOT: np.int32,
+    PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32,
 }
 
 
@@ -50,7 +50,9 @@ class semk_op(C.Structure):
         ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
         ("g_stride", C.c_int64), ("G", C.c_void_p),
         ("patch_node_ptr", C.c_void_p), ("pnode", C.c_void_p), ("patch_npriv", C.c_void_p),
-        ("patch_slot_base", C.c_void_p), ("eloc", C.c_void_p), ("elem_color", C.c_void_p),
+        ("patch_nnodes", C.c_void_p),
+        ("patch_slot_base", C.c_void_p), ("eloc", C.c_void_p), ("eloc_stride", C.c_int64),
+        ("elem_color", C.c_void_p),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
         ("shared_slot", C.c_void_p),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
     "semk_hostplan_destroy": (None, [_P]),
     "semk_partials_len": (_L, [_L, _L]),
+    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _I]),
     "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P,
                                    _P, _P, _P]),
     "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _P]),
@@ -163,7 +166,7 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
     check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p,
                                    int(elems_per_patch), dir_p, C.byref(handle)))
     try:
-        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(7)}
+        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(8)}
         arrays = {}
         for k, dt in PLAN_ARRAY_DTYPES.items():
             nb = _L(0)

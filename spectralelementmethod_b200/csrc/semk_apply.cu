@@ -138,6 +138,39 @@ struct PatchCfg {
 
 enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 
+// Shared-memory carve-up of the patch kernel (all offsets multiples of 16 B).
+struct PatchSmem {
+  size_t gs, pn, el, yp, ua, bs, red, total;
+};
+__host__ __device__ inline PatchSmem patch_smem_layout(int NN, int PE, int mode, int64_t g_stride,
+                                                       int64_t eloc_stride, int max_patch_nodes) {
+  PatchSmem L;
+  const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
+  const size_t scratch = (size_t)PE * NN;
+  size_t o = 16;  // two mbarriers
+  L.gs = o;
+  o += (mode == MODE_APPLY) ? sizeof(double) * PE * (size_t)g_stride : 0;
+  L.pn = o;
+  o += 4 * mpn4;
+  L.el = o;
+  o += 2 * (size_t)PE * (size_t)eloc_stride;
+  L.yp = o;
+  o += 8 * (mpn4 + (mpn4 & 1));
+  o = (o + 15) & ~(size_t)15;
+  L.ua = o;  // u staging, later scratch A
+  o += (mode == MODE_APPLY) ? 8 * (mpn4 > scratch ? mpn4 : scratch) : 0;
+  o = (o + 15) & ~(size_t)15;
+  L.bs = o;
+  o += (mode == MODE_APPLY) ? 8 * scratch : 0;
+  o = (o + 15) & ~(size_t)15;
+  L.red = o;
+  o += 8 * 32;
+  L.total = o;
+  return L;
+}
+
+constexpr int kGatherBatch = 8;
+
 // MODE_APPLY:    y = A u (masked per flags), optional dot partials.
 // MODE_ASSEMBLE: y = assembly of the element-local field `loc` (slot order).
 template <int N, int PE, int MODE>
@@ -148,54 +181,86 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   constexpr int NN = N * N;
   constexpr int kThreads = PatchCfg<N, PE>::kThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [mbar 16 B][Gs PE*g_stride][up mpn][yp mpn][A PE*NN][B PE*NN][red 32]
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
-  double *Gs = reinterpret_cast<double *>(smem_raw + 16);
-  const int gs_len = (MODE == MODE_APPLY) ? PE * (int)op.g_stride : 0;
-  double *up = Gs + gs_len;
-  double *yp = up + op.max_patch_nodes;
-  double *As = yp + op.max_patch_nodes;
-  double *Bs = As + ((MODE == MODE_APPLY) ? PE * NN : 0);
-  double *red = Bs + ((MODE == MODE_APPLY) ? PE * NN : 0);
+  const PatchSmem L =
+      patch_smem_layout(NN, PE, MODE, op.g_stride, op.eloc_stride, op.max_patch_nodes);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0]: tables, [1]: G
+  double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
+  uint32_t *pn_s = reinterpret_cast<uint32_t *>(smem_raw + L.pn);
+  uint16_t *el_s = reinterpret_cast<uint16_t *>(smem_raw + L.el);
+  double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
+  double *up = reinterpret_cast<double *>(smem_raw + L.ua);  // aliases scratch A
+  double *As = up;
+  double *Bs = reinterpret_cast<double *>(smem_raw + L.bs);
+  double *red = reinterpret_cast<double *>(smem_raw + L.red);
 
   const int tid = threadIdx.x;
   const int64_t patch = blockIdx.x;
   const int64_t slot0 = patch * PE;
   const int le = tid / N, t = tid - le * N;
+  const int lec = le < PE ? le : 0;
   const bool active = (le < PE) && (slot0 + le < op.n_elem);
-  const int64_t slot = slot0 + (le < PE ? le : 0);
+  const int ES = (int)op.eloc_stride;
 
-  if (MODE == MODE_APPLY) {
-    if (tid == 0) {
-      semk_mbar_init(mbar, 1);
-      semk_fence_mbar_init();
-      const uint32_t bytes = (uint32_t)(PE * op.g_stride * sizeof(double));
-      semk_mbar_expect_tx(mbar, bytes);
-      semk_bulk_g2s(Gs, op.G + slot0 * op.g_stride, bytes, mbar);
-    }
-  }
-
-  // ---- gather the patch's nodal values --------------------------------------
+  // ---- stage the patch's tables (and geometric factors) with the TMA engine ----
   const int n0 = op.patch_node_ptr[patch];
-  const int npn = op.patch_node_ptr[patch + 1] - n0;
-  const int npriv = op.patch_npriv[patch];
-  for (int k = tid; k < npn; k += kThreads) {
+  if (tid == 0) {
+    semk_mbar_init(&mbar[0], 1);
+    semk_mbar_init(&mbar[1], 1);
+    semk_fence_mbar_init();
+    const uint32_t pn_bytes = 4u * (uint32_t)(op.patch_node_ptr[patch + 1] - n0);
+    const uint32_t el_bytes = 2u * (uint32_t)(PE * ES);
+    semk_mbar_expect_tx(&mbar[0], pn_bytes + el_bytes);
+    semk_bulk_g2s(pn_s, op.pnode + n0, pn_bytes, &mbar[0]);
+    semk_bulk_g2s(el_s, op.eloc + slot0 * ES, el_bytes, &mbar[0]);
     if (MODE == MODE_APPLY) {
-      const uint32_t pn = op.pnode[n0 + k];
-      double v = u[pn & SEMK_NODE_ID_MASK];
-      if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) v = 0.0;
-      up[k] = v;
+      const uint32_t g_bytes = (uint32_t)(PE * op.g_stride * sizeof(double));
+      semk_mbar_expect_tx(&mbar[1], g_bytes);
+      semk_bulk_g2s(Gs, op.G + slot0 * op.g_stride, g_bytes, &mbar[1]);
     }
-    yp[k] = 0.0;
   }
-  // element-local index column
-  uint16_t idx[N];
+  const int npn = op.patch_nnodes[patch];
+  const int npriv = op.patch_npriv[patch];
+  const int slot_base = op.patch_slot_base[patch];
   uint8_t color = 255;
+  if (active) color = op.elem_color[slot0 + le];
+  __syncthreads();  // mbarrier initialisation visible to every waiter
+  semk_mbar_wait(&mbar[0], 0);
+
+  // ---- gather the patch's nodal values: batches of independent loads -----------
+  for (int k0 = tid; k0 < npn; k0 += kGatherBatch * kThreads) {
+    if (MODE == MODE_APPLY) {
+      uint32_t pn[kGatherBatch];
+      double v[kGatherBatch];
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j) {
+        const int k = k0 + j * kThreads;
+        pn[j] = (k < npn) ? pn_s[k] : 0xffffffffu;
+      }
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j)
+        v[j] = (pn[j] != 0xffffffffu) ? u[pn[j] & SEMK_NODE_ID_MASK] : 0.0;
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j) {
+        const int k = k0 + j * kThreads;
+        if (k < npn) {
+          up[k] = ((pn[j] & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : v[j];
+          yp[k] = 0.0;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j) {
+        const int k = k0 + j * kThreads;
+        if (k < npn) yp[k] = 0.0;
+      }
+    }
+  }
+  // element-local index column (from the staged table)
+  uint16_t idx[N];
   if (active) {
-    const uint16_t *er = op.eloc + slot * NN;
+    const uint16_t *er = el_s + lec * ES;
 #pragma unroll
     for (int m = 0; m < N; ++m) idx[m] = er[m * N + t];
-    color = op.elem_color[slot];
   }
   __syncthreads();
 
@@ -206,11 +271,12 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
 #pragma unroll
       for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
     }
-    local_poisson<N>(t, active, ucol, ycol, As + (le < PE ? le : 0) * NN,
-                     Bs + (le < PE ? le : 0) * NN, Gs + (le < PE ? le : 0) * op.g_stride, mbar);
+    __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
+    local_poisson<N>(t, active, ucol, ycol, As + lec * NN, Bs + lec * NN,
+                     Gs + lec * op.g_stride, &mbar[1]);
   } else {
     if (active) {
-      const double *lr = loc + slot * NN;
+      const double *lr = loc + (slot0 + le) * NN;
 #pragma unroll
       for (int m = 0; m < N; ++m) ycol[m] = lr[m * N + t];
     }
@@ -227,20 +293,27 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
 
   // ---- write out: private nodes -> y, shared nodes -> interface slots --------
   double dot = 0.0;
-  const int slot_base = op.patch_slot_base[patch];
+  const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
   for (int k = tid; k < npn; k += kThreads) {
-    const uint32_t pn = op.pnode[n0 + k];
+    const uint32_t pn = pn_s[k];
     double v = yp[k];
     if (k < npriv) {
       const uint32_t g = pn & SEMK_NODE_ID_MASK;
-      double uin = (MODE == MODE_APPLY) ? up[k] : 0.0;
-      if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_OUT)) {
+      const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
+      double uin = 0.0;
+      if (MODE == MODE_APPLY) {
+        if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
+        if (dir && (flags & SEMK_MASK_IN)) uin = (flags & SEMK_MASK_OUT) ? uin : 0.0;
+      }
+      if (dir && (flags & SEMK_MASK_OUT)) {
         if (MODE == MODE_APPLY) {
-          v = (flags & SEMK_DIRICHLET_IDENTITY) ? u[g] : 0.0;
+          v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
           uin = v;
         } else {
           v = fill_dirichlet;
         }
+      } else if (dir && (flags & SEMK_MASK_IN)) {
+        uin = 0.0;
       }
       y[g] = v;
       dot = fma(uin, v, dot);
@@ -248,7 +321,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       op.slot_buf[slot_base + (k - npriv)] = v;
     }
   }
-  if (MODE == MODE_APPLY && dot_partials) {
+  if (want_dot) {
     const double s = semk_block_sum(dot, red);
     if (tid == 0) dot_partials[patch] = s;
   }
@@ -269,18 +342,20 @@ __global__ void __launch_bounds__(256)
     const int j0 = op.shared_ptr[i], j1 = op.shared_ptr[i + 1];
     double v = 0.0;
     for (int j = j0; j < j1; ++j) v += op.slot_buf[op.shared_slot[j]];
+    const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
     double uin = 0.0;
     if (MODE == MODE_APPLY) {
-      uin = u[g];
-      if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) uin = 0.0;
+      if (dot_partials || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
     }
-    if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_OUT)) {
+    if (dir && (flags & SEMK_MASK_OUT)) {
       if (MODE == MODE_APPLY) {
-        v = (flags & SEMK_DIRICHLET_IDENTITY) ? u[g] : 0.0;
+        v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
         uin = v;
       } else {
         v = fill_dirichlet;
       }
+    } else if (dir && (flags & SEMK_MASK_IN)) {
+      uin = 0.0;
     }
     y[g] = v;
     dot = fma(uin, v, dot);
@@ -302,7 +377,7 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) out[0] = s;
 }
 
-constexpr int kSharedBlocks = 148 * 4;
+constexpr int kSharedBlocks = 148 * 64;   // upper bound on shared_nodes_kernel CTAs
 
 // ---- simple atomic-scatter kernel (independent cross-check) -------------------
 template <int N, int PE>
@@ -392,8 +467,8 @@ struct PatchLaunch {
   static int run(const semk_op &op, const double *u, const double *loc, double *y, int flags,
                  double fill, double *partials, cudaStream_t st) {
     constexpr int NN = N * N;
-    size_t smem = 16 + sizeof(double) * (2 * (size_t)op.max_patch_nodes + 32);
-    if (MODE == MODE_APPLY) smem += sizeof(double) * ((size_t)PE * op.g_stride + 2 * PE * NN);
+    const size_t smem =
+        patch_smem_layout(NN, PE, MODE, op.g_stride, op.eloc_stride, op.max_patch_nodes).total;
     auto kern = patch_kernel<N, PE, MODE>;
     if (smem > 227 * 1024) {
       semk_set_error("patch kernel: shared memory request exceeds 227 KB");
@@ -447,8 +522,9 @@ int check_op(const semk_op *op, const char *who) {
     semk_set_error(std::string(who) + ": elems_per_patch must be 4, 8 or 16");
     return SEMK_ERR_UNSUPPORTED;
   }
-  if (!op->patch_node_ptr || !op->pnode || !op->patch_npriv || !op->patch_slot_base ||
-      !op->eloc || !op->elem_color || (op->n_slots > 0 && !op->slot_buf) ||
+  if (!op->patch_node_ptr || !op->pnode || !op->patch_npriv || !op->patch_nnodes ||
+      !op->patch_slot_base || !op->eloc || !op->elem_color || (op->eloc_stride & 7) != 0 ||
+      op->eloc_stride < op->n1 * op->n1 || (op->n_slots > 0 && !op->slot_buf) ||
       (op->n_shared > 0 && (!op->shared_node || !op->shared_ptr || !op->shared_slot))) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
     return SEMK_ERR_INVALID;
@@ -465,6 +541,13 @@ int check_op(const semk_op *op, const char *who) {
 extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
   (void)n_shared;
   return n_patch + kSharedBlocks + 8;
+}
+
+extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_stride,
+                                         int64_t eloc_stride, int max_patch_nodes) {
+  return (int64_t)patch_smem_layout(n1 * n1, elems_per_patch, MODE_APPLY, g_stride, eloc_stride,
+                                    max_patch_nodes)
+      .total;
 }
 
 extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double *y, int flags,

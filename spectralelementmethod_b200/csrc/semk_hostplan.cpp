@@ -29,7 +29,8 @@ struct semk_hostplan {
   int pe = 0;
   int64_t n_elem = 0, n_nodes = 0;
   int64_t scalars[SEMK_PS_COUNT] = {0};
-  std::vector<int32_t> patch_node_ptr, patch_npriv, patch_slot_base, shared_ptr, shared_slot;
+  std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
+      shared_slot;
   std::vector<uint32_t> pnode, shared_node;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
@@ -54,6 +55,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     return SEMK_ERR_UNSUPPORTED;
   }
   const int NN = n1 * n1;
+  const int ES = (NN + 7) & ~7;  // eloc row stride (uint16): 16-byte multiples for TMA
   const int PE = elems_per_patch;
   if ((int64_t)PE * NN > 65535) {
     semk_set_error("semk_hostplan_create: patch too large for 16-bit local indices");
@@ -124,8 +126,9 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     // pass 2: per-patch tables
     P->patch_node_ptr.assign(n_patch + 1, 0);
     P->patch_npriv.assign(n_patch, 0);
+    P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
-    P->eloc.assign((size_t)n_slot_elems * NN, 0);
+    P->eloc.assign((size_t)n_slot_elems * ES, 0);
     P->elem_color.assign(n_slot_elems, 0);
     std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
     std::vector<uint32_t> priv, shar, colmask;
@@ -173,14 +176,17 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         semk_set_error("semk_hostplan_create: interface slot count overflows int32");
         return SEMK_ERR_UNSUPPORTED;
       }
+      // pad to a multiple of 4 entries: every patch's list starts 16-byte aligned (TMA)
+      while (P->pnode.size() & 3u) P->pnode.push_back(0xffffffffu);
       P->patch_node_ptr[p + 1] = (int32_t)P->pnode.size();
+      P->patch_nnodes[p] = np + ns;
       max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
 
       // element-local index table + greedy colouring
       colmask.assign(np + ns, 0u);
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
-        uint16_t *er = P->eloc.data() + (size_t)s * NN;
+        uint16_t *er = P->eloc.data() + (size_t)s * ES;
         uint32_t forbidden = 0;
         for (int k = 0; k < NN; ++k) {
           const int32_t loc = local_of[row[k]];
@@ -225,6 +231,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     P->scalars[SEMK_PS_MAX_PATCH_NODES] = max_patch_nodes;
     P->scalars[SEMK_PS_MAX_COLORS] = max_colors;
     P->scalars[SEMK_PS_N_SLOT_ELEMS] = n_slot_elems;
+    P->scalars[SEMK_PS_ELOC_STRIDE] = ES;
   } catch (const std::bad_alloc &) {
     delete P;
     semk_set_error("semk_hostplan_create: out of host memory");
@@ -260,6 +267,7 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_SHARED_NODE: return vec_ptr(plan->shared_node, n_bytes);
     case SEMK_PA_SHARED_PTR: return vec_ptr(plan->shared_ptr, n_bytes);
     case SEMK_PA_SHARED_SLOT: return vec_ptr(plan->shared_slot, n_bytes);
+    case SEMK_PA_PATCH_NNODES: return vec_ptr(plan->patch_nnodes, n_bytes);
     default: return nullptr;
   }
 }

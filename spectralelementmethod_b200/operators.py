@@ -36,9 +36,15 @@ def g_stride_of(n1):
     return nn3 + (nn3 & 1)          # even => 16-byte multiples for the TMA bulk copy
 
 
+def eloc_stride_of(n1):
+    return (n1 * n1 + 7) & ~7       # uint16 entries per element row (16-byte multiples)
+
+
 def patch_smem_bytes(n1, pe, max_patch_nodes):
-    nn = n1 * n1
-    return 16 + 8 * (pe * g_stride_of(n1) + 2 * max_patch_nodes + 2 * pe * nn + 32)
+    """Dynamic shared memory of one CTA of the apply kernel (asks the library,
+    which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
+    return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_stride_of(n1), eloc_stride_of(n1),
+                                                 int(max_patch_nodes)))
 
 
 def choose_elems_per_patch(n1):
@@ -144,7 +150,7 @@ class PoissonOperator(object):
 
         t = {}
         for k in (_lib.PA_PATCH_NODE_PTR, _lib.PA_PATCH_NPRIV, _lib.PA_PATCH_SLOT_BASE,
-                  _lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT):
+                  _lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT, _lib.PA_PATCH_NNODES):
             t[k] = torch.from_numpy(ar[k]).to(self.dev)
         for k in (_lib.PA_PNODE, _lib.PA_SHARED_NODE):
             t[k] = device.as_i32_bits(ar[k], self.dev)
@@ -201,6 +207,8 @@ class PoissonOperator(object):
         op.patch_node_ptr = t[_lib.PA_PATCH_NODE_PTR].data_ptr()
         op.pnode = t[_lib.PA_PNODE].data_ptr()
         op.patch_npriv = t[_lib.PA_PATCH_NPRIV].data_ptr()
+        op.patch_nnodes = t[_lib.PA_PATCH_NNODES].data_ptr()
+        op.eloc_stride = sc[_lib.PS_ELOC_STRIDE]
         op.patch_slot_base = t[_lib.PA_PATCH_SLOT_BASE].data_ptr()
         op.eloc = t[_lib.PA_ELOC].data_ptr()
         op.elem_color = t[_lib.PA_ELEM_COLOR].data_ptr()

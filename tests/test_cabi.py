@@ -42,8 +42,8 @@ def test_version_and_error_channel():
 
 
 def test_struct_layout_matches_header():
-    # 24 fields; 8-byte aligned pointers after two int32 pairs
-    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 6 * 8 + 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8
+    # 26 fields; 8-byte aligned pointers after two int32 pairs
+    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 8 * 8 + 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.semk_pcg_info) == 24
 
 
@@ -64,21 +64,27 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     pnode = ar[_lib.PA_PNODE]
     npriv = ar[_lib.PA_PATCH_NPRIV]
     base = ar[_lib.PA_PATCH_SLOT_BASE]
-    eloc = ar[_lib.PA_ELOC].reshape(-1, NN)
+    ES = sc[_lib.PS_ELOC_STRIDE]
+    assert ES % 8 == 0 and NN <= ES < NN + 8
+    eloc = ar[_lib.PA_ELOC].reshape(-1, ES)[:, :NN]
+    nnodes = ar[_lib.PA_PATCH_NNODES]
+    assert np.all(ptr % 4 == 0)
     color = ar[_lib.PA_ELEM_COLOR]
     eos = ar[_lib.PA_ELEM_OF_SLOT]
     assert sorted(eos.tolist()) == list(range(E))
+    pad = pnode == 0xFFFFFFFF
     ids = pnode & _lib.NODE_ID_MASK
-    shared_flag = (pnode & _lib.NODE_SHARED) != 0
-    dir_flag = (pnode & _lib.NODE_DIRICHLET) != 0
+    shared_flag = ((pnode & _lib.NODE_SHARED) != 0) & ~pad
+    dir_flag = ((pnode & _lib.NODE_DIRICHLET) != 0) & ~pad
     if dirichlet is not None:
-        assert np.array_equal(dir_flag, dirichlet[ids].astype(bool))
+        assert np.array_equal(dir_flag[~pad], dirichlet[ids[~pad]].astype(bool))
     else:
         assert not dir_flag.any()
     touched = np.zeros(n_nodes, dtype=int)
     slots_seen = 0
     for p in range(n_patch):
-        a, b = ptr[p], ptr[p + 1]
+        a, b = ptr[p], ptr[p] + nnodes[p]
+        assert np.all(pnode[b:ptr[p + 1]] == 0xFFFFFFFF) and ptr[p + 1] - b < 4
         loc_ids = ids[a:b]
         assert len(set(loc_ids.tolist())) == b - a
         assert not shared_flag[a:a + npriv[p]].any() and shared_flag[a + npriv[p]:b].all()
@@ -101,6 +107,7 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     # private <=> touched by exactly one patch
     is_shared_node = np.zeros(n_nodes, dtype=bool)
     is_shared_node[ids[shared_flag]] = True
+    assert sc[_lib.PS_N_PNODE] == pnode.size
     assert np.array_equal(is_shared_node, touched > 1)
     # CSR of interface slots: every slot exactly once, grouped under its node
     sn = ar[_lib.PA_SHARED_NODE]
@@ -112,7 +119,7 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     assert sorted(ss.tolist()) == list(range(slots_seen))
     slot_node = np.empty(slots_seen, dtype=np.int64)
     for p in range(n_patch):
-        a, b = ptr[p] + npriv[p], ptr[p + 1]
+        a, b = ptr[p] + npriv[p], ptr[p] + nnodes[p]
         slot_node[base[p]:base[p] + (b - a)] = ids[a:b]
     for i in range(sn.size):
         assert np.all(slot_node[ss[sp[i]:sp[i + 1]]] == (sn[i] & _lib.NODE_ID_MASK))
