@@ -78,7 +78,9 @@ enum semk_plan_array {
                                  each patch padded with 0xffffffff to a multiple of 4       */
   SEMK_PA_PATCH_NPRIV = 2,    /* int32  [n_patch]     number of private nodes of the patch   */
   SEMK_PA_PATCH_SLOT_BASE = 3,/* int32  [n_patch]     first interface slot of the patch      */
-  SEMK_PA_ELOC = 4,           /* uint16 [n_slot_elems][eloc_stride] patch-local node indices */
+  SEMK_PA_ELOC = 4,           /* uint16 [n_patch][eloc_patch_stride]: per patch a table
+                                 [m][le][t] (NN*PE entries) of patch-local node indices:
+                                 node (m,t) of the le-th element of the patch            */
   SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
   SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
   SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
@@ -96,7 +98,7 @@ enum semk_plan_scalar {
   SEMK_PS_MAX_PATCH_NODES = 4,
   SEMK_PS_MAX_COLORS = 5,
   SEMK_PS_N_SLOT_ELEMS = 6,   /* n_patch * elems_per_patch (last patch padded) */
-  SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per row of ELOC: NN rounded up to 8 */
+  SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per patch block of ELOC: NN*PE rounded up to 8 */
   SEMK_PS_COUNT = 8
 };
 
@@ -125,15 +127,19 @@ typedef struct semk_op {
   int64_t n_patch;
   int32_t max_patch_nodes;
   int32_t max_colors;
-  int64_t g_stride;         /* doubles between consecutive element slots of G (even) */
-  const double *G;          /* [n_slot_elems][g_stride]: G00[NN], G01[NN], G11[NN] per slot */
+  int64_t g_patch_stride;   /* doubles per patch block of G (even, >= 3*NN*PE)          */
+  const double *G;          /* [n_patch][g_patch_stride]; inside a patch block the factor
+                               c (0: G00, 1: G01, 2: G11) at node (m, t) of the le-th
+                               element sits at ((c*n1 + m)*PE + le)*n1 + t, i.e. rows of
+                               n1*PE doubles indexed by thread (le, t): coalesced, and
+                               bank-conflict free once staged in shared memory           */
   const int32_t *patch_node_ptr;
   const uint32_t *pnode;
   const int32_t *patch_npriv;
   const int32_t *patch_nnodes;
   const int32_t *patch_slot_base;
   const uint16_t *eloc;
-  int64_t eloc_stride;      /* uint16 entries per element row of eloc (multiple of 8) */
+  int64_t eloc_patch_stride;/* uint16 entries per patch block of eloc (multiple of 8)   */
   const uint8_t *elem_color;
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums (scratch)  */
@@ -149,8 +155,8 @@ typedef struct semk_op {
 /* number of doubles the `partials` scratch of an operator must hold */
 int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
 /* dynamic shared memory (bytes) one CTA of the apply kernel needs */
-int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_stride, int64_t eloc_stride,
-                              int max_patch_nodes);
+int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
+                              int64_t eloc_patch_stride, int max_patch_nodes);
 
 /* ------------------------------------------------------------------------
  * K1: geometric factors.  Replaces, per element, Mapping._compute_x_phys /
@@ -163,7 +169,9 @@ int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_stride, int
  * nodes_x/nodes_y: device [n_nodes] (rows of the reference's mesh.nodes);
  * l2g: device uint32 [n_elem][NN]; Einv, D: device [NN]; w: device [n1].
  * elem_of_slot: device int64 [n_elem] or NULL (identity).  Outputs are
- * optional (NULL = skip): G in engine slot order with stride g_stride;
+ * optional (NULL = skip): G in the engine's patch-interleaved layout (see
+ * semk_op.G) for patches of elems_per_patch slots and block stride
+ * g_patch_stride (the caller zero-fills the padding of a ragged last patch);
  * JxW [n_elem][NN], x_phys [n_elem][2][NN], J / invJ [n_elem][2][2][NN],
  * detJ [n_elem][NN] in the reference's element order and layouts.
  * bad_flag: device int32, set to 1 if any detJ <= 0 (caller zeroes it).
@@ -171,15 +179,16 @@ int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_stride, int
 int semk_geom_factors_f64(int n1, int64_t n_elem, const double *nodes_x, const double *nodes_y,
                           const uint32_t *l2g, const double *Einv, const double *D,
                           const double *w, const int64_t *elem_of_slot, double *G,
-                          int64_t g_stride, double *JxW, double *x_phys, double *J,
-                          double *invJ, double *detJ, int32_t *bad_flag, void *stream);
+                          int64_t g_patch_stride, int elems_per_patch, double *JxW,
+                          double *x_phys, double *J, double *invJ, double *detJ,
+                          int32_t *bad_flag, void *stream);
 
 /* G (engine slot layout) from externally supplied factors in the reference's
  * layouts: invJ [n_elem][2][2][NN] (fe.invJ) and JxW [n_elem][NN]
  * (fe.detJxW).  Parity tier T1. */
 int semk_gfactors_from_invj_f64(int n1, int64_t n_elem, const double *invJ, const double *JxW,
-                                const int64_t *elem_of_slot, double *G, int64_t g_stride,
-                                void *stream);
+                                const int64_t *elem_of_slot, double *G, int64_t g_patch_stride,
+                                int elems_per_patch, void *stream);
 
 /* ------------------------------------------------------------------------
  * K2: y = A u, the assembled Poisson stiffness operator, matrix-free.
@@ -199,7 +208,8 @@ int semk_poisson_apply_f64(const semk_op *op, const double *u, double *y, int fl
  * bit).  Kept as the independent cross-check of the patch kernel.
  * l2g: device uint32 [n_elem][NN]; dirichlet: device uint8 [n_nodes] or NULL. */
 int semk_poisson_apply_atomic_f64(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
-                                  const int64_t *elem_of_slot, const double *G, int64_t g_stride,
+                                  const int64_t *elem_of_slot, const double *G,
+                                  int64_t g_patch_stride, int elems_per_patch,
                                   const double *D_host, const uint8_t *dirichlet,
                                   const double *u, double *y, int flags, void *stream);
 
@@ -221,8 +231,9 @@ int semk_assemble_f64(const semk_op *op, const double *loc, double *out, int fla
 
 /* K5: element-local diagonal of the stiffness matrix, diag[p,q] = L[p,q,p,q]
  * (SURVEY.md appendix C closed form), written to loc [n_slot_elems][NN] in
- * engine slot order; assemble with semk_assemble_f64. */
-int semk_poisson_local_diag_f64(const semk_op *op, double *loc, void *stream);
+ * engine slot order; assemble with semk_assemble_f64.  D_dev: device [NN]. */
+int semk_poisson_local_diag_f64(const semk_op *op, const double *D_dev, double *loc,
+                                void *stream);
 
 /* RHS/mass: loc[slot][k] = JxW[elem][k] * f[l2g[elem][k]]  (f NULL = 1, the
  * reference's rhs = JxW, examples/poisson.py:200).  JxW in reference element

@@ -48,10 +48,10 @@ class semk_op(C.Structure):
         ("n1", C.c_int32), ("elems_per_patch", C.c_int32),
         ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
         ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
-        ("g_stride", C.c_int64), ("G", C.c_void_p),
+        ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
         ("patch_node_ptr", C.c_void_p), ("pnode", C.c_void_p), ("patch_npriv", C.c_void_p),
         ("patch_nnodes", C.c_void_p),
-        ("patch_slot_base", C.c_void_p), ("eloc", C.c_void_p), ("eloc_stride", C.c_int64),
+        ("patch_slot_base", C.c_void_p), ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
         ("elem_color", C.c_void_p),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
@@ -78,14 +78,15 @@ SIGNATURES = {
     "semk_hostplan_destroy": (None, [_P]),
     "semk_partials_len": (_L, [_L, _L]),
     "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _I]),
-    "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P,
-                                   _P, _P, _P]),
-    "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _P]),
+    "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P,
+                                   _P, _P, _P, _P]),
+    "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _I, _P]),
     "semk_poisson_apply_f64": (_I, [C.POINTER(semk_op), _P, _P, _I, _P, _P]),
-    "semk_poisson_apply_atomic_f64": (_I, [_I, _L, _L, _P, _P, _P, _L, _P, _P, _P, _P, _I, _P]),
+    "semk_poisson_apply_atomic_f64": (_I, [_I, _L, _L, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I,
+                                           _P]),
     "semk_poisson_apply_host_f64": (_I, [C.POINTER(semk_op), _P, _P, _P, _P, _I, _P]),
     "semk_assemble_f64": (_I, [C.POINTER(semk_op), _P, _P, _I, _D, _P]),
-    "semk_poisson_local_diag_f64": (_I, [C.POINTER(semk_op), _P, _P]),
+    "semk_poisson_local_diag_f64": (_I, [C.POINTER(semk_op), _P, _P, _P]),
     "semk_weighted_local_f64": (_I, [_I, _L, _L, _P, _P, _P, _P, _P, _P]),
     "semk_vec_partials_len": (_L, [_L]),
     "semk_pcg_init_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

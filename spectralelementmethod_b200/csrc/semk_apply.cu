@@ -34,70 +34,81 @@
 
 namespace {
 
-// Differentiation matrix of the order currently in use, row-major [N][N].
-__constant__ double cD[SEMK_MAX_N1 * SEMK_MAX_N1];
-double g_hostD[SEMK_MAX_N1 * SEMK_MAX_N1];
-int g_hostD_n1 = 0;
+// Differentiation matrix, row-major [N][N], passed BY VALUE as a kernel
+// parameter: the entries live in the parameter constant bank and every use
+// below has a compile-time index, so the DFMAs read them through uniform
+// registers (LDCU.128) -- no shared memory, no per-thread registers.
+struct DMat {
+  double v[SEMK_MAX_N1 * SEMK_MAX_N1];
+};
 
-int upload_D(int n1, const double *D_host, cudaStream_t st) {
-  const size_t bytes = sizeof(double) * n1 * n1;
-  if (g_hostD_n1 == n1 && std::memcmp(g_hostD, D_host, bytes) == 0) return SEMK_OK;
-  std::memcpy(g_hostD, D_host, bytes);
-  g_hostD_n1 = n1;
-  // stream-ordered: kernels already queued keep the old table
-  SEMK_CUDA_CHECK(cudaMemcpyToSymbolAsync(cD, g_hostD, bytes, 0, cudaMemcpyHostToDevice, st));
-  return SEMK_OK;
+DMat make_dmat(int n1, const double *D_host) {
+  DMat d;
+  std::memset(&d, 0, sizeof(d));
+  std::memcpy(d.v, D_host, sizeof(double) * n1 * n1);
+  return d;
 }
 
 // out[i] = sum_k D[i][k] v[k]      (derivative along the in-thread axis)
 template <int N>
-__device__ __forceinline__ void apply_D(const double (&v)[N], double (&out)[N]) {
+__device__ __forceinline__ void apply_D(const DMat &dm, const double (&v)[N], double (&out)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc = fma(cD[i * N + k], v[k], acc);
+    for (int k = 0; k < N; ++k) acc = fma(dm.v[i * N + k], v[k], acc);
     out[i] = acc;
   }
 }
 // out[i] = sum_k D[k][i] v[k]      (transpose: the weak-form "test" side)
 template <int N>
-__device__ __forceinline__ void apply_Dt(const double (&v)[N], double (&out)[N]) {
+__device__ __forceinline__ void apply_Dt(const DMat &dm, const double (&v)[N], double (&out)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc = fma(cD[k * N + i], v[k], acc);
+    for (int k = 0; k < N; ++k) acc = fma(dm.v[k * N + i], v[k], acc);
     out[i] = acc;
   }
 }
 
+// Row stride of the CTA-wide transpose scratch: N*PE columns (one per thread)
+// padded so that RS == 1 (mod 16).  With 8-byte words and 16 bank pairs both
+// access patterns of a half-warp are then conflict-free:
+//   column pattern  A[m*RS + tidp]          -> bank = const + tidp
+//   row pattern     A[t*RS + le*N + s]      -> bank = const + t + le*N = const + tidp
+__host__ __device__ constexpr int scratch_row_stride(int N, int PE) {
+  return ((N * PE - 1 + 15) & ~15) + 1;
+}
+
 // The element-local operator for one column-owning thread.
-//   ucol[m] = u[m][t] on entry;  ycol[m] = y[m][t] on exit.
-//   A, B: this element's two N*N shared scratch arrays.
-//   g: this element's G block in shared or global memory (G00, G01, G11);
-//   g_ready: mbarrier guarding a TMA-staged g (nullptr when g is in global).
+//   tidp = le*N + t identifies (element-in-CTA, column);  ucol[m] = u[m][t] on
+//   entry, ycol[m] = y[m][t] on exit.
+//   A, B: CTA-wide scratch, N rows of RS doubles.
+//   g: this thread's column base inside the patch's G block; the factor
+//      (c, m) of this column sits at g[(c*N + m) * g_row].
+//   g_ready: mbarrier guarding a TMA-staged G (nullptr when g is global).
 // Contains four __syncthreads(); every thread of the CTA must call it.
-template <int N>
-__device__ __forceinline__ void local_poisson(int t, bool active, const double (&ucol)[N],
-                                              double (&ycol)[N], double *__restrict__ A,
-                                              double *__restrict__ B,
-                                              const double *__restrict__ g,
-                                              uint64_t *g_ready = nullptr) {
-  constexpr int NN = N * N;
+template <int N, int RS>
+__device__ __forceinline__ void local_poisson(const DMat &dm, int le, int t, bool active,
+                                              const double (&ucol)[N], double (&ycol)[N],
+                                              double *__restrict__ A, double *__restrict__ B,
+                                              const double *__restrict__ g, int g_row,
+                                              uint64_t *g_ready) {
+  const int tidp = le * N + t;
   double ur[N], tmp[N], us[N];
   if (active) {
 #pragma unroll
-    for (int m = 0; m < N; ++m) A[m * N + t] = ucol[m];
+    for (int m = 0; m < N; ++m) A[m * RS + tidp] = ucol[m];
   }
   __syncthreads();
   if (active) {
-    apply_D<N>(ucol, ur);  // ur[m][t] = sum_r D[m][r] u[r][t]
+    apply_D<N>(dm, ucol, ur);  // ur[m][t] = sum_r D[m][r] u[r][t]
 #pragma unroll
-    for (int s = 0; s < N; ++s) tmp[s] = A[t * N + s];  // row t of u
-    apply_D<N>(tmp, us);                                // us[t][n] = sum_s D[n][s] u[t][s]
+    for (int s = 0; s < N; ++s) tmp[s] = A[t * RS + le * N + s];  // row t of u
+    apply_D<N>(dm, tmp, us);                                      // us[t][n] = sum_s D[n][s] u[t][s]
 #pragma unroll
-    for (int n = 0; n < N; ++n) B[t * N + n] = us[n];
+    for (int n = 0; n < N; ++n) B[t * RS + le * N + n] = us[n];
   }
   __syncthreads();
   // G staged by TMA: every thread observes the mbarrier phase itself (acquire)
@@ -106,34 +117,34 @@ __device__ __forceinline__ void local_poisson(int t, bool active, const double (
   if (active) {
 #pragma unroll
     for (int m = 0; m < N; ++m) {
-      const double usc = B[m * N + t];  // us[m][t]
-      const double g00 = g[m * N + t], g01 = g[NN + m * N + t], g11 = g[2 * NN + m * N + t];
+      const double usc = B[m * RS + tidp];  // us[m][t]
+      const double g00 = g[m * g_row], g01 = g[(N + m) * g_row], g11 = g[(2 * N + m) * g_row];
       tmp[m] = g00 * ur[m] + g01 * usc;  // w0[m][t]
       w1[m] = g01 * ur[m] + g11 * usc;   // w1[m][t]
     }
-    apply_Dt<N>(tmp, ycol);  // y0[p][t] = sum_m D[m][p] w0[m][t]
+    apply_Dt<N>(dm, tmp, ycol);  // y0[p][t] = sum_m D[m][p] w0[m][t]
 #pragma unroll
-    for (int m = 0; m < N; ++m) A[m * N + t] = w1[m];
+    for (int m = 0; m < N; ++m) A[m * RS + tidp] = w1[m];
   }
   __syncthreads();
   if (active) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) tmp[n] = A[t * N + n];  // row t of w1
-    apply_Dt<N>(tmp, us);                               // y1[t][q] = sum_n w1[t][n] D[n][q]
+    for (int n = 0; n < N; ++n) tmp[n] = A[t * RS + le * N + n];  // row t of w1
+    apply_Dt<N>(dm, tmp, us);                                     // y1[t][q] = sum_n w1[t][n] D[n][q]
 #pragma unroll
-    for (int q = 0; q < N; ++q) B[t * N + q] = us[q];
+    for (int q = 0; q < N; ++q) B[t * RS + le * N + q] = us[q];
   }
   __syncthreads();
   if (active) {
 #pragma unroll
-    for (int m = 0; m < N; ++m) ycol[m] += B[m * N + t];
+    for (int m = 0; m < N; ++m) ycol[m] += B[m * RS + tidp];
   }
 }
 
 template <int N, int PE>
 struct PatchCfg {
-  static constexpr int NN = N * N;
   static constexpr int kThreads = ((N * PE + 31) / 32) * 32;
+  static constexpr int kRS = scratch_row_stride(N, PE);
 };
 
 enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
@@ -142,20 +153,22 @@ enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 struct PatchSmem {
   size_t gs, pn, el, yp, ua, bs, red, total;
 };
-__host__ __device__ inline PatchSmem patch_smem_layout(int NN, int PE, int mode, int64_t g_stride,
-                                                       int64_t eloc_stride, int max_patch_nodes) {
+__host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
+                                                       int64_t g_patch_stride,
+                                                       int64_t eloc_patch_stride,
+                                                       int max_patch_nodes) {
   PatchSmem L;
   const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
-  const size_t scratch = (size_t)PE * NN;
+  const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
   size_t o = 16;  // two mbarriers
   L.gs = o;
-  o += (mode == MODE_APPLY) ? sizeof(double) * PE * (size_t)g_stride : 0;
+  o += (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
   L.pn = o;
   o += 4 * mpn4;
   L.el = o;
-  o += 2 * (size_t)PE * (size_t)eloc_stride;
+  o += 2 * (size_t)eloc_patch_stride;
   L.yp = o;
-  o += 8 * (mpn4 + (mpn4 & 1));
+  o += 8 * mpn4;
   o = (o + 15) & ~(size_t)15;
   L.ua = o;  // u staging, later scratch A
   o += (mode == MODE_APPLY) ? 8 * (mpn4 > scratch ? mpn4 : scratch) : 0;
@@ -175,14 +188,16 @@ constexpr int kGatherBatch = 8;
 // MODE_ASSEMBLE: y = assembly of the element-local field `loc` (slot order).
 template <int N, int PE, int MODE>
 __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
-    patch_kernel(semk_op op, const double *__restrict__ u, const double *__restrict__ loc,
-                 double *__restrict__ y, int flags, double fill_dirichlet,
-                 double *__restrict__ dot_partials) {
+    patch_kernel(semk_op op, DMat dm, const double *__restrict__ u,
+                 const double *__restrict__ loc, double *__restrict__ y, int flags,
+                 double fill_dirichlet, double *__restrict__ dot_partials) {
   constexpr int NN = N * N;
+  constexpr int NP = N * PE;
   constexpr int kThreads = PatchCfg<N, PE>::kThreads;
+  constexpr int RS = PatchCfg<N, PE>::kRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const PatchSmem L =
-      patch_smem_layout(NN, PE, MODE, op.g_stride, op.eloc_stride, op.max_patch_nodes);
+  const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.eloc_patch_stride,
+                                        op.max_patch_nodes);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0]: tables, [1]: G
   double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
   uint32_t *pn_s = reinterpret_cast<uint32_t *>(smem_raw + L.pn);
@@ -197,9 +212,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   const int64_t patch = blockIdx.x;
   const int64_t slot0 = patch * PE;
   const int le = tid / N, t = tid - le * N;
-  const int lec = le < PE ? le : 0;
   const bool active = (le < PE) && (slot0 + le < op.n_elem);
-  const int ES = (int)op.eloc_stride;
 
   // ---- stage the patch's tables (and geometric factors) with the TMA engine ----
   const int n0 = op.patch_node_ptr[patch];
@@ -208,14 +221,14 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
     semk_mbar_init(&mbar[1], 1);
     semk_fence_mbar_init();
     const uint32_t pn_bytes = 4u * (uint32_t)(op.patch_node_ptr[patch + 1] - n0);
-    const uint32_t el_bytes = 2u * (uint32_t)(PE * ES);
+    const uint32_t el_bytes = 2u * (uint32_t)op.eloc_patch_stride;
     semk_mbar_expect_tx(&mbar[0], pn_bytes + el_bytes);
     semk_bulk_g2s(pn_s, op.pnode + n0, pn_bytes, &mbar[0]);
-    semk_bulk_g2s(el_s, op.eloc + slot0 * ES, el_bytes, &mbar[0]);
+    semk_bulk_g2s(el_s, op.eloc + patch * op.eloc_patch_stride, el_bytes, &mbar[0]);
     if (MODE == MODE_APPLY) {
-      const uint32_t g_bytes = (uint32_t)(PE * op.g_stride * sizeof(double));
+      const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
       semk_mbar_expect_tx(&mbar[1], g_bytes);
-      semk_bulk_g2s(Gs, op.G + slot0 * op.g_stride, g_bytes, &mbar[1]);
+      semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[1]);
     }
   }
   const int npn = op.patch_nnodes[patch];
@@ -255,12 +268,11 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       }
     }
   }
-  // element-local index column (from the staged table)
+  // this thread's column of patch-local node indices (table rows are [m][le][t])
   uint16_t idx[N];
   if (active) {
-    const uint16_t *er = el_s + lec * ES;
 #pragma unroll
-    for (int m = 0; m < N; ++m) idx[m] = er[m * N + t];
+    for (int m = 0; m < N; ++m) idx[m] = el_s[m * NP + tid];
   }
   __syncthreads();
 
@@ -272,8 +284,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
     }
     __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
-    local_poisson<N>(t, active, ucol, ycol, As + lec * NN, Bs + lec * NN,
-                     Gs + lec * op.g_stride, &mbar[1]);
+    local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[1]);
   } else {
     if (active) {
       const double *lr = loc + (slot0 + le) * NN;
@@ -303,7 +314,6 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       double uin = 0.0;
       if (MODE == MODE_APPLY) {
         if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
-        if (dir && (flags & SEMK_MASK_IN)) uin = (flags & SEMK_MASK_OUT) ? uin : 0.0;
       }
       if (dir && (flags & SEMK_MASK_OUT)) {
         if (MODE == MODE_APPLY) {
@@ -377,23 +387,27 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) out[0] = s;
 }
 
-constexpr int kSharedBlocks = 148 * 64;   // upper bound on shared_nodes_kernel CTAs
+constexpr int kSharedBlocks = 148 * 64;  // upper bound on shared_nodes_kernel CTAs
 
 // ---- simple atomic-scatter kernel (independent cross-check) -------------------
-template <int N, int PE>
-__global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
-    atomic_kernel(int64_t n_elem, const uint32_t *__restrict__ l2g,
+// Groups PEA consecutive element slots per CTA; reads the L2G map and the
+// patch-interleaved G straight from global memory.
+template <int N, int PEA>
+__global__ void __launch_bounds__(PatchCfg<N, PEA>::kThreads)
+    atomic_kernel(DMat dm, int64_t n_elem, const uint32_t *__restrict__ l2g,
                   const int64_t *__restrict__ elem_of_slot, const double *__restrict__ G,
-                  int64_t g_stride, const uint8_t *__restrict__ dirichlet,
+                  int64_t g_patch_stride, int pe_plan, const uint8_t *__restrict__ dirichlet,
                   const double *__restrict__ u, double *__restrict__ y, int flags) {
   constexpr int NN = N * N;
-  __shared__ double As[PE * NN], Bs[PE * NN];
+  constexpr int RS = PatchCfg<N, PEA>::kRS;
+  __shared__ double As[N * RS], Bs[N * RS];
   const int tid = threadIdx.x;
   const int le = tid / N, t = tid - le * N;
-  const int64_t slot = (int64_t)blockIdx.x * PE + le;
-  const bool active = (le < PE) && (slot < n_elem);
+  const int64_t slot = (int64_t)blockIdx.x * PEA + le;
+  const bool active = (le < PEA) && (slot < n_elem);
   double ucol[N], ycol[N];
   uint32_t gid[N];
+  const double *g = G;
   if (active) {
     const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
     const uint32_t *row = l2g + e * NN;
@@ -404,10 +418,12 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       if (dirichlet && (flags & SEMK_MASK_IN) && dirichlet[gid[m]]) v = 0.0;
       ucol[m] = v;
     }
+    const int64_t patch = slot / pe_plan;
+    const int lp = (int)(slot - patch * pe_plan);
+    g = G + patch * g_patch_stride + lp * N + t;
   }
-  const int lec = le < PE ? le : 0;
-  local_poisson<N>(t, active, ucol, ycol, As + lec * NN, Bs + lec * NN,
-                   G + (active ? slot : 0) * g_stride);
+  local_poisson<N, RS>(dm, le < PEA ? le : 0, t, active, ucol, ycol, As, Bs, g, N * pe_plan,
+                       nullptr);
   if (active) {
 #pragma unroll
     for (int m = 0; m < N; ++m) atomicAdd(y + gid[m], ycol[m]);
@@ -425,21 +441,25 @@ __global__ void dirichlet_fix_kernel(int64_t n, const uint8_t *__restrict__ diri
 // ---- K5: element-local diagonal ------------------------------------------------
 // diag[p][q] = sum_m G00[m][q] D[m][p]^2 + 2 G01[p][q] D[p][p] D[q][q]
 //            + sum_n G11[p][n] D[n][q]^2
-__global__ void local_diag_kernel(int n1, int64_t n_slot_elems, const double *__restrict__ G,
-                                  int64_t g_stride, double *__restrict__ loc) {
+__global__ void local_diag_kernel(int n1, int pe, int64_t n_slot_elems,
+                                  const double *__restrict__ G, int64_t g_patch_stride,
+                                  const double *__restrict__ D, double *__restrict__ loc) {
   const int NN = n1 * n1;
+  const int NP = n1 * pe;
   const int64_t total = n_slot_elems * NN;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t slot = i / NN;
     const int k = (int)(i - slot * NN);
     const int p = k / n1, q = k - p * n1;
-    const double *g = G + slot * g_stride;
-    double acc = 2.0 * g[NN + k] * cD[p * n1 + p] * cD[q * n1 + q];
+    const int64_t patch = slot / pe;
+    const int lp = (int)(slot - patch * pe);
+    const double *g = G + patch * g_patch_stride + lp * n1;  // + (c*n1 + m)*NP + n
+    double acc = 2.0 * g[(n1 + p) * NP + q] * D[p * n1 + p] * D[q * n1 + q];
     for (int m = 0; m < n1; ++m) {
-      const double d0 = cD[m * n1 + p], d1 = cD[m * n1 + q];
-      acc = fma(g[m * n1 + q], d0 * d0, acc);
-      acc = fma(g[2 * NN + p * n1 + m], d1 * d1, acc);
+      const double d0 = D[m * n1 + p], d1 = D[m * n1 + q];
+      acc = fma(g[m * NP + q], d0 * d0, acc);
+      acc = fma(g[(2 * n1 + p) * NP + m], d1 * d1, acc);
     }
     loc[i] = acc;
   }
@@ -464,11 +484,11 @@ __global__ void weighted_local_kernel(int NN, int64_t n_elem, const double *__re
 template <int PE, int MODE>
 struct PatchLaunch {
   template <int N>
-  static int run(const semk_op &op, const double *u, const double *loc, double *y, int flags,
-                 double fill, double *partials, cudaStream_t st) {
-    constexpr int NN = N * N;
-    const size_t smem =
-        patch_smem_layout(NN, PE, MODE, op.g_stride, op.eloc_stride, op.max_patch_nodes).total;
+  static int run(const semk_op &op, const DMat &dm, const double *u, const double *loc,
+                 double *y, int flags, double fill, double *partials, cudaStream_t st) {
+    const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.eloc_patch_stride,
+                                          op.max_patch_nodes)
+                            .total;
     auto kern = patch_kernel<N, PE, MODE>;
     if (smem > 227 * 1024) {
       semk_set_error("patch kernel: shared memory request exceeds 227 KB");
@@ -480,29 +500,29 @@ struct PatchLaunch {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    kern<<<(unsigned)op.n_patch, PatchCfg<N, PE>::kThreads, smem, st>>>(op, u, loc, y, flags, fill,
-                                                                      partials);
+    kern<<<(unsigned)op.n_patch, PatchCfg<N, PE>::kThreads, smem, st>>>(op, dm, u, loc, y, flags,
+                                                                      fill, partials);
     SEMK_LAUNCH_CHECK("patch_kernel");
     return SEMK_OK;
   }
 };
 
-// elements per patch supported by the compiled kernels, per order
+// elements per patch supported by the compiled kernels
 inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16; }
 
 template <int MODE>
-int launch_patch(const semk_op &op, const double *u, const double *loc, double *y, int flags,
-                 double fill, double *partials, cudaStream_t st) {
-#define SEMK_CALL(NV)                                                                         \
-  do {                                                                                        \
-    int rc;                                                                                   \
-    if (op.elems_per_patch == 16)                                                             \
-      rc = PatchLaunch<16, MODE>::template run<NV>(op, u, loc, y, flags, fill, partials, st); \
-    else if (op.elems_per_patch == 8)                                                         \
-      rc = PatchLaunch<8, MODE>::template run<NV>(op, u, loc, y, flags, fill, partials, st);  \
-    else                                                                                      \
-      rc = PatchLaunch<4, MODE>::template run<NV>(op, u, loc, y, flags, fill, partials, st);  \
-    if (rc != SEMK_OK) return rc;                                                             \
+int launch_patch(const semk_op &op, const DMat &dm, const double *u, const double *loc,
+                 double *y, int flags, double fill, double *partials, cudaStream_t st) {
+#define SEMK_CALL(NV)                                                                     \
+  do {                                                                                    \
+    int rc;                                                                               \
+    if (op.elems_per_patch == 16)                                                         \
+      rc = PatchLaunch<16, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st); \
+    else if (op.elems_per_patch == 8)                                                     \
+      rc = PatchLaunch<8, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st);  \
+    else                                                                                  \
+      rc = PatchLaunch<4, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st);  \
+    if (rc != SEMK_OK) return rc;                                                         \
   } while (0)
   SEMK_DISPATCH_N1(op.n1, SEMK_CALL)
 #undef SEMK_CALL
@@ -522,15 +542,18 @@ int check_op(const semk_op *op, const char *who) {
     semk_set_error(std::string(who) + ": elems_per_patch must be 4, 8 or 16");
     return SEMK_ERR_UNSUPPORTED;
   }
+  const int64_t nnp = (int64_t)op->n1 * op->n1 * op->elems_per_patch;
   if (!op->patch_node_ptr || !op->pnode || !op->patch_npriv || !op->patch_nnodes ||
-      !op->patch_slot_base || !op->eloc || !op->elem_color || (op->eloc_stride & 7) != 0 ||
-      op->eloc_stride < op->n1 * op->n1 || (op->n_slots > 0 && !op->slot_buf) ||
+      !op->patch_slot_base || !op->eloc || !op->elem_color ||
+      (op->eloc_patch_stride & 7) != 0 || op->eloc_patch_stride < nnp ||
+      (op->n_slots > 0 && !op->slot_buf) ||
       (op->n_shared > 0 && (!op->shared_node || !op->shared_ptr || !op->shared_slot))) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
     return SEMK_ERR_INVALID;
   }
-  if ((op->g_stride & 1) != 0) {
-    semk_set_error(std::string(who) + ": g_stride must be even (16-byte TMA granularity)");
+  if ((op->g_patch_stride & 1) != 0 || op->g_patch_stride < 3 * nnp) {
+    semk_set_error(std::string(who) +
+                   ": g_patch_stride must be even (16-byte TMA granularity) and >= 3*NN*PE");
     return SEMK_ERR_INVALID;
   }
   return SEMK_OK;
@@ -543,10 +566,10 @@ extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
   return n_patch + kSharedBlocks + 8;
 }
 
-extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_stride,
-                                         int64_t eloc_stride, int max_patch_nodes) {
-  return (int64_t)patch_smem_layout(n1 * n1, elems_per_patch, MODE_APPLY, g_stride, eloc_stride,
-                                    max_patch_nodes)
+extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
+                                         int64_t eloc_patch_stride, int max_patch_nodes) {
+  return (int64_t)patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
+                                    eloc_patch_stride, max_patch_nodes)
       .total;
 }
 
@@ -558,10 +581,9 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
   SEMK_REQUIRE(op->G && op->D_host, "semk_poisson_apply_f64: missing G or D");
   SEMK_REQUIRE(!dot_out || op->partials, "semk_poisson_apply_f64: dot_out needs op->partials");
   cudaStream_t st = semk_stream(stream);
-  rc = upload_D(op->n1, op->D_host, st);
-  if (rc != SEMK_OK) return rc;
+  const DMat dm = make_dmat(op->n1, op->D_host);
   double *partials = dot_out ? op->partials : nullptr;
-  rc = launch_patch<MODE_APPLY>(*op, u, nullptr, y, flags, 0.0, partials, st);
+  rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, partials, st);
   if (rc != SEMK_OK) return rc;
   int shared_blocks = 0;
   if (op->n_shared > 0) {
@@ -584,7 +606,9 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
   if (rc != SEMK_OK) return rc;
   SEMK_REQUIRE(loc && out, "semk_assemble_f64: null pointer");
   cudaStream_t st = semk_stream(stream);
-  rc = launch_patch<MODE_ASSEMBLE>(*op, nullptr, loc, out, flags, fill_dirichlet, nullptr, st);
+  DMat dm;
+  std::memset(&dm, 0, sizeof(dm));
+  rc = launch_patch<MODE_ASSEMBLE>(*op, dm, nullptr, loc, out, flags, fill_dirichlet, nullptr, st);
   if (rc != SEMK_OK) return rc;
   if (op->n_shared > 0) {
     const int64_t want = (op->n_shared + 255) / 256;
@@ -596,18 +620,18 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
   return SEMK_OK;
 }
 
-extern "C" int semk_poisson_local_diag_f64(const semk_op *op, double *loc, void *stream) {
+extern "C" int semk_poisson_local_diag_f64(const semk_op *op, const double *D_dev, double *loc,
+                                           void *stream) {
   int rc = check_op(op, "semk_poisson_local_diag_f64");
   if (rc != SEMK_OK) return rc;
-  SEMK_REQUIRE(loc && op->G && op->D_host, "semk_poisson_local_diag_f64: null pointer");
+  SEMK_REQUIRE(loc && op->G && D_dev, "semk_poisson_local_diag_f64: null pointer");
   cudaStream_t st = semk_stream(stream);
-  rc = upload_D(op->n1, op->D_host, st);
-  if (rc != SEMK_OK) return rc;
   const int64_t n_slot_elems = op->n_patch * op->elems_per_patch;
   const int64_t total = n_slot_elems * op->n1 * op->n1;
   const int64_t want = (total + 255) / 256;
   const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-  local_diag_kernel<<<grid, 256, 0, st>>>(op->n1, n_slot_elems, op->G, op->g_stride, loc);
+  local_diag_kernel<<<grid, 256, 0, st>>>(op->n1, op->elems_per_patch, n_slot_elems, op->G,
+                                          op->g_patch_stride, D_dev, loc);
   SEMK_LAUNCH_CHECK("local_diag_kernel");
   return SEMK_OK;
 }
@@ -635,22 +659,23 @@ extern "C" int semk_weighted_local_f64(int n1, int64_t n_elem, int64_t n_slot_el
 
 extern "C" int semk_poisson_apply_atomic_f64(int n1, int64_t n_elem, int64_t n_nodes,
                                              const uint32_t *l2g, const int64_t *elem_of_slot,
-                                             const double *G, int64_t g_stride,
-                                             const double *D_host, const uint8_t *dirichlet,
-                                             const double *u, double *y, int flags,
-                                             void *stream) {
+                                             const double *G, int64_t g_patch_stride,
+                                             int elems_per_patch, const double *D_host,
+                                             const uint8_t *dirichlet, const double *u, double *y,
+                                             int flags, void *stream) {
   SEMK_REQUIRE(l2g && G && D_host && u && y && u != y,
                "semk_poisson_apply_atomic_f64: null or aliased pointer");
-  SEMK_REQUIRE(n_elem > 0 && n_nodes > 0, "semk_poisson_apply_atomic_f64: empty problem");
+  SEMK_REQUIRE(n_elem > 0 && n_nodes > 0 && elems_per_patch > 0,
+               "semk_poisson_apply_atomic_f64: empty problem");
+  SEMK_REQUIRE(n1 >= 2 && n1 <= SEMK_MAX_N1, "semk_poisson_apply_atomic_f64: bad n1");
   cudaStream_t st = semk_stream(stream);
-  int rc = upload_D(n1, D_host, st);
-  if (rc != SEMK_OK) return rc;
+  const DMat dm = make_dmat(n1, D_host);
   SEMK_CUDA_CHECK(cudaMemsetAsync(y, 0, sizeof(double) * n_nodes, st));
-  constexpr int PE = 8;
-  const unsigned grid = (unsigned)((n_elem + PE - 1) / PE);
+  constexpr int PEA = 8;
+  const unsigned grid = (unsigned)((n_elem + PEA - 1) / PEA);
 #define SEMK_CALL(NV)                                                                       \
-  atomic_kernel<NV, PE><<<grid, PatchCfg<NV, PE>::kThreads, 0, st>>>(                       \
-      n_elem, l2g, elem_of_slot, G, g_stride, dirichlet, u, y, flags)
+  atomic_kernel<NV, PEA><<<grid, PatchCfg<NV, PEA>::kThreads, 0, st>>>(                     \
+      dm, n_elem, l2g, elem_of_slot, G, g_patch_stride, elems_per_patch, dirichlet, u, y, flags)
   SEMK_DISPATCH_N1(n1, SEMK_CALL)
 #undef SEMK_CALL
   SEMK_LAUNCH_CHECK("atomic_kernel");

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(((N * N + 31) / 32) * 32)
                 const double *__restrict__ nodes_y, const uint32_t *__restrict__ l2g,
                 const double *__restrict__ Einv, const double *__restrict__ D,
                 const double *__restrict__ w, const int64_t *__restrict__ elem_of_slot,
-                double *__restrict__ G, int64_t g_stride, double *__restrict__ JxW,
+                double *__restrict__ G, int64_t g_patch_stride, int pe,
+                double *__restrict__ JxW,
                 double *__restrict__ x_phys, double *__restrict__ Jout,
                 double *__restrict__ invJout, double *__restrict__ detJout,
                 int32_t *__restrict__ bad_flag) {
@@ -95,10 +96,14 @@ __global__ void __launch_bounds__(((N * N + 31) / 32) * 32)
       const double i10 = __dmul_rn(-j10, rdet), i11 = __dmul_rn(j00, rdet);
       const double jw = __dmul_rn(__dmul_rn(det, sw[m]), sw[n]);
       if (G) {
-        double *gs = G + slot * g_stride;
-        gs[k] = jw * (i00 * i00 + i01 * i01);
-        gs[NN + k] = jw * (i00 * i10 + i01 * i11);
-        gs[2 * NN + k] = jw * (i10 * i10 + i11 * i11);
+        // patch-interleaved layout: ((c*N + m)*PE + le)*N + n inside the patch block
+        const int64_t patch = slot / pe;
+        const int lp = (int)(slot - patch * pe);
+        const int64_t grow = (int64_t)N * pe;
+        double *gs = G + patch * g_patch_stride + (int64_t)m * grow + lp * N + n;
+        gs[0] = jw * (i00 * i00 + i01 * i01);
+        gs[N * grow] = jw * (i00 * i10 + i01 * i11);
+        gs[2 * N * grow] = jw * (i10 * i10 + i11 * i11);
       }
       if (JxW) JxW[e * NN + k] = jw;
       if (detJout) detJout[e * NN + k] = det;
@@ -125,11 +130,13 @@ __global__ void __launch_bounds__(((N * N + 31) / 32) * 32)
 }
 
 // G from the reference's own invJ / detJxW arrays (parity tier T1).
-__global__ void gfactors_from_invj_kernel(int NN, int64_t n_elem,
+__global__ void gfactors_from_invj_kernel(int n1, int64_t n_elem,
                                           const double *__restrict__ invJ,
                                           const double *__restrict__ JxW,
                                           const int64_t *__restrict__ elem_of_slot,
-                                          double *__restrict__ G, int64_t g_stride) {
+                                          double *__restrict__ G, int64_t g_patch_stride,
+                                          int pe) {
+  const int NN = n1 * n1;
   const int64_t total = n_elem * NN;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -139,10 +146,14 @@ __global__ void gfactors_from_invj_kernel(int NN, int64_t n_elem,
     const double *ip = invJ + e * 4 * NN;
     const double i00 = ip[k], i01 = ip[NN + k], i10 = ip[2 * NN + k], i11 = ip[3 * NN + k];
     const double jw = JxW[e * NN + k];
-    double *gs = G + slot * g_stride;
-    gs[k] = jw * (i00 * i00 + i01 * i01);
-    gs[NN + k] = jw * (i00 * i10 + i01 * i11);
-    gs[2 * NN + k] = jw * (i10 * i10 + i11 * i11);
+    const int m = k / n1, n = k - m * n1;
+    const int64_t patch = slot / pe;
+    const int lp = (int)(slot - patch * pe);
+    const int64_t row = (int64_t)n1 * pe;
+    double *gs = G + patch * g_patch_stride + (int64_t)m * row + lp * n1 + n;
+    gs[0] = jw * (i00 * i00 + i01 * i01);
+    gs[n1 * row] = jw * (i00 * i10 + i01 * i11);
+    gs[2 * n1 * row] = jw * (i10 * i10 + i11 * i11);
   }
 }
 
@@ -151,19 +162,22 @@ __global__ void gfactors_from_invj_kernel(int NN, int64_t n_elem,
 extern "C" int semk_geom_factors_f64(int n1, int64_t n_elem, const double *nodes_x,
                                      const double *nodes_y, const uint32_t *l2g,
                                      const double *Einv, const double *D, const double *w,
-                                     const int64_t *elem_of_slot, double *G, int64_t g_stride,
-                                     double *JxW, double *x_phys, double *J, double *invJ,
-                                     double *detJ, int32_t *bad_flag, void *stream) {
+                                     const int64_t *elem_of_slot, double *G,
+                                     int64_t g_patch_stride, int elems_per_patch, double *JxW,
+                                     double *x_phys, double *J, double *invJ, double *detJ,
+                                     int32_t *bad_flag, void *stream) {
   SEMK_REQUIRE(n_elem >= 0, "semk_geom_factors_f64: negative n_elem");
   SEMK_REQUIRE(nodes_x && nodes_y && l2g && Einv && D && w && bad_flag,
                "semk_geom_factors_f64: null input pointer");
-  SEMK_REQUIRE(!G || (g_stride >= 3 * n1 * n1), "semk_geom_factors_f64: g_stride too small");
+  SEMK_REQUIRE(!G || (elems_per_patch >= 1 &&
+                      g_patch_stride >= (int64_t)3 * n1 * n1 * elems_per_patch),
+               "semk_geom_factors_f64: g_patch_stride too small");
   if (n_elem == 0) return SEMK_OK;
   const unsigned grid = (unsigned)(n_elem < (1 << 20) ? n_elem : (1 << 20));
 #define SEMK_CALL(NV)                                                                      \
   geom_kernel<NV><<<grid, ((NV * NV + 31) / 32) * 32, 0, semk_stream(stream)>>>(           \
-      n_elem, nodes_x, nodes_y, l2g, Einv, D, w, elem_of_slot, G, g_stride, JxW, x_phys, J, \
-      invJ, detJ, bad_flag)
+      n_elem, nodes_x, nodes_y, l2g, Einv, D, w, elem_of_slot, G, g_patch_stride,           \
+      elems_per_patch > 0 ? elems_per_patch : 1, JxW, x_phys, J, invJ, detJ, bad_flag)
   SEMK_DISPATCH_N1(n1, SEMK_CALL)
 #undef SEMK_CALL
   SEMK_LAUNCH_CHECK("geom_kernel");
@@ -172,18 +186,20 @@ extern "C" int semk_geom_factors_f64(int n1, int64_t n_elem, const double *nodes
 
 extern "C" int semk_gfactors_from_invj_f64(int n1, int64_t n_elem, const double *invJ,
                                            const double *JxW, const int64_t *elem_of_slot,
-                                           double *G, int64_t g_stride, void *stream) {
+                                           double *G, int64_t g_patch_stride,
+                                           int elems_per_patch, void *stream) {
   SEMK_REQUIRE(n1 >= 2 && n1 <= SEMK_MAX_N1, "semk_gfactors_from_invj_f64: bad n1");
   SEMK_REQUIRE(invJ && JxW && G, "semk_gfactors_from_invj_f64: null pointer");
-  SEMK_REQUIRE(g_stride >= 3 * n1 * n1, "semk_gfactors_from_invj_f64: g_stride too small");
+  SEMK_REQUIRE(elems_per_patch >= 1 && g_patch_stride >= (int64_t)3 * n1 * n1 * elems_per_patch,
+               "semk_gfactors_from_invj_f64: g_patch_stride too small");
   if (n_elem <= 0) return SEMK_OK;
   const int NN = n1 * n1;
   const int64_t total = n_elem * NN;
   const int block = 256;
   const int64_t want = (total + block - 1) / block;
   const unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
-  gfactors_from_invj_kernel<<<grid, block, 0, semk_stream(stream)>>>(NN, n_elem, invJ, JxW,
-                                                                     elem_of_slot, G, g_stride);
+  gfactors_from_invj_kernel<<<grid, block, 0, semk_stream(stream)>>>(
+      n1, n_elem, invJ, JxW, elem_of_slot, G, g_patch_stride, elems_per_patch);
   SEMK_LAUNCH_CHECK("gfactors_from_invj_kernel");
   return SEMK_OK;
 }

@@ -55,7 +55,8 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     return SEMK_ERR_UNSUPPORTED;
   }
   const int NN = n1 * n1;
-  const int ES = (NN + 7) & ~7;  // eloc row stride (uint16): 16-byte multiples for TMA
+  // eloc block of one patch: [m][le][t], NN*PE uint16 rounded up to 16-byte multiples (TMA)
+  const int64_t ES = ((int64_t)NN * elems_per_patch + 7) & ~(int64_t)7;
   const int PE = elems_per_patch;
   if ((int64_t)PE * NN > 65535) {
     semk_set_error("semk_hostplan_create: patch too large for 16-bit local indices");
@@ -128,7 +129,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     P->patch_npriv.assign(n_patch, 0);
     P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
-    P->eloc.assign((size_t)n_slot_elems * ES, 0);
+    P->eloc.assign((size_t)n_patch * ES, 0);
     P->elem_color.assign(n_slot_elems, 0);
     std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
     std::vector<uint32_t> priv, shar, colmask;
@@ -186,11 +187,13 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       colmask.assign(np + ns, 0u);
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
-        uint16_t *er = P->eloc.data() + (size_t)s * ES;
+        uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
+        const int le = (int)(s - s0);
         uint32_t forbidden = 0;
         for (int k = 0; k < NN; ++k) {
           const int32_t loc = local_of[row[k]];
-          er[k] = (uint16_t)loc;
+          const int m = k / n1, t = k - m * n1;
+          eb[((size_t)m * PE + le) * n1 + t] = (uint16_t)loc;
           forbidden |= colmask[loc];
         }
         int c = 0;
@@ -200,7 +203,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           semk_set_error("semk_hostplan_create: more than 31 colours needed in a patch");
           return SEMK_ERR_UNSUPPORTED;
         }
-        for (int k = 0; k < NN; ++k) colmask[er[k]] |= (1u << c);
+        for (int k = 0; k < NN; ++k) colmask[local_of[row[k]]] |= (1u << c);
         P->elem_color[s] = (uint8_t)c;
         max_colors = std::max(max_colors, c + 1);
       }

@@ -73,8 +73,9 @@ def basis_tables(basis):
     return tab
 
 
-def geom_factors(tab, nodes_dev, l2g_dev, n_elem, elem_of_slot=None, G=None, g_stride=0,
-                 JxW=None, x_phys=None, J=None, invJ=None, detJ=None, check=True):
+def geom_factors(tab, nodes_dev, l2g_dev, n_elem, elem_of_slot=None, G=None, g_patch_stride=0,
+                 elems_per_patch=1, JxW=None, x_phys=None, J=None, invJ=None, detJ=None,
+                 check=True):
     """Launch K1 (csrc/semk_geom.cu).  Raises AssertionError on a non-positive
     Jacobian, like the reference's ``assert np.all(det_jacobian > 0)``
     (sem/mapping.py:117)."""
@@ -83,8 +84,8 @@ def geom_factors(tab, nodes_dev, l2g_dev, n_elem, elem_of_slot=None, G=None, g_s
     bad = torch.zeros(1, dtype=torch.int32, device=nodes_dev.device)
     _lib.check(lib.semk_geom_factors_f64(
         tab.n1, int(n_elem), ptr(nodes_dev[0]), ptr(nodes_dev[1]), ptr(l2g_dev), ptr(Einv),
-        ptr(D), ptr(w), ptr(elem_of_slot), ptr(G), int(g_stride), ptr(JxW), ptr(x_phys), ptr(J),
-        ptr(invJ), ptr(detJ), ptr(bad), stream_ptr()))
+        ptr(D), ptr(w), ptr(elem_of_slot), ptr(G), int(g_patch_stride), int(elems_per_patch),
+        ptr(JxW), ptr(x_phys), ptr(J), ptr(invJ), ptr(detJ), ptr(bad), stream_ptr()))
     if check and int(bad.item()) != 0:
         raise AssertionError("non-positive Jacobian determinant in the mesh")
 

@@ -31,19 +31,20 @@ _SMEM_TARGET = 76 * 1024     # <= this keeps >= 3 CTAs per SM
 _SMEM_LIMIT = 227 * 1024
 
 
-def g_stride_of(n1):
-    nn3 = 3 * n1 * n1
-    return nn3 + (nn3 & 1)          # even => 16-byte multiples for the TMA bulk copy
+def g_patch_stride_of(n1, pe):
+    n = 3 * n1 * n1 * pe
+    return n + (n & 1)              # even => 16-byte multiples for the TMA bulk copy
 
 
-def eloc_stride_of(n1):
-    return (n1 * n1 + 7) & ~7       # uint16 entries per element row (16-byte multiples)
+def eloc_patch_stride_of(n1, pe):
+    return (n1 * n1 * pe + 7) & ~7  # uint16 entries per patch block (16-byte multiples)
 
 
 def patch_smem_bytes(n1, pe, max_patch_nodes):
     """Dynamic shared memory of one CTA of the apply kernel (asks the library,
     which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
-    return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_stride_of(n1), eloc_stride_of(n1),
+    return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_patch_stride_of(n1, pe),
+                                                 eloc_patch_stride_of(n1, pe),
                                                  int(max_patch_nodes)))
 
 
@@ -165,8 +166,8 @@ class PoissonOperator(object):
         self.n_slots = sc[_lib.PS_N_SLOTS]
 
         f64 = dict(dtype=torch.float64, device=self.dev)
-        self.g_stride = g_stride_of(n1)
-        self.G = torch.zeros((self.n_slot_elems, self.g_stride), **f64)
+        self.g_patch_stride = g_patch_stride_of(n1, pe)
+        self.G = torch.zeros((self.n_patch, self.g_patch_stride), **f64)
         self.JxW = torch.empty((self.n_elem, NN), **f64)
         self.l2g_dev = device.as_i32_bits(l2g, self.dev)
         if geometric_factors is None:
@@ -175,7 +176,8 @@ class PoissonOperator(object):
                 raise NotImplementedError("Only supporting 2D elements right now")
             device.geom_factors(self.tab, nodes_dev, self.l2g_dev, self.n_elem,
                                 elem_of_slot=t[_lib.PA_ELEM_OF_SLOT], G=self.G,
-                                g_stride=self.g_stride, JxW=self.JxW)
+                                g_patch_stride=self.g_patch_stride, elems_per_patch=pe,
+                                JxW=self.JxW)
             del nodes_dev
         else:
             invJ, jxw = geometric_factors
@@ -183,7 +185,7 @@ class PoissonOperator(object):
             self.JxW.copy_(device._f64(np.asarray(jxw).reshape(self.n_elem, NN), self.dev))
             _lib.check(self._lib.semk_gfactors_from_invj_f64(
                 n1, self.n_elem, device.ptr(invJ), device.ptr(self.JxW),
-                device.ptr(t[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G), self.g_stride,
+                device.ptr(t[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G), self.g_patch_stride, pe,
                 device.stream_ptr()))
             torch.cuda.current_stream().synchronize()
             del invJ
@@ -202,13 +204,13 @@ class PoissonOperator(object):
         op.n_elem, op.n_nodes, op.n_patch = self.n_elem, self.n_nodes, self.n_patch
         op.max_patch_nodes = sc[_lib.PS_MAX_PATCH_NODES]
         op.max_colors = sc[_lib.PS_MAX_COLORS]
-        op.g_stride = self.g_stride
+        op.g_patch_stride = self.g_patch_stride
         op.G = self.G.data_ptr()
         op.patch_node_ptr = t[_lib.PA_PATCH_NODE_PTR].data_ptr()
         op.pnode = t[_lib.PA_PNODE].data_ptr()
         op.patch_npriv = t[_lib.PA_PATCH_NPRIV].data_ptr()
         op.patch_nnodes = t[_lib.PA_PATCH_NNODES].data_ptr()
-        op.eloc_stride = sc[_lib.PS_ELOC_STRIDE]
+        op.eloc_patch_stride = sc[_lib.PS_ELOC_STRIDE]
         op.patch_slot_base = t[_lib.PA_PATCH_SLOT_BASE].data_ptr()
         op.eloc = t[_lib.PA_ELOC].data_ptr()
         op.elem_color = t[_lib.PA_ELEM_COLOR].data_ptr()
@@ -275,7 +277,8 @@ class PoissonOperator(object):
             flags = self._masked_flags
         _lib.check(self._lib.semk_poisson_apply_atomic_f64(
             self.n1, self.n_elem, self.n_nodes, device.ptr(self.l2g_dev),
-            device.ptr(self._tables[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G), self.g_stride,
+            device.ptr(self._tables[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G),
+            self.g_patch_stride, self.elems_per_patch,
             device.ptr(self.tab.D_host), device.ptr(self.dirichlet_dev), device.ptr(u),
             device.ptr(y), int(flags), device.stream_ptr()))
         return y
@@ -303,8 +306,8 @@ class PoissonOperator(object):
         """diag(Ahat) (masked: 1 on Dirichlet rows) or diag(A)."""
         loc = torch.empty((self.n_slot_elems, self.n1 * self.n1), dtype=torch.float64,
                           device=self.dev)
-        _lib.check(self._lib.semk_poisson_local_diag_f64(C.byref(self._op), device.ptr(loc),
-                                                         device.stream_ptr()))
+        _lib.check(self._lib.semk_poisson_local_diag_f64(
+            C.byref(self._op), device.ptr(self.tab.dev()[0]), device.ptr(loc), device.stream_ptr()))
         return self.assemble(loc, mask=masked and self.has_dirichlet, fill_dirichlet=1.0)
 
     def rhs(self, f=1.0):

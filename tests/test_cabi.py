@@ -65,8 +65,11 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     npriv = ar[_lib.PA_PATCH_NPRIV]
     base = ar[_lib.PA_PATCH_SLOT_BASE]
     ES = sc[_lib.PS_ELOC_STRIDE]
-    assert ES % 8 == 0 and NN <= ES < NN + 8
-    eloc = ar[_lib.PA_ELOC].reshape(-1, ES)[:, :NN]
+    n1 = int(round(NN ** 0.5))
+    assert ES % 8 == 0 and NN * pe <= ES < NN * pe + 8
+    # per patch a table [m][le][t]; bring it to [slot][m*n1 + t]
+    eloc = ar[_lib.PA_ELOC].reshape(-1, ES)[:, :NN * pe].reshape(-1, n1, pe, n1)
+    eloc = eloc.transpose(0, 2, 1, 3).reshape(-1, NN)
     nnodes = ar[_lib.PA_PATCH_NNODES]
     assert np.all(ptr % 4 == 0)
     color = ar[_lib.PA_ELEM_COLOR]
@@ -175,7 +178,7 @@ def test_patch_size_choice_and_smem_budget():
         p = n1 - 1
         smem = operators.patch_smem_bytes(n1, pe, (bx * p + 1) * (by * p + 1))
         assert smem <= 227 * 1024
-        assert operators.g_stride_of(n1) % 2 == 0
+        assert operators.g_patch_stride_of(n1, pe) % 2 == 0 and operators.eloc_patch_stride_of(n1, pe) % 8 == 0
     assert operators.choose_elems_per_patch(9) == 16
 
 
