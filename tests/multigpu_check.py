@@ -1,0 +1,75 @@
+"""Multi-GPU parity check, launched by hand under torchrun on the GPU box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multigpu_check.py
+
+Every rank builds its strip; rank 0 additionally builds the *global* mesh on
+its own GPU and checks that the distributed apply / RHS / diagonal / PCG
+solution equal the single-GPU results on the rows it holds (gathered by global
+id).  Not collected by pytest (needs N GPUs)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from spectralelementmethod_b200 import discrete, meshgen  # noqa: E402
+from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS  # noqa: E402
+from spectralelementmethod_b200.distributed import DistributedPoisson, StripPartition  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    nxl, ny, p, kind = 24, 20, 8, "C"
+    bounds = (-1.0, -1.0 + 2.0 * world, -1.0, 1.0)
+    part = StripPartition(rank, world, nxl, ny, p, bounds=bounds)
+    dp = DistributedPoisson(part, p, kind)
+    gid = torch.from_numpy(part.global_ids()).to(dev)
+
+    # global problem on every rank's own GPU (small), as the reference
+    gx = meshgen.lattice_coordinates(kind, nxl * world, ny, p, bounds)
+    gmesh = meshgen.structured_quad_mesh(nxl * world, ny, p, kind, bounds, nodes=gx)
+    b1 = LagrangeGaussLobatto(p)
+    gm = discrete.DOFManager(gmesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+    gon = gm.boundary_node_mask("ebc")
+    gop = gm.poisson_operator(dirichlet=gon)
+    assert np.array_equal(dp.on_ebc, gon[part.global_ids()])
+
+    g = torch.Generator(device=dev).manual_seed(7)
+    ug = torch.randn(gop.n_nodes, dtype=torch.float64, device=dev, generator=g)
+    want = gop.apply(ug)
+    dot_ref = torch.zeros(1, dtype=torch.float64, device=dev)
+    gop.apply(ug, dot_out=dot_ref)
+    u = ug[gid].contiguous()
+    dot = torch.zeros(1, dtype=torch.float64, device=dev)
+    y = dp.apply(u, dot_out=dot)
+    dist.all_reduce(dot)
+    err = float((y - want[gid]).norm() / want.norm())
+    assert err < 1e-13, err
+    assert abs(float(dot) - float(dot_ref)) < 1e-11 * abs(float(dot_ref)), (float(dot), float(dot_ref))
+    assert float((dp.diagonal() - gop.diagonal()[gid]).abs().max()) < 1e-11
+    assert float((dp.rhs(1.0) - gop.rhs(1.0)[gid]).abs().max()) < 1e-14
+
+    bg = gop.lift(gop.rhs(1.0), None)
+    xg, info = gop.solve_pcg(bg, rtol=1e-12, check_every=10)
+    b = dp.lift(dp.rhs(1.0), None)
+    assert float((b - bg[gid]).abs().max()) < 1e-13
+    x, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, check_every=10)
+    serr = float((x - xg[gid]).norm() / xg.norm())
+    assert ok and serr < 1e-9, (ok, serr)
+    if rank == 0:
+        print("multigpu_check ok: world=%d apply err %.2e, PCG %d its (single GPU %d), "
+              "solution diff %.2e" % (world, err, it, info.iterations, serr))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+"""Multi-rank host logic on CPU: world_size-2 `gloo` runs of the strip
+partition, the interface exchange, the owner-weighted dot products and the
+distributed PCG driver.  The rank-local operator is played by the CPU oracle
+(test infrastructure) so that no GPU is needed; on the GPU box the same
+classes drive the CUDA operator (bench.py --gpus N, tests/test_gpu_parity.py).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ORACLE_DIR, ROOT, rel_l2
+
+KIND, NXL, NY, P = "C", 3, 4, 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class CpuKernels(object):
+    """Torch-on-CPU stand-in for operators.PCGKernels (same scalar protocol as
+    csrc/semk_vec.cu)."""
+
+    def __init__(self, dirichlet):
+        self.fixed = torch.as_tensor(dirichlet)
+
+    def init(self, b, Ax, dinv, r, p, sc, n_dot):
+        bb = torch.where(self.fixed, torch.zeros_like(b), b)
+        r.copy_(torch.where(self.fixed, torch.zeros_like(b), bb - Ax))
+        p.copy_(dinv * r)
+        sc[0] = torch.dot(r[:n_dot], p[:n_dot])
+        sc[1] = 0.0
+        sc[2] = sc[0]
+        sc[3] = torch.dot(r[:n_dot], r[:n_dot])
+        sc[4] = torch.dot(bb[:n_dot], bb[:n_dot])
+        sc[5:] = 0.0
+
+    def update_xr(self, p, Ap, dinv, x, r, sc, n_dot):
+        ok = bool(sc[1] > 0)
+        alpha = float(sc[0] / sc[1]) if ok else 0.0
+        x += alpha * p
+        r -= alpha * Ap
+        sc[2] = torch.dot(r[:n_dot] * dinv[:n_dot], r[:n_dot])
+        sc[3] = torch.dot(r[:n_dot], r[:n_dot])
+        sc[5] += 1
+        if not ok:
+            sc[7] = 1.0
+
+    def update_p(self, r, dinv, p, sc):
+        beta = float(sc[2] / sc[0]) if float(sc[0]) != 0.0 else 0.0
+        p.mul_(beta).add_(dinv * r)
+        sc[0] = sc[2]
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, ORACLE_DIR)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sem_oracle as so
+        from spectralelementmethod_b200 import discrete
+        from spectralelementmethod_b200.basis_functions import (LagrangeGaussLobatto,
+                                                                TensorProductQS)
+        from spectralelementmethod_b200.distributed import (DistributedOperator, StripPartition,
+                                                            distributed_pcg)
+        bounds = (-1.0, -1.0 + 2.0 * world, -1.0, 1.0)
+        part = StripPartition(rank, world, NXL, NY, P, bounds=bounds)
+        mesh = part.build_local_mesh(KIND)
+        b1 = LagrangeGaussLobatto(P)
+        mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        on = mngr.boundary_node_mask("ebc")
+        l2g = mngr.node_map_array()
+        basis = so.Basis(P)
+        geo = so.geometry(basis, mesh.nodes, l2g)
+        L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+        n = part.n_local
+        A = so.assemble_csr(L, l2g, n)
+        M = (~on).astype(float)
+
+        def local_apply(u, outv, dot):
+            un = u.numpy()
+            y = M * (A @ (M * un)) + (1 - M) * un
+            if outv is None:
+                outv = torch.empty_like(u)
+            outv.copy_(torch.from_numpy(y))
+            if dot is not None:
+                dot[0] = float((M * un) @ (A @ (M * un)) + ((1 - M) * un) @ un)
+            return outv
+
+        dop = DistributedOperator(part, local_apply, dirichlet=on)
+        gid = part.global_ids()
+        rng = np.random.default_rng(5)
+        ug = rng.standard_normal(part.n_global)
+        u = torch.from_numpy(ug[gid].copy())
+        y = dop.apply(u)
+        dotv = dop.owned_dot(u, u)
+
+        # RHS / diagonal / lifted system, assembled across ranks
+        bl = torch.from_numpy(so.assemble_vector(geo["JxW"], l2g, n))
+        dop.exchange_add(bl)
+        dl = torch.from_numpy(A.diagonal().copy())
+        dop.exchange_add(dl)
+        dl[torch.from_numpy(on)] = 1.0
+        x_phys_nodes = np.zeros((2, n))
+        x_phys_nodes[:, l2g.ravel()] = np.moveaxis(geo["x_phys"], 1, 0).reshape(2, -1)
+        g = np.where(on, 0.2 * ((x_phys_nodes[0] + 1) + (x_phys_nodes[1] + 1)), 0.0)
+        gt = torch.from_numpy(g)
+        t = torch.from_numpy(M * (A @ g))
+        dop.exchange_add(t)
+        bh = bl - t
+        bh[torch.from_numpy(on)] = gt[torch.from_numpy(on)]
+        x0 = torch.where(torch.from_numpy(on), bh, torch.zeros_like(bh))
+        it, rel, ok = distributed_pcg(dop, bh, x0, 1.0 / dl, CpuKernels(on), rtol=1e-13,
+                                      maxiter=3000, check_every=7)
+        res = dict(gid=gid, y=y.numpy(), dot=float(dotv), x=x0.numpy(), it=it, ok=ok, rel=rel,
+                   n_owned=part.n_owned, on=on, b=bl.numpy(), d=dl.numpy())
+        torch.save(res, os.path.join(out, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def two_rank_results(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("dist"))
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    return [torch.load(os.path.join(out, "rank%d.pt" % r), weights_only=False) for r in range(world)]
+
+
+def _global_reference():
+    import sem_oracle as so
+    world = 2
+    nxg = NXL * world
+    NX, NYn = nxg * P + 1, NY * P + 1
+    X, Y = np.meshgrid(np.linspace(-1.0, -1.0 + 2.0 * world, NX), np.linspace(-1, 1, NYn),
+                       indexing="ij")
+    s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
+    nodes = np.vstack([(X + s).ravel(), (Y + s).ravel()])
+    l2g = so.mesh_l2g(nxg, NY, P)
+    basis = so.Basis(P)
+    geo = so.geometry(basis, nodes, l2g)
+    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+    n = nodes.shape[1]
+    A = so.assemble_csr(L, l2g, n)
+    on, vals = so.dirichlet_data(nodes, l2g, geo["x_phys"], so.mesh_boundary_faces(nxg, NY))
+    b = so.assemble_vector(geo["JxW"], l2g, n)
+    return dict(A=A, on=on, vals=vals, b=b, n=n, sol=so.solve_direct(A, b, on, vals))
+
+
+def test_partition_description():
+    from spectralelementmethod_b200.distributed import StripPartition
+    parts = [StripPartition(r, 3, 4, 5, 2) for r in range(3)]
+    NYn = 5 * 2 + 1
+    assert [p.n_local for p in parts] == [9 * NYn] * 3
+    assert parts[0].left is None and parts[0].right == 1 and parts[2].right is None
+    assert [p.n_owned for p in parts] == [8 * NYn, 8 * NYn, 9 * NYn]
+    assert sum(p.n_owned for p in parts) == parts[0].n_global == 25 * NYn
+    # shared columns carry the same global ids and bit-identical coordinates
+    assert np.array_equal(parts[0].global_ids()[parts[0].right_slice],
+                          parts[1].global_ids()[parts[1].left_slice])
+    for kind in ("S", "C"):
+        c0, c1 = parts[0].local_coordinates(kind), parts[1].local_coordinates(kind)
+        assert np.array_equal(c0[:, parts[0].right_slice], c1[:, parts[1].left_slice])
+    with pytest.raises(ValueError):
+        StripPartition(3, 3, 4, 5, 2)
+    m0, m2 = parts[0].build_local_mesh(), parts[2].build_local_mesh()
+    assert len(m0._boundary_cells[0]) == 5 + 4 - 1 and len(m2._boundary_cells[0]) == 4
+    assert len(m0._boundary_cells[1]) == 4 and len(m2._boundary_cells[1]) == 5 + 4 - 1
+
+
+def test_two_rank_apply_matches_global_operator(two_rank_results):
+    ref = _global_reference()
+    rng = np.random.default_rng(5)
+    ug = rng.standard_normal(ref["n"])
+    M = (~ref["on"]).astype(float)
+    want = M * (ref["A"] @ (M * ug)) + (1 - M) * ug
+    for r in two_rank_results:
+        assert rel_l2(r["y"], want[r["gid"]]) < 1e-12
+        assert np.array_equal(r["on"], ref["on"][r["gid"]])
+        assert rel_l2(r["b"], ref["b"][r["gid"]]) < 1e-13
+        assert rel_l2(r["d"], (M * ref["A"].diagonal() + (1 - M))[r["gid"]]) < 1e-13
+    # owner-weighted dot counts every node once
+    assert abs(two_rank_results[0]["dot"] - ug @ ug) < 1e-11 * (ug @ ug)
+    assert two_rank_results[0]["dot"] == two_rank_results[1]["dot"]
+
+
+def test_two_rank_pcg_matches_global_direct_solve(two_rank_results):
+    ref = _global_reference()
+    its = {r["it"] for r in two_rank_results}
+    assert len(its) == 1 and all(r["ok"] for r in two_rank_results)
+    for r in two_rank_results:
+        assert rel_l2(r["x"], ref["sol"][r["gid"]]) < 1e-11
+        assert r["rel"] <= 1e-13
