@@ -47,6 +47,8 @@ def parse():
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
     ap.add_argument("--kind", default="S", choices=["S", "C"])
     ap.add_argument("--pe", type=int, default=0, help="elements per patch (0 = automatic)")
+    ap.add_argument("--lookahead", type=int, default=-1,
+                    help="L2 prefetch distance in patches (-1 = resident CTAs, 0 = off)")
     return ap.parse_args()
 
 
@@ -209,7 +211,8 @@ def run_engine(args):
         b1 = LagrangeGaussLobatto(ORDER)
         mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
         on_ebc = mngr.boundary_node_mask("ebc")
-        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None)
+        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None,
+                                   lookahead=None if args.lookahead < 0 else args.lookahead)
         apply_fn = lambda u, out: op.apply(u, out=out)          # noqa: E731
         n_local = n_global = op.n_nodes
         n_global_units = n_global

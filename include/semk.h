@@ -36,6 +36,7 @@ extern "C" {
 
 #define SEMK_VERSION 100          /* 0.1.0 */
 #define SEMK_MAX_N1 17            /* orders 1..16 */
+#define SEMK_PF_LINES 128         /* L2 prefetch hints per patch (cache lines of the nodal vector) */
 
 /* status codes */
 #define SEMK_OK 0
@@ -87,7 +88,13 @@ enum semk_plan_array {
   SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
   SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node    */
   SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
-  SEMK_PA_COUNT = 11
+  SEMK_PA_PATCH_DESC = 11,    /* int32  [n_patch][8]  packed per-patch descriptor the kernel
+                                 reads: {node-list offset, padded length, n nodes, n private,
+                                 first interface slot, 0, 0, 0}                              */
+  SEMK_PA_PF_LINES = 12,      /* uint32 [n_patch][SEMK_PF_LINES] ascending indices of the
+                                 128-byte lines (node id >> 4) holding the patch's nodes,
+                                 0xffffffff-padded: L2 prefetch hints for the nodal vector   */
+  SEMK_PA_COUNT = 13
 };
 
 enum semk_plan_scalar {
@@ -133,11 +140,10 @@ typedef struct semk_op {
                                element sits at ((c*n1 + m)*PE + le)*n1 + t, i.e. rows of
                                n1*PE doubles indexed by thread (le, t): coalesced, and
                                bank-conflict free once staged in shared memory           */
-  const int32_t *patch_node_ptr;
+  const int32_t *patch_desc;/* [n_patch][8] packed descriptors (SEMK_PA_PATCH_DESC)      */
   const uint32_t *pnode;
-  const int32_t *patch_npriv;
-  const int32_t *patch_nnodes;
-  const int32_t *patch_slot_base;
+  const uint32_t *pf_lines; /* [n_patch][SEMK_PF_LINES] prefetch hints, or NULL          */
+  int64_t lookahead;        /* prefetch distance in patches (~ resident CTAs), 0 = off   */
   const uint16_t *eloc;
   int64_t eloc_patch_stride;/* uint16 entries per patch block of eloc (multiple of 8)   */
   const uint8_t *elem_color;
@@ -154,6 +160,10 @@ typedef struct semk_op {
 
 /* number of doubles the `partials` scratch of an operator must hold */
 int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
+/* CTAs of the apply kernel that are co-resident on the current device for this
+ * configuration (the natural prefetch distance `lookahead`); <0 on error */
+int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
+                           int64_t eloc_patch_stride, int max_patch_nodes);
 /* dynamic shared memory (bytes) one CTA of the apply kernel needs */
 int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                               int64_t eloc_patch_stride, int max_patch_nodes);

@@ -20,7 +20,9 @@ MASK_IN, MASK_OUT, DIRICHLET_IDENTITY = 1, 2, 4
 MAX_N1 = 17
 
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
- PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES) = range(11)
+ PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
+ PA_PATCH_DESC, PA_PF_LINES) = range(13)
+PF_LINES = 128
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
  PS_N_SLOT_ELEMS, PS_ELOC_STRIDE) = range(8)
 
@@ -28,7 +30,8 @@ PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
     PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16, PA_ELEM_COLOR: np.uint8,
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
-    PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32,
+    PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PATCH_DESC: np.int32,
+    PA_PF_LINES: np.uint32,
 }
 
 
@@ -49,9 +52,9 @@ class semk_op(C.Structure):
         ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
         ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
         ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
-        ("patch_node_ptr", C.c_void_p), ("pnode", C.c_void_p), ("patch_npriv", C.c_void_p),
-        ("patch_nnodes", C.c_void_p),
-        ("patch_slot_base", C.c_void_p), ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
+        ("patch_desc", C.c_void_p), ("pnode", C.c_void_p), ("pf_lines", C.c_void_p),
+        ("lookahead", C.c_int64),
+        ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
         ("elem_color", C.c_void_p),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
@@ -78,6 +81,7 @@ SIGNATURES = {
     "semk_hostplan_destroy": (None, [_P]),
     "semk_partials_len": (_L, [_L, _L]),
     "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _I]),
+    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _I]),
     "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P,
                                    _P, _P, _P, _P]),
     "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _I, _P]),

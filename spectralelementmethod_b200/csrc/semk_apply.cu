@@ -30,16 +30,36 @@
 //     `shared_nodes_kernel` sums in a fixed order => bit-reproducible.
 #include "semk_common.cuh"
 
+#include <cmath>
 #include <cstring>
 
 namespace {
 
-// Differentiation matrix, row-major [N][N], passed BY VALUE as a kernel
-// parameter: the entries live in the parameter constant bank and every use
-// below has a compile-time index, so the DFMAs read them through uniform
-// registers (LDCU.128) -- no shared memory, no per-thread registers.
+// Differentiation matrix, passed BY VALUE as a kernel parameter: the entries
+// live in the parameter constant bank and every use below has a compile-time
+// index, so the DFMAs read them through uniform registers (LDCU.128) -- no
+// shared memory, no per-thread registers.
+//
+// `v` is the plain row-major matrix (used by the atomic cross-check kernel).
+// `eo[0]` / `eo[1]` hold the even-odd factorisation of D and of D^T used by
+// the production kernel: a GLL differentiation matrix is centro-antisymmetric
+// (D[N-1-i][N-1-k] = -D[i][k]), so with e_k = v_k + v_{N-1-k},
+// o_k = v_k - v_{N-1-k} (k < h = N/2) and the centre value v_c (odd N)
+//     S_i = sum_k M[i][k] o_k,   A_i = sum_k P[i][k] e_k + C[i] v_c,
+//     out_i = S_i + A_i,  out_{N-1-i} = S_i - A_i,
+//     out_c = sum_k R[k] o_k + Dcc v_c
+// with M = (D[i][k] - D[i][N-1-k])/2, P = (D[i][k] + D[i][N-1-k])/2,
+// C[i] = D[i][c], R[k] = D[c][k]: 2h^2 + 2h FMAs + 4h adds instead of N^2
+// FMAs (56 instead of 81 FP64 instructions at N = 9).
+constexpr int kMaxH = SEMK_MAX_N1 / 2;
+struct EvenOdd {
+  double P[kMaxH * kMaxH], M[kMaxH * kMaxH], C[kMaxH], R[kMaxH], Dcc;
+};
 struct DMat {
   double v[SEMK_MAX_N1 * SEMK_MAX_N1];
+};
+struct DMatEO {
+  EvenOdd eo[2];  // [0]: D, [1]: D^T
 };
 
 DMat make_dmat(int n1, const double *D_host) {
@@ -47,6 +67,36 @@ DMat make_dmat(int n1, const double *D_host) {
   std::memset(&d, 0, sizeof(d));
   std::memcpy(d.v, D_host, sizeof(double) * n1 * n1);
   return d;
+}
+
+// Returns false if D is not centro-antisymmetric to 1e-12 (relative).
+bool make_dmat_eo(int n1, const double *D, DMatEO *out) {
+  std::memset(out, 0, sizeof(*out));
+  const int N = n1, h = N / 2, c = (N & 1) ? h : -1;
+  double dmax = 0.0, viol = 0.0;
+  for (int i = 0; i < N; ++i)
+    for (int k = 0; k < N; ++k) {
+      const double a = D[i * N + k], b = D[(N - 1 - i) * N + (N - 1 - k)];
+      dmax = std::fmax(dmax, std::fabs(a));
+      viol = std::fmax(viol, std::fabs(a + b));
+    }
+  if (!(viol <= 1e-12 * dmax)) return false;
+  for (int tr = 0; tr < 2; ++tr) {
+    EvenOdd &E = out->eo[tr];
+    auto d = [&](int i, int k) { return tr ? D[k * N + i] : D[i * N + k]; };
+    for (int i = 0; i < h; ++i) {
+      for (int k = 0; k < h; ++k) {
+        E.M[i * h + k] = 0.5 * (d(i, k) - d(i, N - 1 - k));
+        E.P[i * h + k] = 0.5 * (d(i, k) + d(i, N - 1 - k));
+      }
+      if (c >= 0) {
+        E.C[i] = d(i, c);
+        E.R[i] = d(c, i);
+      }
+    }
+    if (c >= 0) E.Dcc = d(c, c);
+  }
+  return true;
 }
 
 // out[i] = sum_k D[i][k] v[k]      (derivative along the in-thread axis)
@@ -71,6 +121,55 @@ __device__ __forceinline__ void apply_Dt(const DMat &dm, const double (&v)[N], d
     out[i] = acc;
   }
 }
+// Even-odd application of D (TR = 0) or D^T (TR = 1).
+template <int N, int TR>
+__device__ __forceinline__ void apply_eo(const DMatEO &dm, const double (&v)[N],
+                                         double (&out)[N]) {
+  constexpr int h = N / 2;
+  constexpr bool odd = (N & 1) != 0;
+  const EvenOdd &E = dm.eo[TR];
+  double e[h > 0 ? h : 1], o[h > 0 ? h : 1];
+#pragma unroll
+  for (int k = 0; k < h; ++k) {
+    e[k] = v[k] + v[N - 1 - k];
+    o[k] = v[k] - v[N - 1 - k];
+  }
+#pragma unroll
+  for (int i = 0; i < h; ++i) {
+    double S = 0.0, A = odd ? E.C[i] * v[h] : 0.0;
+#pragma unroll
+    for (int k = 0; k < h; ++k) {
+      S = fma(E.M[i * h + k], o[k], S);
+      A = fma(E.P[i * h + k], e[k], A);
+    }
+    out[i] = S + A;
+    out[N - 1 - i] = S - A;
+  }
+  if (odd) {
+    double acc = E.Dcc * v[h];
+#pragma unroll
+    for (int k = 0; k < h; ++k) acc = fma(E.R[k], o[k], acc);
+    out[h] = acc;
+  }
+}
+
+// Uniform front end: the production kernel passes DMatEO, the cross-check DMat.
+template <int N>
+__device__ __forceinline__ void mat_D(const DMat &dm, const double (&v)[N], double (&o)[N]) {
+  apply_D<N>(dm, v, o);
+}
+template <int N>
+__device__ __forceinline__ void mat_Dt(const DMat &dm, const double (&v)[N], double (&o)[N]) {
+  apply_Dt<N>(dm, v, o);
+}
+template <int N>
+__device__ __forceinline__ void mat_D(const DMatEO &dm, const double (&v)[N], double (&o)[N]) {
+  apply_eo<N, 0>(dm, v, o);
+}
+template <int N>
+__device__ __forceinline__ void mat_Dt(const DMatEO &dm, const double (&v)[N], double (&o)[N]) {
+  apply_eo<N, 1>(dm, v, o);
+}
 
 // Row stride of the CTA-wide transpose scratch: N*PE columns (one per thread)
 // padded so that RS == 1 (mod 16).  With 8-byte words and 16 bank pairs both
@@ -89,8 +188,8 @@ __host__ __device__ constexpr int scratch_row_stride(int N, int PE) {
 //      (c, m) of this column sits at g[(c*N + m) * g_row].
 //   g_ready: mbarrier guarding a TMA-staged G (nullptr when g is global).
 // Contains four __syncthreads(); every thread of the CTA must call it.
-template <int N, int RS>
-__device__ __forceinline__ void local_poisson(const DMat &dm, int le, int t, bool active,
+template <int N, int RS, class DM>
+__device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool active,
                                               const double (&ucol)[N], double (&ycol)[N],
                                               double *__restrict__ A, double *__restrict__ B,
                                               const double *__restrict__ g, int g_row,
@@ -103,10 +202,10 @@ __device__ __forceinline__ void local_poisson(const DMat &dm, int le, int t, boo
   }
   __syncthreads();
   if (active) {
-    apply_D<N>(dm, ucol, ur);  // ur[m][t] = sum_r D[m][r] u[r][t]
+    mat_D<N>(dm, ucol, ur);  // ur[m][t] = sum_r D[m][r] u[r][t]
 #pragma unroll
     for (int s = 0; s < N; ++s) tmp[s] = A[t * RS + le * N + s];  // row t of u
-    apply_D<N>(dm, tmp, us);                                      // us[t][n] = sum_s D[n][s] u[t][s]
+    mat_D<N>(dm, tmp, us);                                        // us[t][n] = sum_s D[n][s] u[t][s]
 #pragma unroll
     for (int n = 0; n < N; ++n) B[t * RS + le * N + n] = us[n];
   }
@@ -122,7 +221,7 @@ __device__ __forceinline__ void local_poisson(const DMat &dm, int le, int t, boo
       tmp[m] = g00 * ur[m] + g01 * usc;  // w0[m][t]
       w1[m] = g01 * ur[m] + g11 * usc;   // w1[m][t]
     }
-    apply_Dt<N>(dm, tmp, ycol);  // y0[p][t] = sum_m D[m][p] w0[m][t]
+    mat_Dt<N>(dm, tmp, ycol);  // y0[p][t] = sum_m D[m][p] w0[m][t]
 #pragma unroll
     for (int m = 0; m < N; ++m) A[m * RS + tidp] = w1[m];
   }
@@ -130,7 +229,7 @@ __device__ __forceinline__ void local_poisson(const DMat &dm, int le, int t, boo
   if (active) {
 #pragma unroll
     for (int n = 0; n < N; ++n) tmp[n] = A[t * RS + le * N + n];  // row t of w1
-    apply_Dt<N>(dm, tmp, us);                                     // y1[t][q] = sum_n w1[t][n] D[n][q]
+    mat_Dt<N>(dm, tmp, us);                                       // y1[t][q] = sum_n w1[t][n] D[n][q]
 #pragma unroll
     for (int q = 0; q < N; ++q) B[t * RS + le * N + q] = us[q];
   }
@@ -188,7 +287,7 @@ constexpr int kGatherBatch = 8;
 // MODE_ASSEMBLE: y = assembly of the element-local field `loc` (slot order).
 template <int N, int PE, int MODE>
 __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
-    patch_kernel(semk_op op, DMat dm, const double *__restrict__ u,
+    patch_kernel(semk_op op, DMatEO dm, const double *__restrict__ u,
                  const double *__restrict__ loc, double *__restrict__ y, int flags,
                  double fill_dirichlet, double *__restrict__ dot_partials) {
   constexpr int NN = N * N;
@@ -214,16 +313,41 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   const int le = tid / N, t = tid - le * N;
   const bool active = (le < PE) && (slot0 + le < op.n_elem);
 
+  // ---- look-ahead: the CTA that will run `lookahead` patches later finds its
+  // tables, geometric factors and nodal values already in L2.  One warp loads
+  // that patch's cache-line hints now (latency overlaps everything below) and
+  // issues the prefetches once the current patch's gather is under way.
+  constexpr int kPfWarp = (kThreads > 32) ? 1 : 0;
+  const int lane = tid & 31;
+  const int64_t q = patch + op.lookahead;
+  const bool do_pf = (MODE == MODE_APPLY) && op.lookahead > 0 && q < op.n_patch &&
+                     (tid >> 5) == kPfWarp;
+  uint32_t pf_line[SEMK_PF_LINES / 32];
+  int4 dq = make_int4(0, 0, 0, 0);
+  if (do_pf) {
+#pragma unroll
+    for (int j = 0; j < SEMK_PF_LINES / 32; ++j)
+      pf_line[j] = op.pf_lines[q * SEMK_PF_LINES + lane + 32 * j];
+    if (lane == 0) dq = *reinterpret_cast<const int4 *>(op.patch_desc + q * 8);
+  }
+
   // ---- stage the patch's tables (and geometric factors) with the TMA engine ----
-  const int n0 = op.patch_node_ptr[patch];
+  __shared__ int sdesc[8];
   if (tid == 0) {
+    const int4 d0 = *reinterpret_cast<const int4 *>(op.patch_desc + patch * 8);
+    const int4 d1 = *reinterpret_cast<const int4 *>(op.patch_desc + patch * 8 + 4);
+    sdesc[0] = d0.x;  // offset of the node list in pnode
+    sdesc[1] = d0.y;  // padded length of the node list
+    sdesc[2] = d0.z;  // number of nodes
+    sdesc[3] = d0.w;  // number of private nodes
+    sdesc[4] = d1.x;  // first interface slot
     semk_mbar_init(&mbar[0], 1);
     semk_mbar_init(&mbar[1], 1);
     semk_fence_mbar_init();
-    const uint32_t pn_bytes = 4u * (uint32_t)(op.patch_node_ptr[patch + 1] - n0);
+    const uint32_t pn_bytes = 4u * (uint32_t)d0.y;
     const uint32_t el_bytes = 2u * (uint32_t)op.eloc_patch_stride;
     semk_mbar_expect_tx(&mbar[0], pn_bytes + el_bytes);
-    semk_bulk_g2s(pn_s, op.pnode + n0, pn_bytes, &mbar[0]);
+    semk_bulk_g2s(pn_s, op.pnode + d0.x, pn_bytes, &mbar[0]);
     semk_bulk_g2s(el_s, op.eloc + patch * op.eloc_patch_stride, el_bytes, &mbar[0]);
     if (MODE == MODE_APPLY) {
       const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
@@ -231,12 +355,12 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[1]);
     }
   }
-  const int npn = op.patch_nnodes[patch];
-  const int npriv = op.patch_npriv[patch];
-  const int slot_base = op.patch_slot_base[patch];
   uint8_t color = 255;
   if (active) color = op.elem_color[slot0 + le];
-  __syncthreads();  // mbarrier initialisation visible to every waiter
+  __syncthreads();  // descriptor + mbarrier initialisation visible to every thread
+  const int npn = sdesc[2];
+  const int npriv = sdesc[3];
+  const int slot_base = sdesc[4];
   semk_mbar_wait(&mbar[0], 0);
 
   // ---- gather the patch's nodal values: batches of independent loads -----------
@@ -284,6 +408,18 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
       for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
     }
     __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
+    if (do_pf) {
+#pragma unroll
+      for (int j = 0; j < SEMK_PF_LINES / 32; ++j)
+        if (pf_line[j] != 0xffffffffu) semk_prefetch_l2(u + (size_t)pf_line[j] * 16);
+      if (lane == 0) {
+        semk_bulk_prefetch_l2(op.G + q * op.g_patch_stride,
+                              (uint32_t)(op.g_patch_stride * sizeof(double)));
+        semk_bulk_prefetch_l2(op.eloc + q * op.eloc_patch_stride,
+                              2u * (uint32_t)op.eloc_patch_stride);
+        semk_bulk_prefetch_l2(op.pnode + dq.x, 4u * (uint32_t)dq.y);
+      }
+    }
     local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[1]);
   } else {
     if (active) {
@@ -484,7 +620,7 @@ __global__ void weighted_local_kernel(int NN, int64_t n_elem, const double *__re
 template <int PE, int MODE>
 struct PatchLaunch {
   template <int N>
-  static int run(const semk_op &op, const DMat &dm, const double *u, const double *loc,
+  static int run(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
                  double *y, int flags, double fill, double *partials, cudaStream_t st) {
     const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.eloc_patch_stride,
                                           op.max_patch_nodes)
@@ -511,7 +647,7 @@ struct PatchLaunch {
 inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16; }
 
 template <int MODE>
-int launch_patch(const semk_op &op, const DMat &dm, const double *u, const double *loc,
+int launch_patch(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
                  double *y, int flags, double fill, double *partials, cudaStream_t st) {
 #define SEMK_CALL(NV)                                                                     \
   do {                                                                                    \
@@ -543,8 +679,8 @@ int check_op(const semk_op *op, const char *who) {
     return SEMK_ERR_UNSUPPORTED;
   }
   const int64_t nnp = (int64_t)op->n1 * op->n1 * op->elems_per_patch;
-  if (!op->patch_node_ptr || !op->pnode || !op->patch_npriv || !op->patch_nnodes ||
-      !op->patch_slot_base || !op->eloc || !op->elem_color ||
+  if (!op->patch_desc || !op->pnode || !op->eloc || !op->elem_color ||
+      (op->lookahead > 0 && !op->pf_lines) ||
       (op->eloc_patch_stride & 7) != 0 || op->eloc_patch_stride < nnp ||
       (op->n_slots > 0 && !op->slot_buf) ||
       (op->n_shared > 0 && (!op->shared_node || !op->shared_ptr || !op->shared_slot))) {
@@ -566,6 +702,52 @@ extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
   return n_patch + kSharedBlocks + 8;
 }
 
+namespace {
+template <int PE>
+struct Resident {
+  template <int N>
+  static int query(size_t smem, int *out) {
+    auto kern = patch_kernel<N, PE, MODE_APPLY>;
+    SEMK_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SEMK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        out, kern, PatchCfg<N, PE>::kThreads, smem));
+    return SEMK_OK;
+  }
+};
+}  // namespace
+
+extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
+                                      int64_t eloc_patch_stride, int max_patch_nodes) {
+  if (!pe_supported(elems_per_patch)) return -1;
+  const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
+                                        eloc_patch_stride, max_patch_nodes)
+                          .total;
+  if (smem > 227 * 1024) return -1;
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return -1;
+  auto run = [&]() -> int {
+#define SEMK_CALL(NV)                                                          \
+  do {                                                                         \
+    int rc;                                                                    \
+    if (elems_per_patch == 16)                                                 \
+      rc = Resident<16>::template query<NV>(smem, &per_sm);                    \
+    else if (elems_per_patch == 8)                                             \
+      rc = Resident<8>::template query<NV>(smem, &per_sm);                     \
+    else                                                                       \
+      rc = Resident<4>::template query<NV>(smem, &per_sm);                     \
+    if (rc != SEMK_OK) return rc;                                              \
+  } while (0)
+    SEMK_DISPATCH_N1(n1, SEMK_CALL)
+#undef SEMK_CALL
+    return SEMK_OK;
+  };
+  if (run() != SEMK_OK) return -1;
+  return (int64_t)per_sm * sms;
+}
+
 extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                                          int64_t eloc_patch_stride, int max_patch_nodes) {
   return (int64_t)patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
@@ -581,7 +763,13 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
   SEMK_REQUIRE(op->G && op->D_host, "semk_poisson_apply_f64: missing G or D");
   SEMK_REQUIRE(!dot_out || op->partials, "semk_poisson_apply_f64: dot_out needs op->partials");
   cudaStream_t st = semk_stream(stream);
-  const DMat dm = make_dmat(op->n1, op->D_host);
+  DMatEO dm;
+  if (!make_dmat_eo(op->n1, op->D_host, &dm)) {
+    semk_set_error(
+        "semk_poisson_apply_f64: differentiation matrix is not centro-antisymmetric "
+        "(the engine needs a basis whose nodes are symmetric about 0)");
+    return SEMK_ERR_UNSUPPORTED;
+  }
   double *partials = dot_out ? op->partials : nullptr;
   rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, partials, st);
   if (rc != SEMK_OK) return rc;
@@ -606,7 +794,7 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
   if (rc != SEMK_OK) return rc;
   SEMK_REQUIRE(loc && out, "semk_assemble_f64: null pointer");
   cudaStream_t st = semk_stream(stream);
-  DMat dm;
+  DMatEO dm;
   std::memset(&dm, 0, sizeof(dm));
   rc = launch_patch<MODE_ASSEMBLE>(*op, dm, nullptr, loc, out, flags, fill_dirichlet, nullptr, st);
   if (rc != SEMK_OK) return rc;

@@ -106,6 +106,15 @@ __device__ __forceinline__ void semk_bulk_g2s(void *smem_dst, const void *gmem_s
       : "memory");
 }
 
+// L2 prefetch of one 128-byte line (SASS: CCTL.E.PF2) / of a contiguous block
+// through the TMA engine (SASS: UBLKPF.L2; 16-byte aligned, size % 16 == 0).
+__device__ __forceinline__ void semk_prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void semk_bulk_prefetch_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // Deterministic block reduction of one double (blockDim.x a multiple of 32, <= 1024).
 // Result valid in thread 0.
 __device__ __forceinline__ double semk_block_sum(double v, double *smem_scratch /*[32]*/) {

@@ -122,14 +122,18 @@ class DistributedOperator(object):
         kw = dict(dtype=torch.float64, device=device)
         self._recv_left = torch.empty(NY, **kw) if part.left is not None else None
         self._recv_right = torch.empty(NY, **kw) if part.right is not None else None
-        self._fix_ids = None
+        self._fix_ids = None          # Dirichlet nodes on interface columns
+        self._fix_nonowned = None     # ... those this rank does not own (its right column)
         if dirichlet is not None:
             d = torch.as_tensor(dirichlet).to("cpu").bool()
             ids = []
             if part.left is not None:
                 ids.append(torch.nonzero(d[part.left_slice]).ravel())
             if part.right is not None:
-                ids.append(torch.nonzero(d[part.right_slice]).ravel() + (part.n_local - NY))
+                right = torch.nonzero(d[part.right_slice]).ravel() + (part.n_local - NY)
+                ids.append(right)
+                if right.numel():
+                    self._fix_nonowned = right.to(device)
             if ids:
                 ids = torch.cat(ids)
                 if ids.numel():
@@ -163,6 +167,10 @@ class DistributedOperator(object):
         self.exchange_add(y)
         if self._fix_ids is not None:
             y[self._fix_ids] = u[self._fix_ids]
+        if dot_out is not None and self._fix_nonowned is not None:
+            # identity rows on a shared column were counted by both ranks
+            dup = u[self._fix_nonowned]
+            dot_out -= torch.dot(dup, dup)
         return y
 
     def owned_dot(self, a, b):

@@ -117,7 +117,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True):
+                 elem_order=None, keep_l2g=True, lookahead=None):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -150,10 +150,9 @@ class PoissonOperator(object):
         self.smem_bytes = smem
 
         t = {}
-        for k in (_lib.PA_PATCH_NODE_PTR, _lib.PA_PATCH_NPRIV, _lib.PA_PATCH_SLOT_BASE,
-                  _lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT, _lib.PA_PATCH_NNODES):
+        for k in (_lib.PA_PATCH_DESC, _lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT):
             t[k] = torch.from_numpy(ar[k]).to(self.dev)
-        for k in (_lib.PA_PNODE, _lib.PA_SHARED_NODE):
+        for k in (_lib.PA_PNODE, _lib.PA_SHARED_NODE, _lib.PA_PF_LINES):
             t[k] = device.as_i32_bits(ar[k], self.dev)
         t[_lib.PA_ELOC] = torch.from_numpy(ar[_lib.PA_ELOC].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_COLOR] = torch.from_numpy(ar[_lib.PA_ELEM_COLOR]).to(self.dev)
@@ -206,12 +205,17 @@ class PoissonOperator(object):
         op.max_colors = sc[_lib.PS_MAX_COLORS]
         op.g_patch_stride = self.g_patch_stride
         op.G = self.G.data_ptr()
-        op.patch_node_ptr = t[_lib.PA_PATCH_NODE_PTR].data_ptr()
+        op.patch_desc = t[_lib.PA_PATCH_DESC].data_ptr()
         op.pnode = t[_lib.PA_PNODE].data_ptr()
-        op.patch_npriv = t[_lib.PA_PATCH_NPRIV].data_ptr()
-        op.patch_nnodes = t[_lib.PA_PATCH_NNODES].data_ptr()
+        op.pf_lines = t[_lib.PA_PF_LINES].data_ptr()
         op.eloc_patch_stride = sc[_lib.PS_ELOC_STRIDE]
-        op.patch_slot_base = t[_lib.PA_PATCH_SLOT_BASE].data_ptr()
+        resident = int(self._lib.semk_resident_ctas(n1, pe, self.g_patch_stride,
+                                                    sc[_lib.PS_ELOC_STRIDE],
+                                                    sc[_lib.PS_MAX_PATCH_NODES]))
+        if resident <= 0:
+            raise RuntimeError("semk_resident_ctas failed: " + _lib.last_error())
+        self.resident_ctas = resident
+        op.lookahead = resident if lookahead is None else int(lookahead)
         op.eloc = t[_lib.PA_ELOC].data_ptr()
         op.elem_color = t[_lib.PA_ELEM_COLOR].data_ptr()
         op.n_slots = self.n_slots
