@@ -47,8 +47,8 @@ def parse():
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
     ap.add_argument("--kind", default="S", choices=["S", "C"])
     ap.add_argument("--pe", type=int, default=0, help="elements per patch (0 = automatic)")
-    ap.add_argument("--lookahead", type=int, default=-1,
-                    help="L2 prefetch distance in patches (-1 = resident CTAs, 0 = off)")
+    ap.add_argument("--ablate", type=int, default=0,
+                    help="internal profiling knob: extra apply flag bits (results are wrong)")
     return ap.parse_args()
 
 
@@ -211,9 +211,12 @@ def run_engine(args):
         b1 = LagrangeGaussLobatto(ORDER)
         mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
         on_ebc = mngr.boundary_node_mask("ebc")
-        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None,
-                                   lookahead=None if args.lookahead < 0 else args.lookahead)
-        apply_fn = lambda u, out: op.apply(u, out=out)          # noqa: E731
+        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None)
+        if args.ablate:
+            abl = op._masked_flags | args.ablate
+            apply_fn = lambda u, out: op.apply(u, out=out, flags=abl)   # noqa: E731
+        else:
+            apply_fn = lambda u, out: op.apply(u, out=out)          # noqa: E731
         n_local = n_global = op.n_nodes
         n_global_units = n_global
         workload = ("structured %dx%d-element quad mesh Poisson, p=8, FP64, rcm_order=False "

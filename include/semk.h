@@ -36,7 +36,6 @@ extern "C" {
 
 #define SEMK_VERSION 100          /* 0.1.0 */
 #define SEMK_MAX_N1 17            /* orders 1..16 */
-#define SEMK_PF_LINES 128         /* L2 prefetch hints per patch (cache lines of the nodal vector) */
 
 /* status codes */
 #define SEMK_OK 0
@@ -88,12 +87,11 @@ enum semk_plan_array {
   SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
   SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node    */
   SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
-  SEMK_PA_PATCH_DESC = 11,    /* int32  [n_patch][8]  packed per-patch descriptor the kernel
-                                 reads: {node-list offset, padded length, n nodes, n private,
-                                 first interface slot, 0, 0, 0}                              */
-  SEMK_PA_PF_LINES = 12,      /* uint32 [n_patch][SEMK_PF_LINES] ascending indices of the
-                                 128-byte lines (node id >> 4) holding the patch's nodes,
-                                 0xffffffff-padded: L2 prefetch hints for the nodal vector   */
+  SEMK_PA_PNBLK = 11,         /* uint32 [n_patch][pn_stride] device node blocks, uniform stride:
+                                 {n nodes, n private, first interface slot, 0} followed by
+                                 the patch's node list (as in PNODE), 0xffffffff padded     */
+  SEMK_PA_ELBLK = 12,         /* uint16 [n_patch][el_stride] device index blocks: the ELOC
+                                 table [m][le][t] followed by the PE element colours        */
   SEMK_PA_COUNT = 13
 };
 
@@ -106,7 +104,9 @@ enum semk_plan_scalar {
   SEMK_PS_MAX_COLORS = 5,
   SEMK_PS_N_SLOT_ELEMS = 6,   /* n_patch * elems_per_patch (last patch padded) */
   SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per patch block of ELOC: NN*PE rounded up to 8 */
-  SEMK_PS_COUNT = 8
+  SEMK_PS_PN_STRIDE = 8,      /* uint32 entries per patch block of PNBLK (multiple of 4)       */
+  SEMK_PS_EL_STRIDE = 9,      /* uint16 entries per patch block of ELBLK (multiple of 8)       */
+  SEMK_PS_COUNT = 10
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
@@ -140,13 +140,10 @@ typedef struct semk_op {
                                element sits at ((c*n1 + m)*PE + le)*n1 + t, i.e. rows of
                                n1*PE doubles indexed by thread (le, t): coalesced, and
                                bank-conflict free once staged in shared memory           */
-  const int32_t *patch_desc;/* [n_patch][8] packed descriptors (SEMK_PA_PATCH_DESC)      */
-  const uint32_t *pnode;
-  const uint32_t *pf_lines; /* [n_patch][SEMK_PF_LINES] prefetch hints, or NULL          */
-  int64_t lookahead;        /* prefetch distance in patches (~ resident CTAs), 0 = off   */
-  const uint16_t *eloc;
-  int64_t eloc_patch_stride;/* uint16 entries per patch block of eloc (multiple of 8)   */
-  const uint8_t *elem_color;
+  const uint32_t *pnode;    /* [n_patch][pn_patch_stride] node blocks (SEMK_PA_PNBLK)     */
+  int64_t pn_patch_stride;  /* uint32 entries per node block (multiple of 4)             */
+  const uint16_t *eloc;     /* [n_patch][eloc_patch_stride] index blocks (SEMK_PA_ELBLK) */
+  int64_t eloc_patch_stride;/* uint16 entries per index block (multiple of 8)            */
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums (scratch)  */
   int64_t n_shared;
@@ -161,12 +158,14 @@ typedef struct semk_op {
 /* number of doubles the `partials` scratch of an operator must hold */
 int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
 /* CTAs of the apply kernel that are co-resident on the current device for this
- * configuration (the natural prefetch distance `lookahead`); <0 on error */
+ * configuration = the grid of the persistent kernel; <0 on error */
 int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
-                           int64_t eloc_patch_stride, int max_patch_nodes);
+                           int64_t pn_patch_stride, int64_t eloc_patch_stride,
+                           int max_patch_nodes);
 /* dynamic shared memory (bytes) one CTA of the apply kernel needs */
 int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
-                              int64_t eloc_patch_stride, int max_patch_nodes);
+                              int64_t pn_patch_stride, int64_t eloc_patch_stride,
+                              int max_patch_nodes);
 
 /* ------------------------------------------------------------------------
  * K1: geometric factors.  Replaces, per element, Mapping._compute_x_phys /

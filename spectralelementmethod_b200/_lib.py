@@ -21,17 +21,16 @@ MAX_N1 = 17
 
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
- PA_PATCH_DESC, PA_PF_LINES) = range(13)
-PF_LINES = 128
+ PA_PNBLK, PA_ELBLK) = range(13)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
- PS_N_SLOT_ELEMS, PS_ELOC_STRIDE) = range(8)
+ PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE) = range(10)
 
 PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
     PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16, PA_ELEM_COLOR: np.uint8,
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
-    PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PATCH_DESC: np.int32,
-    PA_PF_LINES: np.uint32,
+    PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
+    PA_ELBLK: np.uint16,
 }
 
 
@@ -52,10 +51,8 @@ class semk_op(C.Structure):
         ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
         ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
         ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
-        ("patch_desc", C.c_void_p), ("pnode", C.c_void_p), ("pf_lines", C.c_void_p),
-        ("lookahead", C.c_int64),
+        ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
-        ("elem_color", C.c_void_p),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
         ("shared_slot", C.c_void_p),
@@ -80,8 +77,8 @@ SIGNATURES = {
     "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
     "semk_hostplan_destroy": (None, [_P]),
     "semk_partials_len": (_L, [_L, _L]),
-    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _I]),
-    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _I]),
+    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _L, _I]),
+    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _L, _I]),
     "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P,
                                    _P, _P, _P, _P]),
     "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _I, _P]),
@@ -171,7 +168,7 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
     check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p,
                                    int(elems_per_patch), dir_p, C.byref(handle)))
     try:
-        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(8)}
+        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(10)}
         arrays = {}
         for k, dt in PLAN_ARRAY_DTYPES.items():
             nb = _L(0)

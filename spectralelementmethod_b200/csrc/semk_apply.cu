@@ -193,7 +193,7 @@ __device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool 
                                               const double (&ucol)[N], double (&ycol)[N],
                                               double *__restrict__ A, double *__restrict__ B,
                                               const double *__restrict__ g, int g_row,
-                                              uint64_t *g_ready) {
+                                              uint64_t *g_ready, uint32_t g_parity = 0) {
   const int tidp = le * N + t;
   double ur[N], tmp[N], us[N];
   if (active) {
@@ -211,7 +211,7 @@ __device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool 
   }
   __syncthreads();
   // G staged by TMA: every thread observes the mbarrier phase itself (acquire)
-  if (g_ready) semk_mbar_wait(g_ready, 0);
+  if (g_ready) semk_mbar_wait(g_ready, g_parity);
   double w1[N];
   if (active) {
 #pragma unroll
@@ -248,24 +248,32 @@ struct PatchCfg {
 
 enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 
-// Shared-memory carve-up of the patch kernel (all offsets multiples of 16 B).
+// Shared-memory carve-up of the persistent patch kernel (offsets multiples of
+// 16 B).  Two pipeline stages of {G block, node block, index block}; one copy
+// of the working arrays.
 struct PatchSmem {
-  size_t gs, pn, el, yp, ua, bs, red, total;
+  size_t stage0, stage_bytes, g_off, pn_off, el_off;  // per stage: G | node block | index block
+  size_t yp, ua, bs, red, total;
 };
 __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
                                                        int64_t g_patch_stride,
+                                                       int64_t pn_patch_stride,
                                                        int64_t eloc_patch_stride,
                                                        int max_patch_nodes) {
   PatchSmem L;
   const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
   const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
-  size_t o = 16;  // two mbarriers
-  L.gs = o;
-  o += (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
-  L.pn = o;
-  o += 4 * mpn4;
-  L.el = o;
-  o += 2 * (size_t)eloc_patch_stride;
+  size_t o = 64;  // four mbarriers: tables[2], G[2]
+  L.stage0 = o;
+  L.g_off = 0;
+  size_t st = (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
+  L.pn_off = st;
+  st += 4 * (size_t)pn_patch_stride;
+  L.el_off = st;
+  st += 2 * (size_t)eloc_patch_stride;
+  st = (st + 15) & ~(size_t)15;
+  L.stage_bytes = st;
+  o += 2 * st;
   L.yp = o;
   o += 8 * mpn4;
   o = (o + 15) & ~(size_t)15;
@@ -283,6 +291,17 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
 
 constexpr int kGatherBatch = 8;
 
+// Persistent, software-pipelined patch kernel.
+//
+// Each CTA loops over patches blockIdx.x, blockIdx.x + gridDim.x, ...  While it
+// works on patch i, the TMA engine is already filling the other pipeline stage
+// with patch i+1's geometric factors, node block and index block (issued one
+// whole patch-time ahead: DRAM latency is off the critical path), and the
+// nodal values of patch i+1 are gathered into registers right after the
+// element operator of patch i, so that the loads are in flight during the
+// colour-ordered assembly and the write-out.  CTAs never exit between patches,
+// so no SM slot idles on CTA launch / retire (~2.4 k cycles each on this chip).
+//
 // MODE_APPLY:    y = A u (masked per flags), optional dot partials.
 // MODE_ASSEMBLE: y = assembly of the element-local field `loc` (slot order).
 template <int N, int PE, int MODE>
@@ -295,12 +314,9 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   constexpr int kThreads = PatchCfg<N, PE>::kThreads;
   constexpr int RS = PatchCfg<N, PE>::kRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.eloc_patch_stride,
-                                        op.max_patch_nodes);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0]: tables, [1]: G
-  double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
-  uint32_t *pn_s = reinterpret_cast<uint32_t *>(smem_raw + L.pn);
-  uint16_t *el_s = reinterpret_cast<uint16_t *>(smem_raw + L.el);
+  const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
+                                        op.eloc_patch_stride, op.max_patch_nodes);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2..3]: G
   double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
   double *up = reinterpret_cast<double *>(smem_raw + L.ua);  // aliases scratch A
   double *As = up;
@@ -308,168 +324,174 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   double *red = reinterpret_cast<double *>(smem_raw + L.red);
 
   const int tid = threadIdx.x;
-  const int64_t patch = blockIdx.x;
-  const int64_t slot0 = patch * PE;
   const int le = tid / N, t = tid - le * N;
-  const bool active = (le < PE) && (slot0 + le < op.n_elem);
+  const uint32_t pn_bytes = 4u * (uint32_t)op.pn_patch_stride;
+  const uint32_t el_bytes = 2u * (uint32_t)op.eloc_patch_stride;
+  const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
 
-  // ---- look-ahead: the CTA that will run `lookahead` patches later finds its
-  // tables, geometric factors and nodal values already in L2.  One warp loads
-  // that patch's cache-line hints now (latency overlaps everything below) and
-  // issues the prefetches once the current patch's gather is under way.
-  constexpr int kPfWarp = (kThreads > 32) ? 1 : 0;
-  const int lane = tid & 31;
-  const int64_t q = patch + op.lookahead;
-  const bool do_pf = (MODE == MODE_APPLY) && op.lookahead > 0 && q < op.n_patch &&
-                     (tid >> 5) == kPfWarp;
-  uint32_t pf_line[SEMK_PF_LINES / 32];
-  int4 dq = make_int4(0, 0, 0, 0);
-  if (do_pf) {
-#pragma unroll
-    for (int j = 0; j < SEMK_PF_LINES / 32; ++j)
-      pf_line[j] = op.pf_lines[q * SEMK_PF_LINES + lane + 32 * j];
-    if (lane == 0) dq = *reinterpret_cast<const int4 *>(op.patch_desc + q * 8);
-  }
-
-  // ---- stage the patch's tables (and geometric factors) with the TMA engine ----
-  __shared__ int sdesc[8];
-  if (tid == 0) {
-    const int4 d0 = *reinterpret_cast<const int4 *>(op.patch_desc + patch * 8);
-    const int4 d1 = *reinterpret_cast<const int4 *>(op.patch_desc + patch * 8 + 4);
-    sdesc[0] = d0.x;  // offset of the node list in pnode
-    sdesc[1] = d0.y;  // padded length of the node list
-    sdesc[2] = d0.z;  // number of nodes
-    sdesc[3] = d0.w;  // number of private nodes
-    sdesc[4] = d1.x;  // first interface slot
-    semk_mbar_init(&mbar[0], 1);
-    semk_mbar_init(&mbar[1], 1);
-    semk_fence_mbar_init();
-    const uint32_t pn_bytes = 4u * (uint32_t)d0.y;
-    const uint32_t el_bytes = 2u * (uint32_t)op.eloc_patch_stride;
-    semk_mbar_expect_tx(&mbar[0], pn_bytes + el_bytes);
-    semk_bulk_g2s(pn_s, op.pnode + d0.x, pn_bytes, &mbar[0]);
-    semk_bulk_g2s(el_s, op.eloc + patch * op.eloc_patch_stride, el_bytes, &mbar[0]);
+  auto stage_ptr = [&](int s) { return smem_raw + L.stage0 + (size_t)s * L.stage_bytes; };
+  auto issue_loads = [&](int64_t patch, int s) {  // one thread
+    unsigned char *base = stage_ptr(s);
+    semk_mbar_expect_tx(&mbar[s], pn_bytes + el_bytes);
+    semk_bulk_g2s(base + L.pn_off, op.pnode + patch * op.pn_patch_stride, pn_bytes, &mbar[s]);
+    semk_bulk_g2s(base + L.el_off, op.eloc + patch * op.eloc_patch_stride, el_bytes, &mbar[s]);
     if (MODE == MODE_APPLY) {
-      const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
-      semk_mbar_expect_tx(&mbar[1], g_bytes);
-      semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[1]);
+      semk_mbar_expect_tx(&mbar[2 + s], g_bytes);
+      semk_bulk_g2s(base + L.g_off, op.G + patch * op.g_patch_stride, g_bytes, &mbar[2 + s]);
     }
-  }
-  uint8_t color = 255;
-  if (active) color = op.elem_color[slot0 + le];
-  __syncthreads();  // descriptor + mbarrier initialisation visible to every thread
-  const int npn = sdesc[2];
-  const int npriv = sdesc[3];
-  const int slot_base = sdesc[4];
-  semk_mbar_wait(&mbar[0], 0);
+  };
 
-  // ---- gather the patch's nodal values: batches of independent loads -----------
-  for (int k0 = tid; k0 < npn; k0 += kGatherBatch * kThreads) {
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) semk_mbar_init(&mbar[i], 1);
+    semk_fence_mbar_init();
+    if ((int64_t)blockIdx.x < op.n_patch) issue_loads(blockIdx.x, 0);
+  }
+  __syncthreads();  // mbarrier initialisation visible to every waiter
+
+  // nodal values of the patch about to be processed, staged in registers
+  uint32_t gpn[kGatherBatch];
+  double gv[kGatherBatch];
+  auto gather_to_regs = [&](const uint32_t *pn_blk) {
+    const int nn = (int)pn_blk[0];
+#pragma unroll
+    for (int j = 0; j < kGatherBatch; ++j) {
+      const int k = tid + j * kThreads;
+      gpn[j] = (k < nn) ? pn_blk[4 + k] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < kGatherBatch; ++j)
+      gv[j] = (gpn[j] != 0xffffffffu) ? u[gpn[j] & SEMK_NODE_ID_MASK] : 0.0;
+  };
+  if (MODE == MODE_APPLY && (int64_t)blockIdx.x < op.n_patch) {
+    semk_mbar_wait(&mbar[0], 0);
+    gather_to_regs(reinterpret_cast<const uint32_t *>(stage_ptr(0) + L.pn_off));
+  }
+
+  double dot = 0.0;
+  const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
+  int it = 0;
+  for (int64_t patch = blockIdx.x; patch < op.n_patch; patch += gridDim.x, ++it) {
+    const int s = it & 1;
+    const uint32_t par = (uint32_t)((it >> 1) & 1);
+    const int64_t next = patch + gridDim.x;
+    const bool has_next = next < op.n_patch;
+    // stage s^1 was released by the barrier that ended the previous iteration
+    if (tid == 0 && has_next) issue_loads(next, s ^ 1);
+
+    unsigned char *sb = stage_ptr(s);
+    const double *Gs = reinterpret_cast<const double *>(sb + L.g_off);
+    const uint32_t *pn_blk = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
+    const uint16_t *el_s = reinterpret_cast<const uint16_t *>(sb + L.el_off);
+    semk_mbar_wait(&mbar[s], par);
+    const int npn = (int)pn_blk[0];
+    const int npriv = (int)pn_blk[1];
+    const int slot_base = (int)pn_blk[2];
+    const uint32_t *pn_s = pn_blk + 4;
+    const int64_t slot0 = patch * PE;
+    const bool active = (le < PE) && (slot0 + le < op.n_elem);
+
+    // ---- nodal values (prefetched into registers) -> shared memory ----------------
     if (MODE == MODE_APPLY) {
-      uint32_t pn[kGatherBatch];
-      double v[kGatherBatch];
 #pragma unroll
       for (int j = 0; j < kGatherBatch; ++j) {
-        const int k = k0 + j * kThreads;
-        pn[j] = (k < npn) ? pn_s[k] : 0xffffffffu;
-      }
-#pragma unroll
-      for (int j = 0; j < kGatherBatch; ++j)
-        v[j] = (pn[j] != 0xffffffffu) ? u[pn[j] & SEMK_NODE_ID_MASK] : 0.0;
-#pragma unroll
-      for (int j = 0; j < kGatherBatch; ++j) {
-        const int k = k0 + j * kThreads;
+        const int k = tid + j * kThreads;
         if (k < npn) {
-          up[k] = ((pn[j] & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : v[j];
+          up[k] = ((gpn[j] & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : gv[j];
           yp[k] = 0.0;
         }
       }
+      for (int k = tid + kGatherBatch * kThreads; k < npn; k += kThreads) {  // oversized patch
+        const uint32_t pn = pn_s[k];
+        const double v = u[pn & SEMK_NODE_ID_MASK];
+        up[k] = ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : v;
+        yp[k] = 0.0;
+      }
     } else {
-#pragma unroll
-      for (int j = 0; j < kGatherBatch; ++j) {
-        const int k = k0 + j * kThreads;
-        if (k < npn) yp[k] = 0.0;
-      }
+      for (int k = tid; k < npn; k += kThreads) yp[k] = 0.0;
     }
-  }
-  // this thread's column of patch-local node indices (table rows are [m][le][t])
-  uint16_t idx[N];
-  if (active) {
-#pragma unroll
-    for (int m = 0; m < N; ++m) idx[m] = el_s[m * NP + tid];
-  }
-  __syncthreads();
-
-  double ycol[N];
-  if (MODE == MODE_APPLY) {
-    double ucol[N];
+    // this thread's column of patch-local node indices (table rows are [m][le][t]),
+    // and the colour of its element (stored behind the table)
+    uint16_t idx[N];
+    int color = 255;
     if (active) {
 #pragma unroll
-      for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
-    }
-    __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
-    if (do_pf) {
-#pragma unroll
-      for (int j = 0; j < SEMK_PF_LINES / 32; ++j)
-        if (pf_line[j] != 0xffffffffu) semk_prefetch_l2(u + (size_t)pf_line[j] * 16);
-      if (lane == 0) {
-        semk_bulk_prefetch_l2(op.G + q * op.g_patch_stride,
-                              (uint32_t)(op.g_patch_stride * sizeof(double)));
-        semk_bulk_prefetch_l2(op.eloc + q * op.eloc_patch_stride,
-                              2u * (uint32_t)op.eloc_patch_stride);
-        semk_bulk_prefetch_l2(op.pnode + dq.x, 4u * (uint32_t)dq.y);
-      }
-    }
-    local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[1]);
-  } else {
-    if (active) {
-      const double *lr = loc + (slot0 + le) * NN;
-#pragma unroll
-      for (int m = 0; m < N; ++m) ycol[m] = lr[m * N + t];
-    }
-  }
-
-  // ---- assemble inside the patch, colour by colour (no atomics) -------------
-  for (int c = 0; c < op.max_colors; ++c) {
-    if (active && color == c) {
-#pragma unroll
-      for (int m = 0; m < N; ++m) yp[idx[m]] += ycol[m];
+      for (int m = 0; m < N; ++m) idx[m] = el_s[m * NP + tid];
+      color = el_s[NN * PE + le];
     }
     __syncthreads();
-  }
 
-  // ---- write out: private nodes -> y, shared nodes -> interface slots --------
-  double dot = 0.0;
-  const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
-  for (int k = tid; k < npn; k += kThreads) {
-    const uint32_t pn = pn_s[k];
-    double v = yp[k];
-    if (k < npriv) {
-      const uint32_t g = pn & SEMK_NODE_ID_MASK;
-      const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
-      double uin = 0.0;
-      if (MODE == MODE_APPLY) {
-        if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
+    double ycol[N];
+    if (MODE == MODE_APPLY) {
+      double ucol[N];
+      if (active) {
+#pragma unroll
+        for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
       }
-      if (dir && (flags & SEMK_MASK_OUT)) {
-        if (MODE == MODE_APPLY) {
-          v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
-          uin = v;
-        } else {
-          v = fill_dirichlet;
-        }
-      } else if (dir && (flags & SEMK_MASK_IN)) {
-        uin = 0.0;
+      __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
+      if (flags & 0x100) {  // profiling ablation (internal): skip the element operator
+        semk_mbar_wait(&mbar[2 + s], par);
+#pragma unroll
+        for (int m = 0; m < N; ++m) ycol[m] = ucol[m] + Gs[m * NP + tid];
+      } else {
+        local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2 + s],
+                             par);
       }
-      y[g] = v;
-      dot = fma(uin, v, dot);
+      // next patch: its node block landed long ago; start its gather now so the
+      // loads fly during the assembly and write-out below
+      if (has_next) {
+        semk_mbar_wait(&mbar[s ^ 1], (uint32_t)(((it + 1) >> 1) & 1));
+        gather_to_regs(reinterpret_cast<const uint32_t *>(stage_ptr(s ^ 1) + L.pn_off));
+      }
     } else {
-      op.slot_buf[slot_base + (k - npriv)] = v;
+      if (active) {
+        const double *lr = loc + (slot0 + le) * NN;
+#pragma unroll
+        for (int m = 0; m < N; ++m) ycol[m] = lr[m * N + t];
+      }
     }
+
+    // ---- assemble inside the patch, colour by colour (no atomics) -------------
+    for (int c = 0; c < op.max_colors; ++c) {
+      if (active && color == c) {
+#pragma unroll
+        for (int m = 0; m < N; ++m) yp[idx[m]] += ycol[m];
+      }
+      __syncthreads();
+    }
+
+    // ---- write out: private nodes -> y, shared nodes -> interface slots --------
+    for (int k = tid; k < npn; k += kThreads) {
+      const uint32_t pn = pn_s[k];
+      double v = yp[k];
+      if (k < npriv) {
+        const uint32_t g = pn & SEMK_NODE_ID_MASK;
+        const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
+        double uin = 0.0;
+        if (MODE == MODE_APPLY) {
+          if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
+        }
+        if (dir && (flags & SEMK_MASK_OUT)) {
+          if (MODE == MODE_APPLY) {
+            v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
+            uin = v;
+          } else {
+            v = fill_dirichlet;
+          }
+        } else if (dir && (flags & SEMK_MASK_IN)) {
+          uin = 0.0;
+        }
+        y[g] = v;
+        dot = fma(uin, v, dot);
+      } else {
+        op.slot_buf[slot_base + (k - npriv)] = v;
+      }
+    }
+    __syncthreads();  // stage s, yp and the scratch are free for the next iteration
   }
   if (want_dot) {
-    const double s = semk_block_sum(dot, red);
-    if (tid == 0) dot_partials[patch] = s;
+    const double sres = semk_block_sum(dot, red);
+    if (tid == 0) dot_partials[blockIdx.x] = sres;
   }
 }
 
@@ -619,26 +641,52 @@ __global__ void weighted_local_kernel(int NN, int64_t n_elem, const double *__re
 
 template <int PE, int MODE>
 struct PatchLaunch {
+  // CTAs per SM of this instantiation for the given dynamic shared memory
+  template <int N>
+  static int occupancy(size_t smem, int *per_sm, int *sms) {
+    static size_t configured = 0;  // per instantiation; one device per process
+    static int cached_per_sm = 0, cached_sms = 0;
+    auto kern = patch_kernel<N, PE, MODE>;
+    if (smem > configured || cached_per_sm == 0) {
+      SEMK_CUDA_CHECK(
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SEMK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &cached_per_sm, kern, PatchCfg<N, PE>::kThreads, smem));
+      int dev = 0;
+      SEMK_CUDA_CHECK(cudaGetDevice(&dev));
+      SEMK_CUDA_CHECK(cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev));
+      configured = smem;
+    }
+    *per_sm = cached_per_sm;
+    *sms = cached_sms;
+    return SEMK_OK;
+  }
+
   template <int N>
   static int run(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
-                 double *y, int flags, double fill, double *partials, cudaStream_t st) {
-    const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.eloc_patch_stride,
-                                          op.max_patch_nodes)
+                 double *y, int flags, double fill, double *partials, cudaStream_t st,
+                 int *grid_out) {
+    const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
+                                          op.eloc_patch_stride, op.max_patch_nodes)
                             .total;
-    auto kern = patch_kernel<N, PE, MODE>;
     if (smem > 227 * 1024) {
       semk_set_error("patch kernel: shared memory request exceeds 227 KB");
       return SEMK_ERR_UNSUPPORTED;
     }
-    static size_t configured = 0;  // per instantiation; one device per process
-    if (smem > configured) {
-      SEMK_CUDA_CHECK(
-          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+    int per_sm = 0, sms = 0;
+    int rc = occupancy<N>(smem, &per_sm, &sms);
+    if (rc != SEMK_OK) return rc;
+    if (per_sm < 1) {
+      semk_set_error("patch kernel: does not fit on an SM");
+      return SEMK_ERR_UNSUPPORTED;
     }
-    kern<<<(unsigned)op.n_patch, PatchCfg<N, PE>::kThreads, smem, st>>>(op, dm, u, loc, y, flags,
-                                                                      fill, partials);
+    // persistent grid: every CTA stays resident and loops over its patches
+    const int64_t resident = (int64_t)per_sm * sms;
+    const unsigned grid = (unsigned)(op.n_patch < resident ? op.n_patch : resident);
+    patch_kernel<N, PE, MODE><<<grid, PatchCfg<N, PE>::kThreads, smem, st>>>(
+        op, dm, u, loc, y, flags, fill, partials);
     SEMK_LAUNCH_CHECK("patch_kernel");
+    if (grid_out) *grid_out = (int)grid;
     return SEMK_OK;
   }
 };
@@ -648,16 +696,20 @@ inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16; }
 
 template <int MODE>
 int launch_patch(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
-                 double *y, int flags, double fill, double *partials, cudaStream_t st) {
+                 double *y, int flags, double fill, double *partials, cudaStream_t st,
+                 int *grid_out) {
 #define SEMK_CALL(NV)                                                                     \
   do {                                                                                    \
     int rc;                                                                               \
     if (op.elems_per_patch == 16)                                                         \
-      rc = PatchLaunch<16, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st); \
+      rc = PatchLaunch<16, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st, \
+                                                   grid_out); \
     else if (op.elems_per_patch == 8)                                                     \
-      rc = PatchLaunch<8, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st);  \
+      rc = PatchLaunch<8, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st,   \
+                                                  grid_out);  \
     else                                                                                  \
-      rc = PatchLaunch<4, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st);  \
+      rc = PatchLaunch<4, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st,   \
+                                                  grid_out);  \
     if (rc != SEMK_OK) return rc;                                                         \
   } while (0)
   SEMK_DISPATCH_N1(op.n1, SEMK_CALL)
@@ -679,9 +731,10 @@ int check_op(const semk_op *op, const char *who) {
     return SEMK_ERR_UNSUPPORTED;
   }
   const int64_t nnp = (int64_t)op->n1 * op->n1 * op->elems_per_patch;
-  if (!op->patch_desc || !op->pnode || !op->eloc || !op->elem_color ||
-      (op->lookahead > 0 && !op->pf_lines) ||
-      (op->eloc_patch_stride & 7) != 0 || op->eloc_patch_stride < nnp ||
+  if (!op->pnode || !op->eloc || (op->pn_patch_stride & 3) != 0 ||
+      op->pn_patch_stride < 4 + op->max_patch_nodes ||
+      (op->eloc_patch_stride & 7) != 0 ||
+      op->eloc_patch_stride < nnp + op->elems_per_patch ||
       (op->n_slots > 0 && !op->slot_buf) ||
       (op->n_shared > 0 && (!op->shared_node || !op->shared_ptr || !op->shared_slot))) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
@@ -702,43 +755,26 @@ extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
   return n_patch + kSharedBlocks + 8;
 }
 
-namespace {
-template <int PE>
-struct Resident {
-  template <int N>
-  static int query(size_t smem, int *out) {
-    auto kern = patch_kernel<N, PE, MODE_APPLY>;
-    SEMK_CUDA_CHECK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SEMK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        out, kern, PatchCfg<N, PE>::kThreads, smem));
-    return SEMK_OK;
-  }
-};
-}  // namespace
-
 extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
-                                      int64_t eloc_patch_stride, int max_patch_nodes) {
+                                      int64_t pn_patch_stride, int64_t eloc_patch_stride,
+                                      int max_patch_nodes) {
   if (!pe_supported(elems_per_patch)) return -1;
   const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                        eloc_patch_stride, max_patch_nodes)
+                                        pn_patch_stride, eloc_patch_stride, max_patch_nodes)
                           .total;
   if (smem > 227 * 1024) return -1;
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-    return -1;
+  int per_sm = 0, sms = 0;
   auto run = [&]() -> int {
-#define SEMK_CALL(NV)                                                          \
-  do {                                                                         \
-    int rc;                                                                    \
-    if (elems_per_patch == 16)                                                 \
-      rc = Resident<16>::template query<NV>(smem, &per_sm);                    \
-    else if (elems_per_patch == 8)                                             \
-      rc = Resident<8>::template query<NV>(smem, &per_sm);                     \
-    else                                                                       \
-      rc = Resident<4>::template query<NV>(smem, &per_sm);                     \
-    if (rc != SEMK_OK) return rc;                                              \
+#define SEMK_CALL(NV)                                                                  \
+  do {                                                                                 \
+    int rc;                                                                            \
+    if (elems_per_patch == 16)                                                         \
+      rc = PatchLaunch<16, MODE_APPLY>::template occupancy<NV>(smem, &per_sm, &sms);   \
+    else if (elems_per_patch == 8)                                                     \
+      rc = PatchLaunch<8, MODE_APPLY>::template occupancy<NV>(smem, &per_sm, &sms);    \
+    else                                                                               \
+      rc = PatchLaunch<4, MODE_APPLY>::template occupancy<NV>(smem, &per_sm, &sms);    \
+    if (rc != SEMK_OK) return rc;                                                      \
   } while (0)
     SEMK_DISPATCH_N1(n1, SEMK_CALL)
 #undef SEMK_CALL
@@ -749,9 +785,10 @@ extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_pat
 }
 
 extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
-                                         int64_t eloc_patch_stride, int max_patch_nodes) {
+                                         int64_t pn_patch_stride, int64_t eloc_patch_stride,
+                                         int max_patch_nodes) {
   return (int64_t)patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                    eloc_patch_stride, max_patch_nodes)
+                                    pn_patch_stride, eloc_patch_stride, max_patch_nodes)
       .total;
 }
 
@@ -771,18 +808,19 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
     return SEMK_ERR_UNSUPPORTED;
   }
   double *partials = dot_out ? op->partials : nullptr;
-  rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, partials, st);
+  int grid = 0;
+  rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, partials, st, &grid);
   if (rc != SEMK_OK) return rc;
   int shared_blocks = 0;
   if (op->n_shared > 0) {
     const int64_t want = (op->n_shared + 255) / 256;
     shared_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
     shared_nodes_kernel<MODE_APPLY><<<shared_blocks, 256, 0, st>>>(*op, u, y, flags, 0.0, partials,
-                                                                  op->n_patch);
+                                                                  grid);
     SEMK_LAUNCH_CHECK("shared_nodes_kernel");
   }
   if (dot_out) {
-    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, op->n_patch + shared_blocks, dot_out);
+    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, grid + shared_blocks, dot_out);
     SEMK_LAUNCH_CHECK("reduce_partials_kernel");
   }
   return SEMK_OK;
@@ -796,7 +834,8 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
   cudaStream_t st = semk_stream(stream);
   DMatEO dm;
   std::memset(&dm, 0, sizeof(dm));
-  rc = launch_patch<MODE_ASSEMBLE>(*op, dm, nullptr, loc, out, flags, fill_dirichlet, nullptr, st);
+  rc = launch_patch<MODE_ASSEMBLE>(*op, dm, nullptr, loc, out, flags, fill_dirichlet, nullptr, st,
+                                   nullptr);
   if (rc != SEMK_OK) return rc;
   if (op->n_shared > 0) {
     const int64_t want = (op->n_shared + 255) / 256;

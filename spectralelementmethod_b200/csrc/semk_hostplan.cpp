@@ -31,8 +31,8 @@ struct semk_hostplan {
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
       shared_slot;
-  std::vector<int32_t> patch_desc;
-  std::vector<uint32_t> pnode, shared_node, pf_lines;
+  std::vector<uint32_t> pnode, shared_node, pnblk;
+  std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
   std::vector<int64_t> elem_of_slot;
@@ -130,9 +130,6 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     P->patch_npriv.assign(n_patch, 0);
     P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
-    P->patch_desc.assign((size_t)n_patch * 8, 0);
-    P->pf_lines.assign((size_t)n_patch * SEMK_PF_LINES, 0xffffffffu);
-    std::vector<uint32_t> lines;
     P->eloc.assign((size_t)n_patch * ES, 0);
     P->elem_color.assign(n_slot_elems, 0);
     std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
@@ -185,23 +182,6 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       while (P->pnode.size() & 3u) P->pnode.push_back(0xffffffffu);
       P->patch_node_ptr[p + 1] = (int32_t)P->pnode.size();
       P->patch_nnodes[p] = np + ns;
-      {
-        int32_t *d = P->patch_desc.data() + (size_t)p * 8;
-        d[0] = P->patch_node_ptr[p];
-        d[1] = P->patch_node_ptr[p + 1] - P->patch_node_ptr[p];
-        d[2] = np + ns;
-        d[3] = np;
-        d[4] = P->patch_slot_base[p];
-        // cache lines (16 doubles) of the nodal vector this patch touches
-        lines.clear();
-        for (uint32_t g : priv) lines.push_back(g >> 4);
-        for (uint32_t g : shar) lines.push_back(g >> 4);
-        std::sort(lines.begin(), lines.end());
-        lines.erase(std::unique(lines.begin(), lines.end()), lines.end());
-        const size_t nl = std::min<size_t>(lines.size(), SEMK_PF_LINES);
-        std::copy(lines.begin(), lines.begin() + nl,
-                  P->pf_lines.begin() + (size_t)p * SEMK_PF_LINES);
-      }
       max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
 
       // element-local index table + greedy colouring
@@ -239,6 +219,30 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       semk_set_error("semk_hostplan_create: patch node table overflows int32");
       return SEMK_ERR_UNSUPPORTED;
     }
+
+    // Uniform-stride device blocks, one TMA bulk copy each per patch:
+    //   node block  = {n nodes, n private, first slot, 0} + node list, 0xffffffff padded
+    //   index block = [m][le][t] patch-local indices + PE element colours (uint16)
+    const int64_t pn_stride = 4 + ((max_patch_nodes + 3) & ~(int64_t)3);
+    const int64_t el_stride = ((int64_t)NN * PE + PE + 7) & ~(int64_t)7;
+    P->pnblk.assign((size_t)n_patch * pn_stride, 0xffffffffu);
+    P->elblk.assign((size_t)n_patch * el_stride, 0);
+    for (int64_t p = 0; p < n_patch; ++p) {
+      uint32_t *blk = P->pnblk.data() + (size_t)p * pn_stride;
+      const int32_t nn = P->patch_nnodes[p];
+      blk[0] = (uint32_t)nn;
+      blk[1] = (uint32_t)P->patch_npriv[p];
+      blk[2] = (uint32_t)P->patch_slot_base[p];
+      blk[3] = 0;
+      std::copy(P->pnode.begin() + P->patch_node_ptr[p], P->pnode.begin() + P->patch_node_ptr[p] + nn,
+                blk + 4);
+      uint16_t *eb = P->elblk.data() + (size_t)p * el_stride;
+      std::copy(P->eloc.begin() + (size_t)p * ES, P->eloc.begin() + (size_t)p * ES + (size_t)NN * PE,
+                eb);
+      for (int le = 0; le < PE; ++le) eb[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
+    }
+    P->scalars[SEMK_PS_PN_STRIDE] = pn_stride;
+    P->scalars[SEMK_PS_EL_STRIDE] = el_stride;
 
     // CSR of interface slots per shared node (slots in ascending patch order)
     for (int64_t i = 0; i < n_shared; ++i) P->shared_ptr[i + 1] += P->shared_ptr[i];
@@ -292,8 +296,8 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_SHARED_PTR: return vec_ptr(plan->shared_ptr, n_bytes);
     case SEMK_PA_SHARED_SLOT: return vec_ptr(plan->shared_slot, n_bytes);
     case SEMK_PA_PATCH_NNODES: return vec_ptr(plan->patch_nnodes, n_bytes);
-    case SEMK_PA_PATCH_DESC: return vec_ptr(plan->patch_desc, n_bytes);
-    case SEMK_PA_PF_LINES: return vec_ptr(plan->pf_lines, n_bytes);
+    case SEMK_PA_PNBLK: return vec_ptr(plan->pnblk, n_bytes);
+    case SEMK_PA_ELBLK: return vec_ptr(plan->elblk, n_bytes);
     default: return nullptr;
   }
 }

@@ -27,7 +27,7 @@ from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
 __all__ = ["PoissonOperator", "PCGInfo", "default_element_order", "choose_elems_per_patch"]
 
 _TILES = {16: (4, 4), 8: (2, 4), 4: (2, 2)}
-_SMEM_TARGET = 76 * 1024     # <= this keeps >= 3 CTAs per SM
+_SMEM_TARGET = 113 * 1024    # <= this keeps >= 2 persistent CTAs per SM
 _SMEM_LIMIT = 227 * 1024
 
 
@@ -37,13 +37,18 @@ def g_patch_stride_of(n1, pe):
 
 
 def eloc_patch_stride_of(n1, pe):
-    return (n1 * n1 * pe + 7) & ~7  # uint16 entries per patch block (16-byte multiples)
+    return (n1 * n1 * pe + pe + 7) & ~7   # index table + PE colours, 16-byte multiples
+
+
+def pn_patch_stride_of(max_patch_nodes):
+    return 4 + ((int(max_patch_nodes) + 3) & ~3)   # header + node list
 
 
 def patch_smem_bytes(n1, pe, max_patch_nodes):
     """Dynamic shared memory of one CTA of the apply kernel (asks the library,
     which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
     return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_patch_stride_of(n1, pe),
+                                                 pn_patch_stride_of(max_patch_nodes),
                                                  eloc_patch_stride_of(n1, pe),
                                                  int(max_patch_nodes)))
 
@@ -117,7 +122,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, lookahead=None):
+                 elem_order=None, keep_l2g=True):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -150,12 +155,11 @@ class PoissonOperator(object):
         self.smem_bytes = smem
 
         t = {}
-        for k in (_lib.PA_PATCH_DESC, _lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT):
+        for k in (_lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT):
             t[k] = torch.from_numpy(ar[k]).to(self.dev)
-        for k in (_lib.PA_PNODE, _lib.PA_SHARED_NODE, _lib.PA_PF_LINES):
+        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_NODE):
             t[k] = device.as_i32_bits(ar[k], self.dev)
-        t[_lib.PA_ELOC] = torch.from_numpy(ar[_lib.PA_ELOC].view(np.int16)).to(self.dev)
-        t[_lib.PA_ELEM_COLOR] = torch.from_numpy(ar[_lib.PA_ELEM_COLOR]).to(self.dev)
+        t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
         self._tables = t
         self.elem_of_slot_host = ar[_lib.PA_ELEM_OF_SLOT]
@@ -205,19 +209,16 @@ class PoissonOperator(object):
         op.max_colors = sc[_lib.PS_MAX_COLORS]
         op.g_patch_stride = self.g_patch_stride
         op.G = self.G.data_ptr()
-        op.patch_desc = t[_lib.PA_PATCH_DESC].data_ptr()
-        op.pnode = t[_lib.PA_PNODE].data_ptr()
-        op.pf_lines = t[_lib.PA_PF_LINES].data_ptr()
-        op.eloc_patch_stride = sc[_lib.PS_ELOC_STRIDE]
+        op.pnode = t[_lib.PA_PNBLK].data_ptr()
+        op.pn_patch_stride = sc[_lib.PS_PN_STRIDE]
+        op.eloc = t[_lib.PA_ELBLK].data_ptr()
+        op.eloc_patch_stride = sc[_lib.PS_EL_STRIDE]
         resident = int(self._lib.semk_resident_ctas(n1, pe, self.g_patch_stride,
-                                                    sc[_lib.PS_ELOC_STRIDE],
+                                                    sc[_lib.PS_PN_STRIDE], sc[_lib.PS_EL_STRIDE],
                                                     sc[_lib.PS_MAX_PATCH_NODES]))
         if resident <= 0:
             raise RuntimeError("semk_resident_ctas failed: " + _lib.last_error())
-        self.resident_ctas = resident
-        op.lookahead = resident if lookahead is None else int(lookahead)
-        op.eloc = t[_lib.PA_ELOC].data_ptr()
-        op.elem_color = t[_lib.PA_ELEM_COLOR].data_ptr()
+        self.resident_ctas = resident      # grid of the persistent apply kernel
         op.n_slots = self.n_slots
         op.slot_buf = self.slot_buf.data_ptr()
         op.n_shared = self.n_shared

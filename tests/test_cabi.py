@@ -42,8 +42,8 @@ def test_version_and_error_channel():
 
 
 def test_struct_layout_matches_header():
-    # 25 fields; 8-byte aligned pointers after two int32 pairs
-    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 7 * 8 + 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8
+    # 22 fields; 8-byte aligned pointers after two int32 pairs
+    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.semk_pcg_info) == 24
 
 
@@ -111,16 +111,21 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     is_shared_node = np.zeros(n_nodes, dtype=bool)
     is_shared_node[ids[shared_flag]] = True
     assert sc[_lib.PS_N_PNODE] == pnode.size
-    # packed descriptors and prefetch hints
-    desc = ar[_lib.PA_PATCH_DESC].reshape(n_patch, 8)
-    assert np.array_equal(desc[:, 0], ptr[:-1]) and np.array_equal(desc[:, 1], np.diff(ptr))
-    assert np.array_equal(desc[:, 2], nnodes) and np.array_equal(desc[:, 3], npriv)
-    assert np.array_equal(desc[:, 4], base) and not desc[:, 5:].any()
-    pfl = ar[_lib.PA_PF_LINES].reshape(n_patch, _lib.PF_LINES)
+    # uniform-stride device blocks mirror the compact tables
+    PS, ELS = sc[_lib.PS_PN_STRIDE], sc[_lib.PS_EL_STRIDE]
+    assert PS % 4 == 0 and PS >= 4 + sc[_lib.PS_MAX_PATCH_NODES] and ELS % 8 == 0
+    pnblk = ar[_lib.PA_PNBLK].reshape(n_patch, PS)
+    elblk = ar[_lib.PA_ELBLK].reshape(n_patch, ELS)
     for p in range(n_patch):
-        want = np.unique(ids[ptr[p]:ptr[p] + nnodes[p]] >> 4)[:_lib.PF_LINES]
-        assert np.array_equal(pfl[p, :want.size], want)
-        assert np.all(pfl[p, want.size:] == 0xFFFFFFFF)
+        assert pnblk[p, 0] == nnodes[p] and pnblk[p, 1] == npriv[p] and pnblk[p, 2] == base[p]
+        assert np.array_equal(pnblk[p, 4:4 + nnodes[p]], pnode[ptr[p]:ptr[p] + nnodes[p]])
+        assert np.all(pnblk[p, 4 + nnodes[p]:] == 0xFFFFFFFF)
+        assert np.array_equal(elblk[p, :NN * pe], ar[_lib.PA_ELOC].reshape(-1, ES)[p, :NN * pe])
+        assert np.array_equal(elblk[p, NN * pe:NN * pe + pe], color[p * pe:(p + 1) * pe])
+    # private <=> touched by exactly one patch
+    is_shared_node = np.zeros(n_nodes, dtype=bool)
+    is_shared_node[ids[shared_flag]] = True
+    assert sc[_lib.PS_N_PNODE] == pnode.size
     assert np.array_equal(is_shared_node, touched > 1)
     # CSR of interface slots: every slot exactly once, grouped under its node
     sn = ar[_lib.PA_SHARED_NODE]
