@@ -188,12 +188,17 @@ __host__ __device__ constexpr int scratch_row_stride(int N, int PE) {
 //      (c, m) of this column sits at g[(c*N + m) * g_row].
 //   g_ready: mbarrier guarding a TMA-staged G (nullptr when g is global).
 // Contains four __syncthreads(); every thread of the CTA must call it.
-template <int N, int RS, class DM>
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+template <int N, int RS, class DM, class Hook = NoHook>
 __device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool active,
                                               const double (&ucol)[N], double (&ycol)[N],
                                               double *__restrict__ A, double *__restrict__ B,
                                               const double *__restrict__ g, int g_row,
-                                              uint64_t *g_ready, uint32_t g_parity = 0) {
+                                              uint64_t *g_ready, uint32_t g_parity = 0,
+                                              Hook g_consumed = Hook()) {
   const int tidp = le * N + t;
   double ur[N], tmp[N], us[N];
   if (active) {
@@ -226,6 +231,7 @@ __device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool 
     for (int m = 0; m < N; ++m) A[m * RS + tidp] = w1[m];
   }
   __syncthreads();
+  g_consumed();  // every thread has read its G entries: the G buffer may be refilled
   if (active) {
 #pragma unroll
     for (int n = 0; n < N; ++n) tmp[n] = A[t * RS + le * N + n];  // row t of w1
@@ -249,10 +255,10 @@ struct PatchCfg {
 enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 
 // Shared-memory carve-up of the persistent patch kernel (offsets multiples of
-// 16 B).  Two pipeline stages of {G block, node block, index block}; one copy
-// of the working arrays.
+// 16 B): one G buffer, two stages of {node block, index block}, one copy of
+// the working arrays.
 struct PatchSmem {
-  size_t stage0, stage_bytes, g_off, pn_off, el_off;  // per stage: G | node block | index block
+  size_t gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
   size_t yp, ua, bs, red, total;
 };
 __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
@@ -263,12 +269,12 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
   PatchSmem L;
   const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
   const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
-  size_t o = 64;  // four mbarriers: tables[2], G[2]
+  size_t o = 32;  // three mbarriers: tables[2], G
+  L.gs = o;
+  o += (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
   L.stage0 = o;
-  L.g_off = 0;
-  size_t st = (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
-  L.pn_off = st;
-  st += 4 * (size_t)pn_patch_stride;
+  L.pn_off = 0;
+  size_t st = 4 * (size_t)pn_patch_stride;
   L.el_off = st;
   st += 2 * (size_t)eloc_patch_stride;
   st = (st + 15) & ~(size_t)15;
@@ -280,13 +286,31 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
   L.ua = o;  // u staging, later scratch A
   o += (mode == MODE_APPLY) ? 8 * (mpn4 > scratch ? mpn4 : scratch) : 0;
   o = (o + 15) & ~(size_t)15;
-  L.bs = o;
-  o += (mode == MODE_APPLY) ? 8 * scratch : 0;
-  o = (o + 15) & ~(size_t)15;
-  L.red = o;
-  o += 8 * 32;
+  L.bs = o;  // scratch B; its head doubles as the block-reduction scratch at the very end
+  const size_t bsz = (mode == MODE_APPLY) ? 8 * scratch : 0;
+  o += bsz > 256 ? bsz : 256;
+  L.red = L.bs;
   L.total = o;
   return L;
+}
+
+// Resident CTAs per SM the kernel is compiled for (register budget): what the
+// shared-memory footprint of the standard tiles (4x4, 2x4, 2x2 elements) allows.
+__host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
+  const int bx = PE == 16 ? 4 : 2, by = PE == 4 ? 2 : 4, p = N - 1;
+  const long long mpn = (long long)(bx * p + 1) * (by * p + 1);
+  const long long mpn4 = (mpn + 3) & ~3LL;
+  const long long nn = (long long)N * N;
+  const long long g = 8 * ((3 * nn * PE + 1) & ~1LL);
+  const long long tab = 2 * ((4 * (4 + mpn4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
+  const long long scr = 8LL * N * scratch_row_stride(N, PE);
+  const long long ua = 8 * mpn4 > scr ? 8 * mpn4 : scr;
+  const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
+  const long long by_smem = 233472 / total;
+  const int threads = ((N * PE + 31) / 32) * 32;
+  const long long by_regs = 65536 / ((long long)threads * 96);  // assume <= 96 registers/thread
+  long long r = by_smem < by_regs ? by_smem : by_regs;
+  return r < 1 ? 1 : (r > 8 ? 8 : (int)r);
 }
 
 constexpr int kGatherBatch = 8;
@@ -305,7 +329,7 @@ constexpr int kGatherBatch = 8;
 // MODE_APPLY:    y = A u (masked per flags), optional dot partials.
 // MODE_ASSEMBLE: y = assembly of the element-local field `loc` (slot order).
 template <int N, int PE, int MODE>
-__global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
+__global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N, PE))
     patch_kernel(semk_op op, DMatEO dm, const double *__restrict__ u,
                  const double *__restrict__ loc, double *__restrict__ y, int flags,
                  double fill_dirichlet, double *__restrict__ dot_partials) {
@@ -316,7 +340,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
                                         op.eloc_patch_stride, op.max_patch_nodes);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2..3]: G
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2]: G
+  double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
   double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
   double *up = reinterpret_cast<double *>(smem_raw + L.ua);  // aliases scratch A
   double *As = up;
@@ -330,22 +355,25 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
   const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
 
   auto stage_ptr = [&](int s) { return smem_raw + L.stage0 + (size_t)s * L.stage_bytes; };
-  auto issue_loads = [&](int64_t patch, int s) {  // one thread
+  auto issue_tables = [&](int64_t patch, int s) {  // one thread
     unsigned char *base = stage_ptr(s);
     semk_mbar_expect_tx(&mbar[s], pn_bytes + el_bytes);
     semk_bulk_g2s(base + L.pn_off, op.pnode + patch * op.pn_patch_stride, pn_bytes, &mbar[s]);
     semk_bulk_g2s(base + L.el_off, op.eloc + patch * op.eloc_patch_stride, el_bytes, &mbar[s]);
-    if (MODE == MODE_APPLY) {
-      semk_mbar_expect_tx(&mbar[2 + s], g_bytes);
-      semk_bulk_g2s(base + L.g_off, op.G + patch * op.g_patch_stride, g_bytes, &mbar[2 + s]);
-    }
+  };
+  auto issue_g = [&](int64_t patch) {  // one thread
+    semk_mbar_expect_tx(&mbar[2], g_bytes);
+    semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[2]);
   };
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) semk_mbar_init(&mbar[i], 1);
+    for (int i = 0; i < 3; ++i) semk_mbar_init(&mbar[i], 1);
     semk_fence_mbar_init();
-    if ((int64_t)blockIdx.x < op.n_patch) issue_loads(blockIdx.x, 0);
+    if ((int64_t)blockIdx.x < op.n_patch) {
+      issue_tables(blockIdx.x, 0);
+      if (MODE == MODE_APPLY) issue_g(blockIdx.x);
+    }
   }
   __syncthreads();  // mbarrier initialisation visible to every waiter
 
@@ -377,10 +405,9 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
     const int64_t next = patch + gridDim.x;
     const bool has_next = next < op.n_patch;
     // stage s^1 was released by the barrier that ended the previous iteration
-    if (tid == 0 && has_next) issue_loads(next, s ^ 1);
+    if (tid == 0 && has_next) issue_tables(next, s ^ 1);
 
     unsigned char *sb = stage_ptr(s);
-    const double *Gs = reinterpret_cast<const double *>(sb + L.g_off);
     const uint32_t *pn_blk = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
     const uint16_t *el_s = reinterpret_cast<const uint16_t *>(sb + L.el_off);
     semk_mbar_wait(&mbar[s], par);
@@ -429,14 +456,14 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads)
         for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
       }
       __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
-      if (flags & 0x100) {  // profiling ablation (internal): skip the element operator
-        semk_mbar_wait(&mbar[2 + s], par);
-#pragma unroll
-        for (int m = 0; m < N; ++m) ycol[m] = ucol[m] + Gs[m * NP + tid];
-      } else {
-        local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2 + s],
-                             par);
-      }
+      // The single G buffer is refilled for the next patch as soon as every thread
+      // has consumed this patch's factors (hook runs right after that barrier):
+      // the copy then has the rest of this patch and the start of the next to land.
+      auto refill_g = [&]() {
+        if (tid == 0 && has_next) issue_g(next);
+      };
+      local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2],
+                           (uint32_t)(it & 1), refill_g);
       // next patch: its node block landed long ago; start its gather now so the
       // loads fly during the assembly and write-out below
       if (has_next) {
