@@ -283,8 +283,8 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
   L.yp = o;
   o += 8 * mpn4;
   o = (o + 15) & ~(size_t)15;
-  L.ua = o;  // u staging, later scratch A
-  o += (mode == MODE_APPLY) ? 8 * (mpn4 > scratch ? mpn4 : scratch) : 0;
+  L.ua = o;  // scratch A
+  o += (mode == MODE_APPLY) ? 8 * scratch : 0;
   o = (o + 15) & ~(size_t)15;
   L.bs = o;  // scratch B; its head doubles as the block-reduction scratch at the very end
   const size_t bsz = (mode == MODE_APPLY) ? 8 * scratch : 0;
@@ -304,7 +304,7 @@ __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
   const long long g = 8 * ((3 * nn * PE + 1) & ~1LL);
   const long long tab = 2 * ((4 * (4 + mpn4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
   const long long scr = 8LL * N * scratch_row_stride(N, PE);
-  const long long ua = 8 * mpn4 > scr ? 8 * mpn4 : scr;
+  const long long ua = scr;
   const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
   const long long by_smem = 233472 / total;
   const int threads = ((N * PE + 31) / 32) * 32;
@@ -343,8 +343,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2]: G
   double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
   double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
-  double *up = reinterpret_cast<double *>(smem_raw + L.ua);  // aliases scratch A
-  double *As = up;
+  double *As = reinterpret_cast<double *>(smem_raw + L.ua);
   double *Bs = reinterpret_cast<double *>(smem_raw + L.bs);
   double *red = reinterpret_cast<double *>(smem_raw + L.red);
 
@@ -377,24 +376,35 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   }
   __syncthreads();  // mbarrier initialisation visible to every waiter
 
-  // nodal values of the patch about to be processed, staged in registers
-  uint32_t gpn[kGatherBatch];
-  double gv[kGatherBatch];
-  auto gather_to_regs = [&](const uint32_t *pn_blk) {
-    const int nn = (int)pn_blk[0];
+  // This thread's column of nodal values for the patch about to be processed,
+  // gathered straight from global memory through the staged tables (entries of
+  // nodes shared by several elements of the patch hit L1) and carried in
+  // registers across the loop: the gather for patch i+1 is issued right after
+  // the element operator of patch i, so its latency hides behind the assembly
+  // and write-out of patch i.
+  double ucol[N];
+  auto gather_column = [&](int s_tab, int64_t patch_of) {
+    const unsigned char *sbn = stage_ptr(s_tab);
+    const uint32_t *pnb = reinterpret_cast<const uint32_t *>(sbn + L.pn_off) + 4;
+    const uint16_t *elb = reinterpret_cast<const uint16_t *>(sbn + L.el_off);
+    const bool act = (le < PE) && (patch_of * PE + le < op.n_elem);
+    if (act) {
+      uint32_t pn[N];
 #pragma unroll
-    for (int j = 0; j < kGatherBatch; ++j) {
-      const int k = tid + j * kThreads;
-      gpn[j] = (k < nn) ? pn_blk[4 + k] : 0xffffffffu;
+      for (int m = 0; m < N; ++m) pn[m] = pnb[elb[m * NP + tid]];
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        const double v = u[pn[m] & SEMK_NODE_ID_MASK];
+        ucol[m] = ((pn[m] & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : v;
+      }
     }
-#pragma unroll
-    for (int j = 0; j < kGatherBatch; ++j)
-      gv[j] = (gpn[j] != 0xffffffffu) ? u[gpn[j] & SEMK_NODE_ID_MASK] : 0.0;
   };
+  for (int k = tid; k < op.max_patch_nodes; k += kThreads) yp[k] = 0.0;
   if (MODE == MODE_APPLY && (int64_t)blockIdx.x < op.n_patch) {
     semk_mbar_wait(&mbar[0], 0);
-    gather_to_regs(reinterpret_cast<const uint32_t *>(stage_ptr(0) + L.pn_off));
+    gather_column(0, blockIdx.x);
   }
+  __syncthreads();
 
   double dot = 0.0;
   const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
@@ -418,25 +428,6 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     const int64_t slot0 = patch * PE;
     const bool active = (le < PE) && (slot0 + le < op.n_elem);
 
-    // ---- nodal values (prefetched into registers) -> shared memory ----------------
-    if (MODE == MODE_APPLY) {
-#pragma unroll
-      for (int j = 0; j < kGatherBatch; ++j) {
-        const int k = tid + j * kThreads;
-        if (k < npn) {
-          up[k] = ((gpn[j] & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : gv[j];
-          yp[k] = 0.0;
-        }
-      }
-      for (int k = tid + kGatherBatch * kThreads; k < npn; k += kThreads) {  // oversized patch
-        const uint32_t pn = pn_s[k];
-        const double v = u[pn & SEMK_NODE_ID_MASK];
-        up[k] = ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : v;
-        yp[k] = 0.0;
-      }
-    } else {
-      for (int k = tid; k < npn; k += kThreads) yp[k] = 0.0;
-    }
     // this thread's column of patch-local node indices (table rows are [m][le][t]),
     // and the colour of its element (stored behind the table)
     uint16_t idx[N];
@@ -446,16 +437,9 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       for (int m = 0; m < N; ++m) idx[m] = el_s[m * NP + tid];
       color = el_s[NN * PE + le];
     }
-    __syncthreads();
 
     double ycol[N];
     if (MODE == MODE_APPLY) {
-      double ucol[N];
-      if (active) {
-#pragma unroll
-        for (int m = 0; m < N; ++m) ucol[m] = up[idx[m]];
-      }
-      __syncthreads();  // `up` is dead from here on: its storage becomes scratch A
       // The single G buffer is refilled for the next patch as soon as every thread
       // has consumed this patch's factors (hook runs right after that barrier):
       // the copy then has the rest of this patch and the start of the next to land.
@@ -464,11 +448,10 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       };
       local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2],
                            (uint32_t)(it & 1), refill_g);
-      // next patch: its node block landed long ago; start its gather now so the
-      // loads fly during the assembly and write-out below
+      // next patch: its tables landed long ago; start its gather now
       if (has_next) {
         semk_mbar_wait(&mbar[s ^ 1], (uint32_t)(((it + 1) >> 1) & 1));
-        gather_to_regs(reinterpret_cast<const uint32_t *>(stage_ptr(s ^ 1) + L.pn_off));
+        gather_column(s ^ 1, next);
       }
     } else {
       if (active) {
@@ -487,31 +470,47 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       __syncthreads();
     }
 
-    // ---- write out: private nodes -> y, shared nodes -> interface slots --------
-    for (int k = tid; k < npn; k += kThreads) {
-      const uint32_t pn = pn_s[k];
-      double v = yp[k];
-      if (k < npriv) {
-        const uint32_t g = pn & SEMK_NODE_ID_MASK;
-        const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
-        double uin = 0.0;
-        if (MODE == MODE_APPLY) {
-          if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
-        }
-        if (dir && (flags & SEMK_MASK_OUT)) {
+    // ---- write out: private nodes -> y, shared nodes -> interface slots; the
+    // accumulator is cleared for the next patch on the way --------------------------
+    for (int k0 = tid; k0 < npn; k0 += kGatherBatch * kThreads) {
+      uint32_t pnv[kGatherBatch];
+      double vv[kGatherBatch];
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j) {
+        const int k = k0 + j * kThreads;
+        const bool in = k < npn;
+        pnv[j] = in ? pn_s[k] : 0xffffffffu;
+        vv[j] = in ? yp[k] : 0.0;
+        if (in) yp[k] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j) {
+        const int k = k0 + j * kThreads;
+        if (k >= npn) continue;
+        const uint32_t pn = pnv[j];
+        double v = vv[j];
+        if (k < npriv) {
+          const uint32_t g = pn & SEMK_NODE_ID_MASK;
+          const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
+          double uin = 0.0;
           if (MODE == MODE_APPLY) {
-            v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
-            uin = v;
-          } else {
-            v = fill_dirichlet;
+            if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
           }
-        } else if (dir && (flags & SEMK_MASK_IN)) {
-          uin = 0.0;
+          if (dir && (flags & SEMK_MASK_OUT)) {
+            if (MODE == MODE_APPLY) {
+              v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
+              uin = v;
+            } else {
+              v = fill_dirichlet;
+            }
+          } else if (dir && (flags & SEMK_MASK_IN)) {
+            uin = 0.0;
+          }
+          y[g] = v;
+          dot = fma(uin, v, dot);
+        } else {
+          op.slot_buf[slot_base + (k - npriv)] = v;
         }
-        y[g] = v;
-        dot = fma(uin, v, dot);
-      } else {
-        op.slot_buf[slot_base + (k - npriv)] = v;
       }
     }
     __syncthreads();  // stage s, yp and the scratch are free for the next iteration
