@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   // the element operator of patch i, so its latency hides behind the assembly
   // and write-out of patch i.
   double ucol[N];
+  uint32_t ucol_dir = 0;  // bit m set: entry m of the staged column is a Dirichlet node
   auto gather_column = [&](int s_tab, int64_t patch_of) {
     const unsigned char *sbn = stage_ptr(s_tab);
     const uint32_t *pnb = reinterpret_cast<const uint32_t *>(sbn + L.pn_off) + 4;
@@ -392,10 +393,13 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       uint32_t pn[N];
 #pragma unroll
       for (int m = 0; m < N; ++m) pn[m] = pnb[elb[m * NP + tid]];
+      // loads only: nothing below may depend on the values until the next patch
+      // starts, or the warp would stall here instead of overlapping the latency
+      ucol_dir = 0;
 #pragma unroll
       for (int m = 0; m < N; ++m) {
-        const double v = u[pn[m] & SEMK_NODE_ID_MASK];
-        ucol[m] = ((pn[m] & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_IN)) ? 0.0 : v;
+        ucol[m] = u[pn[m] & SEMK_NODE_ID_MASK];
+        ucol_dir |= (pn[m] >> 31) << m;
       }
     }
   };
@@ -440,6 +444,11 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
 
     double ycol[N];
     if (MODE == MODE_APPLY) {
+      if ((flags & SEMK_MASK_IN) && ucol_dir) {
+#pragma unroll
+        for (int m = 0; m < N; ++m)
+          if ((ucol_dir >> m) & 1u) ucol[m] = 0.0;
+      }
       // The single G buffer is refilled for the next patch as soon as every thread
       // has consumed this patch's factors (hook runs right after that barrier):
       // the copy then has the rest of this patch and the start of the next to land.
