@@ -83,7 +83,7 @@ enum semk_plan_array {
                                  node (m,t) of the le-th element of the patch            */
   SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
   SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
-  SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
+  SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, by first interface slot */
   SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
   SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node    */
   SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */

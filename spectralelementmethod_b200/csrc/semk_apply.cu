@@ -192,13 +192,14 @@ struct NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
 
-template <int N, int RS, class DM, class Hook = NoHook>
+template <int N, int RS, class DM, class Hook = NoHook, class Hook0 = NoHook>
 __device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool active,
                                               const double (&ucol)[N], double (&ycol)[N],
                                               double *__restrict__ A, double *__restrict__ B,
                                               const double *__restrict__ g, int g_row,
                                               uint64_t *g_ready, uint32_t g_parity = 0,
-                                              Hook g_consumed = Hook()) {
+                                              Hook g_consumed = Hook(),
+                                              Hook0 after_first_barrier = Hook0()) {
   const int tidp = le * N + t;
   double ur[N], tmp[N], us[N];
   if (active) {
@@ -206,6 +207,7 @@ __device__ __forceinline__ void local_poisson(const DM &dm, int le, int t, bool 
     for (int m = 0; m < N; ++m) A[m * RS + tidp] = ucol[m];
   }
   __syncthreads();
+  after_first_barrier();  // every thread has left the previous patch's write-out
   if (active) {
     mat_D<N>(dm, ucol, ur);  // ur[m][t] = sum_r D[m][r] u[r][t]
 #pragma unroll
@@ -418,9 +420,6 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     const uint32_t par = (uint32_t)((it >> 1) & 1);
     const int64_t next = patch + gridDim.x;
     const bool has_next = next < op.n_patch;
-    // stage s^1 was released by the barrier that ended the previous iteration
-    if (tid == 0 && has_next) issue_tables(next, s ^ 1);
-
     unsigned char *sb = stage_ptr(s);
     const uint32_t *pn_blk = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
     const uint16_t *el_s = reinterpret_cast<const uint16_t *>(sb + L.el_off);
@@ -455,14 +454,21 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       auto refill_g = [&]() {
         if (tid == 0 && has_next) issue_g(next);
       };
+      // Table stage s^1 (patch i-1's tables) is free once every thread has passed the
+      // first barrier of this patch's operator: no end-of-patch barrier is needed.
+      auto refill_tables = [&]() {
+        if (tid == 0 && has_next) issue_tables(next, s ^ 1);
+      };
       local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2],
-                           (uint32_t)(it & 1), refill_g);
+                           (uint32_t)(it & 1), refill_g, refill_tables);
       // next patch: its tables landed long ago; start its gather now
       if (has_next) {
         semk_mbar_wait(&mbar[s ^ 1], (uint32_t)(((it + 1) >> 1) & 1));
         gather_column(s ^ 1, next);
       }
     } else {
+      __syncthreads();  // previous patch's write-out done: its table stage may be refilled
+      if (tid == 0 && has_next) issue_tables(next, s ^ 1);
       if (active) {
         const double *lr = loc + (slot0 + le) * NN;
 #pragma unroll
@@ -522,7 +528,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
         }
       }
     }
-    __syncthreads();  // stage s, yp and the scratch are free for the next iteration
+    // no barrier here: the next patch's first operator barrier orders this write-out
+    // (reads of stage s and of yp) before anything that could overwrite them
   }
   if (want_dot) {
     const double sres = semk_block_sum(dot, red);
@@ -543,8 +550,19 @@ __global__ void __launch_bounds__(256)
     const uint32_t pn = op.shared_node[i];
     const uint32_t g = pn & SEMK_NODE_ID_MASK;
     const int j0 = op.shared_ptr[i], j1 = op.shared_ptr[i + 1];
-    double v = 0.0;
-    for (int j = j0; j < j1; ++j) v += op.slot_buf[op.shared_slot[j]];
+    // the usual cases (an edge: 2 patches, a corner: 4) with independent loads
+    double v;
+    if (j1 - j0 == 2) {
+      const int s0 = op.shared_slot[j0], s1 = op.shared_slot[j0 + 1];
+      v = op.slot_buf[s0] + op.slot_buf[s1];
+    } else if (j1 - j0 == 4) {
+      const int s0 = op.shared_slot[j0], s1 = op.shared_slot[j0 + 1];
+      const int s2 = op.shared_slot[j0 + 2], s3 = op.shared_slot[j0 + 3];
+      v = ((op.slot_buf[s0] + op.slot_buf[s1]) + op.slot_buf[s2]) + op.slot_buf[s3];
+    } else {
+      v = 0.0;
+      for (int j = j0; j < j1; ++j) v += op.slot_buf[op.shared_slot[j]];
+    }
     const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
     double uin = 0.0;
     if (MODE == MODE_APPLY) {

@@ -252,6 +252,32 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       for (const auto &pr : slot_pairs) P->shared_slot[fill[pr.first]++] = pr.second;
     }
 
+    // Order the shared nodes by their first interface slot (= slot order of the lowest
+    // patch touching them) instead of by node id: consecutive threads of the interface
+    // kernel then read consecutive slots, also along patch edges that run across the
+    // node numbering.
+    if (n_shared > 0) {
+      std::vector<int32_t> order(n_shared);
+      for (int64_t i = 0; i < n_shared; ++i) order[i] = (int32_t)i;
+      std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return P->shared_slot[P->shared_ptr[a]] < P->shared_slot[P->shared_ptr[b]];
+      });
+      std::vector<uint32_t> node2(n_shared);
+      std::vector<int32_t> ptr2(n_shared + 1, 0), slot2(n_slots);
+      int32_t at = 0;
+      for (int64_t i = 0; i < n_shared; ++i) {
+        const int32_t o = order[i];
+        node2[i] = P->shared_node[o];
+        ptr2[i] = at;
+        for (int32_t j = P->shared_ptr[o]; j < P->shared_ptr[o + 1]; ++j)
+          slot2[at++] = P->shared_slot[j];
+      }
+      ptr2[n_shared] = at;
+      P->shared_node.swap(node2);
+      P->shared_ptr.swap(ptr2);
+      P->shared_slot.swap(slot2);
+    }
+
     P->scalars[SEMK_PS_N_PATCH] = n_patch;
     P->scalars[SEMK_PS_N_PNODE] = (int64_t)P->pnode.size();
     P->scalars[SEMK_PS_N_SLOTS] = n_slots;

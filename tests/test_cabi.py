@@ -132,8 +132,12 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     sp = ar[_lib.PA_SHARED_PTR]
     ss = ar[_lib.PA_SHARED_SLOT]
     assert sc[_lib.PS_N_SHARED] == sn.size == is_shared_node.sum()
-    assert np.all(np.diff((sn & _lib.NODE_ID_MASK).astype(np.int64)) > 0)
+    assert len(set((sn & _lib.NODE_ID_MASK).tolist())) == sn.size
     assert sp[0] == 0 and sp[-1] == ss.size == slots_seen
+    first = ss[sp[:-1]]
+    assert np.all(np.diff(first) > 0)               # ordered by first interface slot
+    for i in range(sn.size):
+        assert np.all(np.diff(ss[sp[i]:sp[i + 1]]) > 0)
     assert sorted(ss.tolist()) == list(range(slots_seen))
     slot_node = np.empty(slots_seen, dtype=np.int64)
     for p in range(n_patch):
