@@ -83,7 +83,7 @@ enum semk_plan_array {
                                  node (m,t) of the le-th element of the patch            */
   SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
   SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
-  SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, by first interface slot */
+  SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
   SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
   SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node    */
   SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
@@ -92,7 +92,11 @@ enum semk_plan_array {
                                  the patch's node list (as in PNODE), 0xffffffff padded     */
   SEMK_PA_ELBLK = 12,         /* uint16 [n_patch][el_stride] device index blocks: the ELOC
                                  table [m][le][t] followed by the PE element colours        */
-  SEMK_PA_COUNT = 13
+  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared][4] {node id | flags, slot 0, slot 1, ext}: what the
+                                 interface kernel reads; ext = 0xffffffff or offset in SHARED_EXT */
+  SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         {extra count, extra slots...} for nodes shared
+                                 by more than two patches                                       */
+  SEMK_PA_COUNT = 15
 };
 
 enum semk_plan_scalar {
@@ -147,9 +151,8 @@ typedef struct semk_op {
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums (scratch)  */
   int64_t n_shared;
-  const uint32_t *shared_node;
-  const int32_t *shared_ptr;
-  const int32_t *shared_slot;
+  const uint32_t *shared_rec; /* [n_shared][4] packed interface records (SEMK_PA_SHARED_REC) */
+  const uint32_t *shared_ext; /* overflow slot lists (SEMK_PA_SHARED_EXT)                    */
   double *partials;         /* [semk_partials_len()] dot-product scratch    */
   const double *D_host;     /* HOST pointer, [NN] differentiation matrix    */
   const uint8_t *dirichlet; /* [n_nodes] 1 = essential-BC node, or NULL (PCG: not an unknown) */

@@ -21,7 +21,7 @@ MAX_N1 = 17
 
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
- PA_PNBLK, PA_ELBLK) = range(13)
+ PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT) = range(15)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
  PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE) = range(10)
 
@@ -30,7 +30,7 @@ PLAN_ARRAY_DTYPES = {
     PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16, PA_ELEM_COLOR: np.uint8,
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
     PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
-    PA_ELBLK: np.uint16,
+    PA_ELBLK: np.uint16, PA_SHARED_REC: np.uint32, PA_SHARED_EXT: np.uint32,
 }
 
 
@@ -54,8 +54,7 @@ class semk_op(C.Structure):
         ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
-        ("n_shared", C.c_int64), ("shared_node", C.c_void_p), ("shared_ptr", C.c_void_p),
-        ("shared_slot", C.c_void_p),
+        ("n_shared", C.c_int64), ("shared_rec", C.c_void_p), ("shared_ext", C.c_void_p),
         ("partials", C.c_void_p), ("D_host", C.c_void_p), ("dirichlet", C.c_void_p),
     ]
 

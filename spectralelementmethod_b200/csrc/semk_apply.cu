@@ -547,21 +547,14 @@ __global__ void __launch_bounds__(256)
   double dot = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < op.n_shared;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t pn = op.shared_node[i];
+    const uint4 rec = reinterpret_cast<const uint4 *>(op.shared_rec)[i];
+    const uint32_t pn = rec.x;
     const uint32_t g = pn & SEMK_NODE_ID_MASK;
-    const int j0 = op.shared_ptr[i], j1 = op.shared_ptr[i + 1];
-    // the usual cases (an edge: 2 patches, a corner: 4) with independent loads
-    double v;
-    if (j1 - j0 == 2) {
-      const int s0 = op.shared_slot[j0], s1 = op.shared_slot[j0 + 1];
-      v = op.slot_buf[s0] + op.slot_buf[s1];
-    } else if (j1 - j0 == 4) {
-      const int s0 = op.shared_slot[j0], s1 = op.shared_slot[j0 + 1];
-      const int s2 = op.shared_slot[j0 + 2], s3 = op.shared_slot[j0 + 3];
-      v = ((op.slot_buf[s0] + op.slot_buf[s1]) + op.slot_buf[s2]) + op.slot_buf[s3];
-    } else {
-      v = 0.0;
-      for (int j = j0; j < j1; ++j) v += op.slot_buf[op.shared_slot[j]];
+    double v = op.slot_buf[rec.y] + op.slot_buf[rec.z];  // ascending patch order
+    if (rec.w != 0xffffffffu) {                           // corner nodes: 3+ patches
+      const uint32_t *ext = op.shared_ext + rec.w;
+      const uint32_t extra = ext[0];
+      for (uint32_t j = 0; j < extra; ++j) v += op.slot_buf[ext[1 + j]];
     }
     const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
     double uin = 0.0;
@@ -789,7 +782,7 @@ int check_op(const semk_op *op, const char *who) {
       (op->eloc_patch_stride & 7) != 0 ||
       op->eloc_patch_stride < nnp + op->elems_per_patch ||
       (op->n_slots > 0 && !op->slot_buf) ||
-      (op->n_shared > 0 && (!op->shared_node || !op->shared_ptr || !op->shared_slot))) {
+      (op->n_shared > 0 && (!op->shared_rec || !op->shared_ext))) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
     return SEMK_ERR_INVALID;
   }

@@ -31,7 +31,7 @@ struct semk_hostplan {
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
       shared_slot;
-  std::vector<uint32_t> pnode, shared_node, pnblk;
+  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext;
   std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
@@ -252,31 +252,24 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       for (const auto &pr : slot_pairs) P->shared_slot[fill[pr.first]++] = pr.second;
     }
 
-    // Order the shared nodes by their first interface slot (= slot order of the lowest
-    // patch touching them) instead of by node id: consecutive threads of the interface
-    // kernel then read consecutive slots, also along patch edges that run across the
-    // node numbering.
-    if (n_shared > 0) {
-      std::vector<int32_t> order(n_shared);
-      for (int64_t i = 0; i < n_shared; ++i) order[i] = (int32_t)i;
-      std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-        return P->shared_slot[P->shared_ptr[a]] < P->shared_slot[P->shared_ptr[b]];
-      });
-      std::vector<uint32_t> node2(n_shared);
-      std::vector<int32_t> ptr2(n_shared + 1, 0), slot2(n_slots);
-      int32_t at = 0;
-      for (int64_t i = 0; i < n_shared; ++i) {
-        const int32_t o = order[i];
-        node2[i] = P->shared_node[o];
-        ptr2[i] = at;
-        for (int32_t j = P->shared_ptr[o]; j < P->shared_ptr[o + 1]; ++j)
-          slot2[at++] = P->shared_slot[j];
+    // Packed records for the interface kernel: {node id | flags, slot 0, slot 1, ext};
+    // ext = 0xffffffff for the usual two contributors, else an offset into SHARED_EXT
+    // where {extra count, extra slots...} continue the list (ascending patch order).
+    P->shared_rec.assign((size_t)n_shared * 4, 0xffffffffu);
+    for (int64_t i = 0; i < n_shared; ++i) {
+      uint32_t *r = P->shared_rec.data() + (size_t)i * 4;
+      const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
+      r[0] = P->shared_node[i];
+      r[1] = (uint32_t)P->shared_slot[j0];
+      r[2] = (uint32_t)P->shared_slot[j0 + 1];
+      if (cnt > 2) {
+        r[3] = (uint32_t)P->shared_ext.size();
+        P->shared_ext.push_back((uint32_t)(cnt - 2));
+        for (int32_t j = j0 + 2; j < j0 + cnt; ++j)
+          P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
       }
-      ptr2[n_shared] = at;
-      P->shared_node.swap(node2);
-      P->shared_ptr.swap(ptr2);
-      P->shared_slot.swap(slot2);
     }
+    if (P->shared_ext.empty()) P->shared_ext.push_back(0);
 
     P->scalars[SEMK_PS_N_PATCH] = n_patch;
     P->scalars[SEMK_PS_N_PNODE] = (int64_t)P->pnode.size();
@@ -324,6 +317,8 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_PATCH_NNODES: return vec_ptr(plan->patch_nnodes, n_bytes);
     case SEMK_PA_PNBLK: return vec_ptr(plan->pnblk, n_bytes);
     case SEMK_PA_ELBLK: return vec_ptr(plan->elblk, n_bytes);
+    case SEMK_PA_SHARED_REC: return vec_ptr(plan->shared_rec, n_bytes);
+    case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
     default: return nullptr;
   }
 }

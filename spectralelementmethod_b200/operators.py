@@ -155,9 +155,7 @@ class PoissonOperator(object):
         self.smem_bytes = smem
 
         t = {}
-        for k in (_lib.PA_SHARED_PTR, _lib.PA_SHARED_SLOT):
-            t[k] = torch.from_numpy(ar[k]).to(self.dev)
-        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_NODE):
+        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT):
             t[k] = device.as_i32_bits(ar[k], self.dev)
         t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
@@ -222,9 +220,8 @@ class PoissonOperator(object):
         op.n_slots = self.n_slots
         op.slot_buf = self.slot_buf.data_ptr()
         op.n_shared = self.n_shared
-        op.shared_node = t[_lib.PA_SHARED_NODE].data_ptr() if self.n_shared else None
-        op.shared_ptr = t[_lib.PA_SHARED_PTR].data_ptr() if self.n_shared else None
-        op.shared_slot = t[_lib.PA_SHARED_SLOT].data_ptr() if self.n_shared else None
+        op.shared_rec = t[_lib.PA_SHARED_REC].data_ptr() if self.n_shared else None
+        op.shared_ext = t[_lib.PA_SHARED_EXT].data_ptr() if self.n_shared else None
         op.partials = self.partials.data_ptr()
         op.D_host = self.tab.D_host.ctypes.data
         op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None

@@ -42,8 +42,8 @@ def test_version_and_error_channel():
 
 
 def test_struct_layout_matches_header():
-    # 22 fields; 8-byte aligned pointers after two int32 pairs
-    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 3 * 8 + 8 + 8 + 8
+    # 21 fields; 8-byte aligned pointers after two int32 pairs
+    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 2 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.semk_pcg_info) == 24
 
 
@@ -132,12 +132,20 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     sp = ar[_lib.PA_SHARED_PTR]
     ss = ar[_lib.PA_SHARED_SLOT]
     assert sc[_lib.PS_N_SHARED] == sn.size == is_shared_node.sum()
-    assert len(set((sn & _lib.NODE_ID_MASK).tolist())) == sn.size
+    assert np.all(np.diff((sn & _lib.NODE_ID_MASK).astype(np.int64)) > 0)
     assert sp[0] == 0 and sp[-1] == ss.size == slots_seen
-    first = ss[sp[:-1]]
-    assert np.all(np.diff(first) > 0)               # ordered by first interface slot
+    # packed records mirror the CSR (slots in ascending patch order)
+    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 4)
+    ext = ar[_lib.PA_SHARED_EXT]
+    assert rec.shape[0] == sn.size
     for i in range(sn.size):
-        assert np.all(np.diff(ss[sp[i]:sp[i + 1]]) > 0)
+        lst = ss[sp[i]:sp[i + 1]]
+        assert np.all(np.diff(lst) > 0) and lst.size >= 2
+        got = [rec[i, 1], rec[i, 2]]
+        if rec[i, 3] != 0xFFFFFFFF:
+            k = rec[i, 3]
+            got += ext[k + 1:k + 1 + ext[k]].tolist()
+        assert rec[i, 0] == sn[i] and got == lst.tolist()
     assert sorted(ss.tolist()) == list(range(slots_seen))
     slot_node = np.empty(slots_seen, dtype=np.int64)
     for p in range(n_patch):
