@@ -304,7 +304,9 @@ __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
   const long long mpn4 = (mpn + 3) & ~3LL;
   const long long nn = (long long)N * N;
   const long long g = 8 * ((3 * nn * PE + 1) & ~1LL);
-  const long long tab = 2 * ((4 * (4 + mpn4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
+  const long long perim4 = (2LL * (bx * p + 1) + 2LL * (by * p + 1) - 4 + 3) & ~3LL;
+  const long long tab =
+      2 * ((4 * (4 + mpn4 + perim4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
   const long long scr = 8LL * N * scratch_row_stride(N, PE);
   const long long ua = scr;
   const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     semk_mbar_wait(&mbar[s], par);
     const int npn = (int)pn_blk[0];
     const int npriv = (int)pn_blk[1];
-    const int slot_base = (int)pn_blk[2];
+    const uint32_t *pn_slot = pn_blk + pn_blk[2];  // device slots of the shared nodes
     const uint32_t *pn_s = pn_blk + 4;
     const int64_t slot0 = patch * PE;
     const bool active = (le < PE) && (slot0 + le < op.n_elem);
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
           y[g] = v;
           dot = fma(uin, v, dot);
         } else {
-          op.slot_buf[slot_base + (k - npriv)] = v;
+          op.slot_buf[pn_slot[k - npriv]] = v;
         }
       }
     }
@@ -547,15 +549,13 @@ __global__ void __launch_bounds__(256)
   double dot = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < op.n_shared;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 rec = reinterpret_cast<const uint4 *>(op.shared_rec)[i];
+    const uint2 rec = reinterpret_cast<const uint2 *>(op.shared_rec)[i];
     const uint32_t pn = rec.x;
     const uint32_t g = pn & SEMK_NODE_ID_MASK;
-    double v = op.slot_buf[rec.y] + op.slot_buf[rec.z];  // ascending patch order
-    if (rec.w != 0xffffffffu) {                           // corner nodes: 3+ patches
-      const uint32_t *ext = op.shared_ext + rec.w;
-      const uint32_t extra = ext[0];
-      for (uint32_t j = 0; j < extra; ++j) v += op.slot_buf[ext[1 + j]];
-    }
+    const double *sl = op.slot_buf + (rec.y & 0x0fffffffu);
+    const uint32_t cnt = rec.y >> 28;
+    double v = sl[0] + sl[1];  // ascending patch order: deterministic
+    for (uint32_t j = 2; j < cnt; ++j) v += sl[j];
     const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
     double uin = 0.0;
     if (MODE == MODE_APPLY) {
@@ -782,7 +782,7 @@ int check_op(const semk_op *op, const char *who) {
       (op->eloc_patch_stride & 7) != 0 ||
       op->eloc_patch_stride < nnp + op->elems_per_patch ||
       (op->n_slots > 0 && !op->slot_buf) ||
-      (op->n_shared > 0 && (!op->shared_rec || !op->shared_ext))) {
+      (op->n_shared > 0 && !op->shared_rec)) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
     return SEMK_ERR_INVALID;
   }

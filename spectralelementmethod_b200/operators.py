@@ -40,15 +40,24 @@ def eloc_patch_stride_of(n1, pe):
     return (n1 * n1 * pe + pe + 7) & ~7   # index table + PE colours, 16-byte multiples
 
 
-def pn_patch_stride_of(max_patch_nodes):
-    return 4 + ((int(max_patch_nodes) + 3) & ~3)   # header + node list
+def pn_patch_stride_of(max_patch_nodes, max_patch_shared=None):
+    """header + node list + device slot ids of the shared nodes"""
+    if max_patch_shared is None:            # worst case estimate: every node shared
+        max_patch_shared = max_patch_nodes
+    return 4 + ((int(max_patch_nodes) + 3) & ~3) + ((int(max_patch_shared) + 3) & ~3)
 
 
-def patch_smem_bytes(n1, pe, max_patch_nodes):
+def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None):
     """Dynamic shared memory of one CTA of the apply kernel (asks the library,
     which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
+    if pn_stride is None:
+        p = n1 - 1
+        bx, by = _TILES[pe]
+        # shared nodes of an interior structured tile = its perimeter nodes
+        perim = 2 * (bx * p + 1) + 2 * (by * p + 1) - 4
+        pn_stride = pn_patch_stride_of(max_patch_nodes, min(perim, max_patch_nodes))
     return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_patch_stride_of(n1, pe),
-                                                 pn_patch_stride_of(max_patch_nodes),
+                                                 int(pn_stride),
                                                  eloc_patch_stride_of(n1, pe),
                                                  int(max_patch_nodes)))
 
@@ -147,7 +156,7 @@ class PoissonOperator(object):
             elem_order = default_element_order(mesh, pe)
         sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
         self.plan_scalars = sc
-        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES])
+        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE])
         if smem > _SMEM_LIMIT:
             raise NotImplementedError(
                 "patch of %d elements needs %d B of shared memory (> 227 KB); pass a smaller "
@@ -155,7 +164,7 @@ class PoissonOperator(object):
         self.smem_bytes = smem
 
         t = {}
-        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT):
+        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_REC):
             t[k] = device.as_i32_bits(ar[k], self.dev)
         t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
@@ -221,7 +230,6 @@ class PoissonOperator(object):
         op.slot_buf = self.slot_buf.data_ptr()
         op.n_shared = self.n_shared
         op.shared_rec = t[_lib.PA_SHARED_REC].data_ptr() if self.n_shared else None
-        op.shared_ext = t[_lib.PA_SHARED_EXT].data_ptr() if self.n_shared else None
         op.partials = self.partials.data_ptr()
         op.D_host = self.tab.D_host.ctypes.data
         op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None
