@@ -539,7 +539,11 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   }
 }
 
-// Sum the interface slots of every shared node in a fixed order.
+// Sum the interface slots of every shared node in a fixed order.  Each thread
+// handles kSharedUnroll nodes with all record loads, then all slot loads, in
+// flight together: the kernel is a two-level dependent gather and is purely
+// latency-bound otherwise.
+constexpr int kSharedUnroll = 4;
 template <int MODE>
 __global__ void __launch_bounds__(256)
     shared_nodes_kernel(semk_op op, const double *__restrict__ u, double *__restrict__ y,
@@ -547,32 +551,51 @@ __global__ void __launch_bounds__(256)
                         int64_t partial_offset) {
   __shared__ double red[32];
   double dot = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < op.n_shared;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const uint2 rec = reinterpret_cast<const uint2 *>(op.shared_rec)[i];
-    const uint32_t pn = rec.x;
-    const uint32_t g = pn & SEMK_NODE_ID_MASK;
-    const double *sl = op.slot_buf + (rec.y & 0x0fffffffu);
-    const uint32_t cnt = rec.y >> 28;
-    double v = sl[0] + sl[1];  // ascending patch order: deterministic
-    for (uint32_t j = 2; j < cnt; ++j) v += sl[j];
-    const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
-    double uin = 0.0;
-    if (MODE == MODE_APPLY) {
-      if (dot_partials || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < op.n_shared;
+       i0 += stride * kSharedUnroll) {
+    uint2 rec[kSharedUnroll];
+    double a[kSharedUnroll], b[kSharedUnroll];
+#pragma unroll
+    for (int k = 0; k < kSharedUnroll; ++k) {
+      const int64_t i = i0 + k * stride;
+      rec[k] = (i < op.n_shared) ? reinterpret_cast<const uint2 *>(op.shared_rec)[i]
+                                 : make_uint2(0xffffffffu, 0u);
     }
-    if (dir && (flags & SEMK_MASK_OUT)) {
+#pragma unroll
+    for (int k = 0; k < kSharedUnroll; ++k) {
+      const bool on = rec[k].x != 0xffffffffu;
+      const double *sl = op.slot_buf + (rec[k].y & 0x0fffffffu);
+      a[k] = on ? sl[0] : 0.0;
+      b[k] = on ? sl[1] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kSharedUnroll; ++k) {
+      if (rec[k].x == 0xffffffffu) continue;
+      const uint32_t pn = rec[k].x;
+      const uint32_t g = pn & SEMK_NODE_ID_MASK;
+      const double *sl = op.slot_buf + (rec[k].y & 0x0fffffffu);
+      const uint32_t cnt = rec[k].y >> 28;
+      double v = a[k] + b[k];  // ascending patch order: deterministic
+      for (uint32_t j = 2; j < cnt; ++j) v += sl[j];
+      const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
+      double uin = 0.0;
       if (MODE == MODE_APPLY) {
-        v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
-        uin = v;
-      } else {
-        v = fill_dirichlet;
+        if (dot_partials || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
       }
-    } else if (dir && (flags & SEMK_MASK_IN)) {
-      uin = 0.0;
+      if (dir && (flags & SEMK_MASK_OUT)) {
+        if (MODE == MODE_APPLY) {
+          v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
+          uin = v;
+        } else {
+          v = fill_dirichlet;
+        }
+      } else if (dir && (flags & SEMK_MASK_IN)) {
+        uin = 0.0;
+      }
+      y[g] = v;
+      dot = fma(uin, v, dot);
     }
-    y[g] = v;
-    dot = fma(uin, v, dot);
   }
   if (MODE == MODE_APPLY && dot_partials) {
     const double s = semk_block_sum(dot, red);
@@ -859,7 +882,7 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
   if (rc != SEMK_OK) return rc;
   int shared_blocks = 0;
   if (op->n_shared > 0) {
-    const int64_t want = (op->n_shared + 255) / 256;
+    const int64_t want = (op->n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
     shared_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
     shared_nodes_kernel<MODE_APPLY><<<shared_blocks, 256, 0, st>>>(*op, u, y, flags, 0.0, partials,
                                                                   grid);
@@ -884,7 +907,7 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
                                    nullptr);
   if (rc != SEMK_OK) return rc;
   if (op->n_shared > 0) {
-    const int64_t want = (op->n_shared + 255) / 256;
+    const int64_t want = (op->n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
     const int blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
     shared_nodes_kernel<MODE_ASSEMBLE><<<blocks, 256, 0, st>>>(*op, nullptr, out, flags,
                                                               fill_dirichlet, nullptr, 0);

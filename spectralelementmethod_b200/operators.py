@@ -97,7 +97,7 @@ def _morton_order(cx, cy):
     return np.argsort(key, kind="stable").astype(np.int64)
 
 
-def default_element_order(mesh, elems_per_patch):
+def default_element_order(mesh, elems_per_patch, tile=None):
     """Engine slot order (slot -> element) that makes consecutive runs of
     ``elems_per_patch`` elements compact patches: tiles of a structured grid
     when the mesh builder recorded one, else a Morton curve through the cell
@@ -105,7 +105,9 @@ def default_element_order(mesh, elems_per_patch):
     shape = getattr(mesh, "_structured_shape", None)
     if shape is not None and shape[0] * shape[1] == mesh.n_cells:
         nx, ny = shape
-        bx, by = _TILES[elems_per_patch]
+        bx, by = tile if tile is not None else _TILES[elems_per_patch]
+        if bx * by != elems_per_patch:
+            raise ValueError("tile shape does not match elems_per_patch")
         ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
         key = ((ex // bx) * ((ny + by - 1) // by) + ey // by) * (bx * by) + (ex % bx) * by + ey % by
         return np.argsort(key, kind="stable").astype(np.int64)
@@ -131,7 +133,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True):
+                 elem_order=None, keep_l2g=True, tile=None):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -153,7 +155,7 @@ class PoissonOperator(object):
 
         pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
         if elem_order is None:
-            elem_order = default_element_order(mesh, pe)
+            elem_order = default_element_order(mesh, pe, tile)
         sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
         self.plan_scalars = sc
         smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE])
