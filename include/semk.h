@@ -77,28 +77,26 @@ enum semk_plan_array {
   SEMK_PA_PNODE = 1,          /* uint32 [n_pnode]     global id | flags; private nodes first;
                                  each patch padded with 0xffffffff to a multiple of 4       */
   SEMK_PA_PATCH_NPRIV = 2,    /* int32  [n_patch]     number of private nodes of the patch   */
-  SEMK_PA_PATCH_SLOT_BASE = 3,/* int32  [n_patch]     offset of the patch's shared nodes in PSLOT */
+  SEMK_PA_PATCH_SLOT_BASE = 3,/* int32  [n_patch]     first interface slot of the patch      */
   SEMK_PA_ELOC = 4,           /* uint16 [n_patch][eloc_patch_stride]: per patch a table
                                  [m][le][t] (NN*PE entries) of patch-local node indices:
                                  node (m,t) of the le-th element of the patch            */
   SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
   SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
   SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
-  SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  device slots of shared node i are
-                                 [ptr[i], ptr[i+1]), one per touching patch, ascending patch   */
-  SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     patch-order position (PATCH_SLOT_BASE[p] + k)
-                                 of each device slot: inverse of PSLOT                          */
+  SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
+  SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node,
+                                 ascending patch (slot = PATCH_SLOT_BASE[p] + k)             */
   SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
   SEMK_PA_PNBLK = 11,         /* uint32 [n_patch][pn_stride] device node blocks, uniform stride:
-                                 {n nodes, n private, offset of slot ids, 0}, the patch's node
-                                 list (as in PNODE, 0xffffffff padded) and, at the given offset,
-                                 the device slot of each of its shared nodes                   */
+                                 {n nodes, n private, first interface slot, 0} followed by
+                                 the patch's node list (as in PNODE), 0xffffffff padded     */
   SEMK_PA_ELBLK = 12,         /* uint16 [n_patch][el_stride] device index blocks: the ELOC
                                  table [m][le][t] followed by the PE element colours        */
-  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared][2] {node id | flags, first slot | count << 28}:
-                                 what the interface kernel reads                            */
-  SEMK_PA_PSLOT = 14,         /* int32  [n_slots]     device slot of the k-th shared node of
-                                 patch p, at PATCH_SLOT_BASE[p] + k                         */
+  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared][4] {node id | flags, slot 0, slot 1, ext}: what the
+                                 interface kernel reads; ext = 0xffffffff or offset in SHARED_EXT */
+  SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         {extra count, extra slots...} for nodes shared
+                                 by more than two patches                                       */
   SEMK_PA_COUNT = 15
 };
 
@@ -113,8 +111,7 @@ enum semk_plan_scalar {
   SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per patch block of ELOC: NN*PE rounded up to 8 */
   SEMK_PS_PN_STRIDE = 8,      /* uint32 entries per patch block of PNBLK (multiple of 4)       */
   SEMK_PS_EL_STRIDE = 9,      /* uint16 entries per patch block of ELBLK (multiple of 8)       */
-  SEMK_PS_PN_SLOT_OFF = 10,   /* offset of the slot ids inside a PNBLK block                   */
-  SEMK_PS_COUNT = 11
+  SEMK_PS_COUNT = 10
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
@@ -153,9 +150,10 @@ typedef struct semk_op {
   const uint16_t *eloc;     /* [n_patch][eloc_patch_stride] index blocks (SEMK_PA_ELBLK) */
   int64_t eloc_patch_stride;/* uint16 entries per index block (multiple of 8)            */
   int64_t n_slots;
-  double *slot_buf;         /* [n_slots] interface partial sums, node-ordered (scratch) */
+  double *slot_buf;         /* [n_slots] interface partial sums, contiguous per patch (scratch) */
   int64_t n_shared;
-  const uint32_t *shared_rec; /* [n_shared][2] packed interface records (SEMK_PA_SHARED_REC) */
+  const uint32_t *shared_rec; /* [n_shared][4] packed interface records (SEMK_PA_SHARED_REC) */
+  const uint32_t *shared_ext; /* overflow slot lists (SEMK_PA_SHARED_EXT)                    */
   double *partials;         /* [semk_partials_len()] dot-product scratch    */
   const double *D_host;     /* HOST pointer, [NN] differentiation matrix    */
   const uint8_t *dirichlet; /* [n_nodes] 1 = essential-BC node, or NULL (PCG: not an unknown) */

@@ -297,16 +297,14 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
 }
 
 // Resident CTAs per SM the kernel is compiled for (register budget): what the
-// shared-memory footprint of the standard tiles (4x4, 2x4, 2x2 elements) allows.
+// shared-memory footprint of the standard tiles (2x8, 1x8, 1x4 elements) allows.
 __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
-  const int bx = PE == 16 ? 4 : 2, by = PE == 4 ? 2 : 4, p = N - 1;
+  const int bx = PE == 16 ? 2 : 1, by = PE == 4 ? 4 : 8, p = N - 1;
   const long long mpn = (long long)(bx * p + 1) * (by * p + 1);
   const long long mpn4 = (mpn + 3) & ~3LL;
   const long long nn = (long long)N * N;
   const long long g = 8 * ((3 * nn * PE + 1) & ~1LL);
-  const long long perim4 = (2LL * (bx * p + 1) + 2LL * (by * p + 1) - 4 + 3) & ~3LL;
-  const long long tab =
-      2 * ((4 * (4 + mpn4 + perim4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
+  const long long tab = 2 * ((4 * (4 + mpn4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
   const long long scr = 8LL * N * scratch_row_stride(N, PE);
   const long long ua = scr;
   const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
@@ -428,7 +426,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     semk_mbar_wait(&mbar[s], par);
     const int npn = (int)pn_blk[0];
     const int npriv = (int)pn_blk[1];
-    const uint32_t *pn_slot = pn_blk + pn_blk[2];  // device slots of the shared nodes
+    const int slot_base = (int)pn_blk[2];
     const uint32_t *pn_s = pn_blk + 4;
     const int64_t slot0 = patch * PE;
     const bool active = (le < PE) && (slot0 + le < op.n_elem);
@@ -526,7 +524,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
           y[g] = v;
           dot = fma(uin, v, dot);
         } else {
-          op.slot_buf[pn_slot[k - npriv]] = v;
+          op.slot_buf[slot_base + (k - npriv)] = v;
         }
       }
     }
@@ -554,30 +552,31 @@ __global__ void __launch_bounds__(256)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < op.n_shared;
        i0 += stride * kSharedUnroll) {
-    uint2 rec[kSharedUnroll];
+    uint4 rec[kSharedUnroll];
     double a[kSharedUnroll], b[kSharedUnroll];
 #pragma unroll
     for (int k = 0; k < kSharedUnroll; ++k) {
       const int64_t i = i0 + k * stride;
-      rec[k] = (i < op.n_shared) ? reinterpret_cast<const uint2 *>(op.shared_rec)[i]
-                                 : make_uint2(0xffffffffu, 0u);
+      rec[k] = (i < op.n_shared) ? reinterpret_cast<const uint4 *>(op.shared_rec)[i]
+                                 : make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu);
     }
 #pragma unroll
     for (int k = 0; k < kSharedUnroll; ++k) {
       const bool on = rec[k].x != 0xffffffffu;
-      const double *sl = op.slot_buf + (rec[k].y & 0x0fffffffu);
-      a[k] = on ? sl[0] : 0.0;
-      b[k] = on ? sl[1] : 0.0;
+      a[k] = on ? op.slot_buf[rec[k].y] : 0.0;
+      b[k] = on ? op.slot_buf[rec[k].z] : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < kSharedUnroll; ++k) {
       if (rec[k].x == 0xffffffffu) continue;
       const uint32_t pn = rec[k].x;
       const uint32_t g = pn & SEMK_NODE_ID_MASK;
-      const double *sl = op.slot_buf + (rec[k].y & 0x0fffffffu);
-      const uint32_t cnt = rec[k].y >> 28;
       double v = a[k] + b[k];  // ascending patch order: deterministic
-      for (uint32_t j = 2; j < cnt; ++j) v += sl[j];
+      if (rec[k].w != 0xffffffffu) {  // corner nodes: 3+ patches
+        const uint32_t *ext = op.shared_ext + rec[k].w;
+        const uint32_t extra = ext[0];
+        for (uint32_t j = 0; j < extra; ++j) v += op.slot_buf[ext[1 + j]];
+      }
       const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
       double uin = 0.0;
       if (MODE == MODE_APPLY) {
@@ -805,7 +804,7 @@ int check_op(const semk_op *op, const char *who) {
       (op->eloc_patch_stride & 7) != 0 ||
       op->eloc_patch_stride < nnp + op->elems_per_patch ||
       (op->n_slots > 0 && !op->slot_buf) ||
-      (op->n_shared > 0 && !op->shared_rec)) {
+      (op->n_shared > 0 && (!op->shared_rec || !op->shared_ext))) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
     return SEMK_ERR_INVALID;
   }

@@ -31,8 +31,7 @@ struct semk_hostplan {
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
       shared_slot;
-  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec;
-  std::vector<int32_t> pslot;
+  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext;
   std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
@@ -229,34 +228,31 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       for (const auto &pr : slot_pairs) P->shared_slot[fill[pr.first]++] = pr.second;
     }
 
-    // Device slot numbering is NODE-ordered: the partial sums of shared node i live at
-    // slots [shared_ptr[i], shared_ptr[i+1]) in ascending patch order, so the interface
-    // kernel reads them as one contiguous 16..32-byte run.  PSLOT maps a patch's k-th
-    // shared node (patch-order position patch_slot_base[p] + k) to its device slot.
-    P->pslot.assign(n_slots, 0);
-    for (int64_t j = 0; j < n_slots; ++j) P->pslot[P->shared_slot[j]] = (int32_t)j;
-    // Packed records for the interface kernel: {node id | flags, first slot | count << 28}
-    P->shared_rec.assign((size_t)n_shared * 2, 0);
+    // Device slots are PATCH-ordered: patch p writes the partial sums of its shared nodes
+    // to the contiguous run [patch_slot_base[p], +n shared) (coalesced stores).  Packed
+    // records for the interface kernel: {node id | flags, slot 0, slot 1, ext}; ext =
+    // 0xffffffff for the usual two contributors, else an offset into SHARED_EXT where
+    // {extra count, extra slots...} continue the list (ascending patch order).
+    P->shared_rec.assign((size_t)n_shared * 4, 0xffffffffu);
     for (int64_t i = 0; i < n_shared; ++i) {
+      uint32_t *r = P->shared_rec.data() + (size_t)i * 4;
       const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
-      if (cnt > 15 || j0 >= (1 << 28)) {
-        delete P;
-        semk_set_error("semk_hostplan_create: shared node touched by > 15 patches or > 2^28 slots");
-        return SEMK_ERR_UNSUPPORTED;
+      r[0] = P->shared_node[i];
+      r[1] = (uint32_t)P->shared_slot[j0];
+      r[2] = (uint32_t)P->shared_slot[j0 + 1];
+      if (cnt > 2) {
+        r[3] = (uint32_t)P->shared_ext.size();
+        P->shared_ext.push_back((uint32_t)(cnt - 2));
+        for (int32_t j = j0 + 2; j < j0 + cnt; ++j)
+          P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
       }
-      P->shared_rec[2 * i] = P->shared_node[i];
-      P->shared_rec[2 * i + 1] = (uint32_t)j0 | ((uint32_t)cnt << 28);
     }
+    if (P->shared_ext.empty()) P->shared_ext.push_back(0);
 
     // Uniform-stride device blocks, one TMA bulk copy each per patch:
     //   node block  = {n nodes, n private, first slot, 0} + node list, 0xffffffff padded
     //   index block = [m][le][t] patch-local indices + PE element colours (uint16)
-    int64_t max_patch_shared = 0;
-    for (int64_t p = 0; p < n_patch; ++p)
-      max_patch_shared = std::max<int64_t>(max_patch_shared,
-                                           P->patch_nnodes[p] - P->patch_npriv[p]);
-    const int64_t pn_slot_off = 4 + ((max_patch_nodes + 3) & ~(int64_t)3);
-    const int64_t pn_stride = pn_slot_off + ((max_patch_shared + 3) & ~(int64_t)3);
+    const int64_t pn_stride = 4 + ((max_patch_nodes + 3) & ~(int64_t)3);
     const int64_t el_stride = ((int64_t)NN * PE + PE + 7) & ~(int64_t)7;
     P->pnblk.assign((size_t)n_patch * pn_stride, 0xffffffffu);
     P->elblk.assign((size_t)n_patch * el_stride, 0);
@@ -265,20 +261,16 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       const int32_t nn = P->patch_nnodes[p];
       blk[0] = (uint32_t)nn;
       blk[1] = (uint32_t)P->patch_npriv[p];
-      blk[2] = (uint32_t)pn_slot_off;  // where this block's device slot ids start
+      blk[2] = (uint32_t)P->patch_slot_base[p];
       blk[3] = 0;
       std::copy(P->pnode.begin() + P->patch_node_ptr[p], P->pnode.begin() + P->patch_node_ptr[p] + nn,
                 blk + 4);
-      const int32_t nsh = nn - P->patch_npriv[p];
-      for (int32_t k = 0; k < nsh; ++k)
-        blk[pn_slot_off + k] = (uint32_t)P->pslot[P->patch_slot_base[p] + k];
       uint16_t *eb = P->elblk.data() + (size_t)p * el_stride;
       std::copy(P->eloc.begin() + (size_t)p * ES, P->eloc.begin() + (size_t)p * ES + (size_t)NN * PE,
                 eb);
       for (int le = 0; le < PE; ++le) eb[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
     }
     P->scalars[SEMK_PS_PN_STRIDE] = pn_stride;
-    P->scalars[SEMK_PS_PN_SLOT_OFF] = pn_slot_off;
     P->scalars[SEMK_PS_EL_STRIDE] = el_stride;
 
     P->scalars[SEMK_PS_N_PATCH] = n_patch;
@@ -328,7 +320,7 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_PNBLK: return vec_ptr(plan->pnblk, n_bytes);
     case SEMK_PA_ELBLK: return vec_ptr(plan->elblk, n_bytes);
     case SEMK_PA_SHARED_REC: return vec_ptr(plan->shared_rec, n_bytes);
-    case SEMK_PA_PSLOT: return vec_ptr(plan->pslot, n_bytes);
+    case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
     default: return nullptr;
   }
 }

@@ -42,8 +42,8 @@ def test_version_and_error_channel():
 
 
 def test_struct_layout_matches_header():
-    # 20 fields; 8-byte aligned pointers after two int32 pairs
-    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 1 * 8 + 8 + 8 + 8
+    # 21 fields; 8-byte aligned pointers after two int32 pairs
+    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 2 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.semk_pcg_info) == 24
 
 
@@ -113,18 +113,13 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     assert sc[_lib.PS_N_PNODE] == pnode.size
     # uniform-stride device blocks mirror the compact tables
     PS, ELS = sc[_lib.PS_PN_STRIDE], sc[_lib.PS_EL_STRIDE]
-    SO = sc[_lib.PS_PN_SLOT_OFF]
-    pslot = ar[_lib.PA_PSLOT]
-    assert PS % 4 == 0 and SO >= 4 + sc[_lib.PS_MAX_PATCH_NODES] and SO % 4 == 0 and ELS % 8 == 0
+    assert PS % 4 == 0 and PS >= 4 + sc[_lib.PS_MAX_PATCH_NODES] and ELS % 8 == 0
     pnblk = ar[_lib.PA_PNBLK].reshape(n_patch, PS)
     elblk = ar[_lib.PA_ELBLK].reshape(n_patch, ELS)
     for p in range(n_patch):
-        assert pnblk[p, 0] == nnodes[p] and pnblk[p, 1] == npriv[p] and pnblk[p, 2] == SO
+        assert pnblk[p, 0] == nnodes[p] and pnblk[p, 1] == npriv[p] and pnblk[p, 2] == base[p]
         assert np.array_equal(pnblk[p, 4:4 + nnodes[p]], pnode[ptr[p]:ptr[p] + nnodes[p]])
-        assert np.all(pnblk[p, 4 + nnodes[p]:SO] == 0xFFFFFFFF)
-        nsh = nnodes[p] - npriv[p]
-        assert SO + nsh <= PS
-        assert np.array_equal(pnblk[p, SO:SO + nsh], pslot[base[p]:base[p] + nsh])
+        assert np.all(pnblk[p, 4 + nnodes[p]:] == 0xFFFFFFFF)
         assert np.array_equal(elblk[p, :NN * pe], ar[_lib.PA_ELOC].reshape(-1, ES)[p, :NN * pe])
         assert np.array_equal(elblk[p, NN * pe:NN * pe + pe], color[p * pe:(p + 1) * pe])
     # private <=> touched by exactly one patch
@@ -139,15 +134,18 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     assert sc[_lib.PS_N_SHARED] == sn.size == is_shared_node.sum()
     assert np.all(np.diff((sn & _lib.NODE_ID_MASK).astype(np.int64)) > 0)
     assert sp[0] == 0 and sp[-1] == ss.size == slots_seen
-    # device slots are node-ordered; PSLOT is the inverse of SHARED_SLOT
-    assert np.array_equal(pslot[ss], np.arange(slots_seen))
-    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 2)
+    # packed records mirror the CSR (slots in ascending patch order)
+    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 4)
+    ext = ar[_lib.PA_SHARED_EXT]
     assert rec.shape[0] == sn.size
-    assert np.array_equal(rec[:, 0], sn)
-    assert np.array_equal(rec[:, 1] & 0x0FFFFFFF, sp[:-1])
-    assert np.array_equal(rec[:, 1] >> 28, np.diff(sp))
     for i in range(sn.size):
-        assert np.all(np.diff(ss[sp[i]:sp[i + 1]]) > 0)     # ascending patch order
+        lst = ss[sp[i]:sp[i + 1]]
+        assert np.all(np.diff(lst) > 0) and lst.size >= 2
+        got = [rec[i, 1], rec[i, 2]]
+        if rec[i, 3] != 0xFFFFFFFF:
+            k = rec[i, 3]
+            got += ext[k + 1:k + 1 + ext[k]].tolist()
+        assert rec[i, 0] == sn[i] and got == lst.tolist()
 
 
 @pytest.mark.parametrize("nx,ny,p,pe", [(8, 8, 8, 16), (5, 3, 4, 16), (7, 5, 2, 8), (3, 3, 10, 4),
@@ -161,9 +159,9 @@ def test_hostplan_structured(nx, ny, p, pe):
     dirichlet = (rng.uniform(size=n_nodes) < 0.2).astype(np.uint8)
     l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, dirichlet)
     check_plan(l2g, n_nodes, sc, ar, pe, dirichlet)
-    if (nx, ny, p, pe) == (8, 8, 8, 16):
+    if (nx, ny, p, pe) == (8, 8, 8, 16):          # 2x8 tiles: a 4x1 arrangement of patches
         assert sc[_lib.PS_N_PATCH] == 4 and sc[_lib.PS_MAX_COLORS] == 4
-        assert sc[_lib.PS_MAX_PATCH_NODES] == 33 * 33 and sc[_lib.PS_N_SHARED] == 129
+        assert sc[_lib.PS_MAX_PATCH_NODES] == 17 * 65 and sc[_lib.PS_N_SHARED] == 3 * 65
 
 
 def test_hostplan_scrambled_numbering_and_order():
@@ -207,7 +205,9 @@ def test_default_element_order_tiles():
     mesh = meshgen.structured_quad_mesh(8, 8, 1)
     order = operators.default_element_order(mesh, 16)
     first = sorted(order[:16].tolist())
-    assert first == sorted(ex * 8 + ey for ex in range(4) for ey in range(4))
+    assert first == sorted(ex * 8 + ey for ex in range(2) for ey in range(8))
+    o44 = operators.default_element_order(mesh, 16, tile=(4, 4))
+    assert sorted(o44[:16].tolist()) == sorted(ex * 8 + ey for ex in range(4) for ey in range(4))
     mesh._structured_shape = None
     mo = operators.default_element_order(mesh, 16)
     assert sorted(mo.tolist()) == list(range(64))
