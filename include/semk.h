@@ -93,11 +93,15 @@ enum semk_plan_array {
                                  the patch's node list (as in PNODE), 0xffffffff padded     */
   SEMK_PA_ELBLK = 12,         /* uint16 [n_patch][el_stride] device index blocks: the ELOC
                                  table [m][le][t] followed by the PE element colours        */
-  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared][4] {node id | flags, slot 0, slot 1, ext}: what the
-                                 interface kernel reads; ext = 0xffffffff or offset in SHARED_EXT */
+  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared_rec][4] {node id | flags, slot 0, slot 1, ext} for the
+                                 shared nodes not covered by a chunk; ext = 0xffffffff or offset
+                                 in SHARED_EXT                                                   */
   SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         {extra count, extra slots...} for nodes shared
                                  by more than two patches                                       */
-  SEMK_PA_COUNT = 15
+  SEMK_PA_SHARED_CHUNK = 15,  /* uint32 [n_shared_chunk][8] affine chunks of <= 32 two-patch nodes:
+                                 {node0, dn, a0, da, b0, db, len, Dirichlet mask};
+                                 node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
+  SEMK_PA_COUNT = 16
 };
 
 enum semk_plan_scalar {
@@ -111,7 +115,9 @@ enum semk_plan_scalar {
   SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per patch block of ELOC: NN*PE rounded up to 8 */
   SEMK_PS_PN_STRIDE = 8,      /* uint32 entries per patch block of PNBLK (multiple of 4)       */
   SEMK_PS_EL_STRIDE = 9,      /* uint16 entries per patch block of ELBLK (multiple of 8)       */
-  SEMK_PS_COUNT = 10
+  SEMK_PS_N_SHARED_CHUNK = 10,/* number of affine interface chunks                             */
+  SEMK_PS_N_SHARED_REC = 11,  /* number of per-node interface records                          */
+  SEMK_PS_COUNT = 12
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
@@ -151,15 +157,18 @@ typedef struct semk_op {
   int64_t eloc_patch_stride;/* uint16 entries per index block (multiple of 8)            */
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums, contiguous per patch (scratch) */
-  int64_t n_shared;
+  int64_t n_shared;           /* number of per-node interface records                        */
   const uint32_t *shared_rec; /* [n_shared][4] packed interface records (SEMK_PA_SHARED_REC) */
   const uint32_t *shared_ext; /* overflow slot lists (SEMK_PA_SHARED_EXT)                    */
+  int64_t n_shared_chunk;     /* number of affine interface chunks                           */
+  const uint32_t *shared_chunk; /* [n_shared_chunk][8] (SEMK_PA_SHARED_CHUNK)                */
   double *partials;         /* [semk_partials_len()] dot-product scratch    */
   const double *D_host;     /* HOST pointer, [NN] differentiation matrix    */
   const uint8_t *dirichlet; /* [n_nodes] 1 = essential-BC node, or NULL (PCG: not an unknown) */
 } semk_op;
 
-/* number of doubles the `partials` scratch of an operator must hold */
+/* number of doubles the `partials` scratch of an operator must hold
+ * (n_shared = total number of shared nodes, SEMK_PS_N_SHARED) */
 int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
 /* CTAs of the apply kernel that are co-resident on the current device for this
  * configuration = the grid of the persistent kernel; <0 on error */

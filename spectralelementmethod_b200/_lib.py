@@ -21,9 +21,10 @@ MAX_N1 = 17
 
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
- PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT) = range(15)
+ PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT, PA_SHARED_CHUNK) = range(16)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
- PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE) = range(10)
+ PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE, PS_N_SHARED_CHUNK,
+ PS_N_SHARED_REC) = range(12)
 
 PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
@@ -31,6 +32,7 @@ PLAN_ARRAY_DTYPES = {
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
     PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
     PA_ELBLK: np.uint16, PA_SHARED_REC: np.uint32, PA_SHARED_EXT: np.uint32,
+    PA_SHARED_CHUNK: np.uint32,
 }
 
 
@@ -55,6 +57,7 @@ class semk_op(C.Structure):
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_rec", C.c_void_p), ("shared_ext", C.c_void_p),
+        ("n_shared_chunk", C.c_int64), ("shared_chunk", C.c_void_p),
         ("partials", C.c_void_p), ("D_host", C.c_void_p), ("dirichlet", C.c_void_p),
     ]
 
@@ -167,7 +170,7 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
     check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p,
                                    int(elems_per_patch), dir_p, C.byref(handle)))
     try:
-        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(10)}
+        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(12)}
         arrays = {}
         for k, dt in PLAN_ARRAY_DTYPES.items():
             nb = _L(0)

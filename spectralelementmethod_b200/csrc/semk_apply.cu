@@ -537,66 +537,98 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   }
 }
 
-// Sum the interface slots of every shared node in a fixed order.  Each thread
-// handles kSharedUnroll nodes with all record loads, then all slot loads, in
-// flight together: the kernel is a two-level dependent gather and is purely
-// latency-bound otherwise.
+// Interface reduction: sum the partial sums of every shared node in a fixed
+// order (ascending patch) and write the node's final value.
+//   CTAs [0, chunk_blocks): one warp per affine chunk of <= 32 two-patch nodes --
+//     node ids and both slot runs are arithmetic progressions, so a whole patch
+//     edge is reduced with coalesced accesses and 32 bytes of table per chunk;
+//   remaining CTAs: per-node records (corner nodes, irregular pairs), each thread
+//     kSharedUnroll nodes with all record loads, then all slot loads, in flight.
 constexpr int kSharedUnroll = 4;
+constexpr int kChunkWarps = 8;  // chunks per CTA of 256 threads
+
+template <int MODE>
+__device__ __forceinline__ double finish_shared_node(const semk_op &op, uint32_t g, bool dir,
+                                                     double v, const double *__restrict__ u,
+                                                     double *__restrict__ y, int flags,
+                                                     double fill_dirichlet, bool want_dot) {
+  double uin = 0.0;
+  if (MODE == MODE_APPLY) {
+    if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
+  }
+  if (dir && (flags & SEMK_MASK_OUT)) {
+    if (MODE == MODE_APPLY) {
+      v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
+      uin = v;
+    } else {
+      v = fill_dirichlet;
+    }
+  } else if (dir && (flags & SEMK_MASK_IN)) {
+    uin = 0.0;
+  }
+  y[g] = v;
+  return uin * v;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
     shared_nodes_kernel(semk_op op, const double *__restrict__ u, double *__restrict__ y,
                         int flags, double fill_dirichlet, double *__restrict__ dot_partials,
-                        int64_t partial_offset) {
+                        int64_t partial_offset, int chunk_blocks) {
   __shared__ double red[32];
   double dot = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < op.n_shared;
-       i0 += stride * kSharedUnroll) {
-    uint4 rec[kSharedUnroll];
-    double a[kSharedUnroll], b[kSharedUnroll];
-#pragma unroll
-    for (int k = 0; k < kSharedUnroll; ++k) {
-      const int64_t i = i0 + k * stride;
-      rec[k] = (i < op.n_shared) ? reinterpret_cast<const uint4 *>(op.shared_rec)[i]
-                                 : make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu);
-    }
-#pragma unroll
-    for (int k = 0; k < kSharedUnroll; ++k) {
-      const bool on = rec[k].x != 0xffffffffu;
-      a[k] = on ? op.slot_buf[rec[k].y] : 0.0;
-      b[k] = on ? op.slot_buf[rec[k].z] : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < kSharedUnroll; ++k) {
-      if (rec[k].x == 0xffffffffu) continue;
-      const uint32_t pn = rec[k].x;
-      const uint32_t g = pn & SEMK_NODE_ID_MASK;
-      double v = a[k] + b[k];  // ascending patch order: deterministic
-      if (rec[k].w != 0xffffffffu) {  // corner nodes: 3+ patches
-        const uint32_t *ext = op.shared_ext + rec[k].w;
-        const uint32_t extra = ext[0];
-        for (uint32_t j = 0; j < extra; ++j) v += op.slot_buf[ext[1 + j]];
+  const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
+  if ((int)blockIdx.x < chunk_blocks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * kChunkWarps + (threadIdx.x >> 5);
+    if (c < op.n_shared_chunk) {
+      const uint4 c0 = reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c];
+      const uint4 c1 = reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c + 1];
+      // c0 = {node0, dn, a0, da}, c1 = {b0, db, len, Dirichlet mask}
+      if (lane < (int)c1.z) {
+        const uint32_t g = c0.x + (uint32_t)lane * c0.y;
+        const double va = op.slot_buf[c0.z + (uint32_t)lane * c0.w];
+        const double vb = op.slot_buf[c1.x + (uint32_t)lane * c1.y];
+        dot += finish_shared_node<MODE>(op, g, ((c1.w >> lane) & 1u) != 0, va + vb, u, y, flags,
+                                        fill_dirichlet, want_dot);
       }
-      const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
-      double uin = 0.0;
-      if (MODE == MODE_APPLY) {
-        if (dot_partials || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
+    }
+  } else {
+    const int64_t nb = (int64_t)gridDim.x - chunk_blocks;
+    const int64_t stride = nb * blockDim.x;
+    for (int64_t i0 = ((int64_t)blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x;
+         i0 < op.n_shared; i0 += stride * kSharedUnroll) {
+      uint4 rec[kSharedUnroll];
+      double a[kSharedUnroll], b[kSharedUnroll];
+#pragma unroll
+      for (int k = 0; k < kSharedUnroll; ++k) {
+        const int64_t i = i0 + k * stride;
+        rec[k] = (i < op.n_shared) ? reinterpret_cast<const uint4 *>(op.shared_rec)[i]
+                                   : make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu);
       }
-      if (dir && (flags & SEMK_MASK_OUT)) {
-        if (MODE == MODE_APPLY) {
-          v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
-          uin = v;
-        } else {
-          v = fill_dirichlet;
+#pragma unroll
+      for (int k = 0; k < kSharedUnroll; ++k) {
+        const bool on = rec[k].x != 0xffffffffu;
+        a[k] = on ? op.slot_buf[rec[k].y] : 0.0;
+        b[k] = on ? op.slot_buf[rec[k].z] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < kSharedUnroll; ++k) {
+        if (rec[k].x == 0xffffffffu) continue;
+        const uint32_t pn = rec[k].x;
+        double v = a[k] + b[k];  // ascending patch order: deterministic
+        if (rec[k].w != 0xffffffffu) {  // corner nodes: 3+ patches
+          const uint32_t *ext = op.shared_ext + rec[k].w;
+          const uint32_t extra = ext[0];
+          for (uint32_t j = 0; j < extra; ++j) v += op.slot_buf[ext[1 + j]];
         }
-      } else if (dir && (flags & SEMK_MASK_IN)) {
-        uin = 0.0;
+        dot += finish_shared_node<MODE>(op, pn & SEMK_NODE_ID_MASK,
+                                        (pn & SEMK_NODE_DIRICHLET) != 0, v, u, y, flags,
+                                        fill_dirichlet, want_dot);
       }
-      y[g] = v;
-      dot = fma(uin, v, dot);
     }
   }
-  if (MODE == MODE_APPLY && dot_partials) {
+  if (want_dot) {
     const double s = semk_block_sum(dot, red);
     if (threadIdx.x == 0) dot_partials[partial_offset + blockIdx.x] = s;
   }
@@ -613,7 +645,13 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) out[0] = s;
 }
 
-constexpr int kSharedBlocks = 148 * 64;  // upper bound on shared_nodes_kernel CTAs
+constexpr int kSharedBlocks = 148 * 64;  // upper bound on the per-node part of the interface kernel
+
+inline void interface_blocks(const semk_op &op, int *chunk_blocks, int *rec_blocks) {
+  *chunk_blocks = (int)((op.n_shared_chunk + kChunkWarps - 1) / kChunkWarps);
+  const int64_t want = (op.n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
+  *rec_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
+}
 
 // ---- simple atomic-scatter kernel (independent cross-check) -------------------
 // Groups PEA consecutive element slots per CTA; reads the L2G map and the
@@ -804,7 +842,8 @@ int check_op(const semk_op *op, const char *who) {
       (op->eloc_patch_stride & 7) != 0 ||
       op->eloc_patch_stride < nnp + op->elems_per_patch ||
       (op->n_slots > 0 && !op->slot_buf) ||
-      (op->n_shared > 0 && (!op->shared_rec || !op->shared_ext))) {
+      (op->n_shared > 0 && (!op->shared_rec || !op->shared_ext)) ||
+      (op->n_shared_chunk > 0 && !op->shared_chunk)) {
     semk_set_error(std::string(who) + ": operator tables incomplete");
     return SEMK_ERR_INVALID;
   }
@@ -819,8 +858,8 @@ int check_op(const semk_op *op, const char *who) {
 }  // namespace
 
 extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
-  (void)n_shared;
-  return n_patch + kSharedBlocks + 8;
+  // persistent grid (<= n_patch) + chunk CTAs (<= n_shared / 2 / 8 + 1) + record CTAs
+  return n_patch + n_shared / (2 * kChunkWarps) + kSharedBlocks + 16;
 }
 
 extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
@@ -880,11 +919,12 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
   rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, partials, st, &grid);
   if (rc != SEMK_OK) return rc;
   int shared_blocks = 0;
-  if (op->n_shared > 0) {
-    const int64_t want = (op->n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
-    shared_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
+  if (op->n_shared > 0 || op->n_shared_chunk > 0) {
+    int chunk_blocks = 0, rec_blocks = 0;
+    interface_blocks(*op, &chunk_blocks, &rec_blocks);
+    shared_blocks = chunk_blocks + rec_blocks;
     shared_nodes_kernel<MODE_APPLY><<<shared_blocks, 256, 0, st>>>(*op, u, y, flags, 0.0, partials,
-                                                                  grid);
+                                                                  grid, chunk_blocks);
     SEMK_LAUNCH_CHECK("shared_nodes_kernel");
   }
   if (dot_out) {
@@ -905,11 +945,11 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
   rc = launch_patch<MODE_ASSEMBLE>(*op, dm, nullptr, loc, out, flags, fill_dirichlet, nullptr, st,
                                    nullptr);
   if (rc != SEMK_OK) return rc;
-  if (op->n_shared > 0) {
-    const int64_t want = (op->n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
-    const int blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
-    shared_nodes_kernel<MODE_ASSEMBLE><<<blocks, 256, 0, st>>>(*op, nullptr, out, flags,
-                                                              fill_dirichlet, nullptr, 0);
+  if (op->n_shared > 0 || op->n_shared_chunk > 0) {
+    int chunk_blocks = 0, rec_blocks = 0;
+    interface_blocks(*op, &chunk_blocks, &rec_blocks);
+    shared_nodes_kernel<MODE_ASSEMBLE><<<chunk_blocks + rec_blocks, 256, 0, st>>>(
+        *op, nullptr, out, flags, fill_dirichlet, nullptr, 0, chunk_blocks);
     SEMK_LAUNCH_CHECK("shared_nodes_kernel");
   }
   return SEMK_OK;

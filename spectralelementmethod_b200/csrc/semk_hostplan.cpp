@@ -31,7 +31,7 @@ struct semk_hostplan {
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
       shared_slot;
-  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext;
+  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk;
   std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
@@ -229,25 +229,113 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     }
 
     // Device slots are PATCH-ordered: patch p writes the partial sums of its shared nodes
-    // to the contiguous run [patch_slot_base[p], +n shared) (coalesced stores).  Packed
-    // records for the interface kernel: {node id | flags, slot 0, slot 1, ext}; ext =
-    // 0xffffffff for the usual two contributors, else an offset into SHARED_EXT where
-    // {extra count, extra slots...} continue the list (ascending patch order).
-    P->shared_rec.assign((size_t)n_shared * 4, 0xffffffffu);
-    for (int64_t i = 0; i < n_shared; ++i) {
-      uint32_t *r = P->shared_rec.data() + (size_t)i * 4;
-      const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
-      r[0] = P->shared_node[i];
-      r[1] = (uint32_t)P->shared_slot[j0];
-      r[2] = (uint32_t)P->shared_slot[j0 + 1];
-      if (cnt > 2) {
-        r[3] = (uint32_t)P->shared_ext.size();
-        P->shared_ext.push_back((uint32_t)(cnt - 2));
-        for (int32_t j = j0 + 2; j < j0 + cnt; ++j)
-          P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
+    // to the contiguous run [patch_slot_base[p], +n shared) (coalesced stores).
+    //
+    // Interface reduction tables.  Nodes shared by exactly two patches are grouped by
+    // patch pair and cut into AFFINE CHUNKS of up to 32 nodes
+    //     node_k = node0 + k*dn,  slotA_k = a0 + k*da,  slotB_k = b0 + k*db   (k < len)
+    // (a whole patch edge of a structured mesh is one or a few chunks), 8 words each:
+    //     {node0, dn, a0, da, b0, db, len, Dirichlet bit mask}.
+    // One warp reduces one chunk with coalesced accesses and no per-node record.
+    // Everything else (corner nodes touched by 3+ patches, isolated pairs) keeps a
+    // per-node record {node id | flags, slot 0, slot 1, ext}; ext = 0xffffffff or an
+    // offset into SHARED_EXT where {extra count, extra slots...} continue the list.
+    // Slots are always summed in ascending patch order, so results are deterministic.
+    {
+      std::vector<int32_t> patch_of_slot(n_slots);
+      for (int64_t p = 0; p < n_patch; ++p) {
+        const int32_t s0 = P->patch_slot_base[p];
+        const int32_t s1 = s0 + (P->patch_nnodes[p] - P->patch_npriv[p]);
+        for (int32_t sidx = s0; sidx < s1; ++sidx) patch_of_slot[sidx] = (int32_t)p;
       }
+      struct Pair {
+        int32_t pa, pb, sa, sb;
+        uint32_t node;
+      };
+      std::vector<Pair> pairs;
+      std::vector<uint8_t> in_chunk(n_shared, 0);
+      std::vector<int32_t> pair_index;  // shared index of each entry of `pairs`
+      for (int64_t i = 0; i < n_shared; ++i) {
+        const int32_t j0 = P->shared_ptr[i];
+        if (P->shared_ptr[i + 1] - j0 != 2) continue;
+        const int32_t sa = P->shared_slot[j0], sb = P->shared_slot[j0 + 1];
+        pairs.push_back({patch_of_slot[sa], patch_of_slot[sb], sa, sb, P->shared_node[i]});
+      }
+      std::vector<int32_t> ord(pairs.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int32_t)i;
+      std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+        const Pair &a = pairs[x], &b = pairs[y];
+        if (a.pa != b.pa) return a.pa < b.pa;
+        if (a.pb != b.pb) return a.pb < b.pb;
+        return a.sa < b.sa;
+      });
+      std::vector<uint8_t> taken(pairs.size(), 0);
+      size_t s = 0;
+      while (s < ord.size()) {
+        const Pair &f = pairs[ord[s]];
+        size_t e = s + 1;
+        int32_t dn = 0, da = 0, db = 0;
+        if (e < ord.size()) {
+          const Pair &g = pairs[ord[e]];
+          if (g.pa == f.pa && g.pb == f.pb) {
+            dn = (int32_t)((int64_t)(g.node & SEMK_NODE_ID_MASK) -
+                           (int64_t)(f.node & SEMK_NODE_ID_MASK));
+            da = g.sa - f.sa;
+            db = g.sb - f.sb;
+            ++e;
+            while (e < ord.size() && e - s < 32) {
+              const Pair &h = pairs[ord[e]], &q = pairs[ord[e - 1]];
+              if (h.pa != f.pa || h.pb != f.pb) break;
+              if ((int64_t)(h.node & SEMK_NODE_ID_MASK) - (int64_t)(q.node & SEMK_NODE_ID_MASK) !=
+                      dn ||
+                  h.sa - q.sa != da || h.sb - q.sb != db)
+                break;
+              ++e;
+            }
+          }
+        }
+        const size_t len = e - s;
+        if (len >= 2) {
+          uint32_t mask = 0;
+          for (size_t k = 0; k < len; ++k) {
+            if (pairs[ord[s + k]].node & SEMK_NODE_DIRICHLET) mask |= (1u << k);
+            taken[ord[s + k]] = 1;
+          }
+          P->shared_chunk.push_back(f.node & SEMK_NODE_ID_MASK);
+          P->shared_chunk.push_back((uint32_t)dn);
+          P->shared_chunk.push_back((uint32_t)f.sa);
+          P->shared_chunk.push_back((uint32_t)da);
+          P->shared_chunk.push_back((uint32_t)f.sb);
+          P->shared_chunk.push_back((uint32_t)db);
+          P->shared_chunk.push_back((uint32_t)len);
+          P->shared_chunk.push_back(mask);
+        }
+        s = e;
+      }
+      // per-node records for everything not covered by a chunk (ascending id)
+      size_t pi = 0;
+      for (int64_t i = 0; i < n_shared; ++i) {
+        const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
+        if (cnt == 2) {
+          const bool t = taken[pi++] != 0;
+          if (t) continue;
+        }
+        P->shared_rec.push_back(P->shared_node[i]);
+        P->shared_rec.push_back((uint32_t)P->shared_slot[j0]);
+        P->shared_rec.push_back((uint32_t)P->shared_slot[j0 + 1]);
+        if (cnt > 2) {
+          P->shared_rec.push_back((uint32_t)P->shared_ext.size());
+          P->shared_ext.push_back((uint32_t)(cnt - 2));
+          for (int32_t j = j0 + 2; j < j0 + cnt; ++j)
+            P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
+        } else {
+          P->shared_rec.push_back(0xffffffffu);
+        }
+      }
+      if (P->shared_ext.empty()) P->shared_ext.push_back(0);
+      if (P->shared_rec.empty()) P->shared_rec.assign(4, 0xffffffffu);
+      if (P->shared_chunk.empty()) P->shared_chunk.assign(8, 0);
     }
-    if (P->shared_ext.empty()) P->shared_ext.push_back(0);
 
     // Uniform-stride device blocks, one TMA bulk copy each per patch:
     //   node block  = {n nodes, n private, first slot, 0} + node list, 0xffffffff padded
@@ -271,6 +359,16 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       for (int le = 0; le < PE; ++le) eb[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
     }
     P->scalars[SEMK_PS_PN_STRIDE] = pn_stride;
+    {
+      // counts of the interface tables (the vectors hold one dummy entry when empty)
+      int64_t n_chunk = 0, n_rec = 0;
+      if (!(P->shared_chunk.size() == 8 && P->shared_chunk[6] == 0))
+        n_chunk = (int64_t)P->shared_chunk.size() / 8;
+      if (!(P->shared_rec.size() == 4 && P->shared_rec[0] == 0xffffffffu))
+        n_rec = (int64_t)P->shared_rec.size() / 4;
+      P->scalars[SEMK_PS_N_SHARED_CHUNK] = n_chunk;
+      P->scalars[SEMK_PS_N_SHARED_REC] = n_rec;
+    }
     P->scalars[SEMK_PS_EL_STRIDE] = el_stride;
 
     P->scalars[SEMK_PS_N_PATCH] = n_patch;
@@ -321,6 +419,7 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_ELBLK: return vec_ptr(plan->elblk, n_bytes);
     case SEMK_PA_SHARED_REC: return vec_ptr(plan->shared_rec, n_bytes);
     case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
+    case SEMK_PA_SHARED_CHUNK: return vec_ptr(plan->shared_chunk, n_bytes);
     default: return nullptr;
   }
 }

@@ -162,7 +162,7 @@ class PoissonOperator(object):
         self.smem_bytes = smem
 
         t = {}
-        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT):
+        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT, _lib.PA_SHARED_CHUNK):
             t[k] = device.as_i32_bits(ar[k], self.dev)
         t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
@@ -226,9 +226,11 @@ class PoissonOperator(object):
         self.resident_ctas = resident      # grid of the persistent apply kernel
         op.n_slots = self.n_slots
         op.slot_buf = self.slot_buf.data_ptr()
-        op.n_shared = self.n_shared
-        op.shared_rec = t[_lib.PA_SHARED_REC].data_ptr() if self.n_shared else None
-        op.shared_ext = t[_lib.PA_SHARED_EXT].data_ptr() if self.n_shared else None
+        op.n_shared = sc[_lib.PS_N_SHARED_REC]
+        op.shared_rec = t[_lib.PA_SHARED_REC].data_ptr()
+        op.shared_ext = t[_lib.PA_SHARED_EXT].data_ptr()
+        op.n_shared_chunk = sc[_lib.PS_N_SHARED_CHUNK]
+        op.shared_chunk = t[_lib.PA_SHARED_CHUNK].data_ptr()
         op.partials = self.partials.data_ptr()
         op.D_host = self.tab.D_host.ctypes.data
         op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None

@@ -42,8 +42,8 @@ def test_version_and_error_channel():
 
 
 def test_struct_layout_matches_header():
-    # 21 fields; 8-byte aligned pointers after two int32 pairs
-    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 2 * 8 + 8 + 8 + 8
+    # 23 fields; 8-byte aligned pointers after two int32 pairs
+    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.semk_pcg_info) == 24
 
 
@@ -134,18 +134,34 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     assert sc[_lib.PS_N_SHARED] == sn.size == is_shared_node.sum()
     assert np.all(np.diff((sn & _lib.NODE_ID_MASK).astype(np.int64)) > 0)
     assert sp[0] == 0 and sp[-1] == ss.size == slots_seen
-    # packed records mirror the CSR (slots in ascending patch order)
-    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 4)
+    # interface tables: affine chunks + per-node records together cover every shared node
+    # exactly once with its slots in ascending patch order
     ext = ar[_lib.PA_SHARED_EXT]
-    assert rec.shape[0] == sn.size
-    for i in range(sn.size):
-        lst = ss[sp[i]:sp[i + 1]]
-        assert np.all(np.diff(lst) > 0) and lst.size >= 2
-        got = [rec[i, 1], rec[i, 2]]
-        if rec[i, 3] != 0xFFFFFFFF:
-            k = rec[i, 3]
-            got += ext[k + 1:k + 1 + ext[k]].tolist()
-        assert rec[i, 0] == sn[i] and got == lst.tolist()
+    nch, nrec = sc[_lib.PS_N_SHARED_CHUNK], sc[_lib.PS_N_SHARED_REC]
+    chunk = ar[_lib.PA_SHARED_CHUNK].reshape(-1, 8)[:nch].astype(np.int64)
+    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 4)[:nrec]
+    want = {int(sn[i] & _lib.NODE_ID_MASK): (ss[sp[i]:sp[i + 1]].tolist(),
+                                             bool(sn[i] & _lib.NODE_DIRICHLET))
+            for i in range(sn.size)}
+    seen = {}
+    for node0, dn, a0, da, b0, db, ln, mask in chunk.tolist():
+        assert 2 <= ln <= 32
+        dn, da, db = (np.int64(v).astype(np.int32) if False else (v - (1 << 32) if v >= (1 << 31) else v)
+                      for v in (dn, da, db))
+        for k in range(ln):
+            g = node0 + k * dn
+            assert g not in seen
+            seen[g] = ([a0 + k * da, b0 + k * db], bool((mask >> k) & 1))
+    for r in rec.tolist():
+        g = r[0] & _lib.NODE_ID_MASK
+        lst = [r[1], r[2]]
+        if r[3] != 0xFFFFFFFF:
+            lst += ext[r[3] + 1:r[3] + 1 + ext[r[3]]].tolist()
+        assert g not in seen
+        seen[g] = (lst, bool(r[0] & _lib.NODE_DIRICHLET))
+    assert seen == want
+    for lst, _ in want.values():
+        assert lst == sorted(lst) and len(lst) >= 2
 
 
 @pytest.mark.parametrize("nx,ny,p,pe", [(8, 8, 8, 16), (5, 3, 4, 16), (7, 5, 2, 8), (3, 3, 10, 4),
