@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
 //   remaining CTAs: per-node records (corner nodes, irregular pairs), each thread
 //     kSharedUnroll nodes with all record loads, then all slot loads, in flight.
 constexpr int kSharedUnroll = 4;
-constexpr int kChunkWarps = 8;  // chunks per CTA of 256 threads
+constexpr int kChunkWarps = 8;   // warps per CTA of 256 threads
+constexpr int kChunkUnroll = 4;  // chunks per warp
 
 template <int MODE>
 __device__ __forceinline__ double finish_shared_node(const semk_op &op, uint32_t g, bool dir,
@@ -580,17 +581,33 @@ __global__ void __launch_bounds__(256)
   const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
   if ((int)blockIdx.x < chunk_blocks) {
     const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * kChunkWarps + (threadIdx.x >> 5);
-    if (c < op.n_shared_chunk) {
-      const uint4 c0 = reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c];
-      const uint4 c1 = reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c + 1];
+    // each warp reduces kChunkUnroll chunks: all table loads first, then all slot
+    // loads, then the stores (three dependent memory levels, kept wide)
+    const int64_t cbase =
+        ((int64_t)blockIdx.x * kChunkWarps + (threadIdx.x >> 5)) * kChunkUnroll;
+    uint4 c0[kChunkUnroll], c1[kChunkUnroll];
+    double va[kChunkUnroll], vb[kChunkUnroll];
+#pragma unroll
+    for (int k = 0; k < kChunkUnroll; ++k) {
+      const int64_t c = cbase + k;
+      const bool on = c < op.n_shared_chunk;
       // c0 = {node0, dn, a0, da}, c1 = {b0, db, len, Dirichlet mask}
-      if (lane < (int)c1.z) {
-        const uint32_t g = c0.x + (uint32_t)lane * c0.y;
-        const double va = op.slot_buf[c0.z + (uint32_t)lane * c0.w];
-        const double vb = op.slot_buf[c1.x + (uint32_t)lane * c1.y];
-        dot += finish_shared_node<MODE>(op, g, ((c1.w >> lane) & 1u) != 0, va + vb, u, y, flags,
-                                        fill_dirichlet, want_dot);
+      c0[k] = on ? reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c] : make_uint4(0, 0, 0, 0);
+      c1[k] = on ? reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c + 1]
+                 : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kChunkUnroll; ++k) {
+      const bool on = lane < (int)c1[k].z;
+      va[k] = on ? op.slot_buf[c0[k].z + (uint32_t)lane * c0[k].w] : 0.0;
+      vb[k] = on ? op.slot_buf[c1[k].x + (uint32_t)lane * c1[k].y] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kChunkUnroll; ++k) {
+      if (lane < (int)c1[k].z) {
+        const uint32_t g = c0[k].x + (uint32_t)lane * c0[k].y;
+        dot += finish_shared_node<MODE>(op, g, ((c1[k].w >> lane) & 1u) != 0, va[k] + vb[k], u, y,
+                                        flags, fill_dirichlet, want_dot);
       }
     }
   } else {
@@ -648,7 +665,8 @@ __global__ void __launch_bounds__(1024)
 constexpr int kSharedBlocks = 148 * 64;  // upper bound on the per-node part of the interface kernel
 
 inline void interface_blocks(const semk_op &op, int *chunk_blocks, int *rec_blocks) {
-  *chunk_blocks = (int)((op.n_shared_chunk + kChunkWarps - 1) / kChunkWarps);
+  const int64_t per_block = (int64_t)kChunkWarps * kChunkUnroll;
+  *chunk_blocks = (int)((op.n_shared_chunk + per_block - 1) / per_block);
   const int64_t want = (op.n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
   *rec_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
 }
