@@ -35,8 +35,8 @@ ORDER = 8
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--nx", type=int, default=0, help="elements per side per GPU (0 = config default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -70,29 +70,36 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self._proc = None
         self._thr = None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                for line in out.stdout.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+    def _reader(self):
+        for line in self._proc.stdout:
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) >= 9:
+                self.rows.append(cells)
 
     def __enter__(self):
-        self._thr = threading.Thread(target=self._run, daemon=True)
-        self._thr.start()
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._thr = threading.Thread(target=self._reader, daemon=True)
+            self._thr.start()
+            time.sleep(0.15)        # first sample lands before the timed region starts
+        except Exception:
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._thr.join(timeout=6)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=3)
+            except Exception:
+                self._proc.kill()
+            self._thr.join(timeout=3)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -116,11 +123,7 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------
 # CPU baseline (the oracle port of the reference's apply), bounded sample
 # --------------------------------------------------------------------------
-def cpu_baseline(n_side, kind, target_seconds=12.0):
-    """The reference's operator apply on host cores: dense local stiffness
-    (examples/poisson.py:181-193) applied element by element
-    (examples/squirmer-axisymmetric.py:284-295) in a Python loop -- exactly how
-    the reference does it -- on an n_side x n_side, p = 8 sample mesh."""
+def _cpu_problem(n_side, kind):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import sem_oracle as so
@@ -129,19 +132,37 @@ def cpu_baseline(n_side, kind, target_seconds=12.0):
     geo = so.geometry(basis, nodes, l2g)
     L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
     u = np.sin(3 * nodes[0]) * np.cos(2 * nodes[1])
-    so.apply_dense_local(L, l2g, u)                     # warm-up
+    if so.c_lib() is not None:
+        fn = lambda: so.apply_dense_c(L, l2g, u)                 # noqa: E731
+        how = ("dense local apply, C/OpenMP restatement (oracle/sem_oracle_c.c), %d threads"
+               % so.c_threads())
+        cores = so.c_threads()
+    else:
+        fn = lambda: so.apply_dense_local(L, l2g, u)             # noqa: E731
+        how = "dense local einsum loop, single Python thread (oracle/sem_oracle.py)"
+        cores = 1
+    return fn, nodes.shape[1], how, cores
+
+
+def cpu_baseline(n_side, kind, target_seconds=10.0):
+    """The reference's operator apply on host cores: dense 4-index local
+    stiffness (examples/poisson.py:181-193) applied element by element and
+    scatter-added (examples/squirmer-axisymmetric.py:284-295) -- the oracle
+    port, with every host thread it can use -- on an n_side x n_side, p = 8
+    sample of the workload (the dense Lse needs 52 KB per element, so the full
+    1024 x 1024 mesh cannot even be stored: 55 GB)."""
+    fn, ndof, how, cores = _cpu_problem(n_side, kind)
+    fn()
     reps, t0 = 0, time.perf_counter()
     while True:
-        so.apply_dense_local(L, l2g, u)
+        fn()
         reps += 1
         el = time.perf_counter() - t0
-        if el >= target_seconds or reps >= 200:
+        if el >= target_seconds or reps >= 1000:
             break
-    ndof = nodes.shape[1]
-    return {"value": ndof * reps / el / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "port",
-            "sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s, dense local einsum "
-                      "loop (oracle/sem_oracle.py:apply_dense_local)" % (n_side, n_side, ORDER,
-                                                                         ndof, reps, el)}
+    return {"value": ndof * reps / el / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "port",
+            "sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s; %s"
+                      % (n_side, n_side, ORDER, ndof, reps, el, how)}
 
 
 def run_reference(args):
@@ -151,25 +172,16 @@ def run_reference(args):
     if rank != 0:
         return
     n_side = args.cpu_sample or 64
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import sem_oracle as so
-    basis = so.Basis(ORDER)
-    nodes, l2g = so.build_case(args.kind, n_side, n_side, ORDER, False, False)
-    geo = so.geometry(basis, nodes, l2g)
-    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
-    u = np.sin(3 * nodes[0]) * np.cos(2 * nodes[1])
-    ndof = nodes.shape[1]
+    fn, ndof, how, cores = _cpu_problem(n_side, args.kind)
     for _ in range(max(args.warmup, 1)):
-        so.apply_dense_local(L, l2g, u)
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        so.apply_dense_local(L, l2g, u)
+        fn()
     el = time.perf_counter() - t0
     value = ndof * args.steps / el / 1e9
-    sample = ("%dx%d elements p=%d (%d DOF) per step: bounded sample of the 1024x1024 workload; "
-              "dense local einsum loop, single Python thread like the reference"
-              % (n_side, n_side, ORDER, ndof))
+    sample = ("%dx%d elements p=%d (%d DOF) per step: bounded sample of the 1024x1024 workload; %s"
+              % (n_side, n_side, ORDER, ndof, how))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GDOF/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -177,7 +189,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "structured quad mesh Poisson p=8 FP64 (CPU sample %dx%d)"
                                % (n_side, n_side)},
-        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -248,11 +260,11 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     # ---- device-resident apply: W warm-ups, K timed steps ----------------------
-    for _ in range(max(args.warmup, 3)):
-        apply_fn(u, out)
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:      # samples clocks from the warm-up onwards
+        for _ in range(max(args.warmup, 3)):
+            apply_fn(u, out)
+        barrier()
         ev0.record()
         for _ in range(args.steps):
             apply_fn(u, out)

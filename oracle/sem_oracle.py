@@ -438,3 +438,50 @@ def run_case(kind, nx, ny, p, sc, rcm, solve=True, python_loop_apply=False):
             A = assemble_csr(L, l2g, n)
             out["solution"] = solve_direct(A, out["b"], on, vals)
     return out
+
+
+# --------------------------------------------------------------------------
+# C/OpenMP restatement of the dense local apply (all host threads)
+# --------------------------------------------------------------------------
+_C_LIB = None
+
+
+def c_lib():
+    """ctypes handle of oracle/_build/libsem_oracle_c.so (built by
+    oracle/build_c.sh / __graft_entry__.build()), or None if not built."""
+    global _C_LIB
+    if _C_LIB is None:
+        import ctypes
+        path = os.path.join(_HERE, "_build", "libsem_oracle_c.so")
+        if not os.path.exists(path):
+            return None
+        os.environ.setdefault("OMP_PROC_BIND", "true")   # unpinned threads scale negatively
+        lib = ctypes.CDLL(path)
+        lib.sem_oracle_c_threads.restype = ctypes.c_int
+        lib.sem_oracle_c_apply_dense.restype = None
+        lib.sem_oracle_c_apply_dense.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int64] + \
+            [ctypes.c_void_p] * 4
+        _C_LIB = lib
+    return _C_LIB
+
+
+def apply_dense_c(L, l2g, u):
+    """y[L2G] += L_e . u[L2G] over all elements with OpenMP (same contraction
+    as apply_dense_local; examples/squirmer-axisymmetric.py:268-295)."""
+    lib = c_lib()
+    if lib is None:
+        raise RuntimeError("oracle C library not built (run oracle/build_c.sh)")
+    E, N = l2g.shape[0], l2g.shape[1]
+    NN = N * N
+    Lc = np.ascontiguousarray(L, dtype=np.float64).reshape(E, NN, NN)
+    idx = np.ascontiguousarray(l2g, dtype=np.uint32).reshape(E, NN)
+    uc = np.ascontiguousarray(u, dtype=np.float64)
+    y = np.empty_like(uc)
+    lib.sem_oracle_c_apply_dense(E, NN, uc.size, Lc.ctypes.data, idx.ctypes.data, uc.ctypes.data,
+                                 y.ctypes.data)
+    return y
+
+
+def c_threads():
+    lib = c_lib()
+    return int(lib.sem_oracle_c_threads()) if lib is not None else 1

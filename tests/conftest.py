@@ -16,6 +16,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The shared libraries are build artefacts (git-ignored): build them once if absent.
+    lib = os.path.join(ROOT, "spectralelementmethod_b200", "csrc", "libsemk.so")
+    olib = os.path.join(ROOT, "oracle", "_build", "libsem_oracle_c.so")
+    if not (os.path.exists(lib) and os.path.exists(olib)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def golden_case_names():

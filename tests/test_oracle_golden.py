@@ -75,3 +75,16 @@ def test_pcg_on_oracle_matrix_matches_direct_solution():
     sol[free] = x
     assert rel_l2(sol, g["solution"]) < TOL
     assert 100 < it < 400      # 218 iterations at n=4
+
+
+def test_c_openmp_restatement_matches_python_loop():
+    """oracle/sem_oracle_c.c (the all-threads CPU baseline) == the NumPy loop."""
+    if so.c_lib() is None:
+        pytest.skip("oracle C library not built")
+    for name in ("C534_dm", "C888_sc_rcm"):
+        g = load_case(name)
+        L = so.local_stiffness(so.Basis(g["p"]), g["invJ"], g["JxW"])
+        y = so.apply_dense_c(L, g["l2g"], g["u"])
+        assert rel_l2(y, g["Au"]) < TOL
+        assert rel_l2(y, so.apply_dense_batched(L, g["l2g"], g["u"])) < 1e-13
+    assert so.c_threads() >= 1
