@@ -261,13 +261,13 @@ enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 // the working arrays.
 struct PatchSmem {
   size_t gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
-  size_t yp, ua, bs, red, total;
+  size_t yp, carry, carry_len, ua, bs, red, total;
 };
 __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
                                                        int64_t g_patch_stride,
                                                        int64_t pn_patch_stride,
                                                        int64_t eloc_patch_stride,
-                                                       int max_patch_nodes) {
+                                                       int max_patch_nodes, int max_carry) {
   PatchSmem L;
   const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
   const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
@@ -285,6 +285,9 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
   L.yp = o;
   o += 8 * mpn4;
   o = (o + 15) & ~(size_t)15;
+  L.carry = o;  // two buffers of partial sums carried from one patch to the next
+  L.carry_len = ((size_t)max_carry + 1) & ~(size_t)1;
+  o += 2 * 8 * L.carry_len;
   L.ua = o;  // scratch A
   o += (mode == MODE_APPLY) ? 8 * scratch : 0;
   o = (o + 15) & ~(size_t)15;
@@ -307,7 +310,8 @@ __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
   const long long tab = 2 * ((4 * (4 + mpn4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
   const long long scr = 8LL * N * scratch_row_stride(N, PE);
   const long long ua = scr;
-  const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
+  const long long carry = 16LL * ((by * p + 2) & ~1LL);
+  const long long total = 32 + g + tab + 8 * mpn4 + carry + ua + (scr > 256 ? scr : 256) + 1024;
   const long long by_smem = 233472 / total;
   const int threads = ((N * PE + 31) / 32) * 32;
   const long long by_regs = 65536 / ((long long)threads * 96);  // assume <= 96 registers/thread
@@ -341,8 +345,10 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   constexpr int RS = PatchCfg<N, PE>::kRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
-                                        op.eloc_patch_stride, op.max_patch_nodes);
+                                        op.eloc_patch_stride, op.max_patch_nodes,
+                                        (int)op.max_carry);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2]: G
+  double *carry = reinterpret_cast<double *>(smem_raw + L.carry);
   double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
   double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
   double *As = reinterpret_cast<double *>(smem_raw + L.ua);
@@ -367,13 +373,23 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[2]);
   };
 
+  // this CTA's patch sequence: a contiguous range (plan built with ranges: nodes
+  // shared by consecutive patches are carried in shared memory) or round-robin
+  const int64_t step = op.patches_per_range > 0 ? 1 : (int64_t)gridDim.x;
+  const int64_t p_first =
+      op.patches_per_range > 0 ? (int64_t)blockIdx.x * op.patches_per_range : (int64_t)blockIdx.x;
+  int64_t p_end = op.n_patch;
+  if (op.patches_per_range > 0) {
+    const int64_t e = p_first + op.patches_per_range;
+    p_end = e < op.n_patch ? e : op.n_patch;
+  }
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) semk_mbar_init(&mbar[i], 1);
     semk_fence_mbar_init();
-    if ((int64_t)blockIdx.x < op.n_patch) {
-      issue_tables(blockIdx.x, 0);
-      if (MODE == MODE_APPLY) issue_g(blockIdx.x);
+    if (p_first < p_end) {
+      issue_tables(p_first, 0);
+      if (MODE == MODE_APPLY) issue_g(p_first);
     }
   }
   __syncthreads();  // mbarrier initialisation visible to every waiter
@@ -406,20 +422,20 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     }
   };
   for (int k = tid; k < op.max_patch_nodes; k += kThreads) yp[k] = 0.0;
-  if (MODE == MODE_APPLY && (int64_t)blockIdx.x < op.n_patch) {
+  if (MODE == MODE_APPLY && p_first < p_end) {
     semk_mbar_wait(&mbar[0], 0);
-    gather_column(0, blockIdx.x);
+    gather_column(0, p_first);
   }
   __syncthreads();
 
   double dot = 0.0;
   const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
   int it = 0;
-  for (int64_t patch = blockIdx.x; patch < op.n_patch; patch += gridDim.x, ++it) {
+  for (int64_t patch = p_first; patch < p_end; patch += step, ++it) {
     const int s = it & 1;
     const uint32_t par = (uint32_t)((it >> 1) & 1);
-    const int64_t next = patch + gridDim.x;
-    const bool has_next = next < op.n_patch;
+    const int64_t next = patch + step;
+    const bool has_next = next < p_end;
     unsigned char *sb = stage_ptr(s);
     const uint32_t *pn_blk = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
     const uint16_t *el_s = reinterpret_cast<const uint16_t *>(sb + L.el_off);
@@ -427,6 +443,9 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     const int npn = (int)pn_blk[0];
     const int npriv = (int)pn_blk[1];
     const int slot_base = (int)pn_blk[2];
+    const int ncin = (int)(pn_blk[3] & 0xffffu), ncout = (int)(pn_blk[3] >> 16);
+    const double *carry_in = carry + (size_t)((it & 1) ^ 1) * L.carry_len;  // from patch i-1
+    double *carry_out = carry + (size_t)(it & 1) * L.carry_len;            // for patch i+1
     const uint32_t *pn_s = pn_blk + 4;
     const int64_t slot0 = patch * PE;
     const bool active = (le < PE) && (slot0 + le < op.n_elem);
@@ -505,6 +524,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
         const uint32_t pn = pnv[j];
         double v = vv[j];
         if (k < npriv) {
+          if (k < ncin) v += carry_in[k];  // partial sum of the previous patch
           const uint32_t g = pn & SEMK_NODE_ID_MASK;
           const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
           double uin = 0.0;
@@ -523,8 +543,10 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
           }
           y[g] = v;
           dot = fma(uin, v, dot);
+        } else if (k < npriv + ncout) {
+          carry_out[k - npriv] = v;  // completed by the next patch of this CTA
         } else {
-          op.slot_buf[slot_base + (k - npriv)] = v;
+          op.slot_buf[slot_base + (k - npriv - ncout)] = v;
         }
       }
     }
@@ -791,7 +813,8 @@ struct PatchLaunch {
                  double *y, int flags, double fill, double *partials, cudaStream_t st,
                  int *grid_out) {
     const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
-                                          op.eloc_patch_stride, op.max_patch_nodes)
+                                          op.eloc_patch_stride, op.max_patch_nodes,
+                                          (int)op.max_carry)
                             .total;
     if (smem > 227 * 1024) {
       semk_set_error("patch kernel: shared memory request exceeds 227 KB");
@@ -804,9 +827,14 @@ struct PatchLaunch {
       semk_set_error("patch kernel: does not fit on an SM");
       return SEMK_ERR_UNSUPPORTED;
     }
-    // persistent grid: every CTA stays resident and loops over its patches
+    // persistent grid: every CTA stays resident and loops over its patches -- the
+    // contiguous ranges the plan was built for, or round-robin over the resident CTAs
     const int64_t resident = (int64_t)per_sm * sms;
-    const unsigned grid = (unsigned)(op.n_patch < resident ? op.n_patch : resident);
+    unsigned grid;
+    if (op.patches_per_range > 0)
+      grid = (unsigned)((op.n_patch + op.patches_per_range - 1) / op.patches_per_range);
+    else
+      grid = (unsigned)(op.n_patch < resident ? op.n_patch : resident);
     patch_kernel<N, PE, MODE><<<grid, PatchCfg<N, PE>::kThreads, smem, st>>>(
         op, dm, u, loc, y, flags, fill, partials);
     SEMK_LAUNCH_CHECK("patch_kernel");
@@ -882,10 +910,11 @@ extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
 
 extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
                                       int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                                      int max_patch_nodes) {
+                                      int max_patch_nodes, int max_carry) {
   if (!pe_supported(elems_per_patch)) return -1;
   const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                        pn_patch_stride, eloc_patch_stride, max_patch_nodes)
+                                        pn_patch_stride, eloc_patch_stride, max_patch_nodes,
+                                        max_carry)
                           .total;
   if (smem > 227 * 1024) return -1;
   int per_sm = 0, sms = 0;
@@ -911,9 +940,10 @@ extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_pat
 
 extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                                          int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                                         int max_patch_nodes) {
+                                         int max_patch_nodes, int max_carry) {
   return (int64_t)patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                    pn_patch_stride, eloc_patch_stride, max_patch_nodes)
+                                    pn_patch_stride, eloc_patch_stride, max_patch_nodes,
+                                    max_carry)
       .total;
 }
 

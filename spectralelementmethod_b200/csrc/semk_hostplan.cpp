@@ -30,7 +30,7 @@ struct semk_hostplan {
   int64_t n_elem = 0, n_nodes = 0;
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
-      shared_slot;
+      shared_slot, patch_ncin, patch_ncout;
   std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk;
   std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
@@ -40,7 +40,8 @@ struct semk_hostplan {
 
 extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
                                     const int64_t *elem_order, int elems_per_patch,
-                                    const uint8_t *dirichlet, semk_hostplan **out) {
+                                    const uint8_t *dirichlet, int64_t n_ranges,
+                                    semk_hostplan **out) {
   if (!out) return SEMK_ERR_INVALID;
   *out = nullptr;
   if (n1 < 2 || n1 > SEMK_MAX_N1) {
@@ -96,8 +97,16 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       }
     }
 
+    // The persistent kernel gives CTA r the contiguous patch range [r*C, (r+1)*C).
+    // A node touched by exactly two patches q, q+1 of one range is CARRIED: the CTA
+    // keeps q's partial sum in shared memory and adds it when it assembles q+1 (which
+    // then owns the node), instead of going through an interface slot.
+    const int64_t C = (n_ranges > 0) ? (n_patch + n_ranges - 1) / n_ranges : 0;
+    P->scalars[SEMK_PS_PATCHES_PER_RANGE] = C;
+
     // pass 1: which nodes are touched by more than one patch
-    std::vector<int32_t> first_patch(n_nodes, -1);
+    //   multi = 0 private, 1 shared (interface slots), 2 carried from first to first+1
+    std::vector<int32_t> first_patch(n_nodes, -1), second_patch(n_nodes, -1);
     std::vector<uint8_t> multi(n_nodes, 0);
     for (int64_t p = 0; p < n_patch; ++p) {
       const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
@@ -105,18 +114,29 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         for (int k = 0; k < NN; ++k) {
           const uint32_t g = row[k];
-          if (first_patch[g] < 0)
+          if (first_patch[g] < 0) {
             first_patch[g] = (int32_t)p;
-          else if (first_patch[g] != (int32_t)p)
-            multi[g] = 1;
+          } else if (first_patch[g] != (int32_t)p) {
+            if (second_patch[g] < 0) {
+              second_patch[g] = (int32_t)p;
+              multi[g] = 2;  // provisional: exactly two patches so far
+            } else if (second_patch[g] != (int32_t)p) {
+              multi[g] = 1;  // three or more
+            }
+          }
         }
       }
     }
+    for (int64_t g = 0; g < n_nodes; ++g)
+      if (multi[g] == 2) {
+        const int64_t a = first_patch[g], b = second_patch[g];
+        if (!(C > 0 && b == a + 1 && a / C == b / C)) multi[g] = 1;
+      }
 
     // shared node list (ascending id) and slot counts
     std::vector<int32_t> shared_index(n_nodes, -1);
     for (int64_t g = 0; g < n_nodes; ++g)
-      if (multi[g]) {
+      if (multi[g] == 1) {
         shared_index[g] = (int32_t)P->shared_node.size();
         uint32_t v = (uint32_t)g | SEMK_NODE_SHARED;
         if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
@@ -128,12 +148,15 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     // pass 2: per-patch tables
     P->patch_node_ptr.assign(n_patch + 1, 0);
     P->patch_npriv.assign(n_patch, 0);
+    P->patch_ncin.assign(n_patch, 0);
+    P->patch_ncout.assign(n_patch, 0);
     P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
     P->eloc.assign((size_t)n_patch * ES, 0);
     P->elem_color.assign(n_slot_elems, 0);
     std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
-    std::vector<uint32_t> priv, shar, colmask;
+    std::vector<uint32_t> priv, shar, cin, cout_, colmask;
+    int64_t max_carry = 0;
     std::vector<std::pair<int32_t, int32_t>> slot_pairs;  // (shared index, slot)
     int64_t max_patch_nodes = 0, n_slots = 0;
     int max_colors = 1;
@@ -141,31 +164,55 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
       priv.clear();
       shar.clear();
+      cin.clear();
+      cout_.clear();
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         for (int k = 0; k < NN; ++k) {
           const uint32_t g = row[k];
           if (local_of[g] == -1) {
             local_of[g] = -2;  // mark as collected
-            (multi[g] ? shar : priv).push_back(g);
+            if (multi[g] == 0)
+              priv.push_back(g);
+            else if (multi[g] == 1)
+              shar.push_back(g);
+            else if (first_patch[g] == (int32_t)p)
+              cout_.push_back(g);
+            else
+              cin.push_back(g);
           }
         }
       }
       std::sort(priv.begin(), priv.end());
       std::sort(shar.begin(), shar.end());
-      const int32_t np = (int32_t)priv.size(), ns = (int32_t)shar.size();
+      std::sort(cin.begin(), cin.end());
+      std::sort(cout_.begin(), cout_.end());
+      // node list order: [carry-in | private | carry-out | shared]; the patch writes the
+      // first ncin + nprivate entries to the result vector
+      const int32_t nci = (int32_t)cin.size(), nco = (int32_t)cout_.size();
+      const int32_t np = (int32_t)priv.size() + nci, ns = (int32_t)shar.size();
       P->patch_npriv[p] = np;
+      P->patch_ncin[p] = nci;
+      P->patch_ncout[p] = nco;
+      max_carry = std::max<int64_t>(max_carry, std::max(nci, nco));
       P->patch_slot_base[p] = (int32_t)n_slots;
       for (int32_t k = 0; k < np; ++k) {
-        const uint32_t g = priv[k];
+        const uint32_t g = (k < nci) ? cin[k] : priv[k - nci];
         local_of[g] = k;
+        uint32_t v = g;
+        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
+        P->pnode.push_back(v);
+      }
+      for (int32_t k = 0; k < nco; ++k) {
+        const uint32_t g = cout_[k];
+        local_of[g] = np + k;
         uint32_t v = g;
         if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
         P->pnode.push_back(v);
       }
       for (int32_t k = 0; k < ns; ++k) {
         const uint32_t g = shar[k];
-        local_of[g] = np + k;
+        local_of[g] = np + nco + k;
         uint32_t v = g | SEMK_NODE_SHARED;
         if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
         P->pnode.push_back(v);
@@ -181,11 +228,11 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       // pad to a multiple of 4 entries: every patch's list starts 16-byte aligned (TMA)
       while (P->pnode.size() & 3u) P->pnode.push_back(0xffffffffu);
       P->patch_node_ptr[p + 1] = (int32_t)P->pnode.size();
-      P->patch_nnodes[p] = np + ns;
-      max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
+      P->patch_nnodes[p] = np + nco + ns;
+      max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + nco + ns);
 
       // element-local index table + greedy colouring
-      colmask.assign(np + ns, 0u);
+      colmask.assign(np + nco + ns, 0u);
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
@@ -213,6 +260,8 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       // reset scratch
       for (uint32_t g : priv) local_of[g] = -1;
       for (uint32_t g : shar) local_of[g] = -1;
+      for (uint32_t g : cin) local_of[g] = -1;
+      for (uint32_t g : cout_) local_of[g] = -1;
     }
     if ((int64_t)P->pnode.size() > INT32_MAX) {
       delete P;
@@ -245,7 +294,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       std::vector<int32_t> patch_of_slot(n_slots);
       for (int64_t p = 0; p < n_patch; ++p) {
         const int32_t s0 = P->patch_slot_base[p];
-        const int32_t s1 = s0 + (P->patch_nnodes[p] - P->patch_npriv[p]);
+        const int32_t s1 = s0 + (P->patch_nnodes[p] - P->patch_npriv[p] - P->patch_ncout[p]);
         for (int32_t sidx = s0; sidx < s1; ++sidx) patch_of_slot[sidx] = (int32_t)p;
       }
       struct Pair {
@@ -350,7 +399,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       blk[0] = (uint32_t)nn;
       blk[1] = (uint32_t)P->patch_npriv[p];
       blk[2] = (uint32_t)P->patch_slot_base[p];
-      blk[3] = 0;
+      blk[3] = (uint32_t)P->patch_ncin[p] | ((uint32_t)P->patch_ncout[p] << 16);
       std::copy(P->pnode.begin() + P->patch_node_ptr[p], P->pnode.begin() + P->patch_node_ptr[p] + nn,
                 blk + 4);
       uint16_t *eb = P->elblk.data() + (size_t)p * el_stride;
@@ -359,6 +408,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       for (int le = 0; le < PE; ++le) eb[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
     }
     P->scalars[SEMK_PS_PN_STRIDE] = pn_stride;
+    P->scalars[SEMK_PS_MAX_CARRY] = max_carry;
     {
       // counts of the interface tables (the vectors hold one dummy entry when empty)
       int64_t n_chunk = 0, n_rec = 0;
@@ -420,6 +470,8 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_SHARED_REC: return vec_ptr(plan->shared_rec, n_bytes);
     case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
     case SEMK_PA_SHARED_CHUNK: return vec_ptr(plan->shared_chunk, n_bytes);
+    case SEMK_PA_PATCH_NCIN: return vec_ptr(plan->patch_ncin, n_bytes);
+    case SEMK_PA_PATCH_NCOUT: return vec_ptr(plan->patch_ncout, n_bytes);
     default: return nullptr;
   }
 }

@@ -47,15 +47,17 @@ def pn_patch_stride_of(max_patch_nodes):
     return 4 + ((int(max_patch_nodes) + 3) & ~3)   # header + node list
 
 
-def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None):
+def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None, max_carry=None):
     """Dynamic shared memory of one CTA of the apply kernel (asks the library,
     which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
     if pn_stride is None:
         pn_stride = pn_patch_stride_of(max_patch_nodes)
+    if max_carry is None:
+        max_carry = _TILES[pe][1] * (n1 - 1) + 1
     return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_patch_stride_of(n1, pe),
                                                  int(pn_stride),
                                                  eloc_patch_stride_of(n1, pe),
-                                                 int(max_patch_nodes)))
+                                                 int(max_patch_nodes), int(max_carry)))
 
 
 def choose_elems_per_patch(n1):
@@ -105,7 +107,11 @@ def default_element_order(mesh, elems_per_patch, tile=None):
         if bx * by != elems_per_patch:
             raise ValueError("tile shape does not match elems_per_patch")
         ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
-        key = ((ex // bx) * ((ny + by - 1) // by) + ey // by) * (bx * by) + (ex % bx) * by + ey % by
+        # tiles enumerated down a tile column (tx fastest): consecutive patches share a
+        # whole edge of contiguously numbered nodes, which the persistent kernel carries
+        # from one patch to the next in shared memory
+        ntx = (nx + bx - 1) // bx
+        key = ((ey // by) * ntx + ex // bx) * (bx * by) + (ex % bx) * by + ey % by
         return np.argsort(key, kind="stable").astype(np.int64)
     if not hasattr(mesh, "_centroids"):
         mesh._compute_cell_centroids()
@@ -129,7 +135,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, tile=None):
+                 elem_order=None, keep_l2g=True, tile=None, carry=True):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -152,13 +158,35 @@ class PoissonOperator(object):
         pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
         if elem_order is None:
             elem_order = default_element_order(mesh, pe, tile)
-        sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
+        # The persistent apply kernel runs one CTA per resident slot and gives each a
+        # contiguous range of patches; the plan needs that number to decide which
+        # interface nodes are carried inside a CTA.  Estimate it from the expected patch
+        # footprint, build, and rebuild if the real footprint allows fewer CTAs.
+        est_nodes = min(pe * NN, (_TILES[pe][0] * (n1 - 1) + 1) * (_TILES[pe][1] * (n1 - 1) + 1)
+                        if tile is None else (tile[0] * (n1 - 1) + 1) * (tile[1] * (n1 - 1) + 1))
+        est_carry = (tile[1] if tile is not None else _TILES[pe][1]) * (n1 - 1) + 1
+
+        def resident_for(max_nodes, pn_stride, el_stride, max_carry):
+            r = int(self._lib.semk_resident_ctas(n1, pe, g_patch_stride_of(n1, pe), int(pn_stride),
+                                                 int(el_stride), int(max_nodes), int(max_carry)))
+            if r <= 0:
+                raise NotImplementedError(
+                    "patch of %d elements does not fit in shared memory (%s); pass a smaller "
+                    "elems_per_patch or a more local elem_order" % (pe, _lib.last_error()))
+            return r
+        n_ranges = resident_for(est_nodes, pn_patch_stride_of(est_nodes),
+                                eloc_patch_stride_of(n1, pe), est_carry) if carry else 0
+        for _attempt in range(3):
+            sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet, n_ranges)
+            actual = resident_for(sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE],
+                                  sc[_lib.PS_EL_STRIDE], sc[_lib.PS_MAX_CARRY])
+            if not carry or actual >= min(n_ranges, sc[_lib.PS_N_PATCH]):
+                break
+            n_ranges = actual
         self.plan_scalars = sc
-        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE])
-        if smem > _SMEM_LIMIT:
-            raise NotImplementedError(
-                "patch of %d elements needs %d B of shared memory (> 227 KB); pass a smaller "
-                "elems_per_patch or a more local elem_order" % (pe, smem))
+        self.resident_ctas = actual
+        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE],
+                                sc[_lib.PS_MAX_CARRY])
         self.smem_bytes = smem
 
         t = {}
@@ -218,12 +246,8 @@ class PoissonOperator(object):
         op.pn_patch_stride = sc[_lib.PS_PN_STRIDE]
         op.eloc = t[_lib.PA_ELBLK].data_ptr()
         op.eloc_patch_stride = sc[_lib.PS_EL_STRIDE]
-        resident = int(self._lib.semk_resident_ctas(n1, pe, self.g_patch_stride,
-                                                    sc[_lib.PS_PN_STRIDE], sc[_lib.PS_EL_STRIDE],
-                                                    sc[_lib.PS_MAX_PATCH_NODES]))
-        if resident <= 0:
-            raise RuntimeError("semk_resident_ctas failed: " + _lib.last_error())
-        self.resident_ctas = resident      # grid of the persistent apply kernel
+        op.patches_per_range = sc[_lib.PS_PATCHES_PER_RANGE]
+        op.max_carry = sc[_lib.PS_MAX_CARRY]
         op.n_slots = self.n_slots
         op.slot_buf = self.slot_buf.data_ptr()
         op.n_shared = sc[_lib.PS_N_SHARED_REC]
