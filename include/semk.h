@@ -95,12 +95,11 @@ enum semk_plan_array {
                                  the patch's node list (as in PNODE), 0xffffffff padded     */
   SEMK_PA_ELBLK = 12,         /* uint16 [n_patch][el_stride] device index blocks: the ELOC
                                  table [m][le][t] followed by the PE element colours        */
-  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared_rec][4] {node id | flags, slot 0, slot 1, ext} for the
-                                 shared nodes not covered by a chunk; ext = 0xffffffff or offset
-                                 in SHARED_EXT                                                   */
-  SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         {extra count, extra slots...} for nodes shared
-                                 by more than two patches                                       */
-  SEMK_PA_SHARED_CHUNK = 15,  /* uint32 [n_shared_chunk][8] affine chunks of <= 32 two-patch nodes:
+  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared_rec][8] {node id | flags, count, slot 0..5} for the
+                                 shared nodes touched by 3+ patches (corners); counts above 6:
+                                 slots 0..4 inline, word 7 = offset of the rest in SHARED_EXT   */
+  SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         overflow slot lists of SHARED_REC            */
+  SEMK_PA_SHARED_CHUNK = 15,  /* uint32 [n_shared_chunk][8] affine chunks of 1..32 two-patch nodes:
                                  {node0, dn, a0, da, b0, db, len, Dirichlet mask};
                                  node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
   SEMK_PA_PATCH_NCIN = 16,    /* int32  [n_patch]     nodes carried in from the previous patch of the
@@ -172,7 +171,7 @@ typedef struct semk_op {
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums, contiguous per patch (scratch) */
   int64_t n_shared;           /* number of per-node interface records                        */
-  const uint32_t *shared_rec; /* [n_shared][4] packed interface records (SEMK_PA_SHARED_REC) */
+  const uint32_t *shared_rec; /* [n_shared][8] packed interface records (SEMK_PA_SHARED_REC) */
   const uint32_t *shared_ext; /* overflow slot lists (SEMK_PA_SHARED_EXT)                    */
   int64_t n_shared_chunk;     /* number of affine interface chunks                           */
   const uint32_t *shared_chunk; /* [n_shared_chunk][8] (SEMK_PA_SHARED_CHUNK)                */

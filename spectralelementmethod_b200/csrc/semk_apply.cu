@@ -564,9 +564,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
 //   CTAs [0, chunk_blocks): one warp per affine chunk of <= 32 two-patch nodes --
 //     node ids and both slot runs are arithmetic progressions, so a whole patch
 //     edge is reduced with coalesced accesses and 32 bytes of table per chunk;
-//   remaining CTAs: per-node records (corner nodes, irregular pairs), each thread
-//     kSharedUnroll nodes with all record loads, then all slot loads, in flight.
-constexpr int kSharedUnroll = 4;
+//   remaining CTAs: per-node records (nodes touched by 3+ patches), slot list inline.
 constexpr int kChunkWarps = 8;   // warps per CTA of 256 threads
 constexpr int kChunkUnroll = 4;  // chunks per warp
 
@@ -633,38 +631,31 @@ __global__ void __launch_bounds__(256)
       }
     }
   } else {
+    // per-node records (nodes touched by 3+ patches): one node per thread, the whole
+    // slot list inline in a 32-byte record, so two dependent memory levels
     const int64_t nb = (int64_t)gridDim.x - chunk_blocks;
     const int64_t stride = nb * blockDim.x;
-    for (int64_t i0 = ((int64_t)blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x;
-         i0 < op.n_shared; i0 += stride * kSharedUnroll) {
-      uint4 rec[kSharedUnroll];
-      double a[kSharedUnroll], b[kSharedUnroll];
+    for (int64_t i = ((int64_t)blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x;
+         i < op.n_shared; i += stride) {
+      const uint4 r0 = reinterpret_cast<const uint4 *>(op.shared_rec)[2 * i];
+      const uint4 r1 = reinterpret_cast<const uint4 *>(op.shared_rec)[2 * i + 1];
+      const uint32_t cnt = r0.y;
+      const uint32_t sl[6] = {r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      double val[6];
 #pragma unroll
-      for (int k = 0; k < kSharedUnroll; ++k) {
-        const int64_t i = i0 + k * stride;
-        rec[k] = (i < op.n_shared) ? reinterpret_cast<const uint4 *>(op.shared_rec)[i]
-                                   : make_uint4(0xffffffffu, 0u, 0u, 0xffffffffu);
-      }
+      for (int j = 0; j < 6; ++j)
+        val[j] = ((uint32_t)j < cnt && !(cnt > 6 && j == 5)) ? op.slot_buf[sl[j]] : 0.0;
+      double v = val[0];  // ascending patch order: deterministic
 #pragma unroll
-      for (int k = 0; k < kSharedUnroll; ++k) {
-        const bool on = rec[k].x != 0xffffffffu;
-        a[k] = on ? op.slot_buf[rec[k].y] : 0.0;
-        b[k] = on ? op.slot_buf[rec[k].z] : 0.0;
+      for (int j = 1; j < 6; ++j)
+        if ((uint32_t)j < cnt && !(cnt > 6 && j == 5)) v += val[j];
+      if (cnt > 6) {
+        const uint32_t *ext = op.shared_ext + r1.w;
+        for (uint32_t j = 5; j < cnt; ++j) v += op.slot_buf[ext[j - 5]];
       }
-#pragma unroll
-      for (int k = 0; k < kSharedUnroll; ++k) {
-        if (rec[k].x == 0xffffffffu) continue;
-        const uint32_t pn = rec[k].x;
-        double v = a[k] + b[k];  // ascending patch order: deterministic
-        if (rec[k].w != 0xffffffffu) {  // corner nodes: 3+ patches
-          const uint32_t *ext = op.shared_ext + rec[k].w;
-          const uint32_t extra = ext[0];
-          for (uint32_t j = 0; j < extra; ++j) v += op.slot_buf[ext[1 + j]];
-        }
-        dot += finish_shared_node<MODE>(op, pn & SEMK_NODE_ID_MASK,
-                                        (pn & SEMK_NODE_DIRICHLET) != 0, v, u, y, flags,
-                                        fill_dirichlet, want_dot);
-      }
+      dot += finish_shared_node<MODE>(op, r0.x & SEMK_NODE_ID_MASK,
+                                      (r0.x & SEMK_NODE_DIRICHLET) != 0, v, u, y, flags,
+                                      fill_dirichlet, want_dot);
     }
   }
   if (want_dot) {
@@ -689,7 +680,7 @@ constexpr int kSharedBlocks = 148 * 64;  // upper bound on the per-node part of 
 inline void interface_blocks(const semk_op &op, int *chunk_blocks, int *rec_blocks) {
   const int64_t per_block = (int64_t)kChunkWarps * kChunkUnroll;
   *chunk_blocks = (int)((op.n_shared_chunk + per_block - 1) / per_block);
-  const int64_t want = (op.n_shared + 256 * kSharedUnroll - 1) / (256 * kSharedUnroll);
+  const int64_t want = (op.n_shared + 255) / 256;
   *rec_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
 }
 

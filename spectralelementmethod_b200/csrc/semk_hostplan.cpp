@@ -344,7 +344,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           }
         }
         const size_t len = e - s;
-        if (len >= 2) {
+        {
           uint32_t mask = 0;
           for (size_t k = 0; k < len; ++k) {
             if (pairs[ord[s + k]].node & SEMK_NODE_DIRICHLET) mask |= (1u << k);
@@ -361,7 +361,9 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         }
         s = e;
       }
-      // per-node records for everything not covered by a chunk (ascending id)
+      // per-node records for everything not covered by a chunk (ascending id):
+      // {node | flags, count, slot 0..5}; counts above 6 continue in SHARED_EXT at the
+      // offset stored in the last word ({extra slots...})
       size_t pi = 0;
       for (int64_t i = 0; i < n_shared; ++i) {
         const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
@@ -369,20 +371,19 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           const bool t = taken[pi++] != 0;
           if (t) continue;
         }
-        P->shared_rec.push_back(P->shared_node[i]);
-        P->shared_rec.push_back((uint32_t)P->shared_slot[j0]);
-        P->shared_rec.push_back((uint32_t)P->shared_slot[j0 + 1]);
-        if (cnt > 2) {
-          P->shared_rec.push_back((uint32_t)P->shared_ext.size());
-          P->shared_ext.push_back((uint32_t)(cnt - 2));
-          for (int32_t j = j0 + 2; j < j0 + cnt; ++j)
-            P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
+        uint32_t r[8] = {P->shared_node[i], (uint32_t)cnt, 0, 0, 0, 0, 0, 0};
+        if (cnt <= 6) {
+          for (int32_t j = 0; j < cnt; ++j) r[2 + j] = (uint32_t)P->shared_slot[j0 + j];
         } else {
-          P->shared_rec.push_back(0xffffffffu);
+          for (int32_t j = 0; j < 5; ++j) r[2 + j] = (uint32_t)P->shared_slot[j0 + j];
+          r[7] = (uint32_t)P->shared_ext.size();
+          for (int32_t j = j0 + 5; j < j0 + cnt; ++j)
+            P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
         }
+        P->shared_rec.insert(P->shared_rec.end(), r, r + 8);
       }
       if (P->shared_ext.empty()) P->shared_ext.push_back(0);
-      if (P->shared_rec.empty()) P->shared_rec.assign(4, 0xffffffffu);
+      if (P->shared_rec.empty()) P->shared_rec.assign(8, 0xffffffffu);
       if (P->shared_chunk.empty()) P->shared_chunk.assign(8, 0);
     }
 
@@ -414,8 +415,8 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       int64_t n_chunk = 0, n_rec = 0;
       if (!(P->shared_chunk.size() == 8 && P->shared_chunk[6] == 0))
         n_chunk = (int64_t)P->shared_chunk.size() / 8;
-      if (!(P->shared_rec.size() == 4 && P->shared_rec[0] == 0xffffffffu))
-        n_rec = (int64_t)P->shared_rec.size() / 4;
+      if (!(P->shared_rec.size() == 8 && P->shared_rec[0] == 0xffffffffu))
+        n_rec = (int64_t)P->shared_rec.size() / 8;
       P->scalars[SEMK_PS_N_SHARED_CHUNK] = n_chunk;
       P->scalars[SEMK_PS_N_SHARED_REC] = n_rec;
     }

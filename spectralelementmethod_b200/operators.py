@@ -95,7 +95,7 @@ def _morton_order(cx, cy):
     return np.argsort(key, kind="stable").astype(np.int64)
 
 
-def default_element_order(mesh, elems_per_patch, tile=None):
+def default_element_order(mesh, elems_per_patch, tile=None, columns_first=False):
     """Engine slot order (slot -> element) that makes consecutive runs of
     ``elems_per_patch`` elements compact patches: tiles of a structured grid
     when the mesh builder recorded one, else a Morton curve through the cell
@@ -107,11 +107,17 @@ def default_element_order(mesh, elems_per_patch, tile=None):
         if bx * by != elems_per_patch:
             raise ValueError("tile shape does not match elems_per_patch")
         ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
-        # tiles enumerated down a tile column (tx fastest): consecutive patches share a
-        # whole edge of contiguously numbered nodes, which the persistent kernel carries
-        # from one patch to the next in shared memory
-        ntx = (nx + bx - 1) // bx
-        key = ((ey // by) * ntx + ex // bx) * (bx * by) + (ex % bx) * by + ey % by
+        if columns_first:
+            # tiles enumerated down a tile column (tx fastest): consecutive patches share
+            # a whole edge of contiguously numbered nodes, which the persistent kernel can
+            # carry from one patch to the next in shared memory (carry=True)
+            ntx = (nx + bx - 1) // bx
+            tile_id = (ey // by) * ntx + ex // bx
+        else:
+            # tiles enumerated along the contiguous node direction: the resident CTAs work
+            # on a compact window of the mesh at any time (best DRAM / L2 locality)
+            tile_id = (ex // bx) * ((ny + by - 1) // by) + ey // by
+        key = tile_id * (bx * by) + (ex % bx) * by + ey % by
         return np.argsort(key, kind="stable").astype(np.int64)
     if not hasattr(mesh, "_centroids"):
         mesh._compute_cell_centroids()
@@ -135,7 +141,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, tile=None, carry=True):
+                 elem_order=None, keep_l2g=True, tile=None, carry=False):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -157,7 +163,7 @@ class PoissonOperator(object):
 
         pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
         if elem_order is None:
-            elem_order = default_element_order(mesh, pe, tile)
+            elem_order = default_element_order(mesh, pe, tile, columns_first=carry)
         # The persistent apply kernel runs one CTA per resident slot and gives each a
         # contiguous range of patches; the plan needs that number to decide which
         # interface nodes are carried inside a CTA.  Estimate it from the expected patch

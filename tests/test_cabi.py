@@ -166,24 +166,23 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     ext = ar[_lib.PA_SHARED_EXT]
     nch, nrec = sc[_lib.PS_N_SHARED_CHUNK], sc[_lib.PS_N_SHARED_REC]
     chunk = ar[_lib.PA_SHARED_CHUNK].reshape(-1, 8)[:nch].astype(np.int64)
-    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 4)[:nrec]
+    rec = ar[_lib.PA_SHARED_REC].reshape(-1, 8)[:nrec]
     want = {int(sn[i] & _lib.NODE_ID_MASK): (ss[sp[i]:sp[i + 1]].tolist(),
                                              bool(sn[i] & _lib.NODE_DIRICHLET))
             for i in range(sn.size)}
     seen = {}
     for node0, dn, a0, da, b0, db, ln, mask in chunk.tolist():
-        assert 2 <= ln <= 32
-        dn, da, db = (np.int64(v).astype(np.int32) if False else (v - (1 << 32) if v >= (1 << 31) else v)
-                      for v in (dn, da, db))
+        assert 1 <= ln <= 32
+        dn, da, db = ((v - (1 << 32) if v >= (1 << 31) else v) for v in (dn, da, db))
         for k in range(ln):
             g = node0 + k * dn
             assert g not in seen
             seen[g] = ([a0 + k * da, b0 + k * db], bool((mask >> k) & 1))
     for r in rec.tolist():
         g = r[0] & _lib.NODE_ID_MASK
-        lst = [r[1], r[2]]
-        if r[3] != 0xFFFFFFFF:
-            lst += ext[r[3] + 1:r[3] + 1 + ext[r[3]]].tolist()
+        cnt = r[1]
+        assert cnt >= 3
+        lst = r[2:2 + cnt] if cnt <= 6 else r[2:7] + ext[r[7]:r[7] + cnt - 5].tolist()
         assert g not in seen
         seen[g] = (lst, bool(r[0] & _lib.NODE_DIRICHLET))
     assert seen == want
