@@ -316,8 +316,8 @@ typedef struct semk_pcg_info {
 } semk_pcg_info;
 
 /* Native single-GPU PCG driver on Ahat = M A M + (I - M): solves
- * Ahat x = b from the initial guess in x.  work: device [4*n] (r, p, Ap,
- * spare); sc: device [8]; vec_partials as above.  Convergence
+ * Ahat x = b from the initial guess in x.  work: device [3*(n+32)] or
+ * more (r, p, Ap, 256-byte aligned); sc: device [8]; vec_partials as above.  Convergence
  * ||r|| <= rtol*||b|| is polled every check_every iterations (one 32-byte
  * D2H copy); no other host synchronisation. */
 int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x, const double *dinv,

@@ -21,7 +21,7 @@ constexpr int kVecThreads = 256;
 constexpr int kVecMaxBlocks = 148 * 8;
 
 inline int vec_blocks(int64_t n) {
-  const int64_t want = (n + kVecThreads * 2 - 1) / (kVecThreads * 2);
+  const int64_t want = (n + kVecThreads * 4 - 1) / (kVecThreads * 4);
   return (int)(want < 1 ? 1 : (want < kVecMaxBlocks ? want : kVecMaxBlocks));
 }
 
@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(kVecThreads)
   }
 }
 
+// VEC: all vector pointers are 16-byte aligned -> 128-bit loads/stores, two pairs
+// per thread and iteration in flight (these kernels are pure HBM streams).
+template <bool VEC>
 __global__ void __launch_bounds__(kVecThreads)
     pcg_update_xr_kernel(int64_t n, int64_t n_dot, const double *__restrict__ p,
                          const double *__restrict__ Ap, const double *__restrict__ dinv,
@@ -106,8 +109,9 @@ __global__ void __launch_bounds__(kVecThreads)
   const bool ok = (pAp > 0.0) && (rz == rz);
   const double alpha = ok ? rz / pAp : 0.0;
   double acc[2] = {0.0, 0.0};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  auto one = [&](int64_t i) {
     x[i] = fma(alpha, p[i], x[i]);
     const double ri = fma(-alpha, Ap[i], r[i]);
     r[i] = ri;
@@ -115,6 +119,61 @@ __global__ void __launch_bounds__(kVecThreads)
       acc[0] = fma(ri * dinv[i], ri, acc[0]);
       acc[1] = fma(ri, ri, acc[1]);
     }
+  };
+  if (VEC) {
+    const int64_t npair = n >> 1;
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    const double2 *Ap2 = reinterpret_cast<const double2 *>(Ap);
+    const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    for (int64_t j0 = tid; j0 < npair; j0 += 2 * nthreads) {
+      const int64_t j1 = j0 + nthreads;
+      const bool two = j1 < npair;
+      const double2 pa = p2[j0], aa = Ap2[j0], xa = x2[j0], ra = r2[j0], da = d2[j0];
+      double2 pb = pa, ab = aa, xb = xa, rb = ra, db = da;
+      if (two) {
+        pb = p2[j1];
+        ab = Ap2[j1];
+        xb = x2[j1];
+        rb = r2[j1];
+        db = d2[j1];
+      }
+      double2 xo, ro;
+      xo.x = fma(alpha, pa.x, xa.x);
+      xo.y = fma(alpha, pa.y, xa.y);
+      ro.x = fma(-alpha, aa.x, ra.x);
+      ro.y = fma(-alpha, aa.y, ra.y);
+      x2[j0] = xo;
+      r2[j0] = ro;
+      if (2 * j0 < n_dot) {
+        acc[0] = fma(ro.x * da.x, ro.x, acc[0]);
+        acc[1] = fma(ro.x, ro.x, acc[1]);
+      }
+      if (2 * j0 + 1 < n_dot) {
+        acc[0] = fma(ro.y * da.y, ro.y, acc[0]);
+        acc[1] = fma(ro.y, ro.y, acc[1]);
+      }
+      if (two) {
+        xo.x = fma(alpha, pb.x, xb.x);
+        xo.y = fma(alpha, pb.y, xb.y);
+        ro.x = fma(-alpha, ab.x, rb.x);
+        ro.y = fma(-alpha, ab.y, rb.y);
+        x2[j1] = xo;
+        r2[j1] = ro;
+        if (2 * j1 < n_dot) {
+          acc[0] = fma(ro.x * db.x, ro.x, acc[0]);
+          acc[1] = fma(ro.x, ro.x, acc[1]);
+        }
+        if (2 * j1 + 1 < n_dot) {
+          acc[0] = fma(ro.y * db.y, ro.y, acc[0]);
+          acc[1] = fma(ro.y, ro.y, acc[1]);
+        }
+      }
+    }
+    if ((n & 1) && tid == 0) one(n - 1);
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) one(i);
   }
   double tot[2];
   if (finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
@@ -126,6 +185,7 @@ __global__ void __launch_bounds__(kVecThreads)
   }
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kVecThreads)
     pcg_update_p_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ dinv,
                         double *__restrict__ p, double *__restrict__ sc,
@@ -142,9 +202,37 @@ __global__ void __launch_bounds__(kVecThreads)
     const unsigned long long t = atomicAdd(counter_of(partials), 1ull);
     is_last = (t == (unsigned long long)gridDim.x - 1ull);
   }
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = fma(beta, p[i], dinv[i] * r[i]);
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    const int64_t npair = n >> 1;
+    const double2 *r2 = reinterpret_cast<const double2 *>(r);
+    const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    for (int64_t j0 = tid; j0 < npair; j0 += 2 * nthreads) {
+      const int64_t j1 = j0 + nthreads;
+      const bool two = j1 < npair;
+      const double2 ra = r2[j0], da = d2[j0], pa = p2[j0];
+      double2 rb = ra, db = da, pb = pa;
+      if (two) {
+        rb = r2[j1];
+        db = d2[j1];
+        pb = p2[j1];
+      }
+      double2 o;
+      o.x = fma(beta, pa.x, da.x * ra.x);
+      o.y = fma(beta, pa.y, da.y * ra.y);
+      p2[j0] = o;
+      if (two) {
+        o.x = fma(beta, pb.x, db.x * rb.x);
+        o.y = fma(beta, pb.y, db.y * rb.y);
+        p2[j1] = o;
+      }
+    }
+    if ((n & 1) && tid == 0) p[n - 1] = fma(beta, p[n - 1], dinv[n - 1] * r[n - 1]);
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) p[i] = fma(beta, p[i], dinv[i] * r[i]);
+  }
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
     sc[0] = rz_new;
@@ -181,11 +269,23 @@ extern "C" int semk_pcg_init_f64(int64_t n, int64_t n_dot, const double *b, cons
   return SEMK_OK;
 }
 
+static inline bool aligned16(const void *a, const void *b, const void *c, const void *d,
+                             const void *e) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+           reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(d) |
+           reinterpret_cast<uintptr_t>(e)) &
+          15u) == 0;
+}
+
 static int update_xr(int64_t n, int64_t n_dot, const double *p, const double *Ap,
                      const double *dinv, double *x, double *r, double *sc, double *partials,
                      double tol2, cudaStream_t st) {
-  pcg_update_xr_kernel<<<vec_blocks(n), kVecThreads, 0, st>>>(n, n_dot, p, Ap, dinv, x, r, sc,
-                                                             partials, tol2);
+  if (aligned16(p, Ap, dinv, x, r))
+    pcg_update_xr_kernel<true><<<vec_blocks(n), kVecThreads, 0, st>>>(n, n_dot, p, Ap, dinv, x, r,
+                                                                     sc, partials, tol2);
+  else
+    pcg_update_xr_kernel<false><<<vec_blocks(n), kVecThreads, 0, st>>>(n, n_dot, p, Ap, dinv, x,
+                                                                      r, sc, partials, tol2);
   SEMK_LAUNCH_CHECK("pcg_update_xr_kernel");
   return SEMK_OK;
 }
@@ -204,8 +304,12 @@ extern "C" int semk_pcg_update_p_f64(int64_t n, const double *r, const double *d
                                       double *sc, double *partials, void *stream) {
   SEMK_REQUIRE(n > 0, "semk_pcg_update_p_f64: bad size");
   SEMK_REQUIRE(r && dinv && p && sc && partials, "semk_pcg_update_p_f64: null pointer");
-  pcg_update_p_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(n, r, dinv, p, sc,
-                                                                             partials);
+  if (aligned16(r, dinv, p, p, p))
+    pcg_update_p_kernel<true><<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(
+        n, r, dinv, p, sc, partials);
+  else
+    pcg_update_p_kernel<false><<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(
+        n, r, dinv, p, sc, partials);
   SEMK_LAUNCH_CHECK("pcg_update_p_kernel");
   return SEMK_OK;
 }
@@ -227,7 +331,8 @@ extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
   SEMK_REQUIRE(maxiter >= 0 && check_every >= 1 && rtol >= 0.0, "semk_pcg_solve_f64: bad control");
   cudaStream_t st = semk_stream(stream);
   const int64_t n = op->n_nodes;
-  double *r = work, *p = work + n, *Ap = work + 2 * n;
+  const int64_t n_pad = (n + 31) & ~(int64_t)31;  // keeps the sub-vectors 16-byte aligned
+  double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad;
   const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
   const double tol2 = rtol * rtol;
   static double *h_sc = nullptr;  // pinned landing zone for the 64-byte scalar block

@@ -416,7 +416,7 @@ class PoissonOperator(object):
         else:
             x = self._vec(x0, "x0").clone()
         dinv = self.jacobi_inverse()
-        work = torch.empty(4 * self.n_nodes, dtype=torch.float64, device=self.dev)
+        work = torch.empty(3 * (self.n_nodes + 32), dtype=torch.float64, device=self.dev)
         sc = torch.zeros(8, dtype=torch.float64, device=self.dev)
         info = _lib.semk_pcg_info()
         rc = self._lib.semk_pcg_solve_f64(
