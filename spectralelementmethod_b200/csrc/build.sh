@@ -8,7 +8,7 @@ OBJS=""
 for f in semk_api.cu semk_geom.cu semk_apply.cu semk_vec.cu; do
   o="${f%.cu}.o"
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ semk_common.cuh -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
-    $NVCC $FLAGS ${SEMK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
+    $NVCC $FLAGS ${SEMK_EXTRA_FLAGS:-} ${SEMK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
   fi
   OBJS="$OBJS $o"
 done

@@ -480,6 +480,16 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       };
       local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2],
                            (uint32_t)(it & 1), refill_g, refill_tables);
+      // u . y taken element by element: sum_e (Q_e u) . y_e = u . (sum_e Q_e^T y_e), so the
+      // write-out never looks at u again.  Dirichlet rows are left out here (under MASK_IN
+      // their entries of u are zero anyway) and come back as identity rows below.
+      if (want_dot && active) {
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          const bool drop = (flags & SEMK_MASK_OUT) && ((ucol_dir >> m) & 1u);
+          dot = fma(drop ? 0.0 : ucol[m], ycol[m], dot);
+        }
+      }
       // next patch: its tables landed long ago; start its gather now
       if (has_next) {
         semk_mbar_wait(&mbar[s ^ 1], (uint32_t)(((it + 1) >> 1) & 1));
@@ -526,23 +536,18 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
         if (k < npriv) {
           if (k < ncin) v += carry_in[k];  // partial sum of the previous patch
           const uint32_t g = pn & SEMK_NODE_ID_MASK;
-          const bool dir = (pn & SEMK_NODE_DIRICHLET) != 0;
-          double uin = 0.0;
-          if (MODE == MODE_APPLY) {
-            if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
-          }
-          if (dir && (flags & SEMK_MASK_OUT)) {
+          if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_OUT)) {
             if (MODE == MODE_APPLY) {
-              v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
-              uin = v;
+              v = 0.0;
+              if (flags & SEMK_DIRICHLET_IDENTITY) {
+                v = u[g];
+                dot = fma(v, v, dot);  // the identity rows' share of u . y
+              }
             } else {
               v = fill_dirichlet;
             }
-          } else if (dir && (flags & SEMK_MASK_IN)) {
-            uin = 0.0;
           }
           y[g] = v;
-          dot = fma(uin, v, dot);
         } else if (k < npriv + ncout) {
           carry_out[k - npriv] = v;  // completed by the next patch of this CTA
         } else {
@@ -568,27 +573,27 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
 constexpr int kChunkWarps = 8;   // warps per CTA of 256 threads
 constexpr int kChunkUnroll = 4;  // chunks per warp
 
+// Writes the final value of a shared node; returns its identity-row share of u . y
+// (the rest of u . y is taken element by element in the patch kernel).
 template <int MODE>
 __device__ __forceinline__ double finish_shared_node(const semk_op &op, uint32_t g, bool dir,
                                                      double v, const double *__restrict__ u,
                                                      double *__restrict__ y, int flags,
                                                      double fill_dirichlet, bool want_dot) {
-  double uin = 0.0;
-  if (MODE == MODE_APPLY) {
-    if (want_dot || (dir && (flags & SEMK_MASK_OUT))) uin = u[g];
-  }
+  double d = 0.0;
   if (dir && (flags & SEMK_MASK_OUT)) {
     if (MODE == MODE_APPLY) {
-      v = (flags & SEMK_DIRICHLET_IDENTITY) ? uin : 0.0;
-      uin = v;
+      v = 0.0;
+      if (flags & SEMK_DIRICHLET_IDENTITY) {
+        v = u[g];
+        d = v * v;
+      }
     } else {
       v = fill_dirichlet;
     }
-  } else if (dir && (flags & SEMK_MASK_IN)) {
-    uin = 0.0;
   }
   y[g] = v;
-  return uin * v;
+  return want_dot ? d : 0.0;
 }
 
 template <int MODE>

@@ -41,10 +41,23 @@ def test_version_and_error_channel():
     assert lib.semk_device_available() in (0, 1)
 
 
-def test_struct_layout_matches_header():
-    # 25 fields; 8-byte aligned pointers after two int32 pairs
-    assert ctypes.sizeof(_lib.semk_op) == 8 + 3 * 8 + 8 + 2 * 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8
-    assert ctypes.sizeof(_lib.semk_pcg_info) == 24
+def test_struct_layout_matches_header(tmp_path):
+    # compile the header with gcc and compare sizeof / offsetof of every field with ctypes
+    fields = [f[0] for f in _lib.semk_op._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "semk.h"', 'int main(void) {',
+           '  printf("%zu %zu\\n", sizeof(struct semk_op), sizeof(struct semk_pcg_info));']
+    src += ['  printf("%%zu\\n", offsetof(struct semk_op, %s));' % f for f in fields]
+    src += ['  return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    import subprocess
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) == ctypes.sizeof(_lib.semk_op)
+    assert int(out[1]) == ctypes.sizeof(_lib.semk_pcg_info) == 24
+    for f, off in zip(fields, out[2:]):
+        assert getattr(_lib.semk_op, f).offset == int(off), f
 
 
 def _plan(nx, ny, p, pe, order=None, dirichlet=None, n_ranges=0):
