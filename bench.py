@@ -48,8 +48,6 @@ def parse():
     ap.add_argument("--kind", default="S", choices=["S", "C"])
     ap.add_argument("--pe", type=int, default=0, help="elements per patch (0 = automatic)")
     ap.add_argument("--tile", default="", help="patch tile shape bx,by (elements), e.g. 2,8")
-    ap.add_argument("--carry", action="store_true",
-                    help="carry interface nodes between consecutive patches of a CTA range")
     ap.add_argument("--ablate", type=int, default=0,
                     help="internal profiling knob: extra apply flag bits (results are wrong)")
     return ap.parse_args()
@@ -227,8 +225,7 @@ def run_engine(args):
         mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
         on_ebc = mngr.boundary_node_mask("ebc")
         tile = tuple(int(v) for v in args.tile.split(",")) if args.tile else None
-        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None, tile=tile,
-                                   carry=args.carry)
+        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None, tile=tile)
         if args.ablate:
             abl = op._masked_flags | args.ablate
             apply_fn = lambda u, out: op.apply(u, out=out, flags=abl)   # noqa: E731

@@ -75,10 +75,10 @@ typedef struct semk_hostplan semk_hostplan;
 enum semk_plan_array {
   SEMK_PA_PATCH_NODE_PTR = 0, /* int32  [n_patch+1]   offsets into PNODE (multiples of 4)    */
   SEMK_PA_PNODE = 1,          /* uint32 [n_pnode]     global id | flags, per patch in the order
-                                 [carried-in | private | carried-out | shared], each class
-                                 ascending; padded with 0xffffffff to a multiple of 4       */
-  SEMK_PA_PATCH_NPRIV = 2,    /* int32  [n_patch]     leading nodes of the list the patch itself writes
-                                 to the result: carried-in nodes, then private nodes        */
+                                 [private | shared], each class ascending; padded with
+                                 0xffffffff to a multiple of 4                              */
+  SEMK_PA_PATCH_NPRIV = 2,    /* int32  [n_patch]     private nodes: the leading entries of the list,
+                                 which the patch itself writes to the result                */
   SEMK_PA_PATCH_SLOT_BASE = 3,/* int32  [n_patch]     first interface slot of the patch      */
   SEMK_PA_ELOC = 4,           /* uint16 [n_patch][eloc_patch_stride]: per patch a table
                                  [m][le][t] (NN*PE entries) of patch-local node indices:
@@ -90,11 +90,14 @@ enum semk_plan_array {
   SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node,
                                  ascending patch (slot = PATCH_SLOT_BASE[p] + k)             */
   SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
-  SEMK_PA_PNBLK = 11,         /* uint32 [n_patch][pn_stride] device node blocks, uniform stride:
-                                 {n nodes, n private, first interface slot, 0} followed by
-                                 the patch's node list (as in PNODE), 0xffffffff padded     */
-  SEMK_PA_ELBLK = 12,         /* uint16 [n_patch][el_stride] device index blocks: the ELOC
-                                 table [m][le][t] followed by the PE element colours        */
+  SEMK_PA_PNBLK = 11,         /* uint32 [n_pn_unique][pn_stride] device node blocks: a patch's node
+                                 list as in PNODE but RELATIVE to the patch's smallest node
+                                 id (flags kept in the top bits), 0xffffffff padded.
+                                 Identical blocks are stored once; PATCH_HDR word 5 says
+                                 which block a patch uses                                   */
+  SEMK_PA_ELBLK = 12,         /* uint16 [n_el_unique][el_stride] device index blocks: the ELOC
+                                 table [m][le][t] followed by the PE element colours;
+                                 deduplicated like PNBLK (PATCH_HDR word 6)                 */
   SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared_rec][8] {node id | flags, count, slot 0..5} for the
                                  shared nodes touched by 3+ patches (corners); counts above 6:
                                  slots 0..4 inline, word 7 = offset of the rest in SHARED_EXT   */
@@ -102,10 +105,9 @@ enum semk_plan_array {
   SEMK_PA_SHARED_CHUNK = 15,  /* uint32 [n_shared_chunk][8] affine chunks of 1..32 two-patch nodes:
                                  {node0, dn, a0, da, b0, db, len, Dirichlet mask};
                                  node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
-  SEMK_PA_PATCH_NCIN = 16,    /* int32  [n_patch]     nodes carried in from the previous patch of the
-                                 same CTA range (the patch adds the carried partial sums)   */
-  SEMK_PA_PATCH_NCOUT = 17,   /* int32  [n_patch]     nodes carried out to the next patch         */
-  SEMK_PA_COUNT = 18
+  SEMK_PA_PATCH_HDR = 16,     /* uint32 [n_patch][8]  {n nodes, n private, first interface slot, 0,
+                                 base node id, PNBLK block, ELBLK block, 0}                   */
+  SEMK_PA_COUNT = 17
 };
 
 enum semk_plan_scalar {
@@ -121,8 +123,8 @@ enum semk_plan_scalar {
   SEMK_PS_EL_STRIDE = 9,      /* uint16 entries per patch block of ELBLK (multiple of 8)       */
   SEMK_PS_N_SHARED_CHUNK = 10,/* number of affine interface chunks                             */
   SEMK_PS_N_SHARED_REC = 11,  /* number of per-node interface records                          */
-  SEMK_PS_PATCHES_PER_RANGE = 12, /* C: CTA r of the persistent kernel owns patches [rC, (r+1)C)  */
-  SEMK_PS_MAX_CARRY = 13,     /* largest carried-in / carried-out count of a patch             */
+  SEMK_PS_N_PN_UNIQUE = 12,   /* distinct node blocks in PNBLK                                 */
+  SEMK_PS_N_EL_UNIQUE = 13,   /* distinct index blocks in ELBLK                                */
   SEMK_PS_COUNT = 14
 };
 
@@ -131,14 +133,10 @@ enum semk_plan_scalar {
  *      permutation, slot -> element (NULL = identity); consecutive runs of
  *      elems_per_patch slots form one patch.  dirichlet: host uint8 [n_nodes]
  *      (1 = essential-BC node, the reference's on_ebc polarity,
- *      sem/discrete.py:505) or NULL.  n_ranges: number of CTAs of the
- *      persistent apply kernel (semk_resident_ctas); CTA r processes the
- *      contiguous patch range [r*C, (r+1)*C), C = ceil(n_patch / n_ranges), and
- *      nodes shared only by two consecutive patches of one range are carried in
- *      shared memory instead of through interface slots.  0 = no carrying. */
+ *      sem/discrete.py:505) or NULL. */
 int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
                          const int64_t *elem_order, int elems_per_patch,
-                         const uint8_t *dirichlet, int64_t n_ranges, semk_hostplan **out);
+                         const uint8_t *dirichlet, semk_hostplan **out);
 int64_t semk_hostplan_scalar(const semk_hostplan *plan, int which);
 const void *semk_hostplan_array(const semk_hostplan *plan, int which, int64_t *n_bytes);
 void semk_hostplan_destroy(semk_hostplan *plan);
@@ -155,18 +153,16 @@ typedef struct semk_op {
   int64_t n_patch;
   int32_t max_patch_nodes;
   int32_t max_colors;
-  int64_t patches_per_range;/* C of the plan (SEMK_PS_PATCHES_PER_RANGE); 0: one patch per step,
-                               round-robin over the grid                                   */
-  int64_t max_carry;        /* SEMK_PS_MAX_CARRY                                            */
   int64_t g_patch_stride;   /* doubles per patch block of G (even, >= 3*NN*PE)          */
   const double *G;          /* [n_patch][g_patch_stride]; inside a patch block the factor
                                c (0: G00, 1: G01, 2: G11) at node (m, t) of the le-th
                                element sits at ((c*n1 + m)*PE + le)*n1 + t, i.e. rows of
                                n1*PE doubles indexed by thread (le, t): coalesced, and
                                bank-conflict free once staged in shared memory           */
-  const uint32_t *pnode;    /* [n_patch][pn_patch_stride] node blocks (SEMK_PA_PNBLK)     */
+  const uint32_t *patch_hdr;/* [n_patch][8] per-patch headers (SEMK_PA_PATCH_HDR)           */
+  const uint32_t *pnode;    /* [n_pn_unique][pn_patch_stride] node blocks (SEMK_PA_PNBLK)  */
   int64_t pn_patch_stride;  /* uint32 entries per node block (multiple of 4)             */
-  const uint16_t *eloc;     /* [n_patch][eloc_patch_stride] index blocks (SEMK_PA_ELBLK) */
+  const uint16_t *eloc;     /* [n_el_unique][eloc_patch_stride] index blocks (SEMK_PA_ELBLK) */
   int64_t eloc_patch_stride;/* uint16 entries per index block (multiple of 8)            */
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums, contiguous per patch (scratch) */
@@ -187,11 +183,11 @@ int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
  * configuration = the grid of the persistent kernel; <0 on error */
 int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
                            int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                           int max_patch_nodes, int max_carry);
+                           int max_patch_nodes);
 /* dynamic shared memory (bytes) one CTA of the apply kernel needs */
 int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                               int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                              int max_patch_nodes, int max_carry);
+                              int max_patch_nodes);
 
 /* ------------------------------------------------------------------------
  * K1: geometric factors.  Replaces, per element, Mapping._compute_x_phys /

@@ -21,11 +21,12 @@ MAX_N1 = 17
 
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
- PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT, PA_SHARED_CHUNK, PA_PATCH_NCIN,
- PA_PATCH_NCOUT) = range(18)
+ PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT, PA_SHARED_CHUNK,
+ PA_PATCH_HDR) = range(17)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
  PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE, PS_N_SHARED_CHUNK,
- PS_N_SHARED_REC, PS_PATCHES_PER_RANGE, PS_MAX_CARRY) = range(14)
+ PS_N_SHARED_REC, PS_N_PN_UNIQUE, PS_N_EL_UNIQUE) = range(14)
+PS_COUNT = 14
 
 PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
@@ -33,7 +34,7 @@ PLAN_ARRAY_DTYPES = {
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
     PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
     PA_ELBLK: np.uint16, PA_SHARED_REC: np.uint32, PA_SHARED_EXT: np.uint32,
-    PA_SHARED_CHUNK: np.uint32, PA_PATCH_NCIN: np.int32, PA_PATCH_NCOUT: np.int32,
+    PA_SHARED_CHUNK: np.uint32, PA_PATCH_HDR: np.uint32,
 }
 
 
@@ -53,9 +54,8 @@ class semk_op(C.Structure):
         ("n1", C.c_int32), ("elems_per_patch", C.c_int32),
         ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
         ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
-        ("patches_per_range", C.c_int64), ("max_carry", C.c_int64),
         ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
-        ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
+        ("patch_hdr", C.c_void_p), ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_rec", C.c_void_p), ("shared_ext", C.c_void_p),
@@ -76,13 +76,13 @@ SIGNATURES = {
     "semk_version": (_I, []),
     "semk_last_error": (C.c_char_p, []),
     "semk_device_available": (_I, []),
-    "semk_hostplan_create": (_I, [_I, _L, _L, _P, _P, _I, _P, _L, C.POINTER(_P)]),
+    "semk_hostplan_create": (_I, [_I, _L, _L, _P, _P, _I, _P, C.POINTER(_P)]),
     "semk_hostplan_scalar": (_L, [_P, _I]),
     "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
     "semk_hostplan_destroy": (None, [_P]),
     "semk_partials_len": (_L, [_L, _L]),
-    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _L, _I, _I]),
-    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _L, _I, _I]),
+    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _L, _I]),
+    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _L, _I]),
     "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P,
                                    _P, _P, _P, _P]),
     "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _I, _P]),
@@ -151,7 +151,7 @@ def require_device():
                            "the operator engine has no CPU fallback")
 
 
-def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None, n_ranges=0):
+def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None):
     """Run the host plan builder; returns (scalars dict, arrays dict of numpy copies)."""
     lib = load()
     l2g = np.ascontiguousarray(l2g, dtype=np.uint32).reshape(-1, n1 * n1)
@@ -170,9 +170,9 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
         dir_p = dirichlet.ctypes.data
     handle = _P()
     check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p,
-                                   int(elems_per_patch), dir_p, int(n_ranges), C.byref(handle)))
+                                   int(elems_per_patch), dir_p, C.byref(handle)))
     try:
-        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(14)}
+        scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(PS_COUNT)}
         arrays = {}
         for k, dt in PLAN_ARRAY_DTYPES.items():
             nb = _L(0)

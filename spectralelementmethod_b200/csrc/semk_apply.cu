@@ -256,22 +256,25 @@ struct PatchCfg {
 
 enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 
+
 // Shared-memory carve-up of the persistent patch kernel (offsets multiples of
 // 16 B): one G buffer, two stages of {node block, index block}, one copy of
 // the working arrays.
 struct PatchSmem {
-  size_t gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
-  size_t yp, carry, carry_len, ua, bs, red, total;
+  size_t hdr, gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
+  size_t yp, ua, bs, red, total;
 };
 __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
                                                        int64_t g_patch_stride,
                                                        int64_t pn_patch_stride,
                                                        int64_t eloc_patch_stride,
-                                                       int max_patch_nodes, int max_carry) {
+                                                       int max_patch_nodes) {
   PatchSmem L;
   const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
   const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
   size_t o = 32;  // three mbarriers: tables[2], G
+  L.hdr = o;      // two 32-byte patch headers (ring)
+  o += 64;
   L.gs = o;
   o += (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
   L.stage0 = o;
@@ -285,9 +288,6 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
   L.yp = o;
   o += 8 * mpn4;
   o = (o + 15) & ~(size_t)15;
-  L.carry = o;  // two buffers of partial sums carried from one patch to the next
-  L.carry_len = ((size_t)max_carry + 1) & ~(size_t)1;
-  o += 2 * 8 * L.carry_len;
   L.ua = o;  // scratch A
   o += (mode == MODE_APPLY) ? 8 * scratch : 0;
   o = (o + 15) & ~(size_t)15;
@@ -307,11 +307,10 @@ __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
   const long long mpn4 = (mpn + 3) & ~3LL;
   const long long nn = (long long)N * N;
   const long long g = 8 * ((3 * nn * PE + 1) & ~1LL);
-  const long long tab = 2 * ((4 * (4 + mpn4) + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL);
+  const long long tab = 2 * ((4 * mpn4 + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL) + 64;
   const long long scr = 8LL * N * scratch_row_stride(N, PE);
   const long long ua = scr;
-  const long long carry = 16LL * ((by * p + 2) & ~1LL);
-  const long long total = 32 + g + tab + 8 * mpn4 + carry + ua + (scr > 256 ? scr : 256) + 1024;
+  const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
   const long long by_smem = 233472 / total;
   const int threads = ((N * PE + 31) / 32) * 32;
   const long long by_regs = 65536 / ((long long)threads * 96);  // assume <= 96 registers/thread
@@ -345,10 +344,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   constexpr int RS = PatchCfg<N, PE>::kRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
-                                        op.eloc_patch_stride, op.max_patch_nodes,
-                                        (int)op.max_carry);
+                                        op.eloc_patch_stride, op.max_patch_nodes);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2]: G
-  double *carry = reinterpret_cast<double *>(smem_raw + L.carry);
   double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
   double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
   double *As = reinterpret_cast<double *>(smem_raw + L.ua);
@@ -362,33 +359,45 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
 
   auto stage_ptr = [&](int s) { return smem_raw + L.stage0 + (size_t)s * L.stage_bytes; };
-  auto issue_tables = [&](int64_t patch, int s) {  // one thread
+  // Patch headers travel two patches ahead through a 2-entry ring: the header of patch
+  // i+1 names the (deduplicated) table blocks the copy for patch i+1 must fetch, so it
+  // has to be in shared memory when that copy is issued, during patch i.
+  uint32_t *hdr_ring = reinterpret_cast<uint32_t *>(smem_raw + L.hdr);
+  // one thread: tables of `patch` (blocks pi, ei) into stage s, plus -- if it exists --
+  // the header of the patch after it (`patch_after`) into ring entry `slot_after`
+  auto issue_tables = [&](uint32_t pi, uint32_t ei, int s, int64_t patch_after, int slot_after) {
     unsigned char *base = stage_ptr(s);
-    semk_mbar_expect_tx(&mbar[s], pn_bytes + el_bytes);
-    semk_bulk_g2s(base + L.pn_off, op.pnode + patch * op.pn_patch_stride, pn_bytes, &mbar[s]);
-    semk_bulk_g2s(base + L.el_off, op.eloc + patch * op.eloc_patch_stride, el_bytes, &mbar[s]);
+    const bool more = patch_after >= 0;
+    semk_mbar_expect_tx(&mbar[s], pn_bytes + el_bytes + (more ? 32u : 0u));
+    semk_bulk_g2s(base + L.pn_off, op.pnode + (int64_t)pi * op.pn_patch_stride, pn_bytes, &mbar[s]);
+    semk_bulk_g2s(base + L.el_off, op.eloc + (int64_t)ei * op.eloc_patch_stride, el_bytes, &mbar[s]);
+    if (more) semk_bulk_g2s(hdr_ring + 8 * slot_after, op.patch_hdr + 8 * patch_after, 32u, &mbar[s]);
   };
   auto issue_g = [&](int64_t patch) {  // one thread
     semk_mbar_expect_tx(&mbar[2], g_bytes);
     semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[2]);
   };
 
-  // this CTA's patch sequence: a contiguous range (plan built with ranges: nodes
-  // shared by consecutive patches are carried in shared memory) or round-robin
-  const int64_t step = op.patches_per_range > 0 ? 1 : (int64_t)gridDim.x;
-  const int64_t p_first =
-      op.patches_per_range > 0 ? (int64_t)blockIdx.x * op.patches_per_range : (int64_t)blockIdx.x;
-  int64_t p_end = op.n_patch;
-  if (op.patches_per_range > 0) {
-    const int64_t e = p_first + op.patches_per_range;
-    p_end = e < op.n_patch ? e : op.n_patch;
-  }
+  // this CTA's patch sequence: round-robin over the grid, so that at any time the
+  // resident CTAs work on a compact window of the mesh (DRAM page / L2 locality)
+  const int64_t step = (int64_t)gridDim.x;
+  const int64_t p_first = (int64_t)blockIdx.x;
+  const int64_t p_end = op.n_patch;
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) semk_mbar_init(&mbar[i], 1);
     semk_fence_mbar_init();
     if (p_first < p_end) {
-      issue_tables(p_first, 0);
+      // the first header is read directly (block indices needed right now) and also
+      // copied into ring entry 0; the second patch's header goes to entry 1
+      const uint32_t pi = op.patch_hdr[8 * p_first + 5], ei = op.patch_hdr[8 * p_first + 6];
+      const int64_t p2 = p_first + step;
+      unsigned char *base = stage_ptr(0);
+      semk_mbar_expect_tx(&mbar[0], pn_bytes + el_bytes + 32u + (p2 < p_end ? 32u : 0u));
+      semk_bulk_g2s(base + L.pn_off, op.pnode + (int64_t)pi * op.pn_patch_stride, pn_bytes, &mbar[0]);
+      semk_bulk_g2s(base + L.el_off, op.eloc + (int64_t)ei * op.eloc_patch_stride, el_bytes, &mbar[0]);
+      semk_bulk_g2s(hdr_ring, op.patch_hdr + 8 * p_first, 32u, &mbar[0]);
+      if (p2 < p_end) semk_bulk_g2s(hdr_ring + 8, op.patch_hdr + 8 * p2, 32u, &mbar[0]);
       if (MODE == MODE_APPLY) issue_g(p_first);
     }
   }
@@ -404,7 +413,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   uint32_t ucol_dir = 0;  // bit m set: entry m of the staged column is a Dirichlet node
   auto gather_column = [&](int s_tab, int64_t patch_of) {
     const unsigned char *sbn = stage_ptr(s_tab);
-    const uint32_t *pnb = reinterpret_cast<const uint32_t *>(sbn + L.pn_off) + 4;
+    const uint32_t *pnb = reinterpret_cast<const uint32_t *>(sbn + L.pn_off);
+    const uint32_t id0 = hdr_ring[8 * s_tab + 4];  // ring entry = iteration parity = stage
     const uint16_t *elb = reinterpret_cast<const uint16_t *>(sbn + L.el_off);
     const bool act = (le < PE) && (patch_of * PE + le < op.n_elem);
     if (act) {
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       ucol_dir = 0;
 #pragma unroll
       for (int m = 0; m < N; ++m) {
-        ucol[m] = u[pn[m] & SEMK_NODE_ID_MASK];
+        ucol[m] = u[id0 + (pn[m] & SEMK_NODE_ID_MASK)];
         ucol_dir |= (pn[m] >> 31) << m;
       }
     }
@@ -437,16 +447,14 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     const int64_t next = patch + step;
     const bool has_next = next < p_end;
     unsigned char *sb = stage_ptr(s);
-    const uint32_t *pn_blk = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
+    const uint32_t *pn_s = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
     const uint16_t *el_s = reinterpret_cast<const uint16_t *>(sb + L.el_off);
     semk_mbar_wait(&mbar[s], par);
-    const int npn = (int)pn_blk[0];
-    const int npriv = (int)pn_blk[1];
-    const int slot_base = (int)pn_blk[2];
-    const int ncin = (int)(pn_blk[3] & 0xffffu), ncout = (int)(pn_blk[3] >> 16);
-    const double *carry_in = carry + (size_t)((it & 1) ^ 1) * L.carry_len;  // from patch i-1
-    double *carry_out = carry + (size_t)(it & 1) * L.carry_len;            // for patch i+1
-    const uint32_t *pn_s = pn_blk + 4;
+    const uint32_t *hdr = hdr_ring + 8 * s;  // read before this patch's first barrier
+    const int npn = (int)hdr[0];
+    const int npriv = (int)hdr[1];
+    const int slot_base = (int)hdr[2];
+    const uint32_t id0 = hdr[4];
     const int64_t slot0 = patch * PE;
     const bool active = (le < PE) && (slot0 + le < op.n_elem);
 
@@ -476,7 +484,11 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       // Table stage s^1 (patch i-1's tables) is free once every thread has passed the
       // first barrier of this patch's operator: no end-of-patch barrier is needed.
       auto refill_tables = [&]() {
-        if (tid == 0 && has_next) issue_tables(next, s ^ 1);
+        if (tid == 0 && has_next) {
+          const uint32_t *hn = hdr_ring + 8 * (s ^ 1);  // header of the next patch
+          const int64_t after = next + step;
+          issue_tables(hn[5], hn[6], s ^ 1, after < p_end ? after : -1, s);
+        }
       };
       local_poisson<N, RS>(dm, le, t, active, ucol, ycol, As, Bs, Gs + tid, NP, &mbar[2],
                            (uint32_t)(it & 1), refill_g, refill_tables);
@@ -497,7 +509,11 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       }
     } else {
       __syncthreads();  // previous patch's write-out done: its table stage may be refilled
-      if (tid == 0 && has_next) issue_tables(next, s ^ 1);
+      if (tid == 0 && has_next) {
+        const uint32_t *hn = hdr_ring + 8 * (s ^ 1);
+        const int64_t after = next + step;
+        issue_tables(hn[5], hn[6], s ^ 1, after < p_end ? after : -1, s);
+      }
       if (active) {
         const double *lr = loc + (slot0 + le) * NN;
 #pragma unroll
@@ -534,8 +550,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
         const uint32_t pn = pnv[j];
         double v = vv[j];
         if (k < npriv) {
-          if (k < ncin) v += carry_in[k];  // partial sum of the previous patch
-          const uint32_t g = pn & SEMK_NODE_ID_MASK;
+          const uint32_t g = id0 + (pn & SEMK_NODE_ID_MASK);
           if ((pn & SEMK_NODE_DIRICHLET) && (flags & SEMK_MASK_OUT)) {
             if (MODE == MODE_APPLY) {
               v = 0.0;
@@ -548,10 +563,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
             }
           }
           y[g] = v;
-        } else if (k < npriv + ncout) {
-          carry_out[k - npriv] = v;  // completed by the next patch of this CTA
         } else {
-          op.slot_buf[slot_base + (k - npriv - ncout)] = v;
+          op.slot_buf[slot_base + (k - npriv)] = v;
         }
       }
     }
@@ -809,8 +822,7 @@ struct PatchLaunch {
                  double *y, int flags, double fill, double *partials, cudaStream_t st,
                  int *grid_out) {
     const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
-                                          op.eloc_patch_stride, op.max_patch_nodes,
-                                          (int)op.max_carry)
+                                          op.eloc_patch_stride, op.max_patch_nodes)
                             .total;
     if (smem > 227 * 1024) {
       semk_set_error("patch kernel: shared memory request exceeds 227 KB");
@@ -823,14 +835,9 @@ struct PatchLaunch {
       semk_set_error("patch kernel: does not fit on an SM");
       return SEMK_ERR_UNSUPPORTED;
     }
-    // persistent grid: every CTA stays resident and loops over its patches -- the
-    // contiguous ranges the plan was built for, or round-robin over the resident CTAs
+    // persistent grid: every CTA stays resident and loops over its patches, round-robin
     const int64_t resident = (int64_t)per_sm * sms;
-    unsigned grid;
-    if (op.patches_per_range > 0)
-      grid = (unsigned)((op.n_patch + op.patches_per_range - 1) / op.patches_per_range);
-    else
-      grid = (unsigned)(op.n_patch < resident ? op.n_patch : resident);
+    const unsigned grid = (unsigned)(op.n_patch < resident ? op.n_patch : resident);
     patch_kernel<N, PE, MODE><<<grid, PatchCfg<N, PE>::kThreads, smem, st>>>(
         op, dm, u, loc, y, flags, fill, partials);
     SEMK_LAUNCH_CHECK("patch_kernel");
@@ -879,8 +886,9 @@ int check_op(const semk_op *op, const char *who) {
     return SEMK_ERR_UNSUPPORTED;
   }
   const int64_t nnp = (int64_t)op->n1 * op->n1 * op->elems_per_patch;
-  if (!op->pnode || !op->eloc || (op->pn_patch_stride & 3) != 0 ||
-      op->pn_patch_stride < 4 + op->max_patch_nodes ||
+  if (!op->pnode || !op->eloc || !op->patch_hdr || (op->pn_patch_stride & 3) != 0 ||
+      op->pn_patch_stride < op->max_patch_nodes ||
+      (reinterpret_cast<uintptr_t>(op->patch_hdr) & 15u) != 0 ||
       (op->eloc_patch_stride & 7) != 0 ||
       op->eloc_patch_stride < nnp + op->elems_per_patch ||
       (op->n_slots > 0 && !op->slot_buf) ||
@@ -906,11 +914,10 @@ extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
 
 extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
                                       int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                                      int max_patch_nodes, int max_carry) {
+                                      int max_patch_nodes) {
   if (!pe_supported(elems_per_patch)) return -1;
   const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                        pn_patch_stride, eloc_patch_stride, max_patch_nodes,
-                                        max_carry)
+                                        pn_patch_stride, eloc_patch_stride, max_patch_nodes)
                           .total;
   if (smem > 227 * 1024) return -1;
   int per_sm = 0, sms = 0;
@@ -936,10 +943,9 @@ extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_pat
 
 extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                                          int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                                         int max_patch_nodes, int max_carry) {
+                                         int max_patch_nodes) {
   return (int64_t)patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                    pn_patch_stride, eloc_patch_stride, max_patch_nodes,
-                                    max_carry)
+                                    pn_patch_stride, eloc_patch_stride, max_patch_nodes)
       .total;
 }
 

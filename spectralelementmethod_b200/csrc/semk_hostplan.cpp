@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/semk.h"
@@ -30,8 +31,8 @@ struct semk_hostplan {
   int64_t n_elem = 0, n_nodes = 0;
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
-      shared_slot, patch_ncin, patch_ncout;
-  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk;
+      shared_slot;
+  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk, patch_hdr;
   std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
@@ -40,8 +41,7 @@ struct semk_hostplan {
 
 extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
                                     const int64_t *elem_order, int elems_per_patch,
-                                    const uint8_t *dirichlet, int64_t n_ranges,
-                                    semk_hostplan **out) {
+                                    const uint8_t *dirichlet, semk_hostplan **out) {
   if (!out) return SEMK_ERR_INVALID;
   *out = nullptr;
   if (n1 < 2 || n1 > SEMK_MAX_N1) {
@@ -97,41 +97,22 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       }
     }
 
-    // The persistent kernel gives CTA r the contiguous patch range [r*C, (r+1)*C).
-    // A node touched by exactly two patches q, q+1 of one range is CARRIED: the CTA
-    // keeps q's partial sum in shared memory and adds it when it assembles q+1 (which
-    // then owns the node), instead of going through an interface slot.
-    const int64_t C = (n_ranges > 0) ? (n_patch + n_ranges - 1) / n_ranges : 0;
-    P->scalars[SEMK_PS_PATCHES_PER_RANGE] = C;
-
     // pass 1: which nodes are touched by more than one patch
-    //   multi = 0 private, 1 shared (interface slots), 2 carried from first to first+1
-    std::vector<int32_t> first_patch(n_nodes, -1), second_patch(n_nodes, -1);
-    std::vector<uint8_t> multi(n_nodes, 0);
+    std::vector<int32_t> first_patch(n_nodes, -1);
+    std::vector<uint8_t> multi(n_nodes, 0);  // 0 private, 1 shared (interface slots)
     for (int64_t p = 0; p < n_patch; ++p) {
       const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         for (int k = 0; k < NN; ++k) {
           const uint32_t g = row[k];
-          if (first_patch[g] < 0) {
+          if (first_patch[g] < 0)
             first_patch[g] = (int32_t)p;
-          } else if (first_patch[g] != (int32_t)p) {
-            if (second_patch[g] < 0) {
-              second_patch[g] = (int32_t)p;
-              multi[g] = 2;  // provisional: exactly two patches so far
-            } else if (second_patch[g] != (int32_t)p) {
-              multi[g] = 1;  // three or more
-            }
-          }
+          else if (first_patch[g] != (int32_t)p)
+            multi[g] = 1;
         }
       }
     }
-    for (int64_t g = 0; g < n_nodes; ++g)
-      if (multi[g] == 2) {
-        const int64_t a = first_patch[g], b = second_patch[g];
-        if (!(C > 0 && b == a + 1 && a / C == b / C)) multi[g] = 1;
-      }
 
     // shared node list (ascending id) and slot counts
     std::vector<int32_t> shared_index(n_nodes, -1);
@@ -148,15 +129,12 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     // pass 2: per-patch tables
     P->patch_node_ptr.assign(n_patch + 1, 0);
     P->patch_npriv.assign(n_patch, 0);
-    P->patch_ncin.assign(n_patch, 0);
-    P->patch_ncout.assign(n_patch, 0);
     P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
     P->eloc.assign((size_t)n_patch * ES, 0);
     P->elem_color.assign(n_slot_elems, 0);
     std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
-    std::vector<uint32_t> priv, shar, cin, cout_, colmask;
-    int64_t max_carry = 0;
+    std::vector<uint32_t> priv, shar, colmask;
     std::vector<std::pair<int32_t, int32_t>> slot_pairs;  // (shared index, slot)
     int64_t max_patch_nodes = 0, n_slots = 0;
     int max_colors = 1;
@@ -164,8 +142,6 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
       priv.clear();
       shar.clear();
-      cin.clear();
-      cout_.clear();
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         for (int k = 0; k < NN; ++k) {
@@ -174,45 +150,28 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
             local_of[g] = -2;  // mark as collected
             if (multi[g] == 0)
               priv.push_back(g);
-            else if (multi[g] == 1)
-              shar.push_back(g);
-            else if (first_patch[g] == (int32_t)p)
-              cout_.push_back(g);
             else
-              cin.push_back(g);
+              shar.push_back(g);
           }
         }
       }
       std::sort(priv.begin(), priv.end());
       std::sort(shar.begin(), shar.end());
-      std::sort(cin.begin(), cin.end());
-      std::sort(cout_.begin(), cout_.end());
-      // node list order: [carry-in | private | carry-out | shared]; the patch writes the
-      // first ncin + nprivate entries to the result vector
-      const int32_t nci = (int32_t)cin.size(), nco = (int32_t)cout_.size();
-      const int32_t np = (int32_t)priv.size() + nci, ns = (int32_t)shar.size();
+      // node list order: [private | shared]; the patch writes the private entries to the
+      // result vector itself
+      const int32_t np = (int32_t)priv.size(), ns = (int32_t)shar.size();
       P->patch_npriv[p] = np;
-      P->patch_ncin[p] = nci;
-      P->patch_ncout[p] = nco;
-      max_carry = std::max<int64_t>(max_carry, std::max(nci, nco));
       P->patch_slot_base[p] = (int32_t)n_slots;
       for (int32_t k = 0; k < np; ++k) {
-        const uint32_t g = (k < nci) ? cin[k] : priv[k - nci];
+        const uint32_t g = priv[k];
         local_of[g] = k;
-        uint32_t v = g;
-        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
-        P->pnode.push_back(v);
-      }
-      for (int32_t k = 0; k < nco; ++k) {
-        const uint32_t g = cout_[k];
-        local_of[g] = np + k;
         uint32_t v = g;
         if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
         P->pnode.push_back(v);
       }
       for (int32_t k = 0; k < ns; ++k) {
         const uint32_t g = shar[k];
-        local_of[g] = np + nco + k;
+        local_of[g] = np + k;
         uint32_t v = g | SEMK_NODE_SHARED;
         if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
         P->pnode.push_back(v);
@@ -228,11 +187,11 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       // pad to a multiple of 4 entries: every patch's list starts 16-byte aligned (TMA)
       while (P->pnode.size() & 3u) P->pnode.push_back(0xffffffffu);
       P->patch_node_ptr[p + 1] = (int32_t)P->pnode.size();
-      P->patch_nnodes[p] = np + nco + ns;
-      max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + nco + ns);
+      P->patch_nnodes[p] = np + ns;
+      max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
 
       // element-local index table + greedy colouring
-      colmask.assign(np + nco + ns, 0u);
+      colmask.assign(np + ns, 0u);
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
@@ -260,8 +219,6 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       // reset scratch
       for (uint32_t g : priv) local_of[g] = -1;
       for (uint32_t g : shar) local_of[g] = -1;
-      for (uint32_t g : cin) local_of[g] = -1;
-      for (uint32_t g : cout_) local_of[g] = -1;
     }
     if ((int64_t)P->pnode.size() > INT32_MAX) {
       delete P;
@@ -294,7 +251,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       std::vector<int32_t> patch_of_slot(n_slots);
       for (int64_t p = 0; p < n_patch; ++p) {
         const int32_t s0 = P->patch_slot_base[p];
-        const int32_t s1 = s0 + (P->patch_nnodes[p] - P->patch_npriv[p] - P->patch_ncout[p]);
+        const int32_t s1 = s0 + (P->patch_nnodes[p] - P->patch_npriv[p]);
         for (int32_t sidx = s0; sidx < s1; ++sidx) patch_of_slot[sidx] = (int32_t)p;
       }
       struct Pair {
@@ -388,28 +345,68 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     }
 
     // Uniform-stride device blocks, one TMA bulk copy each per patch:
-    //   node block  = {n nodes, n private, first slot, 0} + node list, 0xffffffff padded
-    //   index block = [m][le][t] patch-local indices + PE element colours (uint16)
-    const int64_t pn_stride = 4 + ((max_patch_nodes + 3) & ~(int64_t)3);
+    //   node block  = the patch's node list RELATIVE to its smallest node id (flags in
+    //                 the top bits as in PNODE), 0xffffffff padded;
+    //   index block = [m][le][t] patch-local indices + PE element colours (uint16).
+    // Identical blocks are stored once (DEDUPLICATED): on a regularly numbered mesh every
+    // interior patch has the same relative node list and the same index table, so the
+    // kernel's table reads become L2 hits instead of DRAM traffic.  The per-patch part
+    // is an 8-word header
+    //   {n nodes, n private, first slot, 0, base node id, node block index, index block
+    //    index, 0}.
+    const int64_t pn_stride = (max_patch_nodes + 3) & ~(int64_t)3;
     const int64_t el_stride = ((int64_t)NN * PE + PE + 7) & ~(int64_t)7;
-    P->pnblk.assign((size_t)n_patch * pn_stride, 0xffffffffu);
-    P->elblk.assign((size_t)n_patch * el_stride, 0);
-    for (int64_t p = 0; p < n_patch; ++p) {
-      uint32_t *blk = P->pnblk.data() + (size_t)p * pn_stride;
-      const int32_t nn = P->patch_nnodes[p];
-      blk[0] = (uint32_t)nn;
-      blk[1] = (uint32_t)P->patch_npriv[p];
-      blk[2] = (uint32_t)P->patch_slot_base[p];
-      blk[3] = (uint32_t)P->patch_ncin[p] | ((uint32_t)P->patch_ncout[p] << 16);
-      std::copy(P->pnode.begin() + P->patch_node_ptr[p], P->pnode.begin() + P->patch_node_ptr[p] + nn,
-                blk + 4);
-      uint16_t *eb = P->elblk.data() + (size_t)p * el_stride;
-      std::copy(P->eloc.begin() + (size_t)p * ES, P->eloc.begin() + (size_t)p * ES + (size_t)NN * PE,
-                eb);
-      for (int le = 0; le < PE; ++le) eb[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
+    P->patch_hdr.assign((size_t)n_patch * 8, 0u);
+    {
+      auto hash_bytes = [](const void *ptr, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(ptr);
+        uint64_t h = 1469598103934665603ull;  // FNV-1a
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+        return h;
+      };
+      std::unordered_multimap<uint64_t, int32_t> pn_seen, el_seen;
+      std::vector<uint32_t> pblk(pn_stride);
+      std::vector<uint16_t> eblk(el_stride);
+      for (int64_t p = 0; p < n_patch; ++p) {
+        const int32_t nn = P->patch_nnodes[p];
+        const uint32_t *src = P->pnode.data() + P->patch_node_ptr[p];
+        uint32_t base = SEMK_NODE_ID_MASK;
+        for (int32_t k = 0; k < nn; ++k) base = std::min(base, src[k] & SEMK_NODE_ID_MASK);
+        if (nn == 0) base = 0;
+        std::fill(pblk.begin(), pblk.end(), 0xffffffffu);
+        for (int32_t k = 0; k < nn; ++k)
+          pblk[k] = ((src[k] & SEMK_NODE_ID_MASK) - base) | (src[k] & ~SEMK_NODE_ID_MASK);
+        std::fill(eblk.begin(), eblk.end(), (uint16_t)0);
+        std::copy(P->eloc.begin() + (size_t)p * ES, P->eloc.begin() + (size_t)p * ES + (size_t)NN * PE,
+                  eblk.begin());
+        for (int le = 0; le < PE; ++le) eblk[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
+
+        auto find_or_add = [&](auto &seen, auto &pool, const auto &blk, int64_t stride) {
+          const size_t bytes = (size_t)stride * sizeof(blk[0]);
+          const uint64_t h = hash_bytes(blk.data(), bytes);
+          auto range = seen.equal_range(h);
+          for (auto it = range.first; it != range.second; ++it)
+            if (std::memcmp(pool.data() + (size_t)it->second * stride, blk.data(), bytes) == 0)
+              return it->second;
+          const int32_t idx = (int32_t)(pool.size() / (size_t)stride);
+          pool.insert(pool.end(), blk.begin(), blk.end());
+          seen.emplace(h, idx);
+          return idx;
+        };
+        const int32_t pi = find_or_add(pn_seen, P->pnblk, pblk, pn_stride);
+        const int32_t ei = find_or_add(el_seen, P->elblk, eblk, el_stride);
+        uint32_t *h = P->patch_hdr.data() + (size_t)p * 8;
+        h[0] = (uint32_t)nn;
+        h[1] = (uint32_t)P->patch_npriv[p];
+        h[2] = (uint32_t)P->patch_slot_base[p];
+        h[4] = base;
+        h[5] = (uint32_t)pi;
+        h[6] = (uint32_t)ei;
+      }
     }
+    P->scalars[SEMK_PS_N_PN_UNIQUE] = (int64_t)(P->pnblk.size() / (size_t)pn_stride);
+    P->scalars[SEMK_PS_N_EL_UNIQUE] = (int64_t)(P->elblk.size() / (size_t)el_stride);
     P->scalars[SEMK_PS_PN_STRIDE] = pn_stride;
-    P->scalars[SEMK_PS_MAX_CARRY] = max_carry;
     {
       // counts of the interface tables (the vectors hold one dummy entry when empty)
       int64_t n_chunk = 0, n_rec = 0;
@@ -471,8 +468,7 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_SHARED_REC: return vec_ptr(plan->shared_rec, n_bytes);
     case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
     case SEMK_PA_SHARED_CHUNK: return vec_ptr(plan->shared_chunk, n_bytes);
-    case SEMK_PA_PATCH_NCIN: return vec_ptr(plan->patch_ncin, n_bytes);
-    case SEMK_PA_PATCH_NCOUT: return vec_ptr(plan->patch_ncout, n_bytes);
+    case SEMK_PA_PATCH_HDR: return vec_ptr(plan->patch_hdr, n_bytes);
     default: return nullptr;
   }
 }

@@ -44,20 +44,18 @@ def eloc_patch_stride_of(n1, pe):
 
 
 def pn_patch_stride_of(max_patch_nodes):
-    return 4 + ((int(max_patch_nodes) + 3) & ~3)   # header + node list
+    return (int(max_patch_nodes) + 3) & ~3   # node list, 16-byte multiples
 
 
-def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None, max_carry=None):
+def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None):
     """Dynamic shared memory of one CTA of the apply kernel (asks the library,
     which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
     if pn_stride is None:
         pn_stride = pn_patch_stride_of(max_patch_nodes)
-    if max_carry is None:
-        max_carry = _TILES[pe][1] * (n1 - 1) + 1
     return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_patch_stride_of(n1, pe),
                                                  int(pn_stride),
                                                  eloc_patch_stride_of(n1, pe),
-                                                 int(max_patch_nodes), int(max_carry)))
+                                                 int(max_patch_nodes)))
 
 
 def choose_elems_per_patch(n1):
@@ -95,7 +93,7 @@ def _morton_order(cx, cy):
     return np.argsort(key, kind="stable").astype(np.int64)
 
 
-def default_element_order(mesh, elems_per_patch, tile=None, columns_first=False):
+def default_element_order(mesh, elems_per_patch, tile=None):
     """Engine slot order (slot -> element) that makes consecutive runs of
     ``elems_per_patch`` elements compact patches: tiles of a structured grid
     when the mesh builder recorded one, else a Morton curve through the cell
@@ -107,16 +105,9 @@ def default_element_order(mesh, elems_per_patch, tile=None, columns_first=False)
         if bx * by != elems_per_patch:
             raise ValueError("tile shape does not match elems_per_patch")
         ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
-        if columns_first:
-            # tiles enumerated down a tile column (tx fastest): consecutive patches share
-            # a whole edge of contiguously numbered nodes, which the persistent kernel can
-            # carry from one patch to the next in shared memory (carry=True)
-            ntx = (nx + bx - 1) // bx
-            tile_id = (ey // by) * ntx + ex // bx
-        else:
-            # tiles enumerated along the contiguous node direction: the resident CTAs work
-            # on a compact window of the mesh at any time (best DRAM / L2 locality)
-            tile_id = (ex // bx) * ((ny + by - 1) // by) + ey // by
+        # tiles enumerated along the contiguous node direction: the resident CTAs work
+        # on a compact window of the mesh at any time (best DRAM / L2 locality)
+        tile_id = (ex // bx) * ((ny + by - 1) // by) + ey // by
         key = tile_id * (bx * by) + (ex % bx) * by + ey % by
         return np.argsort(key, kind="stable").astype(np.int64)
     if not hasattr(mesh, "_centroids"):
@@ -141,7 +132,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, tile=None, carry=False):
+                 elem_order=None, keep_l2g=True, tile=None):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -163,40 +154,23 @@ class PoissonOperator(object):
 
         pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
         if elem_order is None:
-            elem_order = default_element_order(mesh, pe, tile, columns_first=carry)
-        # The persistent apply kernel runs one CTA per resident slot and gives each a
-        # contiguous range of patches; the plan needs that number to decide which
-        # interface nodes are carried inside a CTA.  Estimate it from the expected patch
-        # footprint, build, and rebuild if the real footprint allows fewer CTAs.
-        est_nodes = min(pe * NN, (_TILES[pe][0] * (n1 - 1) + 1) * (_TILES[pe][1] * (n1 - 1) + 1)
-                        if tile is None else (tile[0] * (n1 - 1) + 1) * (tile[1] * (n1 - 1) + 1))
-        est_carry = (tile[1] if tile is not None else _TILES[pe][1]) * (n1 - 1) + 1
-
-        def resident_for(max_nodes, pn_stride, el_stride, max_carry):
-            r = int(self._lib.semk_resident_ctas(n1, pe, g_patch_stride_of(n1, pe), int(pn_stride),
-                                                 int(el_stride), int(max_nodes), int(max_carry)))
-            if r <= 0:
-                raise NotImplementedError(
-                    "patch of %d elements does not fit in shared memory (%s); pass a smaller "
-                    "elems_per_patch or a more local elem_order" % (pe, _lib.last_error()))
-            return r
-        n_ranges = resident_for(est_nodes, pn_patch_stride_of(est_nodes),
-                                eloc_patch_stride_of(n1, pe), est_carry) if carry else 0
-        for _attempt in range(3):
-            sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet, n_ranges)
-            actual = resident_for(sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE],
-                                  sc[_lib.PS_EL_STRIDE], sc[_lib.PS_MAX_CARRY])
-            if not carry or actual >= min(n_ranges, sc[_lib.PS_N_PATCH]):
-                break
-            n_ranges = actual
+            elem_order = default_element_order(mesh, pe, tile)
+        sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
+        actual = int(self._lib.semk_resident_ctas(
+            n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
+            int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_MAX_PATCH_NODES])))
+        if actual <= 0:
+            raise NotImplementedError(
+                "patch of %d elements does not fit in shared memory (%s); pass a smaller "
+                "elems_per_patch or a more local elem_order" % (pe, _lib.last_error()))
         self.plan_scalars = sc
         self.resident_ctas = actual
-        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE],
-                                sc[_lib.PS_MAX_CARRY])
+        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE])
         self.smem_bytes = smem
 
         t = {}
-        for k in (_lib.PA_PNBLK, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT, _lib.PA_SHARED_CHUNK):
+        for k in (_lib.PA_PNBLK, _lib.PA_PATCH_HDR, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT,
+                  _lib.PA_SHARED_CHUNK):
             t[k] = device.as_i32_bits(ar[k], self.dev)
         t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
@@ -248,12 +222,11 @@ class PoissonOperator(object):
         op.max_colors = sc[_lib.PS_MAX_COLORS]
         op.g_patch_stride = self.g_patch_stride
         op.G = self.G.data_ptr()
+        op.patch_hdr = t[_lib.PA_PATCH_HDR].data_ptr()
         op.pnode = t[_lib.PA_PNBLK].data_ptr()
         op.pn_patch_stride = sc[_lib.PS_PN_STRIDE]
         op.eloc = t[_lib.PA_ELBLK].data_ptr()
         op.eloc_patch_stride = sc[_lib.PS_EL_STRIDE]
-        op.patches_per_range = sc[_lib.PS_PATCHES_PER_RANGE]
-        op.max_carry = sc[_lib.PS_MAX_CARRY]
         op.n_slots = self.n_slots
         op.slot_buf = self.slot_buf.data_ptr()
         op.n_shared = sc[_lib.PS_N_SHARED_REC]

@@ -34,7 +34,7 @@ def test_version_and_error_channel():
     lib = _lib.load()
     assert lib.semk_version() == 100
     out = ctypes.c_void_p()
-    rc = lib.semk_hostplan_create(1, 1, 1, None, None, 16, None, 0, ctypes.byref(out))
+    rc = lib.semk_hostplan_create(1, 1, 1, None, None, 16, None, ctypes.byref(out))
     assert rc == _lib.ERR_UNSUPPORTED and b"n1" in lib.semk_last_error()
     with pytest.raises(NotImplementedError):
         _lib.check(rc)
@@ -60,11 +60,11 @@ def test_struct_layout_matches_header(tmp_path):
         assert getattr(_lib.semk_op, f).offset == int(off), f
 
 
-def _plan(nx, ny, p, pe, order=None, dirichlet=None, n_ranges=0):
+def _plan(nx, ny, p, pe, order=None, dirichlet=None):
     N = p + 1
     l2g = meshgen.structured_node_maps(nx, ny, p)
     n_nodes = (nx * p + 1) * (ny * p + 1)
-    sc, ar = _lib.hostplan(N, l2g, n_nodes, order, pe, dirichlet, n_ranges)
+    sc, ar = _lib.hostplan(N, l2g, n_nodes, order, pe, dirichlet)
     return l2g.reshape(-1, N * N), n_nodes, sc, ar
 
 
@@ -87,8 +87,6 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     assert np.all(ptr % 4 == 0)
     color = ar[_lib.PA_ELEM_COLOR]
     eos = ar[_lib.PA_ELEM_OF_SLOT]
-    ncin, ncout = ar[_lib.PA_PATCH_NCIN], ar[_lib.PA_PATCH_NCOUT]
-    C = sc[_lib.PS_PATCHES_PER_RANGE]
     assert sorted(eos.tolist()) == list(range(E))
     pad = pnode == 0xFFFFFFFF
     ids = pnode & _lib.NODE_ID_MASK
@@ -101,29 +99,20 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     touched = np.zeros(n_nodes, dtype=int)
     written = np.zeros(n_nodes, dtype=int)      # how many patches write the node to y
     slots_seen = 0
-    carried = {}
     for p in range(n_patch):
         a, b = ptr[p], ptr[p] + nnodes[p]
         assert np.all(pnode[b:ptr[p + 1]] == 0xFFFFFFFF) and ptr[p + 1] - b < 4
         loc_ids = ids[a:b]
         assert len(set(loc_ids.tolist())) == b - a
-        # classes: [carried-in | private | carried-out | shared], each ascending
-        c0, c1, c2 = ncin[p], npriv[p], npriv[p] + ncout[p]
-        assert 0 <= c0 <= c1 <= c2 <= b - a
-        assert not shared_flag[a:a + c2].any() and shared_flag[a + c2:b].all()
-        for lo, hi in ((0, c0), (c0, c1), (c1, c2), (c2, b - a)):
+        # classes: [private | shared], each ascending
+        c1 = npriv[p]
+        assert 0 <= c1 <= b - a
+        assert not shared_flag[a:a + c1].any() and shared_flag[a + c1:b].all()
+        for lo, hi in ((0, c1), (c1, b - a)):
             assert np.all(np.diff(loc_ids[lo:hi]) > 0)
-        # carried-out nodes of p are exactly the carried-in nodes of p+1 (same range)
-        if ncout[p]:
-            assert C > 0 and (p + 1) // C == p // C
-            assert np.array_equal(loc_ids[c1:c2], ids[ptr[p + 1]:ptr[p + 1] + ncin[p + 1]])
-        if ncin[p]:
-            assert C > 0 and (p - 1) // C == p // C and ncout[p - 1] == ncin[p]
-        for g in loc_ids[c1:c2].tolist():
-            carried[g] = p
         written[loc_ids[:c1]] += 1
         assert base[p] == slots_seen
-        slots_seen += (b - a) - c2
+        slots_seen += (b - a) - c1
         touched[loc_ids] += 1
         s0, s1 = p * pe, min((p + 1) * pe, E)
         # eloc reproduces the L2G rows of the patch's elements
@@ -141,32 +130,36 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     is_shared_node = np.zeros(n_nodes, dtype=bool)
     is_shared_node[ids[shared_flag]] = True
     assert sc[_lib.PS_N_PNODE] == pnode.size
-    # uniform-stride device blocks mirror the compact tables
+    # uniform-stride device blocks mirror the compact tables; identical blocks are stored
+    # once and the per-patch header says which ones a patch uses
     PS, ELS = sc[_lib.PS_PN_STRIDE], sc[_lib.PS_EL_STRIDE]
-    assert PS % 4 == 0 and PS >= 4 + sc[_lib.PS_MAX_PATCH_NODES] and ELS % 8 == 0
-    pnblk = ar[_lib.PA_PNBLK].reshape(n_patch, PS)
-    elblk = ar[_lib.PA_ELBLK].reshape(n_patch, ELS)
+    assert PS % 4 == 0 and PS >= sc[_lib.PS_MAX_PATCH_NODES] and ELS % 8 == 0
+    npu, neu = sc[_lib.PS_N_PN_UNIQUE], sc[_lib.PS_N_EL_UNIQUE]
+    pnblk = ar[_lib.PA_PNBLK].reshape(npu, PS)
+    elblk = ar[_lib.PA_ELBLK].reshape(neu, ELS)
+    hdr = ar[_lib.PA_PATCH_HDR].reshape(n_patch, 8)
+    assert len(set(map(bytes, pnblk))) == npu and len(set(map(bytes, elblk))) == neu
     for p in range(n_patch):
-        assert pnblk[p, 0] == nnodes[p] and pnblk[p, 1] == npriv[p] and pnblk[p, 2] == base[p]
-        assert pnblk[p, 3] == ncin[p] | (ncout[p] << 16)
-        assert np.array_equal(pnblk[p, 4:4 + nnodes[p]], pnode[ptr[p]:ptr[p] + nnodes[p]])
-        assert np.all(pnblk[p, 4 + nnodes[p]:] == 0xFFFFFFFF)
-        assert np.array_equal(elblk[p, :NN * pe], ar[_lib.PA_ELOC].reshape(-1, ES)[p, :NN * pe])
-        assert np.array_equal(elblk[p, NN * pe:NN * pe + pe], color[p * pe:(p + 1) * pe])
-    # every touched node is written by exactly one patch or is a shared (slot) node;
-    # carried nodes are touched by exactly the two consecutive patches
+        h = hdr[p]
+        assert h[0] == nnodes[p] and h[1] == npriv[p] and h[2] == base[p]
+        assert h[3] == 0 and h[7] == 0
+        assert h[5] < npu and h[6] < neu
+        full = pnode[ptr[p]:ptr[p] + nnodes[p]]
+        assert h[4] == (full & _lib.NODE_ID_MASK).min()
+        blk = pnblk[h[5]]
+        rel = (full & _lib.NODE_ID_MASK) - h[4]
+        assert np.array_equal(blk[:nnodes[p]], rel | (full & ~np.uint32(_lib.NODE_ID_MASK)))
+        assert np.all(blk[nnodes[p]:] == 0xFFFFFFFF)
+        eb = elblk[h[6]]
+        assert np.array_equal(eb[:NN * pe], ar[_lib.PA_ELOC].reshape(-1, ES)[p, :NN * pe])
+        assert np.array_equal(eb[NN * pe:NN * pe + pe], color[p * pe:(p + 1) * pe])
+    # every touched node is written by exactly one patch or is a shared (slot) node
     is_shared_node = np.zeros(n_nodes, dtype=bool)
     is_shared_node[ids[shared_flag]] = True
     assert sc[_lib.PS_N_PNODE] == pnode.size
     assert np.array_equal(written == 1, (touched >= 1) & ~is_shared_node)
     assert not (written > 1).any()
-    is_carried = np.zeros(n_nodes, dtype=bool)
-    is_carried[list(carried)] = True
-    assert np.all(touched[is_carried] == 2) and not (is_carried & is_shared_node).any()
-    assert np.array_equal(is_shared_node | is_carried, touched > 1)
-    assert sc[_lib.PS_MAX_CARRY] == max(ncin.max(), ncout.max())
-    if C == 0:
-        assert not is_carried.any()
+    assert np.array_equal(is_shared_node, touched > 1)
     # CSR of interface slots: every slot exactly once, grouped under its node
     sn = ar[_lib.PA_SHARED_NODE]
     sp = ar[_lib.PA_SHARED_PTR]
@@ -203,26 +196,33 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         assert lst == sorted(lst) and len(lst) >= 2
 
 
-@pytest.mark.parametrize("n_ranges", [0, 3])
 @pytest.mark.parametrize("nx,ny,p,pe", [(8, 8, 8, 16), (5, 3, 4, 16), (7, 5, 2, 8), (3, 3, 10, 4),
                                         (1, 1, 3, 16), (6, 6, 1, 4)])
-def test_hostplan_structured(nx, ny, p, pe, n_ranges):
+def test_hostplan_structured(nx, ny, p, pe):
     from spectralelementmethod_b200.discrete import Mesh
     mesh = meshgen.structured_quad_mesh(nx, ny, p)
     order = operators.default_element_order(mesh, pe)
     rng = np.random.default_rng(0)
     n_nodes = (nx * p + 1) * (ny * p + 1)
     dirichlet = (rng.uniform(size=n_nodes) < 0.2).astype(np.uint8)
-    l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, dirichlet, n_ranges)
+    l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, dirichlet)
     check_plan(l2g, n_nodes, sc, ar, pe, dirichlet)
     if (nx, ny, p, pe) == (8, 8, 8, 16):          # 2x8 tiles: a 4x1 arrangement of patches
         assert sc[_lib.PS_N_PATCH] == 4 and sc[_lib.PS_MAX_COLORS] == 4
         assert sc[_lib.PS_MAX_PATCH_NODES] == 17 * 65
-        if n_ranges == 0:
-            assert sc[_lib.PS_N_SHARED] == 3 * 65 and sc[_lib.PS_MAX_CARRY] == 0
-        else:       # ranges of 2 patches: two of the three interfaces are carried
-            assert sc[_lib.PS_PATCHES_PER_RANGE] == 2
-            assert sc[_lib.PS_N_SHARED] == 65 and sc[_lib.PS_MAX_CARRY] == 65
+        assert sc[_lib.PS_N_SHARED] == 3 * 65
+
+
+def test_hostplan_deduplicates_table_blocks():
+    """Regular numbering: interior / edge / corner patches share their relative node list
+    and index table, so the device pools hold 9 blocks however large the mesh."""
+    nx, ny, p, pe = 12, 40, 4, 16
+    mesh = meshgen.structured_quad_mesh(nx, ny, p)
+    order = operators.default_element_order(mesh, pe)
+    l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, None)
+    assert sc[_lib.PS_N_PATCH] == 30
+    assert sc[_lib.PS_N_PN_UNIQUE] == 9 and sc[_lib.PS_N_EL_UNIQUE] <= 9
+    check_plan(l2g, n_nodes, sc, ar, pe)
 
 
 def test_hostplan_scrambled_numbering_and_order():
@@ -234,10 +234,9 @@ def test_hostplan_scrambled_numbering_and_order():
     perm = rng.permutation(n_nodes).astype(np.uint32)
     l2g = perm[l2g]
     order = rng.permutation(nx * ny)
-    for n_ranges in (0, 2):
-        sc, ar = _lib.hostplan(p + 1, l2g, n_nodes, order, pe, None, n_ranges)
-        check_plan(l2g.reshape(nx * ny, -1), n_nodes, sc, ar, pe)
-        assert np.array_equal(ar[_lib.PA_ELEM_OF_SLOT], order)
+    sc, ar = _lib.hostplan(p + 1, l2g, n_nodes, order, pe, None)
+    check_plan(l2g.reshape(nx * ny, -1), n_nodes, sc, ar, pe)
+    assert np.array_equal(ar[_lib.PA_ELEM_OF_SLOT], order)
 
 
 def test_hostplan_rejects_bad_input():
