@@ -291,8 +291,18 @@ def run_engine(args):
     peak, peak_kind = measured_peaks()
     alg_bytes = op.algorithmic_bytes_per_apply
     achieved = alg_bytes / t_kernel / 1e9
+    # measured DRAM bytes of one apply: from the committed ncu capture of this very
+    # configuration (profiles/r01_traffic.json); null for any other workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if (not multi and op.n_elem == 1024 * 1024 and op.elems_per_patch == 16 and not args.tile
+            and args.kind == "S" and os.path.exists(tpath)):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_apply"], tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_kind,
                 "kernel": "patch_kernel<9,16,APPLY> + shared_nodes_kernel (one apply)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "ms_per_launch": t_kernel * 1e3}
@@ -330,27 +340,34 @@ def run_engine(args):
     if args.pcg_iters > 0 or args.pcg_full:
         maxiter = 200000 if args.pcg_full else args.pcg_iters
         if dp is None:
-            gl = None
-            b = op.lift(op.rhs(1.0), gl)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            xs, info = op.solve_pcg(b, rtol=1e-12, maxiter=maxiter, check_every=50)
-            torch.cuda.synchronize()
-            el = time.perf_counter() - t0
-            pcg = {"iterations": info.iterations, "seconds": el, "converged": info.converged,
-                   "rel_residual": info.rel_residual,
-                   "ms_per_iteration": el / max(info.iterations, 1) * 1e3}
+            b = op.lift(op.rhs(1.0), None)
+
+            def run(iters):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                xs, info = op.solve_pcg(b, rtol=1e-12, maxiter=iters, check_every=50)
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0, info.iterations, info.rel_residual, info.converged
         else:
             b = dp.lift(dp.rhs(1.0), None)
-            barrier()
-            t0 = time.perf_counter()
-            xs, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, maxiter=maxiter, check_every=50)
-            barrier()
-            el = time.perf_counter() - t0
-            pcg = {"iterations": it, "seconds": el, "converged": ok, "rel_residual": rel,
-                   "ms_per_iteration": el / max(it, 1) * 1e3}
+
+            def run(iters):
+                barrier()
+                t0 = time.perf_counter()
+                xs, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, maxiter=iters, check_every=50)
+                barrier()
+                return time.perf_counter() - t0, it, rel, ok
+        # ms/iteration from the slope between two capped solves: the fixed cost of a solve
+        # (Jacobi diagonal on first use, work vectors, CUDA-graph capture) cancels
+        run(50)
+        base_iters = 100
+        el0, it0, _, _ = run(base_iters)
+        el, it, rel, ok = run(maxiter if args.pcg_full else base_iters + maxiter)
+        pcg = {"iterations": it, "seconds": el, "converged": ok, "rel_residual": rel,
+               "ms_per_iteration": (el - el0) / max(it - it0, 1) * 1e3,
+               "fixed_seconds_per_solve": max(el0 - it0 * (el - el0) / max(it - it0, 1), 0.0)}
         pcg["note"] = ("homogeneous Dirichlet on ebc, f=1, rtol 1e-12"
-                       + ("" if args.pcg_full else "; capped at %d iterations" % maxiter))
+                       + ("" if args.pcg_full else "; capped at %d iterations" % pcg["iterations"]))
 
     cpu = None
     if rank == 0 and not multi and args.cpu_sample > 0:
