@@ -46,11 +46,18 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=64,
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
     ap.add_argument("--kind", default="S", choices=["S", "C"])
+    ap.add_argument("--order", type=int, default=8,
+                    help="polynomial order (exploration only: the metric is quoted at p = 8)")
     ap.add_argument("--pe", type=int, default=0, help="elements per patch (0 = automatic)")
     ap.add_argument("--tile", default="", help="patch tile shape bx,by (elements), e.g. 2,8")
     ap.add_argument("--ablate", type=int, default=0,
                     help="internal profiling knob: extra apply flag bits (results are wrong)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    global ORDER, METRIC
+    if args.order != ORDER:
+        ORDER = args.order
+        METRIC = "Poisson operator-apply GDOF/s (FP64, p=%d)" % ORDER
+    return args
 
 
 def measured_peaks():
@@ -233,8 +240,8 @@ def run_engine(args):
             apply_fn = lambda u, out: op.apply(u, out=out)          # noqa: E731
         n_local = n_global = op.n_nodes
         n_global_units = n_global
-        workload = ("structured %dx%d-element quad mesh Poisson, p=8, FP64, rcm_order=False "
-                    "(BASELINE configs[1])" % (nx, nx))
+        workload = ("structured %dx%d-element quad mesh Poisson, p=%d, FP64, rcm_order=False "
+                    "(BASELINE configs[1])" % (nx, nx, ORDER))
         dp = None
     else:
         from spectralelementmethod_b200.distributed import DistributedPoisson, StripPartition
