@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--pcg-full", action="store_true", help="run PCG to rtol 1e-12")
     ap.add_argument("--cpu-sample", type=int, default=64,
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU interface exchange: fused NVLink peer-memory kernel or NCCL p2p")
     ap.add_argument("--kind", default="S", choices=["S", "C"])
     ap.add_argument("--order", type=int, default=8,
                     help="polynomial order (exploration only: the metric is quoted at p = 8)")
@@ -247,13 +249,15 @@ def run_engine(args):
         from spectralelementmethod_b200.distributed import DistributedPoisson, StripPartition
         nx = args.nx or 884
         part = StripPartition(rank, world, nx, nx, ORDER, bounds=(-1.0, -1.0 + 2.0 * world, -1.0, 1.0))
-        dp = DistributedPoisson(part, ORDER, args.kind, elems_per_patch=args.pe or None)
+        dp = DistributedPoisson(part, ORDER, args.kind, elems_per_patch=args.pe or None,
+                                exchange=args.exchange)
         op = dp.op
         apply_fn = lambda u, out: dp.apply(u, out=out)          # noqa: E731
         n_local = op.n_nodes
         n_global_units = part.n_global
         workload = ("weak scaling: %dx%d elements p=8 per GPU, strip-partitioned over %d GPUs, "
-                    "NCCL interface exchange (BASELINE configs[4])" % (nx, nx, world))
+                    "%s interface exchange (BASELINE configs[4])"
+                    % (nx, nx, world, "NVLink peer-memory" if args.exchange == "peer" else "NCCL p2p"))
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 

@@ -320,6 +320,42 @@ int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x, const doub
                        double *work, double *sc, double *vec_partials, double rtol,
                        int maxiter, int check_every, semk_pcg_info *info, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Multi-GPU: interface exchange of a strip partition over NVLink peer memory
+ * (the reference itself is single-process -- its serial
+ * analogue is the scatter-add `grhs[inds] += ...`, sem/discrete.py:499).
+ *
+ * Every rank owns one exchange REGION in device memory, exported to its two
+ * neighbours through CUDA IPC:
+ *   bytes [0, 256)  : four uint64 flag words -- [0..1] published by the LEFT
+ *                     neighbour for epoch parity 0 / 1, [2..3] by the RIGHT one;
+ *   then            : double recv[4][n_col] -- [0..1] columns received from the
+ *                     left neighbour (parity 0 / 1), [2..3] from the right one.
+ * ------------------------------------------------------------------------ */
+#define SEMK_PEER_HANDLE_BYTES 64
+int64_t semk_halo_region_bytes(int64_t n_col);
+/* cudaMalloc + zero a region and export it; handle_out: host [64] */
+int semk_peer_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle_out);
+/* map a neighbour's region (handle from its semk_peer_alloc) into this process */
+int semk_peer_open(const unsigned char *handle, void **dev_ptr);
+int semk_peer_close(void *dev_ptr);
+int semk_peer_free(void *dev_ptr);
+/* One kernel: push my boundary columns y[0, n_col) / y[n_local - n_col, n_local)
+ * (partial sums of the local apply) into the neighbours' regions, publish
+ * `epoch` (strictly increasing from 1, the same sequence on every rank), wait
+ * for the neighbours' columns of the same epoch, add them into y, re-impose
+ * the identity rows y = u on Dirichlet nodes of the shared columns
+ * (dirichlet: device uint8 [n_local] or NULL) and subtract the doubly counted
+ * u^2 of the column this rank does not own (the right one) from *dot_inout
+ * (device scalar holding this rank's fused u.y, or NULL).  left_region /
+ * right_region: peer pointers from semk_peer_open, NULL = no neighbour.
+ * status: device int, set to 1 if a neighbour did not show up within ~2 s
+ * (the kernel then gives up instead of hanging the GPU). */
+int semk_halo_exchange_f64(int64_t n_col, int64_t n_local, double *y, const double *u,
+                           const uint8_t *dirichlet, void *my_region, void *left_region,
+                           void *right_region, uint64_t epoch, double *dot_inout, int *status,
+                           void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,12 @@ SIGNATURES = {
     "semk_dot_f64": (_I, [_L, _P, _P, _P, _P, _P]),
     "semk_pcg_solve_f64": (_I, [C.POINTER(semk_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
                                 C.POINTER(semk_pcg_info), _P]),
+    "semk_halo_region_bytes": (_L, [_L]),
+    "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
+    "semk_peer_open": (_I, [_P, C.POINTER(_P)]),
+    "semk_peer_close": (_I, [_P]),
+    "semk_peer_free": (_I, [_P]),
+    "semk_halo_exchange_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
 }
 
 _lib = None

@@ -15,8 +15,12 @@ kernels.  The right neighbour owns a shared column: rank r's owned nodes are
 the prefix [0, n_owned), n_owned = n - NY (n on the last rank), which is what
 the PCG kernels' ``n_dot`` argument expects.
 
-Per operator apply: one local apply (partial sums on the interface columns),
-one neighbour exchange (<= 2 messages of NY doubles each way), two adds.
+Per operator apply: one local apply (partial sums on the interface columns)
+and ONE exchange kernel that pushes the boundary columns into the neighbours'
+memory over NVLink (CUDA IPC peer pointers), waits for theirs, adds them and
+re-imposes the Dirichlet identity rows (``PeerHalo``, csrc/semk_peer.cu).  An
+NCCL send/recv path (``exchange="nccl"``) is kept for comparison and for
+process groups without peer access; the CPU tests use it over gloo.
 p.Ap is taken on the *partial* sums before the exchange: summed over ranks it
 equals the global p.Ap exactly, so it rides on the same all-reduce.
 """
@@ -24,7 +28,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["StripPartition", "DistributedOperator", "distributed_pcg"]
+__all__ = ["StripPartition", "DistributedOperator", "PeerHalo", "distributed_pcg"]
 
 
 class StripPartition(object):
@@ -101,6 +105,70 @@ class StripPartition(object):
         return mesh
 
 
+class PeerHalo(object):
+    """Interface exchange over NVLink peer memory: every rank exports one
+    exchange region (flags + receive buffers) through CUDA IPC and maps its
+    neighbours' regions; ``exchange`` launches the single fused kernel
+    semk_halo_exchange_f64 (push, publish epoch, wait, add, Dirichlet fix-up).
+    All ranks must call ``exchange`` the same number of times (SPMD)."""
+
+    def __init__(self, part, group=None, device=None):
+        import ctypes as C
+        from . import _lib
+        self._lib = lib = _lib.load()
+        self._check = _lib.check
+        self.part = part
+        self.group = group
+        self.device = device
+        self.epoch = 0
+        self._mine = C.c_void_p()
+        self._left = C.c_void_p()
+        self._right = C.c_void_p()
+        nbytes = int(lib.semk_halo_region_bytes(part.NY))
+        handle = (C.c_ubyte * 64)()
+        _lib.check(lib.semk_peer_alloc(nbytes, C.byref(self._mine), handle))
+        handles = [None] * dist.get_world_size(group)
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        for side, peer in ((self._left, part.left), (self._right, part.right)):
+            if peer is not None:
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
+                _lib.check(lib.semk_peer_open(buf, C.byref(side)))
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)
+
+    def exchange(self, y, u=None, dirichlet=None, dot_inout=None):
+        """Sum the interface columns of y across neighbours in place; with
+        ``dirichlet`` (uint8 device mask) also y = u on the Dirichlet nodes of
+        those columns, and the doubly counted u^2 leaves ``dot_inout``."""
+        self.epoch += 1
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.semk_halo_exchange_f64(
+            self.part.NY, y.numel(), y.data_ptr(),
+            u.data_ptr() if u is not None else None,
+            dirichlet.data_ptr() if dirichlet is not None else None,
+            self._mine, self._left, self._right, self.epoch,
+            dot_inout.data_ptr() if dot_inout is not None else None,
+            self.status.data_ptr(), stream))
+        return y
+
+    def check(self):
+        """Raise if a neighbour failed to deliver a column (synchronises)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer halo exchange timed out waiting for a neighbour")
+
+    def close(self):
+        if self._mine:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            for side in (self._left, self._right):
+                if side:
+                    self._lib.semk_peer_close(side)
+                    side.value = None
+            dist.barrier(group=self.group)
+            self._lib.semk_peer_free(self._mine)
+            self._mine.value = None
+
+
 class DistributedOperator(object):
     """Global operator = local operators + interface exchange.
 
@@ -113,11 +181,15 @@ class DistributedOperator(object):
         the sum would double it).
     """
 
-    def __init__(self, part, local_apply, dirichlet=None, group=None, device=None):
+    def __init__(self, part, local_apply, dirichlet=None, group=None, device=None, halo=None):
         self.part = part
         self.local_apply = local_apply
         self.group = group
         self.device = device
+        self.halo = halo              # PeerHalo: fused NVLink exchange (else NCCL / gloo p2p)
+        self._dir_u8 = None
+        if halo is not None and dirichlet is not None:
+            self._dir_u8 = torch.as_tensor(np.asarray(dirichlet).astype(np.uint8)).to(device)
         NY = part.NY
         kw = dict(dtype=torch.float64, device=device)
         self._recv_left = torch.empty(NY, **kw) if part.left is not None else None
@@ -142,6 +214,8 @@ class DistributedOperator(object):
     def exchange_add(self, y):
         """Sum the interface columns of y across neighbouring ranks, in place."""
         part = self.part
+        if self.halo is not None:
+            return self.halo.exchange(y)
         ops = []
         if part.left is not None:
             ops.append(dist.P2POp(dist.isend, y[part.left_slice], part.left, self.group))
@@ -164,6 +238,8 @@ class DistributedOperator(object):
         tensor) receives this rank's share of u.y; all-reduce it for the
         global value."""
         y = self.local_apply(u, out, dot_out)
+        if self.halo is not None:
+            return self.halo.exchange(y, u, self._dir_u8, dot_out)
         self.exchange_add(y)
         if self._fix_ids is not None:
             y[self._fix_ids] = u[self._fix_ids]
@@ -212,6 +288,8 @@ def distributed_pcg(dop, b, x, dinv, kernels, rtol=1e-12, maxiter=200000, check_
             kernels.update_p(r, dinv, p, sc)
             it += 1
         h = sc.cpu()
+        if getattr(dop, "halo", None) is not None:
+            dop.halo.check()
         if float(h[7]) != 0.0:
             from ._lib import SolverFailure
             raise SolverFailure("distributed PCG breakdown (p.Ap <= 0 or non-finite)")
@@ -225,7 +303,7 @@ class DistributedPoisson(object):
     configurations (BASELINE.json configs[4]): local mesh + DOF manager +
     device operator on each rank, interface exchange, global Jacobi-PCG."""
 
-    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None):
+    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None, exchange="peer"):
         from . import discrete
         from .basis_functions import LagrangeGaussLobatto, TensorProductQS
         from .operators import PCGKernels
@@ -238,9 +316,13 @@ class DistributedPoisson(object):
         self.op = self.mngr.poisson_operator(dirichlet=self.on_ebc, elems_per_patch=elems_per_patch)
         self.kernels = PCGKernels(self.op)
         op = self.op
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.halo = PeerHalo(part, group, op.dev) if exchange == "peer" else None
         self.dop = DistributedOperator(
             part, lambda u, out, dot: op.apply(u, out=out, dot_out=dot),
-            dirichlet=self.on_ebc if op.has_dirichlet else None, group=group, device=op.dev)
+            dirichlet=self.on_ebc if op.has_dirichlet else None, group=group, device=op.dev,
+            halo=self.halo)
         self._mask = op.dirichlet_dev.bool() if op.has_dirichlet else None
         self._dinv = None
 

@@ -30,7 +30,6 @@ def main():
     nxl, ny, p, kind = 24, 20, 8, "C"
     bounds = (-1.0, -1.0 + 2.0 * world, -1.0, 1.0)
     part = StripPartition(rank, world, nxl, ny, p, bounds=bounds)
-    dp = DistributedPoisson(part, p, kind)
     gid = torch.from_numpy(part.global_ids()).to(dev)
 
     # global problem on every rank's own GPU (small), as the reference
@@ -40,13 +39,33 @@ def main():
     gm = discrete.DOFManager(gmesh, 1, TensorProductQS(b1, b1), rcm_order=False)
     gon = gm.boundary_node_mask("ebc")
     gop = gm.poisson_operator(dirichlet=gon)
-    assert np.array_equal(dp.on_ebc, gon[part.global_ids()])
 
     g = torch.Generator(device=dev).manual_seed(7)
     ug = torch.randn(gop.n_nodes, dtype=torch.float64, device=dev, generator=g)
     want = gop.apply(ug)
     dot_ref = torch.zeros(1, dtype=torch.float64, device=dev)
     gop.apply(ug, dot_out=dot_ref)
+    bg = gop.lift(gop.rhs(1.0), None)
+    xg, info = gop.solve_pcg(bg, rtol=1e-12, check_every=10)
+    results = {}
+    for exchange in ("peer", "nccl"):
+        dp = DistributedPoisson(part, p, kind, exchange=exchange)
+        assert np.array_equal(dp.on_ebc, gon[part.global_ids()])
+        results[exchange] = check_one(dp, gop, gid, ug, want, dot_ref, bg, xg, dev)
+        if dp.halo is not None:
+            dp.halo.check()
+            dp.halo.close()
+    # the two exchange paths add the same two numbers: bit-identical results
+    assert torch.equal(results["peer"][0], results["nccl"][0])
+    if rank == 0:
+        err, it, serr = results["peer"][1:]
+        print("multigpu_check ok: world=%d apply err %.2e, PCG %d its (single GPU %d), "
+              "solution diff %.2e; peer == nccl bitwise" % (world, err, it, info.iterations, serr))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def check_one(dp, gop, gid, ug, want, dot_ref, bg, xg, dev):
     u = ug[gid].contiguous()
     dot = torch.zeros(1, dtype=torch.float64, device=dev)
     y = dp.apply(u, dot_out=dot)
@@ -57,18 +76,12 @@ def main():
     assert float((dp.diagonal() - gop.diagonal()[gid]).abs().max()) < 1e-11
     assert float((dp.rhs(1.0) - gop.rhs(1.0)[gid]).abs().max()) < 1e-14
 
-    bg = gop.lift(gop.rhs(1.0), None)
-    xg, info = gop.solve_pcg(bg, rtol=1e-12, check_every=10)
     b = dp.lift(dp.rhs(1.0), None)
     assert float((b - bg[gid]).abs().max()) < 1e-13
     x, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, check_every=10)
     serr = float((x - xg[gid]).norm() / xg.norm())
     assert ok and serr < 1e-9, (ok, serr)
-    if rank == 0:
-        print("multigpu_check ok: world=%d apply err %.2e, PCG %d its (single GPU %d), "
-              "solution diff %.2e" % (world, err, it, info.iterations, serr))
-    dist.barrier()
-    dist.destroy_process_group()
+    return y, err, it, serr
 
 
 if __name__ == "__main__":
