@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--pcg-full", action="store_true", help="run PCG to rtol 1e-12")
     ap.add_argument("--cpu-sample", type=int, default=64,
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU interface exchange: fused NVLink peer-memory kernel or NCCL p2p")
     ap.add_argument("--kind", default="S", choices=["S", "C"])
     ap.add_argument("--order", type=int, default=8,
@@ -257,7 +257,7 @@ def run_engine(args):
         n_global_units = part.n_global
         workload = ("weak scaling: %dx%d elements p=8 per GPU, strip-partitioned over %d GPUs, "
                     "%s interface exchange (BASELINE configs[4])"
-                    % (nx, nx, world, "NVLink peer-memory" if args.exchange == "peer" else "NCCL p2p"))
+                    % (nx, nx, world, "NVLink peer-memory" if dp.exchange == "peer" else "NCCL p2p"))
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 

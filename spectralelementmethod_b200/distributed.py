@@ -126,15 +126,37 @@ class PeerHalo(object):
         self._right = C.c_void_p()
         nbytes = int(lib.semk_halo_region_bytes(part.NY))
         handle = (C.c_ubyte * 64)()
-        _lib.check(lib.semk_peer_alloc(nbytes, C.byref(self._mine), handle))
+        # every rank goes through the same collectives whatever fails locally
+        err = None
+        try:
+            _lib.check(lib.semk_peer_alloc(nbytes, C.byref(self._mine), handle))
+        except Exception as e:              # noqa: BLE001
+            err = e
         handles = [None] * dist.get_world_size(group)
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
         for side, peer in ((self._left, part.left), (self._right, part.right)):
-            if peer is not None:
-                buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
-                _lib.check(lib.semk_peer_open(buf, C.byref(side)))
+            if peer is not None and err is None:
+                try:
+                    if handles[peer] is None:
+                        raise RuntimeError("neighbour %d could not export its region" % peer)
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
+                    _lib.check(lib.semk_peer_open(buf, C.byref(side)))
+                except Exception as e:      # noqa: BLE001
+                    err = e
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         dist.barrier(group=group)
+        if err is not None:
+            self._release()
+            raise err
+
+    def _release(self):
+        for side in (self._left, self._right):
+            if side:
+                self._lib.semk_peer_close(side)
+                side.value = None
+        if self._mine:
+            self._lib.semk_peer_free(self._mine)
+            self._mine.value = None
 
     def exchange(self, y, u=None, dirichlet=None, dot_inout=None):
         """Sum the interface columns of y across neighbours in place; with
@@ -157,16 +179,15 @@ class PeerHalo(object):
             raise RuntimeError("peer halo exchange timed out waiting for a neighbour")
 
     def close(self):
-        if self._mine:
-            torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)
-            for side in (self._left, self._right):
-                if side:
-                    self._lib.semk_peer_close(side)
-                    side.value = None
-            dist.barrier(group=self.group)
-            self._lib.semk_peer_free(self._mine)
-            self._mine.value = None
+        """Collective: all ranks unmap their neighbours before anyone frees."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for side in (self._left, self._right):
+            if side:
+                self._lib.semk_peer_close(side)
+                side.value = None
+        dist.barrier(group=self.group)
+        self._release()
 
 
 class DistributedOperator(object):
@@ -303,7 +324,7 @@ class DistributedPoisson(object):
     configurations (BASELINE.json configs[4]): local mesh + DOF manager +
     device operator on each rank, interface exchange, global Jacobi-PCG."""
 
-    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None, exchange="peer"):
+    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None, exchange="auto"):
         from . import discrete
         from .basis_functions import LagrangeGaussLobatto, TensorProductQS
         from .operators import PCGKernels
@@ -316,9 +337,26 @@ class DistributedPoisson(object):
         self.op = self.mngr.poisson_operator(dirichlet=self.on_ebc, elems_per_patch=elems_per_patch)
         self.kernels = PCGKernels(self.op)
         op = self.op
-        if exchange not in ("peer", "nccl"):
-            raise ValueError("exchange must be 'peer' or 'nccl'")
-        self.halo = PeerHalo(part, group, op.dev) if exchange == "peer" else None
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self.halo = None
+        if exchange in ("auto", "peer"):
+            # "auto": every rank tries to map its neighbours; unless ALL succeed (peer access
+            # and CUDA IPC available between all neighbouring GPUs) everyone uses NCCL p2p
+            err = None
+            try:
+                self.halo = PeerHalo(part, group, op.dev)
+            except Exception as e:          # noqa: BLE001 -- reported below or re-raised
+                err = e
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=op.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if float(ok) < 1.0:
+                if exchange == "peer":
+                    raise RuntimeError("peer-memory exchange unavailable: %r" % (err,))
+                if self.halo is not None:
+                    self.halo._release()    # (no collective: the failing ranks are not in it)
+                self.halo = None
+        self.exchange = "peer" if self.halo is not None else "nccl"
         self.dop = DistributedOperator(
             part, lambda u, out, dot: op.apply(u, out=out, dot_out=dot),
             dirichlet=self.on_ebc if op.has_dirichlet else None, group=group, device=op.dev,
