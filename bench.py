@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--nx", type=int, default=0, help="elements per side per GPU (0 = config default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-stages", type=int, default=16,
+                    help="pipeline stages of the host-buffer apply (1 = copy, apply, copy back)")
     ap.add_argument("--pcg-iters", type=int, default=300,
                     help="PCG iterations timed for the time-to-solution estimate (0 = skip)")
     ap.add_argument("--pcg-full", action="store_true", help="run PCG to rtol 1e-12")
@@ -326,7 +328,7 @@ def run_engine(args):
 
     def e2e_step():
         if dp is None:
-            op.apply_host(u_host, y_host, scratch)
+            op.apply_host(u_host, y_host, scratch, stages=args.e2e_stages)
         else:
             scratch[0].copy_(u_host, non_blocking=True)
             dp.apply(scratch[0], out=scratch[1])
@@ -400,6 +402,7 @@ def run_engine(args):
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local * world,
                     "d2h_bytes_per_step": 8 * n_local * world, "steps": args.e2e_steps,
+                    "pipeline_stages": args.e2e_stages if dp is None else 1,
                     "matches_device_result": e2e_ok},
             "gpu_launches": 2 * args.steps,
             "clocks": clocks.summary(),

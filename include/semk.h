@@ -99,7 +99,8 @@ enum semk_plan_array {
                                  table [m][le][t] followed by the PE element colours;
                                  deduplicated like PNBLK (PATCH_HDR word 6)                 */
   SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared_rec][8] {node id | flags, count, slot 0..5} for the
-                                 shared nodes touched by 3+ patches (corners); counts above 6:
+                                 shared nodes touched by 3+ patches (corners), sorted by the
+                                 highest patch touching the node; counts above 6:
                                  slots 0..4 inline, word 7 = offset of the rest in SHARED_EXT   */
   SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         overflow slot lists of SHARED_REC            */
   SEMK_PA_SHARED_CHUNK = 15,  /* uint32 [n_shared_chunk][8] affine chunks of 1..32 two-patch nodes:
@@ -107,7 +108,13 @@ enum semk_plan_array {
                                  node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
   SEMK_PA_PATCH_HDR = 16,     /* uint32 [n_patch][8]  {n nodes, n private, first interface slot, 0,
                                  base node id, PNBLK block, ELBLK block, 0}                   */
-  SEMK_PA_COUNT = 17
+  SEMK_PA_PATCH_MAXNODE = 17, /* uint32 [n_patch]     largest node id of the patch (the smallest is
+                                 PATCH_HDR word 4)                                            */
+  SEMK_PA_CHUNK_MAXPATCH = 18,/* int32  [n_shared_chunk] higher of the two patches of a chunk; the
+                                 chunk table is sorted by it                                  */
+  SEMK_PA_REC_MAXPATCH = 19,  /* int32  [n_shared_rec]   highest patch touching a record's node; the
+                                 record table is sorted by it (then by node id)               */
+  SEMK_PA_COUNT = 20
 };
 
 enum semk_plan_scalar {
@@ -249,6 +256,25 @@ int semk_poisson_apply_atomic_f64(int n1, int64_t n_elem, int64_t n_nodes, const
  * d_u, d_y: device scratch [n_nodes]. */
 int semk_poisson_apply_host_f64(const semk_op *op, const double *u_host, double *y_host,
                                 double *d_u, double *d_y, int flags, void *stream);
+
+/* The same with the three phases PIPELINED over `n_stages` (<= 64) stages of
+ * the patch sequence: while stage i computes, stage i+1's part of u is being
+ * uploaded and stage i-1's part of y downloaded (two internal copy streams;
+ * PCIe is full duplex).  Stage i runs patches [stages[i-1].patch_end,
+ * stages[i].patch_end) and the interface chunks / records up to chunk_end /
+ * rec_end (the tables are sorted by the highest patch involved, so these are
+ * prefixes); it needs u[0, u_need) on the device and makes y[0, y_final)
+ * final.  All five columns are non-decreasing and the last stage ends at
+ * (n_patch, n_shared_chunk, n_shared, n_nodes, n_nodes).  With a numbering
+ * that does not follow the patch order the stage table degenerates (u_need =
+ * n_nodes early, y_final = 0 until the end) and the call behaves like
+ * semk_poisson_apply_host_f64.  Blocks until y_host is complete. */
+typedef struct semk_stage {
+  int64_t patch_end, chunk_end, rec_end, u_need, y_final;
+} semk_stage;
+int semk_poisson_apply_host_staged_f64(const semk_op *op, const semk_stage *stages, int n_stages,
+                                       const double *u_host, double *y_host, double *d_u,
+                                       double *d_y, int flags, void *stream);
 
 /* ------------------------------------------------------------------------
  * K3: generic assembly  out[g] = sum over element-local entries mapped to g

@@ -22,7 +22,7 @@ MAX_N1 = 17
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
  PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT, PA_SHARED_CHUNK,
- PA_PATCH_HDR) = range(17)
+ PA_PATCH_HDR, PA_PATCH_MAXNODE, PA_CHUNK_MAXPATCH, PA_REC_MAXPATCH) = range(20)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
  PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE, PS_N_SHARED_CHUNK,
  PS_N_SHARED_REC, PS_N_PN_UNIQUE, PS_N_EL_UNIQUE) = range(14)
@@ -34,7 +34,8 @@ PLAN_ARRAY_DTYPES = {
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
     PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
     PA_ELBLK: np.uint16, PA_SHARED_REC: np.uint32, PA_SHARED_EXT: np.uint32,
-    PA_SHARED_CHUNK: np.uint32, PA_PATCH_HDR: np.uint32,
+    PA_SHARED_CHUNK: np.uint32, PA_PATCH_HDR: np.uint32, PA_PATCH_MAXNODE: np.uint32,
+    PA_CHUNK_MAXPATCH: np.int32, PA_REC_MAXPATCH: np.int32,
 }
 
 
@@ -62,6 +63,11 @@ class semk_op(C.Structure):
         ("n_shared_chunk", C.c_int64), ("shared_chunk", C.c_void_p),
         ("partials", C.c_void_p), ("D_host", C.c_void_p), ("dirichlet", C.c_void_p),
     ]
+
+
+class semk_stage(C.Structure):
+    _fields_ = [("patch_end", C.c_int64), ("chunk_end", C.c_int64), ("rec_end", C.c_int64),
+                ("u_need", C.c_int64), ("y_final", C.c_int64)]
 
 
 class semk_pcg_info(C.Structure):
@@ -100,6 +106,8 @@ SIGNATURES = {
     "semk_dot_f64": (_I, [_L, _P, _P, _P, _P, _P]),
     "semk_pcg_solve_f64": (_I, [C.POINTER(semk_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
                                 C.POINTER(semk_pcg_info), _P]),
+    "semk_poisson_apply_host_staged_f64": (_I, [C.POINTER(semk_op), C.POINTER(semk_stage), _I, _P, _P,
+                                                _P, _P, _I, _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
     "semk_peer_open": (_I, [_P, C.POINTER(_P)]),

@@ -337,7 +337,8 @@ template <int N, int PE, int MODE>
 __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N, PE))
     patch_kernel(semk_op op, DMatEO dm, const double *__restrict__ u,
                  const double *__restrict__ loc, double *__restrict__ y, int flags,
-                 double fill_dirichlet, double *__restrict__ dot_partials) {
+                 double fill_dirichlet, double *__restrict__ dot_partials, int64_t patch_begin,
+                 int64_t patch_end) {
   constexpr int NN = N * N;
   constexpr int NP = N * PE;
   constexpr int kThreads = PatchCfg<N, PE>::kThreads;
@@ -381,8 +382,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   // this CTA's patch sequence: round-robin over the grid, so that at any time the
   // resident CTAs work on a compact window of the mesh (DRAM page / L2 locality)
   const int64_t step = (int64_t)gridDim.x;
-  const int64_t p_first = (int64_t)blockIdx.x;
-  const int64_t p_end = op.n_patch;
+  const int64_t p_first = patch_begin + (int64_t)blockIdx.x;
+  const int64_t p_end = patch_end;  // (a sub-range of the patches: staged host apply)
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) semk_mbar_init(&mbar[i], 1);
@@ -583,6 +584,12 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
 //     node ids and both slot runs are arithmetic progressions, so a whole patch
 //     edge is reduced with coalesced accesses and 32 bytes of table per chunk;
 //   remaining CTAs: per-node records (nodes touched by 3+ patches), slot list inline.
+// sub-range of the interface tables (both sorted by the highest patch involved, so the
+// entries that are complete after patches [0, P) form a prefix): staged host apply
+struct InterfaceRange {
+  int64_t chunk_begin, chunk_end, rec_begin, rec_end;
+};
+
 constexpr int kChunkWarps = 8;   // warps per CTA of 256 threads
 constexpr int kChunkUnroll = 4;  // chunks per warp
 
@@ -613,7 +620,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
     shared_nodes_kernel(semk_op op, const double *__restrict__ u, double *__restrict__ y,
                         int flags, double fill_dirichlet, double *__restrict__ dot_partials,
-                        int64_t partial_offset, int chunk_blocks) {
+                        int64_t partial_offset, int chunk_blocks, InterfaceRange rng) {
   __shared__ double red[32];
   double dot = 0.0;
   const bool want_dot = (MODE == MODE_APPLY) && (dot_partials != nullptr);
@@ -622,13 +629,13 @@ __global__ void __launch_bounds__(256)
     // each warp reduces kChunkUnroll chunks: all table loads first, then all slot
     // loads, then the stores (three dependent memory levels, kept wide)
     const int64_t cbase =
-        ((int64_t)blockIdx.x * kChunkWarps + (threadIdx.x >> 5)) * kChunkUnroll;
+        rng.chunk_begin + ((int64_t)blockIdx.x * kChunkWarps + (threadIdx.x >> 5)) * kChunkUnroll;
     uint4 c0[kChunkUnroll], c1[kChunkUnroll];
     double va[kChunkUnroll], vb[kChunkUnroll];
 #pragma unroll
     for (int k = 0; k < kChunkUnroll; ++k) {
       const int64_t c = cbase + k;
-      const bool on = c < op.n_shared_chunk;
+      const bool on = c < rng.chunk_end;
       // c0 = {node0, dn, a0, da}, c1 = {b0, db, len, Dirichlet mask}
       c0[k] = on ? reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c] : make_uint4(0, 0, 0, 0);
       c1[k] = on ? reinterpret_cast<const uint4 *>(op.shared_chunk)[2 * c + 1]
@@ -653,8 +660,8 @@ __global__ void __launch_bounds__(256)
     // slot list inline in a 32-byte record, so two dependent memory levels
     const int64_t nb = (int64_t)gridDim.x - chunk_blocks;
     const int64_t stride = nb * blockDim.x;
-    for (int64_t i = ((int64_t)blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x;
-         i < op.n_shared; i += stride) {
+    for (int64_t i = rng.rec_begin + ((int64_t)blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x;
+         i < rng.rec_end; i += stride) {
       const uint4 r0 = reinterpret_cast<const uint4 *>(op.shared_rec)[2 * i];
       const uint4 r1 = reinterpret_cast<const uint4 *>(op.shared_rec)[2 * i + 1];
       const uint32_t cnt = r0.y;
@@ -695,11 +702,27 @@ __global__ void __launch_bounds__(1024)
 
 constexpr int kSharedBlocks = 148 * 64;  // upper bound on the per-node part of the interface kernel
 
-inline void interface_blocks(const semk_op &op, int *chunk_blocks, int *rec_blocks) {
+inline void interface_blocks(const InterfaceRange &r, int *chunk_blocks, int *rec_blocks) {
   const int64_t per_block = (int64_t)kChunkWarps * kChunkUnroll;
-  *chunk_blocks = (int)((op.n_shared_chunk + per_block - 1) / per_block);
-  const int64_t want = (op.n_shared + 255) / 256;
+  *chunk_blocks = (int)((r.chunk_end - r.chunk_begin + per_block - 1) / per_block);
+  const int64_t want = (r.rec_end - r.rec_begin + 255) / 256;
   *rec_blocks = (int)(want < kSharedBlocks ? want : kSharedBlocks);
+}
+
+template <int MODE>
+int launch_interface(const semk_op &op, const double *u, double *y, int flags, double fill,
+                     double *partials, int64_t partial_offset, cudaStream_t st, int *blocks_out,
+                     const InterfaceRange *range = nullptr) {
+  const InterfaceRange all{0, op.n_shared_chunk, 0, op.n_shared};
+  const InterfaceRange r = range ? *range : all;
+  int chunk_blocks = 0, rec_blocks = 0;
+  interface_blocks(r, &chunk_blocks, &rec_blocks);
+  if (blocks_out) *blocks_out = chunk_blocks + rec_blocks;
+  if (chunk_blocks + rec_blocks == 0) return SEMK_OK;
+  shared_nodes_kernel<MODE><<<chunk_blocks + rec_blocks, 256, 0, st>>>(
+      op, u, y, flags, fill, partials, partial_offset, chunk_blocks, r);
+  SEMK_LAUNCH_CHECK("shared_nodes_kernel");
+  return SEMK_OK;
 }
 
 // ---- simple atomic-scatter kernel (independent cross-check) -------------------
@@ -820,7 +843,7 @@ struct PatchLaunch {
   template <int N>
   static int run(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
                  double *y, int flags, double fill, double *partials, cudaStream_t st,
-                 int *grid_out) {
+                 int *grid_out, int64_t pb, int64_t pe) {
     const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
                                           op.eloc_patch_stride, op.max_patch_nodes)
                             .total;
@@ -837,11 +860,13 @@ struct PatchLaunch {
     }
     // persistent grid: every CTA stays resident and loops over its patches, round-robin
     const int64_t resident = (int64_t)per_sm * sms;
-    const unsigned grid = (unsigned)(op.n_patch < resident ? op.n_patch : resident);
-    patch_kernel<N, PE, MODE><<<grid, PatchCfg<N, PE>::kThreads, smem, st>>>(
-        op, dm, u, loc, y, flags, fill, partials);
-    SEMK_LAUNCH_CHECK("patch_kernel");
+    const int64_t np = pe - pb;
+    const unsigned grid = (unsigned)(np < resident ? np : resident);
     if (grid_out) *grid_out = (int)grid;
+    if (grid == 0) return SEMK_OK;
+    patch_kernel<N, PE, MODE><<<grid, PatchCfg<N, PE>::kThreads, smem, st>>>(
+        op, dm, u, loc, y, flags, fill, partials, pb, pe);
+    SEMK_LAUNCH_CHECK("patch_kernel");
     return SEMK_OK;
   }
 };
@@ -852,19 +877,20 @@ inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16; }
 template <int MODE>
 int launch_patch(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
                  double *y, int flags, double fill, double *partials, cudaStream_t st,
-                 int *grid_out) {
+                 int *grid_out, int64_t pb = 0, int64_t pe = -1) {
+  if (pe < 0) pe = op.n_patch;
 #define SEMK_CALL(NV)                                                                     \
   do {                                                                                    \
     int rc;                                                                               \
     if (op.elems_per_patch == 16)                                                         \
       rc = PatchLaunch<16, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st, \
-                                                   grid_out); \
+                                                   grid_out, pb, pe); \
     else if (op.elems_per_patch == 8)                                                     \
       rc = PatchLaunch<8, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st,   \
-                                                  grid_out);  \
+                                                  grid_out, pb, pe);  \
     else                                                                                  \
       rc = PatchLaunch<4, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st,   \
-                                                  grid_out);  \
+                                                  grid_out, pb, pe);  \
     if (rc != SEMK_OK) return rc;                                                         \
   } while (0)
   SEMK_DISPATCH_N1(op.n1, SEMK_CALL)
@@ -969,14 +995,8 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
   rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, partials, st, &grid);
   if (rc != SEMK_OK) return rc;
   int shared_blocks = 0;
-  if (op->n_shared > 0 || op->n_shared_chunk > 0) {
-    int chunk_blocks = 0, rec_blocks = 0;
-    interface_blocks(*op, &chunk_blocks, &rec_blocks);
-    shared_blocks = chunk_blocks + rec_blocks;
-    shared_nodes_kernel<MODE_APPLY><<<shared_blocks, 256, 0, st>>>(*op, u, y, flags, 0.0, partials,
-                                                                  grid, chunk_blocks);
-    SEMK_LAUNCH_CHECK("shared_nodes_kernel");
-  }
+  rc = launch_interface<MODE_APPLY>(*op, u, y, flags, 0.0, partials, grid, st, &shared_blocks);
+  if (rc != SEMK_OK) return rc;
   if (dot_out) {
     reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, grid + shared_blocks, dot_out);
     SEMK_LAUNCH_CHECK("reduce_partials_kernel");
@@ -995,14 +1015,8 @@ extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *o
   rc = launch_patch<MODE_ASSEMBLE>(*op, dm, nullptr, loc, out, flags, fill_dirichlet, nullptr, st,
                                    nullptr);
   if (rc != SEMK_OK) return rc;
-  if (op->n_shared > 0 || op->n_shared_chunk > 0) {
-    int chunk_blocks = 0, rec_blocks = 0;
-    interface_blocks(*op, &chunk_blocks, &rec_blocks);
-    shared_nodes_kernel<MODE_ASSEMBLE><<<chunk_blocks + rec_blocks, 256, 0, st>>>(
-        *op, nullptr, out, flags, fill_dirichlet, nullptr, 0, chunk_blocks);
-    SEMK_LAUNCH_CHECK("shared_nodes_kernel");
-  }
-  return SEMK_OK;
+  return launch_interface<MODE_ASSEMBLE>(*op, nullptr, out, flags, fill_dirichlet, nullptr, 0, st,
+                                         nullptr);
 }
 
 extern "C" int semk_poisson_local_diag_f64(const semk_op *op, const double *D_dev, double *loc,
@@ -1070,6 +1084,101 @@ extern "C" int semk_poisson_apply_atomic_f64(int n1, int64_t n_elem, int64_t n_n
     dirichlet_fix_kernel<<<g2, 256, 0, st>>>(n_nodes, dirichlet, u, y, flags);
     SEMK_LAUNCH_CHECK("dirichlet_fix_kernel");
   }
+  return SEMK_OK;
+}
+
+// Copy streams / events of the staged host apply, one set per device, created on
+// first use (never destroyed: they live as long as the process).
+namespace {
+constexpr int kMaxStages = 64;
+struct HostPipe {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t start = nullptr, up[kMaxStages] = {}, done[kMaxStages] = {}, finish = nullptr;
+  bool ready = false;
+};
+HostPipe *host_pipe() {
+  static HostPipe pipes[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HostPipe &p = pipes[dev];
+  if (!p.ready) {
+    if (cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    auto mk = [](cudaEvent_t *e) {
+      return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    };
+    if (!mk(&p.start) || !mk(&p.finish)) return nullptr;
+    for (int i = 0; i < kMaxStages; ++i)
+      if (!mk(&p.up[i]) || !mk(&p.done[i])) return nullptr;
+    p.ready = true;
+  }
+  return &p;
+}
+}  // namespace
+
+extern "C" int semk_poisson_apply_host_staged_f64(const semk_op *op, const semk_stage *stages,
+                                                  int n_stages, const double *u_host,
+                                                  double *y_host, double *d_u, double *d_y,
+                                                  int flags, void *stream) {
+  int rc = check_op(op, "semk_poisson_apply_host_staged_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(stages && n_stages >= 1 && n_stages <= kMaxStages,
+               "semk_poisson_apply_host_staged_f64: 1..64 stages");
+  SEMK_REQUIRE(u_host && y_host && d_u && d_y && d_u != d_y,
+               "semk_poisson_apply_host_staged_f64: null / aliased buffers");
+  SEMK_REQUIRE(op->G && op->D_host, "semk_poisson_apply_host_staged_f64: missing G or D");
+  {
+    int64_t pp = 0, pc = 0, pr = 0, pu = 0, py = 0;
+    for (int i = 0; i < n_stages; ++i) {
+      const semk_stage &s = stages[i];
+      SEMK_REQUIRE(s.patch_end >= pp && s.chunk_end >= pc && s.rec_end >= pr && s.u_need >= pu &&
+                       s.y_final >= py && s.u_need <= op->n_nodes && s.y_final <= op->n_nodes,
+                   "semk_poisson_apply_host_staged_f64: stage table not monotone");
+      pp = s.patch_end, pc = s.chunk_end, pr = s.rec_end, pu = s.u_need, py = s.y_final;
+    }
+    SEMK_REQUIRE(pp == op->n_patch && pc == op->n_shared_chunk && pr == op->n_shared &&
+                     pu == op->n_nodes && py == op->n_nodes,
+                 "semk_poisson_apply_host_staged_f64: last stage must complete the operator");
+  }
+  DMatEO dm;
+  if (!make_dmat_eo(op->n1, op->D_host, &dm)) {
+    semk_set_error("semk_poisson_apply_host_staged_f64: D is not centro-antisymmetric");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  HostPipe *P = host_pipe();
+  SEMK_REQUIRE(P, "semk_poisson_apply_host_staged_f64: could not create copy streams");
+  cudaStream_t st = semk_stream(stream);
+  // the copy streams start after whatever the caller queued on `stream`
+  SEMK_CUDA_CHECK(cudaEventRecord(P->start, st));
+  SEMK_CUDA_CHECK(cudaStreamWaitEvent(P->h2d, P->start, 0));
+  SEMK_CUDA_CHECK(cudaStreamWaitEvent(P->d2h, P->start, 0));
+  int64_t pb = 0, cb = 0, rb = 0, ub = 0, yb = 0;
+  for (int i = 0; i < n_stages; ++i) {
+    const semk_stage &s = stages[i];
+    // upload the part of u this stage's patches read ...
+    if (s.u_need > ub)
+      SEMK_CUDA_CHECK(cudaMemcpyAsync(d_u + ub, u_host + ub, sizeof(double) * (size_t)(s.u_need - ub),
+                                      cudaMemcpyHostToDevice, P->h2d));
+    SEMK_CUDA_CHECK(cudaEventRecord(P->up[i], P->h2d));
+    SEMK_CUDA_CHECK(cudaStreamWaitEvent(st, P->up[i], 0));
+    // ... run its patches and the interface entries they complete ...
+    rc = launch_patch<MODE_APPLY>(*op, dm, d_u, nullptr, d_y, flags, 0.0, nullptr, st, nullptr, pb,
+                                  s.patch_end);
+    if (rc != SEMK_OK) return rc;
+    const InterfaceRange r{cb, s.chunk_end, rb, s.rec_end};
+    rc = launch_interface<MODE_APPLY>(*op, d_u, d_y, flags, 0.0, nullptr, 0, st, nullptr, &r);
+    if (rc != SEMK_OK) return rc;
+    SEMK_CUDA_CHECK(cudaEventRecord(P->done[i], st));
+    // ... and download the part of y that is final now
+    SEMK_CUDA_CHECK(cudaStreamWaitEvent(P->d2h, P->done[i], 0));
+    if (s.y_final > yb)
+      SEMK_CUDA_CHECK(cudaMemcpyAsync(y_host + yb, d_y + yb, sizeof(double) * (size_t)(s.y_final - yb),
+                                      cudaMemcpyDeviceToHost, P->d2h));
+    pb = s.patch_end, cb = s.chunk_end, rb = s.rec_end, ub = s.u_need, yb = s.y_final;
+  }
+  SEMK_CUDA_CHECK(cudaEventRecord(P->finish, P->d2h));
+  SEMK_CUDA_CHECK(cudaStreamWaitEvent(st, P->finish, 0));
+  SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
   return SEMK_OK;
 }
 

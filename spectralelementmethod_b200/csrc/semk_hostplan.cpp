@@ -32,7 +32,9 @@ struct semk_hostplan {
   int64_t scalars[SEMK_PS_COUNT] = {0};
   std::vector<int32_t> patch_node_ptr, patch_npriv, patch_nnodes, patch_slot_base, shared_ptr,
       shared_slot;
-  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk, patch_hdr;
+  std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk, patch_hdr,
+      patch_maxnode;
+  std::vector<int32_t> chunk_maxpatch, rec_maxpatch;
   std::vector<uint16_t> elblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
@@ -270,9 +272,11 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       std::vector<int32_t> ord(pairs.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int32_t)i;
       std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+        // higher patch first: the chunks that are complete once patches [0, P) have run
+        // form a prefix of the table (staged host apply)
         const Pair &a = pairs[x], &b = pairs[y];
-        if (a.pa != b.pa) return a.pa < b.pa;
         if (a.pb != b.pb) return a.pb < b.pb;
+        if (a.pa != b.pa) return a.pa < b.pa;
         return a.sa < b.sa;
       });
       std::vector<uint8_t> taken(pairs.size(), 0);
@@ -315,12 +319,14 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           P->shared_chunk.push_back((uint32_t)db);
           P->shared_chunk.push_back((uint32_t)len);
           P->shared_chunk.push_back(mask);
+          P->chunk_maxpatch.push_back(f.pb);
         }
         s = e;
       }
-      // per-node records for everything not covered by a chunk (ascending id):
-      // {node | flags, count, slot 0..5}; counts above 6 continue in SHARED_EXT at the
-      // offset stored in the last word ({extra slots...})
+      // per-node records for everything not covered by a chunk, ordered by the highest
+      // patch touching the node (then by id): {node | flags, count, slot 0..5}; counts above
+      // 6 continue in SHARED_EXT at the offset stored in the last word ({extra slots...})
+      std::vector<std::pair<int32_t, int64_t>> rec_order;  // (highest patch, shared index)
       size_t pi = 0;
       for (int64_t i = 0; i < n_shared; ++i) {
         const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
@@ -328,6 +334,12 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           const bool t = taken[pi++] != 0;
           if (t) continue;
         }
+        rec_order.emplace_back(patch_of_slot[P->shared_slot[j0 + cnt - 1]], i);
+      }
+      std::sort(rec_order.begin(), rec_order.end());
+      for (const auto &ro : rec_order) {
+        const int64_t i = ro.second;
+        const int32_t j0 = P->shared_ptr[i], cnt = P->shared_ptr[i + 1] - j0;
         uint32_t r[8] = {P->shared_node[i], (uint32_t)cnt, 0, 0, 0, 0, 0, 0};
         if (cnt <= 6) {
           for (int32_t j = 0; j < cnt; ++j) r[2 + j] = (uint32_t)P->shared_slot[j0 + j];
@@ -338,6 +350,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
             P->shared_ext.push_back((uint32_t)P->shared_slot[j]);
         }
         P->shared_rec.insert(P->shared_rec.end(), r, r + 8);
+        P->rec_maxpatch.push_back(ro.first);
       }
       if (P->shared_ext.empty()) P->shared_ext.push_back(0);
       if (P->shared_rec.empty()) P->shared_rec.assign(8, 0xffffffffu);
@@ -370,9 +383,13 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       for (int64_t p = 0; p < n_patch; ++p) {
         const int32_t nn = P->patch_nnodes[p];
         const uint32_t *src = P->pnode.data() + P->patch_node_ptr[p];
-        uint32_t base = SEMK_NODE_ID_MASK;
-        for (int32_t k = 0; k < nn; ++k) base = std::min(base, src[k] & SEMK_NODE_ID_MASK);
+        uint32_t base = SEMK_NODE_ID_MASK, top = 0;
+        for (int32_t k = 0; k < nn; ++k) {
+          base = std::min(base, src[k] & SEMK_NODE_ID_MASK);
+          top = std::max(top, src[k] & SEMK_NODE_ID_MASK);
+        }
         if (nn == 0) base = 0;
+        P->patch_maxnode.push_back(top);
         std::fill(pblk.begin(), pblk.end(), 0xffffffffu);
         for (int32_t k = 0; k < nn; ++k)
           pblk[k] = ((src[k] & SEMK_NODE_ID_MASK) - base) | (src[k] & ~SEMK_NODE_ID_MASK);
@@ -469,6 +486,9 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
     case SEMK_PA_SHARED_CHUNK: return vec_ptr(plan->shared_chunk, n_bytes);
     case SEMK_PA_PATCH_HDR: return vec_ptr(plan->patch_hdr, n_bytes);
+    case SEMK_PA_PATCH_MAXNODE: return vec_ptr(plan->patch_maxnode, n_bytes);
+    case SEMK_PA_CHUNK_MAXPATCH: return vec_ptr(plan->chunk_maxpatch, n_bytes);
+    case SEMK_PA_REC_MAXPATCH: return vec_ptr(plan->rec_maxpatch, n_bytes);
     default: return nullptr;
   }
 }

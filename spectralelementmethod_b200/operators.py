@@ -175,6 +175,12 @@ class PoissonOperator(object):
         t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
         self._tables = t
+        # what the staged host apply needs to cut the patch sequence into stages
+        hdr = ar[_lib.PA_PATCH_HDR].reshape(-1, 8)
+        self._stage_info = (hdr[:, 4].astype(np.int64), ar[_lib.PA_PATCH_MAXNODE].astype(np.int64),
+                            ar[_lib.PA_CHUNK_MAXPATCH][:sc[_lib.PS_N_SHARED_CHUNK]].astype(np.int64),
+                            ar[_lib.PA_REC_MAXPATCH][:sc[_lib.PS_N_SHARED_REC]].astype(np.int64))
+        self._stage_cache = {}
         self.elem_of_slot_host = ar[_lib.PA_ELEM_OF_SLOT]
         self.n_slot_elems = sc[_lib.PS_N_SLOT_ELEMS]
         self.n_patch = sc[_lib.PS_N_PATCH]
@@ -297,11 +303,45 @@ class PoissonOperator(object):
             device.ptr(y), int(flags), device.stream_ptr()))
         return y
 
-    def apply_host(self, u_host, y_host, scratch=None):
+    def stage_table(self, n_stages):
+        """Cut the patch sequence into ``n_stages`` equal runs and tabulate, per
+        stage, what it needs and what it completes (``semk_stage``):
+        interface chunks / records whose highest patch is done, the prefix of
+        u its patches read, the prefix of y that is final afterwards."""
+        n_stages = max(1, min(int(n_stages), 64, self.n_patch))
+        if n_stages in self._stage_cache:
+            return self._stage_cache[n_stages]
+        pmin, pmax, cmax, rmax = self._stage_info
+        ends = (np.arange(1, n_stages + 1, dtype=np.int64) * self.n_patch) // n_stages
+        need = np.maximum.accumulate(pmax) + 1                   # u read by patches [0, p]
+        # smallest node id still touched by a patch >= p (n_nodes past the end)
+        open_from = np.append(np.minimum.accumulate(pmin[::-1])[::-1], self.n_nodes)
+        arr = (_lib.semk_stage * n_stages)()
+        for i, pe in enumerate(ends.tolist()):
+            last = i == n_stages - 1
+            arr[i].patch_end = pe
+            arr[i].chunk_end = int(np.searchsorted(cmax, pe, side="left"))
+            arr[i].rec_end = int(np.searchsorted(rmax, pe, side="left"))
+            arr[i].u_need = self.n_nodes if last else int(need[pe - 1])
+            arr[i].y_final = self.n_nodes if last else int(open_from[pe])
+        self._stage_cache[n_stages] = (arr, n_stages)
+        return self._stage_cache[n_stages]
+
+    def apply_host(self, u_host, y_host, scratch=None, stages=16):
         """End-to-end call on HOST buffers (numpy float64 or pinned torch CPU
-        tensors): H2D copy, apply, D2H copy, synchronised on return."""
+        tensors): H2D copy, apply, D2H copy, synchronised on return.  With
+        ``stages`` > 1 the three phases are pipelined over that many runs of
+        patches (upload of the next run and download of the previous one
+        overlap the compute; semk_poisson_apply_host_staged_f64)."""
         if scratch is None:
             scratch = (self.new_vector(), self.new_vector())
+        if stages and stages > 1:
+            arr, n = self.stage_table(stages)
+            _lib.check(self._lib.semk_poisson_apply_host_staged_f64(
+                C.byref(self._op), arr, n, device.ptr(u_host), device.ptr(y_host),
+                device.ptr(scratch[0]), device.ptr(scratch[1]), int(self._masked_flags),
+                device.stream_ptr()))
+            return y_host
         _lib.check(self._lib.semk_poisson_apply_host_f64(
             C.byref(self._op), device.ptr(u_host), device.ptr(y_host), device.ptr(scratch[0]),
             device.ptr(scratch[1]), int(self._masked_flags), device.stream_ptr()))

@@ -192,6 +192,21 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         assert g not in seen
         seen[g] = (lst, bool(r[0] & _lib.NODE_DIRICHLET))
     assert seen == want
+    # both interface tables are sorted by the highest patch involved (staged host apply)
+    slot_patch = np.searchsorted(base, np.arange(slots_seen), side="right") - 1
+    cmax, rmax = ar[_lib.PA_CHUNK_MAXPATCH][:nch], ar[_lib.PA_REC_MAXPATCH][:nrec]
+    assert cmax.size == nch and rmax.size == nrec
+    assert np.all(np.diff(cmax) >= 0) and np.all(np.diff(rmax) >= 0)
+    for c, (node0, dn, a0, da, b0, db, ln, mask) in zip(cmax.tolist(), chunk.tolist()):
+        dn, da, db = ((v - (1 << 32) if v >= (1 << 31) else v) for v in (dn, da, db))
+        assert c == slot_patch[b0] == slot_patch[b0 + (ln - 1) * db] > slot_patch[a0]
+    for c, r in zip(rmax.tolist(), rec.tolist()):
+        cnt = r[1]
+        lst = r[2:2 + cnt] if cnt <= 6 else r[2:7] + ext[r[7]:r[7] + cnt - 5].tolist()
+        assert c == slot_patch[lst[-1]]
+    pmax = ar[_lib.PA_PATCH_MAXNODE]
+    for p in range(n_patch):
+        assert pmax[p] == ids[ptr[p]:ptr[p] + nnodes[p]].max()
     for lst, _ in want.values():
         assert lst == sorted(lst) and len(lst) >= 2
 
