@@ -731,6 +731,7 @@ class Mesh(object):
         self._pending = []         # (geometry_id, region_id, node_map) not yet consolidated
         self._n_cells = 0
         self._adj_map = {}         # cell -> list (created lazily)
+        self._adj_array = None     # int64[E, faces], -1 = none (set in bulk by the importer)
         self._region_names = []
         self._region_id_lookup = {}
         self._boundary_names = []
@@ -864,7 +865,13 @@ class Mesh(object):
         blk = self._blocks[b]
         k = i - self._block_start[b]
         geo = self._geometries[blk.geometry_id]
-        adj = self._adj_map.setdefault(i, [None] * geo.n_sub_geometries())
+        adj = self._adj_map.get(i)
+        if adj is None:
+            if self._adj_array is not None:
+                adj = [None if v < 0 else int(v) for v in self._adj_array[i]]
+            else:
+                adj = [None] * geo.n_sub_geometries()
+            self._adj_map[i] = adj
         return Cell(self, geo, blk.node_maps[k], int(blk.region_ids[k]), adj,
                     self._boundary_map.get(i, {}))
 

@@ -75,3 +75,63 @@ def structured_quad_mesh(nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0), nod
         mesh.add_boundary_cells(cell[:, -1], nbc, 1, 3)
     mesh._structured_shape = (nx, ny)
     return mesh
+
+
+def write_gmsh22_binary(path, nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0), shuffle_seed=None):
+    """Write the structured mesh of ``structured_quad_mesh`` as a Gmsh 2.2
+    *binary* ``.msh`` file (the format sem/grid_importers.py:45-218 reads):
+    physical names 1 "ebc" and 2 "nbc" (lines: left + bottom / right + top)
+    and 3 "interior" (quadrilaterals); high-order line and quadrilateral
+    elements in Gmsh's node ordering.  ``shuffle_seed`` permutes the element
+    order inside each block and the node numbering (a mesh generator gives no
+    ordering guarantees).  Test / example helper; p <= 10."""
+    from .grid_importers import GMSH_LINE_TYPES, GMSH_QUAD_TYPES, gmsh_to_lexicographic
+    n1 = p + 1
+    line_type = {v: k for k, v in GMSH_LINE_TYPES.items()}[n1]
+    quad_type = {v: k for k, v in GMSH_QUAD_TYPES.items()}[n1]
+    xy = lattice_coordinates(kind, nx, ny, p, bounds)
+    n_nodes = xy.shape[1]
+    maps = structured_node_maps(nx, ny, p).reshape(nx * ny, n1, n1).astype(np.int64)
+    cell = np.arange(nx * ny).reshape(nx, ny)
+    # boundary lines as (node ids along the face in the face's lexicographic order, phys id)
+    lines, phys = [], []
+    for cells, take, tag in ((cell[0, :], lambda m: m[:, 0, :], 1), (cell[:, 0], lambda m: m[:, :, 0], 1),
+                             (cell[-1, :], lambda m: m[:, -1, :], 2), (cell[:, -1], lambda m: m[:, :, -1], 2)):
+        lines.append(take(maps[cells]))
+        phys.append(np.full(len(cells), tag))
+    lines, phys = np.concatenate(lines), np.concatenate(phys)
+    perm = np.arange(n_nodes)
+    if shuffle_seed is not None:
+        rng = np.random.default_rng(shuffle_seed)
+        perm = rng.permutation(n_nodes)                 # new id of old node k
+        order = rng.permutation(len(lines))
+        lines, phys = lines[order], phys[order]
+        maps = maps[rng.permutation(len(maps))]
+    inv_line = np.argsort(gmsh_to_lexicographic((n1,)))           # gmsh position -> lexicographic
+    inv_quad = np.argsort(gmsh_to_lexicographic((n1, n1)))
+    coords = np.zeros((n_nodes, 3))
+    coords[perm, :2] = xy.T
+    with open(path, "wb") as f:
+        f.write(b"$MeshFormat\n2.2 1 8\n" + np.array([1], dtype="<i4").tobytes() + b"\n$EndMeshFormat\n")
+        f.write(b'$PhysicalNames\n3\n1 1 "ebc"\n1 2 "nbc"\n2 3 "interior"\n$EndPhysicalNames\n')
+        f.write(b"$Nodes\n%d\n" % n_nodes)
+        rec = np.empty(n_nodes, dtype=[("index", "<i4"), ("coord", "<f8", (3,))])
+        rec["index"] = np.arange(1, n_nodes + 1)
+        rec["coord"] = coords
+        f.write(rec.tobytes() + b"\n$EndNodes\n")
+        f.write(b"$Elements\n%d\n" % (len(lines) + len(maps)))
+        first = 1
+        for etype, node_ix, tag in ((line_type, perm[lines][:, inv_line], phys),
+                                    (quad_type, perm[maps.reshape(len(maps), -1)][:, inv_quad],
+                                     np.full(len(maps), 3))):
+            f.write(np.array([etype, len(node_ix), 2], dtype="<i4").tobytes())
+            rec = np.empty(len(node_ix), dtype=[("index", "<u4"), ("tags", "<u4", (2,)),
+                                                ("node_ix", "<u4", (node_ix.shape[1],))])
+            rec["index"] = np.arange(first, first + len(node_ix))
+            rec["tags"][:, 0] = tag
+            rec["tags"][:, 1] = tag
+            rec["node_ix"] = node_ix + 1
+            f.write(rec.tobytes())
+            first += len(node_ix)
+        f.write(b"\n$EndElements\n")
+    return path
