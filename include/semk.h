@@ -107,15 +107,25 @@ enum semk_plan_array {
                                  {node0, dn, a0, da, b0, db, len, Dirichlet mask};
                                  node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
   SEMK_PA_PATCH_HDR = 16,     /* uint32 [n_patch][8]  {n nodes, n private, first interface slot, 0,
-                                 base node id, PNBLK block, ELBLK block, 0}                   */
+                                 base node id, PNBLK block, ELBLK block, INVBLK block}        */
   SEMK_PA_PATCH_MAXNODE = 17, /* uint32 [n_patch]     largest node id of the patch (the smallest is
                                  PATCH_HDR word 4)                                            */
   SEMK_PA_CHUNK_MAXPATCH = 18,/* int32  [n_shared_chunk] higher of the two patches of a chunk; the
                                  chunk table is sorted by it                                  */
   SEMK_PA_REC_MAXPATCH = 19,  /* int32  [n_shared_rec]   highest patch touching a record's node; the
                                  record table is sorted by it (then by node id)               */
-  SEMK_PA_COUNT = 20
+  SEMK_PA_INVBLK = 20,        /* uint16 [n_inv_unique][inv_stride] inverse tables: for patch node k the
+                                 entries [k*inv_width, (k+1)*inv_width) are the positions of
+                                 its element-local contributions in the CTA's transposition
+                                 scratch (m*RS + le*n1 + t, RS = semk_scratch_row_stride),
+                                 ascending element slot, 0xffff padded; deduplicated
+                                 (PATCH_HDR word 7)                                           */
+  SEMK_PA_COUNT = 21
 };
+
+/* Row stride (doubles) of the patch kernel's transposition scratch: rows of
+ * n1*PE thread-indexed entries padded so that the stride is 1 (mod 16). */
+int semk_scratch_row_stride(int n1, int elems_per_patch);
 
 enum semk_plan_scalar {
   SEMK_PS_N_PATCH = 0,
@@ -132,7 +142,10 @@ enum semk_plan_scalar {
   SEMK_PS_N_SHARED_REC = 11,  /* number of per-node interface records                          */
   SEMK_PS_N_PN_UNIQUE = 12,   /* distinct node blocks in PNBLK                                 */
   SEMK_PS_N_EL_UNIQUE = 13,   /* distinct index blocks in ELBLK                                */
-  SEMK_PS_COUNT = 14
+  SEMK_PS_N_INV_UNIQUE = 14,  /* distinct inverse blocks in INVBLK                              */
+  SEMK_PS_INV_WIDTH = 15,     /* contributions stored per node (multiple of 4; 4 = structured)   */
+  SEMK_PS_INV_STRIDE = 16,    /* uint16 entries per inverse block = PN_STRIDE * INV_WIDTH        */
+  SEMK_PS_COUNT = 17
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
@@ -171,6 +184,9 @@ typedef struct semk_op {
   int64_t pn_patch_stride;  /* uint32 entries per node block (multiple of 4)             */
   const uint16_t *eloc;     /* [n_el_unique][eloc_patch_stride] index blocks (SEMK_PA_ELBLK) */
   int64_t eloc_patch_stride;/* uint16 entries per index block (multiple of 8)            */
+  const uint16_t *inv;      /* [n_inv_unique][inv_patch_stride] inverse blocks (SEMK_PA_INVBLK) */
+  int64_t inv_patch_stride; /* uint16 entries per inverse block (SEMK_PS_INV_STRIDE)      */
+  int64_t inv_width;        /* SEMK_PS_INV_WIDTH                                           */
   int64_t n_slots;
   double *slot_buf;         /* [n_slots] interface partial sums, contiguous per patch (scratch) */
   int64_t n_shared;           /* number of per-node interface records                        */
@@ -190,11 +206,11 @@ int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
  * configuration = the grid of the persistent kernel; <0 on error */
 int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
                            int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                           int max_patch_nodes);
+                           int64_t inv_patch_stride);
 /* dynamic shared memory (bytes) one CTA of the apply kernel needs */
 int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                               int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                              int max_patch_nodes);
+                              int64_t inv_patch_stride);
 
 /* ------------------------------------------------------------------------
  * K1: geometric factors.  Replaces, per element, Mapping._compute_x_phys /

@@ -22,11 +22,12 @@ MAX_N1 = 17
 (PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
  PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT, PA_SHARED_CHUNK,
- PA_PATCH_HDR, PA_PATCH_MAXNODE, PA_CHUNK_MAXPATCH, PA_REC_MAXPATCH) = range(20)
+ PA_PATCH_HDR, PA_PATCH_MAXNODE, PA_CHUNK_MAXPATCH, PA_REC_MAXPATCH, PA_INVBLK) = range(21)
 (PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
  PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE, PS_N_SHARED_CHUNK,
- PS_N_SHARED_REC, PS_N_PN_UNIQUE, PS_N_EL_UNIQUE) = range(14)
-PS_COUNT = 14
+ PS_N_SHARED_REC, PS_N_PN_UNIQUE, PS_N_EL_UNIQUE, PS_N_INV_UNIQUE, PS_INV_WIDTH,
+ PS_INV_STRIDE) = range(17)
+PS_COUNT = 17
 
 PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
@@ -35,7 +36,7 @@ PLAN_ARRAY_DTYPES = {
     PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
     PA_ELBLK: np.uint16, PA_SHARED_REC: np.uint32, PA_SHARED_EXT: np.uint32,
     PA_SHARED_CHUNK: np.uint32, PA_PATCH_HDR: np.uint32, PA_PATCH_MAXNODE: np.uint32,
-    PA_CHUNK_MAXPATCH: np.int32, PA_REC_MAXPATCH: np.int32,
+    PA_CHUNK_MAXPATCH: np.int32, PA_REC_MAXPATCH: np.int32, PA_INVBLK: np.uint16,
 }
 
 
@@ -58,6 +59,7 @@ class semk_op(C.Structure):
         ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
         ("patch_hdr", C.c_void_p), ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
+        ("inv", C.c_void_p), ("inv_patch_stride", C.c_int64), ("inv_width", C.c_int64),
         ("n_slots", C.c_int64), ("slot_buf", C.c_void_p),
         ("n_shared", C.c_int64), ("shared_rec", C.c_void_p), ("shared_ext", C.c_void_p),
         ("n_shared_chunk", C.c_int64), ("shared_chunk", C.c_void_p),
@@ -87,8 +89,8 @@ SIGNATURES = {
     "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
     "semk_hostplan_destroy": (None, [_P]),
     "semk_partials_len": (_L, [_L, _L]),
-    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _L, _I]),
-    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _L, _I]),
+    "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _L, _L]),
+    "semk_resident_ctas": (_L, [_I, _I, _L, _L, _L, _L]),
     "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P,
                                    _P, _P, _P, _P]),
     "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _I, _P]),
@@ -108,6 +110,7 @@ SIGNATURES = {
                                 C.POINTER(semk_pcg_info), _P]),
     "semk_poisson_apply_host_staged_f64": (_I, [C.POINTER(semk_op), C.POINTER(semk_stage), _I, _P, _P,
                                                 _P, _P, _I, _P]),
+    "semk_scratch_row_stride": (_I, [_I, _I]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
     "semk_peer_open": (_I, [_P, C.POINTER(_P)]),

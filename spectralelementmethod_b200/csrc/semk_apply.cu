@@ -177,7 +177,7 @@ __device__ __forceinline__ void mat_Dt(const DMatEO &dm, const double (&v)[N], d
 //   column pattern  A[m*RS + tidp]          -> bank = const + tidp
 //   row pattern     A[t*RS + le*N + s]      -> bank = const + t + le*N = const + tidp
 __host__ __device__ constexpr int scratch_row_stride(int N, int PE) {
-  return ((N * PE - 1 + 15) & ~15) + 1;
+  return ((N * PE - 1 + 15) & ~15) + 1;  // == semk_scratch_row_stride (include/semk.h)
 }
 
 // The element-local operator for one column-owning thread.
@@ -262,17 +262,16 @@ enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
 // the working arrays.
 struct PatchSmem {
   size_t hdr, gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
-  size_t yp, ua, bs, red, total;
+  size_t inv, ua, bs, red, total;
 };
 __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
                                                        int64_t g_patch_stride,
                                                        int64_t pn_patch_stride,
                                                        int64_t eloc_patch_stride,
-                                                       int max_patch_nodes) {
+                                                       int64_t inv_patch_stride) {
   PatchSmem L;
-  const size_t mpn4 = ((size_t)max_patch_nodes + 3) & ~(size_t)3;
   const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
-  size_t o = 32;  // three mbarriers: tables[2], G
+  size_t o = 32;  // four mbarriers: tables[2], G, inverse table
   L.hdr = o;      // two 32-byte patch headers (ring)
   o += 64;
   L.gs = o;
@@ -285,15 +284,15 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
   st = (st + 15) & ~(size_t)15;
   L.stage_bytes = st;
   o += 2 * st;
-  L.yp = o;
-  o += 8 * mpn4;
+  L.inv = o;  // inverse table of the patch being written out (single buffer)
+  o += 2 * (size_t)inv_patch_stride;
   o = (o + 15) & ~(size_t)15;
   L.ua = o;  // scratch A
   o += (mode == MODE_APPLY) ? 8 * scratch : 0;
   o = (o + 15) & ~(size_t)15;
-  L.bs = o;  // scratch B; its head doubles as the block-reduction scratch at the very end
-  const size_t bsz = (mode == MODE_APPLY) ? 8 * scratch : 0;
-  o += bsz > 256 ? bsz : 256;
+  L.bs = o;  // scratch B: the element results the write-out gathers from; its head doubles
+             // as the block-reduction scratch at the very end
+  o += 8 * scratch > 256 ? 8 * scratch : 256;
   L.red = L.bs;
   L.total = o;
   return L;
@@ -345,10 +344,10 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   constexpr int RS = PatchCfg<N, PE>::kRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PatchSmem L = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
-                                        op.eloc_patch_stride, op.max_patch_nodes);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2]: G
+                                        op.eloc_patch_stride, op.inv_patch_stride);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);  // [0..1]: tables, [2]: G, [3]: inv
   double *Gs = reinterpret_cast<double *>(smem_raw + L.gs);
-  double *yp = reinterpret_cast<double *>(smem_raw + L.yp);
+  const uint16_t *inv_s = reinterpret_cast<const uint16_t *>(smem_raw + L.inv);
   double *As = reinterpret_cast<double *>(smem_raw + L.ua);
   double *Bs = reinterpret_cast<double *>(smem_raw + L.bs);
   double *red = reinterpret_cast<double *>(smem_raw + L.red);
@@ -358,6 +357,8 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   const uint32_t pn_bytes = 4u * (uint32_t)op.pn_patch_stride;
   const uint32_t el_bytes = 2u * (uint32_t)op.eloc_patch_stride;
   const uint32_t g_bytes = (uint32_t)(op.g_patch_stride * sizeof(double));
+  const uint32_t inv_bytes = 2u * (uint32_t)op.inv_patch_stride;
+  const int inv_w4 = (int)(op.inv_width >> 2);  // 8-byte groups of inverse entries per node
 
   auto stage_ptr = [&](int s) { return smem_raw + L.stage0 + (size_t)s * L.stage_bytes; };
   // Patch headers travel two patches ahead through a 2-entry ring: the header of patch
@@ -374,6 +375,14 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     semk_bulk_g2s(base + L.el_off, op.eloc + (int64_t)ei * op.eloc_patch_stride, el_bytes, &mbar[s]);
     if (more) semk_bulk_g2s(hdr_ring + 8 * slot_after, op.patch_hdr + 8 * patch_after, 32u, &mbar[s]);
   };
+  // The inverse table is single-buffered: patch i's table is fetched right after the
+  // first barrier of patch i (when every thread has left patch i-1's write-out, its last
+  // reader) and is first needed five barriers later, in patch i's own write-out.
+  auto issue_inv = [&](uint32_t block) {  // one thread
+    semk_mbar_expect_tx(&mbar[3], inv_bytes);
+    semk_bulk_g2s(smem_raw + L.inv, op.inv + (int64_t)block * op.inv_patch_stride, inv_bytes,
+                  &mbar[3]);
+  };
   auto issue_g = [&](int64_t patch) {  // one thread
     semk_mbar_expect_tx(&mbar[2], g_bytes);
     semk_bulk_g2s(Gs, op.G + patch * op.g_patch_stride, g_bytes, &mbar[2]);
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
   const int64_t p_end = patch_end;  // (a sub-range of the patches: staged host apply)
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) semk_mbar_init(&mbar[i], 1);
+    for (int i = 0; i < 4; ++i) semk_mbar_init(&mbar[i], 1);
     semk_fence_mbar_init();
     if (p_first < p_end) {
       // the first header is read directly (block indices needed right now) and also
@@ -432,7 +441,6 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       }
     }
   };
-  for (int k = tid; k < op.max_patch_nodes; k += kThreads) yp[k] = 0.0;
   if (MODE == MODE_APPLY && p_first < p_end) {
     semk_mbar_wait(&mbar[0], 0);
     gather_column(0, p_first);
@@ -449,25 +457,16 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
     const bool has_next = next < p_end;
     unsigned char *sb = stage_ptr(s);
     const uint32_t *pn_s = reinterpret_cast<const uint32_t *>(sb + L.pn_off);
-    const uint16_t *el_s = reinterpret_cast<const uint16_t *>(sb + L.el_off);
     semk_mbar_wait(&mbar[s], par);
     const uint32_t *hdr = hdr_ring + 8 * s;  // read before this patch's first barrier
     const int npn = (int)hdr[0];
     const int npriv = (int)hdr[1];
     const int slot_base = (int)hdr[2];
     const uint32_t id0 = hdr[4];
+    const uint32_t inv_block = hdr[7];
     const int64_t slot0 = patch * PE;
     const bool active = (le < PE) && (slot0 + le < op.n_elem);
 
-    // this thread's column of patch-local node indices (table rows are [m][le][t]),
-    // and the colour of its element (stored behind the table)
-    uint16_t idx[N];
-    int color = 255;
-    if (active) {
-#pragma unroll
-      for (int m = 0; m < N; ++m) idx[m] = el_s[m * NP + tid];
-      color = el_s[NN * PE + le];
-    }
 
     double ycol[N];
     if (MODE == MODE_APPLY) {
@@ -485,6 +484,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       // Table stage s^1 (patch i-1's tables) is free once every thread has passed the
       // first barrier of this patch's operator: no end-of-patch barrier is needed.
       auto refill_tables = [&]() {
+        if (tid == 0) issue_inv(inv_block);
         if (tid == 0 && has_next) {
           const uint32_t *hn = hdr_ring + 8 * (s ^ 1);  // header of the next patch
           const int64_t after = next + step;
@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       }
     } else {
       __syncthreads();  // previous patch's write-out done: its table stage may be refilled
+      if (tid == 0) issue_inv(inv_block);
       if (tid == 0 && has_next) {
         const uint32_t *hn = hdr_ring + 8 * (s ^ 1);
         const int64_t after = next + step;
@@ -522,27 +523,53 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       }
     }
 
-    // ---- assemble inside the patch, colour by colour (no atomics) -------------
-    for (int c = 0; c < op.max_colors; ++c) {
-      if (active && color == c) {
+    // ---- assemble by GATHERING (no atomics, no colour phases): every thread leaves its
+    // column of element results in scratch B (its own entries, the ones it just read),
+    // then each patch node sums its <= inv_width contributions in a fixed order (ascending
+    // element slot) straight from B and is stored: private nodes -> y, shared nodes ->
+    // interface slots ------------------------------------------------------------------
+    if (active) {
 #pragma unroll
-        for (int m = 0; m < N; ++m) yp[idx[m]] += ycol[m];
-      }
-      __syncthreads();
+      for (int m = 0; m < N; ++m) Bs[m * RS + le * N + t] = ycol[m];
     }
-
-    // ---- write out: private nodes -> y, shared nodes -> interface slots; the
-    // accumulator is cleared for the next patch on the way --------------------------
+    semk_mbar_wait(&mbar[3], (uint32_t)(it & 1));  // this patch's inverse table has landed
+    __syncthreads();
     for (int k0 = tid; k0 < npn; k0 += kGatherBatch * kThreads) {
       uint32_t pnv[kGatherBatch];
-      double vv[kGatherBatch];
+      uint2 ev[kGatherBatch];
 #pragma unroll
       for (int j = 0; j < kGatherBatch; ++j) {
         const int k = k0 + j * kThreads;
         const bool in = k < npn;
         pnv[j] = in ? pn_s[k] : 0xffffffffu;
-        vv[j] = in ? yp[k] : 0.0;
-        if (in) yp[k] = 0.0;
+        ev[j] = in ? reinterpret_cast<const uint2 *>(inv_s)[(size_t)k * inv_w4]
+                   : make_uint2(0xffffffffu, 0xffffffffu);
+      }
+      double vv[kGatherBatch];
+#pragma unroll
+      for (int j = 0; j < kGatherBatch; ++j) {
+        // (every listed node has at least one contribution)
+        const uint32_t e0 = ev[j].x & 0xffffu, e1 = ev[j].x >> 16;
+        const uint32_t e2 = ev[j].y & 0xffffu, e3 = ev[j].y >> 16;
+        double v = (e0 != 0xffffu) ? Bs[e0] : 0.0;
+        if (e1 != 0xffffu) v += Bs[e1];
+        if (e2 != 0xffffu) v += Bs[e2];
+        if (e3 != 0xffffu) v += Bs[e3];
+        vv[j] = v;
+      }
+      if (inv_w4 > 1) {  // irregular meshes: more than four elements of the patch at a node
+#pragma unroll
+        for (int j = 0; j < kGatherBatch; ++j) {
+          const int k = k0 + j * kThreads;
+          if (k >= npn) continue;
+          for (int w = 1; w < inv_w4; ++w) {
+            const uint2 e = reinterpret_cast<const uint2 *>(inv_s)[(size_t)k * inv_w4 + w];
+            const uint32_t q[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (q[i] != 0xffffu) vv[j] += Bs[q[i]];
+          }
+        }
       }
 #pragma unroll
       for (int j = 0; j < kGatherBatch; ++j) {
@@ -570,8 +597,9 @@ __global__ void __launch_bounds__(PatchCfg<N, PE>::kThreads, patch_min_blocks(N,
       }
     }
     // no barrier here: the next patch's first operator barrier orders this write-out
-    // (reads of stage s and of yp) before anything that could overwrite them
+    // (reads of stage s, of the inverse table and of B) before anything that overwrites them
   }
+  if (want_dot) __syncthreads();  // the reduction scratch aliases B: let the write-out finish
   if (want_dot) {
     const double sres = semk_block_sum(dot, red);
     if (tid == 0) dot_partials[blockIdx.x] = sres;
@@ -845,7 +873,7 @@ struct PatchLaunch {
                  double *y, int flags, double fill, double *partials, cudaStream_t st,
                  int *grid_out, int64_t pb, int64_t pe) {
     const size_t smem = patch_smem_layout(N, PE, MODE, op.g_patch_stride, op.pn_patch_stride,
-                                          op.eloc_patch_stride, op.max_patch_nodes)
+                                          op.eloc_patch_stride, op.inv_patch_stride)
                             .total;
     if (smem > 227 * 1024) {
       semk_set_error("patch kernel: shared memory request exceeds 227 KB");
@@ -912,7 +940,9 @@ int check_op(const semk_op *op, const char *who) {
     return SEMK_ERR_UNSUPPORTED;
   }
   const int64_t nnp = (int64_t)op->n1 * op->n1 * op->elems_per_patch;
-  if (!op->pnode || !op->eloc || !op->patch_hdr || (op->pn_patch_stride & 3) != 0 ||
+  if (!op->pnode || !op->eloc || !op->patch_hdr || !op->inv || (op->pn_patch_stride & 3) != 0 ||
+      op->inv_width < 4 || (op->inv_width & 3) != 0 ||
+      op->inv_patch_stride != op->pn_patch_stride * op->inv_width ||
       op->pn_patch_stride < op->max_patch_nodes ||
       (reinterpret_cast<uintptr_t>(op->patch_hdr) & 15u) != 0 ||
       (op->eloc_patch_stride & 7) != 0 ||
@@ -940,10 +970,10 @@ extern "C" int64_t semk_partials_len(int64_t n_patch, int64_t n_shared) {
 
 extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
                                       int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                                      int max_patch_nodes) {
+                                      int64_t inv_patch_stride) {
   if (!pe_supported(elems_per_patch)) return -1;
   const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                        pn_patch_stride, eloc_patch_stride, max_patch_nodes)
+                                        pn_patch_stride, eloc_patch_stride, inv_patch_stride)
                           .total;
   if (smem > 227 * 1024) return -1;
   int per_sm = 0, sms = 0;
@@ -969,9 +999,9 @@ extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_pat
 
 extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                                          int64_t pn_patch_stride, int64_t eloc_patch_stride,
-                                         int max_patch_nodes) {
+                                         int64_t inv_patch_stride) {
   return (int64_t)patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
-                                    pn_patch_stride, eloc_patch_stride, max_patch_nodes)
+                                    pn_patch_stride, eloc_patch_stride, inv_patch_stride)
       .total;
 }
 

@@ -35,11 +35,15 @@ struct semk_hostplan {
   std::vector<uint32_t> pnode, shared_node, pnblk, shared_rec, shared_ext, shared_chunk, patch_hdr,
       patch_maxnode;
   std::vector<int32_t> chunk_maxpatch, rec_maxpatch;
-  std::vector<uint16_t> elblk;
+  std::vector<uint16_t> elblk, invblk;
   std::vector<uint16_t> eloc;
   std::vector<uint8_t> elem_color;
   std::vector<int64_t> elem_of_slot;
 };
+
+extern "C" int semk_scratch_row_stride(int n1, int elems_per_patch) {
+  return ((n1 * elems_per_patch - 1 + 15) & ~15) + 1;  // == scratch_row_stride (semk_apply.cu)
+}
 
 extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
                                     const int64_t *elem_order, int elems_per_patch,
@@ -366,9 +370,36 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     // kernel's table reads become L2 hits instead of DRAM traffic.  The per-patch part
     // is an 8-word header
     //   {n nodes, n private, first slot, 0, base node id, node block index, index block
-    //    index, 0}.
+    //    index, inverse block index}.
     const int64_t pn_stride = (max_patch_nodes + 3) & ~(int64_t)3;
     const int64_t el_stride = ((int64_t)NN * PE + PE + 7) & ~(int64_t)7;
+    // Inverse tables for the gather-style assembly: for every patch node the positions
+    // of its element-local contributions inside the CTA's transposition scratch
+    // (row m, thread le*n1 + t -> m*RS + le*n1 + t), ascending element slot, 0xffff
+    // padded to INV_WIDTH = the largest number of elements of one patch meeting in a
+    // node, rounded up to a multiple of 4 (4 on a structured mesh).
+    const int RS = semk_scratch_row_stride(n1, PE);
+    if ((int64_t)(n1 - 1) * RS + (int64_t)PE * n1 > 0xfffe) {
+      delete P;
+      semk_set_error("semk_hostplan_create: scratch positions overflow 16 bits");
+      return SEMK_ERR_UNSUPPORTED;
+    }
+    int64_t inv_width = 4;
+    {
+      std::vector<int32_t> cnt(max_patch_nodes, 0);
+      for (int64_t p = 0; p < n_patch; ++p) {
+        const uint16_t *eb = P->eloc.data() + (size_t)p * ES;
+        const int64_t live = std::min<int64_t>(PE, n_elem - p * PE);
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int m = 0; m < n1; ++m)
+          for (int64_t le = 0; le < live; ++le)
+            for (int t = 0; t < n1; ++t) {
+              const int32_t c = ++cnt[eb[((size_t)m * PE + le) * n1 + t]];
+              if (c > inv_width) inv_width = (c + 3) & ~3;
+            }
+      }
+    }
+    const int64_t inv_stride = pn_stride * inv_width;  // uint16 entries per block
     P->patch_hdr.assign((size_t)n_patch * 8, 0u);
     {
       auto hash_bytes = [](const void *ptr, size_t n) {
@@ -377,9 +408,10 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
         return h;
       };
-      std::unordered_multimap<uint64_t, int32_t> pn_seen, el_seen;
+      std::unordered_multimap<uint64_t, int32_t> pn_seen, el_seen, inv_seen;
       std::vector<uint32_t> pblk(pn_stride);
-      std::vector<uint16_t> eblk(el_stride);
+      std::vector<uint16_t> eblk(el_stride), iblk(inv_stride);
+      std::vector<int32_t> fill(max_patch_nodes, 0);
       for (int64_t p = 0; p < n_patch; ++p) {
         const int32_t nn = P->patch_nnodes[p];
         const uint32_t *src = P->pnode.data() + P->patch_node_ptr[p];
@@ -410,8 +442,20 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           seen.emplace(h, idx);
           return idx;
         };
+        std::fill(iblk.begin(), iblk.end(), (uint16_t)0xffff);
+        std::fill(fill.begin(), fill.end(), 0);
+        {
+          const int64_t live = std::min<int64_t>(PE, n_elem - p * PE);
+          for (int64_t le = 0; le < live; ++le)      // ascending element slot: fixed sum order
+            for (int m = 0; m < n1; ++m)
+              for (int t = 0; t < n1; ++t) {
+                const int32_t loc = eblk[((size_t)m * PE + le) * n1 + t];
+                iblk[(size_t)loc * inv_width + fill[loc]++] = (uint16_t)(m * RS + le * n1 + t);
+              }
+        }
         const int32_t pi = find_or_add(pn_seen, P->pnblk, pblk, pn_stride);
         const int32_t ei = find_or_add(el_seen, P->elblk, eblk, el_stride);
+        const int32_t ii = find_or_add(inv_seen, P->invblk, iblk, inv_stride);
         uint32_t *h = P->patch_hdr.data() + (size_t)p * 8;
         h[0] = (uint32_t)nn;
         h[1] = (uint32_t)P->patch_npriv[p];
@@ -419,11 +463,15 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         h[4] = base;
         h[5] = (uint32_t)pi;
         h[6] = (uint32_t)ei;
+        h[7] = (uint32_t)ii;
       }
     }
     P->scalars[SEMK_PS_N_PN_UNIQUE] = (int64_t)(P->pnblk.size() / (size_t)pn_stride);
     P->scalars[SEMK_PS_N_EL_UNIQUE] = (int64_t)(P->elblk.size() / (size_t)el_stride);
     P->scalars[SEMK_PS_PN_STRIDE] = pn_stride;
+    P->scalars[SEMK_PS_N_INV_UNIQUE] = (int64_t)(P->invblk.size() / (size_t)inv_stride);
+    P->scalars[SEMK_PS_INV_WIDTH] = inv_width;
+    P->scalars[SEMK_PS_INV_STRIDE] = inv_stride;
     {
       // counts of the interface tables (the vectors hold one dummy entry when empty)
       int64_t n_chunk = 0, n_rec = 0;
@@ -486,6 +534,7 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_SHARED_EXT: return vec_ptr(plan->shared_ext, n_bytes);
     case SEMK_PA_SHARED_CHUNK: return vec_ptr(plan->shared_chunk, n_bytes);
     case SEMK_PA_PATCH_HDR: return vec_ptr(plan->patch_hdr, n_bytes);
+    case SEMK_PA_INVBLK: return vec_ptr(plan->invblk, n_bytes);
     case SEMK_PA_PATCH_MAXNODE: return vec_ptr(plan->patch_maxnode, n_bytes);
     case SEMK_PA_CHUNK_MAXPATCH: return vec_ptr(plan->chunk_maxpatch, n_bytes);
     case SEMK_PA_REC_MAXPATCH: return vec_ptr(plan->rec_maxpatch, n_bytes);

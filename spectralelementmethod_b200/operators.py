@@ -47,15 +47,17 @@ def pn_patch_stride_of(max_patch_nodes):
     return (int(max_patch_nodes) + 3) & ~3   # node list, 16-byte multiples
 
 
-def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None):
+def patch_smem_bytes(n1, pe, max_patch_nodes, pn_stride=None, inv_stride=None):
     """Dynamic shared memory of one CTA of the apply kernel (asks the library,
     which owns the layout: csrc/semk_apply.cu patch_smem_layout)."""
     if pn_stride is None:
         pn_stride = pn_patch_stride_of(max_patch_nodes)
+    if inv_stride is None:
+        inv_stride = 4 * pn_stride          # inverse table, 4 contributions per node
     return int(_lib.load().semk_patch_smem_bytes(n1, pe, g_patch_stride_of(n1, pe),
                                                  int(pn_stride),
                                                  eloc_patch_stride_of(n1, pe),
-                                                 int(max_patch_nodes)))
+                                                 int(inv_stride)))
 
 
 def choose_elems_per_patch(n1):
@@ -158,14 +160,15 @@ class PoissonOperator(object):
         sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
         actual = int(self._lib.semk_resident_ctas(
             n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
-            int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_MAX_PATCH_NODES])))
+            int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_INV_STRIDE])))
         if actual <= 0:
             raise NotImplementedError(
                 "patch of %d elements does not fit in shared memory (%s); pass a smaller "
                 "elems_per_patch or a more local elem_order" % (pe, _lib.last_error()))
         self.plan_scalars = sc
         self.resident_ctas = actual
-        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE])
+        smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE],
+                                sc[_lib.PS_INV_STRIDE])
         self.smem_bytes = smem
 
         t = {}
@@ -173,6 +176,7 @@ class PoissonOperator(object):
                   _lib.PA_SHARED_CHUNK):
             t[k] = device.as_i32_bits(ar[k], self.dev)
         t[_lib.PA_ELBLK] = torch.from_numpy(ar[_lib.PA_ELBLK].view(np.int16)).to(self.dev)
+        t[_lib.PA_INVBLK] = torch.from_numpy(ar[_lib.PA_INVBLK].view(np.int16)).to(self.dev)
         t[_lib.PA_ELEM_OF_SLOT] = torch.from_numpy(ar[_lib.PA_ELEM_OF_SLOT]).to(self.dev)
         self._tables = t
         # what the staged host apply needs to cut the patch sequence into stages
@@ -233,6 +237,9 @@ class PoissonOperator(object):
         op.pn_patch_stride = sc[_lib.PS_PN_STRIDE]
         op.eloc = t[_lib.PA_ELBLK].data_ptr()
         op.eloc_patch_stride = sc[_lib.PS_EL_STRIDE]
+        op.inv = t[_lib.PA_INVBLK].data_ptr()
+        op.inv_patch_stride = sc[_lib.PS_INV_STRIDE]
+        op.inv_width = sc[_lib.PS_INV_WIDTH]
         op.n_slots = self.n_slots
         op.slot_buf = self.slot_buf.data_ptr()
         op.n_shared = sc[_lib.PS_N_SHARED_REC]

@@ -138,11 +138,14 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     pnblk = ar[_lib.PA_PNBLK].reshape(npu, PS)
     elblk = ar[_lib.PA_ELBLK].reshape(neu, ELS)
     hdr = ar[_lib.PA_PATCH_HDR].reshape(n_patch, 8)
+    niu = sc[_lib.PS_N_INV_UNIQUE]
+    invblk = ar[_lib.PA_INVBLK].reshape(niu, -1)
+    assert len(set(map(bytes, invblk))) == niu
     assert len(set(map(bytes, pnblk))) == npu and len(set(map(bytes, elblk))) == neu
     for p in range(n_patch):
         h = hdr[p]
         assert h[0] == nnodes[p] and h[1] == npriv[p] and h[2] == base[p]
-        assert h[3] == 0 and h[7] == 0
+        assert h[3] == 0
         assert h[5] < npu and h[6] < neu
         full = pnode[ptr[p]:ptr[p] + nnodes[p]]
         assert h[4] == (full & _lib.NODE_ID_MASK).min()
@@ -153,6 +156,22 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         eb = elblk[h[6]]
         assert np.array_equal(eb[:NN * pe], ar[_lib.PA_ELOC].reshape(-1, ES)[p, :NN * pe])
         assert np.array_equal(eb[NN * pe:NN * pe + pe], color[p * pe:(p + 1) * pe])
+        # inverse table: node k <- scratch positions (m*RS + le*n1 + t) of its contributions,
+        # ascending element slot, 0xffff padded
+        W, RS = sc[_lib.PS_INV_WIDTH], ((n1 * pe - 1 + 15) & ~15) + 1
+        assert W % 4 == 0 and W >= 4 and sc[_lib.PS_INV_STRIDE] == PS * W and h[7] < niu
+        ib = invblk[h[7]].reshape(PS, W)
+        live = min(pe, E - p * pe)
+        tab = eb[:NN * pe].reshape(n1, pe, n1)
+        want_inv = [[] for _ in range(nnodes[p])]
+        for le in range(live):
+            for m in range(n1):
+                for t in range(n1):
+                    want_inv[tab[m, le, t]].append(m * RS + le * n1 + t)
+        for k in range(nnodes[p]):
+            c = len(want_inv[k])
+            assert 1 <= c <= W and ib[k, :c].tolist() == want_inv[k] and np.all(ib[k, c:] == 0xFFFF)
+        assert np.all(ib[nnodes[p]:] == 0xFFFF)
     # every touched node is written by exactly one patch or is a shared (slot) node
     is_shared_node = np.zeros(n_nodes, dtype=bool)
     is_shared_node[ids[shared_flag]] = True
