@@ -63,7 +63,7 @@ int semk_device_available(void);
 /* ------------------------------------------------------------------------
  * Host-side plan: groups elements into patches (one CTA each), builds the
  * patch node tables, the per-element patch-local index table, the in-patch
- * colouring and the deterministic interface reduction lists.  Pure host
+ * tables and the deterministic interface reduction lists.  Pure host
  * code, no CUDA call -- usable (and tested) without a GPU.
  *
  * Replaces the bookkeeping of the reference's assembly loop
@@ -83,44 +83,43 @@ enum semk_plan_array {
   SEMK_PA_ELOC = 4,           /* uint16 [n_patch][eloc_patch_stride]: per patch a table
                                  [m][le][t] (NN*PE entries) of patch-local node indices:
                                  node (m,t) of the le-th element of the patch            */
-  SEMK_PA_ELEM_COLOR = 5,     /* uint8  [n_slot_elems] colour of the element in its patch    */
-  SEMK_PA_ELEM_OF_SLOT = 6,   /* int64  [n_elem]      element id stored at engine slot s     */
-  SEMK_PA_SHARED_NODE = 7,    /* uint32 [n_shared]    global id | flags, ascending id        */
-  SEMK_PA_SHARED_PTR = 8,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
-  SEMK_PA_SHARED_SLOT = 9,    /* int32  [n_slots]     interface slots of each shared node,
+  SEMK_PA_ELEM_OF_SLOT = 5,   /* int64  [n_elem]      element id stored at engine slot s     */
+  SEMK_PA_SHARED_NODE = 6,    /* uint32 [n_shared]    global id | flags, ascending id        */
+  SEMK_PA_SHARED_PTR = 7,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
+  SEMK_PA_SHARED_SLOT = 8,    /* int32  [n_slots]     interface slots of each shared node,
                                  ascending patch (slot = PATCH_SLOT_BASE[p] + k)             */
-  SEMK_PA_PATCH_NNODES = 10,  /* int32  [n_patch]     number of distinct nodes of the patch  */
-  SEMK_PA_PNBLK = 11,         /* uint32 [n_pn_unique][pn_stride] device node blocks: a patch's node
+  SEMK_PA_PATCH_NNODES = 9,  /* int32  [n_patch]     number of distinct nodes of the patch  */
+  SEMK_PA_PNBLK = 10,         /* uint32 [n_pn_unique][pn_stride] device node blocks: a patch's node
                                  list as in PNODE but RELATIVE to the patch's smallest node
                                  id (flags kept in the top bits), 0xffffffff padded.
                                  Identical blocks are stored once; PATCH_HDR word 5 says
                                  which block a patch uses                                   */
-  SEMK_PA_ELBLK = 12,         /* uint16 [n_el_unique][el_stride] device index blocks: the ELOC
-                                 table [m][le][t] followed by the PE element colours;
+  SEMK_PA_ELBLK = 11,         /* uint16 [n_el_unique][el_stride] device index blocks: the ELOC
+                                 table [m][le][t];
                                  deduplicated like PNBLK (PATCH_HDR word 6)                 */
-  SEMK_PA_SHARED_REC = 13,    /* uint32 [n_shared_rec][8] {node id | flags, count, slot 0..5} for the
+  SEMK_PA_SHARED_REC = 12,    /* uint32 [n_shared_rec][8] {node id | flags, count, slot 0..5} for the
                                  shared nodes touched by 3+ patches (corners), sorted by the
                                  highest patch touching the node; counts above 6:
                                  slots 0..4 inline, word 7 = offset of the rest in SHARED_EXT   */
-  SEMK_PA_SHARED_EXT = 14,    /* uint32 [...]         overflow slot lists of SHARED_REC            */
-  SEMK_PA_SHARED_CHUNK = 15,  /* uint32 [n_shared_chunk][8] affine chunks of 1..32 two-patch nodes:
+  SEMK_PA_SHARED_EXT = 13,    /* uint32 [...]         overflow slot lists of SHARED_REC            */
+  SEMK_PA_SHARED_CHUNK = 14,  /* uint32 [n_shared_chunk][8] affine chunks of 1..32 two-patch nodes:
                                  {node0, dn, a0, da, b0, db, len, Dirichlet mask};
                                  node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
-  SEMK_PA_PATCH_HDR = 16,     /* uint32 [n_patch][8]  {n nodes, n private, first interface slot, 0,
+  SEMK_PA_PATCH_HDR = 15,     /* uint32 [n_patch][8]  {n nodes, n private, first interface slot, 0,
                                  base node id, PNBLK block, ELBLK block, INVBLK block}        */
-  SEMK_PA_PATCH_MAXNODE = 17, /* uint32 [n_patch]     largest node id of the patch (the smallest is
+  SEMK_PA_PATCH_MAXNODE = 16, /* uint32 [n_patch]     largest node id of the patch (the smallest is
                                  PATCH_HDR word 4)                                            */
-  SEMK_PA_CHUNK_MAXPATCH = 18,/* int32  [n_shared_chunk] higher of the two patches of a chunk; the
+  SEMK_PA_CHUNK_MAXPATCH = 17,/* int32  [n_shared_chunk] higher of the two patches of a chunk; the
                                  chunk table is sorted by it                                  */
-  SEMK_PA_REC_MAXPATCH = 19,  /* int32  [n_shared_rec]   highest patch touching a record's node; the
+  SEMK_PA_REC_MAXPATCH = 18,  /* int32  [n_shared_rec]   highest patch touching a record's node; the
                                  record table is sorted by it (then by node id)               */
-  SEMK_PA_INVBLK = 20,        /* uint16 [n_inv_unique][inv_stride] inverse tables: for patch node k the
+  SEMK_PA_INVBLK = 19,        /* uint16 [n_inv_unique][inv_stride] inverse tables: for patch node k the
                                  entries [k*inv_width, (k+1)*inv_width) are the positions of
                                  its element-local contributions in the CTA's transposition
                                  scratch (m*RS + le*n1 + t, RS = semk_scratch_row_stride),
                                  ascending element slot, 0xffff padded; deduplicated
                                  (PATCH_HDR word 7)                                           */
-  SEMK_PA_COUNT = 21
+  SEMK_PA_COUNT = 20
 };
 
 /* Row stride (doubles) of the patch kernel's transposition scratch: rows of
@@ -133,19 +132,18 @@ enum semk_plan_scalar {
   SEMK_PS_N_SLOTS = 2,
   SEMK_PS_N_SHARED = 3,
   SEMK_PS_MAX_PATCH_NODES = 4,
-  SEMK_PS_MAX_COLORS = 5,
-  SEMK_PS_N_SLOT_ELEMS = 6,   /* n_patch * elems_per_patch (last patch padded) */
-  SEMK_PS_ELOC_STRIDE = 7,    /* uint16 entries per patch block of ELOC: NN*PE rounded up to 8 */
-  SEMK_PS_PN_STRIDE = 8,      /* uint32 entries per patch block of PNBLK (multiple of 4)       */
-  SEMK_PS_EL_STRIDE = 9,      /* uint16 entries per patch block of ELBLK (multiple of 8)       */
-  SEMK_PS_N_SHARED_CHUNK = 10,/* number of affine interface chunks                             */
-  SEMK_PS_N_SHARED_REC = 11,  /* number of per-node interface records                          */
-  SEMK_PS_N_PN_UNIQUE = 12,   /* distinct node blocks in PNBLK                                 */
-  SEMK_PS_N_EL_UNIQUE = 13,   /* distinct index blocks in ELBLK                                */
-  SEMK_PS_N_INV_UNIQUE = 14,  /* distinct inverse blocks in INVBLK                              */
-  SEMK_PS_INV_WIDTH = 15,     /* contributions stored per node (multiple of 4; 4 = structured)   */
-  SEMK_PS_INV_STRIDE = 16,    /* uint16 entries per inverse block = PN_STRIDE * INV_WIDTH        */
-  SEMK_PS_COUNT = 17
+  SEMK_PS_N_SLOT_ELEMS = 5,   /* n_patch * elems_per_patch (last patch padded) */
+  SEMK_PS_ELOC_STRIDE = 6,    /* uint16 entries per patch block of ELOC: NN*PE rounded up to 8 */
+  SEMK_PS_PN_STRIDE = 7,      /* uint32 entries per patch block of PNBLK (multiple of 4)       */
+  SEMK_PS_EL_STRIDE = 8,      /* uint16 entries per patch block of ELBLK (multiple of 8)       */
+  SEMK_PS_N_SHARED_CHUNK = 9,/* number of affine interface chunks                             */
+  SEMK_PS_N_SHARED_REC = 10,  /* number of per-node interface records                          */
+  SEMK_PS_N_PN_UNIQUE = 11,   /* distinct node blocks in PNBLK                                 */
+  SEMK_PS_N_EL_UNIQUE = 12,   /* distinct index blocks in ELBLK                                */
+  SEMK_PS_N_INV_UNIQUE = 13,  /* distinct inverse blocks in INVBLK                              */
+  SEMK_PS_INV_WIDTH = 14,     /* contributions stored per node (multiple of 4; 4 = structured)   */
+  SEMK_PS_INV_STRIDE = 15,    /* uint16 entries per inverse block = PN_STRIDE * INV_WIDTH        */
+  SEMK_PS_COUNT = 16
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
@@ -171,8 +169,7 @@ typedef struct semk_op {
   int64_t n_elem;
   int64_t n_nodes;
   int64_t n_patch;
-  int32_t max_patch_nodes;
-  int32_t max_colors;
+  int64_t max_patch_nodes;
   int64_t g_patch_stride;   /* doubles per patch block of G (even, >= 3*NN*PE)          */
   const double *G;          /* [n_patch][g_patch_stride]; inside a patch block the factor
                                c (0: G00, 1: G01, 2: G11) at node (m, t) of the le-th

@@ -19,19 +19,19 @@ NODE_ID_MASK, NODE_SHARED, NODE_DIRICHLET = 0x3FFFFFFF, 0x40000000, 0x80000000
 MASK_IN, MASK_OUT, DIRICHLET_IDENTITY = 1, 2, 4
 MAX_N1 = 17
 
-(PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC, PA_ELEM_COLOR,
+(PA_PATCH_NODE_PTR, PA_PNODE, PA_PATCH_NPRIV, PA_PATCH_SLOT_BASE, PA_ELOC,
  PA_ELEM_OF_SLOT, PA_SHARED_NODE, PA_SHARED_PTR, PA_SHARED_SLOT, PA_PATCH_NNODES,
  PA_PNBLK, PA_ELBLK, PA_SHARED_REC, PA_SHARED_EXT, PA_SHARED_CHUNK,
- PA_PATCH_HDR, PA_PATCH_MAXNODE, PA_CHUNK_MAXPATCH, PA_REC_MAXPATCH, PA_INVBLK) = range(21)
-(PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES, PS_MAX_COLORS,
+ PA_PATCH_HDR, PA_PATCH_MAXNODE, PA_CHUNK_MAXPATCH, PA_REC_MAXPATCH, PA_INVBLK) = range(20)
+(PS_N_PATCH, PS_N_PNODE, PS_N_SLOTS, PS_N_SHARED, PS_MAX_PATCH_NODES,
  PS_N_SLOT_ELEMS, PS_ELOC_STRIDE, PS_PN_STRIDE, PS_EL_STRIDE, PS_N_SHARED_CHUNK,
  PS_N_SHARED_REC, PS_N_PN_UNIQUE, PS_N_EL_UNIQUE, PS_N_INV_UNIQUE, PS_INV_WIDTH,
- PS_INV_STRIDE) = range(17)
-PS_COUNT = 17
+ PS_INV_STRIDE) = range(16)
+PS_COUNT = 16
 
 PLAN_ARRAY_DTYPES = {
     PA_PATCH_NODE_PTR: np.int32, PA_PNODE: np.uint32, PA_PATCH_NPRIV: np.int32,
-    PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16, PA_ELEM_COLOR: np.uint8,
+    PA_PATCH_SLOT_BASE: np.int32, PA_ELOC: np.uint16,
     PA_ELEM_OF_SLOT: np.int64, PA_SHARED_NODE: np.uint32, PA_SHARED_PTR: np.int32,
     PA_SHARED_SLOT: np.int32, PA_PATCH_NNODES: np.int32, PA_PNBLK: np.uint32,
     PA_ELBLK: np.uint16, PA_SHARED_REC: np.uint32, PA_SHARED_EXT: np.uint32,
@@ -55,7 +55,7 @@ class semk_op(C.Structure):
     _fields_ = [
         ("n1", C.c_int32), ("elems_per_patch", C.c_int32),
         ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
-        ("max_patch_nodes", C.c_int32), ("max_colors", C.c_int32),
+        ("max_patch_nodes", C.c_int64),
         ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
         ("patch_hdr", C.c_void_p), ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),

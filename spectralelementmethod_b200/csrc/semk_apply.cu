@@ -25,7 +25,7 @@
 //   * nodal values are gathered once per patch into shared memory through the
 //     patch node table (coalesced for locality-preserving numberings), with
 //     the Dirichlet mask carried in the table's flag bits.
-//   * assembly inside the patch is by colour (no atomics); private nodes are
+//   * assembly inside the patch is a fixed-order gather (no atomics); private nodes are
 //     stored straight to y, shared nodes go to interface slots that the tiny
 //     `shared_nodes_kernel` sums in a fixed order => bit-reproducible.
 #include "semk_common.cuh"
@@ -306,7 +306,7 @@ __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
   const long long mpn4 = (mpn + 3) & ~3LL;
   const long long nn = (long long)N * N;
   const long long g = 8 * ((3 * nn * PE + 1) & ~1LL);
-  const long long tab = 2 * ((4 * mpn4 + 2 * ((nn * PE + PE + 7) & ~7LL) + 15) & ~15LL) + 64;
+  const long long tab = 2 * ((4 * mpn4 + 2 * ((nn * PE + 7) & ~7LL) + 15) & ~15LL) + 64;
   const long long scr = 8LL * N * scratch_row_stride(N, PE);
   const long long ua = scr;
   const long long total = 32 + g + tab + 8 * mpn4 + ua + (scr > 256 ? scr : 256) + 1024;
@@ -327,7 +327,7 @@ constexpr int kGatherBatch = 8;
 // whole patch-time ahead: DRAM latency is off the critical path), and the
 // nodal values of patch i+1 are gathered into registers right after the
 // element operator of patch i, so that the loads are in flight during the
-// colour-ordered assembly and the write-out.  CTAs never exit between patches,
+// assembly and the write-out.  CTAs never exit between patches,
 // so no SM slot idles on CTA launch / retire (~2.4 k cycles each on this chip).
 //
 // MODE_APPLY:    y = A u (masked per flags), optional dot partials.
@@ -946,7 +946,7 @@ int check_op(const semk_op *op, const char *who) {
       op->pn_patch_stride < op->max_patch_nodes ||
       (reinterpret_cast<uintptr_t>(op->patch_hdr) & 15u) != 0 ||
       (op->eloc_patch_stride & 7) != 0 ||
-      op->eloc_patch_stride < nnp + op->elems_per_patch ||
+      op->eloc_patch_stride < nnp ||
       (op->n_slots > 0 && !op->slot_buf) ||
       (op->n_shared > 0 && (!op->shared_rec || !op->shared_ext)) ||
       (op->n_shared_chunk > 0 && !op->shared_chunk)) {

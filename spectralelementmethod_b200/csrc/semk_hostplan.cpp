@@ -10,9 +10,9 @@
 //                    partial sum to an interface slot and a second, tiny
 //                    kernel sums the slots of each shared node in a fixed
 //                    order (deterministic, no floating-point atomics).
-// Within a patch, elements are greedily coloured so that elements of one
-// colour share no node; the CTA accumulates colour by colour into shared
-// memory without atomics.
+// Within a patch the CTA assembles by gathering: an inverse table lists, for
+// every patch node, where its element-local contributions sit in the CTA's
+// scratch, so each node is summed in a fixed order without atomics.
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -37,7 +37,6 @@ struct semk_hostplan {
   std::vector<int32_t> chunk_maxpatch, rec_maxpatch;
   std::vector<uint16_t> elblk, invblk;
   std::vector<uint16_t> eloc;
-  std::vector<uint8_t> elem_color;
   std::vector<int64_t> elem_of_slot;
 };
 
@@ -138,12 +137,10 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
     P->eloc.assign((size_t)n_patch * ES, 0);
-    P->elem_color.assign(n_slot_elems, 0);
     std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
-    std::vector<uint32_t> priv, shar, colmask;
+    std::vector<uint32_t> priv, shar;
     std::vector<std::pair<int32_t, int32_t>> slot_pairs;  // (shared index, slot)
     int64_t max_patch_nodes = 0, n_slots = 0;
-    int max_colors = 1;
     for (int64_t p = 0; p < n_patch; ++p) {
       const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
       priv.clear();
@@ -196,32 +193,16 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       P->patch_nnodes[p] = np + ns;
       max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
 
-      // element-local index table + greedy colouring
-      colmask.assign(np + ns, 0u);
+      // element-local index table
       for (int64_t s = s0; s < s1; ++s) {
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
         const int le = (int)(s - s0);
-        uint32_t forbidden = 0;
         for (int k = 0; k < NN; ++k) {
-          const int32_t loc = local_of[row[k]];
           const int m = k / n1, t = k - m * n1;
-          eb[((size_t)m * PE + le) * n1 + t] = (uint16_t)loc;
-          forbidden |= colmask[loc];
+          eb[((size_t)m * PE + le) * n1 + t] = (uint16_t)local_of[row[k]];
         }
-        int c = 0;
-        while (c < 31 && (forbidden >> c) & 1u) ++c;
-        if (c >= 31) {
-          delete P;
-          semk_set_error("semk_hostplan_create: more than 31 colours needed in a patch");
-          return SEMK_ERR_UNSUPPORTED;
-        }
-        for (int k = 0; k < NN; ++k) colmask[local_of[row[k]]] |= (1u << c);
-        P->elem_color[s] = (uint8_t)c;
-        max_colors = std::max(max_colors, c + 1);
       }
-      // padded slots of a ragged last patch: colour 255 = never active
-      for (int64_t s = s1; s < s0 + PE; ++s) P->elem_color[s] = 255;
       // reset scratch
       for (uint32_t g : priv) local_of[g] = -1;
       for (uint32_t g : shar) local_of[g] = -1;
@@ -364,7 +345,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     // Uniform-stride device blocks, one TMA bulk copy each per patch:
     //   node block  = the patch's node list RELATIVE to its smallest node id (flags in
     //                 the top bits as in PNODE), 0xffffffff padded;
-    //   index block = [m][le][t] patch-local indices + PE element colours (uint16).
+    //   index block = [m][le][t] patch-local indices (uint16).
     // Identical blocks are stored once (DEDUPLICATED): on a regularly numbered mesh every
     // interior patch has the same relative node list and the same index table, so the
     // kernel's table reads become L2 hits instead of DRAM traffic.  The per-patch part
@@ -372,7 +353,7 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     //   {n nodes, n private, first slot, 0, base node id, node block index, index block
     //    index, inverse block index}.
     const int64_t pn_stride = (max_patch_nodes + 3) & ~(int64_t)3;
-    const int64_t el_stride = ((int64_t)NN * PE + PE + 7) & ~(int64_t)7;
+    const int64_t el_stride = ((int64_t)NN * PE + 7) & ~(int64_t)7;
     // Inverse tables for the gather-style assembly: for every patch node the positions
     // of its element-local contributions inside the CTA's transposition scratch
     // (row m, thread le*n1 + t -> m*RS + le*n1 + t), ascending element slot, 0xffff
@@ -428,7 +409,6 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         std::fill(eblk.begin(), eblk.end(), (uint16_t)0);
         std::copy(P->eloc.begin() + (size_t)p * ES, P->eloc.begin() + (size_t)p * ES + (size_t)NN * PE,
                   eblk.begin());
-        for (int le = 0; le < PE; ++le) eblk[(size_t)NN * PE + le] = P->elem_color[p * PE + le];
 
         auto find_or_add = [&](auto &seen, auto &pool, const auto &blk, int64_t stride) {
           const size_t bytes = (size_t)stride * sizeof(blk[0]);
@@ -489,7 +469,6 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     P->scalars[SEMK_PS_N_SLOTS] = n_slots;
     P->scalars[SEMK_PS_N_SHARED] = n_shared;
     P->scalars[SEMK_PS_MAX_PATCH_NODES] = max_patch_nodes;
-    P->scalars[SEMK_PS_MAX_COLORS] = max_colors;
     P->scalars[SEMK_PS_N_SLOT_ELEMS] = n_slot_elems;
     P->scalars[SEMK_PS_ELOC_STRIDE] = ES;
   } catch (const std::bad_alloc &) {
@@ -522,7 +501,6 @@ extern "C" const void *semk_hostplan_array(const semk_hostplan *plan, int which,
     case SEMK_PA_PATCH_NPRIV: return vec_ptr(plan->patch_npriv, n_bytes);
     case SEMK_PA_PATCH_SLOT_BASE: return vec_ptr(plan->patch_slot_base, n_bytes);
     case SEMK_PA_ELOC: return vec_ptr(plan->eloc, n_bytes);
-    case SEMK_PA_ELEM_COLOR: return vec_ptr(plan->elem_color, n_bytes);
     case SEMK_PA_ELEM_OF_SLOT: return vec_ptr(plan->elem_of_slot, n_bytes);
     case SEMK_PA_SHARED_NODE: return vec_ptr(plan->shared_node, n_bytes);
     case SEMK_PA_SHARED_PTR: return vec_ptr(plan->shared_ptr, n_bytes);

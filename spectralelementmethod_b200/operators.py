@@ -40,7 +40,7 @@ def g_patch_stride_of(n1, pe):
 
 
 def eloc_patch_stride_of(n1, pe):
-    return (n1 * n1 * pe + pe + 7) & ~7   # index table + PE colours, 16-byte multiples
+    return (n1 * n1 * pe + 7) & ~7   # index table, 16-byte multiples
 
 
 def pn_patch_stride_of(max_patch_nodes):
@@ -229,7 +229,6 @@ class PoissonOperator(object):
         op.n1, op.elems_per_patch = n1, pe
         op.n_elem, op.n_nodes, op.n_patch = self.n_elem, self.n_nodes, self.n_patch
         op.max_patch_nodes = sc[_lib.PS_MAX_PATCH_NODES]
-        op.max_colors = sc[_lib.PS_MAX_COLORS]
         op.g_patch_stride = self.g_patch_stride
         op.G = self.G.data_ptr()
         op.patch_hdr = t[_lib.PA_PATCH_HDR].data_ptr()

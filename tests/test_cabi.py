@@ -85,7 +85,6 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     eloc = eloc.transpose(0, 2, 1, 3).reshape(-1, NN)
     nnodes = ar[_lib.PA_PATCH_NNODES]
     assert np.all(ptr % 4 == 0)
-    color = ar[_lib.PA_ELEM_COLOR]
     eos = ar[_lib.PA_ELEM_OF_SLOT]
     assert sorted(eos.tolist()) == list(range(E))
     pad = pnode == 0xFFFFFFFF
@@ -117,14 +116,7 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         s0, s1 = p * pe, min((p + 1) * pe, E)
         # eloc reproduces the L2G rows of the patch's elements
         assert np.array_equal(loc_ids[eloc[s0:s1].astype(int)], l2g[eos[s0:s1]])
-        # colouring: elements of one colour share no node
-        for c in set(color[s0:s1].tolist()):
-            sel = [s for s in range(s0, s1) if color[s] == c]
-            allnodes = np.concatenate([eloc[s] for s in sel])
-            assert len(set(allnodes.tolist())) == allnodes.size
-        assert np.all(color[s1:(p + 1) * pe] == 255)
         assert (b - a) <= sc[_lib.PS_MAX_PATCH_NODES]
-    assert color[color != 255].max() + 1 == sc[_lib.PS_MAX_COLORS]
     assert slots_seen == sc[_lib.PS_N_SLOTS]
     # private <=> touched by exactly one patch
     is_shared_node = np.zeros(n_nodes, dtype=bool)
@@ -155,7 +147,6 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         assert np.all(blk[nnodes[p]:] == 0xFFFFFFFF)
         eb = elblk[h[6]]
         assert np.array_equal(eb[:NN * pe], ar[_lib.PA_ELOC].reshape(-1, ES)[p, :NN * pe])
-        assert np.array_equal(eb[NN * pe:NN * pe + pe], color[p * pe:(p + 1) * pe])
         # inverse table: node k <- scratch positions (m*RS + le*n1 + t) of its contributions,
         # ascending element slot, 0xffff padded
         W, RS = sc[_lib.PS_INV_WIDTH], ((n1 * pe - 1 + 15) & ~15) + 1
@@ -242,7 +233,7 @@ def test_hostplan_structured(nx, ny, p, pe):
     l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, dirichlet)
     check_plan(l2g, n_nodes, sc, ar, pe, dirichlet)
     if (nx, ny, p, pe) == (8, 8, 8, 16):          # 2x8 tiles: a 4x1 arrangement of patches
-        assert sc[_lib.PS_N_PATCH] == 4 and sc[_lib.PS_MAX_COLORS] == 4
+        assert sc[_lib.PS_N_PATCH] == 4
         assert sc[_lib.PS_MAX_PATCH_NODES] == 17 * 65
         assert sc[_lib.PS_N_SHARED] == 3 * 65
 
