@@ -619,7 +619,10 @@ struct InterfaceRange {
 };
 
 constexpr int kChunkWarps = 8;   // warps per CTA of 256 threads
-constexpr int kChunkUnroll = 4;  // chunks per warp
+#ifndef SEMK_CHUNK_UNROLL
+#define SEMK_CHUNK_UNROLL 4
+#endif
+constexpr int kChunkUnroll = SEMK_CHUNK_UNROLL;  // chunks per warp
 
 // Writes the final value of a shared node; returns its identity-row share of u . y
 // (the rest of u . y is taken element by element in the patch kernel).

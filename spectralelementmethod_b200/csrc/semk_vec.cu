@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(kVecThreads)
 
 // VEC: all vector pointers are 16-byte aligned -> 128-bit loads/stores, two pairs
 // per thread and iteration in flight (these kernels are pure HBM streams).
-template <bool VEC>
+// XP ("x rides with p"): the native driver defers x += alpha p from the first kernel to
+// the second one, which reads p anyway -- one vector pass less per iteration (6 + 4
+// instead of 7 + 4).  The two public entry points keep x in the first kernel.
+template <bool VEC, bool XP>
 __global__ void __launch_bounds__(kVecThreads)
     pcg_update_xr_kernel(int64_t n, int64_t n_dot, const double *__restrict__ p,
                          const double *__restrict__ Ap, const double *__restrict__ dinv,
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(kVecThreads)
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   auto one = [&](int64_t i) {
-    x[i] = fma(alpha, p[i], x[i]);
+    if (!XP) x[i] = fma(alpha, p[i], x[i]);
     const double ri = fma(-alpha, Ap[i], r[i]);
     r[i] = ri;
     if (i < n_dot) {
@@ -127,46 +130,40 @@ __global__ void __launch_bounds__(kVecThreads)
     const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
     double2 *x2 = reinterpret_cast<double2 *>(x);
     double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 zero2 = make_double2(0.0, 0.0);
     for (int64_t j0 = tid; j0 < npair; j0 += 2 * nthreads) {
-      const int64_t j1 = j0 + nthreads;
-      const bool two = j1 < npair;
-      const double2 pa = p2[j0], aa = Ap2[j0], xa = x2[j0], ra = r2[j0], da = d2[j0];
-      double2 pb = pa, ab = aa, xb = xa, rb = ra, db = da;
-      if (two) {
-        pb = p2[j1];
-        ab = Ap2[j1];
-        xb = x2[j1];
-        rb = r2[j1];
-        db = d2[j1];
+      const int64_t jj[2] = {j0, j0 + nthreads};
+      const bool on[2] = {true, jj[1] < npair};
+      double2 pv[2], av[2], xv[2], rv[2], dv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {  // all loads of both pairs first
+        av[q] = on[q] ? Ap2[jj[q]] : zero2;
+        rv[q] = on[q] ? r2[jj[q]] : zero2;
+        dv[q] = on[q] ? d2[jj[q]] : zero2;
+        if (!XP) {
+          pv[q] = on[q] ? p2[jj[q]] : zero2;
+          xv[q] = on[q] ? x2[jj[q]] : zero2;
+        }
       }
-      double2 xo, ro;
-      xo.x = fma(alpha, pa.x, xa.x);
-      xo.y = fma(alpha, pa.y, xa.y);
-      ro.x = fma(-alpha, aa.x, ra.x);
-      ro.y = fma(-alpha, aa.y, ra.y);
-      x2[j0] = xo;
-      r2[j0] = ro;
-      if (2 * j0 < n_dot) {
-        acc[0] = fma(ro.x * da.x, ro.x, acc[0]);
-        acc[1] = fma(ro.x, ro.x, acc[1]);
-      }
-      if (2 * j0 + 1 < n_dot) {
-        acc[0] = fma(ro.y * da.y, ro.y, acc[0]);
-        acc[1] = fma(ro.y, ro.y, acc[1]);
-      }
-      if (two) {
-        xo.x = fma(alpha, pb.x, xb.x);
-        xo.y = fma(alpha, pb.y, xb.y);
-        ro.x = fma(-alpha, ab.x, rb.x);
-        ro.y = fma(-alpha, ab.y, rb.y);
-        x2[j1] = xo;
-        r2[j1] = ro;
-        if (2 * j1 < n_dot) {
-          acc[0] = fma(ro.x * db.x, ro.x, acc[0]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!on[q]) continue;
+        double2 ro;
+        ro.x = fma(-alpha, av[q].x, rv[q].x);
+        ro.y = fma(-alpha, av[q].y, rv[q].y);
+        r2[jj[q]] = ro;
+        if (!XP) {
+          double2 xo;
+          xo.x = fma(alpha, pv[q].x, xv[q].x);
+          xo.y = fma(alpha, pv[q].y, xv[q].y);
+          x2[jj[q]] = xo;
+        }
+        if (2 * jj[q] < n_dot) {
+          acc[0] = fma(ro.x * dv[q].x, ro.x, acc[0]);
           acc[1] = fma(ro.x, ro.x, acc[1]);
         }
-        if (2 * j1 + 1 < n_dot) {
-          acc[0] = fma(ro.y * db.y, ro.y, acc[0]);
+        if (2 * jj[q] + 1 < n_dot) {
+          acc[0] = fma(ro.y * dv[q].y, ro.y, acc[0]);
           acc[1] = fma(ro.y, ro.y, acc[1]);
         }
       }
@@ -185,57 +182,81 @@ __global__ void __launch_bounds__(kVecThreads)
   }
 }
 
-template <bool VEC>
+// p = z + beta p (z = dinv r).  XP: also x += alpha p_old; on the iteration that
+// converged (sc[6] == 1, set by the first kernel) only that last x update is done and
+// the state moves on to 2 = frozen.
+template <bool VEC, bool XP>
 __global__ void __launch_bounds__(kVecThreads)
     pcg_update_p_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ dinv,
-                        double *__restrict__ p, double *__restrict__ sc,
+                        double *__restrict__ p, double *__restrict__ x, double *__restrict__ sc,
                         double *__restrict__ partials) {
   const volatile double *vsc = sc;
-  if (vsc[6] != 0.0 || vsc[7] != 0.0) return;
-  const double rz_new = vsc[2], rz = vsc[0];
+  const double conv = vsc[6];
+  if (vsc[7] != 0.0 || conv == 2.0 || (!XP && conv != 0.0)) return;
+  const double rz_new = vsc[2], rz = vsc[0], pAp = vsc[1];
   const double beta = (rz != 0.0) ? rz_new / rz : 0.0;
+  const double alpha = XP ? rz / pAp : 0.0;  // the first kernel vetted pAp > 0
+  const bool move_p = conv == 0.0;
   __shared__ bool is_last;
   __syncthreads();  // every thread of this CTA has read the scalars
   if (threadIdx.x == 0) {
-    // every CTA has read sc[0] before it arrives; the last arrival rotates rz
+    // every CTA has read the scalars before it arrives; the last arrival rotates them
     __threadfence();
     const unsigned long long t = atomicAdd(counter_of(partials), 1ull);
     is_last = (t == (unsigned long long)gridDim.x - 1ull);
   }
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  auto one = [&](int64_t i) {
+    const double pi = p[i];
+    if (XP) x[i] = fma(alpha, pi, x[i]);
+    if (move_p) p[i] = fma(beta, pi, dinv[i] * r[i]);
+  };
   if (VEC) {
     const int64_t npair = n >> 1;
     const double2 *r2 = reinterpret_cast<const double2 *>(r);
     const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
     double2 *p2 = reinterpret_cast<double2 *>(p);
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    const double2 zero2 = make_double2(0.0, 0.0);
     for (int64_t j0 = tid; j0 < npair; j0 += 2 * nthreads) {
-      const int64_t j1 = j0 + nthreads;
-      const bool two = j1 < npair;
-      const double2 ra = r2[j0], da = d2[j0], pa = p2[j0];
-      double2 rb = ra, db = da, pb = pa;
-      if (two) {
-        rb = r2[j1];
-        db = d2[j1];
-        pb = p2[j1];
+      const int64_t jj[2] = {j0, j0 + nthreads};
+      const bool on[2] = {true, jj[1] < npair};
+      double2 rv[2], dv[2], pv[2], xv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        pv[q] = on[q] ? p2[jj[q]] : zero2;
+        rv[q] = (on[q] && move_p) ? r2[jj[q]] : zero2;
+        dv[q] = (on[q] && move_p) ? d2[jj[q]] : zero2;
+        if (XP) xv[q] = on[q] ? x2[jj[q]] : zero2;
       }
-      double2 o;
-      o.x = fma(beta, pa.x, da.x * ra.x);
-      o.y = fma(beta, pa.y, da.y * ra.y);
-      p2[j0] = o;
-      if (two) {
-        o.x = fma(beta, pb.x, db.x * rb.x);
-        o.y = fma(beta, pb.y, db.y * rb.y);
-        p2[j1] = o;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!on[q]) continue;
+        if (XP) {
+          double2 xo;
+          xo.x = fma(alpha, pv[q].x, xv[q].x);
+          xo.y = fma(alpha, pv[q].y, xv[q].y);
+          x2[jj[q]] = xo;
+        }
+        if (move_p) {
+          double2 o;
+          o.x = fma(beta, pv[q].x, dv[q].x * rv[q].x);
+          o.y = fma(beta, pv[q].y, dv[q].y * rv[q].y);
+          p2[jj[q]] = o;
+        }
       }
     }
-    if ((n & 1) && tid == 0) p[n - 1] = fma(beta, p[n - 1], dinv[n - 1] * r[n - 1]);
+    if ((n & 1) && tid == 0) one(n - 1);
   } else {
-    for (int64_t i = tid; i < n; i += nthreads) p[i] = fma(beta, p[i], dinv[i] * r[i]);
+    for (int64_t i = tid; i < n; i += nthreads) one(i);
   }
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
-    sc[0] = rz_new;
+    if (move_p)
+      sc[0] = rz_new;
+    else
+      sc[6] = 2.0;  // the converged iterate is complete: frozen from now on
     *counter_of(partials) = 0ull;
   }
 }
@@ -279,14 +300,31 @@ static inline bool aligned16(const void *a, const void *b, const void *c, const 
 
 static int update_xr(int64_t n, int64_t n_dot, const double *p, const double *Ap,
                      const double *dinv, double *x, double *r, double *sc, double *partials,
-                     double tol2, cudaStream_t st) {
-  if (aligned16(p, Ap, dinv, x, r))
-    pcg_update_xr_kernel<true><<<vec_blocks(n), kVecThreads, 0, st>>>(n, n_dot, p, Ap, dinv, x, r,
-                                                                     sc, partials, tol2);
-  else
-    pcg_update_xr_kernel<false><<<vec_blocks(n), kVecThreads, 0, st>>>(n, n_dot, p, Ap, dinv, x,
-                                                                      r, sc, partials, tol2);
+                     double tol2, bool x_rides_with_p, cudaStream_t st) {
+  const bool vec = aligned16(p, Ap, dinv, x, r);
+  const dim3 g(vec_blocks(n)), b(kVecThreads);
+#define SEMK_GO(V, X) \
+  pcg_update_xr_kernel<V, X><<<g, b, 0, st>>>(n, n_dot, p, Ap, dinv, x, r, sc, partials, tol2)
+  if (vec && x_rides_with_p) SEMK_GO(true, true);
+  else if (vec) SEMK_GO(true, false);
+  else if (x_rides_with_p) SEMK_GO(false, true);
+  else SEMK_GO(false, false);
+#undef SEMK_GO
   SEMK_LAUNCH_CHECK("pcg_update_xr_kernel");
+  return SEMK_OK;
+}
+
+static int update_p(int64_t n, const double *r, const double *dinv, double *p, double *x,
+                    double *sc, double *partials, cudaStream_t st) {
+  const bool vec = aligned16(r, dinv, p, x ? x : p, p);
+  const dim3 g(vec_blocks(n)), b(kVecThreads);
+#define SEMK_GO(V, X) pcg_update_p_kernel<V, X><<<g, b, 0, st>>>(n, r, dinv, p, x, sc, partials)
+  if (vec && x) SEMK_GO(true, true);
+  else if (vec) SEMK_GO(true, false);
+  else if (x) SEMK_GO(false, true);
+  else SEMK_GO(false, false);
+#undef SEMK_GO
+  SEMK_LAUNCH_CHECK("pcg_update_p_kernel");
   return SEMK_OK;
 }
 
@@ -297,21 +335,14 @@ extern "C" int semk_pcg_update_xr_f64(int64_t n, int64_t n_dot, const double *p,
   SEMK_REQUIRE(p && Ap && dinv && x && r && sc && partials,
                "semk_pcg_update_xr_f64: null pointer");
   // tol2 < 0: the device-side convergence freeze is disabled (caller decides)
-  return update_xr(n, n_dot, p, Ap, dinv, x, r, sc, partials, -1.0, semk_stream(stream));
+  return update_xr(n, n_dot, p, Ap, dinv, x, r, sc, partials, -1.0, false, semk_stream(stream));
 }
 
 extern "C" int semk_pcg_update_p_f64(int64_t n, const double *r, const double *dinv, double *p,
                                       double *sc, double *partials, void *stream) {
   SEMK_REQUIRE(n > 0, "semk_pcg_update_p_f64: bad size");
   SEMK_REQUIRE(r && dinv && p && sc && partials, "semk_pcg_update_p_f64: null pointer");
-  if (aligned16(r, dinv, p, p, p))
-    pcg_update_p_kernel<true><<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(
-        n, r, dinv, p, sc, partials);
-  else
-    pcg_update_p_kernel<false><<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(
-        n, r, dinv, p, sc, partials);
-  SEMK_LAUNCH_CHECK("pcg_update_p_kernel");
-  return SEMK_OK;
+  return update_p(n, r, dinv, p, nullptr, sc, partials, semk_stream(stream));
 }
 
 extern "C" int semk_dot_f64(int64_t n, const double *a, const double *b, double *out,
@@ -361,9 +392,10 @@ extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
   auto one_iteration = [&]() -> int {
     int e = semk_poisson_apply_f64(op, p, Ap, flags, sc + 1, st);
     if (e != SEMK_OK) return e;
-    e = update_xr(n, n, p, Ap, dinv, x, r, sc, vec_partials, tol2, st);
+    // x += alpha p rides with the p update (one vector pass less per iteration)
+    e = update_xr(n, n, p, Ap, dinv, x, r, sc, vec_partials, tol2, true, st);
     if (e != SEMK_OK) return e;
-    return semk_pcg_update_p_f64(n, r, dinv, p, sc, vec_partials, st);
+    return update_p(n, r, dinv, p, x, sc, vec_partials, st);
   };
 
   // Capture `check_every` iterations once and replay: removes per-launch host

@@ -374,3 +374,37 @@ def test_host_apply_staged_equals_device_apply(kind, nx, ny, p, sc, rcm, pe, sta
     y2 = np.full(op.n_nodes, np.nan)
     op.apply_host(u, y2, stages=stages)
     assert np.array_equal(y2, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rtol,check_every", [(1e-3, 7), (1e-6, 1), (1e-9, 50)])
+def test_native_pcg_matches_kernel_by_kernel_pcg(rtol, check_every):
+    """The native driver (CUDA graph, x += alpha p deferred into the p-update kernel,
+    iterate frozen on the device at convergence) stops at the same iteration with the same
+    iterate as a loop over the public kernels, including the very last x update."""
+    from spectralelementmethod_b200.operators import PCGKernels
+    mesh, mngr = build_package_case("C", 12, 10, 6, False, False)
+    op = mngr.poisson_operator(dirichlet=mngr.boundary_node_mask("ebc"))
+    b = op.lift(op.rhs(1.0), None)
+    x_native, info = op.solve_pcg(b, rtol=rtol, check_every=check_every)
+    assert info.converged and info.rel_residual <= rtol
+
+    k = PCGKernels(op)
+    n = op.n_nodes
+    x = torch.zeros_like(b)
+    m = op.dirichlet_dev.bool()
+    x[m] = b[m]
+    r, p, Ap = torch.empty_like(b), torch.empty_like(b), torch.empty_like(b)
+    sc = torch.zeros(8, dtype=torch.float64, device=b.device)
+    dinv = op.jacobi_inverse()
+    op.apply(x, out=Ap)
+    k.init(b, Ap, dinv, r, p, sc, n)
+    its = 0
+    while float(sc[3]) > rtol * rtol * float(sc[4]):
+        op.apply(p, out=Ap, dot_out=sc[1:2])
+        k.update_xr(p, Ap, dinv, x, r, sc, n)
+        k.update_p(r, dinv, p, sc)
+        its += 1
+        assert its < 5000
+    assert its == info.iterations
+    assert float((x - x_native).norm() / x.norm()) < 1e-13
