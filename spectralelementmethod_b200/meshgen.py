@@ -135,3 +135,95 @@ def write_gmsh22_binary(path, nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0)
             first += len(node_ix)
         f.write(b"\n$EndElements\n")
     return path
+
+
+def quad_mesh_from_vertices(vertices, quads, p, boundary=None):
+    """Unstructured mesh of straight-sided quadrilaterals of order ``p``.
+
+    vertices : float[V, 2]; quads : int[E, 4] vertex ids in the order
+    (u0, u1) = (0,0), (0,1), (1,0), (1,1) (the lexicographic corner order of
+    ``Quadrilateral``).  High-order nodes are the equispaced bilinear lattice
+    of every cell; nodes on a shared edge get one id (vertices first, then edge
+    interiors, then cell interiors).  ``boundary``: name of a boundary to which
+    every unshared face is assigned (default: none).  Test / example helper for
+    meshes with irregular vertices (3, 5, 6 ... cells around a point)."""
+    vertices = np.asarray(vertices, dtype=np.float64)
+    quads = np.asarray(quads, dtype=np.int64).reshape(-1, 4)
+    n1 = p + 1
+    V, E = len(vertices), len(quads)
+    s = np.linspace(0.0, 1.0, n1)
+    edge_ids = {}
+    coords = [vertices]
+    n_nodes = V
+    maps = np.empty((E, n1, n1), dtype=np.int64)
+    # (corner a, corner b, index expression of the edge from a to b)
+    edges = [(0, 1, lambda k: (0, k)), (2, 3, lambda k: (p, k)),
+             (0, 2, lambda k: (k, 0)), (1, 3, lambda k: (k, p))]
+    face_count = {}
+    for e, q in enumerate(quads):
+        x00, x01, x10, x11 = vertices[q]
+        maps[e, 0, 0], maps[e, 0, p], maps[e, p, 0], maps[e, p, p] = q
+        for a, b, at in edges:
+            va, vb = int(q[a]), int(q[b])
+            key = (min(va, vb), max(va, vb))
+            face_count[key] = face_count.get(key, 0) + 1
+            if p > 1:
+                if key not in edge_ids:
+                    edge_ids[key] = n_nodes
+                    lo, hi = vertices[key[0]], vertices[key[1]]
+                    coords.append(lo + s[1:-1, None] * (hi - lo))
+                    n_nodes += p - 1
+                first = edge_ids[key]
+                for k in range(1, p):
+                    kk = k if va == key[0] else p - k      # position counted from the lower vertex
+                    maps[e][at(k)] = first + kk - 1
+        if p > 1:
+            a, b = np.meshgrid(s[1:-1], s[1:-1], indexing="ij")
+            xy = ((1 - a)[..., None] * ((1 - b)[..., None] * x00 + b[..., None] * x01)
+                  + a[..., None] * ((1 - b)[..., None] * x10 + b[..., None] * x11))
+            maps[e, 1:-1, 1:-1] = n_nodes + np.arange((p - 1) ** 2).reshape(p - 1, p - 1)
+            coords.append(xy.reshape(-1, 2))
+            n_nodes += (p - 1) ** 2
+    mesh = Mesh(2)
+    mesh.set_nodes(np.ascontiguousarray(np.concatenate(coords).T))
+    g = mesh.add_geometry(Quadrilateral(n1, n1))
+    r = mesh.new_region("interior")
+    mesh.add_cells(maps.astype(np.uint32), g, r)
+    if boundary is not None:
+        bid = mesh.new_boundary(boundary)
+        for e, q in enumerate(quads):
+            for face, (a, b) in enumerate(((0, 1), (2, 3), (0, 2), (1, 3))):
+                key = (min(int(q[a]), int(q[b])), max(int(q[a]), int(q[b])))
+                if face_count[key] == 1:
+                    mesh.add_boundary_cell(e, bid, 1, face)
+    return mesh
+
+
+def pinwheel_mesh(n_cells, p, boundary="ebc", rings=1):
+    """``n_cells`` quadrilaterals around one interior vertex (valence
+    ``n_cells``: 3, 5, 6 ... are irregular), optionally surrounded by further
+    rings of cells.  Cell k of ring 0 spans the centre, ray k, ray k+1 and an
+    outer corner between them."""
+    ang = 2.0 * np.pi * np.arange(n_cells) / n_cells
+    half = np.pi / n_cells
+    verts = [np.zeros(2)]
+    ray = lambda rad: [rad * np.array([np.cos(a), np.sin(a)]) for a in ang]          # noqa: E731
+    mid = lambda rad: [rad * np.array([np.cos(a + half), np.sin(a + half)]) for a in ang]   # noqa: E731
+    quads = []
+    verts += ray(1.0) + mid(1.5)
+    A = lambda k: 1 + k % n_cells                       # noqa: E731
+    B = lambda k: 1 + n_cells + k % n_cells             # noqa: E731
+    for k in range(n_cells):
+        quads.append((0, A(k + 1), A(k), B(k)))         # (0,0) centre, (0,1) ray k+1, (1,0) ray k
+    base_a, base_b = A, B
+    for ring in range(1, rings):
+        off = len(verts)
+        verts += ray(1.0 + ring) + mid(1.5 + ring)
+        A2 = lambda k, o=off: o + k % n_cells           # noqa: E731
+        B2 = lambda k, o=off: o + n_cells + k % n_cells  # noqa: E731
+        for k in range(n_cells):
+            # two cells per sector: over the ray and over the corner
+            quads.append((base_a(k), base_b(k), A2(k), B2(k)))
+            quads.append((base_b(k), base_a(k + 1), B2(k), A2(k + 1)))
+        base_a, base_b = A2, B2
+    return quad_mesh_from_vertices(np.array(verts), np.array(quads), p, boundary)

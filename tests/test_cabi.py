@@ -264,6 +264,19 @@ def test_hostplan_scrambled_numbering_and_order():
     assert np.array_equal(ar[_lib.PA_ELEM_OF_SLOT], order)
 
 
+@pytest.mark.parametrize("n_cells,p,rings,pe", [(5, 3, 1, 16), (6, 2, 2, 8), (3, 4, 2, 4), (7, 3, 3, 16)])
+def test_hostplan_irregular_vertices(n_cells, p, rings, pe):
+    """3 / 5 / 6 / 7 cells around a vertex: inverse tables wider than 4 entries."""
+    mesh = meshgen.pinwheel_mesh(n_cells, p, rings=rings)
+    l2g = mesh.node_map_array().reshape(mesh.n_cells, -1)
+    sc, ar = _lib.hostplan(p + 1, l2g, mesh.n_nodes, None, pe, None)
+    check_plan(l2g, mesh.n_nodes, sc, ar, pe)
+    if n_cells >= 5 and pe >= n_cells:
+        assert sc[_lib.PS_INV_WIDTH] == 8
+    if n_cells == 3:
+        assert sc[_lib.PS_INV_WIDTH] == 4
+
+
 def test_hostplan_rejects_bad_input():
     l2g = meshgen.structured_node_maps(2, 2, 2)
     with pytest.raises(ValueError):

@@ -408,3 +408,45 @@ def test_native_pcg_matches_kernel_by_kernel_pcg(rtol, check_every):
         assert its < 5000
     assert its == info.iterations
     assert float((x - x_native).norm() / x.norm()) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_cells,p,rings,pe", [(5, 3, 1, 16), (6, 4, 1, 8), (3, 5, 1, 4), (5, 2, 2, 16),
+                                                (7, 3, 2, 16), (5, 8, 3, 16), (6, 6, 2, 4)])
+def test_irregular_vertices_vs_oracle(n_cells, p, rings, pe):
+    """Unstructured meshes with 3, 5, 6, 7 cells around a vertex: more than four elements
+    of one patch meet in a node, so the inverse tables are 8 entries wide (the wide path
+    of the gather-style assembly).  Apply, diagonal, load vector, PCG and the staged host
+    call against the oracle on the same mesh."""
+    mesh = meshgen.pinwheel_mesh(n_cells, p, rings=rings)
+    b1 = LagrangeGaussLobatto(p)
+    mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+    on = mngr.boundary_node_mask("ebc")
+    l2g = mngr.node_map_array()
+    basis = so.Basis(p)
+    geo = so.geometry(basis, mesh.nodes, l2g)
+    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+    op = mngr.poisson_operator(dirichlet=on, elems_per_patch=pe)
+    if n_cells >= 5 and mesh.n_cells <= pe:      # all cells around the vertex in one patch
+        assert op.plan_scalars[_lib.PS_INV_WIDTH] == 8
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal(op.n_nodes)
+    ref = so.apply_dense_batched(L, l2g, u)
+    y = host(op.apply_unmasked(dev(u)))
+    assert rel_l2(y, ref) < TOL
+    assert rel_l2(host(op.apply_atomic(dev(u), flags=0)), ref) < TOL
+    assert rel_l2(host(op.diagonal(masked=False)),
+                  so.assemble_vector(so.local_diagonal(L), l2g, op.n_nodes)) < TOL
+    bref = so.assemble_vector(geo["JxW"], l2g, op.n_nodes)
+    assert rel_l2(host(op.rhs(1.0)), bref) < TOL
+    # masked operator and solve: u = g on the outer boundary
+    x, yy = mesh.nodes
+    vals = np.where(on, 0.3 * x - 0.2 * yy + 0.1, 0.0)
+    A = so.assemble_csr(L, l2g, op.n_nodes)
+    want = so.solve_direct(A, bref, on, vals)
+    sol, info = op.solve(1.0, dev(vals), rtol=1e-13)
+    assert info.converged and rel_l2(host(sol), want) < 1e-10
+    # pipelined host-buffer call, bit-identical to the device-resident apply
+    yh = np.full(op.n_nodes, np.nan)
+    op.apply_host(u, yh, stages=3)
+    assert np.array_equal(yh, host(op.apply(dev(u))))
