@@ -241,6 +241,15 @@ int semk_gfactors_from_invj_f64(int n1, int64_t n_elem, const double *invJ, cons
                                 const int64_t *elem_of_slot, double *G, int64_t g_patch_stride,
                                 int elems_per_patch, void *stream);
 
+/* Weighted stiffness: G <- weight * G node by node, weight in the reference's
+ * element-local layout [n_elem][NN].  Turns the operator into the stiffness
+ * of -div(weight grad u): the rho-weighted twin of the Poisson recipe, the
+ * four `rho_JxW` einsums of examples/squirmer-axisymmetric.py:194-213
+ * (weight = x_phys[0] there). */
+int semk_scale_gfactors_f64(int n1, int64_t n_elem, const double *weight,
+                            const int64_t *elem_of_slot, double *G, int64_t g_patch_stride,
+                            int elems_per_patch, void *stream);
+
 /* ------------------------------------------------------------------------
  * K2: y = A u, the assembled Poisson stiffness operator, matrix-free.
  * Replaces the dense local apply np.einsum('pqrs,rs', L, u[L2G])

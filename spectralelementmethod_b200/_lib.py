@@ -111,6 +111,7 @@ SIGNATURES = {
     "semk_poisson_apply_host_staged_f64": (_I, [C.POINTER(semk_op), C.POINTER(semk_stage), _I, _P, _P,
                                                 _P, _P, _I, _P]),
     "semk_scratch_row_stride": (_I, [_I, _I]),
+    "semk_scale_gfactors_f64": (_I, [_I, _L, _P, _P, _P, _L, _I, _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
     "semk_peer_open": (_I, [_P, C.POINTER(_P)]),

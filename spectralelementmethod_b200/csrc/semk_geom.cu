@@ -157,6 +157,29 @@ __global__ void gfactors_from_invj_kernel(int n1, int64_t n_elem,
   }
 }
 
+// G <- weight * G, node by node (weight in the reference's element-local layout).
+__global__ void scale_gfactors_kernel(int n1, int64_t n_elem, const double *__restrict__ weight,
+                                      const int64_t *__restrict__ elem_of_slot,
+                                      double *__restrict__ G, int64_t g_patch_stride, int pe) {
+  const int NN = n1 * n1;
+  const int64_t total = n_elem * NN;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t slot = i / NN;
+    const int k = (int)(i - slot * NN);
+    const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
+    const double w = weight[e * NN + k];
+    const int m = k / n1, n = k - m * n1;
+    const int64_t patch = slot / pe;
+    const int lp = (int)(slot - patch * pe);
+    const int64_t row = (int64_t)n1 * pe;
+    double *gs = G + patch * g_patch_stride + (int64_t)m * row + lp * n1 + n;
+    gs[0] *= w;
+    gs[n1 * row] *= w;
+    gs[2 * n1 * row] *= w;
+  }
+}
+
 }  // namespace
 
 extern "C" int semk_geom_factors_f64(int n1, int64_t n_elem, const double *nodes_x,
@@ -201,5 +224,24 @@ extern "C" int semk_gfactors_from_invj_f64(int n1, int64_t n_elem, const double 
   gfactors_from_invj_kernel<<<grid, block, 0, semk_stream(stream)>>>(
       n1, n_elem, invJ, JxW, elem_of_slot, G, g_patch_stride, elems_per_patch);
   SEMK_LAUNCH_CHECK("gfactors_from_invj_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_scale_gfactors_f64(int n1, int64_t n_elem, const double *weight,
+                                       const int64_t *elem_of_slot, double *G,
+                                       int64_t g_patch_stride, int elems_per_patch,
+                                       void *stream) {
+  SEMK_REQUIRE(n1 >= 2 && n1 <= SEMK_MAX_N1, "semk_scale_gfactors_f64: bad n1");
+  SEMK_REQUIRE(weight && G, "semk_scale_gfactors_f64: null pointer");
+  SEMK_REQUIRE(elems_per_patch >= 1 && g_patch_stride >= (int64_t)3 * n1 * n1 * elems_per_patch,
+               "semk_scale_gfactors_f64: g_patch_stride too small");
+  if (n_elem <= 0) return SEMK_OK;
+  const int64_t total = n_elem * n1 * n1;
+  const int block = 256;
+  const int64_t want = (total + block - 1) / block;
+  const unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
+  scale_gfactors_kernel<<<grid, block, 0, semk_stream(stream)>>>(n1, n_elem, weight, elem_of_slot, G,
+                                                                g_patch_stride, elems_per_patch);
+  SEMK_LAUNCH_CHECK("scale_gfactors_kernel");
   return SEMK_OK;
 }

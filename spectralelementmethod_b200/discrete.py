@@ -241,6 +241,10 @@ class DOFManager(object):
             use externally supplied factors (e.g. the reference's own
             ``fe.invJ`` / ``fe.detJxW``) instead of the device geometry kernel
             (parity tier T1).
+        weight (keyword) : float[E, N, N] element-local nodal values or a
+            callable ``w(x, y)`` on device tensors -- the operator becomes the
+            stiffness of -div(w grad u) (the rho-weighted twin of the recipe,
+            examples/squirmer-axisymmetric.py:194-213).
         """
         if self._dpn != 1:
             raise NotImplementedError("poisson_operator supports one DOF per node")

@@ -134,7 +134,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, tile=None):
+                 elem_order=None, keep_l2g=True, tile=None, weight=None):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -196,14 +196,17 @@ class PoissonOperator(object):
         self.G = torch.zeros((self.n_patch, self.g_patch_stride), **f64)
         self.JxW = torch.empty((self.n_elem, NN), **f64)
         self.l2g_dev = device.as_i32_bits(l2g, self.dev)
+        x_phys = None
         if geometric_factors is None:
             nodes_dev = torch.from_numpy(np.ascontiguousarray(mesh.nodes, dtype=np.float64)).to(self.dev)
             if nodes_dev.shape[0] != 2:
                 raise NotImplementedError("Only supporting 2D elements right now")
+            if callable(weight):
+                x_phys = torch.empty((self.n_elem, 2, NN), **f64)
             device.geom_factors(self.tab, nodes_dev, self.l2g_dev, self.n_elem,
                                 elem_of_slot=t[_lib.PA_ELEM_OF_SLOT], G=self.G,
                                 g_patch_stride=self.g_patch_stride, elems_per_patch=pe,
-                                JxW=self.JxW)
+                                JxW=self.JxW, x_phys=x_phys)
             del nodes_dev
         else:
             invJ, jxw = geometric_factors
@@ -215,6 +218,26 @@ class PoissonOperator(object):
                 device.stream_ptr()))
             torch.cuda.current_stream().synchronize()
             del invJ
+        # weighted stiffness -div(w grad u): scale the geometric factors node by node (the
+        # rho_JxW einsums of examples/squirmer-axisymmetric.py:194-213 with w = x_phys[0])
+        self.weighted = weight is not None
+        if weight is not None:
+            if callable(weight):
+                if x_phys is None:
+                    raise ValueError("a callable weight needs the device geometry "
+                                     "(geometric_factors=None)")
+                w = weight(x_phys[:, 0, :], x_phys[:, 1, :])
+                w = torch.as_tensor(w, dtype=torch.float64, device=self.dev).expand(self.n_elem, NN)
+            else:
+                w = device._f64(np.asarray(weight, dtype=np.float64).reshape(self.n_elem, NN),
+                                self.dev)
+            w = w.contiguous()
+            _lib.check(self._lib.semk_scale_gfactors_f64(
+                n1, self.n_elem, device.ptr(w), device.ptr(t[_lib.PA_ELEM_OF_SLOT]),
+                device.ptr(self.G), self.g_patch_stride, pe, device.stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+            del w
+        del x_phys
         if not keep_l2g:
             self.l2g_dev = None
 

@@ -450,3 +450,29 @@ def test_irregular_vertices_vs_oracle(n_cells, p, rings, pe):
     yh = np.full(op.n_nodes, np.nan)
     op.apply_host(u, yh, stages=3)
     assert np.array_equal(yh, host(op.apply(dev(u))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,nx,ny,p,as_callable", [("C", 6, 5, 8, True), ("S", 4, 7, 5, False),
+                                                     ("C", 3, 3, 10, True)])
+def test_weighted_stiffness_vs_oracle(kind, nx, ny, p, as_callable):
+    """rho-weighted twin of the stiffness recipe (the four `rho_JxW` einsums of
+    examples/squirmer-axisymmetric.py:194-213): weight w = 2 + x at the GLL points."""
+    mesh, mngr = build_package_case(kind, nx, ny, p, False, False)
+    r = so.run_case(kind, nx, ny, p, False, False, solve=False)
+    basis = so.Basis(p)
+    geo = so.geometry(basis, r["nodes"], r["l2g"])
+    rho = 2.0 + geo["x_phys"][:, 0]
+    L = so.local_stiffness(basis, geo["invJ"], rho * geo["JxW"])
+    if as_callable:
+        op = mngr.poisson_operator(weight=lambda x, y: 2.0 + x)
+    else:
+        op = mngr.poisson_operator(weight=rho)
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(mngr.ndof)
+    ref = so.apply_dense_batched(L, r["l2g"], u)
+    assert rel_l2(host(op.apply_unmasked(dev(u))), ref) < TOL
+    assert rel_l2(host(op.diagonal(masked=False)),
+                  so.assemble_vector(so.local_diagonal(L), r["l2g"], mngr.ndof)) < TOL
+    # the load vector is not weighted
+    assert rel_l2(host(op.rhs(1.0)), so.assemble_vector(geo["JxW"], r["l2g"], mngr.ndof)) < TOL
