@@ -395,8 +395,9 @@ def run_engine(args):
             "config": {"workload": workload, "order": ORDER, "dof_total": int(n_global_units),
                        "dof_per_gpu": int(n_local), "elements_per_gpu": int(op.n_elem),
                        "elems_per_patch": op.elems_per_patch, "kind": args.kind,
-                       "resident_ctas": getattr(op, "resident_ctas", None) if not multi else None,
-                       "smem_bytes_per_cta": getattr(op, "smem_bytes", None) if not multi else None,
+                       "resident_ctas": getattr(op, "resident_ctas", None),
+                       "grid_cap": getattr(op, "max_ctas", 0) or None,
+                       "smem_bytes_per_cta": getattr(op, "smem_bytes", None),
                        "l2_policy": "inputs (>= 2.6 GB per GPU) exceed the 126 MB L2; no flush",
                        "setup_seconds": t_setup},
             "roofline": roofline,

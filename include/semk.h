@@ -83,7 +83,7 @@ enum semk_plan_array {
   SEMK_PA_ELOC = 4,           /* uint16 [n_patch][eloc_patch_stride]: per patch a table
                                  [m][le][t] (NN*PE entries) of patch-local node indices:
                                  node (m,t) of the le-th element of the patch            */
-  SEMK_PA_ELEM_OF_SLOT = 5,   /* int64  [n_elem]      element id stored at engine slot s     */
+  SEMK_PA_ELEM_OF_SLOT = 5,   /* int64  [n_order]     element id stored at engine slot s, -1 = empty */
   SEMK_PA_SHARED_NODE = 6,    /* uint32 [n_shared]    global id | flags, ascending id        */
   SEMK_PA_SHARED_PTR = 7,     /* int32  [n_shared+1]  offsets into SHARED_SLOT               */
   SEMK_PA_SHARED_SLOT = 8,    /* int32  [n_slots]     interface slots of each shared node,
@@ -147,13 +147,16 @@ enum semk_plan_scalar {
 };
 
 /* l2g: host uint32 [n_elem][NN] (the reference's cell.node_ind_lexicographic,
- *      sem/discrete.py:810-812, stacked).  elem_order: host int64 [n_elem]
- *      permutation, slot -> element (NULL = identity); consecutive runs of
- *      elems_per_patch slots form one patch.  dirichlet: host uint8 [n_nodes]
- *      (1 = essential-BC node, the reference's on_ebc polarity,
- *      sem/discrete.py:505) or NULL. */
+ *      sem/discrete.py:810-812, stacked).  elem_order: host int64 [n_order]
+ *      engine order, slot -> element (NULL = identity, n_order ignored);
+ *      consecutive runs of elems_per_patch slots form one patch.  Every
+ *      element appears exactly once; entries equal to -1 are EMPTY slots
+ *      (padding that keeps patches compact tiles when the mesh is not a whole
+ *      number of tiles); no patch may consist of empty slots only.
+ *      dirichlet: host uint8 [n_nodes] (1 = essential-BC node, the reference's
+ *      on_ebc polarity, sem/discrete.py:505) or NULL. */
 int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
-                         const int64_t *elem_order, int elems_per_patch,
+                         const int64_t *elem_order, int64_t n_order, int elems_per_patch,
                          const uint8_t *dirichlet, semk_hostplan **out);
 int64_t semk_hostplan_scalar(const semk_hostplan *plan, int which);
 const void *semk_hostplan_array(const semk_hostplan *plan, int which, int64_t *n_bytes);
@@ -166,10 +169,16 @@ void semk_hostplan_destroy(semk_hostplan *plan);
 typedef struct semk_op {
   int32_t n1;               /* points per direction */
   int32_t elems_per_patch;
-  int64_t n_elem;
+  int64_t n_elem;           /* engine slots: elements + empty padding slots (n_order of the plan) */
   int64_t n_nodes;
   int64_t n_patch;
   int64_t max_patch_nodes;
+  int64_t max_ctas;         /* 0, or a cap on the persistent grid of the apply kernel.  CTA b runs
+                               patches b, b + grid, ...: when the grid is a multiple of the
+                               number of patches per tile column of a structured mesh every
+                               CTA stays on one tile row for ever and the apply runs ~10 %
+                               slower (measured: 111 tiles per column, grid 444); capping the
+                               grid at resident - 1 removes the resonance                   */
   int64_t g_patch_stride;   /* doubles per patch block of G (even, >= 3*NN*PE)          */
   const double *G;          /* [n_patch][g_patch_stride]; inside a patch block the factor
                                c (0: G00, 1: G01, 2: G11) at node (m, t) of the le-th

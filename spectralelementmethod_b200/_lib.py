@@ -55,7 +55,7 @@ class semk_op(C.Structure):
     _fields_ = [
         ("n1", C.c_int32), ("elems_per_patch", C.c_int32),
         ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("n_patch", C.c_int64),
-        ("max_patch_nodes", C.c_int64),
+        ("max_patch_nodes", C.c_int64), ("max_ctas", C.c_int64),
         ("g_patch_stride", C.c_int64), ("G", C.c_void_p),
         ("patch_hdr", C.c_void_p), ("pnode", C.c_void_p), ("pn_patch_stride", C.c_int64),
         ("eloc", C.c_void_p), ("eloc_patch_stride", C.c_int64),
@@ -84,7 +84,7 @@ SIGNATURES = {
     "semk_version": (_I, []),
     "semk_last_error": (C.c_char_p, []),
     "semk_device_available": (_I, []),
-    "semk_hostplan_create": (_I, [_I, _L, _L, _P, _P, _I, _P, C.POINTER(_P)]),
+    "semk_hostplan_create": (_I, [_I, _L, _L, _P, _P, _L, _I, _P, C.POINTER(_P)]),
     "semk_hostplan_scalar": (_L, [_P, _I]),
     "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
     "semk_hostplan_destroy": (None, [_P]),
@@ -177,8 +177,8 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
     order_p = None
     if elem_order is not None:
         elem_order = np.ascontiguousarray(elem_order, dtype=np.int64)
-        if elem_order.shape != (n_elem,):
-            raise ValueError("elem_order must have one entry per element")
+        if elem_order.ndim != 1 or elem_order.size < n_elem:
+            raise ValueError("elem_order must have one entry per element (plus -1 padding slots)")
         order_p = elem_order.ctypes.data
     dir_p = None
     if dirichlet is not None:
@@ -187,7 +187,8 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
             raise ValueError("dirichlet mask must have one entry per node")
         dir_p = dirichlet.ctypes.data
     handle = _P()
-    check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p,
+    n_order = 0 if elem_order is None else int(elem_order.size)
+    check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p, n_order,
                                    int(elems_per_patch), dir_p, C.byref(handle)))
     try:
         scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(PS_COUNT)}

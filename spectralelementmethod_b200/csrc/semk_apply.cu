@@ -771,12 +771,14 @@ __global__ void __launch_bounds__(PatchCfg<N, PEA>::kThreads)
   const int tid = threadIdx.x;
   const int le = tid / N, t = tid - le * N;
   const int64_t slot = (int64_t)blockIdx.x * PEA + le;
-  const bool active = (le < PEA) && (slot < n_elem);
+  bool active = (le < PEA) && (slot < n_elem);
+  int64_t e = -1;
+  if (active) e = elem_of_slot ? elem_of_slot[slot] : slot;
+  active = active && e >= 0;  // (a negative entry is an empty slot of the engine order)
   double ucol[N], ycol[N];
   uint32_t gid[N];
   const double *g = G;
   if (active) {
-    const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
     const uint32_t *row = l2g + e * NN;
 #pragma unroll
     for (int m = 0; m < N; ++m) {
@@ -842,8 +844,11 @@ __global__ void weighted_local_kernel(int NN, int64_t n_elem, const double *__re
     const int64_t slot = i / NN;
     const int k = (int)(i - slot * NN);
     const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
-    double v = JxW[e * NN + k];
-    if (f) v *= f[l2g[e * NN + k]];
+    double v = 0.0;  // empty slot
+    if (e >= 0) {
+      v = JxW[e * NN + k];
+      if (f) v *= f[l2g[e * NN + k]];
+    }
     loc[i] = v;
   }
 }
@@ -892,7 +897,10 @@ struct PatchLaunch {
     // persistent grid: every CTA stays resident and loops over its patches, round-robin
     const int64_t resident = (int64_t)per_sm * sms;
     const int64_t np = pe - pb;
-    const unsigned grid = (unsigned)(np < resident ? np : resident);
+    // (op.max_ctas: the caller may cap the grid, e.g. to keep it from being a multiple of
+    // the number of patches per tile column -- see semk.h)
+    const int64_t want = (op.max_ctas > 0 && op.max_ctas < resident) ? op.max_ctas : resident;
+    const unsigned grid = (unsigned)(np < want ? np : want);
     if (grid_out) *grid_out = (int)grid;
     if (grid == 0) return SEMK_OK;
     patch_kernel<N, PE, MODE><<<grid, PatchCfg<N, PE>::kThreads, smem, st>>>(

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(((N * N + 31) / 32) * 32)
 
   for (int64_t slot = blockIdx.x; slot < n_elem; slot += gridDim.x) {
     const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
+    if (e < 0) continue;  // empty slot of the engine order (uniform over the CTA): G stays 0
     const uint32_t *row = l2g + e * NN;
     const uint32_t g0 = row[0];
     const double ox = nodes_x[g0], oy = nodes_y[g0];
@@ -143,6 +144,7 @@ __global__ void gfactors_from_invj_kernel(int n1, int64_t n_elem,
     const int64_t slot = i / NN;
     const int k = (int)(i - slot * NN);
     const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
+    if (e < 0) continue;
     const double *ip = invJ + e * 4 * NN;
     const double i00 = ip[k], i01 = ip[NN + k], i10 = ip[2 * NN + k], i11 = ip[3 * NN + k];
     const double jw = JxW[e * NN + k];
@@ -168,6 +170,7 @@ __global__ void scale_gfactors_kernel(int n1, int64_t n_elem, const double *__re
     const int64_t slot = i / NN;
     const int k = (int)(i - slot * NN);
     const int64_t e = elem_of_slot ? elem_of_slot[slot] : slot;
+    if (e < 0) continue;
     const double w = weight[e * NN + k];
     const int m = k / n1, n = k - m * n1;
     const int64_t patch = slot / pe;

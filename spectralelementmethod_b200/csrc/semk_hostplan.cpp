@@ -45,8 +45,9 @@ extern "C" int semk_scratch_row_stride(int n1, int elems_per_patch) {
 }
 
 extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
-                                    const int64_t *elem_order, int elems_per_patch,
-                                    const uint8_t *dirichlet, semk_hostplan **out) {
+                                    const int64_t *elem_order, int64_t n_order,
+                                    int elems_per_patch, const uint8_t *dirichlet,
+                                    semk_hostplan **out) {
   if (!out) return SEMK_ERR_INVALID;
   *out = nullptr;
   if (n1 < 2 || n1 > SEMK_MAX_N1) {
@@ -76,22 +77,51 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     P->pe = PE;
     P->n_elem = n_elem;
     P->n_nodes = n_nodes;
-    const int64_t n_patch = (n_elem + PE - 1) / PE;
+    // The engine order may contain EMPTY slots (-1): padding that keeps every patch a
+    // compact tile when the mesh is not a whole number of tiles.
+    if (!elem_order || n_order <= 0) n_order = n_elem;
+    if (n_order < n_elem) {
+      delete P;
+      semk_set_error("semk_hostplan_create: elem_order shorter than the number of elements");
+      return SEMK_ERR_INVALID;
+    }
+    const int64_t n_patch = (n_order + PE - 1) / PE;
     const int64_t n_slot_elems = n_patch * PE;
 
     // slot -> element
-    P->elem_of_slot.resize(n_elem);
+    P->elem_of_slot.resize(n_order);
     {
       std::vector<uint8_t> seen(n_elem, 0);
-      for (int64_t s = 0; s < n_elem; ++s) {
+      int64_t n_seen = 0;
+      for (int64_t s = 0; s < n_order; ++s) {
         int64_t e = elem_order ? elem_order[s] : s;
+        if (e == -1) {
+          P->elem_of_slot[s] = -1;
+          continue;
+        }
         if (e < 0 || e >= n_elem || seen[e]) {
           delete P;
           semk_set_error("semk_hostplan_create: elem_order is not a permutation");
           return SEMK_ERR_INVALID;
         }
         seen[e] = 1;
+        ++n_seen;
         P->elem_of_slot[s] = e;
+      }
+      if (n_seen != n_elem) {
+        delete P;
+        semk_set_error("semk_hostplan_create: elem_order is not a permutation");
+        return SEMK_ERR_INVALID;
+      }
+      for (int64_t p = 0; p < n_patch; ++p) {
+        bool any = false;
+        for (int64_t s = p * PE; s < std::min<int64_t>((p + 1) * PE, n_order); ++s)
+          any = any || P->elem_of_slot[s] >= 0;
+        if (!any) {
+          delete P;
+          semk_set_error("semk_hostplan_create: a patch consists of empty slots only");
+          return SEMK_ERR_INVALID;
+        }
       }
     }
     for (int64_t i = 0; i < n_elem * NN; ++i) {
@@ -106,8 +136,9 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     std::vector<int32_t> first_patch(n_nodes, -1);
     std::vector<uint8_t> multi(n_nodes, 0);  // 0 private, 1 shared (interface slots)
     for (int64_t p = 0; p < n_patch; ++p) {
-      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
+      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_order);
       for (int64_t s = s0; s < s1; ++s) {
+        if (P->elem_of_slot[s] < 0) continue;
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         for (int k = 0; k < NN; ++k) {
           const uint32_t g = row[k];
@@ -142,10 +173,11 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
     std::vector<std::pair<int32_t, int32_t>> slot_pairs;  // (shared index, slot)
     int64_t max_patch_nodes = 0, n_slots = 0;
     for (int64_t p = 0; p < n_patch; ++p) {
-      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_elem);
+      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_order);
       priv.clear();
       shar.clear();
       for (int64_t s = s0; s < s1; ++s) {
+        if (P->elem_of_slot[s] < 0) continue;
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         for (int k = 0; k < NN; ++k) {
           const uint32_t g = row[k];
@@ -193,8 +225,10 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       P->patch_nnodes[p] = np + ns;
       max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
 
-      // element-local index table
+      // element-local index table (empty slots keep index 0: a valid node of the patch;
+      // their geometric factors are zero, so they contribute exact zeros)
       for (int64_t s = s0; s < s1; ++s) {
+        if (P->elem_of_slot[s] < 0) continue;
         const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
         uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
         const int le = (int)(s - s0);
@@ -370,11 +404,12 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       std::vector<int32_t> cnt(max_patch_nodes, 0);
       for (int64_t p = 0; p < n_patch; ++p) {
         const uint16_t *eb = P->eloc.data() + (size_t)p * ES;
-        const int64_t live = std::min<int64_t>(PE, n_elem - p * PE);
+        const int64_t live = std::min<int64_t>(PE, n_order - p * PE);
         std::fill(cnt.begin(), cnt.end(), 0);
         for (int m = 0; m < n1; ++m)
           for (int64_t le = 0; le < live; ++le)
             for (int t = 0; t < n1; ++t) {
+              if (P->elem_of_slot[p * PE + le] < 0) continue;
               const int32_t c = ++cnt[eb[((size_t)m * PE + le) * n1 + t]];
               if (c > inv_width) inv_width = (c + 3) & ~3;
             }
@@ -425,13 +460,15 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         std::fill(iblk.begin(), iblk.end(), (uint16_t)0xffff);
         std::fill(fill.begin(), fill.end(), 0);
         {
-          const int64_t live = std::min<int64_t>(PE, n_elem - p * PE);
-          for (int64_t le = 0; le < live; ++le)      // ascending element slot: fixed sum order
+          const int64_t live = std::min<int64_t>(PE, n_order - p * PE);
+          for (int64_t le = 0; le < live; ++le) {    // ascending element slot: fixed sum order
+            if (P->elem_of_slot[p * PE + le] < 0) continue;
             for (int m = 0; m < n1; ++m)
               for (int t = 0; t < n1; ++t) {
                 const int32_t loc = eblk[((size_t)m * PE + le) * n1 + t];
                 iblk[(size_t)loc * inv_width + fill[loc]++] = (uint16_t)(m * RS + le * n1 + t);
               }
+          }
         }
         const int32_t pi = find_or_add(pn_seen, P->pnblk, pblk, pn_stride);
         const int32_t ei = find_or_add(el_seen, P->elblk, eblk, el_stride);

@@ -109,9 +109,16 @@ def default_element_order(mesh, elems_per_patch, tile=None):
         ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
         # tiles enumerated along the contiguous node direction: the resident CTAs work
         # on a compact window of the mesh at any time (best DRAM / L2 locality)
-        tile_id = (ex // bx) * ((ny + by - 1) // by) + ey // by
+        ntx, nty = (nx + bx - 1) // bx, (ny + by - 1) // by
+        tile_id = (ex // bx) * nty + ey // by
         key = tile_id * (bx * by) + (ex % bx) * by + ey % by
-        return np.argsort(key, kind="stable").astype(np.int64)
+        if nx % bx == 0 and ny % by == 0:
+            return np.argsort(key, kind="stable").astype(np.int64)
+        # the mesh is not a whole number of tiles: one patch per tile all the same, the
+        # missing elements of the ragged tiles become empty slots (-1)
+        order = np.full(ntx * nty * bx * by, -1, dtype=np.int64)
+        order[key] = np.arange(nx * ny, dtype=np.int64)
+        return order
     if not hasattr(mesh, "_centroids"):
         mesh._compute_cell_centroids()
     return _morton_order(mesh._centroids[:, 0], mesh._centroids[:, 1])
@@ -143,7 +150,7 @@ class PoissonOperator(object):
         n1 = self.n1 = self.tab.n1
         NN = n1 * n1
         l2g = mesh.node_map_array().reshape(-1, NN)
-        self.n_elem = int(l2g.shape[0])
+        self.n_elem = int(l2g.shape[0])          # elements; engine slots: self.n_order
         self.n_nodes = int(mesh.n_nodes)
         self.dev = torch.device("cuda", torch.cuda.current_device())
 
@@ -155,9 +162,12 @@ class PoissonOperator(object):
         self.has_dirichlet = dirichlet is not None and bool(dirichlet.any())
 
         pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
+        user_order = elem_order is not None
         if elem_order is None:
             elem_order = default_element_order(mesh, pe, tile)
         sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
+        # engine slots = elements + empty padding slots (-1 entries of the order)
+        self.n_order = int(ar[_lib.PA_ELEM_OF_SLOT].size)
         actual = int(self._lib.semk_resident_ctas(
             n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
             int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_INV_STRIDE])))
@@ -167,6 +177,16 @@ class PoissonOperator(object):
                 "elems_per_patch or a more local elem_order" % (pe, _lib.last_error()))
         self.plan_scalars = sc
         self.resident_ctas = actual
+        # CTA b of the persistent kernel runs patches b, b + grid, ...; a grid that is a
+        # multiple of the patches per tile column would pin every CTA to one tile row (a
+        # measured 10 % slowdown): step off the resonance by one CTA
+        self.max_ctas = 0
+        shape = getattr(mesh, "_structured_shape", None)
+        if shape is not None and not user_order:
+            by = (tile if tile is not None else _TILES[pe])[1]
+            per_column = -(-shape[1] // by)
+            if per_column > 1 and actual > 1 and (actual % per_column == 0 or per_column % actual == 0):
+                self.max_ctas = actual - 1
         smem = patch_smem_bytes(n1, pe, sc[_lib.PS_MAX_PATCH_NODES], sc[_lib.PS_PN_STRIDE],
                                 sc[_lib.PS_INV_STRIDE])
         self.smem_bytes = smem
@@ -203,7 +223,7 @@ class PoissonOperator(object):
                 raise NotImplementedError("Only supporting 2D elements right now")
             if callable(weight):
                 x_phys = torch.empty((self.n_elem, 2, NN), **f64)
-            device.geom_factors(self.tab, nodes_dev, self.l2g_dev, self.n_elem,
+            device.geom_factors(self.tab, nodes_dev, self.l2g_dev, self.n_order,
                                 elem_of_slot=t[_lib.PA_ELEM_OF_SLOT], G=self.G,
                                 g_patch_stride=self.g_patch_stride, elems_per_patch=pe,
                                 JxW=self.JxW, x_phys=x_phys)
@@ -213,7 +233,7 @@ class PoissonOperator(object):
             invJ = device._f64(np.asarray(invJ).reshape(self.n_elem, 4, NN), self.dev)
             self.JxW.copy_(device._f64(np.asarray(jxw).reshape(self.n_elem, NN), self.dev))
             _lib.check(self._lib.semk_gfactors_from_invj_f64(
-                n1, self.n_elem, device.ptr(invJ), device.ptr(self.JxW),
+                n1, self.n_order, device.ptr(invJ), device.ptr(self.JxW),
                 device.ptr(t[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G), self.g_patch_stride, pe,
                 device.stream_ptr()))
             torch.cuda.current_stream().synchronize()
@@ -233,7 +253,7 @@ class PoissonOperator(object):
                                 self.dev)
             w = w.contiguous()
             _lib.check(self._lib.semk_scale_gfactors_f64(
-                n1, self.n_elem, device.ptr(w), device.ptr(t[_lib.PA_ELEM_OF_SLOT]),
+                n1, self.n_order, device.ptr(w), device.ptr(t[_lib.PA_ELEM_OF_SLOT]),
                 device.ptr(self.G), self.g_patch_stride, pe, device.stream_ptr()))
             torch.cuda.current_stream().synchronize()
             del w
@@ -250,8 +270,9 @@ class PoissonOperator(object):
 
         op = _lib.semk_op()
         op.n1, op.elems_per_patch = n1, pe
-        op.n_elem, op.n_nodes, op.n_patch = self.n_elem, self.n_nodes, self.n_patch
+        op.n_elem, op.n_nodes, op.n_patch = self.n_order, self.n_nodes, self.n_patch
         op.max_patch_nodes = sc[_lib.PS_MAX_PATCH_NODES]
+        op.max_ctas = self.max_ctas
         op.g_patch_stride = self.g_patch_stride
         op.G = self.G.data_ptr()
         op.patch_hdr = t[_lib.PA_PATCH_HDR].data_ptr()
@@ -325,7 +346,7 @@ class PoissonOperator(object):
         if flags is None:
             flags = self._masked_flags
         _lib.check(self._lib.semk_poisson_apply_atomic_f64(
-            self.n1, self.n_elem, self.n_nodes, device.ptr(self.l2g_dev),
+            self.n1, self.n_order, self.n_nodes, device.ptr(self.l2g_dev),
             device.ptr(self._tables[_lib.PA_ELEM_OF_SLOT]), device.ptr(self.G),
             self.g_patch_stride, self.elems_per_patch,
             device.ptr(self.tab.D_host), device.ptr(self.dirichlet_dev), device.ptr(u),
@@ -409,7 +430,7 @@ class PoissonOperator(object):
         loc = torch.empty((self.n_slot_elems, self.n1 * self.n1), dtype=torch.float64,
                           device=self.dev)
         _lib.check(self._lib.semk_weighted_local_f64(
-            self.n1, self.n_elem, self.n_slot_elems, device.ptr(self.JxW),
+            self.n1, self.n_order, self.n_slot_elems, device.ptr(self.JxW),
             device.ptr(self.l2g_dev), device.ptr(self._tables[_lib.PA_ELEM_OF_SLOT]),
             device.ptr(fv), device.ptr(loc), device.stream_ptr()))
         b = self.assemble(loc)

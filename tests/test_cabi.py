@@ -34,7 +34,7 @@ def test_version_and_error_channel():
     lib = _lib.load()
     assert lib.semk_version() == 100
     out = ctypes.c_void_p()
-    rc = lib.semk_hostplan_create(1, 1, 1, None, None, 16, None, ctypes.byref(out))
+    rc = lib.semk_hostplan_create(1, 1, 1, None, None, 0, 16, None, ctypes.byref(out))
     assert rc == _lib.ERR_UNSUPPORTED and b"n1" in lib.semk_last_error()
     with pytest.raises(NotImplementedError):
         _lib.check(rc)
@@ -72,7 +72,9 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     NN = l2g.shape[1]
     E = l2g.shape[0]
     n_patch = sc[_lib.PS_N_PATCH]
-    assert n_patch == -(-E // pe) and sc[_lib.PS_N_SLOT_ELEMS] == n_patch * pe
+    eos = ar[_lib.PA_ELEM_OF_SLOT]
+    n_order = eos.size                      # engine slots: elements + empty (-1) padding slots
+    assert n_patch == -(-n_order // pe) and sc[_lib.PS_N_SLOT_ELEMS] == n_patch * pe
     ptr = ar[_lib.PA_PATCH_NODE_PTR]
     pnode = ar[_lib.PA_PNODE]
     npriv = ar[_lib.PA_PATCH_NPRIV]
@@ -85,8 +87,7 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
     eloc = eloc.transpose(0, 2, 1, 3).reshape(-1, NN)
     nnodes = ar[_lib.PA_PATCH_NNODES]
     assert np.all(ptr % 4 == 0)
-    eos = ar[_lib.PA_ELEM_OF_SLOT]
-    assert sorted(eos.tolist()) == list(range(E))
+    assert sorted(eos[eos >= 0].tolist()) == list(range(E)) and np.all(eos >= -1)
     pad = pnode == 0xFFFFFFFF
     ids = pnode & _lib.NODE_ID_MASK
     shared_flag = ((pnode & _lib.NODE_SHARED) != 0) & ~pad
@@ -113,9 +114,13 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         assert base[p] == slots_seen
         slots_seen += (b - a) - c1
         touched[loc_ids] += 1
-        s0, s1 = p * pe, min((p + 1) * pe, E)
-        # eloc reproduces the L2G rows of the patch's elements
-        assert np.array_equal(loc_ids[eloc[s0:s1].astype(int)], l2g[eos[s0:s1]])
+        s0, s1 = p * pe, min((p + 1) * pe, n_order)
+        live = np.flatnonzero(eos[s0:s1] >= 0) + s0
+        assert live.size >= 1
+        # eloc reproduces the L2G rows of the patch's elements (empty slots: index 0)
+        assert np.array_equal(loc_ids[eloc[live].astype(int)], l2g[eos[live]])
+        holes = np.setdiff1d(np.arange(s0, s1), live)
+        assert np.all(eloc[holes] == 0)
         assert (b - a) <= sc[_lib.PS_MAX_PATCH_NODES]
     assert slots_seen == sc[_lib.PS_N_SLOTS]
     # private <=> touched by exactly one patch
@@ -152,10 +157,11 @@ def check_plan(l2g, n_nodes, sc, ar, pe, dirichlet=None):
         W, RS = sc[_lib.PS_INV_WIDTH], ((n1 * pe - 1 + 15) & ~15) + 1
         assert W % 4 == 0 and W >= 4 and sc[_lib.PS_INV_STRIDE] == PS * W and h[7] < niu
         ib = invblk[h[7]].reshape(PS, W)
-        live = min(pe, E - p * pe)
         tab = eb[:NN * pe].reshape(n1, pe, n1)
         want_inv = [[] for _ in range(nnodes[p])]
-        for le in range(live):
+        for le in range(min(pe, n_order - p * pe)):
+            if eos[p * pe + le] < 0:
+                continue
             for m in range(n1):
                 for t in range(n1):
                     want_inv[tab[m, le, t]].append(m * RS + le * n1 + t)
@@ -275,6 +281,25 @@ def test_hostplan_irregular_vertices(n_cells, p, rings, pe):
         assert sc[_lib.PS_INV_WIDTH] == 8
     if n_cells == 3:
         assert sc[_lib.PS_INV_WIDTH] == 4
+
+
+def test_hostplan_ragged_tiles_are_padded():
+    """A mesh that is not a whole number of 2x8 tiles: the default order pads the ragged
+    tiles with empty slots, so every patch stays one compact tile."""
+    nx, ny, p, pe = 5, 20, 3, 16
+    mesh = meshgen.structured_quad_mesh(nx, ny, p)
+    order = operators.default_element_order(mesh, pe)
+    assert order.size == 3 * 3 * 16 and (order == -1).sum() == 3 * 3 * 16 - nx * ny
+    l2g, n_nodes, sc, ar = _plan(nx, ny, p, pe, order, None)
+    check_plan(l2g, n_nodes, sc, ar, pe)
+    assert sc[_lib.PS_N_PATCH] == 9
+    assert sc[_lib.PS_MAX_PATCH_NODES] == (2 * p + 1) * (8 * p + 1)     # never more than a full tile
+    # holes inside a patch, and a patch of holes only is rejected
+    bad = np.concatenate([np.arange(nx * ny), np.full(16, -1)])
+    with pytest.raises(ValueError):
+        _lib.hostplan(p + 1, l2g, n_nodes, bad, pe, None)
+    with pytest.raises(ValueError):
+        _lib.hostplan(p + 1, l2g, n_nodes, np.arange(nx * ny - 1), pe, None)   # an element missing
 
 
 def test_hostplan_rejects_bad_input():

@@ -476,3 +476,29 @@ def test_weighted_stiffness_vs_oracle(kind, nx, ny, p, as_callable):
                   so.assemble_vector(so.local_diagonal(L), r["l2g"], mngr.ndof)) < TOL
     # the load vector is not weighted
     assert rel_l2(host(op.rhs(1.0)), so.assemble_vector(geo["JxW"], r["l2g"], mngr.ndof)) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny,p,pe", [(5, 20, 4, 16), (3, 11, 8, 16), (7, 9, 3, 8), (2, 5, 6, 4)])
+def test_ragged_tiles_padded_with_empty_slots(nx, ny, p, pe):
+    """Meshes that are not a whole number of tiles: empty slots in the engine order keep the
+    patches compact; they must contribute exact zeros everywhere."""
+    mesh, mngr = build_package_case("C", nx, ny, p, False, False)
+    r = so.run_case("C", nx, ny, p, False, False, solve=True)
+    op = mngr.poisson_operator(dirichlet=r["on_ebc"], elems_per_patch=pe)
+    assert op.n_order > op.n_elem
+    rng = np.random.default_rng(9)
+    u = rng.standard_normal(mngr.ndof)
+    ref = so.apply_dense_batched(r["L"], r["l2g"], u)
+    assert rel_l2(host(op.apply_unmasked(dev(u))), ref) < TOL
+    assert rel_l2(host(op.apply_atomic(dev(u), flags=0)), ref) < TOL
+    assert rel_l2(host(op.diagonal(masked=False)), r["diag"]) < TOL
+    assert rel_l2(host(op.rhs(1.0)), r["b"]) < TOL
+    f = rng.standard_normal(mngr.ndof)
+    bf = so.assemble_vector(r["JxW"] * f[r["l2g"]], r["l2g"], mngr.ndof)
+    assert rel_l2(host(op.rhs(dev(f))), bf) < TOL
+    d = torch.zeros(1, dtype=torch.float64, device="cuda")
+    y = op.apply(dev(u), dot_out=d)
+    assert abs(float(d) - float(torch.dot(dev(u), y))) < 1e-11 * abs(float(d))
+    x, info = op.solve(1.0, dev(r["ebc_vals"]), rtol=1e-13)
+    assert info.converged and rel_l2(host(x), r["solution"]) < 1e-10
