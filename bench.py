@@ -347,6 +347,8 @@ def run_engine(args):
         e2e_el = float(t)
     e2e_value = n_global_units / (e2e_el / args.e2e_steps) / 1e9
     e2e_ok = bool(torch.equal(y_host.to(dev), out)) if dp is None else True
+    if dp is not None and dp.halo is not None:
+        dp.halo.check()         # a neighbour that never delivered a column would have raised a flag
 
     # ---- PCG time-to-solution (reported beside the headline) -----------------------
     pcg = None
