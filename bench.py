@@ -407,7 +407,8 @@ def run_engine(args):
                     "d2h_bytes_per_step": 8 * n_local * world, "steps": args.e2e_steps,
                     "pipeline_stages": args.e2e_stages if dp is None else 1,
                     "matches_device_result": e2e_ok},
-            "gpu_launches": 2 * args.steps,
+            # own kernels per apply: patch kernel + interface kernel (+ the fused exchange kernel)
+            "gpu_launches": (3 if (dp is not None and dp.halo is not None) else 2) * args.steps,
             "clocks": clocks.summary(),
             "pcg": pcg,
         }
