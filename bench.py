@@ -198,8 +198,12 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "structured quad mesh Poisson p=8 FP64 (CPU sample %dx%d)"
-                               % (n_side, n_side)},
+        # the engine arm's workload; every step is a bounded sample of it (cpu_baseline.sample)
+        "config": {"workload": ("structured 1024x1024-element quad mesh Poisson, p=%d, FP64, "
+                                "rcm_order=False (BASELINE configs[1])" % ORDER) if args.gpus <= 1 else
+                               ("weak scaling: 884x884 elements p=8 per GPU, strip-partitioned over %d "
+                                "GPUs (BASELINE configs[4])" % args.gpus),
+                   "order": ORDER, "sample_elements_per_side": n_side},
         "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0,
