@@ -16,8 +16,10 @@ import numpy as np
 import pytest
 import torch
 
+import os
+
 import sem_oracle as so
-from conftest import build_package_case, golden_case_names, load_case, rel_l2
+from conftest import ROOT, build_package_case, golden_case_names, load_case, rel_l2
 from spectralelementmethod_b200 import _lib, device, meshgen
 from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
 from spectralelementmethod_b200 import discrete
@@ -502,3 +504,25 @@ def test_ragged_tiles_padded_with_empty_slots(nx, ny, p, pe):
     assert abs(float(d) - float(torch.dot(dev(u), y))) < 1e-11 * abs(float(d))
     x, info = op.solve(1.0, dev(r["ebc_vals"]), rtol=1e-13)
     assert info.converged and rel_l2(host(x), r["solution"]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_poisson_example_reproduces_the_reference_solution(tmp_path):
+    """examples/poisson.py (the reference's example flow on the engine), on the mesh of the
+    golden case S448_sc, directly built and through a Gmsh file: the reference's own
+    Schur-complement direct solve (tests/golden, frozen from the live reference)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "poisson_example", os.path.join(ROOT, "examples", "poisson.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    g = load_case("S448_sc")
+    mngr, on_ebc, vals, u, info = ex.run(n=4, order=8, kind="S", rtol=1e-13, quiet=True)
+    assert np.array_equal(mngr.node_map_array(), g["l2g"]) and np.array_equal(on_ebc, g["on_ebc"])
+    assert np.allclose(vals, g["ebc_vals"], rtol=0.0, atol=1e-14)   # device x_phys: last bits
+    assert info.converged and rel_l2(u, g["solution"]) < 1e-11
+    # the same problem read from a .msh file: same solution at the same coordinates
+    m2, on2, vals2, u2, info2 = ex.run(n=4, order=8, kind="S", rtol=1e-13, quiet=True,
+                                       write_msh=str(tmp_path / "plate.msh"))
+    key = lambda m: np.lexsort(np.round(m.mesh.nodes, 12))        # noqa: E731
+    assert rel_l2(u2[key(m2)], u[key(mngr)]) < 1e-11
