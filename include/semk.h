@@ -350,13 +350,18 @@ int semk_pcg_init_f64(int64_t n, int64_t n_dot, const double *b, const double *A
                       const double *dinv, const uint8_t *dirichlet, double *r, double *p,
                       double *sc, double *partials, void *stream);
 /* alpha = sc[0]/sc[1];  x += alpha p;  r -= alpha Ap;  sc[2] = r.(dinv r), sc[3] = r.r,
- * sc[5] += 1; sc[7] = 1 on breakdown (pAp <= 0 or NaN; x, r are then left unchanged) */
+ * sc[5] += 1; sc[7] = 1 on breakdown (pAp <= 0 or NaN; x, r are then left unchanged).
+ * x == NULL: x is left alone here and updated by semk_pcg_update_px_f64, which reads p
+ * anyway (one vector pass less per iteration). */
 int semk_pcg_update_xr_f64(int64_t n, int64_t n_dot, const double *p, const double *Ap,
                            const double *dinv, double *x, double *r, double *sc,
                            double *partials, void *stream);
 /* beta = sc[2]/sc[0];  p = dinv*r + beta p;  then sc[0] = sc[2] */
 int semk_pcg_update_p_f64(int64_t n, const double *r, const double *dinv, double *p, double *sc,
                           double *partials, void *stream);
+/* the same, plus x += alpha p_old with alpha = sc[0]/sc[1] (pairs with x == NULL above) */
+int semk_pcg_update_px_f64(int64_t n, const double *r, const double *dinv, double *p, double *x,
+                           double *sc, double *partials, void *stream);
 /* out[0] = sum_{k<n} a_k b_k (deterministic two-stage reduction) */
 int semk_dot_f64(int64_t n, const double *a, const double *b, double *out, double *partials,
                  void *stream);

@@ -105,6 +105,7 @@ SIGNATURES = {
     "semk_pcg_init_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "semk_pcg_update_xr_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "semk_pcg_update_p_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
+    "semk_pcg_update_px_f64": (_I, [_L, _P, _P, _P, _P, _P, _P, _P]),
     "semk_dot_f64": (_I, [_L, _P, _P, _P, _P, _P]),
     "semk_pcg_solve_f64": (_I, [C.POINTER(semk_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
                                 C.POINTER(semk_pcg_info), _P]),

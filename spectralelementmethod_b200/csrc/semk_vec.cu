@@ -332,10 +332,11 @@ extern "C" int semk_pcg_update_xr_f64(int64_t n, int64_t n_dot, const double *p,
                                       const double *dinv, double *x, double *r, double *sc,
                                       double *partials, void *stream) {
   SEMK_REQUIRE(n > 0 && n_dot >= 0 && n_dot <= n, "semk_pcg_update_xr_f64: bad sizes");
-  SEMK_REQUIRE(p && Ap && dinv && x && r && sc && partials,
-               "semk_pcg_update_xr_f64: null pointer");
-  // tol2 < 0: the device-side convergence freeze is disabled (caller decides)
-  return update_xr(n, n_dot, p, Ap, dinv, x, r, sc, partials, -1.0, false, semk_stream(stream));
+  SEMK_REQUIRE(p && Ap && dinv && r && sc && partials, "semk_pcg_update_xr_f64: null pointer");
+  // tol2 < 0: the device-side convergence freeze is disabled (caller decides).
+  // x == NULL: the caller updates x together with p (semk_pcg_update_px_f64).
+  return update_xr(n, n_dot, p, Ap, dinv, x ? x : r, r, sc, partials, -1.0, x == nullptr,
+                   semk_stream(stream));
 }
 
 extern "C" int semk_pcg_update_p_f64(int64_t n, const double *r, const double *dinv, double *p,
@@ -343,6 +344,13 @@ extern "C" int semk_pcg_update_p_f64(int64_t n, const double *r, const double *d
   SEMK_REQUIRE(n > 0, "semk_pcg_update_p_f64: bad size");
   SEMK_REQUIRE(r && dinv && p && sc && partials, "semk_pcg_update_p_f64: null pointer");
   return update_p(n, r, dinv, p, nullptr, sc, partials, semk_stream(stream));
+}
+
+extern "C" int semk_pcg_update_px_f64(int64_t n, const double *r, const double *dinv, double *p,
+                                      double *x, double *sc, double *partials, void *stream) {
+  SEMK_REQUIRE(n > 0, "semk_pcg_update_px_f64: bad size");
+  SEMK_REQUIRE(r && dinv && p && x && sc && partials, "semk_pcg_update_px_f64: null pointer");
+  return update_p(n, r, dinv, p, x, sc, partials, semk_stream(stream));
 }
 
 extern "C" int semk_dot_f64(int64_t n, const double *a, const double *b, double *out,

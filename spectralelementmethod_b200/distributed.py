@@ -301,12 +301,19 @@ def distributed_pcg(dop, b, x, dinv, kernels, rtol=1e-12, maxiter=200000, check_
         return 0, (float(h[3]) / bb) ** 0.5 if bb > 0 else 0.0, True
     it = 0
     while it < maxiter:
+        fused = hasattr(kernels, "update_px")   # x += alpha p rides with the p update
         for _ in range(min(check_every, maxiter - it)):
             dop.apply(p, out=Ap, dot_out=sc[1:2])
             dist.all_reduce(sc[1:2], group=dop.group)
-            kernels.update_xr(p, Ap, dinv, x, r, sc, n_dot)
+            if fused:
+                kernels.update_r(p, Ap, dinv, r, sc, n_dot)
+            else:
+                kernels.update_xr(p, Ap, dinv, x, r, sc, n_dot)
             dist.all_reduce(sc[2:4], group=dop.group)
-            kernels.update_p(r, dinv, p, sc)
+            if fused:
+                kernels.update_px(r, dinv, p, x, sc)
+            else:
+                kernels.update_p(r, dinv, p, sc)
             it += 1
         h = sc.cpu()
         if getattr(dop, "halo", None) is not None:

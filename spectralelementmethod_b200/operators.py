@@ -539,6 +539,18 @@ class PCGKernels(object):
             self.n, int(n_dot), device.ptr(p), device.ptr(Ap), device.ptr(dinv), device.ptr(x),
             device.ptr(r), device.ptr(sc), device.ptr(self.op.vec_partials), device.stream_ptr()))
 
+    def update_r(self, p, Ap, dinv, r, sc, n_dot):
+        """update_xr without the x update (paired with update_px)."""
+        _lib.check(self._lib.semk_pcg_update_xr_f64(
+            self.n, int(n_dot), device.ptr(p), device.ptr(Ap), device.ptr(dinv), None,
+            device.ptr(r), device.ptr(sc), device.ptr(self.op.vec_partials), device.stream_ptr()))
+
+    def update_px(self, r, dinv, p, x, sc):
+        """p = dinv r + beta p and x += alpha p_old in one pass."""
+        _lib.check(self._lib.semk_pcg_update_px_f64(
+            self.n, device.ptr(r), device.ptr(dinv), device.ptr(p), device.ptr(x), device.ptr(sc),
+            device.ptr(self.op.vec_partials), device.stream_ptr()))
+
     def update_p(self, r, dinv, p, sc):
         _lib.check(self._lib.semk_pcg_update_p_f64(
             self.n, device.ptr(r), device.ptr(dinv), device.ptr(p), device.ptr(sc),

@@ -410,6 +410,17 @@ def test_native_pcg_matches_kernel_by_kernel_pcg(rtol, check_every):
         assert its < 5000
     assert its == info.iterations
     assert float((x - x_native).norm() / x.norm()) < 1e-13
+    # the public fused pair (x updated together with p, as the distributed loop does):
+    # the same arithmetic in a different kernel -> bit-identical iterate
+    x2 = torch.zeros_like(b)
+    x2[m] = b[m]
+    op.apply(x2, out=Ap)
+    k.init(b, Ap, dinv, r, p, sc, n)
+    for _ in range(its):
+        op.apply(p, out=Ap, dot_out=sc[1:2])
+        k.update_r(p, Ap, dinv, r, sc, n)
+        k.update_px(r, dinv, p, x2, sc)
+    assert torch.equal(x2, x)
 
 
 @pytest.mark.gpu
