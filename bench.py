@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--pcg-iters", type=int, default=300,
                     help="PCG iterations timed for the time-to-solution estimate (0 = skip)")
     ap.add_argument("--pcg-full", action="store_true", help="run PCG to rtol 1e-12")
+    ap.add_argument("--no-condensed", action="store_true",
+                    help="skip the statically condensed operator (reported beside the headline)")
     ap.add_argument("--cpu-sample", type=int, default=64,
                     help="elements per side of the CPU-baseline sample mesh (0 = skip)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
@@ -216,6 +218,77 @@ def run_reference(args):
 # --------------------------------------------------------------------------
 # engine arm
 # --------------------------------------------------------------------------
+def run_condensed(args, nx, dev, peak):
+    """The reference's own solver formulation on the device (DOFManagerSC: local Schur
+    complements, condensed system over the element-exterior DOFs, interior
+    back-substitution; sem/discrete.py:404-528) on the same mesh: condensed apply and
+    Jacobi-PCG per iteration, reported beside the matrix-free headline."""
+    import torch
+    from spectralelementmethod_b200 import discrete, meshgen
+    from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+    t0 = time.perf_counter()
+    mesh = meshgen.structured_quad_mesh(nx, nx, ORDER, args.kind)
+    b1 = LagrangeGaussLobatto(ORDER)
+    mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+    on = mngr.boundary_node_mask("ebc")
+    t_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sc = mngr.condensed_poisson_operator(dirichlet=on)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    sdiag = torch.empty((sc.n_elem, sc.n_ext_loc), dtype=torch.float64, device=dev)
+    sc._element_pass(1, S=sc.S, sdiag_loc=sdiag)          # the Schur pass alone, timed
+    ev1.record()
+    torch.cuda.synchronize()
+    t_schur = ev0.elapsed_time(ev1) / 1e3
+    del sdiag
+    u = torch.randn(sc.n_ext, dtype=torch.float64, device=dev,
+                    generator=torch.Generator(device=dev).manual_seed(0))
+    out = torch.empty_like(u)
+    for _ in range(5):
+        sc.apply(u, out=out)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        sc.apply(u, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_apply = ev0.elapsed_time(ev1) / 1e3 / args.steps
+    alg = sc.algorithmic_bytes_per_apply
+    res = {"formulation": "static condensation (DOFManagerSC), packed local Schur complements",
+           "dof_exterior": sc.n_ext, "dof_total": sc.n_nodes, "elements": sc.n_elem,
+           "host_numbering_seconds": t_host, "setup_seconds": t_setup,
+           "schur_pass_seconds": t_schur,
+           "ms_per_apply": t_apply * 1e3, "algorithmic_bytes_per_apply": alg,
+           "achieved_GBps": alg / t_apply / 1e9, "frac_of_hbm_peak": alg / t_apply / 1e9 / peak,
+           "gdof_total_per_s": sc.n_nodes / t_apply / 1e9}
+    if args.pcg_iters > 0 or args.pcg_full:
+        b = sc.lift(sc.rhs(1.0), None)
+
+        def run(iters):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            xs, info = sc.solve_pcg(b, rtol=1e-12, maxiter=iters, check_every=50)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, info, xs
+        run(50)
+        el0, i0, _ = run(100)
+        el, info, xs = run(200000 if args.pcg_full else 100 + args.pcg_iters)
+        ms_it = (el - el0) / max(info.iterations - i0.iterations, 1) * 1e3
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sc.backsolve(xs, 1.0)
+        torch.cuda.synchronize()
+        res["pcg"] = {"iterations": info.iterations, "seconds": el, "converged": info.converged,
+                      "rel_residual": info.rel_residual, "ms_per_iteration": ms_it,
+                      "backsolve_seconds": time.perf_counter() - t0,
+                      "note": "homogeneous Dirichlet on ebc, f=1, rtol 1e-12"
+                              + ("" if args.pcg_full else "; capped")}
+    return res
+
+
 def run_engine(args):
     import numpy as np
     import torch
@@ -388,6 +461,13 @@ def run_engine(args):
         pcg["note"] = ("homogeneous Dirichlet on ebc, f=1, rtol 1e-12"
                        + ("" if args.pcg_full else "; capped at %d iterations" % pcg["iterations"]))
 
+    condensed = None
+    if not multi and not args.no_condensed and 2 <= ORDER <= 10:
+        try:
+            condensed = run_condensed(args, nx, dev, peak)
+        except Exception as exc:       # reported, never fatal for the headline line
+            condensed = {"error": repr(exc)}
+
     cpu = None
     if rank == 0 and not multi and args.cpu_sample > 0:
         cpu = cpu_baseline(args.cpu_sample, args.kind)
@@ -415,6 +495,7 @@ def run_engine(args):
             "gpu_launches": (3 if (dp is not None and dp.halo is not None) else 2) * args.steps,
             "clocks": clocks.summary(),
             "pcg": pcg,
+            "condensed": condensed,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -383,6 +383,93 @@ int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x, const doub
                        int maxiter, int check_every, semk_pcg_info *info, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Static condensation on the device: the reference's
+ * actual solver formulation, DOFManagerSC (sem/discrete.py:283-528).  Element
+ * interiors are eliminated element by element,
+ *     S_e = A_ee - A_ei A_ii^{-1} A_ie,   g_e = f_e - A_ei A_ii^{-1} f_i
+ * (compute_local_sc_system, sem/discrete.py:438-476), the condensed system over
+ * the element-exterior DOFs is solved (here: Jacobi-PCG instead of
+ * spsolve, :502-511) and the interiors follow by back-substitution
+ * (_solve_interior_dofs, :513-524).
+ *
+ * Requires the exterior-first numbering of DOFManagerSC (:314-359): global
+ * ids [0, n_ext) are the element-exterior nodes.  The local exterior order is
+ * the reference's hierarchical one (4 vertices, then the open edges xi0=-1,
+ * xi0=+1, xi1=-1, xi1=+1; sem/geometry.py:151-212), n_ext_loc = 4p entries;
+ * the local interior order is lexicographic, (p-1)^2 entries.  Orders 2..10
+ * (n1 = 3..11: the reference's own table range).
+ *
+ * The local stiffness is never stored: it is rebuilt from the geometric
+ * factors G (engine layout, see semk_op.G) inside the element kernel, the
+ * interior block is Cholesky-factorised in shared memory (A_ii = L L^T),
+ * Z = L^{-1} A_ie, and S_e = A_ee - Z^T Z is kept PACKED (lower triangle, row
+ * major, s_stride = n_ext_loc (n_ext_loc + 1) / 2 doubles per element).
+ * ------------------------------------------------------------------------ */
+typedef struct semk_sc_op {
+  int32_t n1;
+  int32_t n_ext_loc;          /* 4 (n1 - 1) */
+  int64_t n_elem;             /* elements, reference element order */
+  int64_t n_ext;              /* element-exterior global nodes = the leading ids */
+  int64_t s_stride;           /* doubles per element block of S */
+  const double *S;            /* [n_elem][s_stride] packed local Schur complements */
+  const uint32_t *l2g_ext;    /* [n_elem][n_ext_loc] global ids of the exterior nodes of each
+                                 element, hierarchical local order (fe.global_dof_ind_hier
+                                 [:ndof_exterior], sem/discrete.py:491-492) */
+  double *y_loc;              /* [n_elem][n_ext_loc] scratch: element-local results */
+  const uint32_t *node_ptr;   /* [n_ext + 1] CSR offsets into node_pos */
+  const uint32_t *node_pos;   /* [n_elem * n_ext_loc] for every exterior node the positions
+                                 (elem * n_ext_loc + k) of its element-local entries,
+                                 ascending: the fixed summation order of the assembly */
+  const uint8_t *dirichlet;   /* [n_ext] 1 = essential-BC node (on_ebc of
+                                 DOFManagerSC.solve, sem/discrete.py:502-505), or NULL */
+  double *partials;           /* [semk_vec_partials_len()] dot-product scratch, zeroed once */
+} semk_sc_op;
+
+/* what the element kernel produces (bit-or) */
+#define SEMK_SC_SCHUR 1       /* S (packed) and, if sdiag_loc != NULL, its diagonal          */
+#define SEMK_SC_RHS 2         /* g_loc = f_e - A_ei A_ii^{-1} f_i                            */
+#define SEMK_SC_BACKSOLVE 4   /* u_i = A_ii^{-1} (f_i - A_ie u_e) written into u             */
+
+/* One pass of the element kernel (one CTA per element).
+ * slot_of_elem: device int64 [n_elem], engine slot holding element e's factors in G
+ *   (inverse of SEMK_PA_ELEM_OF_SLOT), or NULL = identity; G / g_patch_stride /
+ *   elems_per_patch as in semk_op (elems_per_patch = 1: plain [n_elem][3][NN] blocks).
+ * D: device [NN].  ext_loc: device int32 [n_ext_loc] lexicographic local index of the
+ *   k-th exterior node.  l2g: device uint32 [n_elem][NN].
+ * Load f (modes RHS, BACKSOLVE): f_loc[k] = f_scale * JxW[e][k] * (f_nodal ?
+ *   f_nodal[l2g[e][k]] : 1)  -- the reference's rhs = JxW (examples/poisson.py:200).
+ * SCHUR: S_out [n_elem][s_stride]; sdiag_loc [n_elem][n_ext_loc] or NULL.
+ * RHS: g_loc [n_elem][n_ext_loc].  BACKSOLVE: u device [n_nodes], exterior entries
+ *   read, interior entries written.
+ * bad_flag: device int32, set to 1 when an interior block is not positive definite. */
+int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem, const double *G,
+                        int64_t g_patch_stride, int elems_per_patch, const double *D,
+                        const int32_t *ext_loc, const uint32_t *l2g, const double *JxW,
+                        const double *f_nodal, double f_scale, int mode, double *S_out,
+                        int64_t s_stride, double *sdiag_loc, double *g_loc, double *u,
+                        int32_t *bad_flag, void *stream);
+
+/* y = S u over the exterior DOFs: per element y_loc = S_e u[l2g_ext] (dense symmetric
+ * 4p x 4p product from the packed block), then every exterior node sums its entries of
+ * y_loc in the fixed order of node_pos.  flags as semk_poisson_apply_f64 (Dirichlet
+ * elimination of sem/discrete.py:505-510); dot_out: device double or NULL, receives
+ * u . y.  Deterministic: no floating-point atomics.  u, y: device [n_ext], distinct. */
+int semk_sc_apply_f64(const semk_sc_op *op, const double *u, double *y, int flags,
+                      double *dot_out, void *stream);
+
+/* out[g] = sum of loc[node_pos[..]] for every exterior node (`grhs[inds_ext] += ...`,
+ * sem/discrete.py:499); loc: device [n_elem][n_ext_loc].  SEMK_MASK_OUT writes
+ * fill_dirichlet on Dirichlet rows. */
+int semk_sc_assemble_f64(const semk_sc_op *op, const double *loc, double *out, int flags,
+                         double fill_dirichlet, void *stream);
+
+/* Jacobi-PCG on Shat = M S M + (I - M); arguments as semk_pcg_solve_f64 with vectors
+ * of length n_ext. */
+int semk_sc_pcg_solve_f64(const semk_sc_op *op, const double *b, double *x, const double *dinv,
+                          double *work, double *sc, double *vec_partials, double rtol,
+                          int maxiter, int check_every, semk_pcg_info *info, void *stream);
+
+/* ------------------------------------------------------------------------
  * Multi-GPU: interface exchange of a strip partition over NVLink peer memory
  * (the reference itself is single-process -- its serial
  * analogue is the scatter-add `grhs[inds] += ...`, sem/discrete.py:499).

@@ -389,6 +389,32 @@ def solve_schur(L, JxW, l2g, n_ext, on_ebc, vals):
     return sol
 
 
+def condensed_system(p, invJ, JxW, l2g):
+    """Local Schur complements, condensed local loads and the assembled condensed
+    system over the element-exterior DOFs: compute_local_sc_system /
+    assemble_global_sc_system (sem/discrete.py:438-500) with the Poisson recipe
+    of examples/poisson.py:166-200.  Requires the exterior-first numbering."""
+    N, nn, ne = p + 1, (p + 1) ** 2, 4 * p
+    L = local_stiffness(Basis(p), invJ, JxW)
+    E = L.shape[0]
+    h = hier_order(N).astype(np.int64)
+    Lm = L.reshape(E, nn, nn)[:, h][:, :, h]               # reorder_local_system_hier
+    rh = JxW.reshape(E, nn)[:, h]
+    ids = l2g.reshape(E, nn).astype(np.int64)[:, h][:, :ne]
+    Aee, Aei, Aie, Aii = Lm[:, :ne, :ne], Lm[:, :ne, ne:], Lm[:, ne:, :ne], Lm[:, ne:, ne:]
+    X = np.swapaxes(np.linalg.solve(np.swapaxes(Aii, 1, 2), np.swapaxes(Aei, 1, 2)), 1, 2)
+    S = Aee - X @ Aie
+    gl = rh[:, :ne] - np.einsum("eij,ej->ei", X, rh[:, ne:])
+    n_ext = int(ids.max()) + 1
+    rows = np.repeat(ids, ne, axis=1).ravel()
+    cols = np.tile(ids, (1, ne)).ravel()
+    Sg = sparse.coo_matrix((S.reshape(-1), (rows, cols)), shape=(n_ext, n_ext)).tocsr()
+    grhs = np.zeros(n_ext)
+    np.add.at(grhs, ids.ravel(), gl.ravel())
+    return dict(S=S, g_loc=gl, ids=ids, Sg=Sg, grhs=grhs, n_ext=n_ext, Aii=Aii, Aie=Aie,
+                f_int=rh[:, ne:], int_ids=l2g.reshape(E, nn).astype(np.int64)[:, h][:, ne:])
+
+
 def pcg_jacobi(A, b, x0, rtol, maxiter):
     """Plain Jacobi-PCG on an assembled SPD matrix (protocol of SURVEY.md
     8(d): stop on the recursive residual ||r|| <= rtol ||b||).  Checker for

@@ -67,6 +67,19 @@ class semk_op(C.Structure):
     ]
 
 
+class semk_sc_op(C.Structure):
+    _fields_ = [
+        ("n1", C.c_int32), ("n_ext_loc", C.c_int32),
+        ("n_elem", C.c_int64), ("n_ext", C.c_int64), ("s_stride", C.c_int64),
+        ("S", C.c_void_p), ("l2g_ext", C.c_void_p), ("y_loc", C.c_void_p),
+        ("node_ptr", C.c_void_p), ("node_pos", C.c_void_p), ("dirichlet", C.c_void_p),
+        ("partials", C.c_void_p),
+    ]
+
+
+SC_SCHUR, SC_RHS, SC_BACKSOLVE = 1, 2, 4
+
+
 class semk_stage(C.Structure):
     _fields_ = [("patch_end", C.c_int64), ("chunk_end", C.c_int64), ("rec_end", C.c_int64),
                 ("u_need", C.c_int64), ("y_final", C.c_int64)]
@@ -113,6 +126,12 @@ SIGNATURES = {
                                                 _P, _P, _I, _P]),
     "semk_scratch_row_stride": (_I, [_I, _I]),
     "semk_scale_gfactors_f64": (_I, [_I, _L, _P, _P, _P, _L, _I, _P]),
+    "semk_sc_element_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L, _P,
+                                 _P, _P, _P, _P]),
+    "semk_sc_apply_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _P, _P]),
+    "semk_sc_assemble_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _D, _P]),
+    "semk_sc_pcg_solve_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
+                                   C.POINTER(semk_pcg_info), _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
     "semk_peer_open": (_I, [_P, C.POINTER(_P)]),

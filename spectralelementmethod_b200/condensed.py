@@ -1,0 +1,343 @@
+"""Static condensation on the device.
+
+The reference's solver formulation is ``DOFManagerSC`` (sem/discrete.py:283-528):
+per element the interior DOFs are eliminated, ``S_e = A_ee - A_ei A_ii^-1 A_ie``
+(compute_local_sc_system, :438-476), the condensed system over the element-
+exterior DOFs is assembled as COO triplets (:478-500) and solved with SuperLU
+(:502-511), and the interiors follow by per-element back-substitution (:513-524).
+
+``CondensedPoissonOperator`` is that path on one GPU, matrix-based per element
+and assembly-free globally:
+
+    sc = dof_mngr.condensed_poisson_operator(dirichlet=on_ebc)   # DOFManagerSC
+    y  = sc.apply(u_ext)                  # y = Shat u, Shat = M S M + (I - M)
+    g  = sc.rhs(f=1.0)                    # condensed load  Q_e^T (f_e - A_ei A_ii^-1 f_i)
+    u, info = sc.solve(1.0, ebc_values)   # PCG on the exterior DOFs + interior back-solve
+
+Condensed vectors are ``torch.float64`` CUDA tensors of length ``n_ext`` =
+``dof_mngr.ndof_exterior`` (the leading ids of the exterior-first numbering);
+``solve`` returns the full nodal vector.  The local Schur complements are
+built by the element kernel of csrc/semk_sc.cu from the same geometric factors
+the matrix-free operator uses and stored packed (2p(4p+1) doubles per
+element); nothing here falls back to NumPy.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, device
+from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
+from .operators import PCGInfo
+
+__all__ = ["CondensedPoissonOperator"]
+
+
+def condensed_tables(l2g, ext_loc, n_ext):
+    """Host tables of the condensed operator (pure NumPy, T0 tier):
+    ``l2g_ext[E, 4p]`` = global ids of each element's exterior nodes in the
+    hierarchical local order (fe.global_dof_ind_hier[:ndof_exterior],
+    sem/discrete.py:491-492) and the node -> entries table of the assembly:
+    ``node_pos[node_ptr[g]:node_ptr[g+1]]`` are the positions ``e * 4p + k`` of
+    the entries of node g, ascending (a stable sort) -- the fixed summation
+    order that replaces ``grhs[inds_ext] += ...`` (sem/discrete.py:499)."""
+    l2g_ext = np.ascontiguousarray(l2g[:, ext_loc], dtype=np.uint32)
+    if int(l2g_ext.max()) >= n_ext:
+        raise AssertionError("exterior nodes are not numbered first")
+    if l2g_ext.size >= 2 ** 32:
+        raise NotImplementedError("more than 2^32 element-exterior entries")
+    flat = l2g_ext.ravel()
+    node_pos = np.argsort(flat, kind="stable").astype(np.uint32)
+    counts = np.bincount(flat, minlength=n_ext)
+    if (counts == 0).any():
+        raise AssertionError("an exterior id is not used by any element")
+    node_ptr = np.zeros(n_ext + 1, dtype=np.uint32)
+    np.cumsum(counts, out=node_ptr[1:])
+    return l2g_ext, node_ptr, node_pos
+
+
+class CondensedPoissonOperator(object):
+    def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, weight=None):
+        _lib.require_device()
+        self._lib = _lib.load()
+        mesh = dof_mngr.mesh
+        if not getattr(mesh, "condensed", False):
+            raise ValueError("static condensation needs the exterior-first numbering of "
+                             "DOFManagerSC (sem/discrete.py:314-359)")
+        if dof_mngr.ndof_per_node != 1:
+            raise NotImplementedError("condensed_poisson_operator supports one DOF per node")
+        self.dof_mngr = dof_mngr
+        self.n_nodes = int(mesh.n_nodes)
+        self.n_ext = int(mesh.n_nodes_cell_exterior)
+        full_mask = None
+        if dirichlet is not None:
+            dirichlet = np.asarray(dirichlet)
+            if dirichlet.dtype != np.bool_ or dirichlet.shape not in ((self.n_nodes,),
+                                                                      (self.n_ext,)):
+                raise ValueError("dirichlet must be bool[n_nodes] or bool[ndof_exterior] "
+                                 "(True = essential-BC node)")
+            full_mask = np.zeros(self.n_nodes, dtype=bool)
+            full_mask[:dirichlet.size] = dirichlet
+            if full_mask[self.n_ext:].any():
+                raise ValueError("essential-BC nodes must be element-exterior nodes")
+        self.tab = device.basis_tables(dof_mngr._basis)
+        n1 = self.n1 = self.tab.n1
+        if n1 < 3 or n1 > 11:
+            raise NotImplementedError("static condensation supports orders 2..10")
+        NN = n1 * n1
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+
+        geo = mesh.get_geometries()[0]
+        ext_loc = np.ascontiguousarray(geo.exterior_node_ind, dtype=np.int32)
+        m = np.arange(1, n1 - 1)
+        lex_interior = (m[:, None] * n1 + m[None, :]).ravel()
+        if not np.array_equal(np.asarray(geo.interior_node_ind, dtype=np.int64), lex_interior):
+            raise AssertionError("interior local order is not lexicographic")
+        self.n_ext_loc = int(ext_loc.size)
+        self.n_int_loc = NN - self.n_ext_loc
+        self.s_stride = self.n_ext_loc * (self.n_ext_loc + 1) // 2
+        self.ext_loc_host = ext_loc
+
+        l2g = mesh.node_map_array().reshape(-1, NN)
+        self.n_elem = int(l2g.shape[0])
+        l2g_ext, node_ptr, node_pos = condensed_tables(l2g, ext_loc, self.n_ext)
+        self.l2g_ext_host = l2g_ext
+
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self._t = dict(
+            ext_loc=torch.from_numpy(ext_loc).to(self.dev),
+            l2g_ext=device.as_i32_bits(l2g_ext, self.dev),
+            node_ptr=device.as_i32_bits(node_ptr, self.dev),
+            node_pos=device.as_i32_bits(node_pos, self.dev),
+        )
+        self.l2g_dev = device.as_i32_bits(l2g, self.dev)
+
+        # geometric factors, one plain [3][NN] block per element in reference element order
+        # (the engine layout of semk_op.G with one-element patches)
+        self.g_stride = (3 * NN + 1) & ~1
+        self.G = torch.zeros((self.n_elem, self.g_stride), **f64)
+        self.JxW = torch.empty((self.n_elem, NN), **f64)
+        x_phys = None
+        if geometric_factors is None:
+            nodes_dev = torch.from_numpy(np.ascontiguousarray(mesh.nodes, dtype=np.float64)).to(self.dev)
+            if nodes_dev.shape[0] != 2:
+                raise NotImplementedError("Only supporting 2D elements right now")
+            if callable(weight):
+                x_phys = torch.empty((self.n_elem, 2, NN), **f64)
+            device.geom_factors(self.tab, nodes_dev, self.l2g_dev, self.n_elem, G=self.G,
+                                g_patch_stride=self.g_stride, elems_per_patch=1, JxW=self.JxW,
+                                x_phys=x_phys)
+            del nodes_dev
+        else:
+            invJ, jxw = geometric_factors
+            invJ = device._f64(np.asarray(invJ).reshape(self.n_elem, 4, NN), self.dev)
+            self.JxW.copy_(device._f64(np.asarray(jxw).reshape(self.n_elem, NN), self.dev))
+            _lib.check(self._lib.semk_gfactors_from_invj_f64(
+                n1, self.n_elem, device.ptr(invJ), device.ptr(self.JxW), None,
+                device.ptr(self.G), self.g_stride, 1, device.stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+            del invJ
+        if weight is not None:      # stiffness of -div(w grad u), as PoissonOperator(weight=...)
+            if callable(weight):
+                if x_phys is None:
+                    raise ValueError("a callable weight needs the device geometry")
+                w = weight(x_phys[:, 0, :], x_phys[:, 1, :])
+                w = torch.as_tensor(w, dtype=torch.float64, device=self.dev).expand(self.n_elem, NN)
+            else:
+                w = device._f64(np.asarray(weight, dtype=np.float64).reshape(self.n_elem, NN),
+                                self.dev)
+            w = w.contiguous()
+            _lib.check(self._lib.semk_scale_gfactors_f64(
+                n1, self.n_elem, device.ptr(w), None, device.ptr(self.G), self.g_stride, 1,
+                device.stream_ptr()))
+            torch.cuda.current_stream().synchronize()
+            del w
+        del x_phys
+
+        self.has_dirichlet = full_mask is not None and bool(full_mask.any())
+        self.dirichlet_host = None if full_mask is None else full_mask[:self.n_ext].copy()
+        self.dirichlet_dev = (torch.from_numpy(self.dirichlet_host.astype(np.uint8)).to(self.dev)
+                              if full_mask is not None else None)
+        self.S = torch.empty((self.n_elem, self.s_stride), **f64)
+        self.y_loc = torch.empty((self.n_elem, self.n_ext_loc), **f64)
+        self.partials = torch.zeros(int(self._lib.semk_vec_partials_len(self.n_ext)), **f64)
+        self.vec_partials = torch.zeros(int(self._lib.semk_vec_partials_len(self.n_ext)), **f64)
+        self._bad = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+        op = _lib.semk_sc_op()
+        op.n1, op.n_ext_loc = n1, self.n_ext_loc
+        op.n_elem, op.n_ext, op.s_stride = self.n_elem, self.n_ext, self.s_stride
+        op.S = self.S.data_ptr()
+        op.l2g_ext = self._t["l2g_ext"].data_ptr()
+        op.y_loc = self.y_loc.data_ptr()
+        op.node_ptr = self._t["node_ptr"].data_ptr()
+        op.node_pos = self._t["node_pos"].data_ptr()
+        op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None
+        op.partials = self.partials.data_ptr()
+        self._op = op
+        self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
+
+        sdiag = torch.empty((self.n_elem, self.n_ext_loc), **f64)
+        self._element_pass(_lib.SC_SCHUR, S=self.S, sdiag_loc=sdiag)
+        self._diag_unmasked = self.assemble(sdiag)
+        del sdiag
+        self._dinv = None
+
+    # -- element kernel ----------------------------------------------------------------
+    def _full_vec(self, v, name):
+        if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float64
+                and v.is_contiguous() and v.numel() == self.n_nodes):
+            raise ValueError("%s must be a contiguous float64 CUDA tensor of length n_nodes" % name)
+        return v
+
+    def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=1.0):
+        """One launch of sc_element_kernel (csrc/semk_sc.cu)."""
+        f_nodal, f_scale = None, 1.0
+        if isinstance(f, torch.Tensor):
+            f_nodal = self._full_vec(f, "f")
+        elif np.ndim(f) == 0:
+            f_scale = float(f)
+        else:
+            f_nodal = self._full_vec(self.from_host(f), "f")
+        self._bad.zero_()
+        _lib.check(self._lib.semk_sc_element_f64(
+            self.n1, self.n_elem, None, device.ptr(self.G), self.g_stride, 1,
+            device.ptr(self.tab.dev()[0]), device.ptr(self._t["ext_loc"]),
+            device.ptr(self.l2g_dev), device.ptr(self.JxW), device.ptr(f_nodal), f_scale,
+            int(mode), device.ptr(S), self.s_stride, device.ptr(sdiag_loc), device.ptr(g_loc),
+            device.ptr(u), device.ptr(self._bad), device.stream_ptr()))
+        if int(self._bad.item()) != 0:
+            raise AssertionError("an element-interior stiffness block is not positive definite")
+
+    # -- helpers -----------------------------------------------------------------------
+    def _vec(self, v, name="vector"):
+        if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float64
+                and v.is_contiguous() and v.numel() == self.n_ext):
+            raise ValueError("%s must be a contiguous float64 CUDA tensor of length "
+                             "ndof_exterior" % name)
+        return v
+
+    def new_vector(self, fill=None):
+        if fill is None:
+            return torch.empty(self.n_ext, dtype=torch.float64, device=self.dev)
+        return torch.full((self.n_ext,), float(fill), dtype=torch.float64, device=self.dev)
+
+    def from_host(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+
+    @property
+    def algorithmic_bytes_per_apply(self):
+        """Packed S_e + one uint32 L2G entry per element-exterior node, read u,
+        write y."""
+        return (8 * self.s_stride + 4 * self.n_ext_loc) * self.n_elem + 16 * self.n_ext
+
+    def local_schur(self):
+        """The local Schur complements as dense host arrays ``[E, 4p, 4p]``
+        (tests; compare with compute_local_sc_system, sem/discrete.py:438-476)."""
+        ne = self.n_ext_loc
+        packed = self.S.cpu().numpy()
+        out = np.zeros((self.n_elem, ne, ne))
+        r, c = np.tril_indices(ne)
+        out[:, r, c] = packed
+        out[:, c, r] = packed
+        return out
+
+    # -- operator ----------------------------------------------------------------------
+    def apply(self, u, out=None, flags=None, dot_out=None):
+        """y = Shat u over the exterior DOFs (S u with ``flags=0``)."""
+        self._vec(u, "u")
+        y = self.new_vector() if out is None else self._vec(out, "out")
+        if flags is None:
+            flags = self._masked_flags
+        _lib.check(self._lib.semk_sc_apply_f64(
+            C.byref(self._op), device.ptr(u), device.ptr(y), int(flags), device.ptr(dot_out),
+            device.stream_ptr()))
+        return y
+
+    def apply_unmasked(self, u, out=None):
+        return self.apply(u, out=out, flags=0)
+
+    def assemble(self, loc, out=None, mask=False, fill_dirichlet=0.0):
+        """Sum an element-local exterior field ``loc[E, 4p]`` into a condensed
+        vector (``grhs[inds_ext] += ...``, sem/discrete.py:499)."""
+        y = self.new_vector() if out is None else self._vec(out, "out")
+        _lib.check(self._lib.semk_sc_assemble_f64(
+            C.byref(self._op), device.ptr(loc), device.ptr(y), MASK_OUT if mask else 0,
+            float(fill_dirichlet), device.stream_ptr()))
+        return y
+
+    def diagonal(self, masked=True):
+        d = self._diag_unmasked.clone()
+        if masked and self.has_dirichlet:
+            d[self.dirichlet_dev.bool()] = 1.0
+        return d
+
+    def rhs(self, f=1.0):
+        """Condensed load vector: assembled ``f_e - A_ei A_ii^-1 f_i`` with the
+        element load ``JxW . f`` (examples/poisson.py:200; scalar or nodal f)."""
+        g_loc = torch.empty((self.n_elem, self.n_ext_loc), dtype=torch.float64, device=self.dev)
+        self._element_pass(_lib.SC_RHS, g_loc=g_loc, f=f)
+        return self.assemble(g_loc)
+
+    def lift(self, b, dirichlet_values=None):
+        """RHS of the SPD system: free rows b_f - S_fe g_e, Dirichlet rows g_e
+        (sem/discrete.py:505-509)."""
+        self._vec(b, "b")
+        if not self.has_dirichlet:
+            return b.clone()
+        mask = self.dirichlet_dev.bool()
+        g = torch.zeros_like(b)
+        if dirichlet_values is not None:
+            gv = dirichlet_values if isinstance(dirichlet_values, torch.Tensor) \
+                else self.from_host(dirichlet_values)
+            gv = gv[:self.n_ext]
+            g[mask] = gv[mask]
+        t = self.apply(g, flags=MASK_OUT)
+        out = b - t
+        out[mask] = g[mask]
+        return out
+
+    def jacobi_inverse(self):
+        if self._dinv is None:
+            self._dinv = 1.0 / self.diagonal(masked=True)
+        return self._dinv
+
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
+        """Jacobi-PCG on Shat x = b (b already lifted); returns (x, PCGInfo)."""
+        self._vec(b, "b")
+        if x0 is None:
+            x = torch.zeros_like(b)
+            if self.has_dirichlet:
+                m = self.dirichlet_dev.bool()
+                x[m] = b[m]
+        else:
+            x = self._vec(x0, "x0").clone()
+        dinv = self.jacobi_inverse()
+        work = torch.empty(3 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
+        sc = torch.zeros(8, dtype=torch.float64, device=self.dev)
+        info = _lib.semk_pcg_info()
+        rc = self._lib.semk_sc_pcg_solve_f64(
+            C.byref(self._op), device.ptr(b), device.ptr(x), device.ptr(dinv), device.ptr(work),
+            device.ptr(sc), device.ptr(self.vec_partials), float(rtol), int(maxiter),
+            int(check_every), C.byref(info), device.stream_ptr())
+        _lib.check(rc)
+        return x, PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
+
+    def backsolve(self, x_ext, f=1.0, out=None):
+        """Full nodal vector from the exterior solution: interiors
+        ``u_i = A_ii^-1 (f_i - A_ie u_e)`` element by element
+        (_solve_interior_dofs, sem/discrete.py:513-524)."""
+        self._vec(x_ext, "x_ext")
+        u = (torch.empty(self.n_nodes, dtype=torch.float64, device=self.dev) if out is None
+             else self._full_vec(out, "out"))
+        u[:self.n_ext].copy_(x_ext)
+        self._element_pass(_lib.SC_BACKSOLVE, u=u, f=f)
+        return u
+
+    def solve(self, f=1.0, dirichlet_values=None, **pcg_kwargs):
+        """The whole DOFManagerSC.solve path (sem/discrete.py:526-528): condensed
+        load, Dirichlet lifting, PCG on the exterior DOFs, interior
+        back-substitution.  Returns (u[n_nodes], PCGInfo)."""
+        b = self.lift(self.rhs(f), dirichlet_values)
+        x, info = self.solve_pcg(b, **pcg_kwargs)
+        return self.backsolve(x, f), info

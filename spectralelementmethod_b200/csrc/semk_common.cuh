@@ -133,4 +133,42 @@ __device__ __forceinline__ double semk_block_sum(double v, double *smem_scratch 
   __syncthreads();
   return t;
 }
+// ---- deterministic grid-wide reduction shared by the vector kernels (semk_vec.cu) and
+// the condensed operator (semk_sc.cu).  partials layout: [kSemkRedMaxBlocks][4] doubles,
+// then one 64-bit arrival counter (zeroed once by the caller; every reduction leaves it
+// at zero).  Grids that use it have at most kSemkRedMaxBlocks CTAs.
+constexpr int kSemkRedMaxBlocks = 148 * 8;
+__device__ __forceinline__ unsigned long long *semk_red_counter(double *partials) {
+  return reinterpret_cast<unsigned long long *>(partials + 4 * kSemkRedMaxBlocks);
+}
+// Publish this CTA's NV partial sums; returns true (to all threads) in the CTA
+// that arrives last, with `tot[0..NV)` holding the fixed-order totals in thread 0.
+template <int NV>
+__device__ __forceinline__ bool semk_finish_reduction(double (&v)[NV], double *partials,
+                                                      double (&tot)[NV]) {
+  __shared__ double red[32];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const double s = semk_block_sum(v[j], red);
+    if (threadIdx.x == 0) partials[4 * blockIdx.x + j] = s;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(semk_red_counter(partials), 1ull);
+    is_last = (t == (unsigned long long)gridDim.x - 1ull);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+      s += __ldcg(partials + 4 * b + j);
+    tot[j] = semk_block_sum(s, red);
+  }
+  if (threadIdx.x == 0) *semk_red_counter(partials) = 0ull;
+  return true;
+}
 #endif

@@ -1,0 +1,447 @@
+// semk_sc.cu -- static condensation on the device.
+//
+// The reference's solver formulation (DOFManagerSC, sem/discrete.py:283-528):
+// eliminate the (p-1)^2 interior DOFs of every element,
+//     S_e = A_ee - A_ei A_ii^{-1} A_ie,   g_e = f_e - A_ei A_ii^{-1} f_i
+// (compute_local_sc_system, :438-476), assemble and solve the condensed system
+// over the element-exterior DOFs (:478-511) and recover the interiors element
+// by element (:513-524).  Here:
+//
+//   sc_element_kernel<N>  one CTA per element.  Rebuilds the 4-index local
+//       stiffness of examples/poisson.py:166-193 entry by entry from the
+//       geometric factors (closed form below), Cholesky-factorises the interior
+//       block in shared memory (A_ii = L L^T), Z = L^{-1} [A_ie | f_i], and
+//       writes  S_e = A_ee - Z^T Z (packed lower triangle),
+//               g_e = f_e - Z^T (L^{-1} f_i),
+//               u_i = L^{-T} (L^{-1} f_i - Z u_e)      (back-substitution).
+//       Set-up / once-per-solve work; the factorisation is recomputed instead
+//       of stored (19 KB per element at p = 8 against 4 KB for S_e).
+//   sc_matvec_kernel<N>   the condensed apply, HBM-bound: streams the packed
+//       S_e blocks (evict-first loads) into shared memory, gathers the 4p
+//       exterior values through the L2G map and forms y_loc = S_e u_e, one
+//       thread per row, fixed summation order.
+//   sc_node_kernel        every exterior node sums its entries of y_loc in the
+//       fixed order of the node -> entries table (the reference's
+//       `grhs[inds_ext] += ...`, :499, without atomics), applies the Dirichlet
+//       elimination (:505-510) and takes the fused u.y.
+//
+// Local stiffness entry (p,q),(r,s) of  y = D^T (G00 ur + G01 us) + (G01 ur + G11 us) D,
+// ur = D u, us = u D^T:
+//   A = [q==s] sum_m D[m][p] G00[m][q] D[m][r]  +  D[r][p] G01[r][q] D[q][s]
+//     + D[p][r] G01[p][s] D[s][q]               +  [p==r] sum_n G11[p][n] D[n][s] D[n][q]
+#include <math.h>
+
+#include "semk_common.cuh"
+
+namespace {
+
+constexpr int kScThreads = 128;
+constexpr int kScTX = 16, kScTY = 8;  // trailing-update thread tile of the factorisation
+
+template <int N>
+struct ScCfg {
+  static constexpr int NN = N * N;
+  static constexpr int NE = 4 * (N - 1);         // exterior nodes of an element
+  static constexpr int NI = (N - 2) * (N - 2);   // interior nodes
+  static constexpr int NS = NE * (NE + 1) / 2;   // packed S_e (always even)
+  static constexpr int LDI = NI | 1;             // odd row strides: conflict-free columns
+  static constexpr int LDZ = NE + 1;             // NE columns of A_ie + the load column
+  static constexpr int kDoubles =
+      3 * NN + NN + NI * LDI + NI * LDZ + NE * NE + NI + NE + NE + NI;
+  static constexpr size_t kSmem = sizeof(double) * kDoubles + sizeof(int) * (NE + 4);
+  static constexpr int EPB = kScThreads / NE;    // elements per CTA step of the matvec
+  static constexpr size_t kMatvecSmem = sizeof(double) * (size_t)EPB * (NS + NE);
+};
+
+struct ScElemArgs {
+  int64_t n_elem;
+  const int64_t *slot_of_elem;
+  const double *G;
+  int64_t g_patch_stride;
+  int pe;
+  const double *D;
+  const int32_t *ext_loc;
+  const uint32_t *l2g;
+  const double *JxW;
+  const double *f_nodal;
+  double f_scale;
+  int mode;
+  double *S_out;
+  int64_t s_stride;
+  double *sdiag_loc;
+  double *g_loc;
+  double *u;
+  int32_t *bad_flag;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
+  using C = ScCfg<N>;
+  constexpr int NN = C::NN, NE = C::NE, NI = C::NI, NS = C::NS, LDI = C::LDI, LDZ = C::LDZ;
+  constexpr int M = N - 2;
+  extern __shared__ __align__(16) double sc_smem[];
+  double *sG = sc_smem;            // [3][N][N] geometric factors G00, G01, G11
+  double *sD = sG + 3 * NN;        // [N][N]
+  double *sA = sD + NN;            // [NI][LDI] interior block -> Cholesky factor (lower)
+  double *sZ = sA + NI * LDI;      // [NI][LDZ] A_ie | f_i  ->  L^{-1} of both
+  double *sE = sZ + NI * LDZ;      // [NE][NE] A_ee (lower part used)
+  double *sInv = sE + NE * NE;     // [NI] 1 / L[i][i]
+  double *sFe = sInv + NI;         // [NE] exterior part of the load
+  double *sUe = sFe + NE;          // [NE] exterior values (back-substitution)
+  double *sT = sUe + NE;           // [NI] back-substitution vector
+  int *sExt = reinterpret_cast<int *>(sT + NI);  // [NE] lexicographic index of exterior k
+  int *sBad = sExt + NE;
+  const int tid = threadIdx.x;
+  const int tx = tid % kScTX, ty = tid / kScTX;
+  const int NP = N * a.pe;
+  const bool need_f = (a.mode & (SEMK_SC_RHS | SEMK_SC_BACKSOLVE)) != 0;
+
+  auto entry = [&](int p, int q, int r, int s) -> double {
+    double v = sD[r * N + p] * sG[NN + r * N + q] * sD[q * N + s] +
+               sD[p * N + r] * sG[NN + p * N + s] * sD[s * N + q];
+    if (q == s) {
+#pragma unroll
+      for (int m = 0; m < N; ++m) v = fma(sD[m * N + p] * sD[m * N + r], sG[m * N + q], v);
+    }
+    if (p == r) {
+#pragma unroll
+      for (int n = 0; n < N; ++n)
+        v = fma(sD[n * N + s] * sD[n * N + q], sG[2 * NN + p * N + n], v);
+    }
+    return v;
+  };
+
+  for (int64_t e = blockIdx.x; e < a.n_elem; e += gridDim.x) {
+    __syncthreads();  // the previous element is completely done with shared memory
+    {
+      const int64_t slot = a.slot_of_elem ? a.slot_of_elem[e] : e;
+      const int64_t patch = slot / a.pe;
+      const int lp = (int)(slot - patch * a.pe);
+      const double *g = a.G + patch * a.g_patch_stride + lp * N;
+      for (int i = tid; i < 3 * NN; i += kScThreads) {
+        const int c = i / NN, k = i - c * NN;
+        const int m = k / N, n = k - m * N;
+        sG[i] = g[(c * N + m) * NP + n];
+      }
+      for (int i = tid; i < NN; i += kScThreads) sD[i] = a.D[i];
+      for (int i = tid; i < NE; i += kScThreads) sExt[i] = a.ext_loc[i];
+      if (tid == 0) *sBad = 0;
+    }
+    __syncthreads();
+    // ---- local stiffness blocks --------------------------------------------------
+    for (int idx = tid; idx < NI * NI; idx += kScThreads) {
+      const int i = idx / NI, j = idx - i * NI;
+      if (j <= i) sA[i * LDI + j] = entry(1 + i / M, 1 + i % M, 1 + j / M, 1 + j % M);
+    }
+    for (int idx = tid; idx < NI * NE; idx += kScThreads) {
+      const int i = idx / NE, k = idx - i * NE;
+      const int x = sExt[k];
+      sZ[i * LDZ + k] = entry(1 + i / M, 1 + i % M, x / N, x % N);
+    }
+    for (int idx = tid; idx < NE * NE; idx += kScThreads) {
+      const int k = idx / NE, l = idx - k * NE;
+      if (l <= k) {
+        const int x = sExt[k], z = sExt[l];
+        sE[idx] = entry(x / N, x % N, z / N, z % N);
+      }
+    }
+    if (need_f) {
+      const double *jw = a.JxW + e * NN;
+      const uint32_t *row = a.l2g + e * NN;
+      for (int i = tid; i < NI; i += kScThreads) {
+        const int k = (1 + i / M) * N + 1 + i % M;
+        const double f = a.f_nodal ? a.f_nodal[row[k]] : 1.0;
+        sZ[i * LDZ + NE] = a.f_scale * jw[k] * f;
+      }
+      for (int k = tid; k < NE; k += kScThreads) {
+        const int x = sExt[k];
+        const double f = a.f_nodal ? a.f_nodal[row[x]] : 1.0;
+        sFe[k] = a.f_scale * jw[x] * f;
+        if (a.mode & SEMK_SC_BACKSOLVE) sUe[k] = a.u[row[x]];
+      }
+    }
+    __syncthreads();
+    // ---- A_ii = L L^T, right-looking, in place (lower triangle) --------------------
+    for (int k = 0; k < NI; ++k) {
+      const double d = sA[k * LDI + k];  // nobody writes (k,k) during step k
+      const double inv = 1.0 / sqrt(d);
+      if (tid == 0) {
+        sInv[k] = inv;
+        if (!(d > 0.0)) *sBad = 1;
+      }
+      for (int i = k + 1 + tid; i < NI; i += kScThreads) sA[i * LDI + k] *= inv;
+      __syncthreads();
+      for (int i = k + 1 + ty; i < NI; i += kScTY) {
+        const double lik = sA[i * LDI + k];
+        for (int j = k + 1 + tx; j <= i; j += kScTX)
+          sA[i * LDI + j] = fma(-lik, sA[j * LDI + k], sA[i * LDI + j]);
+      }
+      __syncthreads();
+    }
+    // ---- Z = L^{-1} [A_ie | f_i]: one thread per column, forward substitution -------
+    if (tid < NE + (need_f ? 1 : 0)) {
+      for (int i = 0; i < NI; ++i) {
+        double acc = sZ[i * LDZ + tid];
+        for (int j = 0; j < i; ++j) acc = fma(-sA[i * LDI + j], sZ[j * LDZ + tid], acc);
+        sZ[i * LDZ + tid] = acc * sInv[i];
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && *sBad) *a.bad_flag = 1;
+    // ---- S_e = A_ee - Z^T Z (packed lower triangle, row major) ----------------------
+    if (a.mode & SEMK_SC_SCHUR) {
+      double *So = a.S_out + e * a.s_stride;
+      for (int q = tid; q < NS; q += kScThreads) {
+        int k = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+        while ((k + 1) * (k + 2) / 2 <= q) ++k;
+        while (k * (k + 1) / 2 > q) --k;
+        const int l = q - k * (k + 1) / 2;
+        double acc = sE[k * NE + l];
+        for (int i = 0; i < NI; ++i) acc = fma(-sZ[i * LDZ + k], sZ[i * LDZ + l], acc);
+        So[q] = acc;
+        if (k == l && a.sdiag_loc) a.sdiag_loc[e * NE + k] = acc;
+      }
+    }
+    // ---- g_e = f_e - Z^T (L^{-1} f_i) ------------------------------------------------
+    if (a.mode & SEMK_SC_RHS) {
+      for (int k = tid; k < NE; k += kScThreads) {
+        double acc = sFe[k];
+        for (int i = 0; i < NI; ++i) acc = fma(-sZ[i * LDZ + k], sZ[i * LDZ + NE], acc);
+        a.g_loc[e * NE + k] = acc;
+      }
+    }
+    // ---- u_i = L^{-T} (L^{-1} f_i - Z u_e) -------------------------------------------
+    if (a.mode & SEMK_SC_BACKSOLVE) {
+      for (int i = tid; i < NI; i += kScThreads) {
+        double acc = sZ[i * LDZ + NE];
+        for (int k = 0; k < NE; ++k) acc = fma(-sZ[i * LDZ + k], sUe[k], acc);
+        sT[i] = acc;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        for (int i = NI - 1; i >= 0; --i) {
+          const double xi = sT[i] * sInv[i];
+          __syncwarp();
+          if (tid == 0) sT[i] = xi;
+          for (int j = tid; j < i; j += 32) sT[j] = fma(-sA[i * LDI + j], xi, sT[j]);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      const uint32_t *row = a.l2g + e * NN;
+      for (int i = tid; i < NI; i += kScThreads) a.u[row[(1 + i / M) * N + 1 + i % M]] = sT[i];
+    }
+  }
+}
+
+// ---- condensed apply, element part: y_loc = S_e u[l2g_ext] ------------------------------
+template <int N>
+__global__ void __launch_bounds__(kScThreads)
+    sc_matvec_kernel(int64_t n_elem, const double *__restrict__ S,
+                     const uint32_t *__restrict__ l2g_ext, const double *__restrict__ u,
+                     const uint8_t *__restrict__ mask_in, double *__restrict__ y_loc) {
+  using C = ScCfg<N>;
+  constexpr int NE = C::NE, NS = C::NS, EPB = C::EPB;
+  extern __shared__ __align__(16) double sc_smem[];
+  double *sS = sc_smem;            // [EPB][NS]
+  double *sU = sS + EPB * NS;      // [EPB][NE]
+  const int tid = threadIdx.x;
+  const int le = tid / NE, k = tid - le * NE;
+  const int64_t n_groups = (n_elem + EPB - 1) / EPB;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int64_t e0 = grp * EPB;
+    const int ne = (int)((n_elem - e0) < (int64_t)EPB ? (n_elem - e0) : (int64_t)EPB);
+    // the S blocks are read exactly once per apply: streaming loads keep u / y_loc in L2
+    const double2 *src = reinterpret_cast<const double2 *>(S + e0 * NS);
+    double2 *dst = reinterpret_cast<double2 *>(sS);
+    const int n2 = ne * (NS / 2);
+    for (int q = tid; q < n2; q += kScThreads) dst[q] = __ldcs(src + q);
+    const bool on = le < ne;
+    if (on) {
+      const uint32_t g = l2g_ext[(e0 + le) * NE + k];
+      double v = u[g];
+      if (mask_in && mask_in[g]) v = 0.0;
+      sU[le * NE + k] = v;
+    }
+    __syncthreads();
+    if (on) {
+      const double *s = sS + le * NS;
+      const double *uu = sU + le * NE;
+      const int kk = k * (k + 1) / 2;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        const int idx = (j <= k) ? kk + j : j * (j + 1) / 2 + k;
+        acc = fma(s[idx], uu[j], acc);
+      }
+      y_loc[(e0 + le) * NE + k] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- condensed apply / assembly, node part ------------------------------------------------
+constexpr int kNodeThreads = 256;
+
+__global__ void __launch_bounds__(kNodeThreads)
+    sc_node_kernel(int64_t n_ext, const uint32_t *__restrict__ node_ptr,
+                   const uint32_t *__restrict__ node_pos, const double *__restrict__ loc,
+                   const uint8_t *__restrict__ dirichlet, const double *__restrict__ u,
+                   double *__restrict__ y, int flags, double fill, double *__restrict__ partials,
+                   double *__restrict__ dot_out) {
+  double acc[1] = {0.0};
+  const bool mask_out = dirichlet && (flags & SEMK_MASK_OUT);
+  const bool identity = (flags & SEMK_DIRICHLET_IDENTITY) && u;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_ext;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t q0 = node_ptr[g], q1 = node_ptr[g + 1];
+    double s = 0.0;
+    for (uint32_t q = q0; q < q1; ++q) s += loc[node_pos[q]];
+    if (mask_out && dirichlet[g]) s = identity ? u[g] : fill;
+    y[g] = s;
+    if (dot_out) acc[0] = fma(u[g], s, acc[0]);
+  }
+  if (dot_out) {
+    double tot[1];
+    if (semk_finish_reduction<1>(acc, partials, tot) && threadIdx.x == 0) dot_out[0] = tot[0];
+  }
+}
+
+inline unsigned node_blocks(int64_t n) {
+  const int64_t want = (n + kNodeThreads - 1) / kNodeThreads;
+  return (unsigned)(want < 1 ? 1 : (want < kSemkRedMaxBlocks ? want : kSemkRedMaxBlocks));
+}
+
+int check_sc_op(const semk_sc_op *op, const char *who) {
+  if (!op) {
+    semk_set_error(std::string(who) + ": null operator");
+    return SEMK_ERR_INVALID;
+  }
+  if (op->n1 < 3 || op->n1 > 11) {
+    semk_set_error(std::string(who) + ": static condensation supports orders 2..10");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  const int ne = 4 * (op->n1 - 1);
+  if (op->n_ext_loc != ne || op->s_stride != (int64_t)ne * (ne + 1) / 2 || op->n_elem <= 0 ||
+      op->n_ext <= 0 || !op->S || !op->l2g_ext || !op->y_loc || !op->node_ptr ||
+      !op->node_pos) {
+    semk_set_error(std::string(who) + ": inconsistent semk_sc_op");
+    return SEMK_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(op->S) & 15u) != 0) {
+    semk_set_error(std::string(who) + ": S must be 16-byte aligned");
+    return SEMK_ERR_INVALID;
+  }
+  return SEMK_OK;
+}
+
+}  // namespace
+
+#define SEMK_DISPATCH_SC(n1, CALL)                                                   \
+  switch (n1) {                                                                      \
+    case 3: CALL(3); break;                                                          \
+    case 4: CALL(4); break;                                                          \
+    case 5: CALL(5); break;                                                          \
+    case 6: CALL(6); break;                                                          \
+    case 7: CALL(7); break;                                                          \
+    case 8: CALL(8); break;                                                          \
+    case 9: CALL(9); break;                                                          \
+    case 10: CALL(10); break;                                                        \
+    case 11: CALL(11); break;                                                        \
+    default:                                                                         \
+      semk_set_error("static condensation supports orders 2..10 (n1 in [3, 11])");   \
+      return SEMK_ERR_UNSUPPORTED;                                                   \
+  }
+
+extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem,
+                                   const double *G, int64_t g_patch_stride, int elems_per_patch,
+                                   const double *D, const int32_t *ext_loc, const uint32_t *l2g,
+                                   const double *JxW, const double *f_nodal, double f_scale,
+                                   int mode, double *S_out, int64_t s_stride, double *sdiag_loc,
+                                   double *g_loc, double *u, int32_t *bad_flag, void *stream) {
+  SEMK_REQUIRE(n_elem > 0 && G && D && ext_loc && bad_flag &&
+                   elems_per_patch > 0 && g_patch_stride > 0,
+               "semk_sc_element_f64: bad argument");
+  SEMK_REQUIRE(mode != 0 && (mode & ~7) == 0, "semk_sc_element_f64: bad mode");
+  if (n1 < 3 || n1 > 11) {
+    semk_set_error("semk_sc_element_f64: static condensation supports orders 2..10");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  const int ne = 4 * (n1 - 1);
+  if (mode & SEMK_SC_SCHUR)
+    SEMK_REQUIRE(S_out && s_stride == (int64_t)ne * (ne + 1) / 2,
+                 "semk_sc_element_f64: SCHUR needs S_out and the packed stride");
+  if (mode & SEMK_SC_RHS)
+    SEMK_REQUIRE(g_loc && JxW && l2g, "semk_sc_element_f64: RHS needs g_loc, JxW, l2g");
+  if (mode & SEMK_SC_BACKSOLVE)
+    SEMK_REQUIRE(u && JxW && l2g, "semk_sc_element_f64: BACKSOLVE needs u, JxW, l2g");
+  ScElemArgs a;
+  a.n_elem = n_elem;
+  a.slot_of_elem = slot_of_elem;
+  a.G = G;
+  a.g_patch_stride = g_patch_stride;
+  a.pe = elems_per_patch;
+  a.D = D;
+  a.ext_loc = ext_loc;
+  a.l2g = l2g;
+  a.JxW = JxW;
+  a.f_nodal = f_nodal;
+  a.f_scale = f_scale;
+  a.mode = mode;
+  a.S_out = S_out;
+  a.s_stride = s_stride;
+  a.sdiag_loc = sdiag_loc;
+  a.g_loc = g_loc;
+  a.u = u;
+  a.bad_flag = bad_flag;
+  cudaStream_t st = semk_stream(stream);
+  const unsigned grid = (unsigned)(n_elem < 148 * 16 ? n_elem : 148 * 16);
+#define SEMK_CALL(NV)                                                                      \
+  do {                                                                                     \
+    SEMK_CUDA_CHECK(cudaFuncSetAttribute(sc_element_kernel<NV>,                       \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         (int)ScCfg<NV>::kSmem));                          \
+    sc_element_kernel<NV><<<grid, kScThreads, ScCfg<NV>::kSmem, st>>>(a);             \
+  } while (0)
+  SEMK_DISPATCH_SC(n1, SEMK_CALL)
+#undef SEMK_CALL
+  SEMK_LAUNCH_CHECK("sc_element_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_apply_f64(const semk_sc_op *op, const double *u, double *y, int flags,
+                                 double *dot_out, void *stream) {
+  int rc = check_sc_op(op, "semk_sc_apply_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(u && y && u != y, "semk_sc_apply_f64: null / aliased vectors");
+  SEMK_REQUIRE(!dot_out || op->partials, "semk_sc_apply_f64: dot_out needs op->partials");
+  cudaStream_t st = semk_stream(stream);
+  const uint8_t *mask_in = (op->dirichlet && (flags & SEMK_MASK_IN)) ? op->dirichlet : nullptr;
+#define SEMK_CALL(NV)                                                                      \
+  do {                                                                                     \
+    const int64_t groups = (op->n_elem + ScCfg<NV>::EPB - 1) / ScCfg<NV>::EPB;             \
+    const unsigned grid = (unsigned)(groups < 148 * 12 ? groups : 148 * 12);               \
+    sc_matvec_kernel<NV><<<grid, kScThreads, ScCfg<NV>::kMatvecSmem, st>>>(                 \
+        op->n_elem, op->S, op->l2g_ext, u, mask_in, op->y_loc);                            \
+  } while (0)
+  SEMK_DISPATCH_SC(op->n1, SEMK_CALL)
+#undef SEMK_CALL
+  SEMK_LAUNCH_CHECK("sc_matvec_kernel");
+  sc_node_kernel<<<node_blocks(op->n_ext), kNodeThreads, 0, st>>>(
+      op->n_ext, op->node_ptr, op->node_pos, op->y_loc, op->dirichlet, u, y, flags, 0.0,
+      op->partials, dot_out);
+  SEMK_LAUNCH_CHECK("sc_node_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_assemble_f64(const semk_sc_op *op, const double *loc, double *out,
+                                    int flags, double fill_dirichlet, void *stream) {
+  int rc = check_sc_op(op, "semk_sc_assemble_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(loc && out, "semk_sc_assemble_f64: null pointer");
+  sc_node_kernel<<<node_blocks(op->n_ext), kNodeThreads, 0, semk_stream(stream)>>>(
+      op->n_ext, op->node_ptr, op->node_pos, loc, op->dirichlet, nullptr, out,
+      flags & SEMK_MASK_OUT, fill_dirichlet, nullptr, nullptr);
+  SEMK_LAUNCH_CHECK("sc_node_kernel");
+  return SEMK_OK;
+}

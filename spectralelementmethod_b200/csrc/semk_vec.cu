@@ -18,47 +18,21 @@
 namespace {
 
 constexpr int kVecThreads = 256;
-constexpr int kVecMaxBlocks = 148 * 8;
+constexpr int kVecMaxBlocks = kSemkRedMaxBlocks;
 
 inline int vec_blocks(int64_t n) {
   const int64_t want = (n + kVecThreads * 4 - 1) / (kVecThreads * 4);
   return (int)(want < 1 ? 1 : (want < kVecMaxBlocks ? want : kVecMaxBlocks));
 }
 
-// partials layout: [kVecMaxBlocks][4] doubles, then one 64-bit arrival counter
+// partials layout and the last-arrival reduction: semk_common.cuh
 __device__ __forceinline__ unsigned long long *counter_of(double *partials) {
-  return reinterpret_cast<unsigned long long *>(partials + 4 * kVecMaxBlocks);
+  return semk_red_counter(partials);
 }
-
-// Publish this CTA's NV partial sums; returns true (to all threads) in the CTA
-// that arrives last, with `tot[0..NV)` holding the fixed-order totals in thread 0.
 template <int NV>
 __device__ __forceinline__ bool finish_reduction(double (&v)[NV], double *partials,
                                                  double (&tot)[NV]) {
-  __shared__ double red[32];
-  __shared__ bool is_last;
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const double s = semk_block_sum(v[j], red);
-    if (threadIdx.x == 0) partials[4 * blockIdx.x + j] = s;
-  }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long t = atomicAdd(counter_of(partials), 1ull);
-    is_last = (t == (unsigned long long)gridDim.x - 1ull);
-  }
-  __syncthreads();
-  if (!is_last) return false;
-  __threadfence();
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    double s = 0.0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-      s += __ldcg(partials + 4 * b + j);
-    tot[j] = semk_block_sum(s, red);
-  }
-  if (threadIdx.x == 0) *counter_of(partials) = 0ull;
-  return true;
+  return semk_finish_reduction<NV>(v, partials, tot);
 }
 
 __global__ void __launch_bounds__(kVecThreads)
@@ -361,25 +335,22 @@ extern "C" int semk_dot_f64(int64_t n, const double *a, const double *b, double 
   return SEMK_OK;
 }
 
-extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
-                                  const double *dinv, double *work, double *sc,
-                                  double *vec_partials, double rtol, int maxiter, int check_every,
-                                  semk_pcg_info *info, void *stream) {
-  SEMK_REQUIRE(op && b && x && dinv && work && sc && vec_partials && info,
-               "semk_pcg_solve_f64: null pointer");
-  SEMK_REQUIRE(maxiter >= 0 && check_every >= 1 && rtol >= 0.0, "semk_pcg_solve_f64: bad control");
-  cudaStream_t st = semk_stream(stream);
-  const int64_t n = op->n_nodes;
+// The native PCG loop, generic over the operator: `apply(in, out, dot)` queues
+// out = Ahat in on `st` and, when dot != nullptr, leaves in.out in *dot (device).
+template <class ApplyFn>
+static int pcg_solve_impl(ApplyFn apply, int64_t n, const uint8_t *dirichlet, const double *b,
+                          double *x, const double *dinv, double *work, double *sc,
+                          double *vec_partials, double rtol, int maxiter, int check_every,
+                          semk_pcg_info *info, cudaStream_t st) {
   const int64_t n_pad = (n + 31) & ~(int64_t)31;  // keeps the sub-vectors 16-byte aligned
   double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad;
-  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
   const double tol2 = rtol * rtol;
   static double *h_sc = nullptr;  // pinned landing zone for the 64-byte scalar block
   if (!h_sc) SEMK_CUDA_CHECK(cudaMallocHost(&h_sc, 8 * sizeof(double)));
 
-  int rc = semk_poisson_apply_f64(op, x, Ap, flags, nullptr, st);
+  int rc = apply(x, Ap, nullptr);
   if (rc != SEMK_OK) return rc;
-  rc = semk_pcg_init_f64(n, n, b, Ap, dinv, op->dirichlet, r, p, sc, vec_partials, st);
+  rc = semk_pcg_init_f64(n, n, b, Ap, dinv, dirichlet, r, p, sc, vec_partials, st);
   if (rc != SEMK_OK) return rc;
 
   auto poll = [&]() -> int {
@@ -398,7 +369,7 @@ extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
   }
 
   auto one_iteration = [&]() -> int {
-    int e = semk_poisson_apply_f64(op, p, Ap, flags, sc + 1, st);
+    int e = apply(p, Ap, sc + 1);
     if (e != SEMK_OK) return e;
     // x += alpha p rides with the p update (one vector pass less per iteration)
     e = update_xr(n, n, p, Ap, dinv, x, r, sc, vec_partials, tol2, true, st);
@@ -432,7 +403,7 @@ extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
   while (launched < maxiter) {
     if (use_graph) {
       if (cudaGraphLaunch(exec, st) != cudaSuccess) {
-        semk_set_error("semk_pcg_solve_f64: cudaGraphLaunch failed");
+        semk_set_error("PCG driver: cudaGraphLaunch failed");
         rc = SEMK_ERR_CUDA;
         break;
       }
@@ -460,8 +431,43 @@ extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
   info->status = status;
   info->rel_residual = sqrt(h_sc[3] / h_sc[4]);
   if (status == SEMK_ERR_BREAKDOWN) {
-    semk_set_error("semk_pcg_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
+    semk_set_error("PCG driver: breakdown (p.Ap <= 0 or non-finite)");
     return SEMK_ERR_BREAKDOWN;
   }
   return SEMK_OK;
+}
+
+extern "C" int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x,
+                                  const double *dinv, double *work, double *sc,
+                                  double *vec_partials, double rtol, int maxiter, int check_every,
+                                  semk_pcg_info *info, void *stream) {
+  SEMK_REQUIRE(op && b && x && dinv && work && sc && vec_partials && info,
+               "semk_pcg_solve_f64: null pointer");
+  SEMK_REQUIRE(maxiter >= 0 && check_every >= 1 && rtol >= 0.0, "semk_pcg_solve_f64: bad control");
+  cudaStream_t st = semk_stream(stream);
+  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
+  auto apply = [&](const double *in, double *out, double *dot) -> int {
+    return semk_poisson_apply_f64(op, in, out, flags, dot, st);
+  };
+  return pcg_solve_impl(apply, op->n_nodes, op->dirichlet, b, x, dinv, work, sc, vec_partials,
+                        rtol, maxiter, check_every, info, st);
+}
+
+// The same loop on the statically condensed operator Shat = M S M + (I - M) over the
+// element-exterior DOFs (sem/discrete.py:502-511 solves that system with SuperLU).
+extern "C" int semk_sc_pcg_solve_f64(const semk_sc_op *op, const double *b, double *x,
+                                     const double *dinv, double *work, double *sc,
+                                     double *vec_partials, double rtol, int maxiter,
+                                     int check_every, semk_pcg_info *info, void *stream) {
+  SEMK_REQUIRE(op && b && x && dinv && work && sc && vec_partials && info,
+               "semk_sc_pcg_solve_f64: null pointer");
+  SEMK_REQUIRE(maxiter >= 0 && check_every >= 1 && rtol >= 0.0,
+               "semk_sc_pcg_solve_f64: bad control");
+  cudaStream_t st = semk_stream(stream);
+  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
+  auto apply = [&](const double *in, double *out, double *dot) -> int {
+    return semk_sc_apply_f64(op, in, out, flags, dot, st);
+  };
+  return pcg_solve_impl(apply, op->n_ext, op->dirichlet, b, x, dinv, work, sc, vec_partials,
+                        rtol, maxiter, check_every, info, st);
 }

@@ -312,6 +312,18 @@ class DOFManagerSC(DOFManager):
         perm[n_ext:] = np.arange(n_ext, n)
         mesh._permute_nodes(perm)
 
+    def condensed_poisson_operator(self, dirichlet=None, **kwargs):
+        """The statically condensed Poisson operator on the GPU: local Schur
+        complements, condensed apply / PCG over the element-exterior DOFs and
+        interior back-substitution (the device twin of assemble_global_sc_system
+        + solve; additive API, see condensed.CondensedPoissonOperator).
+
+        dirichlet : bool[n_nodes] or bool[ndof_exterior], optional -- True on
+            essential-BC nodes (the ``on_ebc`` polarity of ``solve``).
+        """
+        from .condensed import CondensedPoissonOperator
+        return CondensedPoissonOperator(self, dirichlet=dirichlet, **kwargs)
+
     # -- Schur-complement assembly (host; kept for literal drop-in use) ------------
     def init_global_linear_system(self):
         """Empty COO Schur system over the exterior DOFs and a zero RHS

@@ -47,6 +47,9 @@ def test_struct_layout_matches_header(tmp_path):
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "semk.h"', 'int main(void) {',
            '  printf("%zu %zu\\n", sizeof(struct semk_op), sizeof(struct semk_pcg_info));']
     src += ['  printf("%%zu\\n", offsetof(struct semk_op, %s));' % f for f in fields]
+    sc_fields = [f[0] for f in _lib.semk_sc_op._fields_]
+    src += ['  printf("%zu\\n", sizeof(struct semk_sc_op));']
+    src += ['  printf("%%zu\\n", offsetof(struct semk_sc_op, %s));' % f for f in sc_fields]
     src += ['  return 0; }']
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -58,6 +61,10 @@ def test_struct_layout_matches_header(tmp_path):
     assert int(out[1]) == ctypes.sizeof(_lib.semk_pcg_info) == 24
     for f, off in zip(fields, out[2:]):
         assert getattr(_lib.semk_op, f).offset == int(off), f
+    rest = out[2 + len(fields):]
+    assert int(rest[0]) == ctypes.sizeof(_lib.semk_sc_op)
+    for f, off in zip(sc_fields, rest[1:]):
+        assert getattr(_lib.semk_sc_op, f).offset == int(off), f
 
 
 def _plan(nx, ny, p, pe, order=None, dirichlet=None):

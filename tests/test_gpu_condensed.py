@@ -1,0 +1,152 @@
+"""Parity of the device static-condensation path (csrc/semk_sc.cu, SURVEY.md
+8(f) row 1) with the reference's DOFManagerSC formulation
+(sem/discrete.py:404-528).
+
+Anchors: the golden solutions frozen from the live reference's
+``DOFManagerSC.solve`` (tests/golden/case_*_sc*.npz), the CPU oracle's local
+Schur complements / condensed system built from the reference's own invJ and
+detJxW (tier T1) and from the device geometry (tier T2), and size-independent
+properties at a larger size.  Tolerance: 1e-12 relative L2 (BASELINE.json).
+"""
+import numpy as np
+import pytest
+import torch
+
+import sem_oracle as so
+from conftest import build_package_case, golden_case_names, load_case, rel_l2
+from spectralelementmethod_b200 import _lib, discrete, meshgen
+from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+SC_CASES = [n for n in golden_case_names() if "_sc" in n]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def oracle_condensed(g):
+    """The condensed system of a golden case from the reference's own invJ / detJxW
+    (oracle/sem_oracle.py:condensed_system, pinned in tests/test_oracle_golden.py)."""
+    return so.condensed_system(int(g["p"]), g["invJ"], g["JxW"], g["l2g"])
+
+
+def condensed_operator(name, tier):
+    g = load_case(name)
+    mesh, mngr = build_package_case(g["kind"], g["nx"], g["ny"], g["p"], g["sc"], g["rcm"])
+    kw = {}
+    if tier == "T1":
+        kw["geometric_factors"] = (g["invJ"], g["JxW"])
+    sc = mngr.condensed_poisson_operator(dirichlet=g["on_ebc"], **kw)
+    return g, mngr, sc
+
+
+@pytest.mark.parametrize("name", SC_CASES)
+@pytest.mark.parametrize("tier", ["T1", "T2"])
+def test_local_schur_and_condensed_system_vs_oracle(name, tier):
+    g, mngr, sc = condensed_operator(name, tier)
+    ref = oracle_condensed(g)
+    assert sc.n_ext == ref["n_ext"] == mngr.ndof_exterior
+    assert np.array_equal(sc.l2g_ext_host.astype(np.int64), ref["ids"])
+    S = sc.local_schur()
+    assert S.shape == ref["S"].shape
+    assert rel_l2(S, ref["S"]) < TOL
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(sc.n_ext)
+    dot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    y = host(sc.apply(dev(u), flags=0, dot_out=dot))
+    want = ref["Sg"] @ u
+    assert rel_l2(y, want) < TOL
+    assert abs(float(dot.item()) - u @ want) <= 1e-11 * abs(u @ want) + 1e-11
+    # Dirichlet elimination: Shat = M S M + (I - M)
+    on = g["on_ebc"][:sc.n_ext]
+    uf = np.where(on, 0.0, u)
+    want_m = np.where(on, u, ref["Sg"] @ uf)
+    assert rel_l2(host(sc.apply(dev(u))), want_m) < TOL
+    assert rel_l2(host(sc.diagonal(masked=False)), ref["Sg"].diagonal()) < TOL
+    assert rel_l2(host(sc.rhs(1.0)), ref["grhs"]) < TOL
+    # bit-reproducible
+    y2 = host(sc.apply(dev(u), flags=0))
+    assert np.array_equal(y, y2)
+
+
+@pytest.mark.parametrize("name", SC_CASES)
+@pytest.mark.parametrize("tier", ["T1", "T2"])
+def test_condensed_solve_vs_reference_golden(name, tier):
+    g, mngr, sc = condensed_operator(name, tier)
+    u, info = sc.solve(1.0, g["ebc_vals"], rtol=1e-13)
+    assert info.converged, info
+    assert u.numel() == mngr.ndof
+    assert rel_l2(host(u), g["solution"]) < TOL
+
+
+def test_condensed_solve_matches_uncondensed_pcg_with_nodal_load():
+    mesh, mngr = build_package_case("C", 12, 10, 6, True, True)
+    x, y = mesh.nodes
+    on = mngr.boundary_node_mask("ebc")
+    vals = np.where(on, 0.2 * ((x + 1) + (y + 1)), 0.0)
+    f = 1.0 + np.sin(2 * x) * np.cos(3 * y)
+    sc = mngr.condensed_poisson_operator(dirichlet=on)
+    u_sc, info_sc = sc.solve(f, vals, rtol=1e-13)
+    full = mngr.poisson_operator(dirichlet=on)
+    u_full, info_full = full.solve(dev(f), vals, rtol=1e-13)
+    assert info_sc.converged and info_full.converged
+    assert rel_l2(host(u_sc), host(u_full)) < 1e-11
+    assert info_sc.iterations < info_full.iterations
+    # the condensed solution satisfies the FULL system: true residual of Ahat u = bhat
+    b = full.lift(full.rhs(dev(f)), vals)
+    r = b - full.apply(u_sc)
+    assert float(r.norm() / b.norm()) < 1e-11
+
+
+def test_condensed_properties_at_size():
+    # 96 x 96 elements of order 8: 590 k DOF, 147 k exterior DOF
+    mesh, mngr = build_package_case("C", 96, 96, 8, True, False)
+    on = mngr.boundary_node_mask("ebc")
+    sc = mngr.condensed_poisson_operator(dirichlet=on)
+    n = sc.n_ext
+    rng = np.random.default_rng(1)
+    u, v = dev(rng.standard_normal(n)), dev(rng.standard_normal(n))
+    Su, Sv = sc.apply_unmasked(u), sc.apply_unmasked(v)
+    assert abs(float(v @ Su - u @ Sv)) <= 1e-11 * float(Su.norm() * v.norm())      # symmetric
+    ones = sc.new_vector(1.0)
+    assert float(sc.apply_unmasked(ones).abs().max()) <= 1e-10 * float(Su.abs().max())  # S 1 = 0
+    lin = sc.apply_unmasked(2.0 * u - 3.0 * v)
+    assert float((lin - (2.0 * Su - 3.0 * Sv)).norm() / lin.norm()) < 1e-13
+    assert torch.equal(sc.apply_unmasked(u), Su)                                   # deterministic
+    x_nodes, y_nodes = mesh.nodes
+    vals = np.where(on, 0.2 * ((x_nodes + 1) + (y_nodes + 1)), 0.0)
+    sol, info = sc.solve(1.0, vals, rtol=1e-12)
+    assert info.converged
+    full = mngr.poisson_operator(dirichlet=on)
+    b = full.lift(full.rhs(1.0), vals)
+    r = b - full.apply(sol)
+    assert float(r.norm() / b.norm()) < 1e-10
+
+
+def test_condensed_operator_errors():
+    mesh, mngr = build_package_case("S", 3, 2, 4, False, False)
+    with pytest.raises(ValueError):                       # needs DOFManagerSC
+        from spectralelementmethod_b200.condensed import CondensedPoissonOperator
+        CondensedPoissonOperator(mngr)
+    mesh, mngr = build_package_case("S", 3, 2, 4, True, False)
+    bad = np.zeros(mngr.ndof, dtype=bool)
+    bad[-1] = True                                        # an element-interior node
+    with pytest.raises(ValueError):
+        mngr.condensed_poisson_operator(dirichlet=bad)
+    mesh = meshgen.structured_quad_mesh(2, 2, 12)
+    b1 = LagrangeGaussLobatto(12)
+    mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+    with pytest.raises(NotImplementedError):              # the reference's range: order <= 10
+        mngr.condensed_poisson_operator()
+    sc = build_package_case("S", 3, 2, 4, True, False)[1].condensed_poisson_operator()
+    with pytest.raises(ValueError):
+        sc.apply(torch.zeros(3, dtype=torch.float64, device="cuda"))
+    lib = _lib.load()
+    assert lib.semk_sc_apply_f64(None, None, None, 0, None, None) == _lib.ERR_INVALID

@@ -261,3 +261,33 @@ def test_schur_helpers_on_a_synthetic_local_system():
     sol = np.zeros(16)
     mngr.solve(gsys, [(Ah, bh)], sol, np.zeros(ne, dtype=bool))
     assert np.allclose(sol[fe.global_dof_ind_hier], x, atol=1e-10)
+
+
+def test_condensed_tables_host():
+    """Tables of the device static-condensation path (condensed.condensed_tables):
+    exterior L2G in hierarchical order and the node -> entries lists."""
+    from spectralelementmethod_b200.condensed import condensed_tables
+    g = load_case("C448_sc_rcm")
+    mesh, mngr = build_package_case(g["kind"], g["nx"], g["ny"], g["p"], g["sc"], g["rcm"])
+    N = g["p"] + 1
+    geo = mesh.get_geometries()[0]
+    ext_loc = np.asarray(geo.exterior_node_ind)
+    assert np.array_equal(ext_loc, geo.hierarchical_node_order[:4 * g["p"]])
+    l2g = mesh.node_map_array().reshape(-1, N * N)
+    l2g_ext, ptr, pos = condensed_tables(l2g, ext_loc, mngr.ndof_exterior)
+    # the live reference's fe.global_dof_ind_hier (golden), exterior part
+    assert np.array_equal(l2g_ext, g["hier"][:, :4 * g["p"]])
+    for e, fe in enumerate(mngr.finite_elements()):
+        assert np.array_equal(l2g_ext[e], fe.global_dof_ind_hier[:fe.ndof_exterior])
+    assert ptr[0] == 0 and ptr[-1] == l2g_ext.size and pos.size == l2g_ext.size
+    flat = l2g_ext.ravel()
+    for node in (0, 1, mngr.ndof_exterior // 2, mngr.ndof_exterior - 1):
+        mine = pos[ptr[node]:ptr[node + 1]]
+        assert (flat[mine] == node).all() and (np.diff(mine.astype(np.int64)) > 0).all()
+        assert mine.size == (flat == node).sum()
+    # scatter-add through the table == np.add.at
+    loc = np.random.default_rng(0).standard_normal(flat.size)
+    want = np.zeros(mngr.ndof_exterior)
+    np.add.at(want, flat, loc)
+    got = np.add.reduceat(loc[pos], ptr[:-1].astype(np.int64))
+    assert np.allclose(got, want, rtol=0, atol=1e-13)

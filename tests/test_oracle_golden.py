@@ -77,6 +77,29 @@ def test_pcg_on_oracle_matrix_matches_direct_solution():
     assert 100 < it < 400      # 218 iterations at n=4
 
 
+@pytest.mark.parametrize("name", [n for n in golden_case_names() if "_sc" in n])
+def test_condensed_system_reproduces_reference_solution(name):
+    """oracle.condensed_system (checker of the device static-condensation path):
+    solving its assembled Schur system and back-substituting gives the
+    reference's DOFManagerSC.solve result (sem/discrete.py:502-528)."""
+    from scipy.sparse.linalg import spsolve
+    g = load_case(name)
+    c = so.condensed_system(int(g["p"]), g["invJ"], g["JxW"], g["l2g"])
+    n_ext = c["n_ext"]
+    assert np.allclose(c["S"], np.swapaxes(c["S"], 1, 2), rtol=0, atol=1e-11)
+    on = g["on_ebc"][:n_ext]
+    assert not g["on_ebc"][n_ext:].any()
+    free = ~on
+    sol = g["ebc_vals"].copy()
+    ext = sol[:n_ext]
+    A1 = c["Sg"][free]
+    ext[free] = spsolve(A1[:, free].tocsc(), c["grhs"][free] - A1[:, on] @ ext[on])
+    inner = np.linalg.solve(c["Aii"], (c["f_int"] - np.einsum("eij,ej->ei", c["Aie"],
+                                                              sol[c["ids"]]))[..., None])
+    sol[c["int_ids"]] = inner[..., 0]
+    assert rel_l2(sol, g["solution"]) < TOL
+
+
 def test_c_openmp_restatement_matches_python_loop():
     """oracle/sem_oracle_c.c (the all-threads CPU baseline) == the NumPy loop."""
     if so.c_lib() is None:
