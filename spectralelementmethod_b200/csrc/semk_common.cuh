@@ -105,6 +105,21 @@ __device__ __forceinline__ void semk_bulk_g2s(void *smem_dst, const void *gmem_s
       "l"(gmem_src), "r"(bytes), "r"(semk_smem_u32(bar))
       : "memory");
 }
+// The same with an L2 eviction-priority hint (data that is streamed exactly once).
+__device__ __forceinline__ uint64_t semk_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void semk_bulk_g2s_hint(void *smem_dst, const void *gmem_src,
+                                                   uint32_t bytes, uint64_t *bar,
+                                                   uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(semk_smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(semk_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 
 // L2 prefetch of one 128-byte line (SASS: CCTL.E.PF2) / of a contiguous block
 // through the TMA engine (SASS: UBLKPF.L2; 16-byte aligned, size % 16 == 0).

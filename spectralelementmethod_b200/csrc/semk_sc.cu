@@ -16,10 +16,10 @@
 //               u_i = L^{-T} (L^{-1} f_i - Z u_e)      (back-substitution).
 //       Set-up / once-per-solve work; the factorisation is recomputed instead
 //       of stored (19 KB per element at p = 8 against 4 KB for S_e).
-//   sc_matvec_kernel<N>   the condensed apply, HBM-bound: streams the packed
-//       S_e blocks (evict-first loads) into shared memory, gathers the 4p
-//       exterior values through the L2G map and forms y_loc = S_e u_e, one
-//       thread per row, fixed summation order.
+//   sc_matvec_kernel<N>   the condensed apply, HBM-bound: persistent CTAs stream the
+//       packed S_e blocks through a double-buffered TMA pipeline (evict-first),
+//       gather the 4p exterior values through the L2G map one group ahead and
+//       form y_loc = S_e u_e, one thread per row, fixed summation order.
 //   sc_node_kernel        every exterior node sums its entries of y_loc in the
 //       fixed order of the node -> entries table (the reference's
 //       `grhs[inds_ext] += ...`, :499, without atomics), applies the Dirichlet
@@ -50,7 +50,6 @@ struct ScCfg {
       3 * NN + NN + NI * LDI + NI * LDZ + NE * NE + NI + NE + NE + NI;
   static constexpr size_t kSmem = sizeof(double) * kDoubles + sizeof(int) * (NE + 4);
   static constexpr int EPB = kScThreads / NE;    // elements per CTA step of the matvec
-  static constexpr size_t kMatvecSmem = sizeof(double) * (size_t)EPB * (NS + NE);
 };
 
 struct ScElemArgs {
@@ -79,7 +78,7 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
   using C = ScCfg<N>;
   constexpr int NN = C::NN, NE = C::NE, NI = C::NI, NS = C::NS, LDI = C::LDI, LDZ = C::LDZ;
   constexpr int M = N - 2;
-  extern __shared__ __align__(16) double sc_smem[];
+  extern __shared__ __align__(128) double sc_smem[];
   double *sG = sc_smem;            // [3][N][N] geometric factors G00, G01, G11
   double *sD = sG + 3 * NN;        // [N][N]
   double *sA = sD + NN;            // [NI][LDI] interior block -> Cholesky factor (lower)
@@ -235,49 +234,91 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
 }
 
 // ---- condensed apply, element part: y_loc = S_e u[l2g_ext] ------------------------------
+// Persistent and double-buffered: while group i (EPB elements) is being multiplied,
+// the TMA engine (cp.async.bulk, evict-first: S is streamed exactly once per apply)
+// fills the other stage with the S blocks of the CTA's next group and every thread has
+// its next u value in flight (index load, then value load); one barrier per group.
+// One thread per row of S_e; entry (r, c), r >= c, of the packed block sits at
+// r (r + 1) / 2 + c, so a half-warp reading one column hits 16 distinct banks
+// (triangular numbers are a permutation mod 16).
 template <int N>
 __global__ void __launch_bounds__(kScThreads)
     sc_matvec_kernel(int64_t n_elem, const double *__restrict__ S,
-                     const uint32_t *__restrict__ l2g_ext, const double *__restrict__ u,
-                     const uint8_t *__restrict__ mask_in, double *__restrict__ y_loc) {
+                         const uint32_t *__restrict__ l2g_ext, const double *__restrict__ u,
+                         const uint8_t *__restrict__ mask_in, double *__restrict__ y_loc) {
   using C = ScCfg<N>;
   constexpr int NE = C::NE, NS = C::NS, EPB = C::EPB;
-  extern __shared__ __align__(16) double sc_smem[];
-  double *sS = sc_smem;            // [EPB][NS]
-  double *sU = sS + EPB * NS;      // [EPB][NE]
+  constexpr int STG = EPB * NS, UST = EPB * NE;
+  extern __shared__ __align__(128) double sc_smem[];
+  double *sS = sc_smem;                                            // [2][EPB][NS]
+  double *sU = sS + 2 * STG;                                       // [2][EPB][NE]
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(sU + 2 * UST);     // [2]
   const int tid = threadIdx.x;
   const int le = tid / NE, k = tid - le * NE;
+  const bool lane_on = le < EPB;
   const int64_t n_groups = (n_elem + EPB - 1) / EPB;
-  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int64_t e0 = grp * EPB;
-    const int ne = (int)((n_elem - e0) < (int64_t)EPB ? (n_elem - e0) : (int64_t)EPB);
-    // the S blocks are read exactly once per apply: streaming loads keep u / y_loc in L2
-    const double2 *src = reinterpret_cast<const double2 *>(S + e0 * NS);
-    double2 *dst = reinterpret_cast<double2 *>(sS);
-    const int n2 = ne * (NS / 2);
-    for (int q = tid; q < n2; q += kScThreads) dst[q] = __ldcs(src + q);
-    const bool on = le < ne;
-    if (on) {
-      const uint32_t g = l2g_ext[(e0 + le) * NE + k];
-      double v = u[g];
+  const uint64_t policy = semk_policy_evict_first();
+  if (tid == 0) {
+    semk_mbar_init(&mbar[0], 1);
+    semk_mbar_init(&mbar[1], 1);
+    semk_fence_mbar_init();
+  }
+  __syncthreads();
+  auto count_of = [&](int64_t grp) -> int {
+    const int64_t left = n_elem - grp * EPB;
+    return (int)(left < (int64_t)EPB ? left : (int64_t)EPB);
+  };
+  auto issue = [&](int64_t grp, int s) {  // thread 0
+    const uint32_t bytes = (uint32_t)(count_of(grp) * NS * sizeof(double));
+    semk_mbar_expect_tx(&mbar[s], bytes);
+    semk_bulk_g2s_hint(sS + s * STG, S + grp * EPB * NS, bytes, &mbar[s], policy);
+  };
+  auto gather = [&](int64_t grp) -> double {
+    double v = 0.0;
+    if (lane_on && le < count_of(grp)) {
+      const uint32_t g = l2g_ext[(grp * EPB + le) * NE + k];
+      v = u[g];
       if (mask_in && mask_in[g]) v = 0.0;
-      sU[le * NE + k] = v;
     }
-    __syncthreads();
-    if (on) {
-      const double *s = sS + le * NS;
-      const double *uu = sU + le * NE;
+    return v;
+  };
+  int64_t grp = blockIdx.x;
+  if (grp >= n_groups) return;
+  if (tid == 0) issue(grp, 0);
+  double unext = gather(grp);
+  if (lane_on) sU[tid] = unext;
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const int s = it & 1;
+    const int64_t nxt = grp + gridDim.x;
+    const bool more = nxt < n_groups;
+    if (more) {
+      if (tid == 0) issue(nxt, s ^ 1);  // stage s^1 was last read before the barrier below
+      unext = gather(nxt);
+    }
+    semk_mbar_wait(&mbar[s], (uint32_t)((it >> 1) & 1));
+    if (lane_on && le < count_of(grp)) {
+      const double *sm = sS + s * STG + le * NS;
+      const double *uu = sU + s * UST + le * NE;
       const int kk = k * (k + 1) / 2;
       double acc = 0.0;
 #pragma unroll
       for (int j = 0; j < NE; ++j) {
         const int idx = (j <= k) ? kk + j : j * (j + 1) / 2 + k;
-        acc = fma(s[idx], uu[j], acc);
+        acc = fma(sm[idx], uu[j], acc);
       }
-      y_loc[(e0 + le) * NE + k] = acc;
+      y_loc[(grp * EPB + le) * NE + k] = acc;
     }
+    if (!more) break;
+    if (lane_on) sU[(s ^ 1) * UST + tid] = unext;
     __syncthreads();
+    grp = nxt;
   }
+}
+
+template <int N>
+constexpr size_t sc_matvec_smem() {
+  return sizeof(double) * (2 * (size_t)ScCfg<N>::EPB * (ScCfg<N>::NS + ScCfg<N>::NE)) + 16;
 }
 
 // ---- condensed apply / assembly, node part ------------------------------------------------
@@ -417,12 +458,25 @@ extern "C" int semk_sc_apply_f64(const semk_sc_op *op, const double *u, double *
   SEMK_REQUIRE(!dot_out || op->partials, "semk_sc_apply_f64: dot_out needs op->partials");
   cudaStream_t st = semk_stream(stream);
   const uint8_t *mask_in = (op->dirichlet && (flags & SEMK_MASK_IN)) ? op->dirichlet : nullptr;
+  int n_sm = 148;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      (void)cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
 #define SEMK_CALL(NV)                                                                      \
   do {                                                                                     \
     const int64_t groups = (op->n_elem + ScCfg<NV>::EPB - 1) / ScCfg<NV>::EPB;             \
-    const unsigned grid = (unsigned)(groups < 148 * 12 ? groups : 148 * 12);               \
-    sc_matvec_kernel<NV><<<grid, kScThreads, ScCfg<NV>::kMatvecSmem, st>>>(                 \
-        op->n_elem, op->S, op->l2g_ext, u, mask_in, op->y_loc);                            \
+    {                                                                                      \
+      int per_sm = 0;                                                                      \
+      SEMK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                       \
+          &per_sm, sc_matvec_kernel<NV>, kScThreads, sc_matvec_smem<NV>()));       \
+      if (per_sm < 1) per_sm = 1;                                                          \
+      const int64_t cap = (int64_t)n_sm * per_sm;                                          \
+      const unsigned grid = (unsigned)(groups < cap ? groups : cap);                       \
+      sc_matvec_kernel<NV><<<grid, kScThreads, sc_matvec_smem<NV>(), st>>>(         \
+          op->n_elem, op->S, op->l2g_ext, u, mask_in, op->y_loc);                          \
+    }                                                                                      \
   } while (0)
   SEMK_DISPATCH_SC(op->n1, SEMK_CALL)
 #undef SEMK_CALL
