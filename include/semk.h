@@ -470,6 +470,20 @@ int semk_sc_pcg_solve_f64(const semk_sc_op *op, const double *b, double *x, cons
                           int maxiter, int check_every, semk_pcg_info *info, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Field evaluation: DOFManager.values_at_nodes
+ * (sem/discrete.py:235-258) -- GLL coefficients -> values at the equispaced
+ * mesh nodes, element by element through TensorProduct.interpolate_on_grid_eq
+ * (sem/basis_functions.py:539-569).  l2g: device uint32 [n_elem][NN];
+ * Emat: device [NN], the 1-D matrix `_interp_eq_mat` (basis functions at the
+ * equispaced points); winner: device uint8 [n_elem][NN], 1 where the element
+ * is the LAST one of the reference's loop containing that node (its value is
+ * the one the reference keeps); coeffs, values: device [n_nodes], distinct.
+ * ------------------------------------------------------------------------ */
+int semk_values_at_nodes_f64(int n1, int64_t n_elem, const uint32_t *l2g, const uint8_t *winner,
+                             const double *Emat, const double *coeffs, double *values,
+                             void *stream);
+
+/* ------------------------------------------------------------------------
  * Multi-GPU: interface exchange of a strip partition over NVLink peer memory
  * (the reference itself is single-process -- its serial
  * analogue is the scatter-add `grhs[inds] += ...`, sem/discrete.py:499).

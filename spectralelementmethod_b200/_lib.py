@@ -132,6 +132,7 @@ SIGNATURES = {
     "semk_sc_assemble_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _D, _P]),
     "semk_sc_pcg_solve_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
                                    C.POINTER(semk_pcg_info), _P]),
+    "semk_values_at_nodes_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
     "semk_peer_open": (_I, [_P, C.POINTER(_P)]),

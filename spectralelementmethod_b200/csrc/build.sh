@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3"
 OBJS=""
-for f in semk_api.cu semk_geom.cu semk_apply.cu semk_vec.cu semk_peer.cu semk_sc.cu; do
+for f in semk_api.cu semk_geom.cu semk_apply.cu semk_vec.cu semk_peer.cu semk_sc.cu semk_field.cu; do
   o="${f%.cu}.o"
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ semk_common.cuh -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
     $NVCC $FLAGS ${SEMK_EXTRA_FLAGS:-} ${SEMK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &

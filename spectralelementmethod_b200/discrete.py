@@ -193,12 +193,50 @@ class DOFManager(object):
 
     def values_at_nodes(self, coeffs):
         """GLL coefficients -> values at the (equispaced) mesh nodes
-        (sem/discrete.py:235-258), all cells at once."""
+        (sem/discrete.py:235-258), all cells at once.  A CUDA tensor (e.g. a
+        solution of ``poisson_operator(...).solve``) is resampled on the device
+        (csrc/semk_field.cu) and a CUDA tensor is returned."""
+        if not isinstance(coeffs, np.ndarray) and hasattr(coeffs, "is_cuda"):
+            return self._values_at_nodes_device(coeffs)
         out = np.empty_like(coeffs)
         for blk in self._mesh._blocks_flushed():
             maps = blk.node_maps
             out[..., maps] = self._basis.interpolate_on_grid_eq(coeffs[..., maps])
         return out
+
+    def _values_at_nodes_device(self, coeffs):
+        import ctypes as C  # noqa: F401
+        import torch
+        from . import _lib, device
+        if not (coeffs.is_cuda and coeffs.dtype == torch.float64
+                and coeffs.shape[-1] == self._mesh.n_nodes):
+            raise ValueError("coeffs must be a float64 CUDA tensor [..., n_nodes]")
+        lib = _lib.load()
+        tab = device.basis_tables(self._basis)
+        NN = tab.n1 * tab.n1
+        cache = getattr(self, "_field_tables", None)
+        if cache is None or cache[0] != coeffs.device:
+            l2g = self.node_map_array().reshape(-1, NN)
+            flat = l2g.ravel()
+            # the reference's loop overwrites shared nodes: the last element containing a
+            # node wins (fancy assignment keeps the last value for repeated indices)
+            last = np.empty(self._mesh.n_nodes, dtype=np.int64)
+            last[flat] = np.arange(flat.size, dtype=np.int64)
+            winner = (last[flat] == np.arange(flat.size, dtype=np.int64)).astype(np.uint8)
+            sub = [b for _, b in self._basis.iter_subbases()][0]
+            cache = (coeffs.device, device.as_i32_bits(l2g, coeffs.device),
+                     torch.from_numpy(winner).to(coeffs.device),
+                     device._f64(np.ascontiguousarray(sub.interp_eq_mat), coeffs.device),
+                     int(l2g.shape[0]))
+            self._field_tables = cache
+        _, l2g_dev, winner_dev, emat_dev, n_elem = cache
+        src = coeffs.contiguous().reshape(-1, coeffs.shape[-1])
+        out = torch.empty_like(src)
+        for i in range(src.shape[0]):
+            _lib.check(lib.semk_values_at_nodes_f64(
+                tab.n1, n_elem, device.ptr(l2g_dev), device.ptr(winner_dev), device.ptr(emat_dev),
+                device.ptr(src[i]), device.ptr(out[i]), device.stream_ptr()))
+        return out.reshape(coeffs.shape)
 
     def get_global_matrix_equation(self):
         raise NotImplementedError()

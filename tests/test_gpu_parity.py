@@ -537,3 +537,55 @@ def test_poisson_example_reproduces_the_reference_solution(tmp_path):
                                        write_msh=str(tmp_path / "plate.msh"))
     key = lambda m: np.lexsort(np.round(m.mesh.nodes, 12))        # noqa: E731
     assert rel_l2(u2[key(m2)], u[key(mngr)]) < 1e-11
+
+
+# --------------------------------------------------------------------------
+# field evaluation
+# --------------------------------------------------------------------------
+def _values_cases():
+    import glob
+    return sorted(os.path.basename(p)[7:-4]
+                  for p in glob.glob(os.path.join(ROOT, "tests", "golden", "values_*.npz")))
+
+
+@pytest.mark.parametrize("name", _values_cases())
+def test_values_at_nodes_device_and_point_interpolation_vs_reference(name):
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "values_%s.npz" % name)))
+    nx, ny, p, sc, rcm, kind = d["meta"].tolist()
+    mesh, mngr = build_package_case(chr(kind), nx, ny, p, bool(sc), bool(rcm))
+    got = mngr.values_at_nodes(dev(d["coeffs"]))
+    assert got.is_cuda and tuple(got.shape) == d["values"].shape
+    assert rel_l2(host(got), d["values"]) < TOL
+    # last-writer-wins on shared nodes: bit-identical to the host mirror's choice of element,
+    # and bit-reproducible
+    assert torch.equal(got, mngr.values_at_nodes(dev(d["coeffs"])))
+    one = mngr.values_at_nodes(dev(d["coeffs"][1]))
+    assert torch.equal(one, got[1])
+    # DOFManager.interpolate (point location + inverse map on the device geometry)
+    mesh._compute_cell_centroids()
+    pts = np.array([mngr.interpolate(d["coeffs"], pt) for pt in d["points"]])
+    assert rel_l2(pts, d["point_values"]) < 1e-10
+    with pytest.raises(ValueError):
+        mngr.values_at_nodes(dev(d["coeffs"][0][:-1]))
+
+
+def test_values_at_nodes_device_at_size_reproduces_polynomials():
+    # a degree-p polynomial in the parametric coordinates of an affine mesh is reproduced
+    # exactly by the GLL -> equispaced resampling: coefficients = values at the GLL points
+    p, n = 8, 64
+    mesh, mngr = build_package_case("S", n, n, p, False, False)
+    N = p + 1
+    b1 = LagrangeGaussLobatto(p)
+    gll = np.asarray(b1.nodes)
+    l2g = mngr.node_map_array().reshape(-1, N, N)
+    x, y = mesh.nodes
+    h = 2.0 / n
+    ex, ey = np.divmod(np.arange(n * n), n)
+    # physical coordinates of the GLL points of every element
+    xg = (-1.0 + h * ex)[:, None, None] + h * (gll[None, :, None] + 1.0) / 2.0 + 0 * gll[None, None, :]
+    yg = (-1.0 + h * ey)[:, None, None] + h * (gll[None, None, :] + 1.0) / 2.0 + 0 * gll[None, :, None]
+    f = lambda a, b: (1.0 + a) ** 3 * (0.5 - b) ** 2 + a * b      # noqa: E731
+    coeffs = np.zeros(mesh.n_nodes)
+    coeffs[l2g] = f(xg, yg)            # continuous: shared nodes get the same value from both sides
+    got = host(mngr.values_at_nodes(dev(coeffs)))
+    assert rel_l2(got, f(x, y)) < 1e-13

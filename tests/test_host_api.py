@@ -291,3 +291,24 @@ def test_condensed_tables_host():
     np.add.at(want, flat, loc)
     got = np.add.reduceat(loc[pos], ptr[:-1].astype(np.int64))
     assert np.allclose(got, want, rtol=0, atol=1e-13)
+
+
+def _values_cases():
+    import glob
+    import os
+    from conftest import GOLDEN
+    return sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "values_*.npz")))
+
+
+@pytest.mark.parametrize("name", _values_cases())
+def test_values_at_nodes_host_vs_reference(name):
+    """DOFManager.values_at_nodes (sem/discrete.py:235-258) against the live
+    reference's output (oracle/make_golden_values.py), two stacked fields."""
+    import os
+    from conftest import GOLDEN, rel_l2
+    d = dict(np.load(os.path.join(GOLDEN, "values_%s.npz" % name)))
+    nx, ny, p, sc, rcm, kind = d["meta"].tolist()
+    mesh, mngr = build_package_case(chr(kind), nx, ny, p, bool(sc), bool(rcm))
+    v = mngr.values_at_nodes(d["coeffs"])
+    assert v.shape == d["values"].shape
+    assert rel_l2(v, d["values"]) < 1e-14
