@@ -467,6 +467,29 @@ def run_engine(args):
             condensed = run_condensed(args, nx, dev, peak)
         except Exception as exc:       # reported, never fatal for the headline line
             condensed = {"error": repr(exc)}
+    if multi and not args.no_condensed and 2 <= ORDER <= 10 and args.pcg_iters > 0:
+        # distributed PCG on the condensed system (every rank must take the same path: the
+        # constructor and the solves are collective, so no try/except here)
+        from spectralelementmethod_b200.distributed import DistributedCondensedPoisson
+        dc = DistributedCondensedPoisson(part, ORDER, args.kind, exchange=args.exchange)
+        bc = dc.lift(dc.rhs(1.0), None)
+
+        def run_c(iters):
+            barrier()
+            t0 = time.perf_counter()
+            xs, it, rel, ok = dc.solve_pcg(bc, rtol=1e-12, maxiter=iters, check_every=50)
+            barrier()
+            return time.perf_counter() - t0, it, rel, ok
+        run_c(50)
+        el0, it0, _, _ = run_c(100)
+        el, it, rel, ok = run_c(200000 if args.pcg_full else 100 + args.pcg_iters)
+        condensed = {"formulation": "static condensation, strip-partitioned, distributed PCG on "
+                                    "the exterior DOFs (%s exchange)" % dc.exchange,
+                     "dof_exterior_per_gpu": dc.sc.n_ext,
+                     "pcg": {"iterations": it, "seconds": el, "converged": ok, "rel_residual": rel,
+                             "ms_per_iteration": (el - el0) / max(it - it0, 1) * 1e3}}
+        if dc.halo is not None:
+            dc.halo.check()
 
     cpu = None
     if rank == 0 and not multi and args.cpu_sample > 0:

@@ -28,7 +28,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["StripPartition", "DistributedOperator", "PeerHalo", "distributed_pcg"]
+__all__ = ["StripPartition", "CondensedStripView", "DistributedOperator", "PeerHalo",
+           "distributed_pcg", "DistributedPoisson", "DistributedCondensedPoisson"]
 
 
 class StripPartition(object):
@@ -103,6 +104,34 @@ class StripPartition(object):
         mesh.add_boundary_cells(cell[:, -1], nbc, 1, 3)
         mesh._structured_shape = (nx, ny)
         return mesh
+
+
+class CondensedStripView(object):
+    """A strip partition seen through the exterior-first numbering of
+    ``DOFManagerSC`` (sem/discrete.py:314-359) on the rank-local mesh: condensed
+    vectors have ``n_ext`` entries, and because the renumbering keeps the
+    exterior nodes in ascending old id, the column shared with the left
+    neighbour is still ids ``[0, NY)`` and the one shared with the right
+    neighbour ids ``[n_ext - NY, n_ext)``, in the same order along the column
+    (every node of an interface column is an element-exterior node).  Exposes
+    the attributes ``DistributedOperator`` / ``PeerHalo`` / ``distributed_pcg``
+    read from a ``StripPartition``."""
+
+    def __init__(self, part, n_ext):
+        self.base = part
+        self.rank, self.world = part.rank, part.world
+        self.left, self.right = part.left, part.right
+        self.NY = part.NY
+        self.n_local = int(n_ext)
+        self.n_owned = self.n_local - (self.NY if self.right is not None else 0)
+
+    @property
+    def left_slice(self):
+        return slice(0, self.NY)
+
+    @property
+    def right_slice(self):
+        return slice(self.n_local - self.NY, self.n_local)
 
 
 class PeerHalo(object):
@@ -410,3 +439,108 @@ class DistributedPoisson(object):
         it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
                                       maxiter=maxiter, check_every=check_every)
         return x, it, rel, ok
+
+
+class DistributedCondensedPoisson(object):
+    """The statically condensed Poisson path (condensed.CondensedPoissonOperator,
+    the reference's DOFManagerSC formulation, sem/discrete.py:404-528) on a strip
+    partition: each rank condenses its own elements (the Schur complements are
+    element-local, so nothing changes there), the condensed apply exchanges the
+    interface columns of the exterior vector exactly like the uncondensed one
+    (``CondensedStripView``), PCG runs on the exterior DOFs of all ranks and the
+    interior back-substitution is rank-local."""
+
+    def __init__(self, part, order, kind="S", group=None, exchange="auto"):
+        from . import discrete, meshgen
+        from .basis_functions import LagrangeGaussLobatto, TensorProductQS
+        from .operators import PCGKernels
+        self.part = part
+        self.group = group
+        self.mesh = part.build_local_mesh(kind)
+        b1 = LagrangeGaussLobatto(order)
+        self.mngr = discrete.DOFManagerSC(self.mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        self.on_ebc = self.mngr.boundary_node_mask("ebc")
+        self.sc = sc = self.mngr.condensed_poisson_operator(dirichlet=self.on_ebc)
+        self.view = CondensedStripView(part, sc.n_ext)
+        # new local id -> lexicographic local id (StripPartition.global_ids() is indexed by those)
+        lex = meshgen.structured_node_maps(part.nx_local, part.ny, part.p).reshape(-1)
+        self.lexicographic_ids = np.empty(self.mesh.n_nodes, dtype=np.int64)
+        self.lexicographic_ids[self.mngr.node_map_array().reshape(-1)] = lex
+        self.kernels = PCGKernels(sc, n=sc.n_ext)
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        self.halo = None
+        if exchange in ("auto", "peer"):
+            err = None
+            try:
+                self.halo = PeerHalo(self.view, group, sc.dev)
+            except Exception as e:          # noqa: BLE001 -- reported below or re-raised
+                err = e
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=sc.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if float(ok) < 1.0:
+                if exchange == "peer":
+                    raise RuntimeError("peer-memory exchange unavailable: %r" % (err,))
+                if self.halo is not None:
+                    self.halo._release()
+                self.halo = None
+        self.exchange = "peer" if self.halo is not None else "nccl"
+        on_ext = self.on_ebc[:sc.n_ext]
+        self.dop = DistributedOperator(
+            self.view, lambda u, out, dot: sc.apply(u, out=out, dot_out=dot),
+            dirichlet=on_ext if sc.has_dirichlet else None, group=group, device=sc.dev,
+            halo=self.halo)
+        self._mask = sc.dirichlet_dev.bool() if sc.has_dirichlet else None
+        self._dinv = None
+
+    def global_ids(self):
+        """Global (lexicographic, whole-mesh) node id of every local node in
+        this rank's exterior-first numbering."""
+        return self.part.global_ids()[self.lexicographic_ids]
+
+    def apply(self, u, out=None, dot_out=None):
+        return self.dop.apply(u, out=out, dot_out=dot_out)
+
+    def diagonal(self):
+        d = self.sc.diagonal(masked=False)
+        self.dop.exchange_add(d)
+        if self._mask is not None:
+            d[self._mask] = 1.0
+        return d
+
+    def rhs(self, f=1.0):
+        return self.dop.exchange_add(self.sc.rhs(f))
+
+    def lift(self, b, g=None):
+        if self._mask is None:
+            return b.clone()
+        gv = torch.zeros_like(b)
+        if g is not None:
+            gv[self._mask] = g[:self.sc.n_ext][self._mask]
+        from ._lib import MASK_OUT
+        t = self.sc.apply(gv, flags=MASK_OUT)
+        self.dop.exchange_add(t)
+        out = b - t
+        out[self._mask] = gv[self._mask]
+        return out
+
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
+        if x0 is None:
+            x = torch.zeros_like(b)
+            if self._mask is not None:
+                x[self._mask] = b[self._mask]
+        else:
+            x = x0.clone()
+        if self._dinv is None:
+            self._dinv = 1.0 / self.diagonal()
+        it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
+                                      maxiter=maxiter, check_every=check_every)
+        return x, it, rel, ok
+
+    def solve(self, f=1.0, dirichlet_values=None, **pcg_kwargs):
+        """Condensed load, lifting, distributed PCG on the exterior DOFs, rank-local
+        interior back-substitution.  Returns (u_local[n_nodes], iterations,
+        rel_residual, converged)."""
+        b = self.lift(self.rhs(f), dirichlet_values)
+        x, it, rel, ok = self.solve_pcg(b, **pcg_kwargs)
+        return self.sc.backsolve(x, f), it, rel, ok

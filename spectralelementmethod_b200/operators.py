@@ -522,10 +522,12 @@ class PCGKernels(object):
     (used by distributed.distributed_pcg, where the loop is driven from Python
     so that NCCL all-reduces can sit between the kernels)."""
 
-    def __init__(self, op):
+    def __init__(self, op, n=None):
         self.op = op
         self._lib = op._lib
-        self.n = op.n_nodes
+        # vector length: the operator's nodal vectors, or the condensed (exterior) vectors of
+        # a CondensedPoissonOperator (same scratch / mask attributes)
+        self.n = op.n_nodes if n is None else int(n)
 
     def init(self, b, Ax, dinv, r, p, sc, n_dot):
         _lib.check(self._lib.semk_pcg_init_f64(

@@ -19,7 +19,8 @@ sys.path.insert(0, ROOT)
 
 from spectralelementmethod_b200 import discrete, meshgen  # noqa: E402
 from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS  # noqa: E402
-from spectralelementmethod_b200.distributed import DistributedPoisson, StripPartition  # noqa: E402
+from spectralelementmethod_b200.distributed import (DistributedCondensedPoisson, DistributedPoisson,  # noqa: E402
+                                                    StripPartition)
 
 
 def main():
@@ -57,10 +58,25 @@ def main():
             dp.halo.close()
     # the two exchange paths add the same two numbers: bit-identical results
     assert torch.equal(results["peer"][0], results["nccl"][0])
+    # statically condensed path: distributed PCG on the exterior DOFs + local back-solve
+    sc_res = {}
+    for exchange in ("peer", "nccl"):
+        dc = DistributedCondensedPoisson(part, p, kind, exchange=exchange)
+        cg = torch.from_numpy(dc.global_ids()).to(dev)
+        xs, it_sc, rel_sc, ok_sc = dc.solve(1.0, None, rtol=1e-12, check_every=10)
+        serr_sc = float((xs - xg[cg]).norm() / xg.norm())
+        assert ok_sc and serr_sc < 1e-9, (ok_sc, serr_sc)
+        sc_res[exchange] = (xs, it_sc, serr_sc)
+        if dc.halo is not None:
+            dc.halo.check()
+            dc.halo.close()
+    assert torch.equal(sc_res["peer"][0], sc_res["nccl"][0])
     if rank == 0:
         err, it, serr = results["peer"][1:]
         print("multigpu_check ok: world=%d apply err %.2e, PCG %d its (single GPU %d), "
               "solution diff %.2e; peer == nccl bitwise" % (world, err, it, info.iterations, serr))
+        print("multigpu_check condensed ok: PCG %d its, solution diff %.2e vs the single-GPU "
+              "uncondensed solve; peer == nccl bitwise" % (sc_res["peer"][1], sc_res["peer"][2]))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -203,3 +203,119 @@ def test_two_rank_pcg_matches_global_direct_solve(two_rank_results):
     for r in two_rank_results:
         assert rel_l2(r["x"], ref["sol"][r["gid"]]) < 1e-11
         assert r["rel"] <= 1e-13
+
+
+# --------------------------------------------------------------------------
+# statically condensed operator on two ranks (CondensedStripView)
+# --------------------------------------------------------------------------
+def _worker_condensed(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, ORACLE_DIR)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sem_oracle as so
+        from spectralelementmethod_b200 import discrete, meshgen
+        from spectralelementmethod_b200.basis_functions import (LagrangeGaussLobatto,
+                                                                TensorProductQS)
+        from spectralelementmethod_b200.distributed import (CondensedStripView,
+                                                            DistributedOperator, StripPartition,
+                                                            distributed_pcg)
+        bounds = (-1.0, -1.0 + 2.0 * world, -1.0, 1.0)
+        part = StripPartition(rank, world, NXL, NY, P, bounds=bounds)
+        mesh = part.build_local_mesh(KIND)
+        b1 = LagrangeGaussLobatto(P)
+        mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        on_full = mngr.boundary_node_mask("ebc")
+        l2g = mngr.node_map_array()
+        lex = meshgen.structured_node_maps(NXL, NY, P).reshape(-1)
+        lex_ids = np.empty(mesh.n_nodes, dtype=np.int64)
+        lex_ids[l2g.reshape(-1)] = lex
+        gid = part.global_ids()[lex_ids]
+        basis = so.Basis(P)
+        geo = so.geometry(basis, mesh.nodes, l2g)
+        c = so.condensed_system(P, geo["invJ"], geo["JxW"], l2g)
+        n_ext = c["n_ext"]
+        view = CondensedStripView(part, n_ext)
+        # interface columns keep their place and order in the exterior-first numbering
+        assert np.array_equal(lex_ids[view.left_slice], np.arange(part.NY))
+        assert np.array_equal(lex_ids[view.right_slice],
+                              np.arange(part.n_local - part.NY, part.n_local))
+        on = on_full[:n_ext]
+        assert not on_full[n_ext:].any()
+        S = c["Sg"]
+        M = (~on).astype(float)
+
+        def local_apply(u, outv, dot):
+            un = u.numpy()
+            y = M * (S @ (M * un)) + (1 - M) * un
+            if outv is None:
+                outv = torch.empty_like(u)
+            outv.copy_(torch.from_numpy(y))
+            if dot is not None:
+                dot[0] = float((M * un) @ (S @ (M * un)) + ((1 - M) * un) @ un)
+            return outv
+
+        dop = DistributedOperator(view, local_apply, dirichlet=on)
+        bl = torch.from_numpy(c["grhs"].copy())
+        dop.exchange_add(bl)
+        dl = torch.from_numpy(S.diagonal().copy())
+        dop.exchange_add(dl)
+        dl[torch.from_numpy(on)] = 1.0
+        x, y = mesh.nodes
+        # Dirichlet data from the (bit-identical across ranks) node coordinates
+        g = np.where(on_full, 0.3 * x - 0.2 * y + 0.1, 0.0)
+        ge = g[:n_ext]
+        t = torch.from_numpy(M * (S @ ge))
+        dop.exchange_add(t)
+        bh = bl - t
+        ont = torch.from_numpy(on)
+        bh[ont] = torch.from_numpy(ge)[ont]
+        x0 = torch.where(ont, bh, torch.zeros_like(bh))
+        it, rel, ok = distributed_pcg(dop, bh, x0, 1.0 / dl, CpuKernels(on), rtol=1e-13,
+                                      maxiter=3000, check_every=7)
+        # rank-local interior back-substitution (sem/discrete.py:513-524)
+        sol = np.zeros(mesh.n_nodes)
+        sol[:n_ext] = x0.numpy()
+        inner = np.linalg.solve(c["Aii"], (c["f_int"] - np.einsum("eij,ej->ei", c["Aie"],
+                                                                  sol[c["ids"]]))[..., None])
+        sol[c["int_ids"]] = inner[..., 0]
+        torch.save(dict(gid=gid, sol=sol, it=it, ok=ok, rel=rel, n_owned=view.n_owned,
+                        n_ext=n_ext, coords=np.asarray(mesh.nodes)),
+                   os.path.join(out, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def two_rank_condensed(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("dist_sc"))
+    world = 2
+    mp.spawn(_worker_condensed, args=(world, _free_port(), out), nprocs=world, join=True)
+    return [torch.load(os.path.join(out, "rank%d.pt" % r), weights_only=False) for r in range(world)]
+
+
+def test_two_rank_condensed_pcg_matches_global_direct_solve(two_rank_condensed):
+    import sem_oracle as so
+    ref = _global_reference()
+    # same problem with the Dirichlet data of the condensed workers
+    world = 2
+    nxg = NXL * world
+    NX, NYn = nxg * P + 1, NY * P + 1
+    X, Y = np.meshgrid(np.linspace(-1.0, -1.0 + 2.0 * world, NX), np.linspace(-1, 1, NYn),
+                       indexing="ij")
+    s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
+    xg, yg = (X + s).ravel(), (Y + s).ravel()
+    vals = np.where(ref["on"], 0.3 * xg - 0.2 * yg + 0.1, 0.0)
+    want = so.solve_direct(ref["A"], ref["b"], ref["on"], vals)
+    its = {r["it"] for r in two_rank_condensed}
+    assert len(its) == 1 and all(r["ok"] for r in two_rank_condensed)
+    total_owned = 0
+    for r in two_rank_condensed:
+        assert np.array_equal(r["coords"][0], xg[r["gid"]])      # the id maps line up
+        assert rel_l2(r["sol"], want[r["gid"]]) < 1e-11
+        total_owned += r["n_owned"]
+    # owned exterior nodes of all ranks = distinct exterior nodes of the global mesh
+    n_int = (NXL * world) * NY * (P - 1) ** 2
+    assert total_owned == ref["n"] - n_int
