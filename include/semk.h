@@ -449,6 +449,19 @@ int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem, con
                         int64_t s_stride, double *sdiag_loc, double *g_loc, double *u,
                         int32_t *bad_flag, void *stream);
 
+/* The same element kernel on the CALLER'S OWN local systems instead of the Poisson
+ * recipe -- the literal inputs of DOFManagerSC.assemble_global_sc_system / solve
+ * (sem/discrete.py:478-528): A_hier device [n_elem][NN][NN] and f_hier device
+ * [n_elem][NN], the dense local matrices / right-hand sides in HIERARCHICAL local
+ * order (reorder_local_system_hier, :428-436: the 4p exterior DOFs first); l2g_hier:
+ * device uint32 [n_elem][NN] = fe.global_dof_ind_hier (:491-492).  The local matrices
+ * must be symmetric with positive definite interior blocks (Cholesky; bad_flag
+ * otherwise); only their lower triangles are read.  Outputs as semk_sc_element_f64. */
+int semk_sc_element_dense_f64(int n1, int64_t n_elem, const double *A_hier, const double *f_hier,
+                              const uint32_t *l2g_hier, int mode, double *S_out, int64_t s_stride,
+                              double *sdiag_loc, double *g_loc, double *u, int32_t *bad_flag,
+                              void *stream);
+
 /* y = S u over the exterior DOFs: per element y_loc = S_e u[l2g_ext] (dense symmetric
  * 4p x 4p product from the packed block), then every exterior node sums its entries of
  * y_loc in the fixed order of node_pos.  flags as semk_poisson_apply_f64 (Dirichlet

@@ -30,7 +30,7 @@ from . import _lib, device
 from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
 from .operators import PCGInfo
 
-__all__ = ["CondensedPoissonOperator"]
+__all__ = ["CondensedPoissonOperator", "CondensedLocalSystems", "condensed_tables"]
 
 
 def condensed_tables(l2g, ext_loc, n_ext):
@@ -58,6 +58,13 @@ def condensed_tables(l2g, ext_loc, n_ext):
 
 class CondensedPoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, weight=None):
+        self._init_common(dof_mngr, dirichlet)
+        self._init_geometry(geometric_factors, weight)
+        self._schur_pass()
+
+    def _init_common(self, dof_mngr, dirichlet):
+        """Masks, local orders, the exterior L2G / node -> entries tables, S and the
+        scratch of the condensed operator (everything but the local systems)."""
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -111,9 +118,15 @@ class CondensedPoissonOperator(object):
             node_pos=device.as_i32_bits(node_pos, self.dev),
         )
         self.l2g_dev = device.as_i32_bits(l2g, self.dev)
+        self._finish_common(full_mask)
 
-        # geometric factors, one plain [3][NN] block per element in reference element order
-        # (the engine layout of semk_op.G with one-element patches)
+    def _init_geometry(self, geometric_factors, weight):
+        """Geometric factors, one plain [3][NN] block per element in reference element
+        order (the engine layout of semk_op.G with one-element patches)."""
+        mesh = self.dof_mngr.mesh
+        n1 = self.n1
+        NN = n1 * n1
+        f64 = dict(dtype=torch.float64, device=self.dev)
         self.g_stride = (3 * NN + 1) & ~1
         self.G = torch.zeros((self.n_elem, self.g_stride), **f64)
         self.JxW = torch.empty((self.n_elem, NN), **f64)
@@ -154,6 +167,9 @@ class CondensedPoissonOperator(object):
             del w
         del x_phys
 
+    def _finish_common(self, full_mask):
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        n1 = self.n1
         self.has_dirichlet = full_mask is not None and bool(full_mask.any())
         self.dirichlet_host = None if full_mask is None else full_mask[:self.n_ext].copy()
         self.dirichlet_dev = (torch.from_numpy(self.dirichlet_host.astype(np.uint8)).to(self.dev)
@@ -177,7 +193,9 @@ class CondensedPoissonOperator(object):
         self._op = op
         self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
 
-        sdiag = torch.empty((self.n_elem, self.n_ext_loc), **f64)
+    def _schur_pass(self):
+        """Local Schur complements (packed, kept) and the assembled diagonal."""
+        sdiag = torch.empty((self.n_elem, self.n_ext_loc), dtype=torch.float64, device=self.dev)
         self._element_pass(_lib.SC_SCHUR, S=self.S, sdiag_loc=sdiag)
         self._diag_unmasked = self.assemble(sdiag)
         del sdiag
@@ -341,3 +359,58 @@ class CondensedPoissonOperator(object):
         b = self.lift(self.rhs(f), dirichlet_values)
         x, info = self.solve_pcg(b, **pcg_kwargs)
         return self.backsolve(x, f), info
+
+
+class CondensedLocalSystems(CondensedPoissonOperator):
+    """Static condensation of the CALLER'S OWN dense local systems: the literal
+    inputs of ``DOFManagerSC.assemble_global_sc_system`` / ``solve``
+    (sem/discrete.py:478-528) -- per element a symmetric local matrix and
+    right-hand side in hierarchical local order (``reorder_local_system_hier``,
+    :428-436) -- condensed, solved (PCG on the exterior DOFs) and back-substituted
+    on the device.  Interior blocks must be positive definite (Cholesky).
+
+        cs = CondensedLocalSystems(dof_mngr, lmats_h[E, NN, NN], lrhs_h[E, NN], dirichlet=on_ebc)
+        u, info = cs.solve(dirichlet_values)
+    """
+
+    def __init__(self, dof_mngr, lmats_h, lrhs_h, dirichlet=None, symmetry_rtol=1e-10):
+        self._init_common(dof_mngr, dirichlet)
+        NN = self.n1 * self.n1
+        lmats_h = np.asarray(lmats_h, dtype=np.float64)
+        lrhs_h = np.asarray(lrhs_h, dtype=np.float64)
+        if lmats_h.shape != (self.n_elem, NN, NN) or lrhs_h.shape != (self.n_elem, NN):
+            raise ValueError("local systems must be [n_cells, NN, NN] matrices and [n_cells, NN] "
+                             "right-hand sides in hierarchical local order")
+        scale = np.abs(lmats_h).max()
+        if np.abs(lmats_h - np.swapaxes(lmats_h, 1, 2)).max() > symmetry_rtol * max(scale, 1e-300):
+            raise NotImplementedError("the device static condensation needs symmetric local "
+                                      "matrices (Cholesky of the interior blocks)")
+        geo = dof_mngr.mesh.get_geometries()[0]
+        hier = np.asarray(geo.hierarchical_node_order, dtype=np.int64)
+        l2g = dof_mngr.mesh.node_map_array().reshape(-1, NN)
+        self._A = device._f64(lmats_h, self.dev)
+        self._f = device._f64(lrhs_h, self.dev)
+        self._l2g_hier = device.as_i32_bits(np.ascontiguousarray(l2g[:, hier]), self.dev)
+        self._schur_pass()
+
+    def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=None):
+        self._bad.zero_()
+        _lib.check(self._lib.semk_sc_element_dense_f64(
+            self.n1, self.n_elem, device.ptr(self._A), device.ptr(self._f),
+            device.ptr(self._l2g_hier), int(mode), device.ptr(S), self.s_stride,
+            device.ptr(sdiag_loc), device.ptr(g_loc), device.ptr(u), device.ptr(self._bad),
+            device.stream_ptr()))
+        if int(self._bad.item()) != 0:
+            raise AssertionError("an element-interior block is not positive definite")
+
+    def rhs(self, f=None):
+        """Condensed load of the caller's local right-hand sides."""
+        return CondensedPoissonOperator.rhs(self, None)
+
+    def backsolve(self, x_ext, f=None, out=None):
+        return CondensedPoissonOperator.backsolve(self, x_ext, None, out)
+
+    def solve(self, dirichlet_values=None, **pcg_kwargs):
+        b = self.lift(self.rhs(), dirichlet_values)
+        x, info = self.solve_pcg(b, **pcg_kwargs)
+        return self.backsolve(x), info

@@ -71,6 +71,11 @@ struct ScElemArgs {
   double *g_loc;
   double *u;
   int32_t *bad_flag;
+  // dense mode (semk_sc_element_dense_f64): the caller's own local systems, hierarchical
+  // local order (exterior DOFs first), instead of the Poisson recipe on G
+  const double *A_dense;       // [n_elem][NN][NN] or nullptr
+  const double *f_dense;       // [n_elem][NN]
+  const uint32_t *l2g_hier;    // [n_elem][NN] global ids in hierarchical local order
 };
 
 template <int N>
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
 
   for (int64_t e = blockIdx.x; e < a.n_elem; e += gridDim.x) {
     __syncthreads();  // the previous element is completely done with shared memory
-    {
+    if (!a.A_dense) {
       const int64_t slot = a.slot_of_elem ? a.slot_of_elem[e] : e;
       const int64_t patch = slot / a.pe;
       const int lp = (int)(slot - patch * a.pe);
@@ -124,10 +129,36 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
       }
       for (int i = tid; i < NN; i += kScThreads) sD[i] = a.D[i];
       for (int i = tid; i < NE; i += kScThreads) sExt[i] = a.ext_loc[i];
-      if (tid == 0) *sBad = 0;
     }
+    if (tid == 0) *sBad = 0;
     __syncthreads();
     // ---- local stiffness blocks --------------------------------------------------
+    if (a.A_dense) {
+      // the caller's local matrix, hierarchical order: rows / columns [0, NE) exterior,
+      // [NE, NN) interior (reorder_local_system_hier, sem/discrete.py:428-436)
+      const double *A = a.A_dense + e * (int64_t)NN * NN;
+      for (int idx = tid; idx < NI * NI; idx += kScThreads) {
+        const int i = idx / NI, j = idx - i * NI;
+        if (j <= i) sA[i * LDI + j] = A[(int64_t)(NE + i) * NN + NE + j];
+      }
+      for (int idx = tid; idx < NI * NE; idx += kScThreads) {
+        const int i = idx / NE, k = idx - i * NE;
+        sZ[i * LDZ + k] = A[(int64_t)(NE + i) * NN + k];
+      }
+      for (int idx = tid; idx < NE * NE; idx += kScThreads) {
+        const int k = idx / NE, l = idx - k * NE;
+        if (l <= k) sE[idx] = A[(int64_t)k * NN + l];
+      }
+      if (need_f) {
+        const double *fh = a.f_dense + e * (int64_t)NN;
+        const uint32_t *row = a.l2g_hier + e * (int64_t)NN;
+        for (int i = tid; i < NI; i += kScThreads) sZ[i * LDZ + NE] = fh[NE + i];
+        for (int k = tid; k < NE; k += kScThreads) {
+          sFe[k] = fh[k];
+          if (a.mode & SEMK_SC_BACKSOLVE) sUe[k] = a.u[row[k]];
+        }
+      }
+    } else {
     for (int idx = tid; idx < NI * NI; idx += kScThreads) {
       const int i = idx / NI, j = idx - i * NI;
       if (j <= i) sA[i * LDI + j] = entry(1 + i / M, 1 + i % M, 1 + j / M, 1 + j % M);
@@ -144,7 +175,8 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
         sE[idx] = entry(x / N, x % N, z / N, z % N);
       }
     }
-    if (need_f) {
+    }
+    if (need_f && !a.A_dense) {
       const double *jw = a.JxW + e * NN;
       const uint32_t *row = a.l2g + e * NN;
       for (int i = tid; i < NI; i += kScThreads) {
@@ -227,8 +259,13 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
         }
       }
       __syncthreads();
-      const uint32_t *row = a.l2g + e * NN;
-      for (int i = tid; i < NI; i += kScThreads) a.u[row[(1 + i / M) * N + 1 + i % M]] = sT[i];
+      if (a.A_dense) {
+        const uint32_t *row = a.l2g_hier + e * (int64_t)NN;
+        for (int i = tid; i < NI; i += kScThreads) a.u[row[NE + i]] = sT[i];
+      } else {
+        const uint32_t *row = a.l2g + e * NN;
+        for (int i = tid; i < NI; i += kScThreads) a.u[row[(1 + i / M) * N + 1 + i % M]] = sT[i];
+      }
     }
   }
 }
@@ -394,6 +431,8 @@ int check_sc_op(const semk_sc_op *op, const char *who) {
       return SEMK_ERR_UNSUPPORTED;                                                   \
   }
 
+static int launch_sc_element(int n1, const ScElemArgs &a, void *stream);
+
 extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem,
                                    const double *G, int64_t g_patch_stride, int elems_per_patch,
                                    const double *D, const int32_t *ext_loc, const uint32_t *l2g,
@@ -435,6 +474,59 @@ extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_o
   a.g_loc = g_loc;
   a.u = u;
   a.bad_flag = bad_flag;
+  a.A_dense = nullptr;
+  a.f_dense = nullptr;
+  a.l2g_hier = nullptr;
+  return launch_sc_element(n1, a, stream);
+}
+
+extern "C" int semk_sc_element_dense_f64(int n1, int64_t n_elem, const double *A_hier,
+                                         const double *f_hier, const uint32_t *l2g_hier, int mode,
+                                         double *S_out, int64_t s_stride, double *sdiag_loc,
+                                         double *g_loc, double *u, int32_t *bad_flag,
+                                         void *stream) {
+  SEMK_REQUIRE(n_elem > 0 && A_hier && bad_flag, "semk_sc_element_dense_f64: bad argument");
+  SEMK_REQUIRE(mode != 0 && (mode & ~7) == 0, "semk_sc_element_dense_f64: bad mode");
+  if (n1 < 3 || n1 > 11) {
+    semk_set_error("semk_sc_element_dense_f64: static condensation supports orders 2..10");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  const int ne = 4 * (n1 - 1);
+  if (mode & SEMK_SC_SCHUR)
+    SEMK_REQUIRE(S_out && s_stride == (int64_t)ne * (ne + 1) / 2,
+                 "semk_sc_element_dense_f64: SCHUR needs S_out and the packed stride");
+  if (mode & SEMK_SC_RHS)
+    SEMK_REQUIRE(g_loc && f_hier, "semk_sc_element_dense_f64: RHS needs g_loc and f_hier");
+  if (mode & SEMK_SC_BACKSOLVE)
+    SEMK_REQUIRE(u && f_hier && l2g_hier,
+                 "semk_sc_element_dense_f64: BACKSOLVE needs u, f_hier, l2g_hier");
+  ScElemArgs a;
+  a.n_elem = n_elem;
+  a.slot_of_elem = nullptr;
+  a.G = nullptr;
+  a.g_patch_stride = 0;
+  a.pe = 1;
+  a.D = nullptr;
+  a.ext_loc = nullptr;
+  a.l2g = nullptr;
+  a.JxW = nullptr;
+  a.f_nodal = nullptr;
+  a.f_scale = 1.0;
+  a.mode = mode;
+  a.S_out = S_out;
+  a.s_stride = s_stride;
+  a.sdiag_loc = sdiag_loc;
+  a.g_loc = g_loc;
+  a.u = u;
+  a.bad_flag = bad_flag;
+  a.A_dense = A_hier;
+  a.f_dense = f_hier;
+  a.l2g_hier = l2g_hier;
+  return launch_sc_element(n1, a, stream);
+}
+
+static int launch_sc_element(int n1, const ScElemArgs &a, void *stream) {
+  const int64_t n_elem = a.n_elem;
   cudaStream_t st = semk_stream(stream);
   const unsigned grid = (unsigned)(n_elem < 148 * 16 ? n_elem : 148 * 16);
 #define SEMK_CALL(NV)                                                                      \

@@ -362,6 +362,34 @@ class DOFManagerSC(DOFManager):
         from .condensed import CondensedPoissonOperator
         return CondensedPoissonOperator(self, dirichlet=dirichlet, **kwargs)
 
+    def solve_device(self, local_systems, dof_vec, on_ebc, rtol=1e-12, maxiter=200000):
+        """``solve`` on the GPU (sem/discrete.py:526-528 with the Schur assembly of
+        :478-500 folded in): takes the same hierarchically ordered
+        ``local_systems`` = iterable of ``(lmat_h, lrhs_h)`` as
+        ``assemble_global_sc_system`` / ``solve``, the same ``on_ebc`` polarity
+        (True = essential-BC DOF, values read from ``dof_vec``) and writes the
+        solution into ``dof_vec`` in place.  The local matrices must be symmetric
+        with positive definite interior blocks; the condensed system is solved by
+        Jacobi-PCG instead of SuperLU.  Returns the PCG info."""
+        if self._dpn != 1:
+            raise NotImplementedError("solve_device supports one DOF per node")
+        from .condensed import CondensedLocalSystems
+        local_systems = list(local_systems)
+        lm = np.stack([np.asarray(ls[0], dtype=np.float64) for ls in local_systems])
+        lr = np.stack([np.asarray(ls[1], dtype=np.float64) for ls in local_systems])
+        on_ebc = np.asarray(on_ebc)
+        if on_ebc.dtype != np.bool_ or on_ebc.shape != (self.ndof_exterior,):
+            raise ValueError("on_ebc must be bool[ndof_exterior]")
+        cs = CondensedLocalSystems(self, lm, lr, dirichlet=on_ebc)
+        vals = np.zeros(self.ndof)
+        vals[:self.ndof_exterior][on_ebc] = np.asarray(dof_vec)[:self.ndof_exterior][on_ebc]
+        u, info = cs.solve(vals, rtol=rtol, maxiter=maxiter)
+        if not info.converged:
+            from ._lib import SolverFailure
+            raise SolverFailure("condensed PCG did not converge: %r" % (info,))
+        dof_vec[...] = u.cpu().numpy()
+        return info
+
     # -- Schur-complement assembly (host; kept for literal drop-in use) ------------
     def init_global_linear_system(self):
         """Empty COO Schur system over the exterior DOFs and a zero RHS
