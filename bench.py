@@ -180,6 +180,32 @@ def cpu_baseline(n_side, kind, target_seconds=10.0):
                       % (n_side, n_side, ORDER, ndof, reps, el, how)}
 
 
+def cpu_solve_baseline(n_side, kind):
+    """The reference's whole solver pipeline on the host, once, on the same bounded
+    sample: dense local stiffness per element, hierarchical reorder, local Schur
+    complements, COO assembly, spsolve and interior back-substitution
+    (DOFManagerSC, sem/discrete.py:404-528; oracle port, vectorised NumPy/SciPy --
+    the reference itself loops over elements in Python)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sem_oracle as so
+    t0 = time.perf_counter()
+    basis = so.Basis(ORDER)
+    nodes, l2g = so.build_case(kind, n_side, n_side, ORDER, True, False)
+    geo = so.geometry(basis, nodes, l2g)
+    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+    t1 = time.perf_counter()
+    on, vals = so.dirichlet_data(nodes, l2g, geo["x_phys"], so.mesh_boundary_faces(n_side, n_side))
+    ext = so.hier_order(ORDER + 1)[:4 * ORDER]
+    n_ext = int(np.unique(l2g.reshape(l2g.shape[0], -1)[:, ext]).size)
+    so.solve_schur(L, geo["JxW"], l2g, n_ext, on, vals)
+    t2 = time.perf_counter()
+    return {"seconds": t2 - t0, "operator_seconds": t1 - t0, "solve_seconds": t2 - t1,
+            "dof": int(nodes.shape[1]), "kind": "port",
+            "sample": "%dx%d elements p=%d: local operators + Schur + spsolve + back-solve "
+                      "(DOFManagerSC path), NumPy/SciPy" % (n_side, n_side, ORDER)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle
     port; the Python reference cannot travel to the GPU box), rank 0 only."""
@@ -500,6 +526,11 @@ def run_engine(args):
     cpu = None
     if rank == 0 and not multi and args.cpu_sample > 0:
         cpu = cpu_baseline(args.cpu_sample, args.kind)
+        if 2 <= ORDER <= 10:
+            try:
+                cpu["solve"] = cpu_solve_baseline(args.cpu_sample, args.kind)
+            except Exception as exc:     # a reported baseline, never fatal
+                cpu["solve"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {
