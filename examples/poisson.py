@@ -11,6 +11,11 @@ the matrix-free device operator and the device-resident Jacobi-PCG.
     du/dn = 0 on "nbc" (right + top)              (examples/poisson.py:125-143, :200)
 
     python examples/poisson.py [--n 64] [--order 8] [--msh file.msh] [--kind S|C]
+                               [--solver matrix-free|condensed]
+
+``--solver condensed`` follows the reference example literally: static
+condensation of the element interiors (DOFManagerSC, sem/discrete.py:404-528),
+solve on the element-exterior DOFs, interior back-substitution -- on the device.
 
 With ``--msh`` the mesh is read from a Gmsh 2.2 binary file with physical
 names "ebc", "nbc" (lines) and a surface (the reference's examples/meshes/
@@ -30,7 +35,8 @@ from spectralelementmethod_b200 import discrete, grid_importers, meshgen  # noqa
 from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS  # noqa: E402
 
 
-def run(n=16, order=8, msh=None, kind="S", write_msh=None, rtol=1e-12, quiet=False):
+def run(n=16, order=8, msh=None, kind="S", write_msh=None, rtol=1e-12, quiet=False,
+        solver="matrix-free"):
     import torch
     t0 = time.perf_counter()
     if msh is None and write_msh is not None:
@@ -53,7 +59,12 @@ def run(n=16, order=8, msh=None, kind="S", write_msh=None, rtol=1e-12, quiet=Fal
     t_setup = time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    op = mngr.poisson_operator(dirichlet=on_ebc)
+    if solver == "condensed":
+        op = mngr.condensed_poisson_operator(dirichlet=on_ebc)
+    elif solver == "matrix-free":
+        op = mngr.poisson_operator(dirichlet=on_ebc)
+    else:
+        raise ValueError("solver must be 'matrix-free' or 'condensed'")
     u, info = op.solve(f=1.0, dirichlet_values=torch.from_numpy(soln).to(op.dev), rtol=rtol)
     torch.cuda.synchronize()
     t_solve = time.perf_counter() - t0
@@ -61,8 +72,8 @@ def run(n=16, order=8, msh=None, kind="S", write_msh=None, rtol=1e-12, quiet=Fal
     if not quiet:
         print("mesh: %d cells of order %d, %d DOF (%d on the essential boundary)"
               % (mesh.n_cells, order, mngr.ndof, int(on_ebc.sum())))
-        print("host set-up %.2f s; operator + PCG %.2f s: %d iterations, relative residual %.2e"
-              % (t_setup, t_solve, info.iterations, info.rel_residual))
+        print("host set-up %.2f s; %s operator + PCG %.2f s: %d iterations, relative residual %.2e"
+              % (t_setup, solver, t_solve, info.iterations, info.rel_residual))
         print("u: min %.6f  max %.6f  mean %.6f" % (u.min(), u.max(), u.mean()))
     return mngr, on_ebc, soln, u, info
 
@@ -75,8 +86,9 @@ def main():
     ap.add_argument("--msh", default=None, help="Gmsh 2.2 binary mesh to read instead")
     ap.add_argument("--write-msh", default=None,
                     help="write the structured mesh to this .msh file and read it back")
+    ap.add_argument("--solver", default="matrix-free", choices=["matrix-free", "condensed"])
     args = ap.parse_args()
-    run(args.n, args.order, args.msh, args.kind, args.write_msh)
+    run(args.n, args.order, args.msh, args.kind, args.write_msh, solver=args.solver)
 
 
 if __name__ == "__main__":

@@ -537,6 +537,14 @@ def test_poisson_example_reproduces_the_reference_solution(tmp_path):
                                        write_msh=str(tmp_path / "plate.msh"))
     key = lambda m: np.lexsort(np.round(m.mesh.nodes, 12))        # noqa: E731
     assert rel_l2(u2[key(m2)], u[key(mngr)]) < 1e-11
+    # the reference example's own formulation (static condensation), from the .msh file too
+    m3, on3, vals3, u3, info3 = ex.run(n=4, order=8, kind="S", rtol=1e-13, quiet=True,
+                                       solver="condensed")
+    assert info3.converged and rel_l2(u3, g["solution"]) < 1e-11
+    assert info3.iterations < info.iterations
+    m4, on4, vals4, u4, info4 = ex.run(n=4, order=8, kind="S", rtol=1e-13, quiet=True,
+                                       write_msh=str(tmp_path / "plate2.msh"), solver="condensed")
+    assert rel_l2(u4[key(m4)], u[key(mngr)]) < 1e-11
 
 
 # --------------------------------------------------------------------------
