@@ -291,7 +291,16 @@ def run_condensed(args, nx, dev, peak):
            "schur_pass_seconds": t_schur,
            "ms_per_apply": t_apply * 1e3, "algorithmic_bytes_per_apply": alg,
            "achieved_GBps": alg / t_apply / 1e9, "frac_of_hbm_peak": alg / t_apply / 1e9 / peak,
-           "gdof_total_per_s": sc.n_nodes / t_apply / 1e9}
+           "gdof_total_per_s": sc.n_nodes / t_apply / 1e9,
+           "kernel": "sc_matvec_kernel<%d> + sc_node_kernel (one condensed apply)" % (ORDER + 1)}
+    # measured DRAM bytes of one condensed apply, from the committed ncu capture of this very
+    # configuration; null for any other workload
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_condensed.json")
+    res["traffic"] = None
+    if sc.n_elem == 1024 * 1024 and ORDER == 8 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        res["traffic"], res["traffic_source"] = tj["dram_bytes_per_apply"], tj["source"]
     if args.pcg_iters > 0 or args.pcg_full:
         b = sc.lift(sc.rhs(1.0), None)
 
