@@ -23,7 +23,7 @@ from . import discrete
 from . import geometry as geo
 
 __all__ = ["FileFormatError", "load_msh", "parse_format", "gmsh_to_lexicographic",
-           "GMSH_LINE_TYPES", "GMSH_QUAD_TYPES"]
+           "GMSH_LINE_TYPES", "GMSH_QUAD_TYPES", "construct_geometry"]
 
 
 class FileFormatError(Exception):
@@ -42,6 +42,15 @@ def _make_geometry(elem_type):
         n = GMSH_QUAD_TYPES[elem_type]
         return geo.Quadrilateral(n, n)
     raise KeyError(elem_type)
+
+
+def _geometry_factory(elem_type):
+    return lambda: _make_geometry(elem_type)
+
+
+# The reference's public table (sem/grid_importers.py:19-42): Gmsh element type ->
+# zero-argument constructor of the matching geometry object.
+construct_geometry = {t: _geometry_factory(t) for t in list(GMSH_LINE_TYPES) + list(GMSH_QUAD_TYPES)}
 
 
 _ORDER_CACHE = {}

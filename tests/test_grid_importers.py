@@ -129,3 +129,15 @@ def test_large_file_is_fast(tmp_path):
     adj = mesh._adj_array
     assert (adj >= 0).sum() == 2 * (nx * (ny - 1) + ny * (nx - 1))
     assert len(_boundary_rows(mesh)) == 2 * (nx + ny)
+
+
+def test_construct_geometry_table_matches_the_reference_keys():
+    """sem/grid_importers.py:19-42: Gmsh element type -> geometry constructor."""
+    from spectralelementmethod_b200 import geometry as geo
+    table = gi.construct_geometry
+    assert sorted(table) == sorted([1, 8, 26, 27, 28, 62, 63, 64, 65, 66,
+                                    3, 10, 36, 37, 38, 47, 48, 49, 50, 51])
+    line = table[27]()
+    quad = table[49]()
+    assert isinstance(line, geo.Line) and line.shape == (5,)
+    assert isinstance(quad, geo.Quadrilateral) and quad.shape == (9, 9)
