@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--pcg-full", action="store_true", help="run PCG to rtol 1e-12")
     ap.add_argument("--condensed-full", action="store_true",
                     help="run only the condensed PCG to rtol 1e-12 (time to solution)")
+    ap.add_argument("--condensed-multi", action="store_true",
+                    help="under torchrun: also time the distributed condensed PCG (capped); "
+                         "opt-in, the default multi-GPU line is the apply + uncondensed PCG only")
     ap.add_argument("--no-condensed", action="store_true",
                     help="skip the statically condensed operator (reported beside the headline)")
     ap.add_argument("--cpu-sample", type=int, default=64,
@@ -505,7 +508,7 @@ def run_engine(args):
             condensed = run_condensed(args, nx, dev, peak)
         except Exception as exc:       # reported, never fatal for the headline line
             condensed = {"error": repr(exc)}
-    if multi and not args.no_condensed and 2 <= ORDER <= 10 and args.pcg_iters > 0:
+    if multi and (args.condensed_full or args.condensed_multi) and 2 <= ORDER <= 10:
         # distributed PCG on the condensed system (every rank must take the same path: the
         # constructor and the solves are collective, so no try/except here)
         from spectralelementmethod_b200.distributed import DistributedCondensedPoisson
