@@ -319,3 +319,18 @@ def test_two_rank_condensed_pcg_matches_global_direct_solve(two_rank_condensed):
     # owned exterior nodes of all ranks = distinct exterior nodes of the global mesh
     n_int = (NXL * world) * NY * (P - 1) ** 2
     assert total_owned == ref["n"] - n_int
+
+
+def test_condensed_strip_view_description():
+    from spectralelementmethod_b200.distributed import CondensedStripView, StripPartition
+    parts = [StripPartition(r, 3, 4, 5, 2) for r in range(3)]
+    NYn = 5 * 2 + 1
+    # exterior nodes of a 4 x 5 strip of order 2: all nodes but one interior node per element
+    n_ext = parts[0].n_local - 4 * 5
+    views = [CondensedStripView(p, n_ext) for p in parts]
+    assert [v.n_local for v in views] == [n_ext] * 3
+    assert [v.n_owned for v in views] == [n_ext - NYn, n_ext - NYn, n_ext]
+    assert views[1].left == 0 and views[1].right == 2 and views[2].right is None
+    assert views[0].left_slice == slice(0, NYn)
+    assert views[0].right_slice == slice(n_ext - NYn, n_ext)
+    assert views[1].NY == NYn and views[1].base is parts[1]

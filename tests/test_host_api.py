@@ -312,3 +312,14 @@ def test_values_at_nodes_host_vs_reference(name):
     v = mngr.values_at_nodes(d["coeffs"])
     assert v.shape == d["values"].shape
     assert rel_l2(v, d["values"]) < 1e-14
+
+
+def test_condensed_tables_reject_a_numbering_that_is_not_exterior_first():
+    from spectralelementmethod_b200.condensed import condensed_tables
+    mesh, mngr = build_package_case("S", 3, 2, 4, False, False)      # plain DOFManager: lexicographic
+    N = 5
+    geo = mesh.get_geometries()[0]
+    l2g = mesh.node_map_array().reshape(-1, N * N)
+    n_ext_true = mesh.n_nodes - 6 * 9
+    with pytest.raises(AssertionError):
+        condensed_tables(l2g, np.asarray(geo.exterior_node_ind), n_ext_true)
