@@ -205,7 +205,6 @@ class DOFManager(object):
         return out
 
     def _values_at_nodes_device(self, coeffs):
-        import ctypes as C  # noqa: F401
         import torch
         from . import _lib, device
         if not (coeffs.is_cuda and coeffs.dtype == torch.float64
