@@ -483,6 +483,55 @@ int semk_sc_pcg_solve_f64(const semk_sc_op *op, const double *b, double *x, cons
                           int maxiter, int check_every, semk_pcg_info *info, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Two-level preconditioner for the condensed system (additive; the reference
+ * solves it directly, sem/discrete.py:511): Jacobi + a vertex coarse space,
+ *     M^{-1} = diag(Shat)^{-1} + P Ac^{-1} P^T,    Ac = P^T Shat P,
+ * P = linear interpolation along element edges from the element vertices
+ * (condensed.coarse_tables).  Ac is kept as 4 x 4 element matrices
+ * Ace = Phi_e^T S_e Phi_e and applied like the fine operator (element product,
+ * then the fixed-order node sum); Ac^{-1} is an inner Jacobi-PCG to a loose
+ * tolerance.  Makes the outer iteration count independent of the mesh size.
+ * ------------------------------------------------------------------------ */
+typedef struct semk_sc_coarse {
+  int64_t n_v;                /* coarse DOFs = distinct element vertices */
+  const double *Ace;          /* [n_elem][16] element coarse matrices, row major */
+  const uint32_t *vert_c;     /* [n_elem][4] compact vertex ids of every element */
+  double *y_loc_c;            /* [n_elem][4] scratch */
+  const uint32_t *vptr;       /* [n_v + 1] CSR offsets into vpos */
+  const uint32_t *vpos;       /* [n_elem * 4] entries (e * 4 + a) of every vertex, ascending */
+  const uint8_t *dirichlet_c; /* [n_v] 1 = vertex on the essential boundary, or NULL */
+  double *partials;           /* [semk_vec_partials_len()] dot scratch, zeroed once */
+  const uint32_t *pv;         /* [n_ext][2] prolongation: the (at most) two vertices of a node */
+  const double *pw;           /* [n_ext][2] ... and their weights (0 = unused) */
+  const uint32_t *rptr;       /* [n_v + 1] restriction = transpose of the above, CSR */
+  const uint32_t *ridx;       /* [nnz] exterior node of every entry */
+  const double *rw;           /* [nnz] weight of every entry */
+} semk_sc_coarse;
+
+/* Ace = Phi_e^T S_e Phi_e for every element; phi: device [n_ext_loc][4], the local
+ * interpolation matrix; rows of Dirichlet nodes and columns of Dirichlet vertices
+ * (op->dirichlet) are zeroed.  Ace_out: device [n_elem][16]. */
+int semk_sc_coarse_elem_f64(const semk_sc_op *op, const double *phi, double *Ace_out,
+                            void *stream);
+/* y = Ac x (identity rows on Dirichlet vertices with the usual flags); dot_out as in
+ * semk_sc_apply_f64.  x, y: device [n_v], distinct. */
+int semk_sc_coarse_apply_f64(int64_t n_elem, const semk_sc_coarse *cs, const double *x, double *y,
+                             int flags, double *dot_out, void *stream);
+/* out[v] = sum of loc[vpos[..]]; loc: device [n_elem][4] (diagonal of Ac, ...). */
+int semk_sc_coarse_assemble_f64(int64_t n_elem, const semk_sc_coarse *cs, const double *loc,
+                                double *out, void *stream);
+/* Two-level PCG on Shat x = b.  dinv / dinv_c: inverse diagonals of Shat / Ac (1 on
+ * Dirichlet rows).  work: device [4 * (n_ext + 32)]; work_c: device [5 * (n_v + 32)];
+ * sc: device [16]; vec_partials as in semk_pcg_solve_f64.  The inner solves stop at
+ * ||r_c|| <= inner_rtol ||b_c|| or inner_maxiter; *inner_total receives the sum of
+ * their iteration counts (may be NULL).  info as semk_pcg_solve_f64. */
+int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const double *b,
+                           double *x, const double *dinv, const double *dinv_c, double *work,
+                           double *work_c, double *sc, double *vec_partials, double rtol,
+                           int maxiter, double inner_rtol, int inner_maxiter,
+                           semk_pcg_info *info, int64_t *inner_total, void *stream);
+
+/* ------------------------------------------------------------------------
  * Field evaluation: DOFManager.values_at_nodes
  * (sem/discrete.py:235-258) -- GLL coefficients -> values at the equispaced
  * mesh nodes, element by element through TensorProduct.interpolate_on_grid_eq

@@ -80,6 +80,15 @@ class semk_sc_op(C.Structure):
 SC_SCHUR, SC_RHS, SC_BACKSOLVE = 1, 2, 4
 
 
+class semk_sc_coarse(C.Structure):
+    _fields_ = [
+        ("n_v", C.c_int64), ("Ace", C.c_void_p), ("vert_c", C.c_void_p), ("y_loc_c", C.c_void_p),
+        ("vptr", C.c_void_p), ("vpos", C.c_void_p), ("dirichlet_c", C.c_void_p),
+        ("partials", C.c_void_p), ("pv", C.c_void_p), ("pw", C.c_void_p), ("rptr", C.c_void_p),
+        ("ridx", C.c_void_p), ("rw", C.c_void_p),
+    ]
+
+
 class semk_stage(C.Structure):
     _fields_ = [("patch_end", C.c_int64), ("chunk_end", C.c_int64), ("rec_end", C.c_int64),
                 ("u_need", C.c_int64), ("y_final", C.c_int64)]
@@ -133,6 +142,12 @@ SIGNATURES = {
     "semk_sc_assemble_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _D, _P]),
     "semk_sc_pcg_solve_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _P, _P, _P, _P, _D, _I, _I,
                                    C.POINTER(semk_pcg_info), _P]),
+    "semk_sc_coarse_elem_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _P]),
+    "semk_sc_coarse_apply_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _I, _P, _P]),
+    "semk_sc_coarse_assemble_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _P]),
+    "semk_sc_pcg2_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse), _P, _P, _P,
+                                    _P, _P, _P, _P, _P, _D, _I, _D, _I,
+                                    C.POINTER(semk_pcg_info), C.POINTER(C.c_int64), _P]),
     "semk_values_at_nodes_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),

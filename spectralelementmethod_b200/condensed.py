@@ -320,9 +320,84 @@ class CondensedPoissonOperator(object):
             self._dinv = 1.0 / self.diagonal(masked=True)
         return self._dinv
 
-    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
-        """Jacobi-PCG on Shat x = b (b already lifted); returns (x, PCGInfo)."""
+    def _build_coarse(self):
+        """Vertex coarse space of the two-level preconditioner (lazy): host tables
+        (coarse_tables), the element coarse matrices Ace = Phi_e^T S_e Phi_e and the
+        inverse diagonal of the coarse operator, all on the device."""
+        if getattr(self, "_coarse", None) is not None:
+            return self._coarse
+        sub = [b for _, b in self.dof_mngr._basis.iter_subbases()][0]
+        node_ptr = self._t["node_ptr"].cpu().numpy().view(np.uint32)
+        node_pos = self._t["node_pos"].cpu().numpy().view(np.uint32)
+        ct = coarse_tables(self.l2g_ext_host, node_ptr, node_pos, self.dirichlet_host,
+                           np.asarray(sub.nodes))
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        n_v = ct["n_v"]
+        t = dict(
+            phi=device._f64(ct["phi"], self.dev),
+            vert_c=device.as_i32_bits(ct["vert_c"], self.dev),
+            vptr=device.as_i32_bits(ct["vptr"], self.dev),
+            vpos=device.as_i32_bits(ct["vpos"], self.dev),
+            pv=device.as_i32_bits(ct["pv"], self.dev),
+            pw=device._f64(ct["pw"], self.dev),
+            rptr=device.as_i32_bits(ct["rptr"], self.dev),
+            ridx=device.as_i32_bits(ct["ridx"], self.dev),
+            rw=device._f64(ct["rw"], self.dev),
+            dirichlet_c=torch.from_numpy(ct["dirichlet_c"].astype(np.uint8)).to(self.dev),
+            Ace=torch.empty((self.n_elem, 16), **f64),
+            y_loc_c=torch.empty((self.n_elem, 4), **f64),
+            partials=torch.zeros(int(self._lib.semk_vec_partials_len(n_v)), **f64),
+        )
+        _lib.check(self._lib.semk_sc_coarse_elem_f64(
+            C.byref(self._op), device.ptr(t["phi"]), device.ptr(t["Ace"]), device.stream_ptr()))
+        cs = _lib.semk_sc_coarse()
+        cs.n_v = n_v
+        cs.Ace = t["Ace"].data_ptr()
+        cs.vert_c = t["vert_c"].data_ptr()
+        cs.y_loc_c = t["y_loc_c"].data_ptr()
+        cs.vptr = t["vptr"].data_ptr()
+        cs.vpos = t["vpos"].data_ptr()
+        cs.dirichlet_c = t["dirichlet_c"].data_ptr() if self.has_dirichlet else None
+        cs.partials = t["partials"].data_ptr()
+        cs.pv = t["pv"].data_ptr()
+        cs.pw = t["pw"].data_ptr()
+        cs.rptr = t["rptr"].data_ptr()
+        cs.ridx = t["ridx"].data_ptr()
+        cs.rw = t["rw"].data_ptr()
+        # diagonal of the coarse operator: assemble Ace[e][a][a]; 1 on Dirichlet vertices
+        dloc = t["Ace"][:, [0, 5, 10, 15]].contiguous()
+        dc = torch.empty(n_v, **f64)
+        _lib.check(self._lib.semk_sc_coarse_assemble_f64(
+            self.n_elem, C.byref(cs), device.ptr(dloc), device.ptr(dc), device.stream_ptr()))
+        if self.has_dirichlet:
+            dc[t["dirichlet_c"].bool()] = 1.0
+        if not bool((dc > 0).all()):
+            raise AssertionError("coarse operator has a non-positive diagonal entry")
+        t["dinv_c"] = 1.0 / dc
+        self._coarse = (cs, t, n_v)
+        return self._coarse
+
+    def coarse_apply(self, xc, out=None, dot_out=None):
+        """y = Ac x on the vertex coarse space (tests / diagnostics)."""
+        cs, t, n_v = self._build_coarse()
+        y = torch.empty(n_v, dtype=torch.float64, device=self.dev) if out is None else out
+        flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
+        _lib.check(self._lib.semk_sc_coarse_apply_f64(
+            self.n_elem, C.byref(cs), device.ptr(xc), device.ptr(y), flags, device.ptr(dot_out),
+            device.stream_ptr()))
+        return y
+
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25,
+                  preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000):
+        """PCG on Shat x = b (b already lifted); returns (x, PCGInfo).
+
+        preconditioner : "jacobi" (diagonal of Shat) or "two-level" (Jacobi + a
+            vertex coarse space, M^-1 = D^-1 + P Ac^-1 P^T with linear interpolation
+            along element edges and an inner Jacobi-PCG on Ac to ``inner_rtol``):
+            the outer iteration count no longer grows with the mesh size."""
         self._vec(b, "b")
+        if preconditioner not in ("jacobi", "two-level"):
+            raise ValueError("preconditioner must be 'jacobi' or 'two-level'")
         if x0 is None:
             x = torch.zeros_like(b)
             if self.has_dirichlet:
@@ -331,9 +406,24 @@ class CondensedPoissonOperator(object):
         else:
             x = self._vec(x0, "x0").clone()
         dinv = self.jacobi_inverse()
+        info = _lib.semk_pcg_info()
+        if preconditioner == "two-level":
+            cs, t, n_v = self._build_coarse()
+            work = torch.empty(4 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
+            work_c = torch.empty(5 * (n_v + 32), dtype=torch.float64, device=self.dev)
+            sc = torch.zeros(16, dtype=torch.float64, device=self.dev)
+            inner = C.c_int64(0)
+            rc = self._lib.semk_sc_pcg2_solve_f64(
+                C.byref(self._op), C.byref(cs), device.ptr(b), device.ptr(x), device.ptr(dinv),
+                device.ptr(t["dinv_c"]), device.ptr(work), device.ptr(work_c), device.ptr(sc),
+                device.ptr(self.vec_partials), float(rtol), int(maxiter), float(inner_rtol),
+                int(inner_maxiter), C.byref(info), C.byref(inner), device.stream_ptr())
+            _lib.check(rc)
+            out = PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
+            self.last_inner_iterations = int(inner.value)
+            return x, out
         work = torch.empty(3 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
         sc = torch.zeros(8, dtype=torch.float64, device=self.dev)
-        info = _lib.semk_pcg_info()
         rc = self._lib.semk_sc_pcg_solve_f64(
             C.byref(self._op), device.ptr(b), device.ptr(x), device.ptr(dinv), device.ptr(work),
             device.ptr(sc), device.ptr(self.vec_partials), float(rtol), int(maxiter),
@@ -414,3 +504,78 @@ class CondensedLocalSystems(CondensedPoissonOperator):
         b = self.lift(self.rhs(), dirichlet_values)
         x, info = self.solve_pcg(b, **pcg_kwargs)
         return self.backsolve(x), info
+
+
+def coarse_tables(l2g_ext, node_ptr, node_pos, dirichlet, gll_nodes):
+    """Host tables of the vertex coarse space of the two-level preconditioner
+    (additive API, no reference equivalent: the reference solves the condensed
+    system directly, sem/discrete.py:511).
+
+    Coarse DOFs = the distinct element vertices (compact index 0..n_v-1).  The
+    prolongation P interpolates LINEARLY ALONG ELEMENT EDGES: an exterior node
+    at GLL position t on an edge gets (1 - t) and t from the edge's two end
+    vertices, a vertex node gets its own coarse value -- at most two weights
+    per row (``pv``, ``pw``), taken from the first element that contains the
+    node.  Rows of Dirichlet nodes and weights on Dirichlet vertices are zero,
+    so the coarse space vanishes on the essential boundary.
+
+    Returns a dict: ``phi[4p, 4]`` (the local interpolation matrix in the
+    hierarchical exterior order), ``vert_c[E, 4]`` compact vertex ids of every
+    element, ``n_v``, ``dirichlet_c[n_v]``, ``pv[n_ext, 2]`` / ``pw[n_ext, 2]``
+    (prolongation), ``rptr / ridx / rw`` (CSR of the transpose: restriction),
+    ``vptr / vpos`` (vertex -> element-local entries ``e * 4 + a``, ascending:
+    assembly order of the coarse operator)."""
+    l2g_ext = np.asarray(l2g_ext)
+    E, NE = l2g_ext.shape
+    p = NE // 4
+    N = p + 1
+    n_ext = int(node_ptr.size - 1)
+    t = (1.0 + np.asarray(gll_nodes, dtype=np.float64)) / 2.0
+    if t.size != N:
+        raise ValueError("gll_nodes must have p + 1 entries")
+    va = np.zeros(NE, dtype=np.int64)
+    vb = np.zeros(NE, dtype=np.int64)
+    wa = np.zeros(NE)
+    wb = np.zeros(NE)
+    va[:4] = vb[:4] = np.arange(4)
+    wa[:4] = 1.0
+    inner = np.arange(1, N - 1)
+    # hierarchical exterior order (sem/geometry.py:151-212): vertices (0,0), (0,N-1), (N-1,0),
+    # (N-1,N-1); then the open edges m = 0, m = N-1 (running along n), n = 0, n = N-1 (along m)
+    for edge, (a, b) in enumerate(((0, 1), (2, 3), (0, 2), (1, 3))):
+        k = 4 + edge * (N - 2) + np.arange(N - 2)
+        va[k], vb[k] = a, b
+        wa[k], wb[k] = 1.0 - t[inner], t[inner]
+    phi = np.zeros((NE, 4))
+    phi[np.arange(NE), va] += wa
+    phi[np.arange(NE), vb] += wb
+    vert = l2g_ext[:, :4].astype(np.int64)
+    vids = np.unique(vert)
+    n_v = int(vids.size)
+    vmap = np.full(n_ext, -1, dtype=np.int64)
+    vmap[vids] = np.arange(n_v)
+    vert_c = vmap[vert]
+    dirichlet = (np.zeros(n_ext, dtype=bool) if dirichlet is None
+                 else np.asarray(dirichlet, dtype=bool)[:n_ext])
+    dirichlet_c = dirichlet[vids]
+    first = node_pos[node_ptr[:-1].astype(np.int64)].astype(np.int64)
+    e, k = np.divmod(first, NE)
+    pv = np.stack([vert_c[e, va[k]], vert_c[e, vb[k]]], axis=1)
+    pw = np.stack([wa[k], wb[k]], axis=1)
+    pw[dirichlet] = 0.0
+    pw[dirichlet_c[pv]] = 0.0
+    flat_v, flat_w = pv.ravel(), pw.ravel()
+    flat_g = np.repeat(np.arange(n_ext, dtype=np.int64), 2)
+    keep = flat_w != 0.0
+    order = np.argsort(flat_v[keep], kind="stable")
+    ridx = flat_g[keep][order].astype(np.uint32)
+    rw = np.ascontiguousarray(flat_w[keep][order])
+    rptr = np.zeros(n_v + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(flat_v[keep], minlength=n_v), out=rptr[1:])
+    vflat = vert_c.ravel()
+    vpos = np.argsort(vflat, kind="stable").astype(np.uint32)
+    vptr = np.zeros(n_v + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(vflat, minlength=n_v), out=vptr[1:])
+    return dict(phi=phi, vert_c=vert_c.astype(np.uint32), n_v=n_v, dirichlet_c=dirichlet_c,
+                pv=pv.astype(np.uint32), pw=np.ascontiguousarray(pw), rptr=rptr, ridx=ridx, rw=rw,
+                vptr=vptr, vpos=vpos)

@@ -358,6 +358,94 @@ constexpr size_t sc_matvec_smem() {
   return sizeof(double) * (2 * (size_t)ScCfg<N>::EPB * (ScCfg<N>::NS + ScCfg<N>::NE)) + 16;
 }
 
+// ---- vertex coarse space of the two-level preconditioner ----------------------------------
+// Ace = Phi_e^T S_e Phi_e, Phi_e = diag(free nodes) phi diag(free vertices).
+template <int N>
+__global__ void __launch_bounds__(kScThreads)
+    sc_coarse_elem_kernel(int64_t n_elem, const double *__restrict__ S,
+                          const uint32_t *__restrict__ l2g_ext,
+                          const uint8_t *__restrict__ dirichlet, const double *__restrict__ phi,
+                          double *__restrict__ Ace) {
+  using C = ScCfg<N>;
+  constexpr int NE = C::NE, NS = C::NS, EPB = C::EPB;
+  extern __shared__ __align__(128) double sc_smem[];
+  double *sS = sc_smem;                 // [EPB][NS]
+  double *sP0 = sS + EPB * NS;          // [NE][4] phi
+  double *sPhi = sP0 + NE * 4;          // [EPB][NE][4] masked Phi_e
+  double *sT = sPhi + EPB * NE * 4;     // [EPB][NE][4] S_e Phi_e
+  const int tid = threadIdx.x;
+  const int le = tid / NE, k = tid - le * NE;
+  for (int i = tid; i < NE * 4; i += kScThreads) sP0[i] = phi[i];
+  const int64_t n_groups = (n_elem + EPB - 1) / EPB;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    __syncthreads();
+    const int64_t e0 = grp * EPB;
+    const int ne = (int)((n_elem - e0) < (int64_t)EPB ? (n_elem - e0) : (int64_t)EPB);
+    const double2 *src = reinterpret_cast<const double2 *>(S + e0 * NS);
+    double2 *dst = reinterpret_cast<double2 *>(sS);
+    for (int q = tid; q < ne * (NS / 2); q += kScThreads) dst[q] = src[q];
+    const bool on = le < ne;
+    if (on) {
+      const uint32_t *ids = l2g_ext + (e0 + le) * NE;
+      const double fn = (dirichlet && dirichlet[ids[k]]) ? 0.0 : 1.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double fv = (dirichlet && dirichlet[ids[c]]) ? 0.0 : 1.0;  // vertices: k = 0..3
+        sPhi[(le * NE + k) * 4 + c] = sP0[k * 4 + c] * fn * fv;
+      }
+    }
+    __syncthreads();
+    if (on) {
+      const double *s = sS + le * NS;
+      const double *ph = sPhi + le * NE * 4;
+      const int kk = k * (k + 1) / 2;
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        const double sv = s[(j <= k) ? kk + j : j * (j + 1) / 2 + k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[c] = fma(sv, ph[j * 4 + c], t[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sT[(le * NE + k) * 4 + c] = t[c];
+    }
+    __syncthreads();
+    for (int q = tid; q < ne * 16; q += kScThreads) {
+      const int l2 = q >> 4, a = (q >> 2) & 3, c = q & 3;
+      const double *ph = sPhi + l2 * NE * 4;
+      const double *tt = sT + l2 * NE * 4;
+      double acc = 0.0;
+      for (int j = 0; j < NE; ++j) acc = fma(ph[j * 4 + a], tt[j * 4 + c], acc);
+      Ace[(e0 + l2) * 16 + a * 4 + c] = acc;
+    }
+  }
+}
+
+template <int N>
+constexpr size_t sc_coarse_elem_smem() {
+  return sizeof(double) * ((size_t)ScCfg<N>::EPB * ScCfg<N>::NS + (size_t)ScCfg<N>::NE * 4 +
+                           2 * (size_t)ScCfg<N>::EPB * ScCfg<N>::NE * 4);
+}
+
+// element part of the coarse apply: y_loc_c[e][a] = sum_c Ace[e][a][c] x[vert_c[e][c]]
+__global__ void __launch_bounds__(256)
+    sc_coarse_matvec_kernel(int64_t n_elem, const double *__restrict__ Ace,
+                            const uint32_t *__restrict__ vert_c, const double *__restrict__ x,
+                            double *__restrict__ y_loc_c) {
+  const int64_t total = n_elem * 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i >> 2;
+    const double *A = Ace + e * 16 + (i & 3) * 4;
+    const uint32_t *v = vert_c + e * 4;
+    double acc = A[0] * x[v[0]];
+    acc = fma(A[1], x[v[1]], acc);
+    acc = fma(A[2], x[v[2]], acc);
+    acc = fma(A[3], x[v[3]], acc);
+    y_loc_c[i] = acc;
+  }
+}
+
 // ---- condensed apply / assembly, node part ------------------------------------------------
 constexpr int kNodeThreads = 256;
 
@@ -588,6 +676,63 @@ extern "C" int semk_sc_assemble_f64(const semk_sc_op *op, const double *loc, dou
   sc_node_kernel<<<node_blocks(op->n_ext), kNodeThreads, 0, semk_stream(stream)>>>(
       op->n_ext, op->node_ptr, op->node_pos, loc, op->dirichlet, nullptr, out,
       flags & SEMK_MASK_OUT, fill_dirichlet, nullptr, nullptr);
+  SEMK_LAUNCH_CHECK("sc_node_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_coarse_elem_f64(const semk_sc_op *op, const double *phi, double *Ace_out,
+                                       void *stream) {
+  int rc = check_sc_op(op, "semk_sc_coarse_elem_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(phi && Ace_out, "semk_sc_coarse_elem_f64: null pointer");
+  cudaStream_t st = semk_stream(stream);
+#define SEMK_CALL(NV)                                                                      \
+  do {                                                                                     \
+    const int64_t groups = (op->n_elem + ScCfg<NV>::EPB - 1) / ScCfg<NV>::EPB;             \
+    const unsigned grid = (unsigned)(groups < 148 * 8 ? groups : 148 * 8);                 \
+    sc_coarse_elem_kernel<NV><<<grid, kScThreads, sc_coarse_elem_smem<NV>(), st>>>(        \
+        op->n_elem, op->S, op->l2g_ext, op->dirichlet, phi, Ace_out);                      \
+  } while (0)
+  SEMK_DISPATCH_SC(op->n1, SEMK_CALL)
+#undef SEMK_CALL
+  SEMK_LAUNCH_CHECK("sc_coarse_elem_kernel");
+  return SEMK_OK;
+}
+
+static int check_coarse(int64_t n_elem, const semk_sc_coarse *cs, const char *who) {
+  if (!cs || n_elem <= 0 || cs->n_v <= 0 || !cs->Ace || !cs->vert_c || !cs->y_loc_c || !cs->vptr ||
+      !cs->vpos) {
+    semk_set_error(std::string(who) + ": inconsistent semk_sc_coarse");
+    return SEMK_ERR_INVALID;
+  }
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_coarse_apply_f64(int64_t n_elem, const semk_sc_coarse *cs, const double *x,
+                                        double *y, int flags, double *dot_out, void *stream) {
+  int rc = check_coarse(n_elem, cs, "semk_sc_coarse_apply_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(x && y && x != y, "semk_sc_coarse_apply_f64: null / aliased vectors");
+  SEMK_REQUIRE(!dot_out || cs->partials, "semk_sc_coarse_apply_f64: dot_out needs partials");
+  cudaStream_t st = semk_stream(stream);
+  const int64_t want = (n_elem * 4 + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  sc_coarse_matvec_kernel<<<grid, 256, 0, st>>>(n_elem, cs->Ace, cs->vert_c, x, cs->y_loc_c);
+  SEMK_LAUNCH_CHECK("sc_coarse_matvec_kernel");
+  sc_node_kernel<<<node_blocks(cs->n_v), kNodeThreads, 0, st>>>(
+      cs->n_v, cs->vptr, cs->vpos, cs->y_loc_c, cs->dirichlet_c, x, y, flags, 0.0, cs->partials,
+      dot_out);
+  SEMK_LAUNCH_CHECK("sc_node_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_coarse_assemble_f64(int64_t n_elem, const semk_sc_coarse *cs,
+                                           const double *loc, double *out, void *stream) {
+  int rc = check_coarse(n_elem, cs, "semk_sc_coarse_assemble_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(loc && out, "semk_sc_coarse_assemble_f64: null pointer");
+  sc_node_kernel<<<node_blocks(cs->n_v), kNodeThreads, 0, semk_stream(stream)>>>(
+      cs->n_v, cs->vptr, cs->vpos, loc, nullptr, nullptr, out, 0, 0.0, nullptr, nullptr);
   SEMK_LAUNCH_CHECK("sc_node_kernel");
   return SEMK_OK;
 }

@@ -471,3 +471,188 @@ extern "C" int semk_sc_pcg_solve_f64(const semk_sc_op *op, const double *b, doub
   return pcg_solve_impl(apply, op->n_ext, op->dirichlet, b, x, dinv, work, sc, vec_partials,
                         rtol, maxiter, check_every, info, st);
 }
+
+// ---------------------------------------------------------------------------------------
+// Two-level PCG on the condensed system: Jacobi + vertex coarse space (include/semk.h).
+// The outer loop is driven from the host (a few tens of iterations, each containing an
+// inner coarse solve that polls the device anyway); its scalars come back through
+// 8-byte copies.  Inner solves reuse pcg_solve_impl on the coarse operator.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(kVecThreads)
+    resid_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ Ax,
+                 const uint8_t *__restrict__ dirichlet, double *__restrict__ r,
+                 double *__restrict__ bm) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool fixed = dirichlet && dirichlet[i];
+    const double bi = fixed ? 0.0 : b[i];
+    bm[i] = bi;
+    r[i] = fixed ? 0.0 : bi - Ax[i];
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+    scale_kernel(int64_t n, const double *__restrict__ d, const double *__restrict__ r,
+                 double *__restrict__ z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = d[i] * r[i];
+}
+
+// rc = P^T r: one thread per coarse row, fixed summation order
+__global__ void __launch_bounds__(kVecThreads)
+    restrict_kernel(int64_t n_v, const uint32_t *__restrict__ rptr,
+                    const uint32_t *__restrict__ ridx, const double *__restrict__ rw,
+                    const double *__restrict__ r, double *__restrict__ rc) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_v;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (uint32_t q = rptr[v]; q < rptr[v + 1]; ++q) s = fma(rw[q], r[ridx[q]], s);
+    rc[v] = s;
+  }
+}
+
+// z += P xc
+__global__ void __launch_bounds__(kVecThreads)
+    prolong_add_kernel(int64_t n, const uint32_t *__restrict__ pv, const double *__restrict__ pw,
+                       const double *__restrict__ xc, double *__restrict__ z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double wa = pw[2 * i], wb = pw[2 * i + 1];
+    double acc = z[i];
+    if (wa != 0.0) acc = fma(wa, xc[pv[2 * i]], acc);
+    if (wb != 0.0) acc = fma(wb, xc[pv[2 * i + 1]], acc);
+    z[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+    axpy2_kernel(int64_t n, double alpha, const double *__restrict__ p,
+                 const double *__restrict__ Ap, double *__restrict__ x, double *__restrict__ r) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    r[i] = fma(-alpha, Ap[i], r[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+    xpay_kernel(int64_t n, double beta, const double *__restrict__ z, double *__restrict__ p) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+}
+
+}  // namespace
+
+extern "C" int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs,
+                                      const double *b, double *x, const double *dinv,
+                                      const double *dinv_c, double *work, double *work_c,
+                                      double *sc, double *vec_partials, double rtol, int maxiter,
+                                      double inner_rtol, int inner_maxiter, semk_pcg_info *info,
+                                      int64_t *inner_total, void *stream) {
+  SEMK_REQUIRE(op && cs && b && x && dinv && dinv_c && work && work_c && sc && vec_partials && info,
+               "semk_sc_pcg2_solve_f64: null pointer");
+  SEMK_REQUIRE(maxiter >= 0 && inner_maxiter >= 1 && rtol >= 0.0 && inner_rtol > 0.0,
+               "semk_sc_pcg2_solve_f64: bad control");
+  SEMK_REQUIRE(cs->pv && cs->pw && cs->rptr && cs->ridx && cs->rw,
+               "semk_sc_pcg2_solve_f64: missing transfer tables");
+  cudaStream_t st = semk_stream(stream);
+  const int64_t n = op->n_ext, nv = cs->n_v, n_elem = op->n_elem;
+  const int64_t n_pad = (n + 31) & ~(int64_t)31, nv_pad = (nv + 31) & ~(int64_t)31;
+  double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad, *z = work + 3 * n_pad;
+  double *rc = work_c, *xc = work_c + nv_pad, *inner_work = work_c + 2 * nv_pad;
+  double *d_out = sc + 8;  // device scalars of the outer loop; sc[0..8) belong to the inner solves
+  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
+  const dim3 g(vec_blocks(n)), gc(vec_blocks(nv)), blk(kVecThreads);
+  int64_t inner_sum = 0;
+
+  auto fetch = [&](double *host_val) -> int {
+    SEMK_CUDA_CHECK(cudaMemcpyAsync(host_val, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SEMK_OK;
+  };
+  auto dot = [&](const double *a, const double *c, double *host_val) -> int {
+    int e = semk_dot_f64(n, a, c, d_out, vec_partials, st);
+    if (e != SEMK_OK) return e;
+    return fetch(host_val);
+  };
+  auto coarse_apply = [&](const double *in, double *out, double *dptr) -> int {
+    return semk_sc_coarse_apply_f64(n_elem, cs, in, out, flags, dptr, st);
+  };
+  // z = M^{-1} r = dinv r + P Ac^{-1} P^T r
+  auto precondition = [&]() -> int {
+    scale_kernel<<<g, blk, 0, st>>>(n, dinv, r, z);
+    SEMK_LAUNCH_CHECK("scale_kernel");
+    restrict_kernel<<<gc, blk, 0, st>>>(nv, cs->rptr, cs->ridx, cs->rw, r, rc);
+    SEMK_LAUNCH_CHECK("restrict_kernel");
+    SEMK_CUDA_CHECK(cudaMemsetAsync(xc, 0, sizeof(double) * nv, st));
+    semk_pcg_info ii;
+    int e = pcg_solve_impl(coarse_apply, nv, cs->dirichlet_c, rc, xc, dinv_c, inner_work, sc,
+                           vec_partials, inner_rtol, inner_maxiter, 50, &ii, st);
+    if (e != SEMK_OK) return e;
+    inner_sum += ii.iterations;
+    prolong_add_kernel<<<g, blk, 0, st>>>(n, cs->pv, cs->pw, xc, z);
+    SEMK_LAUNCH_CHECK("prolong_add_kernel");
+    return SEMK_OK;
+  };
+
+  int rcode = semk_sc_apply_f64(op, x, Ap, flags, nullptr, st);
+  if (rcode != SEMK_OK) return rcode;
+  resid_kernel<<<g, blk, 0, st>>>(n, b, Ap, op->dirichlet, r, z);  // z = masked b for ||b||
+  SEMK_LAUNCH_CHECK("resid_kernel");
+  double bb = 0.0, rr = 0.0, rz = 0.0;
+  if ((rcode = dot(z, z, &bb)) != SEMK_OK) return rcode;
+  if ((rcode = dot(r, r, &rr)) != SEMK_OK) return rcode;
+  const double tol2 = rtol * rtol;
+  info->bnorm = sqrt(bb);
+  info->iterations = 0;
+  info->status = 0;
+  if (inner_total) *inner_total = 0;
+  if (bb == 0.0 || rr <= tol2 * bb) {
+    info->rel_residual = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    return SEMK_OK;
+  }
+  if ((rcode = precondition()) != SEMK_OK) return rcode;
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  if ((rcode = dot(r, z, &rz)) != SEMK_OK) return rcode;
+  int status = 1, it = 0;
+  while (it < maxiter) {
+    rcode = semk_sc_apply_f64(op, p, Ap, flags, d_out, st);
+    if (rcode != SEMK_OK) return rcode;
+    double pAp = 0.0;
+    if ((rcode = fetch(&pAp)) != SEMK_OK) return rcode;
+    if (!(pAp > 0.0) || !(rz == rz)) {
+      status = SEMK_ERR_BREAKDOWN;
+      break;
+    }
+    const double alpha = rz / pAp;
+    axpy2_kernel<<<g, blk, 0, st>>>(n, alpha, p, Ap, x, r);
+    SEMK_LAUNCH_CHECK("axpy2_kernel");
+    ++it;
+    if ((rcode = dot(r, r, &rr)) != SEMK_OK) return rcode;
+    if (rr <= tol2 * bb) {
+      status = 0;
+      break;
+    }
+    if ((rcode = precondition()) != SEMK_OK) return rcode;
+    double rz_new = 0.0;
+    if ((rcode = dot(r, z, &rz_new)) != SEMK_OK) return rcode;
+    const double beta = rz_new / rz;
+    xpay_kernel<<<g, blk, 0, st>>>(n, beta, z, p);
+    SEMK_LAUNCH_CHECK("xpay_kernel");
+    rz = rz_new;
+  }
+  SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
+  info->iterations = it;
+  info->status = status;
+  info->rel_residual = sqrt(rr / bb);
+  if (inner_total) *inner_total = inner_sum;
+  if (status == SEMK_ERR_BREAKDOWN) {
+    semk_set_error("semk_sc_pcg2_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
+    return SEMK_ERR_BREAKDOWN;
+  }
+  return SEMK_OK;
+}

@@ -50,6 +50,9 @@ def test_struct_layout_matches_header(tmp_path):
     sc_fields = [f[0] for f in _lib.semk_sc_op._fields_]
     src += ['  printf("%zu\\n", sizeof(struct semk_sc_op));']
     src += ['  printf("%%zu\\n", offsetof(struct semk_sc_op, %s));' % f for f in sc_fields]
+    co_fields = [f[0] for f in _lib.semk_sc_coarse._fields_]
+    src += ['  printf("%zu\\n", sizeof(struct semk_sc_coarse));']
+    src += ['  printf("%%zu\\n", offsetof(struct semk_sc_coarse, %s));' % f for f in co_fields]
     src += ['  return 0; }']
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -65,6 +68,10 @@ def test_struct_layout_matches_header(tmp_path):
     assert int(rest[0]) == ctypes.sizeof(_lib.semk_sc_op)
     for f, off in zip(sc_fields, rest[1:]):
         assert getattr(_lib.semk_sc_op, f).offset == int(off), f
+    rest = rest[1 + len(sc_fields):]
+    assert int(rest[0]) == ctypes.sizeof(_lib.semk_sc_coarse)
+    for f, off in zip(co_fields, rest[1:]):
+        assert getattr(_lib.semk_sc_coarse, f).offset == int(off), f
 
 
 def _plan(nx, ny, p, pe, order=None, dirichlet=None):

@@ -1,0 +1,143 @@
+"""Host tables of the two-level preconditioner (condensed.coarse_tables) and a NumPy
+emulation of the device algorithm on the same tables: Jacobi + vertex coarse space on
+the condensed system (csrc/semk_sc.cu coarse kernels, semk_sc_pcg2_solve_f64)."""
+import numpy as np
+import pytest
+
+import sem_oracle as so
+from conftest import load_case, rel_l2
+from spectralelementmethod_b200.condensed import coarse_tables, condensed_tables
+
+
+def _pcg(apply, b, M, rtol, x0=None, maxiter=100000):
+    x = np.zeros_like(b) if x0 is None else x0.copy()
+    r = b - apply(x)
+    z = M(r)
+    p = z.copy()
+    rz, bb, it = r @ z, b @ b, 0
+    while it < maxiter and r @ r > rtol * rtol * bb:
+        Ap = apply(p)
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        z = M(r)
+        rzn = r @ z
+        p = z + (rzn / rz) * p
+        rz = rzn
+        it += 1
+    return x, it
+
+
+def emulate(p, c, on, vals, gll):
+    """The device algorithm in NumPy on the product's host tables; returns
+    (x_jacobi, its_jacobi, x_two_level, its_two_level, tables, Ace)."""
+    N, NE = p + 1, 4 * p
+    n_ext = c["n_ext"]
+    ids, S_e = c["ids"], c["S"]
+    E = ids.shape[0]
+    l2g_ext, nptr, npos = condensed_tables(
+        np.pad(ids, ((0, 0), (0, N * N - NE))).astype(np.uint32), np.arange(NE), n_ext)
+    assert np.array_equal(l2g_ext.astype(np.int64), ids)
+    nptr = nptr.astype(np.int64)
+    D = on[:n_ext]
+    ct = coarse_tables(l2g_ext, nptr, npos, D, gll)
+
+    def fine(u):
+        yl = np.einsum("ekj,ej->ek", S_e, np.where(D, 0.0, u)[ids]).ravel()
+        return np.where(D, u, np.add.reduceat(yl[npos], nptr[:-1]))
+    vc = ct["vert_c"].astype(np.int64)
+    Dc = ct["dirichlet_c"]
+    Phi = ct["phi"][None] * (~D)[ids][:, :, None] * (~Dc)[vc][:, None, :]
+    Ace = np.einsum("eka,ekj,ejc->eac", Phi, S_e, Phi)
+    vptr, vpos = ct["vptr"].astype(np.int64), ct["vpos"].astype(np.int64)
+
+    def coarse(xc):
+        yl = np.einsum("eac,ec->ea", Ace, xc[vc]).ravel()
+        return np.where(Dc, xc, np.add.reduceat(yl[vpos], vptr[:-1]))
+    dc = np.where(Dc, 1.0, np.add.reduceat(np.einsum("eaa->ea", Ace).ravel()[vpos], vptr[:-1]))
+    pv, pw = ct["pv"].astype(np.int64), ct["pw"]
+    rptr, ridx, rw = ct["rptr"].astype(np.int64), ct["ridx"].astype(np.int64), ct["rw"]
+
+    def restrict(r):
+        out = np.zeros(ct["n_v"])
+        nz = rptr[1:] > rptr[:-1]
+        out[nz] = np.add.reduceat(rw * r[ridx], rptr[:-1][nz])
+        return out
+
+    def prolong(xc):
+        return pw[:, 0] * xc[pv[:, 0]] + pw[:, 1] * xc[pv[:, 1]]
+    sdiag = np.add.reduceat(np.einsum("ekk->ek", S_e).ravel()[npos], nptr[:-1])
+    dinv = 1.0 / np.where(D, 1.0, sdiag)
+
+    def two_level(r):
+        xc, _ = _pcg(coarse, restrict(r), lambda q: q / dc, 1e-2)
+        return dinv * r + prolong(xc)
+    gv = np.where(D, vals[:n_ext], 0.0)
+    yl = np.einsum("ekj,ej->ek", S_e, gv[ids]).ravel()
+    b = c["grhs"] - np.where(D, 0.0, np.add.reduceat(yl[npos], nptr[:-1]))
+    b[D] = gv[D]
+    x0 = np.where(D, b, 0.0)
+    xj, itj = _pcg(fine, b, lambda r: dinv * r, 1e-12, x0)
+    x2, it2 = _pcg(fine, b, two_level, 1e-12, x0)
+    return xj, itj, x2, it2, ct, Ace, (restrict, prolong)
+
+
+def test_coarse_tables_structure_and_transpose():
+    g = load_case("C448_sc_rcm")
+    p = int(g["p"])
+    c = so.condensed_system(p, g["invJ"], g["JxW"], g["l2g"])
+    xj, itj, x2, it2, ct, Ace, (restrict, prolong) = emulate(
+        p, c, g["on_ebc"], g["ebc_vals"], so.Basis(p).nodes)
+    n_ext, n_v = c["n_ext"], ct["n_v"]
+    assert n_v == (g["nx"] + 1) * (g["ny"] + 1)
+    assert ct["phi"].shape == (4 * p, 4) and np.allclose(ct["phi"].sum(axis=1), 1.0)
+    assert ct["pv"].shape == (n_ext, 2) and ct["pw"].shape == (n_ext, 2)
+    D = g["on_ebc"][:n_ext]
+    assert not ct["pw"][D].any()                          # Dirichlet rows are empty
+    assert not ct["pw"][ct["dirichlet_c"][ct["pv"].astype(int)]].any()
+    free_rows = ~D
+    full = ct["pw"].sum(axis=1)[free_rows]
+    assert (full <= 1.0 + 1e-15).all() and (full > 0).any()
+    rng = np.random.default_rng(0)
+    r, xc = rng.standard_normal(n_ext), rng.standard_normal(n_v)
+    assert abs(restrict(r) @ xc - r @ prolong(xc)) < 1e-12 * np.linalg.norm(r) * np.linalg.norm(xc)
+    assert np.allclose(Ace, np.swapaxes(Ace, 1, 2), rtol=0, atol=1e-12)
+    # both preconditioners reach the reference's solution; the coarse space cuts the iterations
+    assert rel_l2(x2, g["solution"][:n_ext]) < 1e-11 and rel_l2(xj, g["solution"][:n_ext]) < 1e-11
+    assert it2 < itj
+
+
+@pytest.mark.parametrize("n,limit", [(8, 40), (16, 40)])
+def test_two_level_iterations_do_not_grow_with_the_mesh(n, limit):
+    p = 4
+    basis = so.Basis(p)
+    nodes, l2g = so.build_case("C", n, n, p, True, False)
+    geo = so.geometry(basis, nodes, l2g)
+    c = so.condensed_system(p, geo["invJ"], geo["JxW"], l2g)
+    on, vals = so.dirichlet_data(nodes, l2g, geo["x_phys"], so.mesh_boundary_faces(n, n))
+    xj, itj, x2, it2, ct, Ace, _ = emulate(p, c, on, vals, basis.nodes)
+    assert it2 <= limit and it2 < itj
+    assert rel_l2(x2, xj) < 1e-10
+
+
+def test_prolongation_reproduces_linear_functions_on_straight_edges():
+    p, n = 5, 4
+    basis = so.Basis(p)
+    nodes, l2g = so.build_case("S", n, n, p, True, False)
+    geo = so.geometry(basis, nodes, l2g)
+    c = so.condensed_system(p, geo["invJ"], geo["JxW"], l2g)
+    N, NE = p + 1, 4 * p
+    ids = c["ids"]
+    l2g_ext, nptr, npos = condensed_tables(
+        np.pad(ids, ((0, 0), (0, N * N - NE))).astype(np.uint32), np.arange(NE), c["n_ext"])
+    ct = coarse_tables(l2g_ext, nptr, npos, None, basis.nodes)
+    # physical GLL coordinates of the exterior nodes
+    h = so.hier_order(N)[:NE].astype(int)
+    xg = np.zeros((2, c["n_ext"]))
+    xg[:, ids.ravel()] = np.moveaxis(geo["x_phys"].reshape(ids.shape[0], 2, N * N)[:, :, h], 1, 0
+                                     ).reshape(2, -1)
+    lin = 0.3 + 1.7 * xg[0] - 0.6 * xg[1]
+    vids = np.unique(ids[:, :4])
+    pv, pw = ct["pv"].astype(int), ct["pw"]
+    got = pw[:, 0] * lin[vids][pv[:, 0]] + pw[:, 1] * lin[vids][pv[:, 1]]
+    assert np.allclose(got, lin, rtol=0, atol=1e-13)
