@@ -11,11 +11,12 @@ the matrix-free device operator and the device-resident Jacobi-PCG.
     du/dn = 0 on "nbc" (right + top)              (examples/poisson.py:125-143, :200)
 
     python examples/poisson.py [--n 64] [--order 8] [--msh file.msh] [--kind S|C]
-                               [--solver matrix-free|condensed]
+                               [--solver matrix-free|condensed|condensed-two-level]
 
 ``--solver condensed`` follows the reference example literally: static
 condensation of the element interiors (DOFManagerSC, sem/discrete.py:404-528),
-solve on the element-exterior DOFs, interior back-substitution -- on the device.
+solve on the element-exterior DOFs, interior back-substitution -- on the device;
+``condensed-two-level`` adds the vertex coarse space to the Jacobi preconditioner.
 
 With ``--msh`` the mesh is read from a Gmsh 2.2 binary file with physical
 names "ebc", "nbc" (lines) and a surface (the reference's examples/meshes/
@@ -59,13 +60,17 @@ def run(n=16, order=8, msh=None, kind="S", write_msh=None, rtol=1e-12, quiet=Fal
     t_setup = time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    if solver == "condensed":
+    extra = {}
+    if solver in ("condensed", "condensed-two-level"):
         op = mngr.condensed_poisson_operator(dirichlet=on_ebc)
+        if solver == "condensed-two-level":
+            extra["preconditioner"] = "two-level"
     elif solver == "matrix-free":
         op = mngr.poisson_operator(dirichlet=on_ebc)
     else:
-        raise ValueError("solver must be 'matrix-free' or 'condensed'")
-    u, info = op.solve(f=1.0, dirichlet_values=torch.from_numpy(soln).to(op.dev), rtol=rtol)
+        raise ValueError("solver must be 'matrix-free', 'condensed' or 'condensed-two-level'")
+    u, info = op.solve(f=1.0, dirichlet_values=torch.from_numpy(soln).to(op.dev), rtol=rtol,
+                       **extra)
     torch.cuda.synchronize()
     t_solve = time.perf_counter() - t0
     u = u.cpu().numpy()
@@ -86,7 +91,7 @@ def main():
     ap.add_argument("--msh", default=None, help="Gmsh 2.2 binary mesh to read instead")
     ap.add_argument("--write-msh", default=None,
                     help="write the structured mesh to this .msh file and read it back")
-    ap.add_argument("--solver", default="matrix-free", choices=["matrix-free", "condensed"])
+    ap.add_argument("--solver", default="matrix-free", choices=["matrix-free", "condensed", "condensed-two-level"])
     args = ap.parse_args()
     run(args.n, args.order, args.msh, args.kind, args.write_msh, solver=args.solver)
 
