@@ -42,9 +42,8 @@ def main():
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / steps
     alg = sc.algorithmic_bytes_per_apply
-    print("variant=%s nx=%d p=%d n_ext=%d setup %.1fs  apply %.4f ms  %.0f GB/s algorithmic  "
-          "checksum %.17g" % (os.environ.get("SEMK_SC_MATVEC", "default"), nx, p, sc.n_ext,
-                              t_setup, ms, alg / ms / 1e6, float(out.double().sum())), flush=True)
+    print("nx=%d p=%d n_ext=%d setup %.1fs  apply %.4f ms  %.0f GB/s algorithmic  checksum %.17g"
+          % (nx, p, sc.n_ext, t_setup, ms, alg / ms / 1e6, float(out.double().sum())), flush=True)
 
 
 if __name__ == "__main__":
