@@ -319,8 +319,17 @@ class DOFManagerSC(DOFManager):
             geo = mesh._geometries[blk.geometry_id]
             ext.append(flat[:, geo.exterior_node_ind].ravel())
             itr.append(flat[:, geo.interior_node_ind].ravel())
-        ext_ids = np.unique(np.concatenate(ext).astype(int))
-        int_ids = np.sort(np.concatenate(itr).astype(int))
+        # np.unique / np.sort of the reference, by marking (linear time; the results are the
+        # same sorted id lists): exterior ids may repeat, interior ids are private to a cell
+        ext_flat, int_flat = np.concatenate(ext), np.concatenate(itr)
+        mark = np.zeros(mesh.n_nodes, dtype=bool)
+        mark[ext_flat] = True
+        ext_ids = np.flatnonzero(mark)
+        mark[:] = False
+        mark[int_flat] = True
+        int_ids = np.flatnonzero(mark)
+        if int_ids.size != int_flat.size:          # repeated interior ids: keep the duplicates
+            int_ids = np.sort(int_flat.astype(int))
         order = np.concatenate((ext_ids, int_ids))
         if order.size != mesh.n_nodes:
             raise AssertionError("exterior/interior split does not cover the mesh nodes")
@@ -1014,7 +1023,8 @@ class Mesh(object):
         place and rewrites every node map through the inverse permutation
         (sem/discrete.py:1115-1127)."""
         self.nodes[:, :perm.size] = self.nodes[:, perm]
-        inv = np.zeros_like(perm)
-        inv[perm] = np.arange(perm.size)
+        # inverse permutation in the node maps' own dtype (uint32): half the gather traffic
+        inv = np.zeros(perm.size, dtype=np.uint32 if perm.size < 2 ** 32 else perm.dtype)
+        inv[perm] = np.arange(perm.size, dtype=inv.dtype)
         for blk in self._blocks_flushed():
             blk.node_maps[...] = inv[blk.node_maps]
