@@ -370,7 +370,8 @@ class DOFManagerSC(DOFManager):
         from .condensed import CondensedPoissonOperator
         return CondensedPoissonOperator(self, dirichlet=dirichlet, **kwargs)
 
-    def solve_device(self, local_systems, dof_vec, on_ebc, rtol=1e-12, maxiter=200000):
+    def solve_device(self, local_systems, dof_vec, on_ebc, rtol=1e-12, maxiter=200000,
+                     preconditioner="jacobi"):
         """``solve`` on the GPU (sem/discrete.py:526-528 with the Schur assembly of
         :478-500 folded in): takes the same hierarchically ordered
         ``local_systems`` = iterable of ``(lmat_h, lrhs_h)`` as
@@ -378,7 +379,8 @@ class DOFManagerSC(DOFManager):
         (True = essential-BC DOF, values read from ``dof_vec``) and writes the
         solution into ``dof_vec`` in place.  The local matrices must be symmetric
         with positive definite interior blocks; the condensed system is solved by
-        Jacobi-PCG instead of SuperLU.  Returns the PCG info."""
+        PCG instead of SuperLU (``preconditioner``: "jacobi" or "two-level", see
+        CondensedPoissonOperator.solve_pcg).  Returns the PCG info."""
         if self._dpn != 1:
             raise NotImplementedError("solve_device supports one DOF per node")
         from .condensed import CondensedLocalSystems
@@ -391,7 +393,7 @@ class DOFManagerSC(DOFManager):
         cs = CondensedLocalSystems(self, lm, lr, dirichlet=on_ebc)
         vals = np.zeros(self.ndof)
         vals[:self.ndof_exterior][on_ebc] = np.asarray(dof_vec)[:self.ndof_exterior][on_ebc]
-        u, info = cs.solve(vals, rtol=rtol, maxiter=maxiter)
+        u, info = cs.solve(vals, rtol=rtol, maxiter=maxiter, preconditioner=preconditioner)
         if not info.converged:
             from ._lib import SolverFailure
             raise SolverFailure("condensed PCG did not converge: %r" % (info,))
