@@ -117,11 +117,13 @@ class CondensedStripView(object):
     the attributes ``DistributedOperator`` / ``PeerHalo`` / ``distributed_pcg``
     read from a ``StripPartition``."""
 
-    def __init__(self, part, n_ext):
+    def __init__(self, part, n_ext, column=None):
         self.base = part
         self.rank, self.world = part.rank, part.world
         self.left, self.right = part.left, part.right
-        self.NY = part.NY
+        # entries of one interface column: all its nodes for exterior vectors; ``column`` =
+        # ny + 1 describes vertex (coarse) vectors, whose compact ids are ordered the same way
+        self.NY = part.NY if column is None else int(column)
         self.n_local = int(n_ext)
         self.n_owned = self.n_local - (self.NY if self.right is not None else 0)
 

@@ -334,3 +334,172 @@ def test_condensed_strip_view_description():
     assert views[0].left_slice == slice(0, NYn)
     assert views[0].right_slice == slice(n_ext - NYn, n_ext)
     assert views[1].NY == NYn and views[1].base is parts[1]
+
+
+# --------------------------------------------------------------------------
+# two-level preconditioner on two ranks: algorithm-level emulation (oracle operators,
+# the product's host tables and partition views) of the scheme the device path will use
+# --------------------------------------------------------------------------
+def _worker_two_level(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, ORACLE_DIR)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sem_oracle as so
+        from spectralelementmethod_b200 import discrete, meshgen
+        from spectralelementmethod_b200.basis_functions import (LagrangeGaussLobatto,
+                                                                TensorProductQS)
+        from spectralelementmethod_b200.condensed import coarse_tables, condensed_tables
+        from spectralelementmethod_b200.distributed import (CondensedStripView,
+                                                            DistributedOperator, StripPartition,
+                                                            distributed_pcg)
+        nxl, ny, p = 4, 6, 4
+        bounds = (-1.0, -1.0 + 2.0 * world, -1.0, 1.0)
+        part = StripPartition(rank, world, nxl, ny, p, bounds=bounds)
+        mesh = part.build_local_mesh("C")
+        b1 = LagrangeGaussLobatto(p)
+        mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        on_full = mngr.boundary_node_mask("ebc")
+        l2g = mngr.node_map_array()
+        N, NE = p + 1, 4 * p
+        lex = meshgen.structured_node_maps(nxl, ny, p).reshape(-1)
+        lex_ids = np.empty(mesh.n_nodes, dtype=np.int64)
+        lex_ids[l2g.reshape(-1)] = lex
+        gid = part.global_ids()[lex_ids]
+        geo = so.geometry(so.Basis(p), mesh.nodes, l2g)
+        c = so.condensed_system(p, geo["invJ"], geo["JxW"], l2g)
+        n_ext, ids, S_e = c["n_ext"], c["ids"], c["S"]
+        D = on_full[:n_ext]
+        ext_loc = np.asarray(mesh.get_geometries()[0].exterior_node_ind)
+        l2g_ext, nptr, npos = condensed_tables(l2g.reshape(-1, N * N), ext_loc, n_ext)
+        ct = coarse_tables(l2g_ext, nptr, npos, D, np.asarray(b1.nodes))
+        n_v, Dc = ct["n_v"], ct["dirichlet_c"]
+        vc = ct["vert_c"].astype(np.int64)
+        view_f = CondensedStripView(part, n_ext)
+        view_c = CondensedStripView(part, n_v, column=ny + 1)
+        # the coarse interface columns are the leading / trailing compact vertex ids
+        vids = np.unique(ids[:, :4])
+        assert np.array_equal(lex_ids[vids[view_c.left_slice]], np.arange(0, part.NY, p))
+        assert np.array_equal(lex_ids[vids[view_c.right_slice]],
+                              part.n_local - part.NY + np.arange(0, part.NY, p))
+        Mf, Mc = (~D).astype(float), (~Dc).astype(float)
+        S = c["Sg"]
+        Phi = ct["phi"][None] * (~D)[ids][:, :, None] * (~Dc)[vc][:, None, :]
+        Ace = np.einsum("eka,ekj,ejc->eac", Phi, S_e, Phi)
+        vptr, vpos = ct["vptr"].astype(np.int64), ct["vpos"].astype(np.int64)
+
+        def fine_apply(u, outv, dot):
+            un = u.numpy()
+            y = Mf * (S @ (Mf * un)) + (1 - Mf) * un
+            outv = torch.empty_like(u) if outv is None else outv
+            outv.copy_(torch.from_numpy(y))
+            if dot is not None:
+                dot[0] = float(un @ y)
+            return outv
+
+        def coarse_apply(u, outv, dot):
+            un = u.numpy()
+            yl = np.einsum("eac,ec->ea", Ace, un[vc]).ravel()
+            y = np.where(Dc, un, np.add.reduceat(yl[vpos], vptr[:-1]))
+            outv = torch.empty_like(u) if outv is None else outv
+            outv.copy_(torch.from_numpy(y))
+            if dot is not None:
+                dot[0] = float(un @ y)
+            return outv
+
+        dop = DistributedOperator(view_f, fine_apply, dirichlet=D)
+        dop_c = DistributedOperator(view_c, coarse_apply, dirichlet=Dc)
+        tD, tDc = torch.from_numpy(D), torch.from_numpy(Dc)
+        dl = torch.from_numpy(S.diagonal().copy())
+        dop.exchange_add(dl)
+        dl[tD] = 1.0
+        dcl = torch.from_numpy(np.add.reduceat(np.einsum("eaa->ea", Ace).ravel()[vpos], vptr[:-1]))
+        dop_c.exchange_add(dcl)
+        dcl[tDc] = 1.0
+        pv, pw = ct["pv"].astype(np.int64), ct["pw"]
+        rptr, ridx, rw = ct["rptr"].astype(np.int64), ct["ridx"].astype(np.int64), ct["rw"]
+        owned = np.zeros(n_ext)
+        owned[:view_f.n_owned] = 1.0
+        inner_its = []
+
+        def precondition(r):
+            rn = r.numpy()
+            rc = np.zeros(n_v)
+            nz = rptr[1:] > rptr[:-1]
+            rc[nz] = np.add.reduceat(rw * (owned * rn)[ridx], rptr[:-1][nz])   # owned nodes only
+            rc = torch.from_numpy(rc)
+            dop_c.exchange_add(rc)                                           # + the neighbours' part
+            xc = torch.zeros(n_v, dtype=torch.float64)
+            itc, _, _ = distributed_pcg(dop_c, rc, xc, 1.0 / dcl, CpuKernels(Dc), rtol=1e-2,
+                                        maxiter=500, check_every=1)
+            inner_its.append(itc)
+            xn = xc.numpy()
+            return torch.from_numpy(rn / dl.numpy() + pw[:, 0] * xn[pv[:, 0]] + pw[:, 1] * xn[pv[:, 1]])
+
+        # lifted right-hand side (as in the condensed worker above)
+        bl = torch.from_numpy(c["grhs"].copy())
+        dop.exchange_add(bl)
+        x_, y_ = mesh.nodes
+        g = np.where(on_full, 0.3 * x_ - 0.2 * y_ + 0.1, 0.0)[:n_ext]
+        t = torch.from_numpy(Mf * (S @ g))
+        dop.exchange_add(t)
+        bh = bl - t
+        bh[tD] = torch.from_numpy(g)[tD]
+        x = torch.where(tD, bh, torch.zeros_like(bh))
+        # outer PCG with owner-weighted dots
+        r = torch.where(tD, torch.zeros_like(bh), bh - dop.apply(x))
+        bb = float(dop.owned_dot(torch.where(tD, torch.zeros_like(bh), bh),
+                                 torch.where(tD, torch.zeros_like(bh), bh)))
+        z = precondition(r)
+        pvec = z.clone()
+        rz = float(dop.owned_dot(r, z))
+        it = 0
+        dot = torch.zeros(1, dtype=torch.float64)
+        while it < 200 and float(dop.owned_dot(r, r)) > 1e-26 * bb:
+            Ap = dop.apply(pvec, dot_out=dot)
+            dist.all_reduce(dot)
+            alpha = rz / float(dot)
+            x += alpha * pvec
+            r -= alpha * Ap
+            z = precondition(r)
+            rzn = float(dop.owned_dot(r, z))
+            pvec = z + (rzn / rz) * pvec
+            rz = rzn
+            it += 1
+        sol = np.zeros(mesh.n_nodes)
+        sol[:n_ext] = x.numpy()
+        inner = np.linalg.solve(c["Aii"], (c["f_int"] - np.einsum("eij,ej->ei", c["Aie"],
+                                                                  sol[ids]))[..., None])
+        sol[c["int_ids"]] = inner[..., 0]
+        torch.save(dict(gid=gid, sol=sol, it=it, inner=int(np.sum(inner_its))),
+                   os.path.join(out, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_two_level_pcg_emulation(tmp_path):
+    import sem_oracle as so
+    world, nxl, ny, p = 2, 4, 6, 4
+    out = str(tmp_path)
+    mp.spawn(_worker_two_level, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = [torch.load(os.path.join(out, "rank%d.pt" % r), weights_only=False) for r in range(world)]
+    nxg = nxl * world
+    NX, NYn = nxg * p + 1, ny * p + 1
+    X, Y = np.meshgrid(np.linspace(-1.0, -1.0 + 2.0 * world, NX), np.linspace(-1, 1, NYn),
+                       indexing="ij")
+    s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
+    nodes = np.vstack([(X + s).ravel(), (Y + s).ravel()])
+    l2g = so.mesh_l2g(nxg, ny, p)
+    basis = so.Basis(p)
+    geo = so.geometry(basis, nodes, l2g)
+    L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
+    A = so.assemble_csr(L, l2g, nodes.shape[1])
+    on, _ = so.dirichlet_data(nodes, l2g, geo["x_phys"], so.mesh_boundary_faces(nxg, ny))
+    vals = np.where(on, 0.3 * nodes[0] - 0.2 * nodes[1] + 0.1, 0.0)
+    want = so.solve_direct(A, so.assemble_vector(geo["JxW"], l2g, nodes.shape[1]), on, vals)
+    assert res[0]["it"] == res[1]["it"] and res[0]["it"] < 40       # mesh-independent count
+    assert res[0]["inner"] == res[1]["inner"] > 0
+    for r in res:
+        assert rel_l2(r["sol"], want[r["gid"]]) < 1e-10
