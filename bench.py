@@ -176,7 +176,7 @@ def cpu_baseline(n_side, kind, target_seconds=10.0):
         fn()
         reps += 1
         el = time.perf_counter() - t0
-        if el >= target_seconds or reps >= 1000:
+        if el >= target_seconds or reps >= 100000:
             break
     return {"value": ndof * reps / el / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "port",
             "sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s; %s"
