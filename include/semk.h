@@ -531,6 +531,26 @@ int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const
                            int maxiter, double inner_rtol, int inner_maxiter,
                            semk_pcg_info *info, int64_t *inner_total, void *stream);
 
+/* The pieces of the two-level preconditioner as separate entry points, for the
+ * multi-GPU outer loop (driven from the host so that the interface exchanges and
+ * all-reduces can sit between them):
+ *   resid   : r = b - Ax and b_masked = b, both zero on Dirichlet rows (dirichlet NULL = none)
+ *   scale   : z = d * r
+ *   axpy2   : x += alpha p ; r -= alpha Ap
+ *   xpay    : p = z + beta p
+ *   restrict: rc = P^T r over the fine nodes [0, n_owned) only (owner-weighted)
+ *   prolong : z += P xc */
+int semk_vec_resid_f64(int64_t n, const double *b, const double *Ax, const uint8_t *dirichlet,
+                       double *r, double *b_masked, void *stream);
+int semk_vec_scale_f64(int64_t n, const double *d, const double *r, double *z, void *stream);
+int semk_vec_axpy2_f64(int64_t n, double alpha, const double *p, const double *Ap, double *x,
+                       double *r, void *stream);
+int semk_vec_xpay_f64(int64_t n, double beta, const double *z, double *p, void *stream);
+int semk_sc_restrict_f64(const semk_sc_coarse *cs, const double *r, int64_t n_owned, double *rc,
+                         void *stream);
+int semk_sc_prolong_add_f64(int64_t n_ext, const semk_sc_coarse *cs, const double *xc, double *z,
+                            void *stream);
+
 /* ------------------------------------------------------------------------
  * Field evaluation: DOFManager.values_at_nodes
  * (sem/discrete.py:235-258) -- GLL coefficients -> values at the equispaced

@@ -148,6 +148,12 @@ SIGNATURES = {
     "semk_sc_pcg2_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse), _P, _P, _P,
                                     _P, _P, _P, _P, _P, _D, _I, _D, _I,
                                     C.POINTER(semk_pcg_info), C.POINTER(C.c_int64), _P]),
+    "semk_vec_resid_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
+    "semk_vec_scale_f64": (_I, [_L, _P, _P, _P, _P]),
+    "semk_vec_axpy2_f64": (_I, [_L, _D, _P, _P, _P, _P, _P]),
+    "semk_vec_xpay_f64": (_I, [_L, _D, _P, _P, _P]),
+    "semk_sc_restrict_f64": (_I, [C.POINTER(semk_sc_coarse), _P, _L, _P, _P]),
+    "semk_sc_prolong_add_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _P]),
     "semk_values_at_nodes_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),

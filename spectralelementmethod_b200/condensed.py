@@ -369,11 +369,13 @@ class CondensedPoissonOperator(object):
         dc = torch.empty(n_v, **f64)
         _lib.check(self._lib.semk_sc_coarse_assemble_f64(
             self.n_elem, C.byref(cs), device.ptr(dloc), device.ptr(dc), device.stream_ptr()))
+        t["diag_c_local"] = dc.clone()      # this rank's elements only (distributed: + exchange)
         if self.has_dirichlet:
             dc[t["dirichlet_c"].bool()] = 1.0
         if not bool((dc > 0).all()):
             raise AssertionError("coarse operator has a non-positive diagonal entry")
         t["dinv_c"] = 1.0 / dc
+        t["dirichlet_c_host"] = ct["dirichlet_c"]
         self._coarse = (cs, t, n_v)
         return self._coarse
 

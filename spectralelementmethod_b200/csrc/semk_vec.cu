@@ -505,11 +505,16 @@ __global__ void __launch_bounds__(kVecThreads)
 __global__ void __launch_bounds__(kVecThreads)
     restrict_kernel(int64_t n_v, const uint32_t *__restrict__ rptr,
                     const uint32_t *__restrict__ ridx, const double *__restrict__ rw,
-                    const double *__restrict__ r, double *__restrict__ rc) {
+                    const double *__restrict__ r, int64_t n_owned, double *__restrict__ rc) {
+  // n_owned: only fine nodes [0, n_owned) contribute (multi-GPU: every global node is
+  // restricted by its owner; one GPU: n_owned = n)
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_v;
        v += (int64_t)gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (uint32_t q = rptr[v]; q < rptr[v + 1]; ++q) s = fma(rw[q], r[ridx[q]], s);
+    for (uint32_t q = rptr[v]; q < rptr[v + 1]; ++q) {
+      const uint32_t g = ridx[q];
+      if ((int64_t)g < n_owned) s = fma(rw[q], r[g], s);
+    }
     rc[v] = s;
   }
 }
@@ -586,7 +591,7 @@ extern "C" int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse
   auto precondition = [&]() -> int {
     scale_kernel<<<g, blk, 0, st>>>(n, dinv, r, z);
     SEMK_LAUNCH_CHECK("scale_kernel");
-    restrict_kernel<<<gc, blk, 0, st>>>(nv, cs->rptr, cs->ridx, cs->rw, r, rc);
+    restrict_kernel<<<gc, blk, 0, st>>>(nv, cs->rptr, cs->ridx, cs->rw, r, n, rc);
     SEMK_LAUNCH_CHECK("restrict_kernel");
     SEMK_CUDA_CHECK(cudaMemsetAsync(xc, 0, sizeof(double) * nv, st));
     semk_pcg_info ii;
@@ -654,5 +659,62 @@ extern "C" int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse
     semk_set_error("semk_sc_pcg2_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
     return SEMK_ERR_BREAKDOWN;
   }
+  return SEMK_OK;
+}
+
+// ---- the pieces of the two-level preconditioner as separate entry points (the multi-GPU
+// outer loop, distributed.distributed_two_level_pcg, is driven from Python so that the
+// exchanges and all-reduces can sit between them) -------------------------------------------
+extern "C" int semk_vec_resid_f64(int64_t n, const double *b, const double *Ax,
+                                  const uint8_t *dirichlet, double *r, double *b_masked,
+                                  void *stream) {
+  SEMK_REQUIRE(n > 0 && b && Ax && r && b_masked, "semk_vec_resid_f64: bad argument");
+  resid_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(n, b, Ax, dirichlet, r,
+                                                                      b_masked);
+  SEMK_LAUNCH_CHECK("resid_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_vec_scale_f64(int64_t n, const double *d, const double *r, double *z,
+                                  void *stream) {
+  SEMK_REQUIRE(n > 0 && d && r && z, "semk_vec_scale_f64: bad argument");
+  scale_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(n, d, r, z);
+  SEMK_LAUNCH_CHECK("scale_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_vec_axpy2_f64(int64_t n, double alpha, const double *p, const double *Ap,
+                                  double *x, double *r, void *stream) {
+  SEMK_REQUIRE(n > 0 && p && Ap && x && r, "semk_vec_axpy2_f64: bad argument");
+  axpy2_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(n, alpha, p, Ap, x, r);
+  SEMK_LAUNCH_CHECK("axpy2_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_vec_xpay_f64(int64_t n, double beta, const double *z, double *p,
+                                 void *stream) {
+  SEMK_REQUIRE(n > 0 && z && p, "semk_vec_xpay_f64: bad argument");
+  xpay_kernel<<<vec_blocks(n), kVecThreads, 0, semk_stream(stream)>>>(n, beta, z, p);
+  SEMK_LAUNCH_CHECK("xpay_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_restrict_f64(const semk_sc_coarse *cs, const double *r, int64_t n_owned,
+                                    double *rc, void *stream) {
+  SEMK_REQUIRE(cs && cs->n_v > 0 && cs->rptr && cs->ridx && cs->rw && r && rc && n_owned >= 0,
+               "semk_sc_restrict_f64: bad argument");
+  restrict_kernel<<<vec_blocks(cs->n_v), kVecThreads, 0, semk_stream(stream)>>>(
+      cs->n_v, cs->rptr, cs->ridx, cs->rw, r, n_owned, rc);
+  SEMK_LAUNCH_CHECK("restrict_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_prolong_add_f64(int64_t n_ext, const semk_sc_coarse *cs, const double *xc,
+                                       double *z, void *stream) {
+  SEMK_REQUIRE(n_ext > 0 && cs && cs->pv && cs->pw && xc && z,
+               "semk_sc_prolong_add_f64: bad argument");
+  prolong_add_kernel<<<vec_blocks(n_ext), kVecThreads, 0, semk_stream(stream)>>>(
+      n_ext, cs->pv, cs->pw, xc, z);
+  SEMK_LAUNCH_CHECK("prolong_add_kernel");
   return SEMK_OK;
 }

@@ -29,7 +29,8 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["StripPartition", "CondensedStripView", "DistributedOperator", "PeerHalo",
-           "distributed_pcg", "DistributedPoisson", "DistributedCondensedPoisson"]
+           "distributed_pcg", "distributed_two_level_pcg", "DistributedPoisson",
+           "DistributedCondensedPoisson"]
 
 
 class StripPartition(object):
@@ -357,6 +358,71 @@ def distributed_pcg(dop, b, x, dinv, kernels, rtol=1e-12, maxiter=200000, check_
     return it, (float(h[3]) / bb) ** 0.5, False
 
 
+def distributed_two_level_pcg(dop, dop_c, ops, b, x, rtol=1e-12, maxiter=1000, inner_rtol=1e-2,
+                              inner_maxiter=20000, check_every=25):
+    """PCG over all ranks with the two-level preconditioner of the condensed system,
+    M^-1 = D^-1 + P Ac^-1 P^T (condensed.coarse_tables; single-GPU twin:
+    semk_sc_pcg2_solve_f64).
+
+    dop / dop_c : DistributedOperator of the fine (exterior) and the coarse (vertex)
+        level; their partition views give the owned prefixes for the dot products.
+    ops : the rank-local pieces, device kernels in production and NumPy stand-ins in
+        the CPU test --
+          residual(b, Ax) -> (r, b_masked)       r = b - Ax, zero on Dirichlet rows
+          jacobi(r) -> z                         z = dinv * r  (new vector)
+          restrict(r, n_owned) -> rc             P^T r over the first n_owned fine nodes
+          prolong_add(xc, z)                     z += P xc
+          axpy2(alpha, p, Ap, x, r)              x += alpha p ; r -= alpha Ap
+          xpay(beta, z, p)                       p = z + beta p
+          new_coarse() -> zero coarse vector,  dinv_c, kernels_c (PCG kernels, coarse level)
+    The restriction runs over OWNED fine nodes only and the coarse interface column is
+    then summed across neighbours (every global fine node is restricted exactly once).
+    Returns (outer iterations, relative residual, converged, total inner iterations)."""
+    r, bm = ops.residual(b, dop.apply(x))
+    bb = float(dop.owned_dot(bm, bm))
+    rr = float(dop.owned_dot(r, r))
+    tol2 = rtol * rtol
+    if bb == 0.0 or rr <= tol2 * bb:
+        return 0, (rr / bb) ** 0.5 if bb > 0 else 0.0, True, 0
+    inner_total = 0
+
+    def precondition(res):
+        z = ops.jacobi(res)
+        rc = ops.restrict(res, dop.part.n_owned)
+        dop_c.exchange_add(rc)
+        xc = ops.new_coarse()
+        itc, _, _ = distributed_pcg(dop_c, rc, xc, ops.dinv_c, ops.kernels_c, rtol=inner_rtol,
+                                    maxiter=inner_maxiter, check_every=check_every)
+        ops.prolong_add(xc, z)
+        return z, itc
+
+    z, itc = precondition(r)
+    inner_total += itc
+    p = z.clone()
+    rz = float(dop.owned_dot(r, z))
+    dot = torch.zeros(1, dtype=torch.float64, device=b.device)
+    Ap = torch.empty_like(b)
+    it = 0
+    while it < maxiter:
+        dop.apply(p, out=Ap, dot_out=dot)
+        dist.all_reduce(dot, group=dop.group)
+        pAp = float(dot)
+        if not pAp > 0.0:
+            from ._lib import SolverFailure
+            raise SolverFailure("distributed two-level PCG breakdown (p.Ap <= 0 or non-finite)")
+        ops.axpy2(rz / pAp, p, Ap, x, r)
+        it += 1
+        rr = float(dop.owned_dot(r, r))
+        if rr <= tol2 * bb:
+            return it, (rr / bb) ** 0.5, True, inner_total
+        z, itc = precondition(r)
+        inner_total += itc
+        rz_new = float(dop.owned_dot(r, z))
+        ops.xpay(rz_new / rz, z, p)
+        rz = rz_new
+    return it, (rr / bb) ** 0.5, False, inner_total
+
+
 class DistributedPoisson(object):
     """The whole multi-GPU Poisson path for the strip-partitioned structured
     configurations (BASELINE.json configs[4]): local mesh + DOF manager +
@@ -526,7 +592,10 @@ class DistributedCondensedPoisson(object):
         out[self._mask] = gv[self._mask]
         return out
 
-    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25,
+                  preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000):
+        if preconditioner not in ("jacobi", "two-level"):
+            raise ValueError("preconditioner must be 'jacobi' or 'two-level'")
         if x0 is None:
             x = torch.zeros_like(b)
             if self._mask is not None:
@@ -535,9 +604,107 @@ class DistributedCondensedPoisson(object):
             x = x0.clone()
         if self._dinv is None:
             self._dinv = 1.0 / self.diagonal()
+        if preconditioner == "two-level":
+            ops, dop_c = self._two_level()
+            it, rel, ok, inner = distributed_two_level_pcg(
+                self.dop, dop_c, ops, b, x, rtol=rtol, maxiter=maxiter, inner_rtol=inner_rtol,
+                inner_maxiter=inner_maxiter, check_every=check_every)
+            self.last_inner_iterations = inner
+            return x, it, rel, ok
         it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
                                       maxiter=maxiter, check_every=check_every)
         return x, it, rel, ok
+
+    def _two_level(self):
+        """Coarse level of the two-level preconditioner on the strip partition (lazy):
+        the rank-local coarse operator of condensed.CondensedPoissonOperator, its
+        interface exchange (the coarse interface columns are the leading / trailing
+        ny + 1 compact vertex ids) and the device pieces `distributed_two_level_pcg`
+        strings together.  The scheme is checked on two ranks on CPU
+        (tests/test_distributed.py); this device wiring has NOT run on GPUs yet."""
+        if getattr(self, "_tl", None) is not None:
+            return self._tl
+        import ctypes as C
+        from . import _lib, device
+        from .operators import PCGKernels
+        sc = self.sc
+        lib = sc._lib
+        cs, t, n_v = sc._build_coarse()
+        view_c = CondensedStripView(self.part, n_v, column=self.part.ny + 1)
+        halo_c = None
+        if self.halo is not None:
+            halo_c = PeerHalo(view_c, self.group, sc.dev)
+        dir_c = t["dirichlet_c_host"] if sc.has_dirichlet else None
+        dop_c = DistributedOperator(
+            view_c, lambda u, out, dot: sc.coarse_apply(u, out=out, dot_out=dot),
+            dirichlet=dir_c, group=self.group, device=sc.dev, halo=halo_c)
+        dc = t["diag_c_local"].clone()
+        dop_c.exchange_add(dc)
+        if sc.has_dirichlet:
+            dc[t["dirichlet_c"].bool()] = 1.0
+        dinv = self._dinv
+        n_ext = sc.n_ext
+
+        class _CoarseLevel(object):       # what PCGKernels reads from an operator
+            pass
+        lvl = _CoarseLevel()
+        lvl._lib = lib
+        lvl.n_nodes = n_v
+        lvl.vec_partials = torch.zeros(int(lib.semk_vec_partials_len(n_v)), dtype=torch.float64,
+                                       device=sc.dev)
+        lvl.dirichlet_dev = t["dirichlet_c"]
+        lvl.has_dirichlet = sc.has_dirichlet
+        dirichlet_ptr = device.ptr(sc.dirichlet_dev if sc.has_dirichlet else None)
+
+        class _Ops(object):
+            dinv_c = 1.0 / dc
+            kernels_c = PCGKernels(lvl, n=n_v)
+
+            @staticmethod
+            def residual(bv, Ax):
+                r, bm = torch.empty_like(bv), torch.empty_like(bv)
+                _lib.check(lib.semk_vec_resid_f64(n_ext, device.ptr(bv), device.ptr(Ax),
+                                                  dirichlet_ptr, device.ptr(r), device.ptr(bm),
+                                                  device.stream_ptr()))
+                return r, bm
+
+            @staticmethod
+            def jacobi(r):
+                z = torch.empty_like(r)
+                _lib.check(lib.semk_vec_scale_f64(n_ext, device.ptr(dinv), device.ptr(r),
+                                                  device.ptr(z), device.stream_ptr()))
+                return z
+
+            @staticmethod
+            def restrict(r, n_owned):
+                rc = torch.empty(n_v, dtype=torch.float64, device=sc.dev)
+                _lib.check(lib.semk_sc_restrict_f64(C.byref(cs), device.ptr(r), int(n_owned),
+                                                    device.ptr(rc), device.stream_ptr()))
+                return rc
+
+            @staticmethod
+            def prolong_add(xc, z):
+                _lib.check(lib.semk_sc_prolong_add_f64(n_ext, C.byref(cs), device.ptr(xc),
+                                                       device.ptr(z), device.stream_ptr()))
+
+            @staticmethod
+            def axpy2(alpha, p, Ap, x, r):
+                _lib.check(lib.semk_vec_axpy2_f64(n_ext, float(alpha), device.ptr(p),
+                                                  device.ptr(Ap), device.ptr(x), device.ptr(r),
+                                                  device.stream_ptr()))
+
+            @staticmethod
+            def xpay(beta, z, p):
+                _lib.check(lib.semk_vec_xpay_f64(n_ext, float(beta), device.ptr(z), device.ptr(p),
+                                                 device.stream_ptr()))
+
+            @staticmethod
+            def new_coarse():
+                return torch.zeros(n_v, dtype=torch.float64, device=sc.dev)
+
+        self._tl = (_Ops, dop_c)
+        self._halo_c = halo_c
+        return self._tl
 
     def solve(self, f=1.0, dirichlet_values=None, **pcg_kwargs):
         """Condensed load, lifting, distributed PCG on the exterior DOFs, rank-local

@@ -67,6 +67,15 @@ def main():
         serr_sc = float((xs - xg[cg]).norm() / xg.norm())
         assert ok_sc and serr_sc < 1e-9, (ok_sc, serr_sc)
         sc_res[exchange] = (xs, it_sc, serr_sc)
+        # two-level preconditioner on the partition (device wiring of
+        # distributed.distributed_two_level_pcg)
+        x2, it2, rel2, ok2 = dc.solve(1.0, None, rtol=1e-12, preconditioner="two-level")
+        serr2 = float((x2 - xg[cg]).norm() / xg.norm())
+        assert ok2 and serr2 < 1e-9 and it2 < it_sc, (ok2, serr2, it2, it_sc)
+        sc_res[exchange] += (it2, dc.last_inner_iterations)
+        if getattr(dc, "_halo_c", None) is not None:
+            dc._halo_c.check()
+            dc._halo_c.close()
         if dc.halo is not None:
             dc.halo.check()
             dc.halo.close()
@@ -77,6 +86,8 @@ def main():
               "solution diff %.2e; peer == nccl bitwise" % (world, err, it, info.iterations, serr))
         print("multigpu_check condensed ok: PCG %d its, solution diff %.2e vs the single-GPU "
               "uncondensed solve; peer == nccl bitwise" % (sc_res["peer"][1], sc_res["peer"][2]))
+        print("multigpu_check two-level ok: %d outer / %d inner its"
+              % (sc_res["peer"][3], sc_res["peer"][4]))
     dist.barrier()
     dist.destroy_process_group()
 

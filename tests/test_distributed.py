@@ -420,24 +420,48 @@ def _worker_two_level(rank, world, port, out):
         dcl[tDc] = 1.0
         pv, pw = ct["pv"].astype(np.int64), ct["pw"]
         rptr, ridx, rw = ct["rptr"].astype(np.int64), ct["ridx"].astype(np.int64), ct["rw"]
-        owned = np.zeros(n_ext)
-        owned[:view_f.n_owned] = 1.0
-        inner_its = []
+        class Ops(object):
+            """NumPy stand-ins of the rank-local device pieces."""
+            dinv_c = 1.0 / dcl
+            kernels_c = CpuKernels(Dc)
 
-        def precondition(r):
-            rn = r.numpy()
-            rc = np.zeros(n_v)
-            nz = rptr[1:] > rptr[:-1]
-            rc[nz] = np.add.reduceat(rw * (owned * rn)[ridx], rptr[:-1][nz])   # owned nodes only
-            rc = torch.from_numpy(rc)
-            dop_c.exchange_add(rc)                                           # + the neighbours' part
-            xc = torch.zeros(n_v, dtype=torch.float64)
-            itc, _, _ = distributed_pcg(dop_c, rc, xc, 1.0 / dcl, CpuKernels(Dc), rtol=1e-2,
-                                        maxiter=500, check_every=1)
-            inner_its.append(itc)
-            xn = xc.numpy()
-            return torch.from_numpy(rn / dl.numpy() + pw[:, 0] * xn[pv[:, 0]] + pw[:, 1] * xn[pv[:, 1]])
+            @staticmethod
+            def residual(bv, Ax):
+                bm = torch.where(tD, torch.zeros_like(bv), bv)
+                return torch.where(tD, torch.zeros_like(bv), bv - Ax), bm
 
+            @staticmethod
+            def jacobi(r):
+                return r / dl
+
+            @staticmethod
+            def restrict(r, n_owned):
+                rn = r.numpy().copy()
+                rn[n_owned:] = 0.0                       # owned fine nodes only
+                rc = np.zeros(n_v)
+                nz = rptr[1:] > rptr[:-1]
+                rc[nz] = np.add.reduceat(rw * rn[ridx], rptr[:-1][nz])
+                return torch.from_numpy(rc)
+
+            @staticmethod
+            def prolong_add(xc, z):
+                xn = xc.numpy()
+                z += torch.from_numpy(pw[:, 0] * xn[pv[:, 0]] + pw[:, 1] * xn[pv[:, 1]])
+
+            @staticmethod
+            def axpy2(alpha, p_, Ap, x_, r_):
+                x_ += alpha * p_
+                r_ -= alpha * Ap
+
+            @staticmethod
+            def xpay(beta, z, p_):
+                p_.mul_(beta).add_(z)
+
+            @staticmethod
+            def new_coarse():
+                return torch.zeros(n_v, dtype=torch.float64)
+
+        from spectralelementmethod_b200.distributed import distributed_two_level_pcg
         # lifted right-hand side (as in the condensed worker above)
         bl = torch.from_numpy(c["grhs"].copy())
         dop.exchange_add(bl)
@@ -448,26 +472,11 @@ def _worker_two_level(rank, world, port, out):
         bh = bl - t
         bh[tD] = torch.from_numpy(g)[tD]
         x = torch.where(tD, bh, torch.zeros_like(bh))
-        # outer PCG with owner-weighted dots
-        r = torch.where(tD, torch.zeros_like(bh), bh - dop.apply(x))
-        bb = float(dop.owned_dot(torch.where(tD, torch.zeros_like(bh), bh),
-                                 torch.where(tD, torch.zeros_like(bh), bh)))
-        z = precondition(r)
-        pvec = z.clone()
-        rz = float(dop.owned_dot(r, z))
-        it = 0
-        dot = torch.zeros(1, dtype=torch.float64)
-        while it < 200 and float(dop.owned_dot(r, r)) > 1e-26 * bb:
-            Ap = dop.apply(pvec, dot_out=dot)
-            dist.all_reduce(dot)
-            alpha = rz / float(dot)
-            x += alpha * pvec
-            r -= alpha * Ap
-            z = precondition(r)
-            rzn = float(dop.owned_dot(r, z))
-            pvec = z + (rzn / rz) * pvec
-            rz = rzn
-            it += 1
+        it, rel, ok, inner_total = distributed_two_level_pcg(
+            dop, dop_c, Ops, bh, x, rtol=1e-13, maxiter=200, inner_rtol=1e-2, inner_maxiter=500,
+            check_every=1)
+        assert ok and rel <= 1e-13
+        inner_its = [inner_total]
         sol = np.zeros(mesh.n_nodes)
         sol[:n_ext] = x.numpy()
         inner = np.linalg.solve(c["Aii"], (c["f_int"] - np.einsum("eij,ej->ei", c["Aie"],
