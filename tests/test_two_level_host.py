@@ -141,3 +141,25 @@ def test_prolongation_reproduces_linear_functions_on_straight_edges():
     pv, pw = ct["pv"].astype(int), ct["pw"]
     got = pw[:, 0] * lin[vids][pv[:, 0]] + pw[:, 1] * lin[vids][pv[:, 1]]
     assert np.allclose(got, lin, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("n_cells,rings", [(3, 2), (7, 3)])
+def test_two_level_emulation_on_irregular_vertex_valence(n_cells, rings):
+    """Pinwheel meshes (3 / 7 cells around the centre vertex): the edge-based prolongation
+    and the vertex -> entries lists cope with any valence."""
+    from spectralelementmethod_b200 import discrete, meshgen
+    from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+    p = 4
+    mesh = meshgen.pinwheel_mesh(n_cells, p, rings=rings)
+    b1 = LagrangeGaussLobatto(p)
+    mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=True)
+    on = mngr.boundary_node_mask("ebc")
+    l2g = mngr.node_map_array()
+    geo = so.geometry(so.Basis(p), mesh.nodes, l2g)
+    c = so.condensed_system(p, geo["invJ"], geo["JxW"], l2g)
+    x, y = mesh.nodes
+    vals = np.where(on, 0.3 * x - 0.2 * y + 0.1, 0.0)
+    xj, itj, x2, it2, ct, Ace, (restrict, prolong) = emulate(p, c, on, vals, so.Basis(p).nodes)
+    assert ct["n_v"] == np.unique(c["ids"][:, :4]).size
+    assert n_cells in np.diff(ct["vptr"].astype(np.int64))           # the centre vertex
+    assert rel_l2(x2, xj) < 1e-10 and it2 <= itj
