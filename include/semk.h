@@ -531,6 +531,27 @@ int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const
                            int maxiter, double inner_rtol, int inner_maxiter,
                            semk_pcg_info *info, int64_t *inner_total, void *stream);
 
+/* Third level under the vertex coarse space: the inner coarse solve is preconditioned by
+ * Jacobi + a piecewise-constant aggregation of the vertices (element tiles) with a DENSE
+ * inverse at the top, so that the inner iteration count is mesh-independent as well
+ * (oracle/precond_study_three_level.py).  agg: device uint32 [n_v], aggregate of every
+ * vertex (0xffffffff = none: essential boundary); aptr / aidx: CSR of the vertices of
+ * every aggregate; A3inv: device [n_agg][n_agg], inverse of P2^T Ac P2, row major. */
+typedef struct semk_sc_top {
+  int64_t n_agg;
+  const uint32_t *agg;
+  const uint32_t *aptr;
+  const uint32_t *aidx;
+  const double *A3inv;
+} semk_sc_top;
+/* As semk_sc_pcg2_solve_f64 with the three-level preconditioner.  work_c: device
+ * [6 * (n_v + 32) + 2 * (n_agg + 32)].  Both loops are host-driven. */
+int semk_sc_pcg3_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const semk_sc_top *top,
+                           const double *b, double *x, const double *dinv, const double *dinv_c,
+                           double *work, double *work_c, double *sc, double *vec_partials,
+                           double rtol, int maxiter, double inner_rtol, int inner_maxiter,
+                           semk_pcg_info *info, int64_t *inner_total, void *stream);
+
 /* The pieces of the two-level preconditioner as separate entry points, for the
  * multi-GPU outer loop (driven from the host so that the interface exchanges and
  * all-reduces can sit between them):

@@ -80,6 +80,11 @@ class semk_sc_op(C.Structure):
 SC_SCHUR, SC_RHS, SC_BACKSOLVE = 1, 2, 4
 
 
+class semk_sc_top(C.Structure):
+    _fields_ = [("n_agg", C.c_int64), ("agg", C.c_void_p), ("aptr", C.c_void_p),
+                ("aidx", C.c_void_p), ("A3inv", C.c_void_p)]
+
+
 class semk_sc_coarse(C.Structure):
     _fields_ = [
         ("n_v", C.c_int64), ("Ace", C.c_void_p), ("vert_c", C.c_void_p), ("y_loc_c", C.c_void_p),
@@ -148,6 +153,10 @@ SIGNATURES = {
     "semk_sc_pcg2_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse), _P, _P, _P,
                                     _P, _P, _P, _P, _P, _D, _I, _D, _I,
                                     C.POINTER(semk_pcg_info), C.POINTER(C.c_int64), _P]),
+    "semk_sc_pcg3_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse),
+                                    C.POINTER(semk_sc_top), _P, _P, _P, _P, _P, _P, _P, _P, _D,
+                                    _I, _D, _I, C.POINTER(semk_pcg_info), C.POINTER(C.c_int64),
+                                    _P]),
     "semk_vec_resid_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
     "semk_vec_scale_f64": (_I, [_L, _P, _P, _P, _P]),
     "semk_vec_axpy2_f64": (_I, [_L, _D, _P, _P, _P, _P, _P]),

@@ -30,7 +30,8 @@ from . import _lib, device
 from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
 from .operators import PCGInfo
 
-__all__ = ["CondensedPoissonOperator", "CondensedLocalSystems", "condensed_tables"]
+__all__ = ["CondensedPoissonOperator", "CondensedLocalSystems", "condensed_tables", "coarse_tables",
+           "element_tiles", "aggregate_tables", "top_level_inverse"]
 
 
 def condensed_tables(l2g, ext_loc, n_ext):
@@ -379,6 +380,31 @@ class CondensedPoissonOperator(object):
         self._coarse = (cs, t, n_v)
         return self._coarse
 
+    def _build_top(self, max_tiles=4096):
+        """Third level (lazy): vertex aggregates over element tiles and the dense
+        inverse of the aggregated coarse operator."""
+        if getattr(self, "_top", None) is not None:
+            return self._top
+        cs, t, n_v = self._build_coarse()
+        tile = element_tiles(self.dof_mngr.mesh, self.n_elem, max_tiles)
+        vptr = t["vptr"].cpu().numpy().view(np.uint32)
+        vpos = t["vpos"].cpu().numpy().view(np.uint32)
+        vert_c = t["vert_c"].cpu().numpy().view(np.uint32)
+        at = aggregate_tables(vert_c, vptr, vpos, t["dirichlet_c_host"], tile)
+        A3inv = top_level_inverse(t["Ace"].cpu().numpy(), vert_c, at["agg"], at["n_agg"])
+        tt = dict(agg=device.as_i32_bits(at["agg"], self.dev),
+                  aptr=device.as_i32_bits(at["aptr"], self.dev),
+                  aidx=device.as_i32_bits(at["aidx"], self.dev),
+                  A3inv=device._f64(A3inv, self.dev))
+        top = _lib.semk_sc_top()
+        top.n_agg = at["n_agg"]
+        top.agg = tt["agg"].data_ptr()
+        top.aptr = tt["aptr"].data_ptr()
+        top.aidx = tt["aidx"].data_ptr()
+        top.A3inv = tt["A3inv"].data_ptr()
+        self._top = (top, tt, at["n_agg"])
+        return self._top
+
     def coarse_apply(self, xc, out=None, dot_out=None):
         """y = Ac x on the vertex coarse space (tests / diagnostics)."""
         cs, t, n_v = self._build_coarse()
@@ -398,8 +424,8 @@ class CondensedPoissonOperator(object):
             along element edges and an inner Jacobi-PCG on Ac to ``inner_rtol``):
             the outer iteration count no longer grows with the mesh size."""
         self._vec(b, "b")
-        if preconditioner not in ("jacobi", "two-level"):
-            raise ValueError("preconditioner must be 'jacobi' or 'two-level'")
+        if preconditioner not in ("jacobi", "two-level", "three-level"):
+            raise ValueError("preconditioner must be 'jacobi', 'two-level' or 'three-level'")
         if x0 is None:
             x = torch.zeros_like(b)
             if self.has_dirichlet:
@@ -409,6 +435,25 @@ class CondensedPoissonOperator(object):
             x = self._vec(x0, "x0").clone()
         dinv = self.jacobi_inverse()
         info = _lib.semk_pcg_info()
+        if preconditioner == "three-level":
+            # EXPERIMENTAL: checked against a NumPy emulation on CPU
+            # (tests/test_two_level_host.py); the device path has not run on a GPU yet.
+            cs, t, n_v = self._build_coarse()
+            top, tt, n_agg = self._build_top()
+            work = torch.empty(4 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
+            work_c = torch.empty(6 * (n_v + 32) + 2 * (n_agg + 32), dtype=torch.float64,
+                                 device=self.dev)
+            sc = torch.zeros(16, dtype=torch.float64, device=self.dev)
+            inner = C.c_int64(0)
+            rc = self._lib.semk_sc_pcg3_solve_f64(
+                C.byref(self._op), C.byref(cs), C.byref(top), device.ptr(b), device.ptr(x),
+                device.ptr(dinv), device.ptr(t["dinv_c"]), device.ptr(work), device.ptr(work_c),
+                device.ptr(sc), device.ptr(self.vec_partials), float(rtol), int(maxiter),
+                float(inner_rtol), int(inner_maxiter), C.byref(info), C.byref(inner),
+                device.stream_ptr())
+            _lib.check(rc)
+            self.last_inner_iterations = int(inner.value)
+            return x, PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
         if preconditioner == "two-level":
             cs, t, n_v = self._build_coarse()
             work = torch.empty(4 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
@@ -581,3 +626,66 @@ def coarse_tables(l2g_ext, node_ptr, node_pos, dirichlet, gll_nodes):
     return dict(phi=phi, vert_c=vert_c.astype(np.uint32), n_v=n_v, dirichlet_c=dirichlet_c,
                 pv=pv.astype(np.uint32), pw=np.ascontiguousarray(pw), rptr=rptr, ridx=ridx, rw=rw,
                 vptr=vptr, vpos=vpos)
+
+
+def element_tiles(mesh, n_elem, max_tiles=4096):
+    """Tile id of every element for the aggregation level of the three-level
+    preconditioner: k x k blocks of a structured mesh, runs of k^2 elements along a
+    Morton curve through the centroids otherwise; k is the smallest that gives at
+    most ``max_tiles`` tiles (the top level is inverted densely)."""
+    shape = getattr(mesh, "_structured_shape", None)
+    if shape is not None and shape[0] * shape[1] == n_elem:
+        nx, ny = shape
+        k = 1
+        while -(-nx // k) * -(-ny // k) > max_tiles:
+            k += 1
+        k = max(k, min(4, max(nx, ny)))
+        ex, ey = np.divmod(np.arange(n_elem, dtype=np.int64), ny)
+        return (ex // k) * (-(-ny // k)) + ey // k
+    from .operators import _morton_order
+    if not hasattr(mesh, "_centroids"):
+        mesh._compute_cell_centroids()
+    order = _morton_order(mesh._centroids[:, 0], mesh._centroids[:, 1])
+    per = max(16, -(-n_elem // max_tiles))
+    tile = np.empty(n_elem, dtype=np.int64)
+    tile[order] = np.arange(n_elem, dtype=np.int64) // per
+    return tile
+
+
+def aggregate_tables(vert_c, vptr, vpos, dirichlet_c, tile):
+    """Piecewise-constant aggregation of the coarse (vertex) DOFs: a vertex joins the
+    tile of the first element that contains it; vertices on the essential boundary
+    join nothing.  Returns ``agg[n_v]`` (uint32, 0xffffffff = none), ``n_agg`` and the
+    CSR ``aptr / aidx`` of the vertices of every aggregate."""
+    n_v = int(vptr.size - 1)
+    first_elem = vpos[vptr[:-1].astype(np.int64)].astype(np.int64) // 4
+    free = ~np.asarray(dirichlet_c, dtype=bool)
+    raw = np.asarray(tile, dtype=np.int64)[first_elem]
+    uniq, inv = np.unique(raw[free], return_inverse=True)
+    n_agg = int(uniq.size)
+    agg = np.full(n_v, 0xFFFFFFFF, dtype=np.uint32)
+    agg[free] = inv.astype(np.uint32)
+    free_ids = np.flatnonzero(free)
+    order = np.argsort(inv, kind="stable")
+    aidx = free_ids[order].astype(np.uint32)
+    aptr = np.zeros(n_agg + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(inv, minlength=n_agg), out=aptr[1:])
+    return dict(agg=agg, n_agg=n_agg, aptr=aptr, aidx=aidx)
+
+
+def top_level_inverse(Ace, vert_c, agg, n_agg):
+    """Dense inverse of the third-level operator P2^T Ac P2 from the element coarse
+    matrices (host, set-up only; it enters the preconditioner, not the solution)."""
+    from scipy import sparse
+    a = agg.astype(np.int64)[np.asarray(vert_c, dtype=np.int64)]          # [E, 4]
+    a[a == 0xFFFFFFFF] = -1
+    rows = np.repeat(a, 4, axis=1).ravel()
+    cols = np.tile(a, (1, 4)).ravel()
+    vals = np.asarray(Ace, dtype=np.float64).reshape(-1)
+    ok = (rows >= 0) & (cols >= 0)
+    A3 = sparse.coo_matrix((vals[ok], (rows[ok], cols[ok])), shape=(n_agg, n_agg)).toarray()
+    A3 = 0.5 * (A3 + A3.T)
+    inv = np.linalg.inv(A3)
+    if not np.isfinite(inv).all():
+        raise AssertionError("the aggregated coarse operator is singular")
+    return np.ascontiguousarray(0.5 * (inv + inv.T))

@@ -53,6 +53,9 @@ def test_struct_layout_matches_header(tmp_path):
     co_fields = [f[0] for f in _lib.semk_sc_coarse._fields_]
     src += ['  printf("%zu\\n", sizeof(struct semk_sc_coarse));']
     src += ['  printf("%%zu\\n", offsetof(struct semk_sc_coarse, %s));' % f for f in co_fields]
+    top_fields = [f[0] for f in _lib.semk_sc_top._fields_]
+    src += ['  printf("%zu\\n", sizeof(struct semk_sc_top));']
+    src += ['  printf("%%zu\\n", offsetof(struct semk_sc_top, %s));' % f for f in top_fields]
     src += ['  return 0; }']
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -72,6 +75,10 @@ def test_struct_layout_matches_header(tmp_path):
     assert int(rest[0]) == ctypes.sizeof(_lib.semk_sc_coarse)
     for f, off in zip(co_fields, rest[1:]):
         assert getattr(_lib.semk_sc_coarse, f).offset == int(off), f
+    rest = rest[1 + len(co_fields):]
+    assert int(rest[0]) == ctypes.sizeof(_lib.semk_sc_top)
+    for f, off in zip(top_fields, rest[1:]):
+        assert getattr(_lib.semk_sc_top, f).offset == int(off), f
 
 
 def _plan(nx, ny, p, pe, order=None, dirichlet=None):

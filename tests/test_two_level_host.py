@@ -6,7 +6,8 @@ import pytest
 
 import sem_oracle as so
 from conftest import load_case, rel_l2
-from spectralelementmethod_b200.condensed import coarse_tables, condensed_tables
+from spectralelementmethod_b200.condensed import (aggregate_tables, coarse_tables, condensed_tables,
+                                                   element_tiles, top_level_inverse)
 
 
 def _pcg(apply, b, M, rtol, x0=None, maxiter=100000):
@@ -28,7 +29,7 @@ def _pcg(apply, b, M, rtol, x0=None, maxiter=100000):
     return x, it
 
 
-def emulate(p, c, on, vals, gll):
+def emulate(p, c, on, vals, gll, tile=None, extra=None):
     """The device algorithm in NumPy on the product's host tables; returns
     (x_jacobi, its_jacobi, x_two_level, its_two_level, tables, Ace)."""
     N, NE = p + 1, 4 * p
@@ -69,8 +70,11 @@ def emulate(p, c, on, vals, gll):
     sdiag = np.add.reduceat(np.einsum("ekk->ek", S_e).ravel()[npos], nptr[:-1])
     dinv = 1.0 / np.where(D, 1.0, sdiag)
 
+    inner2 = []
+
     def two_level(r):
-        xc, _ = _pcg(coarse, restrict(r), lambda q: q / dc, 1e-2)
+        xc, itc = _pcg(coarse, restrict(r), lambda q: q / dc, 1e-2)
+        inner2.append(itc)
         return dinv * r + prolong(xc)
     gv = np.where(D, vals[:n_ext], 0.0)
     yl = np.einsum("ekj,ej->ek", S_e, gv[ids]).ravel()
@@ -79,6 +83,27 @@ def emulate(p, c, on, vals, gll):
     x0 = np.where(D, b, 0.0)
     xj, itj = _pcg(fine, b, lambda r: dinv * r, 1e-12, x0)
     x2, it2 = _pcg(fine, b, two_level, 1e-12, x0)
+    if tile is not None:
+        # third level: Jacobi + aggregation with a dense inverse inside the coarse solve
+        at = aggregate_tables(ct["vert_c"], ct["vptr"], ct["vpos"], Dc, tile)
+        A3inv = top_level_inverse(Ace, ct["vert_c"], at["agg"], at["n_agg"])
+        agg = at["agg"].astype(np.int64)
+        valid = agg != 0xFFFFFFFF
+        aptr, aidx = at["aptr"].astype(np.int64), at["aidx"].astype(np.int64)
+        inner3 = []
+
+        def coarse_precond(q):
+            y3 = A3inv @ np.add.reduceat(q[aidx], aptr[:-1])
+            z = q / dc
+            z[valid] += y3[agg[valid]]
+            return z
+
+        def three_level(r):
+            xc, itc = _pcg(coarse, restrict(r), coarse_precond, 1e-2)
+            inner3.append(itc)
+            return dinv * r + prolong(xc)
+        x3, it3 = _pcg(fine, b, three_level, 1e-12, x0)
+        extra.update(x3=x3, it3=it3, inner3=sum(inner3), inner2=sum(inner2), at=at, A3inv=A3inv)
     return xj, itj, x2, it2, ct, Ace, (restrict, prolong)
 
 
@@ -163,3 +188,29 @@ def test_two_level_emulation_on_irregular_vertex_valence(n_cells, rings):
     assert ct["n_v"] == np.unique(c["ids"][:, :4]).size
     assert n_cells in np.diff(ct["vptr"].astype(np.int64))           # the centre vertex
     assert rel_l2(x2, xj) < 1e-10 and it2 <= itj
+
+
+def test_three_level_emulation_cuts_the_inner_iterations():
+    """Aggregation level under the vertex coarse space (condensed.element_tiles /
+    aggregate_tables / top_level_inverse): same outer count and solution, far fewer inner
+    iterations.  NumPy emulation of semk_sc_pcg3_solve_f64 on the product's host tables."""
+    p, n = 4, 24
+    basis = so.Basis(p)
+    nodes, l2g = so.build_case("C", n, n, p, True, False)
+    geo = so.geometry(basis, nodes, l2g)
+    c = so.condensed_system(p, geo["invJ"], geo["JxW"], l2g)
+    on, vals = so.dirichlet_data(nodes, l2g, geo["x_phys"], so.mesh_boundary_faces(n, n))
+
+    class M(object):                      # what element_tiles reads from a mesh
+        _structured_shape = (n, n)
+    tile = element_tiles(M(), n * n, max_tiles=36)           # 4 x 4 element tiles
+    assert np.unique(tile).size == 36
+    extra = {}
+    xj, itj, x2, it2, ct, Ace, _ = emulate(p, c, on, vals, basis.nodes, tile=tile, extra=extra)
+    at = extra["at"]
+    free = ~ct["dirichlet_c"]
+    assert (at["agg"][~free] == 0xFFFFFFFF).all() and (at["agg"][free] < at["n_agg"]).all()
+    assert at["aptr"][-1] == free.sum() and np.array_equal(np.sort(at["aidx"]), np.flatnonzero(free))
+    assert np.allclose(extra["A3inv"], extra["A3inv"].T)
+    assert abs(extra["it3"] - it2) <= 2 and extra["inner3"] * 2 < extra["inner2"]
+    assert rel_l2(extra["x3"], x2) < 1e-10

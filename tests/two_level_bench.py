@@ -1,6 +1,9 @@
 """Time to solution of the two-level preconditioned condensed PCG at config 2 (GPU box):
 
-    python tests/two_level_bench.py [nx] [order] [inner_rtol]
+    python tests/two_level_bench.py [nx] [order] [inner_rtol] [two-level|three-level]
+
+("three-level" = the experimental aggregation level under the vertex coarse space; it is
+compared with the two-level solution in the same run.)
 """
 import os
 import sys
@@ -19,6 +22,7 @@ def main():
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     p = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     inner_rtol = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-2
+    which = sys.argv[4] if len(sys.argv) > 4 else "two-level"
     mesh = meshgen.structured_quad_mesh(nx, nx, p, "S")
     b1 = LagrangeGaussLobatto(p)
     mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
@@ -41,6 +45,22 @@ def main():
                  info.converged, info.rel_residual), flush=True)
     u = sc.backsolve(x, 1.0)
     print("checksum %.15g" % float(u.sum()), flush=True)
+    if which == "three-level":
+        t0 = time.perf_counter()
+        sc._build_top()
+        torch.cuda.synchronize()
+        t_top = time.perf_counter() - t0
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            x3, info3 = sc.solve_pcg(b, rtol=1e-12, preconditioner="three-level",
+                                     inner_rtol=inner_rtol)
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            print("three-level: top build %.2f s; solve %.3f s, %d outer its, %d inner its, "
+                  "converged %s, rel residual %.2e, diff to two-level %.2e"
+                  % (t_top, el, info3.iterations, sc.last_inner_iterations, info3.converged,
+                     info3.rel_residual, float((x3 - x).norm() / x.norm())), flush=True)
 
 
 if __name__ == "__main__":
