@@ -61,6 +61,12 @@ def parse():
                     help="polynomial order (exploration only: the metric is quoted at p = 8)")
     ap.add_argument("--pe", type=int, default=0, help="elements per patch (0 = automatic)")
     ap.add_argument("--tile", default="", help="patch tile shape bx,by (elements), e.g. 2,8")
+    ap.add_argument("--sweep", default="",
+                    help="order sweep on the curved mesh (BASELINE configs[2]): comma list of "
+                         "orders, e.g. 4,6,8,10,12,16; prints one JSON object and writes "
+                         "gpurun_out/r02_sweep.json")
+    ap.add_argument("--sweep-tag", default="", help="suffix of the sweep's output file")
+    ap.add_argument("--ho-mode", default="", help="apply-kernel variant passed to poisson_operator")
     ap.add_argument("--ablate", type=int, default=0,
                     help="internal profiling knob: extra apply flag bits (results are wrong)")
     args = ap.parse_args()
@@ -355,6 +361,72 @@ def run_condensed(args, nx, dev, peak):
     return res
 
 
+SWEEP_NX = {2: 2048, 3: 1536, 4: 1024, 5: 1024, 6: 1024, 7: 1024, 8: 1024, 9: 896, 10: 768,
+            11: 704, 12: 640, 13: 576, 14: 576, 15: 512, 16: 512}
+
+
+def sweep_bytes_per_dof(p):
+    """B(p) = 16 + 28 ((p+1)/p)^2 algorithmic bytes per global DOF per apply."""
+    return 16.0 + 28.0 * ((p + 1.0) / p) ** 2
+
+
+def run_sweep(args):
+    """BASELINE configs[2]: the apply at orders p = 4..16 on the curved (mapped) mesh, one
+    GPU; per order the mesh size keeps ~50-70 M DOF.  One JSON object with a row per order."""
+    import numpy as np
+    import torch
+    from spectralelementmethod_b200 import discrete, meshgen
+    from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    peak, peak_kind = measured_peaks()
+    rows = []
+    for p in [int(v) for v in args.sweep.split(",") if v]:
+        nx = args.nx or SWEEP_NX[p]
+        mesh = meshgen.structured_quad_mesh(nx, nx, p, "C")
+        b1 = LagrangeGaussLobatto(p)
+        mngr = discrete.DOFManager(mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
+        on_ebc = mngr.boundary_node_mask("ebc")
+        kw = {}
+        if args.ho_mode:
+            kw["mode"] = args.ho_mode
+        op = mngr.poisson_operator(dirichlet=on_ebc, elems_per_patch=args.pe or None, **kw)
+        x, y = mesh.nodes
+        u = torch.from_numpy(np.sin(3 * x) * np.cos(2 * y)).to(dev)
+        out = torch.empty_like(u)
+        for _ in range(max(args.warmup, 3)):
+            op.apply(u, out=out)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            op.apply(u, out=out)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = ev0.elapsed_time(ev1) / 1e3 / args.steps
+        alg = op.algorithmic_bytes_per_apply
+        rows.append({"order": p, "elements": "%dx%d" % (nx, nx), "dof": int(op.n_nodes),
+                     "kernel": getattr(op, "kernel_name", None),
+                     "elems_per_patch": op.elems_per_patch,
+                     "resident_ctas": getattr(op, "resident_ctas", None),
+                     "smem_bytes_per_cta": getattr(op, "smem_bytes", None),
+                     "ms_per_apply": t * 1e3, "gdof_per_s": op.n_nodes / t / 1e9,
+                     "algorithmic_bytes": alg, "achieved_GBps": alg / t / 1e9,
+                     "frac_of_hbm_peak": alg / t / 1e9 / peak,
+                     "checksum": float(out.double().sum())})
+        print("sweep p=%d: %.3f ms, %.1f GDOF/s, %.1f %% of peak" %
+              (p, t * 1e3, op.n_nodes / t / 1e9, 100 * alg / t / 1e9 / peak), file=sys.stderr,
+              flush=True)
+        del op, mngr, mesh, u, out
+        torch.cuda.empty_cache()
+    res = {"sweep": "Poisson apply, curved mesh (kind C), FP64, one B200", "steps": args.steps,
+           "peak_GBps": peak, "peak_source": peak_kind, "rows": rows}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "r02_sweep%s.json" % args.sweep_tag), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res), flush=True)
+
+
 def run_engine(args):
     import numpy as np
     import torch
@@ -621,6 +693,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.sweep:
+        run_sweep(args)
     else:
         run_engine(args)
 

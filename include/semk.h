@@ -536,7 +536,9 @@ int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const
  * inverse at the top, so that the inner iteration count is mesh-independent as well
  * (oracle/precond_study_three_level.py).  agg: device uint32 [n_v], aggregate of every
  * vertex (0xffffffff = none: essential boundary); aptr / aidx: CSR of the vertices of
- * every aggregate; A3inv: device [n_agg][n_agg], inverse of P2^T Ac P2, row major. */
+ * every aggregate that this rank OWNS (one GPU: all of them); A3inv: device
+ * [n_agg][n_agg], inverse of P2^T Ac P2, row major.  On several GPUs the aggregate ids
+ * are global and A3inv is replicated. */
 typedef struct semk_sc_top {
   int64_t n_agg;
   const uint32_t *agg;
@@ -544,13 +546,94 @@ typedef struct semk_sc_top {
   const uint32_t *aidx;
   const double *A3inv;
 } semk_sc_top;
-/* As semk_sc_pcg2_solve_f64 with the three-level preconditioner.  work_c: device
- * [6 * (n_v + 32) + 2 * (n_agg + 32)].  Both loops are host-driven. */
-int semk_sc_pcg3_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const semk_sc_top *top,
-                           const double *b, double *x, const double *dinv, const double *dinv_c,
-                           double *work, double *work_c, double *sc, double *vec_partials,
-                           double rtol, int maxiter, double inner_rtol, int inner_maxiter,
-                           semk_pcg_info *info, int64_t *inner_total, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Small-vector all-reduce over NVLink peer memory (no reference equivalent:
+ * the reference is single-process; SURVEY.md 8(e) names the inner products of
+ * the Krylov solver as the second exchange of the partitioned path).  Every
+ * rank owns one REGION, exported through CUDA IPC (semk_peer_alloc /
+ * semk_peer_open) and mapped by every other rank:
+ *   bytes [0, 8)     : uint64 call counter (epoch), advanced by the kernel itself, so
+ *                      launches can be captured in a CUDA graph;
+ *   bytes [64, 128)  : uint64 flag[8] -- flag[s] = last epoch published by rank s;
+ *   bytes [256, ...) : double recv[2][world][capacity] (double-buffered by epoch parity).
+ * One single-CTA kernel per all-reduce: push my vector into every rank's recv slot,
+ * publish the epoch (system-scope release), wait for every rank's flag (acquire), sum
+ * the world slots IN RANK ORDER -- the result is bit-identical on all ranks.
+ * ------------------------------------------------------------------------ */
+#define SEMK_COMM_MAX_WORLD 8
+typedef struct semk_comm {
+  int32_t rank, world;
+  int64_t capacity;                      /* doubles per all-reduce */
+  void *regions[SEMK_COMM_MAX_WORLD];    /* regions[r]: rank r's region (regions[rank] = own) */
+  int32_t *status;                       /* device int, set to 1 when a rank did not show up
+                                            within ~2 s (the kernel gives up instead of hanging) */
+} semk_comm;
+int64_t semk_comm_region_bytes(int32_t world, int64_t capacity);
+/* buf[0, n) <- sum over ranks, in place; n <= capacity; every rank must make the same
+ * sequence of calls.  world == 1: no-op. */
+int semk_comm_allreduce_f64(const semk_comm *comm, double *buf, int64_t n, void *stream);
+
+/* One side-pair of interface columns of a strip partition (semk_halo_exchange_f64) as a
+ * struct, so that a native driver can issue exchanges itself: `epoch` is the last epoch
+ * used and is advanced by whoever issues an exchange (host side, SPMD). */
+typedef struct semk_halo {
+  int64_t n_col;
+  void *mine, *left, *right;            /* regions: own, left / right neighbour (or NULL) */
+  uint64_t epoch;
+  int32_t *status;                      /* device int */
+} semk_halo;
+
+/* How the multilevel solver below is spread over the ranks of a strip partition
+ * (NULL or comm == NULL: one GPU).  Owned DOFs are a prefix on both levels (the right
+ * neighbour owns a shared column): dot products and restrictions run over the owned
+ * prefix and are summed with semk_comm_allreduce_f64; operator applies are followed by
+ * the interface exchange of their level. */
+typedef struct semk_ml_dist {
+  const semk_comm *comm;
+  semk_halo *halo_f;                    /* exterior (fine) vectors */
+  semk_halo *halo_c;                    /* vertex (coarse) vectors */
+  int64_t n_owned_f, n_owned_c;
+} semk_ml_dist;
+
+typedef struct semk_ml_opts {
+  double rtol;                          /* outer: recursive ||r|| <= rtol ||b|| */
+  double inner_rtol;                    /* inner coarse solves */
+  int32_t maxiter, inner_maxiter;
+  int32_t levels;                       /* 2: Jacobi inside the coarse solve; 3: + aggregation */
+  int32_t flexible;                     /* 1: flexible CG (Polak-Ribiere beta), the inner solve
+                                           makes the preconditioner vary from step to step */
+  int32_t inner_chunk;                  /* inner iterations queued between two polls (>= 1) */
+  int32_t reserved;
+} semk_ml_opts;
+
+typedef struct semk_ml_info {
+  int32_t iterations;                   /* outer */
+  int32_t status;                       /* 0 converged, 1 maxiter, SEMK_ERR_BREAKDOWN */
+  double rel_residual;                  /* recursive ||r|| / ||b|| at exit */
+  double true_rel_residual;             /* ||b - Shat x|| / ||b|| recomputed at exit */
+  double bnorm;
+  int64_t inner_iterations;             /* summed over the inner solves */
+  int32_t inner_solves;
+  int32_t reserved;
+} semk_ml_info;
+
+/* Multilevel-preconditioned (flexible) CG on Shat x = b, one entry point for one GPU
+ * and for a strip partition:
+ *     M^{-1} r = dinv r + P xc,   xc ~= Ac^{-1} P^T r  by an inner PCG on the vertex
+ *     coarse operator, itself preconditioned by dinv_c (levels = 2) or by
+ *     dinv_c + P2 A3inv P2^T (levels = 3, `top` required).
+ * The inner iteration keeps its scalars on the device (alpha, beta, convergence and
+ * breakdown flags are produced by single-CTA kernels that also carry the all-reduce),
+ * is queued `inner_chunk` iterations at a time and polled through one 128-byte copy.
+ * work: device [4 * (n_ext + 32)]; work_c: device [6 * (n_v + 32) + 2 * (n_agg + 32)];
+ * sc: device [64]; vec_partials as in semk_pcg_solve_f64.  dinv / dinv_c: inverse
+ * diagonals of the GLOBAL operators (interface entries already summed). */
+int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const semk_sc_top *top,
+                            const semk_ml_dist *dist, const double *b, double *x,
+                            const double *dinv, const double *dinv_c, double *work,
+                            double *work_c, double *sc, double *vec_partials,
+                            const semk_ml_opts *opts, semk_ml_info *info, void *stream);
 
 /* The pieces of the two-level preconditioner as separate entry points, for the
  * multi-GPU outer loop (driven from the host so that the interface exchanges and

@@ -5,17 +5,25 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3"
 OBJS=""
-for f in semk_api.cu semk_geom.cu semk_apply.cu semk_vec.cu semk_peer.cu semk_sc.cu semk_field.cu; do
+PIDS=""
+for f in semk_api.cu semk_geom.cu semk_apply.cu semk_vec.cu semk_peer.cu semk_sc.cu semk_field.cu semk_ml.cu semk_ho.cu semk_locate.cu semk_stokes.cu; do
+  [ -f "$f" ] || continue
   o="${f%.cu}.o"
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ semk_common.cuh -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
+    rm -f "$o"      # a failed compile must not leave a stale, linkable object behind
     $NVCC $FLAGS ${SEMK_EXTRA_FLAGS:-} ${SEMK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
+    PIDS="$PIDS $!"
   fi
   OBJS="$OBJS $o"
 done
 o=semk_hostplan.o
 if [ ! -f "$o" ] || [ semk_hostplan.cpp -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
+  rm -f "$o"
   g++ -O3 -std=c++17 -fPIC -c semk_hostplan.cpp -o "$o" &
+  PIDS="$PIDS $!"
 fi
-wait
+for pid in $PIDS; do
+  wait "$pid" || { echo "build.sh: a compile job failed" >&2; exit 1; }
+done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libsemk.so $OBJS semk_hostplan.o
 echo "built $(pwd)/libsemk.so"

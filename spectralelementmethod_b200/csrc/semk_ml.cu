@@ -1,0 +1,662 @@
+// semk_ml.cu -- multilevel-preconditioned CG on the condensed system, one driver for one
+// GPU and for a strip partition, and the small-vector all-reduce over NVLink peer memory
+// it needs between ranks.
+//
+// What it replaces: the reference solves the condensed (Schur-complement) system over the
+// element-exterior DOFs directly, `spsolve` at sem/discrete.py:502-511, then back-
+// substitutes the interiors (:513-524).  Here the same system is solved iteratively:
+//     outer : (flexible) CG on Shat x = b
+//     M^-1 r = dinv r + P xc,   xc ~= Ac^-1 P^T r        vertex coarse space, inner PCG
+//     inner preconditioner = dinv_c (+ P2 A3inv P2^T, aggregation with a dense inverse)
+// Design (B200-first): every inner iteration is a handful of small kernels whose scalars
+// (alpha, beta, convergence / breakdown flags) never leave the device.  The scalar logic
+// lives in single-CTA "scalar step" kernels which also carry the cross-rank all-reduce:
+// push to every peer's region over NVLink, publish an epoch, wait, sum in rank order.
+// Vector kernels only READ scalars and write per-CTA partial sums, so there is no
+// read/update race on the scalar block and the host only polls it every few iterations.
+#include "semk_common.cuh"
+
+namespace {
+
+constexpr int kT = 256;                 // vector kernels
+constexpr int kMaxBlocks = kSemkRedMaxBlocks;
+constexpr int kStepThreads = 1024;      // scalar-step / all-reduce kernel (one CTA)
+constexpr long long kSpinLimit = 4000000000LL;  // ~2 s of SM clock
+
+inline int blocks_for(int64_t n) {
+  const int64_t want = (n + kT * 4 - 1) / (kT * 4);
+  return (int)(want < 1 ? 1 : (want < kMaxBlocks ? want : kMaxBlocks));
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- scalar block of one PCG level (device doubles) ------------------------------------
+enum {
+  S_RZ = 0,      // r.z of the current direction
+  S_PAP = 1,     // p.Ap (this rank's share until the ALPHA step has run)
+  S_RZN = 2,     // new r.z          } contiguous: reduced together
+  S_ZAP = 3,     // z.Ap (flexible)  }
+  S_RR = 4,      // r.r
+  S_BB = 5,      // b.b
+  S_ALPHA = 6,
+  S_BETA = 7,
+  S_ITER = 8,
+  S_CONV = 9,    // 1 = converged: x is final, later kernels of the chunk do nothing
+  S_BREAK = 10,  // 1 = p.Ap <= 0 or non-finite
+  S_TOL2 = 11,
+  S_LEN = 16
+};
+
+enum { OP_NONE = 0, OP_ALPHA = 1, OP_RR = 2, OP_RR_FIRST = 3, OP_BETA = 4, OP_BETA_FIRST = 5 };
+
+struct CommDev {
+  int rank, world;
+  long long capacity;
+  char *regions[SEMK_COMM_MAX_WORLD];
+  int *status;
+};
+
+__device__ __forceinline__ unsigned long long *region_epoch(char *r) {
+  return reinterpret_cast<unsigned long long *>(r);
+}
+__device__ __forceinline__ unsigned long long *region_flags(char *r) {
+  return reinterpret_cast<unsigned long long *>(r + 64);
+}
+__device__ __forceinline__ double *region_recv(char *r, int parity, int src, long long cap,
+                                               int world) {
+  return reinterpret_cast<double *>(r + 256) + ((long long)parity * world + src) * cap;
+}
+
+// All-reduce buf[0, n) over the ranks (one CTA; all threads call).  Returns false after a
+// time-out (status word raised); buf is then left unreduced.
+__device__ bool comm_allreduce(const CommDev &c, double *buf, int n) {
+  if (c.world <= 1) return true;
+  __shared__ int timed_out;
+  char *mine = c.regions[c.rank];
+  const unsigned long long epoch = *region_epoch(mine) + 1ull;   // same value for all threads
+  const int par = (int)(epoch & 1ull);
+  __syncthreads();                                               // everyone has read the epoch
+  for (int w = 0; w < c.world; ++w) {
+    double *dst = region_recv(c.regions[w], par, c.rank, c.capacity, c.world);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < c.world) {
+    st_release_sys_u64(region_flags(c.regions[threadIdx.x]) + c.rank, epoch);
+    const unsigned long long *f = region_flags(mine) + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(f) < epoch) {
+      if (clock64() - t0 > kSpinLimit) {
+        timed_out = 1;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0) {
+      atomicExch(c.status, 1);
+      *region_epoch(mine) = epoch;
+    }
+    return false;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < c.world; ++w)
+      s += __ldcg(region_recv(mine, par, w, c.capacity, c.world) + i);   // fixed rank order
+    buf[i] = s;
+  }
+  if (threadIdx.x == 0) *region_epoch(mine) = epoch;
+  __syncthreads();
+  return true;
+}
+
+// One scalar step: all-reduce `buf[0, n)` in place, then update the scalar block.
+//   OP_ALPHA      buf = s + S_PAP (1): alpha = rz / pAp, breakdown test
+//   OP_RR[_FIRST] buf ends with r.r at buf[n - 1]: s[S_RR] = it; FIRST also sets b.b = r.r
+//                 (inner solves start from x = 0, so r = b); convergence test
+//                 (and ++iterations unless FIRST)
+//   OP_BETA[_FIRST] buf = s + S_RZN (2): beta (flexible or standard), rz <- rz_new
+__global__ void __launch_bounds__(kStepThreads)
+    ml_step_kernel(CommDev c, double *__restrict__ buf, int n, int op, int flexible,
+                   double *__restrict__ s) {
+  const bool ok = comm_allreduce(c, buf, n);
+  if (threadIdx.x != 0) return;
+  if (!ok) {
+    s[S_BREAK] = 2.0;
+    return;
+  }
+  if (s[S_CONV] != 0.0 || s[S_BREAK] != 0.0) return;   // frozen
+  switch (op) {
+    case OP_ALPHA: {
+      const double pAp = s[S_PAP], rz = s[S_RZ];
+      if (!(pAp > 0.0) || !(rz == rz)) {
+        s[S_BREAK] = 1.0;
+        s[S_ALPHA] = 0.0;
+      } else {
+        s[S_ALPHA] = rz / pAp;
+      }
+      break;
+    }
+    case OP_RR:
+    case OP_RR_FIRST: {
+      const double rr = buf[n - 1];
+      s[S_RR] = rr;
+      if (op == OP_RR_FIRST)
+        s[S_BB] = rr;
+      else
+        s[S_ITER] += 1.0;   // one more completed update of x
+      if (rr <= s[S_TOL2] * s[S_BB]) s[S_CONV] = 1.0;
+      break;
+    }
+    case OP_BETA:
+    case OP_BETA_FIRST: {
+      const double rzn = s[S_RZN];
+      if (op == OP_BETA_FIRST) {
+        s[S_BETA] = 0.0;
+      } else {
+        const double rz = s[S_RZ];
+        s[S_BETA] = (rz != 0.0) ? (flexible ? -s[S_ALPHA] * s[S_ZAP] / rz : rzn / rz) : 0.0;
+      }
+      s[S_RZ] = rzn;
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+__global__ void __launch_bounds__(kStepThreads)
+    allreduce_kernel(CommDev c, double *__restrict__ buf, int n) {
+  (void)comm_allreduce(c, buf, n);
+}
+
+// x += alpha p ; r -= alpha Ap ; z = dinv r ; rr_out = sum_{i < n_dot} r_i^2 (this rank)
+__global__ void __launch_bounds__(kT)
+    ml_update_kernel(int64_t n, int64_t n_dot, const double *__restrict__ p,
+                     const double *__restrict__ Ap, const double *__restrict__ dinv,
+                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+                     const double *__restrict__ s, double *__restrict__ rr_out,
+                     double *__restrict__ partials) {
+  const bool frozen = s[S_CONV] != 0.0 || s[S_BREAK] != 0.0;
+  const double alpha = s[S_ALPHA];
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double ri = r[i];
+    if (!frozen) {
+      x[i] = fma(alpha, p[i], x[i]);
+      ri = fma(-alpha, Ap[i], ri);
+      r[i] = ri;
+    }
+    z[i] = dinv[i] * ri;
+    if (i < n_dot) acc[0] = fma(ri, ri, acc[0]);
+  }
+  double tot[1];
+  if (semk_finish_reduction<1>(acc, partials, tot) && threadIdx.x == 0) rr_out[0] = tot[0];
+}
+
+// z = dinv r ; rr_out = sum_{i < n_dot} r_i^2   (first step of a solve: no direction yet)
+__global__ void __launch_bounds__(kT)
+    ml_first_kernel(int64_t n, int64_t n_dot, const double *__restrict__ dinv,
+                    const double *__restrict__ r, double *__restrict__ z,
+                    double *__restrict__ rr_out, double *__restrict__ partials) {
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i];
+    z[i] = dinv[i] * ri;
+    if (i < n_dot) acc[0] = fma(ri, ri, acc[0]);
+  }
+  double tot[1];
+  if (semk_finish_reduction<1>(acc, partials, tot) && threadIdx.x == 0) rr_out[0] = tot[0];
+}
+
+// (optional) z[v] += y3[agg[v]] ; out2 = { r.z, z.Ap } over the owned prefix
+__global__ void __launch_bounds__(kT)
+    ml_correct_dot_kernel(int64_t n, int64_t n_dot, const uint32_t *__restrict__ agg,
+                          const double *__restrict__ y3, const double *__restrict__ r,
+                          const double *__restrict__ Ap, double *__restrict__ z,
+                          double *__restrict__ out2, double *__restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double zi = z[i];
+    if (agg) {
+      const uint32_t a = agg[i];
+      if (a != 0xffffffffu) {
+        zi += y3[a];
+        z[i] = zi;
+      }
+    }
+    if (i < n_dot) {
+      acc[0] = fma(r[i], zi, acc[0]);
+      if (Ap) acc[1] = fma(zi, Ap[i], acc[1]);
+    }
+  }
+  double tot[2];
+  if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
+    out2[0] = tot[0];
+    out2[1] = tot[1];
+  }
+}
+
+// z += P xc (at most two vertices per fine node) ; out2 = { r.z, z.Ap } over the owned prefix
+__global__ void __launch_bounds__(kT)
+    ml_prolong_dot_kernel(int64_t n, int64_t n_dot, const uint32_t *__restrict__ pv,
+                          const double *__restrict__ pw, const double *__restrict__ xc,
+                          const double *__restrict__ r, const double *__restrict__ Ap,
+                          double *__restrict__ z, double *__restrict__ out2,
+                          double *__restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double wa = pw[2 * i], wb = pw[2 * i + 1];
+    double zi = z[i];
+    if (wa != 0.0) zi = fma(wa, xc[pv[2 * i]], zi);
+    if (wb != 0.0) zi = fma(wb, xc[pv[2 * i + 1]], zi);
+    z[i] = zi;
+    if (i < n_dot) {
+      acc[0] = fma(r[i], zi, acc[0]);
+      if (Ap) acc[1] = fma(zi, Ap[i], acc[1]);
+    }
+  }
+  double tot[2];
+  if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
+    out2[0] = tot[0];
+    out2[1] = tot[1];
+  }
+}
+
+// p = z + beta p  (frozen: nothing)
+__global__ void __launch_bounds__(kT)
+    ml_direction_kernel(int64_t n, const double *__restrict__ z, double *__restrict__ p,
+                        const double *__restrict__ s) {
+  if (s[S_CONV] != 0.0 || s[S_BREAK] != 0.0) return;
+  const double beta = s[S_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+}
+
+// rc = P^T r over the owned fine nodes: one thread per coarse row, fixed order
+__global__ void __launch_bounds__(kT)
+    ml_restrict_kernel(int64_t n_v, const uint32_t *__restrict__ rptr,
+                       const uint32_t *__restrict__ ridx, const double *__restrict__ rw,
+                       const double *__restrict__ r, int64_t n_owned, double *__restrict__ rc) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_v;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (uint32_t q = rptr[v]; q < rptr[v + 1]; ++q) {
+      const uint32_t g = ridx[q];
+      if ((int64_t)g < n_owned) s = fma(rw[q], r[g], s);
+    }
+    rc[v] = s;
+  }
+}
+
+// r3[a] = sum of q over the (owned) vertices of aggregate a: one warp per aggregate
+__global__ void __launch_bounds__(kT)
+    ml_agg_restrict_kernel(int64_t n_agg, const uint32_t *__restrict__ aptr,
+                           const uint32_t *__restrict__ aidx, const double *__restrict__ q,
+                           double *__restrict__ r3) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t a = warp; a < n_agg; a += nwarps) {
+    double s = 0.0;
+    for (uint32_t k = aptr[a] + lane; k < aptr[a + 1]; k += 32) s += q[aidx[k]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) r3[a] = s;
+  }
+}
+
+// y = A x, A dense [n][n] row major: one warp per row, 128-bit loads when n is even
+__global__ void __launch_bounds__(kT)
+    ml_dense_matvec_kernel(int64_t n, const double *__restrict__ A, const double *__restrict__ x,
+                           double *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const double *row = A + i * n;
+    double s0 = 0.0, s1 = 0.0;
+    if ((n & 1) == 0) {
+      const double2 *row2 = reinterpret_cast<const double2 *>(row);
+      const double2 *x2 = reinterpret_cast<const double2 *>(x);
+      for (int64_t j = lane; j < (n >> 1); j += 32) {
+        const double2 a = row2[j], b = x2[j];
+        s0 = fma(a.x, b.x, s0);
+        s1 = fma(a.y, b.y, s1);
+      }
+    } else {
+      for (int64_t j = lane; j < n; j += 32) s0 = fma(row[j], x[j], s0);
+    }
+    double s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+    ml_resid_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ Ax,
+                    const uint8_t *__restrict__ dirichlet, double *__restrict__ r,
+                    int64_t n_dot, double *__restrict__ out2, double *__restrict__ partials) {
+  // r = b - Ax (0 on Dirichlet rows) ; out2 = { r.r, b.b } over the owned prefix (masked b)
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool fixed = dirichlet && dirichlet[i];
+    const double bi = fixed ? 0.0 : b[i];
+    const double ri = fixed ? 0.0 : bi - Ax[i];
+    r[i] = ri;
+    if (i < n_dot) {
+      acc[0] = fma(ri, ri, acc[0]);
+      acc[1] = fma(bi, bi, acc[1]);
+    }
+  }
+  double tot[2];
+  if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
+    out2[0] = tot[0];
+    out2[1] = tot[1];
+  }
+}
+
+CommDev make_comm(const semk_comm *c) {
+  CommDev d{};
+  d.world = 1;
+  if (c) {
+    d.rank = c->rank;
+    d.world = c->world;
+    d.capacity = c->capacity;
+    for (int w = 0; w < SEMK_COMM_MAX_WORLD; ++w) d.regions[w] = static_cast<char *>(c->regions[w]);
+    d.status = c->status;
+  }
+  return d;
+}
+
+int check_comm(const semk_comm *c, const char *who) {
+  if (!c) return SEMK_OK;
+  if (c->world < 1 || c->world > SEMK_COMM_MAX_WORLD || c->rank < 0 || c->rank >= c->world ||
+      c->capacity < 1 || !c->status) {
+    semk_set_error(std::string(who) + ": inconsistent semk_comm");
+    return SEMK_ERR_INVALID;
+  }
+  for (int w = 0; w < c->world; ++w)
+    if (!c->regions[w]) {
+      semk_set_error(std::string(who) + ": semk_comm with an unmapped region");
+      return SEMK_ERR_INVALID;
+    }
+  return SEMK_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t semk_comm_region_bytes(int32_t world, int64_t capacity) {
+  if (world < 1 || world > SEMK_COMM_MAX_WORLD || capacity < 1) return -1;
+  return 256 + 2 * (int64_t)world * capacity * (int64_t)sizeof(double);
+}
+
+extern "C" int semk_comm_allreduce_f64(const semk_comm *comm, double *buf, int64_t n,
+                                       void *stream) {
+  SEMK_REQUIRE(comm && buf && n > 0, "semk_comm_allreduce_f64: bad argument");
+  int rc = check_comm(comm, "semk_comm_allreduce_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(n <= comm->capacity, "semk_comm_allreduce_f64: n exceeds the region capacity");
+  if (comm->world == 1) return SEMK_OK;
+  allreduce_kernel<<<1, kStepThreads, 0, semk_stream(stream)>>>(make_comm(comm), buf, (int)n);
+  SEMK_LAUNCH_CHECK("allreduce_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs,
+                                       const semk_sc_top *top, const semk_ml_dist *dist,
+                                       const double *b, double *x, const double *dinv,
+                                       const double *dinv_c, double *work, double *work_c,
+                                       double *sc, double *vec_partials,
+                                       const semk_ml_opts *opts, semk_ml_info *info,
+                                       void *stream) {
+  SEMK_REQUIRE(op && cs && b && x && dinv && dinv_c && work && work_c && sc && vec_partials &&
+                   opts && info,
+               "semk_sc_mlpcg_solve_f64: null pointer");
+  SEMK_REQUIRE(opts->maxiter >= 0 && opts->inner_maxiter >= 1 && opts->rtol >= 0.0 &&
+                   opts->inner_rtol > 0.0 && (opts->levels == 2 || opts->levels == 3) &&
+                   opts->inner_chunk >= 1,
+               "semk_sc_mlpcg_solve_f64: bad control");
+  SEMK_REQUIRE(cs->pv && cs->pw && cs->rptr && cs->ridx && cs->rw,
+               "semk_sc_mlpcg_solve_f64: missing transfer tables");
+  const bool three = opts->levels == 3;
+  if (three)
+    SEMK_REQUIRE(top && top->n_agg > 0 && top->agg && top->aptr && top->aidx && top->A3inv,
+                 "semk_sc_mlpcg_solve_f64: levels = 3 needs a consistent semk_sc_top");
+  const semk_comm *comm = dist ? dist->comm : nullptr;
+  int rcode = check_comm(comm, "semk_sc_mlpcg_solve_f64");
+  if (rcode != SEMK_OK) return rcode;
+  const bool multi = comm && comm->world > 1;
+  semk_halo *halo_f = multi ? dist->halo_f : nullptr;
+  semk_halo *halo_c = multi ? dist->halo_c : nullptr;
+  if (multi) SEMK_REQUIRE(halo_f && halo_c, "semk_sc_mlpcg_solve_f64: partition without halos");
+  cudaStream_t st = semk_stream(stream);
+  const int64_t n = op->n_ext, nv = cs->n_v, n_elem = op->n_elem;
+  const int64_t na = three ? top->n_agg : 0;
+  const int64_t n_dot = multi ? dist->n_owned_f : n, nv_dot = multi ? dist->n_owned_c : nv;
+  SEMK_REQUIRE(n_dot >= 0 && n_dot <= n && nv_dot >= 0 && nv_dot <= nv,
+               "semk_sc_mlpcg_solve_f64: bad owned prefix");
+  if (multi)
+    SEMK_REQUIRE(comm->capacity >= na + 8, "semk_sc_mlpcg_solve_f64: comm capacity < n_agg + 8");
+  const int64_t n_pad = (n + 31) & ~(int64_t)31, nv_pad = (nv + 31) & ~(int64_t)31;
+  const int64_t na_pad = (na + 31) & ~(int64_t)31;
+  double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad, *z = work + 3 * n_pad;
+  double *rc = work_c, *xc = work_c + nv_pad;          // rc doubles as the inner residual
+  double *pi = work_c + 2 * nv_pad, *Api = work_c + 3 * nv_pad, *zi = work_c + 4 * nv_pad;
+  double *r3 = work_c + 6 * nv_pad, *y3 = r3 + na_pad + 32;   // r3[na] = r.r rides with r3
+  double *so = sc, *si = sc + S_LEN;                   // scalar blocks: outer, inner
+  double *scratch2 = sc + 2 * S_LEN;                   // {r.r, b.b} of the initial residual
+  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
+  const CommDev cd = make_comm(multi ? comm : nullptr);
+  const dim3 g(blocks_for(n)), gc(blocks_for(nv)), blk(kT);
+  const int64_t want_a = (na * 32 + kT - 1) / kT;
+  const dim3 ga((unsigned)(want_a < 1 ? 1 : (want_a < kMaxBlocks ? want_a : kMaxBlocks)));
+  // pinned landing zone for the scalar blocks: per call, so concurrent solves on other
+  // streams / threads do not share it
+  double *h = nullptr;
+  SEMK_CUDA_CHECK(cudaMallocHost(&h, 3 * S_LEN * sizeof(double)));
+  struct Unpin {
+    double *host;
+    ~Unpin() { cudaFreeHost(host); }
+  } unpin{h};
+
+  auto fetch = [&]() -> int {
+    SEMK_CUDA_CHECK(cudaMemcpyAsync(h, sc, 3 * S_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SEMK_OK;
+  };
+  auto step = [&](double *buf, int nred, int opcode, double *s) -> int {
+    // the inner preconditioner is a fixed linear operator: standard beta there
+    const int flex = (s == so) ? opts->flexible : 0;
+    ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, buf, nred, opcode, flex, s);
+    SEMK_LAUNCH_CHECK("ml_step_kernel");
+    return SEMK_OK;
+  };
+  auto exchange = [&](semk_halo *hl, int64_t n_local, double *y, const double *u,
+                      const uint8_t *dir, double *dot) -> int {
+    if (!hl) return SEMK_OK;
+    hl->epoch += 1;
+    return semk_halo_exchange_f64(hl->n_col, n_local, y, u, dir, hl->mine, hl->left, hl->right,
+                                  hl->epoch, dot, hl->status, st);
+  };
+  auto fine_apply = [&](const double *in, double *out, double *dot) -> int {
+    int e = semk_sc_apply_f64(op, in, out, flags, dot, st);
+    if (e != SEMK_OK) return e;
+    return exchange(halo_f, n, out, in, op->dirichlet, dot);
+  };
+  auto coarse_apply = [&](const double *in, double *out, double *dot) -> int {
+    int e = semk_sc_coarse_apply_f64(n_elem, cs, in, out, flags, dot, st);
+    if (e != SEMK_OK) return e;
+    return exchange(halo_c, nv, out, in, cs->dirichlet_c, dot);
+  };
+  // inner preconditioner tail: zi = dinv_c ri is done; add the aggregation correction and
+  // leave {r.z, z.Ap} in si[S_RZN..]; `rr_slot` holds r.r of this rank
+  auto inner_tail = [&](bool first) -> int {
+    int e;
+    if (three) {
+      ml_agg_restrict_kernel<<<ga, blk, 0, st>>>(na, top->aptr, top->aidx, rc, r3);
+      SEMK_LAUNCH_CHECK("ml_agg_restrict_kernel");
+      if ((e = step(r3, (int)na + 1, first ? OP_RR_FIRST : OP_RR, si)) != SEMK_OK) return e;
+      ml_dense_matvec_kernel<<<ga, blk, 0, st>>>(na, top->A3inv, r3, y3);
+      SEMK_LAUNCH_CHECK("ml_dense_matvec_kernel");
+    } else {
+      if ((e = step(r3, 1, first ? OP_RR_FIRST : OP_RR, si)) != SEMK_OK) return e;
+    }
+    ml_correct_dot_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, three ? top->agg : nullptr, y3, rc,
+                                              first ? nullptr : Api, zi, si + S_RZN,
+                                              vec_partials);
+    SEMK_LAUNCH_CHECK("ml_correct_dot_kernel");
+    if ((e = step(si + S_RZN, 2, first ? OP_BETA_FIRST : OP_BETA, si)) != SEMK_OK) return e;
+    ml_direction_kernel<<<gc, blk, 0, st>>>(nv, zi, pi, si);
+    SEMK_LAUNCH_CHECK("ml_direction_kernel");
+    return SEMK_OK;
+  };
+  double *rr_slot = r3 + na;   // r.r of the inner residual, reduced together with r3
+  auto inner_iteration = [&]() -> int {
+    int e = coarse_apply(pi, Api, si + S_PAP);
+    if (e != SEMK_OK) return e;
+    if ((e = step(si + S_PAP, 1, OP_ALPHA, si)) != SEMK_OK) return e;
+    ml_update_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, pi, Api, dinv_c, xc, rc, zi, si, rr_slot,
+                                         vec_partials);
+    SEMK_LAUNCH_CHECK("ml_update_kernel");
+    return inner_tail(false);
+  };
+  int64_t inner_sum = 0;
+  int inner_solves = 0, predicted = 8;
+  // xc ~= Ac^-1 rc (rc is overwritten by the inner residual)
+  auto inner_solve = [&]() -> int {
+    int e;
+    SEMK_CUDA_CHECK(cudaMemsetAsync(xc, 0, sizeof(double) * nv, st));
+    SEMK_CUDA_CHECK(cudaMemsetAsync(si, 0, sizeof(double) * S_TOL2, st));   // keeps S_TOL2
+    SEMK_CUDA_CHECK(cudaMemsetAsync(pi, 0, sizeof(double) * nv, st));
+    ml_first_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, dinv_c, rc, zi, rr_slot, vec_partials);
+    SEMK_LAUNCH_CHECK("ml_first_kernel");
+    if ((e = inner_tail(true)) != SEMK_OK) return e;
+    int launched = 0;
+    int chunk = predicted > 2 ? predicted - 1 : 1;
+    while (launched < opts->inner_maxiter) {
+      if (chunk > opts->inner_maxiter - launched) chunk = opts->inner_maxiter - launched;
+      for (int k = 0; k < chunk; ++k)
+        if ((e = inner_iteration()) != SEMK_OK) return e;
+      launched += chunk;
+      if ((e = fetch()) != SEMK_OK) return e;
+      const double *hi = h + S_LEN;
+      if (hi[S_BREAK] != 0.0) {
+        semk_set_error(hi[S_BREAK] == 2.0
+                           ? "semk_sc_mlpcg_solve_f64: a rank did not arrive at an all-reduce"
+                           : "semk_sc_mlpcg_solve_f64: inner breakdown (p.Ap <= 0 or non-finite)");
+        return hi[S_BREAK] == 2.0 ? SEMK_ERR_CUDA : SEMK_ERR_BREAKDOWN;
+      }
+      if (hi[S_CONV] != 0.0) break;
+      chunk = opts->inner_chunk;
+    }
+    const int its = (int)h[S_LEN + S_ITER];
+    predicted = its;
+    inner_sum += its;
+    ++inner_solves;
+    return SEMK_OK;
+  };
+  // z = dinv r is done by the update kernel; add P Ac^-1 P^T r and leave {r.z, z.Ap}
+  auto precondition = [&](bool first) -> int {
+    ml_restrict_kernel<<<gc, blk, 0, st>>>(nv, cs->rptr, cs->ridx, cs->rw, r, n_dot, rc);
+    SEMK_LAUNCH_CHECK("ml_restrict_kernel");
+    int e = exchange(halo_c, nv, rc, nullptr, nullptr, nullptr);
+    if (e != SEMK_OK) return e;
+    if ((e = inner_solve()) != SEMK_OK) return e;
+    ml_prolong_dot_kernel<<<g, blk, 0, st>>>(n, n_dot, cs->pv, cs->pw, xc, r,
+                                             first ? nullptr : Ap, z, so + S_RZN, vec_partials);
+    SEMK_LAUNCH_CHECK("ml_prolong_dot_kernel");
+    if ((e = step(so + S_RZN, 2, first ? OP_BETA_FIRST : OP_BETA, so)) != SEMK_OK) return e;
+    ml_direction_kernel<<<g, blk, 0, st>>>(n, z, p, so);
+    SEMK_LAUNCH_CHECK("ml_direction_kernel");
+    return SEMK_OK;
+  };
+
+  // ---- outer loop ---------------------------------------------------------------------
+  SEMK_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(double) * 3 * S_LEN, st));
+  const double tol2 = opts->rtol * opts->rtol;
+  h[0] = tol2;
+  h[1] = opts->inner_rtol * opts->inner_rtol;
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(so + S_TOL2, h, sizeof(double), cudaMemcpyHostToDevice, st));
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(si + S_TOL2, h + 1, sizeof(double), cudaMemcpyHostToDevice, st));
+  SEMK_CUDA_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
+  if ((rcode = fine_apply(x, Ap, nullptr)) != SEMK_OK) return rcode;
+  ml_resid_kernel<<<g, blk, 0, st>>>(n, b, Ap, op->dirichlet, r, n_dot, scratch2, vec_partials);
+  SEMK_LAUNCH_CHECK("ml_resid_kernel");
+  if (multi && (rcode = semk_comm_allreduce_f64(comm, scratch2, 2, st)) != SEMK_OK) return rcode;
+  if ((rcode = fetch()) != SEMK_OK) return rcode;
+  double rr = h[2 * S_LEN], bb = h[2 * S_LEN + 1];
+  info->bnorm = sqrt(bb);
+  info->iterations = 0;
+  info->status = 0;
+  info->inner_iterations = 0;
+  info->inner_solves = 0;
+  info->true_rel_residual = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+  info->rel_residual = info->true_rel_residual;
+  if (bb == 0.0 || rr <= tol2 * bb) return SEMK_OK;
+  h[2] = bb;   // (the fetch above has completed: h is free again until the next one)
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(so + S_BB, h + 2, sizeof(double), cudaMemcpyHostToDevice, st));
+  ml_first_kernel<<<g, blk, 0, st>>>(n, n_dot, dinv, r, z, so + S_RR, vec_partials);
+  SEMK_LAUNCH_CHECK("ml_first_kernel");
+  if ((rcode = step(so + S_RR, 1, OP_RR, so)) != SEMK_OK) return rcode;
+  if ((rcode = precondition(true)) != SEMK_OK) return rcode;
+  int status = 1, it = 0;
+  while (it < opts->maxiter) {
+    if ((rcode = fine_apply(p, Ap, so + S_PAP)) != SEMK_OK) return rcode;
+    if ((rcode = step(so + S_PAP, 1, OP_ALPHA, so)) != SEMK_OK) return rcode;
+    ml_update_kernel<<<g, blk, 0, st>>>(n, n_dot, p, Ap, dinv, x, r, z, so, so + S_RR,
+                                        vec_partials);
+    SEMK_LAUNCH_CHECK("ml_update_kernel");
+    if ((rcode = step(so + S_RR, 1, OP_RR, so)) != SEMK_OK) return rcode;
+    if ((rcode = fetch()) != SEMK_OK) return rcode;
+    ++it;
+    rr = h[S_RR];
+    if (h[S_BREAK] != 0.0) {
+      status = SEMK_ERR_BREAKDOWN;
+      break;
+    }
+    if (h[S_CONV] != 0.0) {
+      status = 0;
+      break;
+    }
+    if ((rcode = precondition(false)) != SEMK_OK) return rcode;
+  }
+  // true residual of the returned iterate
+  if ((rcode = fine_apply(x, Ap, nullptr)) != SEMK_OK) return rcode;
+  ml_resid_kernel<<<g, blk, 0, st>>>(n, b, Ap, op->dirichlet, z, n_dot, scratch2, vec_partials);
+  SEMK_LAUNCH_CHECK("ml_resid_kernel");
+  if (multi && (rcode = semk_comm_allreduce_f64(comm, scratch2, 2, st)) != SEMK_OK) return rcode;
+  if ((rcode = fetch()) != SEMK_OK) return rcode;
+  info->iterations = it;
+  info->status = status;
+  info->rel_residual = sqrt(rr / bb);
+  info->true_rel_residual = sqrt(h[2 * S_LEN] / bb);
+  info->inner_iterations = inner_sum;
+  info->inner_solves = inner_solves;
+  if (status == SEMK_ERR_BREAKDOWN) {
+    semk_set_error(h[S_BREAK] == 2.0
+                       ? "semk_sc_mlpcg_solve_f64: a rank did not arrive at an all-reduce"
+                       : "semk_sc_mlpcg_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
+    return h[S_BREAK] == 2.0 ? SEMK_ERR_CUDA : SEMK_ERR_BREAKDOWN;
+  }
+  return SEMK_OK;
+}
