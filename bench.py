@@ -50,6 +50,12 @@ def parse():
     ap.add_argument("--condensed-multi", action="store_true",
                     help="under torchrun: also time the distributed condensed PCG (capped); "
                          "opt-in, the default multi-GPU line is the apply + uncondensed PCG only")
+    ap.add_argument("--two-level", action="store_true",
+                    help="also time the two-level preconditioner (seconds at 67 M DOF)")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="under torchrun: skip the multi-GPU self-check before timing")
+    ap.add_argument("--no-tts", action="store_true",
+                    help="under torchrun: skip the distributed multilevel time to solution")
     ap.add_argument("--no-condensed", action="store_true",
                     help="skip the statically condensed operator (reported beside the headline)")
     ap.add_argument("--cpu-sample", type=int, default=64,
@@ -83,6 +89,31 @@ def measured_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def committed_traffic(name, sources):
+    """Measured DRAM bytes of one apply from the newest committed ncu capture
+    (profiles/rNN_<name>).  ncu cannot run inside a timed bench, so the number is read from
+    the capture -- but only while the kernel sources it was taken from are unchanged: the
+    file records their SHA-256 and a mismatch yields (None, "stale ...") instead of a
+    silently outdated figure."""
+    import glob
+    import hashlib
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_" + name)))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        tj = json.load(f)
+    want = tj.get("source_sha256")
+    if want is not None:
+        h = hashlib.sha256()
+        for src in sources:
+            with open(os.path.join(ROOT, "spectralelementmethod_b200", "csrc", src), "rb") as f:
+                h.update(f.read())
+        if h.hexdigest() != want:
+            return None, "stale: %s changed since the capture %s" % (
+                "+".join(sources), os.path.basename(files[-1]))
+    return tj["dram_bytes_per_apply"], tj["source"]
 
 
 class ClockSampler(object):
@@ -157,6 +188,7 @@ def _cpu_problem(n_side, kind):
     L = so.local_stiffness(basis, geo["invJ"], geo["JxW"])
     u = np.sin(3 * nodes[0]) * np.cos(2 * nodes[1])
     if so.c_lib() is not None:
+        so.c_set_threads(os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1 to its workers
         fn = lambda: so.apply_dense_c(L, l2g, u)                 # noqa: E731
         how = ("dense local apply, C/OpenMP restatement (oracle/sem_oracle_c.c), %d threads"
                % so.c_threads())
@@ -187,6 +219,33 @@ def cpu_baseline(n_side, kind, target_seconds=10.0):
     return {"value": ndof * reps / el / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "port",
             "sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s; %s"
                       % (n_side, n_side, ORDER, ndof, reps, el, how)}
+
+
+def live_reference_baseline(n_side, kind, apply_seconds=3.0):
+    """The UNMODIFIED reference (oracle/_ref, an offline `pip install --target` of
+    /root/reference made by oracle/install_ref.sh; five compatibility shims, no source
+    edits) timed on this host: its own apply -- a Python loop of dense local einsums,
+    examples/squirmer-axisymmetric.py:268-295 -- and its whole DOFManagerSC solver pipeline
+    (sem/discrete.py:283-528), on a bounded n_side x n_side sample.  None when the
+    reference tree did not travel."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import live_reference as lr
+        if not lr.available():
+            return None
+        reps, el, ndof = lr.time_apply(kind, n_side, n_side, ORDER, apply_seconds)
+        pipe = lr.time_pipeline(kind, n_side, n_side, ORDER)
+    except Exception as exc:             # a reported baseline, never fatal
+        return {"error": repr(exc)}
+    return {"kind": "reference", "cores": 1,
+            "apply_gdof_per_s": ndof * reps / el / 1e9,
+            "apply_sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s; the reference's "
+                            "own Python loop of dense local einsums (single thread)"
+                            % (n_side, n_side, ORDER, ndof, reps, el),
+            "solve": dict(pipe, sample="%dx%d elements p=%d: DOFManagerSC numbering, "
+                                       "FiniteElement + local stiffness per element, Schur "
+                                       "assembly, spsolve, back-solve (live reference)"
+                                       % (n_side, n_side, ORDER))}
 
 
 def cpu_solve_baseline(n_side, kind):
@@ -232,6 +291,7 @@ def run_reference(args):
     value = ndof * args.steps / el / 1e9
     sample = ("%dx%d elements p=%d (%d DOF) per step: bounded sample of the 1024x1024 workload; %s"
               % (n_side, n_side, ORDER, ndof, how))
+    live = live_reference_baseline(min(n_side, 24), args.kind) if 2 <= ORDER <= 10 else None
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GDOF/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -244,7 +304,11 @@ def run_reference(args):
                                 "GPUs (BASELINE configs[4])" % args.gpus),
                    "order": ORDER, "sample_elements_per_side": n_side},
         "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "host_cores": os.cpu_count(),
+                         "live_reference": live,
+                         "note": "value = the C/OpenMP port on every host core (faster than the "
+                                 "reference's own Python loop, reported beside it as "
+                                 "live_reference): the conservative denominator"},
         "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -304,12 +368,10 @@ def run_condensed(args, nx, dev, peak):
            "kernel": "sc_matvec_kernel<%d> + sc_node_kernel (one condensed apply)" % (ORDER + 1)}
     # measured DRAM bytes of one condensed apply, from the committed ncu capture of this very
     # configuration; null for any other workload
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_condensed.json")
     res["traffic"] = None
-    if sc.n_elem == 1024 * 1024 and ORDER == 8 and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        res["traffic"], res["traffic_source"] = tj["dram_bytes_per_apply"], tj["source"]
+    if sc.n_elem == 1024 * 1024 and ORDER == 8:
+        res["traffic"], res["traffic_source"] = committed_traffic("traffic_condensed.json",
+                                                                  ["semk_sc.cu"])
     if args.pcg_iters > 0 or args.pcg_full:
         b = sc.lift(sc.rhs(1.0), None)
 
@@ -333,31 +395,47 @@ def run_condensed(args, nx, dev, peak):
                       "backsolve_seconds": time.perf_counter() - t0,
                       "note": "homogeneous Dirichlet on ebc, f=1, rtol 1e-12"
                               + ("" if full else "; capped")}
-    # time to solution with the two-level preconditioner (Jacobi + vertex coarse space): a few
-    # seconds even at 67 M DOF, so it always runs to rtol 1e-12; never fatal for the line
-    try:
-        b2 = sc.lift(sc.rhs(1.0), None)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        sc._build_coarse()
-        torch.cuda.synchronize()
-        t_coarse = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        x2, info2 = sc.solve_pcg(b2, rtol=1e-12, preconditioner="two-level")
-        torch.cuda.synchronize()
-        t_solve = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        sc.backsolve(x2, 1.0)
-        torch.cuda.synchronize()
-        res["two_level_pcg"] = {
-            "preconditioner": "Jacobi + vertex coarse space (inner Jacobi-PCG, rtol 1e-2)",
-            "outer_iterations": info2.iterations, "inner_iterations": sc.last_inner_iterations,
-            "seconds": t_solve, "coarse_build_seconds": t_coarse,
-            "backsolve_seconds": time.perf_counter() - t0, "converged": info2.converged,
-            "rel_residual": info2.rel_residual,
-            "note": "homogeneous Dirichlet on ebc, f=1, rtol 1e-12 (time to solution)"}
-    except Exception as exc:
-        res["two_level_pcg"] = {"error": repr(exc)}
+    # time to solution with the multilevel preconditioner (Jacobi + vertex coarse space +
+    # aggregation level, native driver semk_sc_mlpcg_solve_f64): always runs to rtol 1e-12;
+    # never fatal for the line
+    for pre in ("three-level",) + (("two-level",) if args.two_level else ()):
+        key = pre.replace("-", "_") + "_pcg"
+        try:
+            b2 = sc.lift(sc.rhs(1.0), None)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sc._build_coarse()
+            torch.cuda.synchronize()
+            t_coarse = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            if pre == "three-level":
+                sc._build_top()
+            torch.cuda.synchronize()
+            t_top = time.perf_counter() - t0
+            sc.solve_pcg(b2, rtol=1e-12, maxiter=2, preconditioner=pre)      # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            x2, info2 = sc.solve_pcg(b2, rtol=1e-12, preconditioner=pre)
+            torch.cuda.synchronize()
+            t_solve = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            sc.backsolve(x2, 1.0)
+            torch.cuda.synchronize()
+            res[key] = {
+                "preconditioner": "Jacobi + vertex coarse space"
+                                  + (" + vertex aggregation with a dense inverse (inner PCG, rtol "
+                                     "1e-2)" if pre == "three-level" else " (inner Jacobi-PCG, rtol 1e-2)")
+                                  + ", flexible CG outside",
+                "outer_iterations": info2.iterations, "inner_iterations": info2.inner_iterations,
+                "seconds": t_solve, "coarse_build_seconds": t_coarse, "top_build_seconds": t_top,
+                "backsolve_seconds": time.perf_counter() - t0, "converged": info2.converged,
+                "rel_residual": info2.rel_residual,
+                "true_rel_residual": info2.true_rel_residual,
+                "note": "homogeneous Dirichlet on ebc, f=1, rtol 1e-12 (time to solution); "
+                        "rel_residual is the recursive one, true_rel_residual = ||b - S x|| / ||b|| "
+                        "recomputed from the returned iterate"}
+        except Exception as exc:
+            res[key] = {"error": repr(exc)}
     return res
 
 
@@ -443,6 +521,18 @@ def run_engine(args):
     if multi:
         dist.init_process_group("nccl", device_id=dev)
 
+    parity = None
+    if multi and not args.no_parity:
+        # driver-visible parity of the partitioned path: a small global problem per rank,
+        # distributed apply / dot / PCG / condensed / multilevel against the single-GPU
+        # operator, peer == NCCL bitwise; raises (and fails the run) on any mismatch
+        from spectralelementmethod_b200 import distributed_check
+        t0 = time.perf_counter()
+        parity = distributed_check.run(rank, world, dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        parity["seconds"] = time.perf_counter() - t0
+
     t_setup = time.perf_counter()
     if not multi:
         nx = args.nx or 1024
@@ -522,12 +612,9 @@ def run_engine(args):
     # measured DRAM bytes of one apply: from the committed ncu capture of this very
     # configuration (profiles/r01_traffic.json); null for any other workload
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if (not multi and op.n_elem == 1024 * 1024 and op.elems_per_patch == 16 and not args.tile
-            and args.kind == "S" and os.path.exists(tpath)):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["dram_bytes_per_apply"], tj["source"]
+            and args.kind == "S"):
+        traffic, traffic_src = committed_traffic("traffic.json", ["semk_apply.cu"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_kind,
@@ -561,7 +648,17 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_el = float(t)
     e2e_value = n_global_units / (e2e_el / args.e2e_steps) / 1e9
-    e2e_ok = bool(torch.equal(y_host.to(dev), out)) if dp is None else True
+    if dp is None:
+        e2e_ok = bool(torch.equal(y_host.to(dev), out))
+    else:
+        # the host-buffer step must reproduce the device-resident distributed apply bit for
+        # bit on every rank (same kernels, same two-term interface sums)
+        dp.apply(u, out=out)
+        ok = torch.tensor([1.0 if torch.equal(y_host.to(dev), out) else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        e2e_ok = bool(float(ok) >= 1.0)
+        if not e2e_ok:
+            raise AssertionError("multi-GPU e2e result differs from the device-resident apply")
     if dp is not None and dp.halo is not None:
         dp.halo.check()         # a neighbour that never delivered a column would have raised a flag
 
@@ -632,19 +729,67 @@ def run_engine(args):
         if dc.halo is not None:
             dc.halo.check()
 
-    # the metric's second half, PCG time to solution (rtol 1e-12), by the fastest device path
+    # the metric's second half, PCG time to solution (rtol 1e-12), by the fastest device path:
+    # static condensation + multilevel-preconditioned flexible CG + interior back-solve
     tts = None
-    try:
-        tl = (condensed or {}).get("two_level_pcg") or {}
+    method = ("static condensation + three-level PCG (Jacobi + vertex coarse space + vertex "
+              "aggregation with a dense inverse; native driver semk_sc_mlpcg_solve_f64) + interior "
+              "back-solve; operator set-up reported separately")
+    if not multi:
+        tl = (condensed or {}).get("three_level_pcg") or {}
         if tl.get("converged"):
+            setup_s = (condensed.get("host_numbering_seconds", 0.0) + condensed.get("setup_seconds", 0.0)
+                       + tl.get("coarse_build_seconds", 0.0) + tl.get("top_build_seconds", 0.0))
             tts = {"seconds": tl["seconds"] + tl["backsolve_seconds"], "rtol": 1e-12,
                    "dof": int(n_global_units), "outer_iterations": tl["outer_iterations"],
-                   "method": "static condensation + two-level PCG (Jacobi + vertex coarse space) "
-                             "+ interior back-solve; operator set-up excluded",
-                   "setup_seconds": condensed.get("setup_seconds", 0.0)
-                                    + tl.get("coarse_build_seconds", 0.0)}
-    except Exception:
-        tts = None
+                   "inner_iterations": tl["inner_iterations"],
+                   "rel_residual": tl["rel_residual"],
+                   "true_rel_residual": tl["true_rel_residual"], "method": method,
+                   "setup_seconds": setup_s,
+                   "including_setup_seconds": setup_s + tl["seconds"] + tl["backsolve_seconds"]}
+    elif not args.no_tts and 2 <= ORDER <= 10:
+        # every rank takes the same path: constructor and solves are collective
+        from spectralelementmethod_b200.distributed import DistributedCondensedPoisson
+        del u, out
+        torch.cuda.empty_cache()
+        barrier()
+        t0 = time.perf_counter()
+        dcm = DistributedCondensedPoisson(part, ORDER, args.kind, exchange=args.exchange)
+        bcm = dcm.lift(dcm.rhs(1.0), None)
+        barrier()
+        t_op = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ml = dcm._multilevel(3)
+        barrier()
+        t_ml = time.perf_counter() - t0
+        dcm.solve_pcg(bcm, rtol=1e-12, maxiter=2, preconditioner="three-level")     # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        xs, it, rel, ok = dcm.solve_pcg(bcm, rtol=1e-12, preconditioner="three-level")
+        torch.cuda.synchronize()
+        t_solve = time.perf_counter() - t0
+        us = dcm.sc.backsolve(xs, 1.0)
+        barrier()
+        t_total = time.perf_counter() - t0
+        tt = torch.tensor([t_total, t_solve], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        inf = dcm.last_info
+        chk = torch.tensor([float(us.sum())], dtype=torch.float64, device=dev)
+        tts = {"seconds": float(tt[0]), "solve_seconds": float(tt[1]), "rtol": 1e-12,
+               "dof": int(n_global_units), "converged": bool(ok), "outer_iterations": int(it),
+               "inner_iterations": int(inf.inner_iterations), "rel_residual": float(rel),
+               "true_rel_residual": float(inf.true_rel_residual),
+               "aggregates": int(ml.get("aggregate_tile", 0)) and
+               "%d x %d element tiles" % (ml["aggregate_tile"], ml["aggregate_tile"]),
+               "method": method + "; strip partition, halo exchanges and all-reduces are "
+                                  "peer-memory kernels issued by the driver",
+               "setup_seconds": t_op + t_ml, "operator_setup_seconds": t_op,
+               "multilevel_setup_seconds": t_ml,
+               "including_setup_seconds": t_op + t_ml + float(tt[0]),
+               "rank0_solution_checksum": float(chk)}
+        if not ok:
+            raise AssertionError("distributed multilevel PCG did not converge: %r" % (tts,))
+        dcm.close()
 
     cpu = None
     if rank == 0 and not multi and args.cpu_sample > 0:
@@ -654,6 +799,7 @@ def run_engine(args):
                 cpu["solve"] = cpu_solve_baseline(args.cpu_sample, args.kind)
             except Exception as exc:     # a reported baseline, never fatal
                 cpu["solve"] = {"error": repr(exc)}
+            cpu["live_reference"] = live_reference_baseline(min(args.cpu_sample, 24), args.kind)
 
     if rank == 0:
         line = {
@@ -680,6 +826,7 @@ def run_engine(args):
             "pcg": pcg,
             "condensed": condensed,
             "time_to_solution": tts,
+            "parity": parity,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

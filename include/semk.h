@@ -376,8 +376,11 @@ typedef struct semk_pcg_info {
 /* Native single-GPU PCG driver on Ahat = M A M + (I - M): solves
  * Ahat x = b from the initial guess in x.  work: device [3*(n+32)] or
  * more (r, p, Ap, 256-byte aligned); sc: device [8]; vec_partials as above.  Convergence
- * ||r|| <= rtol*||b|| is polled every check_every iterations (one 32-byte
- * D2H copy); no other host synchronisation. */
+ * ||r|| <= rtol*||b|| is polled every check_every iterations (one 64-byte
+ * D2H copy); no other host synchronisation.  Re-entrant per (host thread, stream,
+ * workspace): concurrent solves need their own work / sc / vec_partials AND their own
+ * operator scratch (op->partials, slot buffers); an operator is bound to one stream at
+ * a time.  At most maxiter iterations are run. */
 int semk_pcg_solve_f64(const semk_op *op, const double *b, double *x, const double *dinv,
                        double *work, double *sc, double *vec_partials, double rtol,
                        int maxiter, int check_every, semk_pcg_info *info, void *stream);
@@ -520,17 +523,6 @@ int semk_sc_coarse_apply_f64(int64_t n_elem, const semk_sc_coarse *cs, const dou
 /* out[v] = sum of loc[vpos[..]]; loc: device [n_elem][4] (diagonal of Ac, ...). */
 int semk_sc_coarse_assemble_f64(int64_t n_elem, const semk_sc_coarse *cs, const double *loc,
                                 double *out, void *stream);
-/* Two-level PCG on Shat x = b.  dinv / dinv_c: inverse diagonals of Shat / Ac (1 on
- * Dirichlet rows).  work: device [4 * (n_ext + 32)]; work_c: device [5 * (n_v + 32)];
- * sc: device [16]; vec_partials as in semk_pcg_solve_f64.  The inner solves stop at
- * ||r_c|| <= inner_rtol ||b_c|| or inner_maxiter; *inner_total receives the sum of
- * their iteration counts (may be NULL).  info as semk_pcg_solve_f64. */
-int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const double *b,
-                           double *x, const double *dinv, const double *dinv_c, double *work,
-                           double *work_c, double *sc, double *vec_partials, double rtol,
-                           int maxiter, double inner_rtol, int inner_maxiter,
-                           semk_pcg_info *info, int64_t *inner_total, void *stream);
-
 /* Third level under the vertex coarse space: the inner coarse solve is preconditioned by
  * Jacobi + a piecewise-constant aggregation of the vertices (element tiles) with a DENSE
  * inverse at the top, so that the inner iteration count is mesh-independent as well
@@ -546,6 +538,13 @@ typedef struct semk_sc_top {
   const uint32_t *aidx;
   const double *A3inv;
 } semk_sc_top;
+
+/* A3 = P2^T Ac P2 (this rank's elements only) from the element coarse matrices cs->Ace:
+ * aptr_all / aidx_all: CSR of ALL local vertices of every aggregate (owned or not).
+ * A3: device [n_agg][n_agg], overwritten.  One thread per row, fixed order, no atomics. */
+int semk_sc_top_assemble_f64(const semk_sc_coarse *cs, int64_t n_agg, const uint32_t *agg,
+                             const uint32_t *aptr_all, const uint32_t *aidx_all, double *A3,
+                             void *stream);
 
 /* ------------------------------------------------------------------------
  * Small-vector all-reduce over NVLink peer memory (no reference equivalent:
@@ -626,7 +625,7 @@ typedef struct semk_ml_info {
  * The inner iteration keeps its scalars on the device (alpha, beta, convergence and
  * breakdown flags are produced by single-CTA kernels that also carry the all-reduce),
  * is queued `inner_chunk` iterations at a time and polled through one 128-byte copy.
- * work: device [4 * (n_ext + 32)]; work_c: device [6 * (n_v + 32) + 2 * (n_agg + 32)];
+ * work: device [4 * (n_ext + 32)]; work_c: device [6 * (n_v + 32) + 2 * (n_agg + 64)];
  * sc: device [64]; vec_partials as in semk_pcg_solve_f64.  dinv / dinv_c: inverse
  * diagonals of the GLOBAL operators (interface entries already summed). */
 int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs, const semk_sc_top *top,

@@ -1,9 +1,11 @@
 """Drive the UNMODIFIED reference (/root/reference/sem) through its current API.
 
-TEST INFRASTRUCTURE ONLY.  Runs only in the development container (the
-reference tree does not exist on the GPU box); used by oracle/make_golden.py to
-freeze golden vectors under tests/golden/ and by tests that are skipped when
-/root/reference is absent.  No product module imports this file.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py to freeze golden
+vectors under tests/golden/, by tests that are skipped when no reference tree is
+reachable, and by bench.py's cpu_baseline / --impl reference legs.  No product module
+imports this file.  The tree is /root/reference in the development container; on the GPU
+box it is oracle/_ref, an offline `pip install --target` of the unmodified reference made
+by oracle/install_ref.sh (git-ignored, not gpurun-ignored: it travels with the snapshot).
 
 The reference has bit-rotted against numpy 2 / scipy 1.18 / python 3.12 and
 needs h5py (absent).  Five monkey-patch shims (no source edits) make it run:
@@ -20,7 +22,18 @@ import warnings
 
 import numpy as np
 
-REF_ROOT = os.environ.get("SEM_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    env = os.environ.get("SEM_REFERENCE_ROOT")
+    if env:
+        return env
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in ("/root/reference", os.path.join(here, "_ref")):
+        if os.path.isdir(os.path.join(cand, "sem")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 _installed = False
 
@@ -216,3 +229,63 @@ def run_case(kind, nx, ny, p, sc, rcm, solve=True):
             sol[free] = spsolve(A[free][:, free].tocsc(), rhs)
         out["solution"] = sol
     return out
+
+
+# --------------------------------------------------------------------------
+# Timing of the UNMODIFIED reference (bench.py cpu_baseline, kind "reference")
+# --------------------------------------------------------------------------
+def time_apply(kind, nx, ny, p, target_seconds=5.0):
+    """The reference's own operator apply (examples/squirmer-axisymmetric.py:268-295 with
+    the dense 4-index local stiffness of examples/poisson.py:181-193): a Python loop over
+    elements, `y[idx] += einsum('pqrs,rs', Lse, u[idx])`.  Returns (applies, seconds, ndof)."""
+    import time
+    mesh = build_mesh(kind, nx, ny, p)
+    mngr = make_manager(mesh, p, False, False)
+    ops = []
+    for fe in mngr.finite_elements(x_phys=True, Jacobian=True):
+        L, _ = local_stiffness(fe)
+        ops.append((fe.node_ind.astype(np.int64), L))
+    x, y = mesh.nodes
+    u = np.sin(3 * x) * np.cos(2 * y)
+
+    def apply():
+        out = np.zeros_like(u)
+        for idx, L in ops:
+            out[idx] += np.einsum("pqrs,rs", L, u[idx])
+        return out
+    apply()
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        apply()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= target_seconds:
+            break
+    return reps, el, int(mngr.ndof)
+
+
+def time_pipeline(kind, nx, ny, p):
+    """The reference's whole solver pipeline, once: DOFManagerSC numbering, FiniteElement
+    geometry + local stiffness per element, hierarchical reorder, Schur assembly, spsolve,
+    interior back-substitution (sem/discrete.py:283-528).  Returns a dict of seconds."""
+    import time
+    t0 = time.perf_counter()
+    mesh = build_mesh(kind, nx, ny, p)
+    mngr = make_manager(mesh, p, True, False)
+    t1 = time.perf_counter()
+    local_systems = []
+    for fe in mngr.finite_elements(x_phys=True, Jacobian=True):
+        L, w = local_stiffness(fe)
+        N = w.shape[0]
+        local_systems.append((L.reshape(N * N, N * N), w.reshape(N * N).copy()))
+    t2 = time.perf_counter()
+    on_ebc, vals = dirichlet_data(mngr, mngr.ndof)
+    lsys = [mngr.reorder_local_system_hier(fe, ls)
+            for fe, ls in zip(mngr.finite_elements(), local_systems)]
+    gsys = mngr.init_global_linear_system()
+    mngr.assemble_global_sc_system(gsys, lsys)
+    sol = vals.copy()
+    mngr.solve(gsys, lsys, sol, on_ebc[:mngr.ndof_exterior])
+    t3 = time.perf_counter()
+    return {"seconds": t3 - t0, "numbering_seconds": t1 - t0, "operator_seconds": t2 - t1,
+            "solve_seconds": t3 - t2, "dof": int(mngr.ndof), "checksum": float(sol.sum())}

@@ -484,6 +484,8 @@ def c_lib():
         os.environ.setdefault("OMP_PROC_BIND", "true")   # unpinned threads scale negatively
         lib = ctypes.CDLL(path)
         lib.sem_oracle_c_threads.restype = ctypes.c_int
+        lib.sem_oracle_c_set_threads.restype = None
+        lib.sem_oracle_c_set_threads.argtypes = [ctypes.c_int]
         lib.sem_oracle_c_apply_dense.restype = None
         lib.sem_oracle_c_apply_dense.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int64] + \
             [ctypes.c_void_p] * 4
@@ -511,3 +513,13 @@ def apply_dense_c(L, l2g, u):
 def c_threads():
     lib = c_lib()
     return int(lib.sem_oracle_c_threads()) if lib is not None else 1
+
+
+def c_set_threads(n=None):
+    """Use ``n`` OpenMP threads (default: every host core) whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its workers).  Returns the count in effect."""
+    lib = c_lib()
+    if lib is None:
+        return 1
+    lib.sem_oracle_c_set_threads(int(n or os.cpu_count() or 1))
+    return c_threads()

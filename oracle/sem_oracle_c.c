@@ -26,6 +26,16 @@ int sem_oracle_c_threads(void) {
 #endif
 }
 
+/* Use n threads from now on whatever OMP_NUM_THREADS says (torchrun exports
+ * OMP_NUM_THREADS=1 to its workers; the CPU baseline is meant to use every host core). */
+void sem_oracle_c_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* L: [E][NN][NN] row-major, l2g: [E][NN] uint32, u, y: [n_nodes]; y is overwritten */
 void sem_oracle_c_apply_dense(int64_t E, int NN, int64_t n_nodes, const double *L,
                               const uint32_t *l2g, const double *u, double *y) {

@@ -94,6 +94,38 @@ class semk_sc_coarse(C.Structure):
     ]
 
 
+COMM_MAX_WORLD = 8
+
+
+class semk_comm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("capacity", C.c_int64),
+                ("regions", C.c_void_p * COMM_MAX_WORLD), ("status", C.c_void_p)]
+
+
+class semk_halo(C.Structure):
+    _fields_ = [("n_col", C.c_int64), ("mine", C.c_void_p), ("left", C.c_void_p),
+                ("right", C.c_void_p), ("epoch", C.c_uint64), ("status", C.c_void_p)]
+
+
+class semk_ml_dist(C.Structure):
+    _fields_ = [("comm", C.POINTER(semk_comm)), ("halo_f", C.POINTER(semk_halo)),
+                ("halo_c", C.POINTER(semk_halo)), ("n_owned_f", C.c_int64),
+                ("n_owned_c", C.c_int64)]
+
+
+class semk_ml_opts(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("inner_rtol", C.c_double), ("maxiter", C.c_int32),
+                ("inner_maxiter", C.c_int32), ("levels", C.c_int32), ("flexible", C.c_int32),
+                ("inner_chunk", C.c_int32), ("reserved", C.c_int32)]
+
+
+class semk_ml_info(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("status", C.c_int32), ("rel_residual", C.c_double),
+                ("true_rel_residual", C.c_double), ("bnorm", C.c_double),
+                ("inner_iterations", C.c_int64), ("inner_solves", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class semk_stage(C.Structure):
     _fields_ = [("patch_end", C.c_int64), ("chunk_end", C.c_int64), ("rec_end", C.c_int64),
                 ("u_need", C.c_int64), ("y_final", C.c_int64)]
@@ -150,13 +182,13 @@ SIGNATURES = {
     "semk_sc_coarse_elem_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _P]),
     "semk_sc_coarse_apply_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _I, _P, _P]),
     "semk_sc_coarse_assemble_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _P]),
-    "semk_sc_pcg2_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse), _P, _P, _P,
-                                    _P, _P, _P, _P, _P, _D, _I, _D, _I,
-                                    C.POINTER(semk_pcg_info), C.POINTER(C.c_int64), _P]),
-    "semk_sc_pcg3_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse),
-                                    C.POINTER(semk_sc_top), _P, _P, _P, _P, _P, _P, _P, _P, _D,
-                                    _I, _D, _I, C.POINTER(semk_pcg_info), C.POINTER(C.c_int64),
-                                    _P]),
+    "semk_sc_top_assemble_f64": (_I, [C.POINTER(semk_sc_coarse), _L, _P, _P, _P, _P, _P]),
+    "semk_comm_region_bytes": (_L, [C.c_int32, _L]),
+    "semk_comm_allreduce_f64": (_I, [C.POINTER(semk_comm), _P, _L, _P]),
+    "semk_sc_mlpcg_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse),
+                                     C.POINTER(semk_sc_top), C.POINTER(semk_ml_dist), _P, _P, _P,
+                                     _P, _P, _P, _P, _P, C.POINTER(semk_ml_opts),
+                                     C.POINTER(semk_ml_info), _P]),
     "semk_vec_resid_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
     "semk_vec_scale_f64": (_I, [_L, _P, _P, _P, _P]),
     "semk_vec_axpy2_f64": (_I, [_L, _D, _P, _P, _P, _P, _P]),

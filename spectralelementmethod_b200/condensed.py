@@ -31,7 +31,7 @@ from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
 from .operators import PCGInfo
 
 __all__ = ["CondensedPoissonOperator", "CondensedLocalSystems", "condensed_tables", "coarse_tables",
-           "element_tiles", "aggregate_tables", "top_level_inverse"]
+           "element_tiles", "aggregate_tables", "aggregate_csr", "top_level_inverse"]
 
 
 def condensed_tables(l2g, ext_loc, n_ext):
@@ -380,29 +380,61 @@ class CondensedPoissonOperator(object):
         self._coarse = (cs, t, n_v)
         return self._coarse
 
-    def _build_top(self, max_tiles=4096):
-        """Third level (lazy): vertex aggregates over element tiles and the dense
-        inverse of the aggregated coarse operator."""
+    def _build_top(self, max_tiles=4096, agg=None, n_agg=None, n_owned_c=None, reduce=None,
+                   source_rank=None):
+        """Third level (lazy): vertex aggregates and the dense inverse of the aggregated
+        coarse operator A3 = P2^T Ac P2, assembled and inverted on the device.
+
+        One GPU: aggregates = element tiles (element_tiles / aggregate_tables).  A strip
+        partition passes ``agg`` (GLOBAL aggregate id of every local vertex), the global
+        ``n_agg``, the owned vertex prefix ``n_owned_c`` and ``reduce`` (sums this rank's A3
+        over all ranks in place) -- the inverse is then replicated on every rank."""
         if getattr(self, "_top", None) is not None:
             return self._top
         cs, t, n_v = self._build_coarse()
-        tile = element_tiles(self.dof_mngr.mesh, self.n_elem, max_tiles)
-        vptr = t["vptr"].cpu().numpy().view(np.uint32)
-        vpos = t["vpos"].cpu().numpy().view(np.uint32)
-        vert_c = t["vert_c"].cpu().numpy().view(np.uint32)
-        at = aggregate_tables(vert_c, vptr, vpos, t["dirichlet_c_host"], tile)
-        A3inv = top_level_inverse(t["Ace"].cpu().numpy(), vert_c, at["agg"], at["n_agg"])
-        tt = dict(agg=device.as_i32_bits(at["agg"], self.dev),
-                  aptr=device.as_i32_bits(at["aptr"], self.dev),
-                  aidx=device.as_i32_bits(at["aidx"], self.dev),
-                  A3inv=device._f64(A3inv, self.dev))
+        if agg is None:
+            tile = element_tiles(self.dof_mngr.mesh, self.n_elem, max_tiles)
+            vptr = t["vptr"].cpu().numpy().view(np.uint32)
+            vpos = t["vpos"].cpu().numpy().view(np.uint32)
+            at = aggregate_tables(t["vert_c"].cpu().numpy().view(np.uint32), vptr, vpos,
+                                  t["dirichlet_c_host"], tile)
+            agg, n_agg = at["agg"], at["n_agg"]
+        agg = np.ascontiguousarray(agg, dtype=np.uint32)
+        n_agg = int(n_agg)
+        n_owned_c = n_v if n_owned_c is None else int(n_owned_c)
+        aptr_all, aidx_all = aggregate_csr(agg, n_agg, n_v)
+        aptr, aidx = aggregate_csr(agg, n_agg, n_owned_c)
+        tt = dict(agg=device.as_i32_bits(agg, self.dev),
+                  aptr=device.as_i32_bits(aptr, self.dev),
+                  aidx=device.as_i32_bits(aidx, self.dev),
+                  aptr_all=device.as_i32_bits(aptr_all, self.dev),
+                  aidx_all=device.as_i32_bits(aidx_all, self.dev))
+        A3 = torch.empty((n_agg, n_agg), dtype=torch.float64, device=self.dev)
+        _lib.check(self._lib.semk_sc_top_assemble_f64(
+            C.byref(cs), n_agg, device.ptr(tt["agg"]), device.ptr(tt["aptr_all"]),
+            device.ptr(tt["aidx_all"]), device.ptr(A3), device.stream_ptr()))
+        if reduce is not None:
+            reduce(A3)
+        A3 = 0.5 * (A3 + A3.t())
+        d = torch.diagonal(A3)
+        d[d == 0.0] = 1.0                     # aggregates without a free vertex
+        # set-up only: dense SPD inverse by the vendor library (it enters the preconditioner,
+        # not the solution); the solve itself runs on this repo's kernels
+        inv = torch.linalg.inv(A3)
+        if not bool(torch.isfinite(inv).all()):
+            raise AssertionError("the aggregated coarse operator is singular")
+        tt["A3inv"] = (0.5 * (inv + inv.t())).contiguous()
+        if source_rank is not None:           # bit-identical copies on every rank
+            import torch.distributed as dist
+            dist.broadcast(tt["A3inv"], src=source_rank)
+        del A3, inv
         top = _lib.semk_sc_top()
-        top.n_agg = at["n_agg"]
+        top.n_agg = n_agg
         top.agg = tt["agg"].data_ptr()
         top.aptr = tt["aptr"].data_ptr()
         top.aidx = tt["aidx"].data_ptr()
         top.A3inv = tt["A3inv"].data_ptr()
-        self._top = (top, tt, at["n_agg"])
+        self._top = (top, tt, n_agg)
         return self._top
 
     def coarse_apply(self, xc, out=None, dot_out=None):
@@ -416,13 +448,19 @@ class CondensedPoissonOperator(object):
         return y
 
     def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25,
-                  preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000):
+                  preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000, flexible=True,
+                  inner_chunk=4, max_tiles=4096, dist=None):
         """PCG on Shat x = b (b already lifted); returns (x, PCGInfo).
 
-        preconditioner : "jacobi" (diagonal of Shat) or "two-level" (Jacobi + a
-            vertex coarse space, M^-1 = D^-1 + P Ac^-1 P^T with linear interpolation
-            along element edges and an inner Jacobi-PCG on Ac to ``inner_rtol``):
-            the outer iteration count no longer grows with the mesh size."""
+        preconditioner : "jacobi" (diagonal of Shat); "two-level" (Jacobi + a vertex coarse
+            space, M^-1 = D^-1 + P Ac^-1 P^T with linear interpolation along element edges
+            and an inner Jacobi-PCG on Ac to ``inner_rtol``): the outer iteration count no
+            longer grows with the mesh size; "three-level": the inner solve is itself
+            preconditioned by Jacobi + an aggregation level with a dense inverse, so the
+            inner count stops growing as well.  The multilevel variants run the native driver
+            semk_sc_mlpcg_solve_f64 (flexible CG outside: the inner solve is inexact) and
+            report the true residual of the returned iterate.
+        dist : (semk_ml_dist, dinv, dinv_c) of a strip partition (distributed.py), else None."""
         self._vec(b, "b")
         if preconditioner not in ("jacobi", "two-level", "three-level"):
             raise ValueError("preconditioner must be 'jacobi', 'two-level' or 'three-level'")
@@ -433,42 +471,34 @@ class CondensedPoissonOperator(object):
                 x[m] = b[m]
         else:
             x = self._vec(x0, "x0").clone()
+        if preconditioner != "jacobi":
+            cs, t, n_v = self._build_coarse()
+            levels = 3 if preconditioner == "three-level" else 2
+            top, n_agg = None, 0
+            if levels == 3:
+                top, tt, n_agg = self._build_top(max_tiles)
+            dptr, dinv, dinv_c = None, self.jacobi_inverse(), t["dinv_c"]
+            if dist is not None:
+                dptr, dinv, dinv_c = C.byref(dist[0]), dist[1], dist[2]
+            work = torch.empty(4 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
+            work_c = torch.empty(6 * (n_v + 32) + 2 * (n_agg + 64), dtype=torch.float64,
+                                 device=self.dev)
+            sc = torch.zeros(64, dtype=torch.float64, device=self.dev)
+            opts = _lib.semk_ml_opts(float(rtol), float(inner_rtol), int(maxiter),
+                                     int(inner_maxiter), levels, 1 if flexible else 0,
+                                     int(inner_chunk), 0)
+            info = _lib.semk_ml_info()
+            rc = self._lib.semk_sc_mlpcg_solve_f64(
+                C.byref(self._op), C.byref(cs), C.byref(top) if top is not None else None, dptr,
+                device.ptr(b), device.ptr(x), device.ptr(dinv), device.ptr(dinv_c),
+                device.ptr(work), device.ptr(work_c), device.ptr(sc),
+                device.ptr(self.vec_partials), C.byref(opts), C.byref(info), device.stream_ptr())
+            _lib.check(rc)
+            self.last_inner_iterations = int(info.inner_iterations)
+            return x, PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm,
+                              info.true_rel_residual, info.inner_iterations, info.inner_solves)
         dinv = self.jacobi_inverse()
         info = _lib.semk_pcg_info()
-        if preconditioner == "three-level":
-            # EXPERIMENTAL: checked against a NumPy emulation on CPU
-            # (tests/test_two_level_host.py); the device path has not run on a GPU yet.
-            cs, t, n_v = self._build_coarse()
-            top, tt, n_agg = self._build_top()
-            work = torch.empty(4 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
-            work_c = torch.empty(6 * (n_v + 32) + 2 * (n_agg + 32), dtype=torch.float64,
-                                 device=self.dev)
-            sc = torch.zeros(16, dtype=torch.float64, device=self.dev)
-            inner = C.c_int64(0)
-            rc = self._lib.semk_sc_pcg3_solve_f64(
-                C.byref(self._op), C.byref(cs), C.byref(top), device.ptr(b), device.ptr(x),
-                device.ptr(dinv), device.ptr(t["dinv_c"]), device.ptr(work), device.ptr(work_c),
-                device.ptr(sc), device.ptr(self.vec_partials), float(rtol), int(maxiter),
-                float(inner_rtol), int(inner_maxiter), C.byref(info), C.byref(inner),
-                device.stream_ptr())
-            _lib.check(rc)
-            self.last_inner_iterations = int(inner.value)
-            return x, PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
-        if preconditioner == "two-level":
-            cs, t, n_v = self._build_coarse()
-            work = torch.empty(4 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
-            work_c = torch.empty(5 * (n_v + 32), dtype=torch.float64, device=self.dev)
-            sc = torch.zeros(16, dtype=torch.float64, device=self.dev)
-            inner = C.c_int64(0)
-            rc = self._lib.semk_sc_pcg2_solve_f64(
-                C.byref(self._op), C.byref(cs), device.ptr(b), device.ptr(x), device.ptr(dinv),
-                device.ptr(t["dinv_c"]), device.ptr(work), device.ptr(work_c), device.ptr(sc),
-                device.ptr(self.vec_partials), float(rtol), int(maxiter), float(inner_rtol),
-                int(inner_maxiter), C.byref(info), C.byref(inner), device.stream_ptr())
-            _lib.check(rc)
-            out = PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
-            self.last_inner_iterations = int(inner.value)
-            return x, out
         work = torch.empty(3 * (self.n_ext + 32), dtype=torch.float64, device=self.dev)
         sc = torch.zeros(8, dtype=torch.float64, device=self.dev)
         rc = self._lib.semk_sc_pcg_solve_f64(
@@ -477,6 +507,16 @@ class CondensedPoissonOperator(object):
             int(check_every), C.byref(info), device.stream_ptr())
         _lib.check(rc)
         return x, PCGInfo(info.iterations, info.status, info.rel_residual, info.bnorm)
+
+    def true_residual(self, b, x):
+        """||b - Shat x|| / ||b|| over the free rows (diagnostics; one apply)."""
+        r = b - self.apply(x)
+        bm = b
+        if self.has_dirichlet:
+            m = self.dirichlet_dev.bool()
+            r = torch.where(m, torch.zeros_like(r), r)
+            bm = torch.where(m, torch.zeros_like(b), b)
+        return float(r.norm() / bm.norm())
 
     def backsolve(self, x_ext, f=1.0, out=None):
         """Full nodal vector from the exterior solution: interiors
@@ -673,9 +713,22 @@ def aggregate_tables(vert_c, vptr, vpos, dirichlet_c, tile):
     return dict(agg=agg, n_agg=n_agg, aptr=aptr, aidx=aidx)
 
 
+def aggregate_csr(agg, n_agg, n_limit):
+    """CSR (aptr, aidx) of the vertices ``v < n_limit`` of every aggregate, ascending."""
+    agg = np.asarray(agg, dtype=np.uint32)[:int(n_limit)]
+    ids = np.flatnonzero(agg != 0xFFFFFFFF)
+    a = agg[ids].astype(np.int64)
+    order = np.argsort(a, kind="stable")
+    aidx = ids[order].astype(np.uint32)
+    aptr = np.zeros(int(n_agg) + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(a, minlength=int(n_agg)), out=aptr[1:])
+    return aptr, aidx
+
+
 def top_level_inverse(Ace, vert_c, agg, n_agg):
     """Dense inverse of the third-level operator P2^T Ac P2 from the element coarse
-    matrices (host, set-up only; it enters the preconditioner, not the solution)."""
+    matrices on the HOST (the NumPy emulation in tests/test_two_level_host.py; the product
+    assembles and inverts it on the device, CondensedPoissonOperator._build_top)."""
     from scipy import sparse
     a = agg.astype(np.int64)[np.asarray(vert_c, dtype=np.int64)]          # [E, 4]
     a[a == 0xFFFFFFFF] = -1

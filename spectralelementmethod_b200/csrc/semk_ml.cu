@@ -375,6 +375,32 @@ __global__ void __launch_bounds__(kT)
   }
 }
 
+// A3 = P2^T Ac P2 from the element coarse matrices, one thread per row: the thread walks
+// the (local) vertices of its aggregate, their element entries and the four columns of
+// each -- a fixed order and no atomics, so the result is bit-reproducible.
+__global__ void __launch_bounds__(kT)
+    ml_top_assemble_kernel(int64_t n_agg, const uint32_t *__restrict__ agg,
+                           const uint32_t *__restrict__ aptr, const uint32_t *__restrict__ aidx,
+                           const uint32_t *__restrict__ vptr, const uint32_t *__restrict__ vpos,
+                           const uint32_t *__restrict__ vert_c, const double *__restrict__ Ace,
+                           double *__restrict__ A3) {
+  const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= n_agg) return;
+  double *row = A3 + a * n_agg;
+  for (uint32_t k = aptr[a]; k < aptr[a + 1]; ++k) {
+    const uint32_t v = aidx[k];
+    for (uint32_t q = vptr[v]; q < vptr[v + 1]; ++q) {
+      const uint32_t ent = vpos[q];            // e * 4 + i
+      const uint32_t e = ent >> 2, i = ent & 3u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t col = agg[vert_c[e * 4 + j]];
+        if (col != 0xffffffffu) row[col] += Ace[(int64_t)e * 16 + i * 4 + j];
+      }
+    }
+  }
+}
+
 CommDev make_comm(const semk_comm *c) {
   CommDev d{};
   d.world = 1;
@@ -419,6 +445,21 @@ extern "C" int semk_comm_allreduce_f64(const semk_comm *comm, double *buf, int64
   if (comm->world == 1) return SEMK_OK;
   allreduce_kernel<<<1, kStepThreads, 0, semk_stream(stream)>>>(make_comm(comm), buf, (int)n);
   SEMK_LAUNCH_CHECK("allreduce_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_top_assemble_f64(const semk_sc_coarse *cs, int64_t n_agg,
+                                       const uint32_t *agg, const uint32_t *aptr_all,
+                                       const uint32_t *aidx_all, double *A3, void *stream) {
+  SEMK_REQUIRE(cs && cs->Ace && cs->vert_c && cs->vptr && cs->vpos && n_agg > 0 && agg &&
+                   aptr_all && aidx_all && A3,
+               "semk_sc_top_assemble_f64: bad argument");
+  cudaStream_t st = semk_stream(stream);
+  SEMK_CUDA_CHECK(cudaMemsetAsync(A3, 0, sizeof(double) * (size_t)n_agg * (size_t)n_agg, st));
+  const unsigned grid = (unsigned)((n_agg + 63) / 64);
+  ml_top_assemble_kernel<<<grid, 64, 0, st>>>(n_agg, agg, aptr_all, aidx_all, cs->vptr, cs->vpos,
+                                              cs->vert_c, cs->Ace, A3);
+  SEMK_LAUNCH_CHECK("ml_top_assemble_kernel");
   return SEMK_OK;
 }
 

@@ -345,7 +345,9 @@ static int pcg_solve_impl(ApplyFn apply, int64_t n, const uint8_t *dirichlet, co
   const int64_t n_pad = (n + 31) & ~(int64_t)31;  // keeps the sub-vectors 16-byte aligned
   double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad;
   const double tol2 = rtol * rtol;
-  static double *h_sc = nullptr;  // pinned landing zone for the 64-byte scalar block
+  // pinned landing zone for the 64-byte scalar block: one per host thread (a solve blocks
+  // its thread while it polls, so solves on different threads / streams never share it)
+  thread_local double *h_sc = nullptr;
   if (!h_sc) SEMK_CUDA_CHECK(cudaMallocHost(&h_sc, 8 * sizeof(double)));
 
   int rc = apply(x, Ap, nullptr);
@@ -401,7 +403,9 @@ static int pcg_solve_impl(ApplyFn apply, int64_t n, const uint8_t *dirichlet, co
   int launched = 0;
   rc = SEMK_OK;
   while (launched < maxiter) {
-    if (use_graph) {
+    // the graph holds exactly check_every iterations: a shorter tail is launched eagerly so
+    // that maxiter is never exceeded
+    if (use_graph && maxiter - launched >= check_every) {
       if (cudaGraphLaunch(exec, st) != cudaSuccess) {
         semk_set_error("PCG driver: cudaGraphLaunch failed");
         rc = SEMK_ERR_CUDA;
@@ -473,10 +477,9 @@ extern "C" int semk_sc_pcg_solve_f64(const semk_sc_op *op, const double *b, doub
 }
 
 // ---------------------------------------------------------------------------------------
-// Two-level PCG on the condensed system: Jacobi + vertex coarse space (include/semk.h).
-// The outer loop is driven from the host (a few tens of iterations, each containing an
-// inner coarse solve that polls the device anyway); its scalars come back through
-// 8-byte copies.  Inner solves reuse pcg_solve_impl on the coarse operator.
+// Small vector kernels of the multilevel preconditioner as separate entry points (the
+// native driver is semk_sc_mlpcg_solve_f64, csrc/semk_ml.cu; these serve tests and
+// host-driven experiments).
 // ---------------------------------------------------------------------------------------
 namespace {
 
@@ -552,116 +555,6 @@ __global__ void __launch_bounds__(kVecThreads)
 
 }  // namespace
 
-extern "C" int semk_sc_pcg2_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs,
-                                      const double *b, double *x, const double *dinv,
-                                      const double *dinv_c, double *work, double *work_c,
-                                      double *sc, double *vec_partials, double rtol, int maxiter,
-                                      double inner_rtol, int inner_maxiter, semk_pcg_info *info,
-                                      int64_t *inner_total, void *stream) {
-  SEMK_REQUIRE(op && cs && b && x && dinv && dinv_c && work && work_c && sc && vec_partials && info,
-               "semk_sc_pcg2_solve_f64: null pointer");
-  SEMK_REQUIRE(maxiter >= 0 && inner_maxiter >= 1 && rtol >= 0.0 && inner_rtol > 0.0,
-               "semk_sc_pcg2_solve_f64: bad control");
-  SEMK_REQUIRE(cs->pv && cs->pw && cs->rptr && cs->ridx && cs->rw,
-               "semk_sc_pcg2_solve_f64: missing transfer tables");
-  cudaStream_t st = semk_stream(stream);
-  const int64_t n = op->n_ext, nv = cs->n_v, n_elem = op->n_elem;
-  const int64_t n_pad = (n + 31) & ~(int64_t)31, nv_pad = (nv + 31) & ~(int64_t)31;
-  double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad, *z = work + 3 * n_pad;
-  double *rc = work_c, *xc = work_c + nv_pad, *inner_work = work_c + 2 * nv_pad;
-  double *d_out = sc + 8;  // device scalars of the outer loop; sc[0..8) belong to the inner solves
-  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
-  const dim3 g(vec_blocks(n)), gc(vec_blocks(nv)), blk(kVecThreads);
-  int64_t inner_sum = 0;
-
-  auto fetch = [&](double *host_val) -> int {
-    SEMK_CUDA_CHECK(cudaMemcpyAsync(host_val, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
-    SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
-    return SEMK_OK;
-  };
-  auto dot = [&](const double *a, const double *c, double *host_val) -> int {
-    int e = semk_dot_f64(n, a, c, d_out, vec_partials, st);
-    if (e != SEMK_OK) return e;
-    return fetch(host_val);
-  };
-  auto coarse_apply = [&](const double *in, double *out, double *dptr) -> int {
-    return semk_sc_coarse_apply_f64(n_elem, cs, in, out, flags, dptr, st);
-  };
-  // z = M^{-1} r = dinv r + P Ac^{-1} P^T r
-  auto precondition = [&]() -> int {
-    scale_kernel<<<g, blk, 0, st>>>(n, dinv, r, z);
-    SEMK_LAUNCH_CHECK("scale_kernel");
-    restrict_kernel<<<gc, blk, 0, st>>>(nv, cs->rptr, cs->ridx, cs->rw, r, n, rc);
-    SEMK_LAUNCH_CHECK("restrict_kernel");
-    SEMK_CUDA_CHECK(cudaMemsetAsync(xc, 0, sizeof(double) * nv, st));
-    semk_pcg_info ii;
-    int e = pcg_solve_impl(coarse_apply, nv, cs->dirichlet_c, rc, xc, dinv_c, inner_work, sc,
-                           vec_partials, inner_rtol, inner_maxiter, 50, &ii, st);
-    if (e != SEMK_OK) return e;
-    inner_sum += ii.iterations;
-    prolong_add_kernel<<<g, blk, 0, st>>>(n, cs->pv, cs->pw, xc, z);
-    SEMK_LAUNCH_CHECK("prolong_add_kernel");
-    return SEMK_OK;
-  };
-
-  int rcode = semk_sc_apply_f64(op, x, Ap, flags, nullptr, st);
-  if (rcode != SEMK_OK) return rcode;
-  resid_kernel<<<g, blk, 0, st>>>(n, b, Ap, op->dirichlet, r, z);  // z = masked b for ||b||
-  SEMK_LAUNCH_CHECK("resid_kernel");
-  double bb = 0.0, rr = 0.0, rz = 0.0;
-  if ((rcode = dot(z, z, &bb)) != SEMK_OK) return rcode;
-  if ((rcode = dot(r, r, &rr)) != SEMK_OK) return rcode;
-  const double tol2 = rtol * rtol;
-  info->bnorm = sqrt(bb);
-  info->iterations = 0;
-  info->status = 0;
-  if (inner_total) *inner_total = 0;
-  if (bb == 0.0 || rr <= tol2 * bb) {
-    info->rel_residual = bb > 0.0 ? sqrt(rr / bb) : 0.0;
-    return SEMK_OK;
-  }
-  if ((rcode = precondition()) != SEMK_OK) return rcode;
-  SEMK_CUDA_CHECK(cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-  if ((rcode = dot(r, z, &rz)) != SEMK_OK) return rcode;
-  int status = 1, it = 0;
-  while (it < maxiter) {
-    rcode = semk_sc_apply_f64(op, p, Ap, flags, d_out, st);
-    if (rcode != SEMK_OK) return rcode;
-    double pAp = 0.0;
-    if ((rcode = fetch(&pAp)) != SEMK_OK) return rcode;
-    if (!(pAp > 0.0) || !(rz == rz)) {
-      status = SEMK_ERR_BREAKDOWN;
-      break;
-    }
-    const double alpha = rz / pAp;
-    axpy2_kernel<<<g, blk, 0, st>>>(n, alpha, p, Ap, x, r);
-    SEMK_LAUNCH_CHECK("axpy2_kernel");
-    ++it;
-    if ((rcode = dot(r, r, &rr)) != SEMK_OK) return rcode;
-    if (rr <= tol2 * bb) {
-      status = 0;
-      break;
-    }
-    if ((rcode = precondition()) != SEMK_OK) return rcode;
-    double rz_new = 0.0;
-    if ((rcode = dot(r, z, &rz_new)) != SEMK_OK) return rcode;
-    const double beta = rz_new / rz;
-    xpay_kernel<<<g, blk, 0, st>>>(n, beta, z, p);
-    SEMK_LAUNCH_CHECK("xpay_kernel");
-    rz = rz_new;
-  }
-  SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
-  info->iterations = it;
-  info->status = status;
-  info->rel_residual = sqrt(rr / bb);
-  if (inner_total) *inner_total = inner_sum;
-  if (status == SEMK_ERR_BREAKDOWN) {
-    semk_set_error("semk_sc_pcg2_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
-    return SEMK_ERR_BREAKDOWN;
-  }
-  return SEMK_OK;
-}
-
 // ---- the pieces of the two-level preconditioner as separate entry points (the multi-GPU
 // outer loop, distributed.distributed_two_level_pcg, is driven from Python so that the
 // exchanges and all-reduces can sit between them) -------------------------------------------
@@ -719,218 +612,3 @@ extern "C" int semk_sc_prolong_add_f64(int64_t n_ext, const semk_sc_coarse *cs, 
   return SEMK_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// Three-level PCG on the condensed system (include/semk.h, semk_sc_pcg3_solve_f64): the
-// inner coarse solve of the two-level scheme gets its own preconditioner, Jacobi + a
-// piecewise-constant aggregation level with a dense inverse at the top, so that the inner
-// iteration count stops growing with the mesh as well.  Both loops are host-driven
-// (host_pcg); nothing above this line is changed by it.
-// ---------------------------------------------------------------------------------------
-namespace {
-
-// r3[a] = sum of q over the vertices of aggregate a: one warp per aggregate, lane-strided
-// partial sums and a fixed shuffle tree (deterministic)
-__global__ void __launch_bounds__(kVecThreads)
-    agg_restrict_kernel(int64_t n_agg, const uint32_t *__restrict__ aptr,
-                        const uint32_t *__restrict__ aidx, const double *__restrict__ q,
-                        double *__restrict__ r3) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t a = warp; a < n_agg; a += nwarps) {
-    double s = 0.0;
-    for (uint32_t k = aptr[a] + lane; k < aptr[a + 1]; k += 32) s += q[aidx[k]];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) r3[a] = s;
-  }
-}
-
-// y = A x, A dense [n][n] row major: one warp per row (deterministic)
-__global__ void __launch_bounds__(kVecThreads)
-    dense_matvec_kernel(int64_t n, const double *__restrict__ A, const double *__restrict__ x,
-                        double *__restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < n; i += nwarps) {
-    const double *row = A + i * n;
-    double s = 0.0;
-    for (int64_t j = lane; j < n; j += 32) s = fma(row[j], x[j], s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[i] = s;
-  }
-}
-
-// z[v] += y3[agg[v]] (vertices without an aggregate -- the essential boundary -- untouched)
-__global__ void __launch_bounds__(kVecThreads)
-    agg_prolong_add_kernel(int64_t n_v, const uint32_t *__restrict__ agg,
-                           const double *__restrict__ y3, double *__restrict__ z) {
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_v;
-       v += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t a = agg[v];
-    if (a != 0xffffffffu) z[v] += y3[a];
-  }
-}
-
-struct HostPcgResult {
-  int iterations = 0;
-  int status = 1;  // 0 converged, 1 maxiter, SEMK_ERR_BREAKDOWN
-  double rel = 0.0, bnorm = 0.0;
-};
-
-// Preconditioned CG driven from the host: apply(in, out, dot_dev) queues out = A in and
-// leaves in.out in *dot_dev; precond() must turn the residual r into z.  Vectors r, p, Ap,
-// z are caller scratch of length n; d_out is one device double.
-template <class Apply, class Precond>
-int host_pcg(Apply apply, Precond precond, int64_t n, const uint8_t *dirichlet, const double *b,
-             double *x, double *r, double *p, double *Ap, double *z, double *d_out,
-             double *partials, double rtol, int maxiter, cudaStream_t st, HostPcgResult *res) {
-  const dim3 g(vec_blocks(n)), blk(kVecThreads);
-  auto fetch = [&](double *host_val) -> int {
-    SEMK_CUDA_CHECK(cudaMemcpyAsync(host_val, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
-    SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
-    return SEMK_OK;
-  };
-  auto dot = [&](const double *a, const double *c, double *host_val) -> int {
-    int e = semk_dot_f64(n, a, c, d_out, partials, st);
-    if (e != SEMK_OK) return e;
-    return fetch(host_val);
-  };
-  int rc = apply(x, Ap, nullptr);
-  if (rc != SEMK_OK) return rc;
-  resid_kernel<<<g, blk, 0, st>>>(n, b, Ap, dirichlet, r, z);  // z = masked b for ||b||
-  SEMK_LAUNCH_CHECK("resid_kernel");
-  double bb = 0.0, rr = 0.0, rz = 0.0;
-  if ((rc = dot(z, z, &bb)) != SEMK_OK) return rc;
-  if ((rc = dot(r, r, &rr)) != SEMK_OK) return rc;
-  const double tol2 = rtol * rtol;
-  res->bnorm = sqrt(bb);
-  res->iterations = 0;
-  res->status = 0;
-  if (bb == 0.0 || rr <= tol2 * bb) {
-    res->rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
-    return SEMK_OK;
-  }
-  if ((rc = precond()) != SEMK_OK) return rc;
-  SEMK_CUDA_CHECK(cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-  if ((rc = dot(r, z, &rz)) != SEMK_OK) return rc;
-  int status = 1, it = 0;
-  while (it < maxiter) {
-    if ((rc = apply(p, Ap, d_out)) != SEMK_OK) return rc;
-    double pAp = 0.0;
-    if ((rc = fetch(&pAp)) != SEMK_OK) return rc;
-    if (!(pAp > 0.0) || !(rz == rz)) {
-      status = SEMK_ERR_BREAKDOWN;
-      break;
-    }
-    axpy2_kernel<<<g, blk, 0, st>>>(n, rz / pAp, p, Ap, x, r);
-    SEMK_LAUNCH_CHECK("axpy2_kernel");
-    ++it;
-    if ((rc = dot(r, r, &rr)) != SEMK_OK) return rc;
-    if (rr <= tol2 * bb) {
-      status = 0;
-      break;
-    }
-    if ((rc = precond()) != SEMK_OK) return rc;
-    double rz_new = 0.0;
-    if ((rc = dot(r, z, &rz_new)) != SEMK_OK) return rc;
-    xpay_kernel<<<g, blk, 0, st>>>(n, rz_new / rz, z, p);
-    SEMK_LAUNCH_CHECK("xpay_kernel");
-    rz = rz_new;
-  }
-  res->iterations = it;
-  res->status = status;
-  res->rel = sqrt(rr / bb);
-  return SEMK_OK;
-}
-
-}  // namespace
-
-extern "C" int semk_sc_pcg3_solve_f64(const semk_sc_op *op, const semk_sc_coarse *cs,
-                                      const semk_sc_top *top, const double *b, double *x,
-                                      const double *dinv, const double *dinv_c, double *work,
-                                      double *work_c, double *sc, double *vec_partials,
-                                      double rtol, int maxiter, double inner_rtol,
-                                      int inner_maxiter, semk_pcg_info *info,
-                                      int64_t *inner_total, void *stream) {
-  SEMK_REQUIRE(op && cs && top && b && x && dinv && dinv_c && work && work_c && sc &&
-                   vec_partials && info,
-               "semk_sc_pcg3_solve_f64: null pointer");
-  SEMK_REQUIRE(maxiter >= 0 && inner_maxiter >= 1 && rtol >= 0.0 && inner_rtol > 0.0,
-               "semk_sc_pcg3_solve_f64: bad control");
-  SEMK_REQUIRE(cs->pv && cs->pw && cs->rptr && cs->ridx && cs->rw,
-               "semk_sc_pcg3_solve_f64: missing transfer tables");
-  SEMK_REQUIRE(top->n_agg > 0 && top->agg && top->aptr && top->aidx && top->A3inv,
-               "semk_sc_pcg3_solve_f64: inconsistent semk_sc_top");
-  cudaStream_t st = semk_stream(stream);
-  const int64_t n = op->n_ext, nv = cs->n_v, na = top->n_agg, n_elem = op->n_elem;
-  const int64_t n_pad = (n + 31) & ~(int64_t)31, nv_pad = (nv + 31) & ~(int64_t)31;
-  const int64_t na_pad = (na + 31) & ~(int64_t)31;
-  double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad, *z = work + 3 * n_pad;
-  double *rc = work_c, *xc = work_c + nv_pad;
-  double *ri = work_c + 2 * nv_pad, *pi = work_c + 3 * nv_pad, *Api = work_c + 4 * nv_pad,
-         *zi = work_c + 5 * nv_pad;
-  double *r3 = work_c + 6 * nv_pad, *y3 = r3 + na_pad;
-  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
-  const dim3 g(vec_blocks(n)), gc(vec_blocks(nv)), blk(kVecThreads);
-  const dim3 ga((unsigned)((na * 32 + kVecThreads - 1) / kVecThreads < kVecMaxBlocks
-                               ? (na * 32 + kVecThreads - 1) / kVecThreads
-                               : kVecMaxBlocks));
-  int64_t inner_sum = 0;
-
-  auto fine_apply = [&](const double *in, double *out, double *dptr) -> int {
-    return semk_sc_apply_f64(op, in, out, flags, dptr, st);
-  };
-  auto coarse_apply = [&](const double *in, double *out, double *dptr) -> int {
-    return semk_sc_coarse_apply_f64(n_elem, cs, in, out, flags, dptr, st);
-  };
-  // coarse-level preconditioner: zi = dinv_c ri + P2 A3^{-1} P2^T ri
-  auto coarse_precond = [&]() -> int {
-    scale_kernel<<<gc, blk, 0, st>>>(nv, dinv_c, ri, zi);
-    SEMK_LAUNCH_CHECK("scale_kernel");
-    agg_restrict_kernel<<<ga, blk, 0, st>>>(na, top->aptr, top->aidx, ri, r3);
-    SEMK_LAUNCH_CHECK("agg_restrict_kernel");
-    dense_matvec_kernel<<<ga, blk, 0, st>>>(na, top->A3inv, r3, y3);
-    SEMK_LAUNCH_CHECK("dense_matvec_kernel");
-    agg_prolong_add_kernel<<<gc, blk, 0, st>>>(nv, top->agg, y3, zi);
-    SEMK_LAUNCH_CHECK("agg_prolong_add_kernel");
-    return SEMK_OK;
-  };
-  // fine-level preconditioner: z = dinv r + P Ac^{-1} P^T r, Ac^{-1} by the inner PCG
-  auto fine_precond = [&]() -> int {
-    scale_kernel<<<g, blk, 0, st>>>(n, dinv, r, z);
-    SEMK_LAUNCH_CHECK("scale_kernel");
-    restrict_kernel<<<gc, blk, 0, st>>>(nv, cs->rptr, cs->ridx, cs->rw, r, n, rc);
-    SEMK_LAUNCH_CHECK("restrict_kernel");
-    SEMK_CUDA_CHECK(cudaMemsetAsync(xc, 0, sizeof(double) * nv, st));
-    HostPcgResult ir;
-    int e = host_pcg(coarse_apply, coarse_precond, nv, cs->dirichlet_c, rc, xc, ri, pi, Api, zi,
-                     sc + 9, vec_partials, inner_rtol, inner_maxiter, st, &ir);
-    if (e != SEMK_OK) return e;
-    if (ir.status == SEMK_ERR_BREAKDOWN) {
-      semk_set_error("semk_sc_pcg3_solve_f64: inner breakdown (p.Ap <= 0 or non-finite)");
-      return SEMK_ERR_BREAKDOWN;
-    }
-    inner_sum += ir.iterations;
-    prolong_add_kernel<<<g, blk, 0, st>>>(n, cs->pv, cs->pw, xc, z);
-    SEMK_LAUNCH_CHECK("prolong_add_kernel");
-    return SEMK_OK;
-  };
-  HostPcgResult res;
-  int rcode = host_pcg(fine_apply, fine_precond, n, op->dirichlet, b, x, r, p, Ap, z, sc + 8,
-                       vec_partials, rtol, maxiter, st, &res);
-  if (rcode != SEMK_OK) return rcode;
-  SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
-  info->iterations = res.iterations;
-  info->status = res.status;
-  info->rel_residual = res.rel;
-  info->bnorm = res.bnorm;
-  if (inner_total) *inner_total = inner_sum;
-  if (res.status == SEMK_ERR_BREAKDOWN) {
-    semk_set_error("semk_sc_pcg3_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
-    return SEMK_ERR_BREAKDOWN;
-  }
-  return SEMK_OK;
-}

@@ -29,7 +29,8 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["StripPartition", "CondensedStripView", "DistributedOperator", "PeerHalo",
-           "distributed_pcg", "distributed_two_level_pcg", "DistributedPoisson",
+           "PeerComm", "distributed_pcg", "distributed_multilevel_pcg",
+           "strip_vertex_aggregates", "DistributedPoisson",
            "DistributedCondensedPoisson"]
 
 
@@ -137,70 +138,108 @@ class CondensedStripView(object):
         return slice(self.n_local - self.NY, self.n_local)
 
 
+def _all_ok(ok, group, device):
+    """Collective AND of a per-rank success flag."""
+    t = torch.tensor([1.0 if ok else 0.0], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return float(t) >= 1.0
+
+
+class _PeerRegions(object):
+    """One exported region per rank + the mappings of a set of peers (CUDA IPC).  Set-up and
+    tear-down are COLLECTIVE and symmetric: either every rank ends up with all its mappings
+    or every rank raises, and nobody frees a region that a peer may still have mapped
+    (close the mappings, barrier, then free)."""
+
+    def __init__(self, nbytes, peers, group, device):
+        import ctypes as C
+        from . import _lib
+        self._lib = lib = _lib.load()
+        self._check = _lib.check
+        self.group, self.device = group, device
+        self.mine = C.c_void_p()
+        self.mapped = {}                     # peer rank -> c_void_p
+        handle = (C.c_ubyte * 64)()
+        err = None
+        try:
+            _lib.check(lib.semk_peer_alloc(int(nbytes), C.byref(self.mine), handle))
+        except Exception as e:              # noqa: BLE001 -- re-raised collectively below
+            err = e
+        handles = [None] * dist.get_world_size(group)
+        dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
+        for peer in peers:
+            if err is not None:
+                break
+            try:
+                if handles[peer] is None:
+                    raise RuntimeError("rank %d could not export its region" % peer)
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
+                ptr = C.c_void_p()
+                _lib.check(lib.semk_peer_open(buf, C.byref(ptr)))
+                self.mapped[peer] = ptr
+            except Exception as e:          # noqa: BLE001
+                err = e
+        if not _all_ok(err is None, group, device):
+            self.close()
+            raise RuntimeError("peer-memory regions unavailable on at least one rank: %r" % (err,))
+
+    def close(self):
+        """Collective: all ranks unmap their peers before anyone frees."""
+        if self.device is not None and torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
+        for ptr in self.mapped.values():
+            if ptr:
+                self._lib.semk_peer_close(ptr)
+        self.mapped = {}
+        dist.barrier(group=self.group)
+        if self.mine:
+            self._lib.semk_peer_free(self.mine)
+            self.mine.value = None
+
+
 class PeerHalo(object):
     """Interface exchange over NVLink peer memory: every rank exports one
     exchange region (flags + receive buffers) through CUDA IPC and maps its
     neighbours' regions; ``exchange`` launches the single fused kernel
     semk_halo_exchange_f64 (push, publish epoch, wait, add, Dirichlet fix-up).
-    All ranks must call ``exchange`` the same number of times (SPMD)."""
+    All ranks must call ``exchange`` the same number of times (SPMD).  ``c`` is the
+    semk_halo struct the native multilevel driver uses to issue exchanges itself; the
+    epoch counter lives there, so Python- and C-issued exchanges share one sequence."""
 
     def __init__(self, part, group=None, device=None):
-        import ctypes as C
         from . import _lib
         self._lib = lib = _lib.load()
         self._check = _lib.check
         self.part = part
         self.group = group
         self.device = device
-        self.epoch = 0
-        self._mine = C.c_void_p()
-        self._left = C.c_void_p()
-        self._right = C.c_void_p()
         nbytes = int(lib.semk_halo_region_bytes(part.NY))
-        handle = (C.c_ubyte * 64)()
-        # every rank goes through the same collectives whatever fails locally
-        err = None
-        try:
-            _lib.check(lib.semk_peer_alloc(nbytes, C.byref(self._mine), handle))
-        except Exception as e:              # noqa: BLE001
-            err = e
-        handles = [None] * dist.get_world_size(group)
-        dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
-        for side, peer in ((self._left, part.left), (self._right, part.right)):
-            if peer is not None and err is None:
-                try:
-                    if handles[peer] is None:
-                        raise RuntimeError("neighbour %d could not export its region" % peer)
-                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
-                    _lib.check(lib.semk_peer_open(buf, C.byref(side)))
-                except Exception as e:      # noqa: BLE001
-                    err = e
+        peers = [q for q in (part.left, part.right) if q is not None]
+        self._regions = _PeerRegions(nbytes, peers, group, device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        dist.barrier(group=group)
-        if err is not None:
-            self._release()
-            raise err
+        self.c = _lib.semk_halo()
+        self.c.n_col = part.NY
+        self.c.mine = self._regions.mine.value
+        self.c.left = self._regions.mapped[part.left].value if part.left is not None else None
+        self.c.right = self._regions.mapped[part.right].value if part.right is not None else None
+        self.c.epoch = 0
+        self.c.status = self.status.data_ptr()
 
-    def _release(self):
-        for side in (self._left, self._right):
-            if side:
-                self._lib.semk_peer_close(side)
-                side.value = None
-        if self._mine:
-            self._lib.semk_peer_free(self._mine)
-            self._mine.value = None
+    @property
+    def epoch(self):
+        return int(self.c.epoch)
 
     def exchange(self, y, u=None, dirichlet=None, dot_inout=None):
         """Sum the interface columns of y across neighbours in place; with
         ``dirichlet`` (uint8 device mask) also y = u on the Dirichlet nodes of
         those columns, and the doubly counted u^2 leaves ``dot_inout``."""
-        self.epoch += 1
+        self.c.epoch += 1
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self._check(self._lib.semk_halo_exchange_f64(
             self.part.NY, y.numel(), y.data_ptr(),
             u.data_ptr() if u is not None else None,
             dirichlet.data_ptr() if dirichlet is not None else None,
-            self._mine, self._left, self._right, self.epoch,
+            self.c.mine, self.c.left, self.c.right, self.c.epoch,
             dot_inout.data_ptr() if dot_inout is not None else None,
             self.status.data_ptr(), stream))
         return y
@@ -211,15 +250,48 @@ class PeerHalo(object):
             raise RuntimeError("peer halo exchange timed out waiting for a neighbour")
 
     def close(self):
-        """Collective: all ranks unmap their neighbours before anyone frees."""
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
-        for side in (self._left, self._right):
-            if side:
-                self._lib.semk_peer_close(side)
-                side.value = None
-        dist.barrier(group=self.group)
-        self._release()
+        self._regions.close()
+
+
+class PeerComm(object):
+    """Small-vector all-reduce over NVLink peer memory (semk_comm_allreduce_f64,
+    csrc/semk_ml.cu): every rank maps every other rank's region; one single-CTA kernel per
+    all-reduce pushes, publishes an epoch, waits and sums in rank order, so the result is
+    bit-identical on all ranks and the launch can sit inside a native solver loop."""
+
+    def __init__(self, rank, world, capacity, group=None, device=None):
+        from . import _lib
+        self._lib = lib = _lib.load()
+        self._check = _lib.check
+        if world > _lib.COMM_MAX_WORLD:
+            raise NotImplementedError("PeerComm supports up to %d ranks" % _lib.COMM_MAX_WORLD)
+        self.rank, self.world, self.capacity = int(rank), int(world), int(capacity)
+        self.group, self.device = group, device
+        nbytes = int(lib.semk_comm_region_bytes(self.world, self.capacity))
+        peers = [q for q in range(self.world) if q != self.rank]
+        self._regions = _PeerRegions(nbytes, peers, group, device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.c = _lib.semk_comm()
+        self.c.rank, self.c.world, self.c.capacity = self.rank, self.world, self.capacity
+        for q in range(self.world):
+            self.c.regions[q] = (self._regions.mine.value if q == self.rank
+                                 else self._regions.mapped[q].value)
+        self.c.status = self.status.data_ptr()
+
+    def allreduce(self, buf, n=None):
+        """buf[:n] <- sum over ranks, in place (float64 CUDA tensor, n <= capacity)."""
+        import ctypes as C
+        n = buf.numel() if n is None else int(n)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.semk_comm_allreduce_f64(C.byref(self.c), buf.data_ptr(), n, stream))
+        return buf
+
+    def check(self):
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer all-reduce timed out waiting for a rank")
+
+    def close(self):
+        self._regions.close()
 
 
 class DistributedOperator(object):
@@ -234,9 +306,11 @@ class DistributedOperator(object):
         the sum would double it).
     """
 
-    def __init__(self, part, local_apply, dirichlet=None, group=None, device=None, halo=None):
+    def __init__(self, part, local_apply, dirichlet=None, group=None, device=None, halo=None,
+                 dot=None):
         self.part = part
         self.local_apply = local_apply
+        self._dot = dot               # dot(a, b, out): the C-ABI reduction (PCGKernels.dot)
         self.group = group
         self.device = device
         self.halo = halo              # PeerHalo: fused NVLink exchange (else NCCL / gloo p2p)
@@ -299,12 +373,17 @@ class DistributedOperator(object):
         if dot_out is not None and self._fix_nonowned is not None:
             # identity rows on a shared column were counted by both ranks
             dup = u[self._fix_nonowned]
-            dot_out -= torch.dot(dup, dup)
+            dot_out -= (dup * dup).sum()
         return y
 
     def owned_dot(self, a, b):
+        """a . b over the owned prefix, summed over the ranks (1-element tensor)."""
         n = self.part.n_owned
-        s = torch.dot(a[:n], b[:n]).reshape(1)
+        if self._dot is not None:
+            s = torch.empty(1, dtype=torch.float64, device=a.device)
+            self._dot(a[:n], b[:n], s)
+        else:                         # CPU stand-in of the tests
+            s = torch.dot(a[:n], b[:n]).reshape(1)
         dist.all_reduce(s, group=self.group)
         return s
 
@@ -358,46 +437,81 @@ def distributed_pcg(dop, b, x, dinv, kernels, rtol=1e-12, maxiter=200000, check_
     return it, (float(h[3]) / bb) ** 0.5, False
 
 
-def distributed_two_level_pcg(dop, dop_c, ops, b, x, rtol=1e-12, maxiter=1000, inner_rtol=1e-2,
-                              inner_maxiter=20000, check_every=25):
-    """PCG over all ranks with the two-level preconditioner of the condensed system,
-    M^-1 = D^-1 + P Ac^-1 P^T (condensed.coarse_tables; single-GPU twin:
-    semk_sc_pcg2_solve_f64).
+def distributed_multilevel_pcg(dop, dop_c, ops, b, x, rtol=1e-12, maxiter=1000, inner_rtol=1e-2,
+                               inner_maxiter=20000, flexible=True, top=None):
+    """Host twin of the native multilevel driver (semk_sc_mlpcg_solve_f64, csrc/semk_ml.cu)
+    on a strip partition: the same algorithm, step by step, with the rank-local pieces
+    injected -- NumPy stand-ins in the world_size-2 gloo tests, which is how the N > 1
+    logic (owned prefixes, interface sums, replicated top level) is covered on CPU.
 
-    dop / dop_c : DistributedOperator of the fine (exterior) and the coarse (vertex)
-        level; their partition views give the owned prefixes for the dot products.
-    ops : the rank-local pieces, device kernels in production and NumPy stand-ins in
-        the CPU test --
-          residual(b, Ax) -> (r, b_masked)       r = b - Ax, zero on Dirichlet rows
-          jacobi(r) -> z                         z = dinv * r  (new vector)
-          restrict(r, n_owned) -> rc             P^T r over the first n_owned fine nodes
-          prolong_add(xc, z)                     z += P xc
-          axpy2(alpha, p, Ap, x, r)              x += alpha p ; r -= alpha Ap
-          xpay(beta, z, p)                       p = z + beta p
-          new_coarse() -> zero coarse vector,  dinv_c, kernels_c (PCG kernels, coarse level)
-    The restriction runs over OWNED fine nodes only and the coarse interface column is
-    then summed across neighbours (every global fine node is restricted exactly once).
+        M^-1 r = D^-1 r + P xc,  xc ~= Ac^-1 P^T r   (inner PCG on the vertex coarse operator,
+        preconditioned by Dc^-1, or by Dc^-1 + P2 A3inv P2^T when ``top`` is given)
+
+    dop / dop_c : DistributedOperator of the fine (exterior) and the coarse (vertex) level.
+    ops : residual(b, Ax) -> (r, b_masked) ; jacobi(r) -> z ; restrict(r, n_owned) -> rc ;
+          prolong_add(xc, z) ; new_coarse() ; dinv_c.
+    top : None, or an object with agg_restrict(q, n_owned) -> r3 (this rank's owned vertices,
+          global aggregate ids), A3inv (replicated dense inverse) and agg_prolong_add(y3, z).
+    The restriction runs over OWNED fine nodes only and the coarse interface column is then
+    summed across neighbours; r3 is summed over all ranks.  ``flexible``: Polak-Ribiere beta
+    (the inner solve makes the preconditioner vary from step to step).
     Returns (outer iterations, relative residual, converged, total inner iterations)."""
+    group = dop.group
+
+    def inner_precond(q):
+        z = ops.dinv_c * q
+        if top is not None:
+            r3 = top.agg_restrict(q, dop_c.part.n_owned)
+            dist.all_reduce(r3, group=group)
+            top.agg_prolong_add(top.A3inv @ r3, z)
+        return z
+
+    def inner_solve(rc):
+        xc = ops.new_coarse()
+        r = rc.clone()
+        bb = float(dop_c.owned_dot(r, r))
+        if bb == 0.0:
+            return xc, 0
+        z = inner_precond(r)
+        p = z.clone()
+        rz = float(dop_c.owned_dot(r, z))
+        Ap = torch.empty_like(p)
+        dot = torch.zeros(1, dtype=torch.float64, device=rc.device)
+        it = 0
+        while it < inner_maxiter:
+            dop_c.apply(p, out=Ap, dot_out=dot)
+            dist.all_reduce(dot, group=group)
+            pAp = float(dot)
+            if not pAp > 0.0:
+                from ._lib import SolverFailure
+                raise SolverFailure("inner PCG breakdown (p.Ap <= 0 or non-finite)")
+            alpha = rz / pAp
+            xc += alpha * p
+            r -= alpha * Ap
+            it += 1
+            if float(dop_c.owned_dot(r, r)) <= inner_rtol * inner_rtol * bb:
+                break
+            z = inner_precond(r)
+            rz_new = float(dop_c.owned_dot(r, z))
+            p.mul_(rz_new / rz).add_(z)
+            rz = rz_new
+        return xc, it
+
+    def precondition(res):
+        z = ops.jacobi(res)
+        rc = ops.restrict(res, dop.part.n_owned)
+        dop_c.exchange_add(rc)
+        xc, itc = inner_solve(rc)
+        ops.prolong_add(xc, z)
+        return z, itc
+
     r, bm = ops.residual(b, dop.apply(x))
     bb = float(dop.owned_dot(bm, bm))
     rr = float(dop.owned_dot(r, r))
     tol2 = rtol * rtol
     if bb == 0.0 or rr <= tol2 * bb:
         return 0, (rr / bb) ** 0.5 if bb > 0 else 0.0, True, 0
-    inner_total = 0
-
-    def precondition(res):
-        z = ops.jacobi(res)
-        rc = ops.restrict(res, dop.part.n_owned)
-        dop_c.exchange_add(rc)
-        xc = ops.new_coarse()
-        itc, _, _ = distributed_pcg(dop_c, rc, xc, ops.dinv_c, ops.kernels_c, rtol=inner_rtol,
-                                    maxiter=inner_maxiter, check_every=check_every)
-        ops.prolong_add(xc, z)
-        return z, itc
-
-    z, itc = precondition(r)
-    inner_total += itc
+    z, inner_total = precondition(r)
     p = z.clone()
     rz = float(dop.owned_dot(r, z))
     dot = torch.zeros(1, dtype=torch.float64, device=b.device)
@@ -405,12 +519,14 @@ def distributed_two_level_pcg(dop, dop_c, ops, b, x, rtol=1e-12, maxiter=1000, i
     it = 0
     while it < maxiter:
         dop.apply(p, out=Ap, dot_out=dot)
-        dist.all_reduce(dot, group=dop.group)
+        dist.all_reduce(dot, group=group)
         pAp = float(dot)
         if not pAp > 0.0:
             from ._lib import SolverFailure
-            raise SolverFailure("distributed two-level PCG breakdown (p.Ap <= 0 or non-finite)")
-        ops.axpy2(rz / pAp, p, Ap, x, r)
+            raise SolverFailure("multilevel PCG breakdown (p.Ap <= 0 or non-finite)")
+        alpha = rz / pAp
+        x += alpha * p
+        r -= alpha * Ap
         it += 1
         rr = float(dop.owned_dot(r, r))
         if rr <= tol2 * bb:
@@ -418,9 +534,34 @@ def distributed_two_level_pcg(dop, dop_c, ops, b, x, rtol=1e-12, maxiter=1000, i
         z, itc = precondition(r)
         inner_total += itc
         rz_new = float(dop.owned_dot(r, z))
-        ops.xpay(rz_new / rz, z, p)
+        beta = -alpha * float(dop.owned_dot(z, Ap)) / rz if flexible else rz_new / rz
+        p.mul_(beta).add_(z)
         rz = rz_new
     return it, (rr / bb) ** 0.5, False, inner_total
+
+
+def strip_vertex_aggregates(part, vertex_lex_ids, dirichlet_c, max_tiles=4096):
+    """GLOBAL aggregate id of every local vertex of a strip partition (third level of the
+    multilevel preconditioner): k x k element tiles of the global mesh; a vertex joins the
+    tile of the element to its lower left, vertices on the essential boundary join nothing
+    (0xffffffff).  Both owners of a shared vertex column compute the same ids because
+    they are derived from GLOBAL lattice positions.  ``vertex_lex_ids``: rank-local
+    lexicographic node id (i * NY + j) of every vertex, in compact vertex order.
+    Returns (agg uint32[n_v], n_agg, k)."""
+    p, NY = part.p, part.NY
+    nxg, ny = part.nx_global, part.ny
+    k = 1
+    while -(-nxg // k) * -(-ny // k) > max_tiles:
+        k += 1
+    k = max(k, min(4, max(nxg, ny)))
+    tx, ty = -(-nxg // k), -(-ny // k)
+    i_node, j_node = np.divmod(np.asarray(vertex_lex_ids, dtype=np.int64), NY)
+    I = part.rank * part.nx_local + i_node // p
+    J = j_node // p
+    tile = (np.maximum(I - 1, 0) // k) * ty + np.maximum(J - 1, 0) // k
+    agg = tile.astype(np.uint32)
+    agg[np.asarray(dirichlet_c, dtype=bool)] = 0xFFFFFFFF
+    return agg, int(tx * ty), int(k)
 
 
 class DistributedPoisson(object):
@@ -445,26 +586,19 @@ class DistributedPoisson(object):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         self.halo = None
         if exchange in ("auto", "peer"):
-            # "auto": every rank tries to map its neighbours; unless ALL succeed (peer access
-            # and CUDA IPC available between all neighbouring GPUs) everyone uses NCCL p2p
-            err = None
+            # PeerHalo sets itself up collectively: either every rank maps its neighbours
+            # or every rank raises; "auto" then falls back to NCCL p2p on all ranks
             try:
                 self.halo = PeerHalo(part, group, op.dev)
-            except Exception as e:          # noqa: BLE001 -- reported below or re-raised
-                err = e
-            ok = torch.tensor([0.0 if err is not None else 1.0], device=op.dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if float(ok) < 1.0:
+            except RuntimeError:
                 if exchange == "peer":
-                    raise RuntimeError("peer-memory exchange unavailable: %r" % (err,))
-                if self.halo is not None:
-                    self.halo._release()    # (no collective: the failing ranks are not in it)
+                    raise
                 self.halo = None
         self.exchange = "peer" if self.halo is not None else "nccl"
         self.dop = DistributedOperator(
             part, lambda u, out, dot: op.apply(u, out=out, dot_out=dot),
             dirichlet=self.on_ebc if op.has_dirichlet else None, group=group, device=op.dev,
-            halo=self.halo)
+            halo=self.halo, dot=self.kernels.dot)
         self._mask = op.dirichlet_dev.bool() if op.has_dirichlet else None
         self._dinv = None
 
@@ -539,25 +673,18 @@ class DistributedCondensedPoisson(object):
             raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         self.halo = None
         if exchange in ("auto", "peer"):
-            err = None
             try:
                 self.halo = PeerHalo(self.view, group, sc.dev)
-            except Exception as e:          # noqa: BLE001 -- reported below or re-raised
-                err = e
-            ok = torch.tensor([0.0 if err is not None else 1.0], device=sc.dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if float(ok) < 1.0:
+            except RuntimeError:
                 if exchange == "peer":
-                    raise RuntimeError("peer-memory exchange unavailable: %r" % (err,))
-                if self.halo is not None:
-                    self.halo._release()
+                    raise
                 self.halo = None
         self.exchange = "peer" if self.halo is not None else "nccl"
         on_ext = self.on_ebc[:sc.n_ext]
         self.dop = DistributedOperator(
             self.view, lambda u, out, dot: sc.apply(u, out=out, dot_out=dot),
             dirichlet=on_ext if sc.has_dirichlet else None, group=group, device=sc.dev,
-            halo=self.halo)
+            halo=self.halo, dot=self.kernels.dot)
         self._mask = sc.dirichlet_dev.bool() if sc.has_dirichlet else None
         self._dinv = None
 
@@ -593,9 +720,16 @@ class DistributedCondensedPoisson(object):
         return out
 
     def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25,
-                  preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000):
-        if preconditioner not in ("jacobi", "two-level"):
-            raise ValueError("preconditioner must be 'jacobi' or 'two-level'")
+                  preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000, flexible=True,
+                  inner_chunk=4, max_tiles=4096):
+        """Distributed PCG on the exterior DOFs.  "jacobi": the host-driven loop
+        (distributed_pcg, NCCL all-reduces).  "two-level" / "three-level": the native
+        multilevel driver (semk_sc_mlpcg_solve_f64) -- every exchange and all-reduce is a
+        peer-memory kernel issued by the driver itself, so it needs exchange="peer".
+        Returns (x, iterations, rel_residual, converged); ``last_info`` keeps the PCGInfo
+        (true residual, inner iterations) of a multilevel solve."""
+        if preconditioner not in ("jacobi", "two-level", "three-level"):
+            raise ValueError("preconditioner must be 'jacobi', 'two-level' or 'three-level'")
         if x0 is None:
             x = torch.zeros_like(b)
             if self._mask is not None:
@@ -604,107 +738,87 @@ class DistributedCondensedPoisson(object):
             x = x0.clone()
         if self._dinv is None:
             self._dinv = 1.0 / self.diagonal()
-        if preconditioner == "two-level":
-            ops, dop_c = self._two_level()
-            it, rel, ok, inner = distributed_two_level_pcg(
-                self.dop, dop_c, ops, b, x, rtol=rtol, maxiter=maxiter, inner_rtol=inner_rtol,
-                inner_maxiter=inner_maxiter, check_every=check_every)
-            self.last_inner_iterations = inner
-            return x, it, rel, ok
+        if preconditioner != "jacobi":
+            ml = self._multilevel(3 if preconditioner == "three-level" else 2, max_tiles)
+            # ranks enter together: the peer kernels give up after ~2 s of waiting
+            torch.cuda.synchronize(self.sc.dev)
+            dist.barrier(group=self.group)
+            xs, info = self.sc.solve_pcg(
+                b, x0=x, rtol=rtol, maxiter=maxiter, preconditioner=preconditioner,
+                inner_rtol=inner_rtol, inner_maxiter=inner_maxiter, flexible=flexible,
+                inner_chunk=inner_chunk, max_tiles=max_tiles,
+                dist=(ml["dist"], self._dinv, ml["dinv_c"]))
+            self.halo.check()
+            ml["halo_c"].check()
+            ml["comm"].check()
+            self.last_info = info
+            self.last_inner_iterations = info.inner_iterations
+            return xs, info.iterations, info.rel_residual, info.converged
         it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
                                       maxiter=maxiter, check_every=check_every)
         return x, it, rel, ok
 
-    def _two_level(self):
-        """Coarse level of the two-level preconditioner on the strip partition (lazy):
-        the rank-local coarse operator of condensed.CondensedPoissonOperator, its
-        interface exchange (the coarse interface columns are the leading / trailing
-        ny + 1 compact vertex ids) and the device pieces `distributed_two_level_pcg`
-        strings together.  The scheme is checked on two ranks on CPU
-        (tests/test_distributed.py); this device wiring has NOT run on GPUs yet."""
-        if getattr(self, "_tl", None) is not None:
-            return self._tl
+    def _multilevel(self, levels, max_tiles=4096):
+        """Coarse levels of the multilevel preconditioner on the strip partition (lazy):
+        the rank-local vertex coarse operator of condensed.CondensedPoissonOperator with its
+        own interface exchange (the coarse interface columns are the leading / trailing
+        ny + 1 compact vertex ids), the global inverse diagonal of the coarse operator, the
+        peer-memory communicator and -- for three levels -- global vertex aggregates with a
+        replicated dense inverse of the aggregated operator."""
+        tl = getattr(self, "_ml", None)
+        if tl is not None and tl["levels"] >= levels:
+            return tl
+        if self.halo is None:
+            raise NotImplementedError("the native multilevel driver needs the peer-memory "
+                                      "exchange (exchange='peer' / 'auto' with peer access)")
         import ctypes as C
-        from . import _lib, device
-        from .operators import PCGKernels
+        from . import _lib
         sc = self.sc
-        lib = sc._lib
         cs, t, n_v = sc._build_coarse()
-        view_c = CondensedStripView(self.part, n_v, column=self.part.ny + 1)
-        halo_c = None
-        if self.halo is not None:
+        if tl is None:
+            view_c = CondensedStripView(self.part, n_v, column=self.part.ny + 1)
             halo_c = PeerHalo(view_c, self.group, sc.dev)
-        dir_c = t["dirichlet_c_host"] if sc.has_dirichlet else None
-        dop_c = DistributedOperator(
-            view_c, lambda u, out, dot: sc.coarse_apply(u, out=out, dot_out=dot),
-            dirichlet=dir_c, group=self.group, device=sc.dev, halo=halo_c)
-        dc = t["diag_c_local"].clone()
-        dop_c.exchange_add(dc)
-        if sc.has_dirichlet:
-            dc[t["dirichlet_c"].bool()] = 1.0
-        dinv = self._dinv
-        n_ext = sc.n_ext
+            dc = t["diag_c_local"].clone()
+            halo_c.exchange(dc)
+            if sc.has_dirichlet:
+                dc[t["dirichlet_c"].bool()] = 1.0
+            tl = dict(levels=2, view_c=view_c, halo_c=halo_c, dinv_c=1.0 / dc, comm=None)
+        n_agg = 0
+        if levels == 3:
+            vids = np.unique(sc.l2g_ext_host[:, :4])
+            agg, n_agg, k = strip_vertex_aggregates(self.part, self.lexicographic_ids[vids],
+                                                    t["dirichlet_c_host"], max_tiles)
+            sc._top = None
+            sc._build_top(agg=agg, n_agg=n_agg, n_owned_c=tl["view_c"].n_owned,
+                          reduce=lambda A: dist.all_reduce(A, group=self.group), source_rank=0)
+            tl["aggregate_tile"] = k
+        if tl["comm"] is None or tl["comm"].capacity < n_agg + 8:
+            if tl["comm"] is not None:
+                tl["comm"].close()
+            tl["comm"] = PeerComm(self.part.rank, self.part.world, max(n_agg + 8, 64), self.group,
+                                  sc.dev)
+        d = _lib.semk_ml_dist()
+        d.comm = C.pointer(tl["comm"].c)
+        d.halo_f = C.pointer(self.halo.c)
+        d.halo_c = C.pointer(tl["halo_c"].c)
+        d.n_owned_f = self.view.n_owned
+        d.n_owned_c = tl["view_c"].n_owned
+        tl["dist"] = d
+        tl["levels"] = levels
+        self._ml = tl
+        return tl
 
-        class _CoarseLevel(object):       # what PCGKernels reads from an operator
-            pass
-        lvl = _CoarseLevel()
-        lvl._lib = lib
-        lvl.n_nodes = n_v
-        lvl.vec_partials = torch.zeros(int(lib.semk_vec_partials_len(n_v)), dtype=torch.float64,
-                                       device=sc.dev)
-        lvl.dirichlet_dev = t["dirichlet_c"]
-        lvl.has_dirichlet = sc.has_dirichlet
-        dirichlet_ptr = device.ptr(sc.dirichlet_dev if sc.has_dirichlet else None)
-
-        class _Ops(object):
-            dinv_c = 1.0 / dc
-            kernels_c = PCGKernels(lvl, n=n_v)
-
-            @staticmethod
-            def residual(bv, Ax):
-                r, bm = torch.empty_like(bv), torch.empty_like(bv)
-                _lib.check(lib.semk_vec_resid_f64(n_ext, device.ptr(bv), device.ptr(Ax),
-                                                  dirichlet_ptr, device.ptr(r), device.ptr(bm),
-                                                  device.stream_ptr()))
-                return r, bm
-
-            @staticmethod
-            def jacobi(r):
-                z = torch.empty_like(r)
-                _lib.check(lib.semk_vec_scale_f64(n_ext, device.ptr(dinv), device.ptr(r),
-                                                  device.ptr(z), device.stream_ptr()))
-                return z
-
-            @staticmethod
-            def restrict(r, n_owned):
-                rc = torch.empty(n_v, dtype=torch.float64, device=sc.dev)
-                _lib.check(lib.semk_sc_restrict_f64(C.byref(cs), device.ptr(r), int(n_owned),
-                                                    device.ptr(rc), device.stream_ptr()))
-                return rc
-
-            @staticmethod
-            def prolong_add(xc, z):
-                _lib.check(lib.semk_sc_prolong_add_f64(n_ext, C.byref(cs), device.ptr(xc),
-                                                       device.ptr(z), device.stream_ptr()))
-
-            @staticmethod
-            def axpy2(alpha, p, Ap, x, r):
-                _lib.check(lib.semk_vec_axpy2_f64(n_ext, float(alpha), device.ptr(p),
-                                                  device.ptr(Ap), device.ptr(x), device.ptr(r),
-                                                  device.stream_ptr()))
-
-            @staticmethod
-            def xpay(beta, z, p):
-                _lib.check(lib.semk_vec_xpay_f64(n_ext, float(beta), device.ptr(z), device.ptr(p),
-                                                 device.stream_ptr()))
-
-            @staticmethod
-            def new_coarse():
-                return torch.zeros(n_v, dtype=torch.float64, device=sc.dev)
-
-        self._tl = (_Ops, dop_c)
-        self._halo_c = halo_c
-        return self._tl
+    def close(self):
+        """Collective tear-down of the peer-memory regions."""
+        tl = getattr(self, "_ml", None)
+        if tl is not None:
+            tl["halo_c"].close()
+            if tl["comm"] is not None:
+                tl["comm"].close()
+            self._ml = None
+        if self.halo is not None:
+            self.halo.close()
+            self.halo = None
 
     def solve(self, f=1.0, dirichlet_values=None, **pcg_kwargs):
         """Condensed load, lifting, distributed PCG on the exterior DOFs, rank-local

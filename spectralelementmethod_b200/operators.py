@@ -125,14 +125,22 @@ def default_element_order(mesh, elems_per_patch, tile=None):
 
 
 class PCGInfo(object):
-    __slots__ = ("iterations", "status", "rel_residual", "bnorm", "converged")
+    """iterations / status / recursive relative residual of a solve; the multilevel driver
+    also reports the TRUE residual ||b - A x|| / ||b|| of the returned iterate and the
+    inner (coarse-level) iteration count."""
+    __slots__ = ("iterations", "status", "rel_residual", "bnorm", "converged",
+                 "true_rel_residual", "inner_iterations", "inner_solves")
 
-    def __init__(self, iterations, status, rel_residual, bnorm):
+    def __init__(self, iterations, status, rel_residual, bnorm, true_rel_residual=None,
+                 inner_iterations=None, inner_solves=None):
         self.iterations = int(iterations)
         self.status = int(status)
         self.rel_residual = float(rel_residual)
         self.bnorm = float(bnorm)
         self.converged = self.status == 0
+        self.true_rel_residual = None if true_rel_residual is None else float(true_rel_residual)
+        self.inner_iterations = None if inner_iterations is None else int(inner_iterations)
+        self.inner_solves = None if inner_solves is None else int(inner_solves)
 
     def __repr__(self):
         return ("PCGInfo(iterations=%d, status=%d, rel_residual=%.3e, bnorm=%.6e)"

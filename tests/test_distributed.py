@@ -423,7 +423,6 @@ def _worker_two_level(rank, world, port, out):
         class Ops(object):
             """NumPy stand-ins of the rank-local device pieces."""
             dinv_c = 1.0 / dcl
-            kernels_c = CpuKernels(Dc)
 
             @staticmethod
             def residual(bv, Ax):
@@ -449,19 +448,43 @@ def _worker_two_level(rank, world, port, out):
                 z += torch.from_numpy(pw[:, 0] * xn[pv[:, 0]] + pw[:, 1] * xn[pv[:, 1]])
 
             @staticmethod
-            def axpy2(alpha, p_, Ap, x_, r_):
-                x_ += alpha * p_
-                r_ -= alpha * Ap
-
-            @staticmethod
-            def xpay(beta, z, p_):
-                p_.mul_(beta).add_(z)
-
-            @staticmethod
             def new_coarse():
                 return torch.zeros(n_v, dtype=torch.float64)
 
-        from spectralelementmethod_b200.distributed import distributed_two_level_pcg
+        # third level: GLOBAL vertex aggregates (both owners of a shared vertex column agree),
+        # A3 = P2^T Ac P2 summed over the ranks, replicated dense inverse
+        from spectralelementmethod_b200.condensed import aggregate_csr
+        from spectralelementmethod_b200.distributed import (distributed_multilevel_pcg,
+                                                            strip_vertex_aggregates)
+        agg, n_agg, ktile = strip_vertex_aggregates(part, lex_ids[vids], Dc, max_tiles=6)
+        valid = agg != 0xFFFFFFFF
+        assert n_agg <= 6 and (agg[valid] < n_agg).all() and not valid[Dc].any()
+        a_e = np.where(valid, agg.astype(np.int64), -1)[vc]                       # [E, 4]
+        A3 = np.zeros((n_agg, n_agg))
+        rows, cols = np.repeat(a_e, 4, axis=1).ravel(), np.tile(a_e, (1, 4)).ravel()
+        okk = (rows >= 0) & (cols >= 0)
+        np.add.at(A3, (rows[okk], cols[okk]), Ace.reshape(-1)[okk])
+        A3t = torch.from_numpy(A3)
+        dist.all_reduce(A3t)
+        A3 = A3t.numpy()
+        A3[np.diag(A3) == 0.0, np.diag(A3) == 0.0] = 1.0
+        aptr_o, aidx_o = aggregate_csr(agg, n_agg, view_c.n_owned)
+
+        class Top(object):
+            A3inv = torch.from_numpy(np.linalg.inv(0.5 * (A3 + A3.T)))
+
+            @staticmethod
+            def agg_restrict(q, n_owned):
+                assert n_owned == view_c.n_owned
+                out = np.zeros(n_agg)
+                np.add.at(out, agg[aidx_o].astype(np.int64), q.numpy()[aidx_o])
+                return torch.from_numpy(out)
+
+            @staticmethod
+            def agg_prolong_add(y3, z):
+                zn = z.numpy()
+                zn[valid] += y3.numpy()[agg[valid].astype(np.int64)]
+
         # lifted right-hand side (as in the condensed worker above)
         bl = torch.from_numpy(c["grhs"].copy())
         dop.exchange_add(bl)
@@ -471,24 +494,26 @@ def _worker_two_level(rank, world, port, out):
         dop.exchange_add(t)
         bh = bl - t
         bh[tD] = torch.from_numpy(g)[tD]
-        x = torch.where(tD, bh, torch.zeros_like(bh))
-        it, rel, ok, inner_total = distributed_two_level_pcg(
-            dop, dop_c, Ops, bh, x, rtol=1e-13, maxiter=200, inner_rtol=1e-2, inner_maxiter=500,
-            check_every=1)
-        assert ok and rel <= 1e-13
-        inner_its = [inner_total]
-        sol = np.zeros(mesh.n_nodes)
-        sol[:n_ext] = x.numpy()
-        inner = np.linalg.solve(c["Aii"], (c["f_int"] - np.einsum("eij,ej->ei", c["Aie"],
-                                                                  sol[ids]))[..., None])
-        sol[c["int_ids"]] = inner[..., 0]
-        torch.save(dict(gid=gid, sol=sol, it=it, inner=int(np.sum(inner_its))),
+        results = {}
+        for name, top, flexible in (("two", None, False), ("three", Top, True)):
+            x = torch.where(tD, bh, torch.zeros_like(bh))
+            it, rel, ok, inner_total = distributed_multilevel_pcg(
+                dop, dop_c, Ops, bh, x, rtol=1e-13, maxiter=200, inner_rtol=1e-2,
+                inner_maxiter=500, flexible=flexible, top=top)
+            assert ok and rel <= 1e-13
+            sol = np.zeros(mesh.n_nodes)
+            sol[:n_ext] = x.numpy()
+            inner = np.linalg.solve(c["Aii"], (c["f_int"] - np.einsum("eij,ej->ei", c["Aie"],
+                                                                      sol[ids]))[..., None])
+            sol[c["int_ids"]] = inner[..., 0]
+            results[name] = dict(sol=sol, it=it, inner=int(inner_total))
+        torch.save(dict(gid=gid, results=results, n_agg=n_agg, ktile=ktile),
                    os.path.join(out, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_two_level_pcg_emulation(tmp_path):
+def test_two_rank_multilevel_pcg_emulation(tmp_path):
     import sem_oracle as so
     world, nxl, ny, p = 2, 4, 6, 4
     out = str(tmp_path)
@@ -508,7 +533,12 @@ def test_two_rank_two_level_pcg_emulation(tmp_path):
     on, _ = so.dirichlet_data(nodes, l2g, geo["x_phys"], so.mesh_boundary_faces(nxg, ny))
     vals = np.where(on, 0.3 * nodes[0] - 0.2 * nodes[1] + 0.1, 0.0)
     want = so.solve_direct(A, so.assemble_vector(geo["JxW"], l2g, nodes.shape[1]), on, vals)
-    assert res[0]["it"] == res[1]["it"] and res[0]["it"] < 40       # mesh-independent count
-    assert res[0]["inner"] == res[1]["inner"] > 0
-    for r in res:
-        assert rel_l2(r["sol"], want[r["gid"]]) < 1e-10
+    for name in ("two", "three"):
+        r0, r1 = res[0]["results"][name], res[1]["results"][name]
+        assert r0["it"] == r1["it"] and r0["it"] < 40                # mesh-independent count
+        assert r0["inner"] == r1["inner"] > 0
+        for r, rk in ((r0, res[0]), (r1, res[1])):
+            assert rel_l2(r["sol"], want[rk["gid"]]) < 1e-10
+    # the aggregation level cuts the inner iterations, the outer count stays
+    two, three = res[0]["results"]["two"], res[0]["results"]["three"]
+    assert three["inner"] < two["inner"] and abs(three["it"] - two["it"]) <= 3
