@@ -931,8 +931,40 @@ class Mesh(object):
             self._append_block(_CellBlock(gid, regions, maps))
             i = j
 
+    def _merge_blocks(self):
+        """Fuse runs of consecutive blocks that share a geometry into one block, so that
+        homogeneity is decided by geometry id and not by how the cells arrived (one
+        ``add_cells`` call per ``$Elements`` header of a Gmsh file -- Gmsh's own writer emits
+        one header per element --, ``add_cell`` after a ``get_cell``, ...).  The reference
+        accepts any blocking (sem/discrete.py:1031-1048 keeps one array per cell).  Cell
+        views handed out before more cells were added keep pointing at the old arrays."""
+        blocks = self._blocks
+        if len(blocks) < 2:
+            return
+        merged, i = [], 0
+        while i < len(blocks):
+            j = i + 1
+            while j < len(blocks) and blocks[j].geometry_id == blocks[i].geometry_id:
+                j += 1
+            if j - i == 1:
+                merged.append(blocks[i])
+            else:
+                merged.append(_CellBlock(
+                    blocks[i].geometry_id,
+                    np.concatenate([b.region_ids for b in blocks[i:j]]),
+                    np.ascontiguousarray(np.concatenate([b.node_maps for b in blocks[i:j]]))))
+            i = j
+        if len(merged) != len(blocks):
+            self._blocks = merged
+            self._block_start = []
+            start = 0
+            for blk in merged:
+                self._block_start.append(start)
+                start += blk.n_cells
+
     def _blocks_flushed(self):
         self._flush()
+        self._merge_blocks()
         return self._blocks
 
     def _is_homogeneous(self):
@@ -950,7 +982,7 @@ class Mesh(object):
         return self._geometries
 
     def get_cell(self, i):
-        self._flush()
+        self._blocks_flushed()
         if i < 0 or i >= self._n_cells:
             raise IndexError("cell number out of range")
         b = bisect.bisect_right(self._block_start, i) - 1

@@ -77,14 +77,17 @@ def structured_quad_mesh(nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0), nod
     return mesh
 
 
-def write_gmsh22_binary(path, nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0), shuffle_seed=None):
+def write_gmsh22_binary(path, nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0), shuffle_seed=None,
+                        elements_per_header=None):
     """Write the structured mesh of ``structured_quad_mesh`` as a Gmsh 2.2
     *binary* ``.msh`` file (the format sem/grid_importers.py:45-218 reads):
     physical names 1 "ebc" and 2 "nbc" (lines: left + bottom / right + top)
     and 3 "interior" (quadrilaterals); high-order line and quadrilateral
     elements in Gmsh's node ordering.  ``shuffle_seed`` permutes the element
     order inside each block and the node numbering (a mesh generator gives no
-    ordering guarantees).  Test / example helper; p <= 10."""
+    ordering guarantees).  ``elements_per_header``: split every element block into
+    headers of at most that many elements (1 = one header per element, the blocking
+    Gmsh's own MSH2 binary writer is reported to use).  Test / example helper; p <= 10."""
     from .grid_importers import GMSH_LINE_TYPES, GMSH_QUAD_TYPES, gmsh_to_lexicographic
     n1 = p + 1
     line_type = {v: k for k, v in GMSH_LINE_TYPES.items()}[n1]
@@ -124,15 +127,18 @@ def write_gmsh22_binary(path, nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0)
         for etype, node_ix, tag in ((line_type, perm[lines][:, inv_line], phys),
                                     (quad_type, perm[maps.reshape(len(maps), -1)][:, inv_quad],
                                      np.full(len(maps), 3))):
-            f.write(np.array([etype, len(node_ix), 2], dtype="<i4").tobytes())
-            rec = np.empty(len(node_ix), dtype=[("index", "<u4"), ("tags", "<u4", (2,)),
-                                                ("node_ix", "<u4", (node_ix.shape[1],))])
-            rec["index"] = np.arange(first, first + len(node_ix))
-            rec["tags"][:, 0] = tag
-            rec["tags"][:, 1] = tag
-            rec["node_ix"] = node_ix + 1
-            f.write(rec.tobytes())
-            first += len(node_ix)
+            chunk = len(node_ix) if not elements_per_header else int(elements_per_header)
+            for c0 in range(0, len(node_ix), max(chunk, 1)):
+                part, ptag = node_ix[c0:c0 + chunk], tag[c0:c0 + chunk]
+                f.write(np.array([etype, len(part), 2], dtype="<i4").tobytes())
+                rec = np.empty(len(part), dtype=[("index", "<u4"), ("tags", "<u4", (2,)),
+                                                 ("node_ix", "<u4", (part.shape[1],))])
+                rec["index"] = np.arange(first, first + len(part))
+                rec["tags"][:, 0] = ptag
+                rec["tags"][:, 1] = ptag
+                rec["node_ix"] = part + 1
+                f.write(rec.tobytes())
+                first += len(part)
         f.write(b"\n$EndElements\n")
     return path
 

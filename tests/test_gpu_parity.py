@@ -341,6 +341,43 @@ def test_full_size_config2_1024x1024_p8():
     harm = torch.from_numpy(c1[:, None] ** 2 - c1[None, :] ** 2).reshape(-1).cuda()
     Ah = op.apply_unmasked(harm).reshape(8193, 8193)
     assert float(Ah[1:-1, 1:-1].abs().max()) < 1e-9
+    del Ah, harm
+    # operator-apply parity on SAMPLED elements at full size (SURVEY hard part 4): the oracle's
+    # dense 4-index local stiffness (examples/poisson.py:181-193) on the 3 x 3 element
+    # neighbourhood of each sampled element, applied to the same global random field --
+    # complete sums for the 81 nodes of the centre element, interface nodes included
+    rng = np.random.default_rng(11)
+    ur = rng.standard_normal(mngr.ndof)
+    y_dev = host(op.apply_unmasked(dev(ur)))
+    basis = so.Basis(8)
+    wq = np.asarray(basis.w)
+    errs_exact, errs_ref = [], []
+    for ex, ey in [(0, 0), (1023, 1023), (0, 511), (512, 0), (377, 911), (1000, 3), (512, 512),
+                   (1023, 0), (640, 1023), (1, 1)]:
+        nb = [i * 1024 + j for i in range(max(ex - 1, 0), min(ex + 2, 1024))
+              for j in range(max(ey - 1, 0), min(ey + 2, 1024))]
+        l2g_s = maps[nb]
+        ids, inv = np.unique(l2g_s, return_inverse=True)
+        inv = inv.reshape(len(nb), 81)
+        centre = np.searchsorted(ids, maps[ex * 1024 + ey].ravel())
+        geo = so.geometry(basis, mesh.nodes, l2g_s)          # the reference's own arithmetic
+        exact_invJ = np.zeros_like(geo["invJ"])
+        exact_invJ[:, 0, 0] = exact_invJ[:, 1, 1] = 1024.0   # 2 / h on the straight mesh
+        exact_JxW = np.broadcast_to((wq[:, None] * wq[None, :]) / 1024.0 ** 2, geo["JxW"].shape)
+        for invJ, JxW, errs in ((exact_invJ, exact_JxW, errs_exact),
+                                (geo["invJ"], geo["JxW"], errs_ref)):
+            L = so.local_stiffness(basis, invJ, JxW).reshape(len(nb), 81, 81)
+            acc = np.zeros(ids.size)
+            np.add.at(acc, inv.ravel(), np.einsum("ekj,ej->ek", L, ur[l2g_s.reshape(len(nb), 81)])
+                      .ravel())
+            want = acc[centre]
+            got = y_dev[ids[centre]]
+            errs.append(np.linalg.norm(got - want) / np.linalg.norm(want))
+    # exact geometric factors (affine elements): the 1e-12 gate of the north star
+    assert max(errs_exact) < 1e-12, errs_exact
+    # the reference's own factors carry cancellation noise ~ 7e-15 * n_side relative
+    # (8e-11 in G at n = 1024), which caps T2 parity at this size
+    assert max(errs_ref) < 2e-9, errs_ref
 
 
 @pytest.mark.gpu

@@ -141,3 +141,46 @@ def test_construct_geometry_table_matches_the_reference_keys():
     quad = table[49]()
     assert isinstance(line, geo.Line) and line.shape == (5,)
     assert isinstance(quad, geo.Quadrilateral) and quad.shape == (9, 9)
+
+
+@pytest.mark.parametrize("per_header", [1, 3])
+def test_any_element_blocking_gives_one_homogeneous_mesh(tmp_path, per_header):
+    """One $Elements header per element (or per few elements) must load into the same,
+    homogeneous mesh as whole-block files: node_map_array / boundary masks / the DOF
+    managers work on it (the reference keeps one array per cell and accepts any blocking,
+    sem/discrete.py:1031-1048)."""
+    nx, ny, p = 5, 4, 3
+    whole = gi.load_msh(meshgen.write_gmsh22_binary(str(tmp_path / "a.msh"), nx, ny, p, "C",
+                                                     shuffle_seed=4), 2)
+    split = gi.load_msh(meshgen.write_gmsh22_binary(str(tmp_path / "b.msh"), nx, ny, p, "C",
+                                                     shuffle_seed=4,
+                                                     elements_per_header=per_header), 2)
+    assert split._is_homogeneous() and split.n_cells == nx * ny
+    assert np.array_equal(split.node_map_array(), whole.node_map_array())
+    assert np.array_equal(split.nodes, whole.nodes)
+    assert np.array_equal(_boundary_rows(split), _boundary_rows(whole))
+    b1 = LagrangeGaussLobatto(p)
+    m1 = discrete.DOFManagerSC(split, 1, TensorProductQS(b1, b1), rcm_order=True)
+    m2 = discrete.DOFManagerSC(whole, 1, TensorProductQS(b1, b1), rcm_order=True)
+    assert np.array_equal(m1.node_map_array(), m2.node_map_array())
+    assert np.array_equal(m1.boundary_node_mask("ebc"), m2.boundary_node_mask("ebc"))
+
+
+def test_blocks_of_one_geometry_merge_whatever_the_call_pattern():
+    from spectralelementmethod_b200.geometry import Quadrilateral
+    nx, ny, p = 3, 3, 2
+    maps = meshgen.structured_node_maps(nx, ny, p).reshape(nx * ny, p + 1, p + 1)
+    mesh = discrete.Mesh(2)
+    mesh.set_nodes(meshgen.lattice_coordinates("S", nx, ny, p, (-1.0, 1.0, -1.0, 1.0)))
+    g = mesh.add_geometry(Quadrilateral(p + 1, p + 1))
+    r = mesh.new_region("interior")
+    mesh.add_cells(maps[:4], g, r)                     # two bulk blocks ...
+    mesh.add_cells(maps[4:6], g, r)
+    first = mesh.get_cell(0).node_ind_lexicographic.copy()
+    for k in range(6, 9):                              # ... and add_cell after a get_cell
+        mesh.add_cell(maps[k], g, r)
+    assert mesh._is_homogeneous() and mesh.n_cells == 9
+    assert np.array_equal(mesh.node_map_array(), maps)
+    assert np.array_equal(mesh.get_cell(0).node_ind_lexicographic, first)
+    assert np.array_equal(mesh.get_cell(7).node_ind_lexicographic, maps[7])
+    assert [c.region_id for c in mesh.cells] == [r] * 9
