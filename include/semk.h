@@ -509,6 +509,12 @@ typedef struct semk_sc_coarse {
   const uint32_t *rptr;       /* [n_v + 1] restriction = transpose of the above, CSR */
   const uint32_t *ridx;       /* [nnz] exterior node of every entry */
   const double *rw;           /* [nnz] weight of every entry */
+  /* optional: the same operator assembled into ELL rows (semk_sc_coarse_ell_build_f64),
+   * column major -- entry k of row v at [k * n_v + v]; identity rows on Dirichlet
+   * vertices.  The multilevel driver prefers it (one SpMV kernel per inner iteration). */
+  int64_t ell_width;          /* 0 = not built */
+  const uint32_t *ell_cols;   /* [ell_width][n_v] */
+  const double *ell_vals;     /* [ell_width][n_v] */
 } semk_sc_coarse;
 
 /* Ace = Phi_e^T S_e Phi_e for every element; phi: device [n_ext_loc][4], the local
@@ -520,6 +526,14 @@ int semk_sc_coarse_elem_f64(const semk_sc_op *op, const double *phi, double *Ace
  * semk_sc_apply_f64.  x, y: device [n_v], distinct. */
 int semk_sc_coarse_apply_f64(int64_t n_elem, const semk_sc_coarse *cs, const double *x, double *y,
                              int flags, double *dot_out, void *stream);
+/* Assemble Ac into ELL rows of `width` entries (<= 32; a vertex of valence d needs 2 d + 1):
+ * cols / vals: device [width][n_v], written; *overflow (device int) is set to 1 if a row
+ * does not fit.  Fixed summation order (ascending element), no atomics. */
+int semk_sc_coarse_ell_build_f64(const semk_sc_coarse *cs, int width, uint32_t *cols, double *vals,
+                                 int32_t *overflow, void *stream);
+/* y = Ac x from the ELL rows (cs->ell_*), dot_out = x . y (or NULL).  x, y distinct. */
+int semk_sc_coarse_ell_apply_f64(const semk_sc_coarse *cs, const double *x, double *y,
+                                 double *dot_out, void *stream);
 /* out[v] = sum of loc[vpos[..]]; loc: device [n_elem][4] (diagonal of Ac, ...). */
 int semk_sc_coarse_assemble_f64(int64_t n_elem, const semk_sc_coarse *cs, const double *loc,
                                 double *out, void *stream);
@@ -536,7 +550,9 @@ typedef struct semk_sc_top {
   const uint32_t *agg;
   const uint32_t *aptr;
   const uint32_t *aidx;
-  const double *A3inv;
+  const double *A3inv;        /* FP64 copy (may be NULL when A3inv_f32 is given) */
+  const float *A3inv_f32;     /* FP32 copy, preferred by the driver: half the bytes per inner
+                                 iteration; the inverse only enters the preconditioner */
 } semk_sc_top;
 
 /* A3 = P2^T Ac P2 (this rank's elements only) from the element coarse matrices cs->Ace:

@@ -82,7 +82,7 @@ SC_SCHUR, SC_RHS, SC_BACKSOLVE = 1, 2, 4
 
 class semk_sc_top(C.Structure):
     _fields_ = [("n_agg", C.c_int64), ("agg", C.c_void_p), ("aptr", C.c_void_p),
-                ("aidx", C.c_void_p), ("A3inv", C.c_void_p)]
+                ("aidx", C.c_void_p), ("A3inv", C.c_void_p), ("A3inv_f32", C.c_void_p)]
 
 
 class semk_sc_coarse(C.Structure):
@@ -91,6 +91,7 @@ class semk_sc_coarse(C.Structure):
         ("vptr", C.c_void_p), ("vpos", C.c_void_p), ("dirichlet_c", C.c_void_p),
         ("partials", C.c_void_p), ("pv", C.c_void_p), ("pw", C.c_void_p), ("rptr", C.c_void_p),
         ("ridx", C.c_void_p), ("rw", C.c_void_p),
+        ("ell_width", C.c_int64), ("ell_cols", C.c_void_p), ("ell_vals", C.c_void_p),
     ]
 
 
@@ -182,6 +183,8 @@ SIGNATURES = {
     "semk_sc_coarse_elem_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _P]),
     "semk_sc_coarse_apply_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _I, _P, _P]),
     "semk_sc_coarse_assemble_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _P]),
+    "semk_sc_coarse_ell_build_f64": (_I, [C.POINTER(semk_sc_coarse), _I, _P, _P, _P, _P]),
+    "semk_sc_coarse_ell_apply_f64": (_I, [C.POINTER(semk_sc_coarse), _P, _P, _P, _P]),
     "semk_sc_top_assemble_f64": (_I, [C.POINTER(semk_sc_coarse), _L, _P, _P, _P, _P, _P]),
     "semk_comm_region_bytes": (_L, [C.c_int32, _L]),
     "semk_comm_allreduce_f64": (_I, [C.POINTER(semk_comm), _P, _L, _P]),

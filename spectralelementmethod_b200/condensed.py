@@ -377,6 +377,22 @@ class CondensedPoissonOperator(object):
             raise AssertionError("coarse operator has a non-positive diagonal entry")
         t["dinv_c"] = 1.0 / dc
         t["dirichlet_c_host"] = ct["dirichlet_c"]
+        # the same operator as ELL rows for the multilevel driver: one SpMV per inner
+        # iteration instead of element product + vertex sum (a vertex of valence d couples
+        # to at most 2 d other vertices)
+        width = 2 * int(np.diff(ct["vptr"].astype(np.int64)).max()) + 1
+        if width <= 32:
+            t["ell_cols"] = torch.empty((width, n_v), dtype=torch.int32, device=self.dev)
+            t["ell_vals"] = torch.empty((width, n_v), **f64)
+            over = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            _lib.check(self._lib.semk_sc_coarse_ell_build_f64(
+                C.byref(cs), width, device.ptr(t["ell_cols"]), device.ptr(t["ell_vals"]),
+                device.ptr(over), device.stream_ptr()))
+            if int(over.item()) != 0:
+                raise AssertionError("ELL row overflow in the coarse operator")
+            cs.ell_width = width
+            cs.ell_cols = t["ell_cols"].data_ptr()
+            cs.ell_vals = t["ell_vals"].data_ptr()
         self._coarse = (cs, t, n_v)
         return self._coarse
 
@@ -427,6 +443,9 @@ class CondensedPoissonOperator(object):
         if source_rank is not None:           # bit-identical copies on every rank
             import torch.distributed as dist
             dist.broadcast(tt["A3inv"], src=source_rank)
+        # what the driver streams every inner iteration: an FP32 copy (symmetric rounding keeps
+        # it symmetric; it only enters the preconditioner)
+        tt["A3inv_f32"] = tt["A3inv"].to(torch.float32).contiguous()
         del A3, inv
         top = _lib.semk_sc_top()
         top.n_agg = n_agg
@@ -434,13 +453,20 @@ class CondensedPoissonOperator(object):
         top.aptr = tt["aptr"].data_ptr()
         top.aidx = tt["aidx"].data_ptr()
         top.A3inv = tt["A3inv"].data_ptr()
+        top.A3inv_f32 = tt["A3inv_f32"].data_ptr()
         self._top = (top, tt, n_agg)
         return self._top
 
-    def coarse_apply(self, xc, out=None, dot_out=None):
-        """y = Ac x on the vertex coarse space (tests / diagnostics)."""
+    def coarse_apply(self, xc, out=None, dot_out=None, ell=False):
+        """y = Ac x on the vertex coarse space (tests / diagnostics); ``ell``: through the
+        assembled ELL rows the multilevel driver uses instead of the element matrices."""
         cs, t, n_v = self._build_coarse()
         y = torch.empty(n_v, dtype=torch.float64, device=self.dev) if out is None else out
+        if ell:
+            _lib.check(self._lib.semk_sc_coarse_ell_apply_f64(
+                C.byref(cs), device.ptr(xc), device.ptr(y), device.ptr(dot_out),
+                device.stream_ptr()))
+            return y
         flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
         _lib.check(self._lib.semk_sc_coarse_apply_f64(
             self.n_elem, C.byref(cs), device.ptr(xc), device.ptr(y), flags, device.ptr(dot_out),

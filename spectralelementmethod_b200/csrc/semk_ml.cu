@@ -54,7 +54,18 @@ enum {
   S_LEN = 16
 };
 
-enum { OP_NONE = 0, OP_ALPHA = 1, OP_RR = 2, OP_RR_FIRST = 3, OP_BETA = 4, OP_BETA_FIRST = 5 };
+enum {
+  OP_NONE = 0,
+  OP_ALPHA = 1,
+  OP_RR = 2,
+  OP_RR_FIRST = 3,
+  OP_BETA = 4,
+  OP_BETA_FIRST = 5,
+  OP_RR2 = 6,            // inner level: buf ends with { r.r, r.(dinv r) }
+  OP_RR2_FIRST = 7,
+  OP_BETA_TOP = 8,       // inner level: r.z = r.(dinv r) + y3.r3, then beta
+  OP_BETA_TOP_FIRST = 9
+};
 
 struct CommDev {
   int rank, world;
@@ -128,10 +139,23 @@ __device__ bool comm_allreduce(const CommDev &c, double *buf, int n) {
 //                 (inner solves start from x = 0, so r = b); convergence test
 //                 (and ++iterations unless FIRST)
 //   OP_BETA[_FIRST] buf = s + S_RZN (2): beta (flexible or standard), rz <- rz_new
+//   OP_RR2[_FIRST] inner level, buf = [r3 (na) | r.r | r.(dinv r)]: as OP_RR, and the Jacobi
+//                 part of r.z is parked in s[S_RZN]
+//   OP_BETA_TOP[_FIRST] inner level, no reduction: r.z = s[S_RZN] + y3 . r3 -- the aggregation
+//                 correction z += P2 y3 contributes (P2 y3).r = y3.(P2^T r) = y3.r3, both
+//                 replicated vectors, so z never has to be formed for the dot -- then beta
 __global__ void __launch_bounds__(kStepThreads)
     ml_step_kernel(CommDev c, double *__restrict__ buf, int n, int op, int flexible,
-                   double *__restrict__ s) {
-  const bool ok = comm_allreduce(c, buf, n);
+                   double *__restrict__ s, const double *__restrict__ y3,
+                   const double *__restrict__ r3v, int na) {
+  const bool ok = n > 0 ? comm_allreduce(c, buf, n) : true;
+  double top_dot = 0.0;
+  if (op == OP_BETA_TOP || op == OP_BETA_TOP_FIRST) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) acc = fma(y3[i], r3v[i], acc);
+    top_dot = semk_block_sum(acc, red);
+  }
   if (threadIdx.x != 0) return;
   if (!ok) {
     s[S_BREAK] = 2.0;
@@ -158,6 +182,26 @@ __global__ void __launch_bounds__(kStepThreads)
       else
         s[S_ITER] += 1.0;   // one more completed update of x
       if (rr <= s[S_TOL2] * s[S_BB]) s[S_CONV] = 1.0;
+      break;
+    }
+    case OP_RR2:
+    case OP_RR2_FIRST: {
+      const double rr = buf[n - 2];
+      s[S_RR] = rr;
+      s[S_RZN] = buf[n - 1];
+      if (op == OP_RR2_FIRST)
+        s[S_BB] = rr;
+      else
+        s[S_ITER] += 1.0;
+      if (rr <= s[S_TOL2] * s[S_BB]) s[S_CONV] = 1.0;
+      break;
+    }
+    case OP_BETA_TOP:
+    case OP_BETA_TOP_FIRST: {
+      const double rzn = s[S_RZN] + top_dot;
+      const double rz = s[S_RZ];
+      s[S_BETA] = (op == OP_BETA_TOP_FIRST || rz == 0.0) ? 0.0 : rzn / rz;
+      s[S_RZ] = rzn;
       break;
     }
     case OP_BETA:
@@ -223,35 +267,6 @@ __global__ void __launch_bounds__(kT)
   if (semk_finish_reduction<1>(acc, partials, tot) && threadIdx.x == 0) rr_out[0] = tot[0];
 }
 
-// (optional) z[v] += y3[agg[v]] ; out2 = { r.z, z.Ap } over the owned prefix
-__global__ void __launch_bounds__(kT)
-    ml_correct_dot_kernel(int64_t n, int64_t n_dot, const uint32_t *__restrict__ agg,
-                          const double *__restrict__ y3, const double *__restrict__ r,
-                          const double *__restrict__ Ap, double *__restrict__ z,
-                          double *__restrict__ out2, double *__restrict__ partials) {
-  double acc[2] = {0.0, 0.0};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    double zi = z[i];
-    if (agg) {
-      const uint32_t a = agg[i];
-      if (a != 0xffffffffu) {
-        zi += y3[a];
-        z[i] = zi;
-      }
-    }
-    if (i < n_dot) {
-      acc[0] = fma(r[i], zi, acc[0]);
-      if (Ap) acc[1] = fma(zi, Ap[i], acc[1]);
-    }
-  }
-  double tot[2];
-  if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
-    out2[0] = tot[0];
-    out2[1] = tot[1];
-  }
-}
-
 // z += P xc (at most two vertices per fine node) ; out2 = { r.z, z.Ap } over the owned prefix
 __global__ void __launch_bounds__(kT)
     ml_prolong_dot_kernel(int64_t n, int64_t n_dot, const uint32_t *__restrict__ pv,
@@ -276,6 +291,154 @@ __global__ void __launch_bounds__(kT)
   if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
     out2[0] = tot[0];
     out2[1] = tot[1];
+  }
+}
+
+// ---- inner (vertex) level: the preconditioned residual z = dinv r + P2 y3 is never stored ----
+// x += alpha p ; r -= alpha Ap (unless first / frozen) ; out2 = { r.r, r.(dinv r) } (owned)
+__global__ void __launch_bounds__(kT)
+    ml_inner_update_kernel(int64_t n, int64_t n_dot, int first, const double *__restrict__ p,
+                           const double *__restrict__ Ap, const double *__restrict__ dinv,
+                           double *__restrict__ x, double *__restrict__ r,
+                           const double *__restrict__ s, double *__restrict__ out2,
+                           double *__restrict__ partials) {
+  const bool move = !first && s[S_CONV] == 0.0 && s[S_BREAK] == 0.0;
+  const double alpha = s[S_ALPHA];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double ri = r[i];
+    if (move) {
+      x[i] = fma(alpha, p[i], x[i]);
+      ri = fma(-alpha, Ap[i], ri);
+      r[i] = ri;
+    }
+    if (i < n_dot) {
+      acc[0] = fma(ri, ri, acc[0]);
+      acc[1] = fma(ri * dinv[i], ri, acc[1]);
+    }
+  }
+  double tot[2];
+  if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
+    out2[0] = tot[0];
+    out2[1] = tot[1];
+  }
+}
+
+// p = dinv r + y3[agg] + beta p  (frozen: nothing; agg == NULL: no aggregation level)
+__global__ void __launch_bounds__(kT)
+    ml_inner_direction_kernel(int64_t n, const double *__restrict__ dinv,
+                              const double *__restrict__ r, const uint32_t *__restrict__ agg,
+                              const double *__restrict__ y3, double *__restrict__ p,
+                              const double *__restrict__ s) {
+  if (s[S_CONV] != 0.0 || s[S_BREAK] != 0.0) return;
+  const double beta = s[S_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double z = dinv[i] * r[i];
+    if (agg) {
+      const uint32_t a = agg[i];
+      if (a != 0xffffffffu) z += y3[a];
+    }
+    p[i] = fma(beta, p[i], z);
+  }
+}
+
+// y = Ac x with Ac in ELL format (column major: entry k of row v at [k * n + v]) ;
+// dot_out = x . y over all local rows.  One thread per row: coalesced matrix reads.
+__global__ void __launch_bounds__(kT)
+    ml_ell_spmv_kernel(int64_t n, int width, const uint32_t *__restrict__ cols,
+                       const double *__restrict__ vals, const double *__restrict__ x,
+                       double *__restrict__ y, double *__restrict__ dot_out,
+                       double *__restrict__ partials) {
+  double acc[1] = {0.0};
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    double sum = 0.0;
+    for (int k = 0; k < width; ++k)
+      sum = fma(vals[(int64_t)k * n + v], x[cols[(int64_t)k * n + v]], sum);
+    y[v] = sum;
+    acc[0] = fma(x[v], sum, acc[0]);
+  }
+  if (dot_out) {
+    double tot[1];
+    if (semk_finish_reduction<1>(acc, partials, tot) && threadIdx.x == 0) dot_out[0] = tot[0];
+  }
+}
+
+// Assemble the vertex coarse operator from the element matrices Ace into ELL rows: one
+// thread per vertex walks its element entries in ascending order (fixed summation order).
+// Row layout: diagonal first, then columns in order of first appearance, padded with
+// (v, 0).  Dirichlet vertices get the identity row.
+__global__ void __launch_bounds__(kT)
+    ml_ell_build_kernel(int64_t n_v, int width, const uint32_t *__restrict__ vptr,
+                        const uint32_t *__restrict__ vpos, const uint32_t *__restrict__ vert_c,
+                        const double *__restrict__ Ace, const uint8_t *__restrict__ dirichlet_c,
+                        uint32_t *__restrict__ cols, double *__restrict__ vals,
+                        int *__restrict__ overflow) {
+  const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= n_v) return;
+  uint32_t lc[32];
+  double lv[32];
+  int cnt = 1;
+  lc[0] = (uint32_t)v;
+  lv[0] = 0.0;
+  for (uint32_t q = vptr[v]; q < vptr[v + 1]; ++q) {
+    const uint32_t ent = vpos[q];
+    const uint32_t e = ent >> 2, i = ent & 3u;
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t cidx = vert_c[e * 4 + j];
+      const double a = Ace[(int64_t)e * 16 + i * 4 + j];
+      int k = 0;
+      while (k < cnt && lc[k] != cidx) ++k;
+      if (k == cnt) {
+        if (cnt >= width) {
+          atomicExch(overflow, 1);
+          continue;
+        }
+        lc[cnt] = cidx;
+        lv[cnt] = 0.0;
+        ++cnt;
+      }
+      lv[k] += a;
+    }
+  }
+  if (dirichlet_c && dirichlet_c[v]) lv[0] = 1.0;
+  for (int k = 0; k < width; ++k) {
+    cols[(int64_t)k * n_v + v] = k < cnt ? lc[k] : (uint32_t)v;
+    vals[(int64_t)k * n_v + v] = k < cnt ? lv[k] : 0.0;
+  }
+}
+
+// y = A x, A dense [n][n] row major in FP32 (the top-level inverse only enters the
+// preconditioner; FP64 accumulation): one warp per row
+__global__ void __launch_bounds__(kT)
+    ml_dense_matvec_f32_kernel(int64_t n, const float *__restrict__ A,
+                               const double *__restrict__ x, double *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const float *row = A + i * n;
+    double s0 = 0.0, s1 = 0.0;
+    if ((n & 3) == 0) {
+      const float4 *row4 = reinterpret_cast<const float4 *>(row);
+      const double2 *x2 = reinterpret_cast<const double2 *>(x);
+      for (int64_t j = lane; j < (n >> 2); j += 32) {
+        const float4 a = row4[j];
+        const double2 b0 = x2[2 * j], b1 = x2[2 * j + 1];
+        s0 = fma((double)a.x, b0.x, s0);
+        s1 = fma((double)a.y, b0.y, s1);
+        s0 = fma((double)a.z, b1.x, s0);
+        s1 = fma((double)a.w, b1.y, s1);
+      }
+    } else {
+      for (int64_t j = lane; j < n; j += 32) s0 = fma((double)row[j], x[j], s0);
+    }
+    double sum = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if (lane == 0) y[i] = sum;
   }
 }
 
@@ -448,6 +611,32 @@ extern "C" int semk_comm_allreduce_f64(const semk_comm *comm, double *buf, int64
   return SEMK_OK;
 }
 
+extern "C" int semk_sc_coarse_ell_build_f64(const semk_sc_coarse *cs, int width, uint32_t *cols,
+                                           double *vals, int32_t *overflow, void *stream) {
+  SEMK_REQUIRE(cs && cs->n_v > 0 && cs->Ace && cs->vert_c && cs->vptr && cs->vpos && cols && vals &&
+                   overflow,
+               "semk_sc_coarse_ell_build_f64: bad argument");
+  SEMK_REQUIRE(width >= 1 && width <= 32, "semk_sc_coarse_ell_build_f64: width outside [1, 32]");
+  const unsigned grid = (unsigned)((cs->n_v + kT - 1) / kT);
+  ml_ell_build_kernel<<<grid, kT, 0, semk_stream(stream)>>>(
+      cs->n_v, width, cs->vptr, cs->vpos, cs->vert_c, cs->Ace, cs->dirichlet_c, cols, vals,
+      overflow);
+  SEMK_LAUNCH_CHECK("ml_ell_build_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_coarse_ell_apply_f64(const semk_sc_coarse *cs, const double *x, double *y,
+                                           double *dot_out, void *stream) {
+  SEMK_REQUIRE(cs && cs->n_v > 0 && cs->ell_width > 0 && cs->ell_cols && cs->ell_vals && x && y &&
+                   x != y,
+               "semk_sc_coarse_ell_apply_f64: bad argument");
+  SEMK_REQUIRE(!dot_out || cs->partials, "semk_sc_coarse_ell_apply_f64: dot_out needs partials");
+  ml_ell_spmv_kernel<<<blocks_for(cs->n_v), kT, 0, semk_stream(stream)>>>(
+      cs->n_v, (int)cs->ell_width, cs->ell_cols, cs->ell_vals, x, y, dot_out, cs->partials);
+  SEMK_LAUNCH_CHECK("ml_ell_spmv_kernel");
+  return SEMK_OK;
+}
+
 extern "C" int semk_sc_top_assemble_f64(const semk_sc_coarse *cs, int64_t n_agg,
                                        const uint32_t *agg, const uint32_t *aptr_all,
                                        const uint32_t *aidx_all, double *A3, void *stream) {
@@ -481,7 +670,8 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
                "semk_sc_mlpcg_solve_f64: missing transfer tables");
   const bool three = opts->levels == 3;
   if (three)
-    SEMK_REQUIRE(top && top->n_agg > 0 && top->agg && top->aptr && top->aidx && top->A3inv,
+    SEMK_REQUIRE(top && top->n_agg > 0 && top->agg && top->aptr && top->aidx &&
+                     (top->A3inv || top->A3inv_f32),
                  "semk_sc_mlpcg_solve_f64: levels = 3 needs a consistent semk_sc_top");
   const semk_comm *comm = dist ? dist->comm : nullptr;
   int rcode = check_comm(comm, "semk_sc_mlpcg_solve_f64");
@@ -502,8 +692,8 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
   const int64_t na_pad = (na + 31) & ~(int64_t)31;
   double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad, *z = work + 3 * n_pad;
   double *rc = work_c, *xc = work_c + nv_pad;          // rc doubles as the inner residual
-  double *pi = work_c + 2 * nv_pad, *Api = work_c + 3 * nv_pad, *zi = work_c + 4 * nv_pad;
-  double *r3 = work_c + 6 * nv_pad, *y3 = r3 + na_pad + 32;   // r3[na] = r.r rides with r3
+  double *pi = work_c + 2 * nv_pad, *Api = work_c + 3 * nv_pad;
+  double *r3 = work_c + 6 * nv_pad, *y3 = r3 + na_pad + 32;   // r3[na..na+2) = {r.r, r.(dinv r)}
   double *so = sc, *si = sc + S_LEN;                   // scalar blocks: outer, inner
   double *scratch2 = sc + 2 * S_LEN;                   // {r.r, b.b} of the initial residual
   const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
@@ -528,7 +718,8 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
   auto step = [&](double *buf, int nred, int opcode, double *s) -> int {
     // the inner preconditioner is a fixed linear operator: standard beta there
     const int flex = (s == so) ? opts->flexible : 0;
-    ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, buf, nred, opcode, flex, s);
+    ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, buf, nred, opcode, flex, s, nullptr, nullptr,
+                                               0);
     SEMK_LAUNCH_CHECK("ml_step_kernel");
     return SEMK_OK;
   };
@@ -544,43 +735,52 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
     if (e != SEMK_OK) return e;
     return exchange(halo_f, n, out, in, op->dirichlet, dot);
   };
+  const bool ell = cs->ell_width > 0 && cs->ell_cols && cs->ell_vals;
   auto coarse_apply = [&](const double *in, double *out, double *dot) -> int {
-    int e = semk_sc_coarse_apply_f64(n_elem, cs, in, out, flags, dot, st);
-    if (e != SEMK_OK) return e;
+    if (ell) {
+      ml_ell_spmv_kernel<<<gc, blk, 0, st>>>(nv, (int)cs->ell_width, cs->ell_cols, cs->ell_vals,
+                                             in, out, dot, cs->partials);
+      SEMK_LAUNCH_CHECK("ml_ell_spmv_kernel");
+    } else {
+      int e = semk_sc_coarse_apply_f64(n_elem, cs, in, out, flags, dot, st);
+      if (e != SEMK_OK) return e;
+    }
     return exchange(halo_c, nv, out, in, cs->dirichlet_c, dot);
   };
-  // inner preconditioner tail: zi = dinv_c ri is done; add the aggregation correction and
-  // leave {r.z, z.Ap} in si[S_RZN..]; `rr_slot` holds r.r of this rank
-  auto inner_tail = [&](bool first) -> int {
+  // One inner iteration (first = the set-up step of a solve: no direction yet).  z = dinv r
+  // + P2 y3 is never stored: its dot with r is r.(dinv r) + y3.r3, and the new direction is
+  // formed straight from r, dinv and y3.  Two all-reduces: p.Ap and [r3 | r.r | r.(dinv r)].
+  auto inner_step = [&](bool first) -> int {
     int e;
+    if (!first) {
+      if ((e = coarse_apply(pi, Api, si + S_PAP)) != SEMK_OK) return e;
+      if ((e = step(si + S_PAP, 1, OP_ALPHA, si)) != SEMK_OK) return e;
+    }
+    ml_inner_update_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, first ? 1 : 0, pi, Api, dinv_c, xc, rc,
+                                               si, r3 + na, vec_partials);
+    SEMK_LAUNCH_CHECK("ml_inner_update_kernel");
     if (three) {
       ml_agg_restrict_kernel<<<ga, blk, 0, st>>>(na, top->aptr, top->aidx, rc, r3);
       SEMK_LAUNCH_CHECK("ml_agg_restrict_kernel");
-      if ((e = step(r3, (int)na + 1, first ? OP_RR_FIRST : OP_RR, si)) != SEMK_OK) return e;
-      ml_dense_matvec_kernel<<<ga, blk, 0, st>>>(na, top->A3inv, r3, y3);
-      SEMK_LAUNCH_CHECK("ml_dense_matvec_kernel");
-    } else {
-      if ((e = step(r3, 1, first ? OP_RR_FIRST : OP_RR, si)) != SEMK_OK) return e;
     }
-    ml_correct_dot_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, three ? top->agg : nullptr, y3, rc,
-                                              first ? nullptr : Api, zi, si + S_RZN,
-                                              vec_partials);
-    SEMK_LAUNCH_CHECK("ml_correct_dot_kernel");
-    if ((e = step(si + S_RZN, 2, first ? OP_BETA_FIRST : OP_BETA, si)) != SEMK_OK) return e;
-    ml_direction_kernel<<<gc, blk, 0, st>>>(nv, zi, pi, si);
-    SEMK_LAUNCH_CHECK("ml_direction_kernel");
+    if ((e = step(r3, (int)na + 2, first ? OP_RR2_FIRST : OP_RR2, si)) != SEMK_OK) return e;
+    if (three) {
+      if (top->A3inv_f32)
+        ml_dense_matvec_f32_kernel<<<ga, blk, 0, st>>>(na, top->A3inv_f32, r3, y3);
+      else
+        ml_dense_matvec_kernel<<<ga, blk, 0, st>>>(na, top->A3inv, r3, y3);
+      SEMK_LAUNCH_CHECK("ml_dense_matvec_kernel");
+    }
+    ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, nullptr, 0,
+                                               first ? OP_BETA_TOP_FIRST : OP_BETA_TOP, 0, si, y3,
+                                               r3, (int)na);
+    SEMK_LAUNCH_CHECK("ml_step_kernel");
+    ml_inner_direction_kernel<<<gc, blk, 0, st>>>(nv, dinv_c, rc, three ? top->agg : nullptr, y3,
+                                                  pi, si);
+    SEMK_LAUNCH_CHECK("ml_inner_direction_kernel");
     return SEMK_OK;
   };
-  double *rr_slot = r3 + na;   // r.r of the inner residual, reduced together with r3
-  auto inner_iteration = [&]() -> int {
-    int e = coarse_apply(pi, Api, si + S_PAP);
-    if (e != SEMK_OK) return e;
-    if ((e = step(si + S_PAP, 1, OP_ALPHA, si)) != SEMK_OK) return e;
-    ml_update_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, pi, Api, dinv_c, xc, rc, zi, si, rr_slot,
-                                         vec_partials);
-    SEMK_LAUNCH_CHECK("ml_update_kernel");
-    return inner_tail(false);
-  };
+  auto inner_iteration = [&]() -> int { return inner_step(false); };
   int64_t inner_sum = 0;
   int inner_solves = 0, predicted = 8;
   // xc ~= Ac^-1 rc (rc is overwritten by the inner residual)
@@ -589,9 +789,7 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
     SEMK_CUDA_CHECK(cudaMemsetAsync(xc, 0, sizeof(double) * nv, st));
     SEMK_CUDA_CHECK(cudaMemsetAsync(si, 0, sizeof(double) * S_TOL2, st));   // keeps S_TOL2
     SEMK_CUDA_CHECK(cudaMemsetAsync(pi, 0, sizeof(double) * nv, st));
-    ml_first_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, dinv_c, rc, zi, rr_slot, vec_partials);
-    SEMK_LAUNCH_CHECK("ml_first_kernel");
-    if ((e = inner_tail(true)) != SEMK_OK) return e;
+    if ((e = inner_step(true)) != SEMK_OK) return e;
     int launched = 0;
     int chunk = predicted > 2 ? predicted - 1 : 1;
     while (launched < opts->inner_maxiter) {

@@ -113,6 +113,30 @@ def test_three_level_at_size_and_on_an_unstructured_mesh():
     assert i3.converged and rel_l2(host(a3), host(aj)) < 1e-10
 
 
+@pytest.mark.parametrize("mesh_kind", ["structured", "pinwheel"])
+def test_coarse_operator_ell_rows_equal_the_element_form(mesh_kind):
+    """The assembled ELL rows of the vertex coarse operator (what the driver multiplies
+    with) against the element-matrix form, Dirichlet identity rows and fused dot included."""
+    if mesh_kind == "structured":
+        mesh, mngr = build_package_case("C", 12, 10, 5, True, True)
+    else:
+        mesh = meshgen.pinwheel_mesh(7, 4, rings=3)
+        b1 = LagrangeGaussLobatto(4)
+        mngr = discrete.DOFManagerSC(mesh, 1, TensorProductQS(b1, b1), rcm_order=True)
+    sc = mngr.condensed_poisson_operator(dirichlet=mngr.boundary_node_mask("ebc"))
+    cs, t, n_v = sc._build_coarse()
+    assert cs.ell_width >= 9
+    xc = torch.from_numpy(np.random.default_rng(4).standard_normal(n_v)).cuda()
+    d1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    y1 = sc.coarse_apply(xc, dot_out=d1)
+    y2 = sc.coarse_apply(xc, dot_out=d2, ell=True)
+    assert rel_l2(host(y2), host(y1)) < 1e-13
+    assert abs(float(d1) - float(d2)) < 1e-12 * abs(float(d1))
+    fixed = t["dirichlet_c"].bool()
+    assert torch.equal(y2[fixed], xc[fixed])
+
+
 def test_top_level_operator_matches_the_host_assembly():
     mesh, mngr = build_package_case("C", 12, 10, 5, True, True)
     on = mngr.boundary_node_mask("ebc")
