@@ -684,6 +684,35 @@ int semk_values_at_nodes_f64(int n1, int64_t n_elem, const uint32_t *l2g, const 
                              const double *Emat, const double *coeffs, double *values,
                              void *stream);
 
+/* Batched point location and field evaluation (rest of SURVEY.md 8(f) row 4):
+ * DOFManager.find_elem_containing_point (sem/discrete.py:263-280: cells tried in ascending
+ * centroid distance), Mapping.inv (sem/mapping.py:146-178: Newton from xi = 0, it_max = 8,
+ * |dx| <= tol = 1e-8, inside iff -1 <= xi <= 1; sem/rootfind.py:22-53) and
+ * DOFManager.interpolate (sem/discrete.py:221-233), one thread per point.
+ *   x_phys    : device [n_elem][2][NN] GLL-point coordinates (semk_geom_factors_f64)
+ *   centroids : device [n_elem][2] mean of the four vertices (sem/discrete.py:1108-1113)
+ *   gll_nodes, bary_wts : device [n1]; D: device [NN]
+ *   bins      : uniform grid bins_x x bins_y of cell size (bin_hx, bin_hy) anchored at
+ *               (bin_x0, bin_y0); bin (i, j) lists elements bin_elems[bin_ptr[i*bins_y+j] ..
+ *               bin_ptr[i*bins_y+j+1]) -- every element must be listed in all bins its
+ *               (slightly inflated) bounding box touches
+ *   points    : device [2][n_points]
+ *   elem_out  : device int64 [n_points], -1 = not inside any candidate (OutsideDomain)
+ *   xi_out    : device [2][n_points] parametric coordinates (NaN when not found)
+ * A Newton run that does not converge within it_max steps counts as "not this element"
+ * (the reference raises SolverFailure there). */
+int semk_locate_points_f64(int n1, int64_t n_elem, const double *x_phys, const double *centroids,
+                           const double *gll_nodes, const double *bary_wts, const double *D,
+                           double bin_x0, double bin_y0, double bin_hx, double bin_hy, int bins_x,
+                           int bins_y, const uint32_t *bin_ptr, const uint32_t *bin_elems,
+                           int64_t n_points, const double *points, int it_max, double tol,
+                           int64_t *elem_out, double *xi_out, void *stream);
+/* values[q] = sum_mn coeffs[l2g[elem[q]][m][n]] l_m(xi0) l_n(xi1) (NaN where elem < 0) */
+int semk_interpolate_points_f64(int n1, int64_t n_points, const int64_t *elem, const double *xi,
+                                const uint32_t *l2g, const double *gll_nodes,
+                                const double *bary_wts, const double *coeffs, double *values,
+                                void *stream);
+
 /* ------------------------------------------------------------------------
  * Multi-GPU: interface exchange of a strip partition over NVLink peer memory
  * (the reference itself is single-process -- its serial

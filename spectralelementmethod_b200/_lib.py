@@ -199,6 +199,9 @@ SIGNATURES = {
     "semk_sc_restrict_f64": (_I, [C.POINTER(semk_sc_coarse), _P, _L, _P, _P]),
     "semk_sc_prolong_add_f64": (_I, [_L, C.POINTER(semk_sc_coarse), _P, _P, _P]),
     "semk_values_at_nodes_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
+    "semk_locate_points_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _I, _P, _P, _L,
+                                    _P, _I, _D, _P, _P, _P]),
+    "semk_interpolate_points_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P]),
     "semk_halo_region_bytes": (_L, [_L]),
     "semk_peer_alloc": (_I, [_L, C.POINTER(_P), _P]),
     "semk_peer_open": (_I, [_P, C.POINTER(_P)]),

@@ -237,6 +237,118 @@ class DOFManager(object):
                 device.ptr(src[i]), device.ptr(out[i]), device.stream_ptr()))
         return out.reshape(coeffs.shape)
 
+    # -- batched point location / evaluation on the device (additive API) -------------------
+    def _locate_tables(self):
+        """Device tables of the batched point location (lazy): GLL-point coordinates of
+        every element (geometry kernel), cell centroids, and a uniform bin grid listing each
+        element in every bin its bounding box (inflated by 10 %) touches."""
+        cache = getattr(self, "_locate_cache", None)
+        if cache is not None:
+            return cache
+        import torch
+        from . import _lib, device
+        _lib.require_device()
+        mesh = self._mesh
+        tab = device.basis_tables(self._map_basis)
+        N = tab.n1
+        NN = N * N
+        l2g = mesh.node_map_array().reshape(-1, NN)
+        E = int(l2g.shape[0])
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nodes_dev = device._f64(mesh.nodes, dev)
+        l2g_dev = device.as_i32_bits(l2g, dev)
+        x_phys = torch.empty((E, 2, NN), dtype=torch.float64, device=dev)
+        device.geom_factors(tab, nodes_dev, l2g_dev, E, x_phys=x_phys, check=False)
+        if not hasattr(mesh, "_centroids"):
+            mesh._compute_cell_centroids()
+        lo = x_phys.amin(dim=2).cpu().numpy()
+        hi = x_phys.amax(dim=2).cpu().numpy()
+        pad = 0.1 * (hi - lo) + 1e-12 * np.abs(hi).max()
+        lo, hi = lo - pad, hi + pad
+        g0, g1 = lo.min(axis=0), hi.max(axis=0)
+        n_side = int(min(4096, max(1, np.ceil(np.sqrt(E)))))
+        h = (g1 - g0) / n_side
+        h[h <= 0] = 1.0
+        i0 = np.clip(np.floor((lo - g0) / h).astype(np.int64), 0, n_side - 1)
+        i1 = np.clip(np.floor((hi - g0) / h).astype(np.int64), 0, n_side - 1)
+        span = i1 - i0 + 1
+        bins, elems = [], []
+        ids = np.arange(E, dtype=np.int64)
+        for di in range(int(span[:, 0].max())):
+            for dj in range(int(span[:, 1].max())):
+                ok = (di < span[:, 0]) & (dj < span[:, 1])
+                bins.append((i0[ok, 0] + di) * n_side + i0[ok, 1] + dj)
+                elems.append(ids[ok])
+        bins, elems = np.concatenate(bins), np.concatenate(elems)
+        order = np.argsort(bins, kind="stable")
+        bin_ptr = np.zeros(n_side * n_side + 1, dtype=np.uint32)
+        np.cumsum(np.bincount(bins, minlength=n_side * n_side), out=bin_ptr[1:])
+        sub = [b for _, b in self._basis.iter_subbases()][0]
+        msub = [b for _, b in self._map_basis.iter_subbases()][0]
+        cache = dict(
+            dev=dev, n1=N, n_elem=E, x_phys=x_phys, l2g=l2g_dev,
+            centroids=device._f64(mesh._centroids, dev),
+            nodes=device._f64(np.asarray(msub.nodes), dev),
+            bw=device._f64(np.asarray(msub.bary_wts), dev),
+            D=device._f64(np.asarray(msub.D1), dev),
+            f_nodes=device._f64(np.asarray(sub.nodes), dev),
+            f_bw=device._f64(np.asarray(sub.bary_wts), dev), f_n1=int(sub.n_coeffs),
+            bin_ptr=device.as_i32_bits(bin_ptr, dev),
+            bin_elems=device.as_i32_bits(elems[order].astype(np.uint32), dev),
+            grid=(float(g0[0]), float(g0[1]), float(h[0]), float(h[1]), n_side))
+        self._locate_cache = cache
+        return cache
+
+    def locate_points(self, points, strict=True):
+        """Batched ``find_elem_containing_point`` on the device (sem/discrete.py:263-280 with
+        Mapping.inv, sem/mapping.py:146-178): ``points[2, M]`` (array or CUDA tensor) ->
+        ``(cells int64[M], x_param float64[2, M])`` as CUDA tensors; the cell found is the one
+        with the nearest centroid among the cells containing the point, like the reference's
+        search order.  ``strict``: raise ``OutsideDomain`` if a point is in no cell (else
+        those entries are -1 / NaN)."""
+        import torch
+        from . import _lib, device
+        t = self._locate_tables()
+        pts = device._f64(points, t["dev"]).reshape(2, -1).contiguous()
+        M = int(pts.shape[1])
+        cells = torch.empty(M, dtype=torch.int64, device=t["dev"])
+        xi = torch.empty((2, M), dtype=torch.float64, device=t["dev"])
+        x0, y0, hx, hy, n_side = t["grid"]
+        _lib.check(_lib.load().semk_locate_points_f64(
+            t["n1"], t["n_elem"], device.ptr(t["x_phys"]), device.ptr(t["centroids"]),
+            device.ptr(t["nodes"]), device.ptr(t["bw"]), device.ptr(t["D"]), x0, y0, hx, hy,
+            n_side, n_side, device.ptr(t["bin_ptr"]), device.ptr(t["bin_elems"]), M,
+            device.ptr(pts), 8, 1e-8, device.ptr(cells), device.ptr(xi), device.stream_ptr()))
+        if strict and M and bool((cells < 0).any()):
+            bad = int(torch.nonzero(cells < 0)[0])
+            raise OutsideDomain("Point {} appears outside the domain of the mesh.".format(
+                pts[:, bad].cpu().numpy()))
+        return cells, xi
+
+    def interpolate_points(self, coeffs, points, strict=True):
+        """Batched ``interpolate`` (sem/discrete.py:221-233): values of the field with GLL
+        coefficients ``coeffs[..., n_nodes]`` (CUDA tensor or array) at ``points[2, M]``;
+        returns a CUDA tensor ``[..., M]``."""
+        import torch
+        from . import _lib, device
+        t = self._locate_tables()
+        if t["f_n1"] != t["n1"]:
+            raise NotImplementedError("only the isoparametric case is usable "
+                                      "(sem/discrete.py:594-597)")
+        cells, xi = self.locate_points(points, strict=strict)
+        c = device._f64(coeffs, t["dev"])
+        if c.shape[-1] != self._mesh.n_nodes:
+            raise ValueError("coeffs must have n_nodes entries along the last axis")
+        src = c.reshape(-1, c.shape[-1]).contiguous()
+        M = int(cells.numel())
+        out = torch.empty((src.shape[0], M), dtype=torch.float64, device=t["dev"])
+        for i in range(src.shape[0]):
+            _lib.check(_lib.load().semk_interpolate_points_f64(
+                t["f_n1"], M, device.ptr(cells), device.ptr(xi), device.ptr(t["l2g"]),
+                device.ptr(t["f_nodes"]), device.ptr(t["f_bw"]), device.ptr(src[i]),
+                device.ptr(out[i]), device.stream_ptr()))
+        return out.reshape(tuple(c.shape[:-1]) + (M,))
+
     def get_global_matrix_equation(self):
         raise NotImplementedError()
 

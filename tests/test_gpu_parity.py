@@ -634,3 +634,64 @@ def test_values_at_nodes_device_at_size_reproduces_polynomials():
     coeffs[l2g] = f(xg, yg)            # continuous: shared nodes get the same value from both sides
     got = host(mngr.values_at_nodes(dev(coeffs)))
     assert rel_l2(got, f(x, y)) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C534_dm", "C448_sc_rcm", "C3310_dm_rcm", "S324_sc"])
+def test_batched_point_location_and_interpolation_vs_reference(name):
+    """locate_points / interpolate_points (csrc/semk_locate.cu) against the live reference's
+    find_elem_containing_point / Mapping.inv / interpolate run point by point
+    (oracle/make_golden_values.py): same cell, parametric coordinates and values."""
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "values_%s.npz" % name)))
+    nx, ny, p, sc, rcm, kind = d["meta"].tolist()
+    mesh, mngr = build_package_case(chr(kind), nx, ny, p, bool(sc), bool(rcm))
+    pts = d["many_points"].T.copy()                       # [2, M]
+    cells, xi = mngr.locate_points(pts)
+    cells, xi = host(cells), host(xi)
+    same = cells == d["many_cells"]
+    # a point on an edge shared by two cells may be claimed by either (exact centroid ties)
+    assert same.mean() > 0.9
+    assert np.abs(xi.T[same] - d["many_xparam"][same]).max() < 1e-8   # Newton stops at |dx| <= 1e-8
+    vals = host(mngr.interpolate_points(d["coeffs"], pts))            # [2, M]
+    assert rel_l2(vals.T, d["many_values"]) < 1e-7                    # (inherits the Newton tolerance)
+    # exact consistency of the pair (cell, xi) with the mapping: x(xi) reproduces the point
+    t = mngr._locate_tables()
+    b1 = LagrangeGaussLobatto(p)
+    xph = host(t["x_phys"]).reshape(-1, 2, p + 1, p + 1)
+    for q in range(0, pts.shape[1], 7):
+        L0 = np.asarray(b1(np.array([xi[0, q]]))).ravel()
+        L1 = np.asarray(b1(np.array([xi[1, q]]))).ravel()
+        back = np.einsum("imn,m,n->i", xph[cells[q]], L0, L1)
+        assert np.abs(back - pts[:, q]).max() < 1e-8
+    # the single-point host path agrees
+    mesh._compute_cell_centroids()
+    one = np.array([mngr.interpolate(d["coeffs"], pts[:, q]) for q in range(5)])
+    assert rel_l2(one, vals.T[:5]) < 1e-7
+    # outside the mesh: strict raises the reference's exception, non-strict marks the entry
+    far = np.array([[3.0], [0.0]])
+    with pytest.raises(discrete.OutsideDomain):
+        mngr.locate_points(far)
+    c2, x2 = mngr.locate_points(np.concatenate([pts[:, :3], far], axis=1), strict=False)
+    assert int(c2[-1]) == -1 and bool(torch.isnan(x2[:, -1]).all()) and int(c2[0]) == cells[0]
+
+
+@pytest.mark.gpu
+def test_batched_point_location_at_size():
+    """10^6 points on a curved 256 x 256 mesh: every point is found, x(xi) maps back, and a
+    polynomial field of degree p is evaluated exactly."""
+    p, n = 6, 256
+    mesh, mngr = build_package_case("C", n, n, p, False, False)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-0.999, 0.999, size=(2, 1000000))
+    cells, xi = mngr.locate_points(pts)
+    assert int(cells.min()) >= 0 and float(xi.abs().max()) <= 1.0
+    # coefficients of f at the GLL points of every element (device geometry)
+    t = mngr._locate_tables()
+    xph = t["x_phys"]                                     # [E, 2, NN]
+    f = lambda a, b: 1.0 + 0.5 * a - 0.25 * b             # noqa: E731  (in every element's space)
+    coeffs = torch.zeros(mesh.n_nodes, dtype=torch.float64, device="cuda")
+    l2g = torch.from_numpy(mngr.node_map_array().reshape(-1, (p + 1) ** 2).astype(np.int64)).cuda()
+    coeffs[l2g] = f(xph[:, 0], xph[:, 1])
+    vals = mngr.interpolate_points(coeffs, pts)
+    want = f(torch.from_numpy(pts[0]).cuda(), torch.from_numpy(pts[1]).cuda())
+    assert float((vals - want).abs().max()) < 1e-7
