@@ -31,6 +31,7 @@ from ._lib import DIRICHLET_IDENTITY, MASK_IN, MASK_OUT
 from .operators import PCGInfo
 
 __all__ = ["CondensedPoissonOperator", "CondensedLocalSystems", "condensed_tables", "coarse_tables",
+           "condensed_tables_device", "coarse_tables_device",
            "element_tiles", "aggregate_tables", "aggregate_csr", "top_level_inverse"]
 
 
@@ -55,6 +56,98 @@ def condensed_tables(l2g, ext_loc, n_ext):
     node_ptr = np.zeros(n_ext + 1, dtype=np.uint32)
     np.cumsum(counts, out=node_ptr[1:])
     return l2g_ext, node_ptr, node_pos
+
+
+def _u32(t):
+    """int32-bit-pattern tensor of uint32 values -> int64 values."""
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
+def condensed_tables_device(l2g_dev, ext_loc, n_ext):
+    """``condensed_tables`` on the device: the same integer tables (stable sort, so the
+    node -> entries order is bit-identical to the host builder's) without the host pass
+    over 32 M entries at config 2.  ``l2g_dev``: int32-bit-pattern CUDA tensor [E, NN].
+    Returns int32-bit-pattern CUDA tensors (l2g_ext, node_ptr, node_pos)."""
+    dev = l2g_dev.device
+    ext = torch.as_tensor(np.asarray(ext_loc, dtype=np.int64), device=dev)
+    l2g_ext = l2g_dev[:, ext].contiguous()
+    flat = _u32(l2g_ext.reshape(-1))
+    if int(flat.max()) >= n_ext:
+        raise AssertionError("exterior nodes are not numbered first")
+    if flat.numel() >= 2 ** 31:
+        raise NotImplementedError("more than 2^31 element-exterior entries")
+    node_pos = torch.sort(flat, stable=True).indices.to(torch.int32)
+    counts = torch.bincount(flat, minlength=n_ext)
+    if bool((counts == 0).any()):
+        raise AssertionError("an exterior id is not used by any element")
+    node_ptr = torch.zeros(n_ext + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=node_ptr[1:])
+    return l2g_ext, node_ptr.to(torch.int32), node_pos
+
+
+def coarse_tables_device(l2g_ext, node_ptr, node_pos, dirichlet, gll_nodes):
+    """``coarse_tables`` on the device (same tables, same orders; see there).  Inputs are the
+    int32-bit-pattern CUDA tensors of ``condensed_tables_device`` and a bool CUDA tensor (or
+    None).  Returns a dict of CUDA tensors (uint32 tables as int32 bit patterns) + n_v."""
+    dev = l2g_ext.device
+    E, NE = l2g_ext.shape
+    p = NE // 4
+    N = p + 1
+    n_ext = int(node_ptr.numel() - 1)
+    t = (1.0 + np.asarray(gll_nodes, dtype=np.float64)) / 2.0
+    if t.size != N:
+        raise ValueError("gll_nodes must have p + 1 entries")
+    va = np.zeros(NE, dtype=np.int64)
+    vb = np.zeros(NE, dtype=np.int64)
+    wa = np.zeros(NE)
+    wb = np.zeros(NE)
+    va[:4] = vb[:4] = np.arange(4)
+    wa[:4] = 1.0
+    inner = np.arange(1, N - 1)
+    for edge, (a, b) in enumerate(((0, 1), (2, 3), (0, 2), (1, 3))):
+        k = 4 + edge * (N - 2) + np.arange(N - 2)
+        va[k], vb[k] = a, b
+        wa[k], wb[k] = 1.0 - t[inner], t[inner]
+    phi = np.zeros((NE, 4))
+    phi[np.arange(NE), va] += wa
+    phi[np.arange(NE), vb] += wb
+    i64 = dict(dtype=torch.int64, device=dev)
+    va_d, vb_d = torch.as_tensor(va, device=dev), torch.as_tensor(vb, device=dev)
+    wa_d, wb_d = torch.as_tensor(wa, device=dev), torch.as_tensor(wb, device=dev)
+    vert = _u32(l2g_ext[:, :4])
+    vids = torch.unique(vert)                                  # sorted
+    n_v = int(vids.numel())
+    vmap = torch.full((n_ext,), -1, **i64)
+    vmap[vids] = torch.arange(n_v, **i64)
+    vert_c = vmap[vert]
+    if dirichlet is None:
+        dirichlet = torch.zeros(n_ext, dtype=torch.bool, device=dev)
+    dirichlet = dirichlet[:n_ext]
+    dirichlet_c = dirichlet[vids]
+    first = _u32(node_pos)[_u32(node_ptr[:-1])]
+    e = torch.div(first, NE, rounding_mode="floor")
+    k = first - e * NE
+    pv = torch.stack([vert_c[e, va_d[k]], vert_c[e, vb_d[k]]], dim=1)
+    pw = torch.stack([wa_d[k], wb_d[k]], dim=1)
+    pw[dirichlet] = 0.0
+    pw[dirichlet_c[pv]] = 0.0
+    flat_v, flat_w = pv.reshape(-1), pw.reshape(-1)
+    flat_g = torch.arange(n_ext, **i64).repeat_interleave(2)
+    keep = flat_w != 0.0
+    kv = flat_v[keep]
+    order = torch.sort(kv, stable=True).indices
+    ridx = flat_g[keep][order]
+    rw = flat_w[keep][order].contiguous()
+    rptr = torch.zeros(n_v + 1, **i64)
+    torch.cumsum(torch.bincount(kv, minlength=n_v), 0, out=rptr[1:])
+    vflat = vert_c.reshape(-1)
+    vpos = torch.sort(vflat, stable=True).indices
+    vptr = torch.zeros(n_v + 1, **i64)
+    torch.cumsum(torch.bincount(vflat, minlength=n_v), 0, out=vptr[1:])
+    i32 = lambda a: a.to(torch.int32).contiguous()             # noqa: E731 (bit patterns < 2^31)
+    return dict(phi=phi, vert_c=i32(vert_c), n_v=n_v, dirichlet_c=dirichlet_c,
+                pv=i32(pv), pw=pw.contiguous(), rptr=i32(rptr), ridx=i32(ridx), rw=rw,
+                vptr=i32(vptr), vpos=i32(vpos))
 
 
 class CondensedPoissonOperator(object):
@@ -108,18 +201,23 @@ class CondensedPoissonOperator(object):
 
         l2g = mesh.node_map_array().reshape(-1, NN)
         self.n_elem = int(l2g.shape[0])
-        l2g_ext, node_ptr, node_pos = condensed_tables(l2g, ext_loc, self.n_ext)
-        self.l2g_ext_host = l2g_ext
-
-        f64 = dict(dtype=torch.float64, device=self.dev)
+        # the integer tables are built on the device (stable sorts: bit-identical to the host
+        # builder `condensed_tables`, tests/test_gpu_condensed.py)
+        self.l2g_dev = device.as_i32_bits(l2g, self.dev)
+        l2g_ext, node_ptr, node_pos = condensed_tables_device(self.l2g_dev, ext_loc, self.n_ext)
+        self._l2g_ext_host = None
         self._t = dict(
             ext_loc=torch.from_numpy(ext_loc).to(self.dev),
-            l2g_ext=device.as_i32_bits(l2g_ext, self.dev),
-            node_ptr=device.as_i32_bits(node_ptr, self.dev),
-            node_pos=device.as_i32_bits(node_pos, self.dev),
+            l2g_ext=l2g_ext, node_ptr=node_ptr, node_pos=node_pos,
         )
-        self.l2g_dev = device.as_i32_bits(l2g, self.dev)
         self._finish_common(full_mask)
+
+    @property
+    def l2g_ext_host(self):
+        """Exterior L2G table on the host, uint32[E, 4p] (downloaded on first use)."""
+        if self._l2g_ext_host is None:
+            self._l2g_ext_host = self._t["l2g_ext"].cpu().numpy().view(np.uint32)
+        return self._l2g_ext_host
 
     def _init_geometry(self, geometric_factors, weight):
         """Geometric factors, one plain [3][NN] block per element in reference element
@@ -328,23 +426,16 @@ class CondensedPoissonOperator(object):
         if getattr(self, "_coarse", None) is not None:
             return self._coarse
         sub = [b for _, b in self.dof_mngr._basis.iter_subbases()][0]
-        node_ptr = self._t["node_ptr"].cpu().numpy().view(np.uint32)
-        node_pos = self._t["node_pos"].cpu().numpy().view(np.uint32)
-        ct = coarse_tables(self.l2g_ext_host, node_ptr, node_pos, self.dirichlet_host,
-                           np.asarray(sub.nodes))
+        ct = coarse_tables_device(self._t["l2g_ext"], self._t["node_ptr"], self._t["node_pos"],
+                                  self.dirichlet_dev.bool() if self.dirichlet_dev is not None
+                                  else None, np.asarray(sub.nodes))
         f64 = dict(dtype=torch.float64, device=self.dev)
         n_v = ct["n_v"]
         t = dict(
             phi=device._f64(ct["phi"], self.dev),
-            vert_c=device.as_i32_bits(ct["vert_c"], self.dev),
-            vptr=device.as_i32_bits(ct["vptr"], self.dev),
-            vpos=device.as_i32_bits(ct["vpos"], self.dev),
-            pv=device.as_i32_bits(ct["pv"], self.dev),
-            pw=device._f64(ct["pw"], self.dev),
-            rptr=device.as_i32_bits(ct["rptr"], self.dev),
-            ridx=device.as_i32_bits(ct["ridx"], self.dev),
-            rw=device._f64(ct["rw"], self.dev),
-            dirichlet_c=torch.from_numpy(ct["dirichlet_c"].astype(np.uint8)).to(self.dev),
+            vert_c=ct["vert_c"], vptr=ct["vptr"], vpos=ct["vpos"], pv=ct["pv"], pw=ct["pw"],
+            rptr=ct["rptr"], ridx=ct["ridx"], rw=ct["rw"],
+            dirichlet_c=ct["dirichlet_c"].to(torch.uint8),
             Ace=torch.empty((self.n_elem, 16), **f64),
             y_loc_c=torch.empty((self.n_elem, 4), **f64),
             partials=torch.zeros(int(self._lib.semk_vec_partials_len(n_v)), **f64),
@@ -376,11 +467,12 @@ class CondensedPoissonOperator(object):
         if not bool((dc > 0).all()):
             raise AssertionError("coarse operator has a non-positive diagonal entry")
         t["dinv_c"] = 1.0 / dc
-        t["dirichlet_c_host"] = ct["dirichlet_c"]
+        t["dirichlet_c_host"] = ct["dirichlet_c"].cpu().numpy()
+        self._vertex_valence_max = int((_u32(ct["vptr"][1:]) - _u32(ct["vptr"][:-1])).max())
         # the same operator as ELL rows for the multilevel driver: one SpMV per inner
         # iteration instead of element product + vertex sum (a vertex of valence d couples
         # to at most 2 d other vertices)
-        width = 2 * int(np.diff(ct["vptr"].astype(np.int64)).max()) + 1
+        width = 2 * self._vertex_valence_max + 1
         if width <= 32:
             t["ell_cols"] = torch.empty((width, n_v), dtype=torch.int32, device=self.dev)
             t["ell_vals"] = torch.empty((width, n_v), **f64)

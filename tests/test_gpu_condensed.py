@@ -192,3 +192,28 @@ def test_condensed_weighted_stiffness_vs_oracle():
     assert rel_l2(host(sc.apply(dev(u))), ref["Sg"] @ u) < TOL
     sc2 = mngr.condensed_poisson_operator(weight=w)
     assert rel_l2(sc2.local_schur(), ref["S"]) < TOL
+
+
+@pytest.mark.parametrize("name", SC_CASES[:4])
+def test_device_built_integer_tables_equal_the_host_builders(name):
+    """condensed_tables_device / coarse_tables_device (stable sorts on the GPU) give the
+    very tables of the NumPy builders (T0 tier: integer tables bit-exact, weights equal)."""
+    from spectralelementmethod_b200.condensed import coarse_tables, condensed_tables
+    g, mngr, sc = condensed_operator(name, "T2")
+    N = int(g["p"]) + 1
+    ext_loc = sc.ext_loc_host
+    l2g = mngr.node_map_array().reshape(-1, N * N)
+    l2g_ext, nptr, npos = condensed_tables(l2g, ext_loc, sc.n_ext)
+    u32 = lambda t: host(t).view(np.uint32)        # noqa: E731
+    assert np.array_equal(u32(sc._t["l2g_ext"]), l2g_ext)
+    assert np.array_equal(u32(sc._t["node_ptr"]), nptr)
+    assert np.array_equal(u32(sc._t["node_pos"]), npos)
+    b1 = LagrangeGaussLobatto(int(g["p"]))
+    ct = coarse_tables(l2g_ext, nptr, npos, sc.dirichlet_host, np.asarray(b1.nodes))
+    cs, t, n_v = sc._build_coarse()
+    assert n_v == ct["n_v"]
+    for key in ("vert_c", "vptr", "vpos", "pv", "rptr", "ridx"):
+        assert np.array_equal(u32(t[key]).reshape(ct[key].shape), ct[key]), key
+    assert np.array_equal(host(t["pw"]), ct["pw"]) and np.array_equal(host(t["rw"]), ct["rw"])
+    assert np.array_equal(host(t["phi"]), ct["phi"])
+    assert np.array_equal(t["dirichlet_c_host"], ct["dirichlet_c"])
