@@ -432,6 +432,8 @@ typedef struct semk_sc_op {
 #define SEMK_SC_SCHUR 1       /* S (packed) and, if sdiag_loc != NULL, its diagonal          */
 #define SEMK_SC_RHS 2         /* g_loc = f_e - A_ei A_ii^{-1} f_i                            */
 #define SEMK_SC_BACKSOLVE 4   /* u_i = A_ii^{-1} (f_i - A_ie u_e) written into u             */
+#define SEMK_SC_STORE 8       /* also keep W = A_ii^{-1} A_ie (W_out), so that later back-
+                                 substitutions are one streaming pass                       */
 
 /* One pass of the element kernel (one CTA per element).
  * slot_of_elem: device int64 [n_elem], engine slot holding element e's factors in G
@@ -444,13 +446,22 @@ typedef struct semk_sc_op {
  * SCHUR: S_out [n_elem][s_stride]; sdiag_loc [n_elem][n_ext_loc] or NULL.
  * RHS: g_loc [n_elem][n_ext_loc].  BACKSOLVE: u device [n_nodes], exterior entries
  *   read, interior entries written.
+ * STORE: W_out device [n_elem][n_ext_loc][n_int] = (A_ii^{-1} A_ie)^T (12.5 KB per element at
+ *   p = 8; 180 GB of HBM make it affordable).  c_out (optional, needs a load): device
+ *   [n_elem][n_int] = A_ii^{-1} f_i.  With both, _solve_interior_dofs (sem/discrete.py:513-524)
+ *   becomes semk_sc_backsolve_stored_f64.
  * bad_flag: device int32, set to 1 when an interior block is not positive definite. */
 int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem, const double *G,
                         int64_t g_patch_stride, int elems_per_patch, const double *D,
                         const int32_t *ext_loc, const uint32_t *l2g, const double *JxW,
                         const double *f_nodal, double f_scale, int mode, double *S_out,
                         int64_t s_stride, double *sdiag_loc, double *g_loc, double *u,
-                        int32_t *bad_flag, void *stream);
+                        double *W_out, double *c_out, int32_t *bad_flag, void *stream);
+/* u_i = c - W u_e for every element (c NULL: zero load): exterior entries of u read,
+ * interior entries written; W, c from semk_sc_element_f64. */
+int semk_sc_backsolve_stored_f64(int n1, int64_t n_elem, const double *W, const double *c,
+                                 const uint32_t *l2g, const int32_t *ext_loc, double *u,
+                                 void *stream);
 
 /* The same element kernel on the CALLER'S OWN local systems instead of the Poisson
  * recipe -- the literal inputs of DOFManagerSC.assemble_global_sc_system / solve
@@ -598,6 +609,19 @@ typedef struct semk_halo {
   uint64_t epoch;
   int32_t *status;                      /* device int */
 } semk_halo;
+
+/* Jacobi-PCG on a strip partition with everything issued natively: exactly one of op
+ * (matrix-free operator, vectors of n_nodes) / sc_op (condensed operator, vectors of n_ext)
+ * is given; after every apply the interface columns are exchanged through `halo`, and the
+ * two reductions of an iteration (p.Ap; [r.r, r.z]) are peer-memory all-reduces through
+ * `comm` (NULL or world 1: one GPU, no exchange).  n_owned: owned prefix for the dot
+ * products.  work: device [3 * (n + 32)]; sc: device [32]; other arguments as
+ * semk_pcg_solve_f64.  dinv: inverse diagonal of the GLOBAL operator. */
+int semk_pcg_dist_solve_f64(const semk_op *op, const semk_sc_op *sc_op, semk_halo *halo,
+                            const semk_comm *comm, int64_t n_owned, const double *b, double *x,
+                            const double *dinv, double *work, double *sc, double *vec_partials,
+                            double rtol, int maxiter, int check_every, semk_pcg_info *info,
+                            void *stream);
 
 /* How the multilevel solver below is spread over the ranks of a strip partition
  * (NULL or comm == NULL: one GPU).  Owned DOFs are a prefix on both levels (the right

@@ -77,7 +77,7 @@ class semk_sc_op(C.Structure):
     ]
 
 
-SC_SCHUR, SC_RHS, SC_BACKSOLVE = 1, 2, 4
+SC_SCHUR, SC_RHS, SC_BACKSOLVE, SC_STORE = 1, 2, 4, 8
 
 
 class semk_sc_top(C.Structure):
@@ -174,7 +174,8 @@ SIGNATURES = {
     "semk_scratch_row_stride": (_I, [_I, _I]),
     "semk_scale_gfactors_f64": (_I, [_I, _L, _P, _P, _P, _L, _I, _P]),
     "semk_sc_element_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L, _P,
-                                 _P, _P, _P, _P]),
+                                 _P, _P, _P, _P, _P, _P]),
+    "semk_sc_backsolve_stored_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
     "semk_sc_element_dense_f64": (_I, [_I, _L, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P, _P]),
     "semk_sc_apply_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _P, _P]),
     "semk_sc_assemble_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _D, _P]),
@@ -188,6 +189,9 @@ SIGNATURES = {
     "semk_sc_top_assemble_f64": (_I, [C.POINTER(semk_sc_coarse), _L, _P, _P, _P, _P, _P]),
     "semk_comm_region_bytes": (_L, [C.c_int32, _L]),
     "semk_comm_allreduce_f64": (_I, [C.POINTER(semk_comm), _P, _L, _P]),
+    "semk_pcg_dist_solve_f64": (_I, [C.POINTER(semk_op), C.POINTER(semk_sc_op),
+                                     C.POINTER(semk_halo), C.POINTER(semk_comm), _L, _P, _P, _P,
+                                     _P, _P, _P, _D, _I, _I, C.POINTER(semk_pcg_info), _P]),
     "semk_sc_mlpcg_solve_f64": (_I, [C.POINTER(semk_sc_op), C.POINTER(semk_sc_coarse),
                                      C.POINTER(semk_sc_top), C.POINTER(semk_ml_dist), _P, _P, _P,
                                      _P, _P, _P, _P, _P, C.POINTER(semk_ml_opts),

@@ -150,8 +150,24 @@ def coarse_tables_device(l2g_ext, node_ptr, node_pos, dirichlet, gll_nodes):
                 vptr=i32(vptr), vpos=i32(vpos))
 
 
+def _load_key(f):
+    """Identity of a load ``f`` for the cached interior solution A_ii^-1 f_i (None: not
+    cacheable)."""
+    if isinstance(f, torch.Tensor):
+        return ("tensor", f.data_ptr(), f._version, tuple(f.shape))
+    if f is None or np.ndim(f) == 0:
+        return ("scalar", None if f is None else float(f))
+    return None
+
+
 class CondensedPoissonOperator(object):
-    def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, weight=None):
+    def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, weight=None,
+                 store_interior="auto"):
+        """store_interior : keep W_e = A_ii^-1 A_ie of every element (12.5 KB per element at
+        p = 8) so that the interior back-substitution is one streaming pass instead of a
+        refactorisation per element; "auto" = when it takes less than a third of the free
+        device memory."""
+        self._store_interior = store_interior
         self._init_common(dof_mngr, dirichlet)
         self._init_geometry(geometric_factors, weight)
         self._schur_pass()
@@ -293,9 +309,20 @@ class CondensedPoissonOperator(object):
         self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
 
     def _schur_pass(self):
-        """Local Schur complements (packed, kept) and the assembled diagonal."""
+        """Local Schur complements (packed, kept), the assembled diagonal and -- memory
+        permitting -- the interior solution operators W_e."""
         sdiag = torch.empty((self.n_elem, self.n_ext_loc), dtype=torch.float64, device=self.dev)
-        self._element_pass(_lib.SC_SCHUR, S=self.S, sdiag_loc=sdiag)
+        self._W = self._c = self._c_key = None
+        mode = _lib.SC_SCHUR
+        want = getattr(self, "_store_interior", False)
+        nbytes = 8 * self.n_elem * self.n_ext_loc * self.n_int_loc
+        if want == "auto":
+            want = 3 * nbytes < torch.cuda.mem_get_info(self.dev)[0]
+        if want and not isinstance(self, CondensedLocalSystems):
+            self._W = torch.empty((self.n_elem, self.n_ext_loc, self.n_int_loc),
+                                  dtype=torch.float64, device=self.dev)
+            mode |= _lib.SC_STORE
+        self._element_pass(mode, S=self.S, sdiag_loc=sdiag, W=self._W)
         self._diag_unmasked = self.assemble(sdiag)
         del sdiag
         self._dinv = None
@@ -307,7 +334,8 @@ class CondensedPoissonOperator(object):
             raise ValueError("%s must be a contiguous float64 CUDA tensor of length n_nodes" % name)
         return v
 
-    def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=1.0):
+    def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=1.0, W=None,
+                      c=None):
         """One launch of sc_element_kernel (csrc/semk_sc.cu)."""
         f_nodal, f_scale = None, 1.0
         if isinstance(f, torch.Tensor):
@@ -322,7 +350,8 @@ class CondensedPoissonOperator(object):
             device.ptr(self.tab.dev()[0]), device.ptr(self._t["ext_loc"]),
             device.ptr(self.l2g_dev), device.ptr(self.JxW), device.ptr(f_nodal), f_scale,
             int(mode), device.ptr(S), self.s_stride, device.ptr(sdiag_loc), device.ptr(g_loc),
-            device.ptr(u), device.ptr(self._bad), device.stream_ptr()))
+            device.ptr(u), device.ptr(W), device.ptr(c), device.ptr(self._bad),
+            device.stream_ptr()))
         if int(self._bad.item()) != 0:
             raise AssertionError("an element-interior stiffness block is not positive definite")
 
@@ -393,7 +422,14 @@ class CondensedPoissonOperator(object):
         """Condensed load vector: assembled ``f_e - A_ei A_ii^-1 f_i`` with the
         element load ``JxW . f`` (examples/poisson.py:200; scalar or nodal f)."""
         g_loc = torch.empty((self.n_elem, self.n_ext_loc), dtype=torch.float64, device=self.dev)
-        self._element_pass(_lib.SC_RHS, g_loc=g_loc, f=f)
+        c, key = None, _load_key(f)
+        if getattr(self, "_W", None) is not None and key is not None:
+            # the interior solution of this load rides along: back-substitution of the same
+            # load later is a stream over W (backsolve)
+            c = torch.empty((self.n_elem, self.n_int_loc), dtype=torch.float64, device=self.dev)
+        self._element_pass(_lib.SC_RHS, g_loc=g_loc, f=f, c=c)
+        if c is not None:
+            self._c, self._c_key = c, key
         return self.assemble(g_loc)
 
     def lift(self, b, dirichlet_values=None):
@@ -644,6 +680,13 @@ class CondensedPoissonOperator(object):
         u = (torch.empty(self.n_nodes, dtype=torch.float64, device=self.dev) if out is None
              else self._full_vec(out, "out"))
         u[:self.n_ext].copy_(x_ext)
+        if (getattr(self, "_W", None) is not None and self._c is not None
+                and self._c_key == _load_key(f)):
+            _lib.check(self._lib.semk_sc_backsolve_stored_f64(
+                self.n1, self.n_elem, device.ptr(self._W), device.ptr(self._c),
+                device.ptr(self.l2g_dev), device.ptr(self._t["ext_loc"]), device.ptr(u),
+                device.stream_ptr()))
+            return u
         self._element_pass(_lib.SC_BACKSOLVE, u=u, f=f)
         return u
 
@@ -688,7 +731,8 @@ class CondensedLocalSystems(CondensedPoissonOperator):
         self._l2g_hier = device.as_i32_bits(np.ascontiguousarray(l2g[:, hier]), self.dev)
         self._schur_pass()
 
-    def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=None):
+    def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=None, W=None,
+                      c=None):
         self._bad.zero_()
         _lib.check(self._lib.semk_sc_element_dense_f64(
             self.n1, self.n_elem, device.ptr(self._A), device.ptr(self._f),

@@ -64,7 +64,8 @@ enum {
   OP_RR2 = 6,            // inner level: buf ends with { r.r, r.(dinv r) }
   OP_RR2_FIRST = 7,
   OP_BETA_TOP = 8,       // inner level: r.z = r.(dinv r) + y3.r3, then beta
-  OP_BETA_TOP_FIRST = 9
+  OP_BETA_TOP_FIRST = 9,
+  OP_RR2_KEEP = 10       // as OP_RR2 for an initial residual: b.b and the count are kept
 };
 
 struct CommDev {
@@ -185,13 +186,14 @@ __global__ void __launch_bounds__(kStepThreads)
       break;
     }
     case OP_RR2:
-    case OP_RR2_FIRST: {
+    case OP_RR2_FIRST:
+    case OP_RR2_KEEP: {
       const double rr = buf[n - 2];
       s[S_RR] = rr;
       s[S_RZN] = buf[n - 1];
       if (op == OP_RR2_FIRST)
         s[S_BB] = rr;
-      else
+      else if (op == OP_RR2)
         s[S_ITER] += 1.0;
       if (rr <= s[S_TOL2] * s[S_BB]) s[S_CONV] = 1.0;
       break;
@@ -895,6 +897,129 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
     semk_set_error(h[S_BREAK] == 2.0
                        ? "semk_sc_mlpcg_solve_f64: a rank did not arrive at an all-reduce"
                        : "semk_sc_mlpcg_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
+    return h[S_BREAK] == 2.0 ? SEMK_ERR_CUDA : SEMK_ERR_BREAKDOWN;
+  }
+  return SEMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Jacobi-PCG on a strip partition, native: the loop of semk_pcg_solve_f64 with the
+// interface exchange after every apply and the two dot-product reductions of an iteration
+// carried by peer-memory all-reduce kernels -- no NCCL call and no host code between the
+// kernels; the host polls 128 bytes every check_every iterations.
+// ---------------------------------------------------------------------------------------
+extern "C" int semk_pcg_dist_solve_f64(const semk_op *op, const semk_sc_op *sc_op, semk_halo *halo,
+                                       const semk_comm *comm, int64_t n_owned, const double *b,
+                                       double *x, const double *dinv, double *work, double *sc,
+                                       double *vec_partials, double rtol, int maxiter,
+                                       int check_every, semk_pcg_info *info, void *stream) {
+  SEMK_REQUIRE((op != nullptr) != (sc_op != nullptr),
+               "semk_pcg_dist_solve_f64: exactly one of op / sc_op must be given");
+  SEMK_REQUIRE(b && x && dinv && work && sc && vec_partials && info,
+               "semk_pcg_dist_solve_f64: null pointer");
+  SEMK_REQUIRE(maxiter >= 0 && check_every >= 1 && rtol >= 0.0,
+               "semk_pcg_dist_solve_f64: bad control");
+  int rcode = check_comm(comm, "semk_pcg_dist_solve_f64");
+  if (rcode != SEMK_OK) return rcode;
+  const bool multi = comm && comm->world > 1;
+  if (multi) SEMK_REQUIRE(halo, "semk_pcg_dist_solve_f64: partition without a halo");
+  cudaStream_t st = semk_stream(stream);
+  const int64_t n = op ? op->n_nodes : sc_op->n_ext;
+  const uint8_t *dirichlet = op ? op->dirichlet : sc_op->dirichlet;
+  const int64_t n_dot = multi ? n_owned : n;
+  SEMK_REQUIRE(n_dot >= 0 && n_dot <= n, "semk_pcg_dist_solve_f64: bad owned prefix");
+  const int64_t n_pad = (n + 31) & ~(int64_t)31;
+  double *r = work, *p = work + n_pad, *Ap = work + 2 * n_pad;
+  double *s0 = sc, *pair = sc + S_LEN;       // scalar block; {r.r, r.(dinv r)} / {r.r, b.b}
+  const int flags = SEMK_MASK_IN | SEMK_MASK_OUT | SEMK_DIRICHLET_IDENTITY;
+  const CommDev cd = make_comm(multi ? comm : nullptr);
+  const dim3 g(blocks_for(n)), blk(kT);
+  double *h = nullptr;
+  SEMK_CUDA_CHECK(cudaMallocHost(&h, 2 * S_LEN * sizeof(double)));
+  struct Unpin {
+    double *host;
+    ~Unpin() { cudaFreeHost(host); }
+  } unpin{h};
+  auto fetch = [&]() -> int {
+    SEMK_CUDA_CHECK(cudaMemcpyAsync(h, sc, 2 * S_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SEMK_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SEMK_OK;
+  };
+  auto step = [&](double *buf, int nred, int opcode) -> int {
+    ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, buf, nred, opcode, 0, s0, nullptr, nullptr, 0);
+    SEMK_LAUNCH_CHECK("ml_step_kernel");
+    return SEMK_OK;
+  };
+  auto apply = [&](const double *in, double *out, double *dot) -> int {
+    int e = op ? semk_poisson_apply_f64(op, in, out, flags, dot, st)
+               : semk_sc_apply_f64(sc_op, in, out, flags, dot, st);
+    if (e != SEMK_OK || !multi) return e;
+    halo->epoch += 1;
+    return semk_halo_exchange_f64(halo->n_col, n, out, in, dirichlet, halo->mine, halo->left,
+                                  halo->right, halo->epoch, dot, halo->status, st);
+  };
+  auto update = [&](int first) -> int {
+    ml_inner_update_kernel<<<g, blk, 0, st>>>(n, n_dot, first, p, Ap, dinv, x, r, s0, pair,
+                                              vec_partials);
+    SEMK_LAUNCH_CHECK("ml_inner_update_kernel");
+    return SEMK_OK;
+  };
+  auto direction = [&]() -> int {
+    ml_inner_direction_kernel<<<g, blk, 0, st>>>(n, dinv, r, nullptr, nullptr, p, s0);
+    SEMK_LAUNCH_CHECK("ml_inner_direction_kernel");
+    return SEMK_OK;
+  };
+
+  SEMK_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(double) * 2 * S_LEN, st));
+  SEMK_CUDA_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
+  if ((rcode = apply(x, Ap, nullptr)) != SEMK_OK) return rcode;
+  ml_resid_kernel<<<g, blk, 0, st>>>(n, b, Ap, dirichlet, r, n_dot, pair, vec_partials);
+  SEMK_LAUNCH_CHECK("ml_resid_kernel");
+  if (multi && (rcode = semk_comm_allreduce_f64(comm, pair, 2, st)) != SEMK_OK) return rcode;
+  if ((rcode = fetch()) != SEMK_OK) return rcode;
+  const double rr0 = h[S_LEN], bb = h[S_LEN + 1], tol2 = rtol * rtol;
+  info->bnorm = sqrt(bb);
+  info->iterations = 0;
+  info->status = 0;
+  info->rel_residual = bb > 0.0 ? sqrt(rr0 / bb) : 0.0;
+  if (bb == 0.0 || rr0 <= tol2 * bb) return SEMK_OK;
+  h[0] = bb;
+  h[1] = tol2;
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(s0 + S_BB, h, sizeof(double), cudaMemcpyHostToDevice, st));
+  SEMK_CUDA_CHECK(cudaMemcpyAsync(s0 + S_TOL2, h + 1, sizeof(double), cudaMemcpyHostToDevice, st));
+  if ((rcode = update(1)) != SEMK_OK) return rcode;
+  if ((rcode = step(pair, 2, OP_RR2_KEEP)) != SEMK_OK) return rcode;
+  if ((rcode = step(nullptr, 0, OP_BETA_TOP_FIRST)) != SEMK_OK) return rcode;
+  if ((rcode = direction()) != SEMK_OK) return rcode;
+  int status = 1, launched = 0;
+  while (launched < maxiter) {
+    const int chunk = check_every < maxiter - launched ? check_every : maxiter - launched;
+    for (int k = 0; k < chunk; ++k) {
+      if ((rcode = apply(p, Ap, s0 + S_PAP)) != SEMK_OK) return rcode;
+      if ((rcode = step(s0 + S_PAP, 1, OP_ALPHA)) != SEMK_OK) return rcode;
+      if ((rcode = update(0)) != SEMK_OK) return rcode;
+      if ((rcode = step(pair, 2, OP_RR2)) != SEMK_OK) return rcode;
+      if ((rcode = step(nullptr, 0, OP_BETA_TOP)) != SEMK_OK) return rcode;
+      if ((rcode = direction()) != SEMK_OK) return rcode;
+    }
+    launched += chunk;
+    if ((rcode = fetch()) != SEMK_OK) return rcode;
+    if (h[S_BREAK] != 0.0) {
+      status = SEMK_ERR_BREAKDOWN;
+      break;
+    }
+    if (h[S_CONV] != 0.0) {
+      status = 0;
+      break;
+    }
+  }
+  info->iterations = (int32_t)h[S_ITER];
+  info->status = status;
+  info->rel_residual = sqrt(h[S_RR] / bb);
+  if (status == SEMK_ERR_BREAKDOWN) {
+    semk_set_error(h[S_BREAK] == 2.0
+                       ? "semk_pcg_dist_solve_f64: a rank did not arrive at an all-reduce"
+                       : "semk_pcg_dist_solve_f64: breakdown (p.Ap <= 0 or non-finite)");
     return h[S_BREAK] == 2.0 ? SEMK_ERR_CUDA : SEMK_ERR_BREAKDOWN;
   }
   return SEMK_OK;

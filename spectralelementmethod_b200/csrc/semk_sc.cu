@@ -73,6 +73,8 @@ struct ScElemArgs {
   int32_t *bad_flag;
   // dense mode (semk_sc_element_dense_f64): the caller's own local systems, hierarchical
   // local order (exterior DOFs first), instead of the Poisson recipe on G
+  double *W_out;               // [n_elem][NE][NI] A_ii^{-1} A_ie, transposed (mode STORE), or nullptr
+  double *c_out;               // [n_elem][NI] A_ii^{-1} f_i (with the load), or nullptr
   const double *A_dense;       // [n_elem][NN][NN] or nullptr
   const double *f_dense;       // [n_elem][NN]
   const uint32_t *l2g_hier;    // [n_elem][NN] global ids in hierarchical local order
@@ -266,6 +268,70 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
         const uint32_t *row = a.l2g + e * NN;
         for (int i = tid; i < NI; i += kScThreads) a.u[row[(1 + i / M) * N + 1 + i % M]] = sT[i];
       }
+    }
+    // ---- keep the interior solution operator: W = A_ii^{-1} A_ie = L^{-T} Z and
+    // c = A_ii^{-1} f_i = L^{-T} (L^{-1} f_i), one thread per column, backward substitution
+    // in place; the back-substitution u_i = c - W u_e then is one streaming pass
+    // (sc_backsolve_stored_kernel) instead of a refactorisation per element ---------------
+    const bool store_w = (a.mode & SEMK_SC_STORE) && a.W_out;
+    const bool store_c = need_f && a.c_out;
+    if (store_w || store_c) {
+      __syncthreads();  // every reader of Z is done
+      const bool mine = (store_w && tid < NE) || (store_c && tid == NE);
+      if (mine) {
+        for (int i = NI - 1; i >= 0; --i) {
+          double acc = sZ[i * LDZ + tid];
+          for (int j = i + 1; j < NI; ++j) acc = fma(-sA[j * LDI + i], sZ[j * LDZ + tid], acc);
+          sZ[i * LDZ + tid] = acc * sInv[i];
+        }
+      }
+      __syncthreads();
+      if (store_w) {
+        double *Wo = a.W_out + e * (int64_t)NE * NI;
+        for (int idx = tid; idx < NE * NI; idx += kScThreads) {
+          const int k = idx / NI, i = idx - k * NI;
+          Wo[idx] = sZ[i * LDZ + k];
+        }
+      }
+      if (store_c) {
+        double *co = a.c_out + e * (int64_t)NI;
+        for (int i = tid; i < NI; i += kScThreads) co[i] = sZ[i * LDZ + NE];
+      }
+    }
+  }
+}
+
+// Back-substitution from the stored interior operator: u_i = c - W u_e for every element,
+// one thread per interior row; W is stored transposed ([NE][NI]), so the NI threads of an
+// element read consecutive doubles.  A pure stream over W (12.5 KB per element at p = 8).
+template <int N>
+__global__ void __launch_bounds__(256)
+    sc_backsolve_stored_kernel(int64_t n_elem, const double *__restrict__ W,
+                               const double *__restrict__ c, const uint32_t *__restrict__ l2g,
+                               const int32_t *__restrict__ ext_loc, double *__restrict__ u) {
+  using C = ScCfg<N>;
+  constexpr int NN = C::NN, NE = C::NE, NI = C::NI, M = N - 2;
+  constexpr int GT = ((NI + 31) / 32) * 32;     // threads per element
+  constexpr int GPB = 256 / GT;                 // elements per CTA step
+  __shared__ double sUe[GPB][NE];
+  const int tid = threadIdx.x;
+  const int grp = tid / GT, i = tid - grp * GT;
+  const int64_t n_steps = (n_elem + GPB - 1) / GPB;
+  for (int64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
+    const int64_t e = step * GPB + grp;
+    const bool on = grp < GPB && e < n_elem;
+    __syncthreads();
+    if (on) {
+      const uint32_t *row = l2g + e * NN;
+      for (int k = i; k < NE; k += GT) sUe[grp][k] = u[row[ext_loc[k]]];
+    }
+    __syncthreads();
+    if (on && i < NI) {
+      const double *Wt = W + e * (int64_t)NE * NI + i;
+      double acc = c ? c[e * (int64_t)NI + i] : 0.0;
+#pragma unroll 8
+      for (int k = 0; k < NE; ++k) acc = fma(-__ldcs(Wt + (int64_t)k * NI), sUe[grp][k], acc);
+      u[l2g[e * NN + (1 + i / M) * N + 1 + i % M]] = acc;
     }
   }
 }
@@ -526,11 +592,15 @@ extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_o
                                    const double *D, const int32_t *ext_loc, const uint32_t *l2g,
                                    const double *JxW, const double *f_nodal, double f_scale,
                                    int mode, double *S_out, int64_t s_stride, double *sdiag_loc,
-                                   double *g_loc, double *u, int32_t *bad_flag, void *stream) {
+                                   double *g_loc, double *u, double *W_out, double *c_out,
+                                   int32_t *bad_flag, void *stream) {
   SEMK_REQUIRE(n_elem > 0 && G && D && ext_loc && bad_flag &&
                    elems_per_patch > 0 && g_patch_stride > 0,
                "semk_sc_element_f64: bad argument");
-  SEMK_REQUIRE(mode != 0 && (mode & ~7) == 0, "semk_sc_element_f64: bad mode");
+  SEMK_REQUIRE(mode != 0 && (mode & ~15) == 0, "semk_sc_element_f64: bad mode");
+  SEMK_REQUIRE(!(mode & SEMK_SC_STORE) || W_out, "semk_sc_element_f64: STORE needs W_out");
+  SEMK_REQUIRE(!c_out || (mode & (SEMK_SC_RHS | SEMK_SC_BACKSOLVE)),
+               "semk_sc_element_f64: c_out needs a load (RHS or BACKSOLVE mode)");
   if (n1 < 3 || n1 > 11) {
     semk_set_error("semk_sc_element_f64: static condensation supports orders 2..10");
     return SEMK_ERR_UNSUPPORTED;
@@ -562,6 +632,8 @@ extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_o
   a.g_loc = g_loc;
   a.u = u;
   a.bad_flag = bad_flag;
+  a.W_out = W_out;
+  a.c_out = c_out;
   a.A_dense = nullptr;
   a.f_dense = nullptr;
   a.l2g_hier = nullptr;
@@ -607,6 +679,8 @@ extern "C" int semk_sc_element_dense_f64(int n1, int64_t n_elem, const double *A
   a.g_loc = g_loc;
   a.u = u;
   a.bad_flag = bad_flag;
+  a.W_out = nullptr;
+  a.c_out = nullptr;
   a.A_dense = A_hier;
   a.f_dense = f_hier;
   a.l2g_hier = l2g_hier;
@@ -627,6 +701,24 @@ static int launch_sc_element(int n1, const ScElemArgs &a, void *stream) {
   SEMK_DISPATCH_SC(n1, SEMK_CALL)
 #undef SEMK_CALL
   SEMK_LAUNCH_CHECK("sc_element_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_backsolve_stored_f64(int n1, int64_t n_elem, const double *W,
+                                           const double *c, const uint32_t *l2g,
+                                           const int32_t *ext_loc, double *u, void *stream) {
+  SEMK_REQUIRE(n_elem > 0 && W && l2g && ext_loc && u, "semk_sc_backsolve_stored_f64: bad argument");
+  cudaStream_t st = semk_stream(stream);
+#define SEMK_CALL(NV)                                                                      \
+  do {                                                                                     \
+    constexpr int GT = ((ScCfg<NV>::NI + 31) / 32) * 32, GPB = 256 / GT;                   \
+    const int64_t steps = (n_elem + GPB - 1) / GPB;                                        \
+    const unsigned grid = (unsigned)(steps < 148 * 16 ? steps : 148 * 16);                 \
+    sc_backsolve_stored_kernel<NV><<<grid, 256, 0, st>>>(n_elem, W, c, l2g, ext_loc, u);   \
+  } while (0)
+  SEMK_DISPATCH_SC(n1, SEMK_CALL)
+#undef SEMK_CALL
+  SEMK_LAUNCH_CHECK("sc_backsolve_stored_kernel");
   return SEMK_OK;
 }
 

@@ -564,6 +564,34 @@ def strip_vertex_aggregates(part, vertex_lex_ids, dirichlet_c, max_tiles=4096):
     return agg, int(tx * ty), int(k)
 
 
+def _native_jacobi_pcg(owner, op_struct, sc_struct, halo, n_owned, b, x, dinv, vec_partials, rtol,
+                       maxiter, check_every):
+    """semk_pcg_dist_solve_f64 on a partition whose exchanges run over peer memory: the
+    whole loop (applies, interface exchanges, both all-reduces of an iteration) is issued by
+    the native driver.  ``owner`` keeps the PeerComm."""
+    import ctypes as C
+    from . import _lib, device
+    lib = _lib.load()
+    if getattr(owner, "_comm", None) is None:
+        owner._comm = PeerComm(halo.part.rank, halo.part.world, 64, owner.group, b.device)
+    n = b.numel()
+    work = torch.empty(3 * (n + 32), dtype=torch.float64, device=b.device)
+    sc = torch.zeros(32, dtype=torch.float64, device=b.device)
+    info = _lib.semk_pcg_info()
+    torch.cuda.synchronize(b.device)        # ranks enter together (the peer kernels give up
+    dist.barrier(group=owner.group)         # after ~2 s of waiting)
+    rc = lib.semk_pcg_dist_solve_f64(
+        C.byref(op_struct) if op_struct is not None else None,
+        C.byref(sc_struct) if sc_struct is not None else None,
+        C.byref(halo.c), C.byref(owner._comm.c), int(n_owned), device.ptr(b), device.ptr(x),
+        device.ptr(dinv), device.ptr(work), device.ptr(sc), device.ptr(vec_partials), float(rtol),
+        int(maxiter), int(check_every), C.byref(info), device.stream_ptr())
+    _lib.check(rc)
+    halo.check()
+    owner._comm.check()
+    return info.iterations, info.rel_residual, info.status == 0
+
+
 class DistributedPoisson(object):
     """The whole multi-GPU Poisson path for the strip-partitioned structured
     configurations (BASELINE.json configs[4]): local mesh + DOF manager +
@@ -629,7 +657,10 @@ class DistributedPoisson(object):
         out[self._mask] = gv[self._mask]
         return out
 
-    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25):
+    def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25, native=True):
+        """Jacobi-PCG over all ranks.  With the peer-memory exchange the native driver
+        semk_pcg_dist_solve_f64 runs the whole loop (``native=False``: the host-driven loop
+        with NCCL all-reduces, which is also what the NCCL / gloo paths use)."""
         if x0 is None:
             x = torch.zeros_like(b)
             if self._mask is not None:
@@ -638,9 +669,23 @@ class DistributedPoisson(object):
             x = x0.clone()
         if self._dinv is None:
             self._dinv = 1.0 / self.diagonal()
+        if self.halo is not None and native:
+            it, rel, ok = _native_jacobi_pcg(self, self.op._op, None, self.halo, self.part.n_owned,
+                                             b, x, self._dinv, self.op.vec_partials, rtol,
+                                             maxiter, check_every)
+            return x, it, rel, ok
         it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
                                       maxiter=maxiter, check_every=check_every)
         return x, it, rel, ok
+
+    def close(self):
+        """Collective tear-down of the peer-memory regions."""
+        if getattr(self, "_comm", None) is not None:
+            self._comm.close()
+            self._comm = None
+        if self.halo is not None:
+            self.halo.close()
+            self.halo = None
 
 
 class DistributedCondensedPoisson(object):
@@ -721,9 +766,10 @@ class DistributedCondensedPoisson(object):
 
     def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25,
                   preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000, flexible=True,
-                  inner_chunk=4, max_tiles=4096):
-        """Distributed PCG on the exterior DOFs.  "jacobi": the host-driven loop
-        (distributed_pcg, NCCL all-reduces).  "two-level" / "three-level": the native
+                  inner_chunk=4, max_tiles=4096, native=True):
+        """Distributed PCG on the exterior DOFs.  "jacobi": semk_pcg_dist_solve_f64 with the
+        peer-memory exchange (``native=False`` or NCCL exchange: the host-driven loop
+        distributed_pcg with NCCL all-reduces).  "two-level" / "three-level": the native
         multilevel driver (semk_sc_mlpcg_solve_f64) -- every exchange and all-reduce is a
         peer-memory kernel issued by the driver itself, so it needs exchange="peer".
         Returns (x, iterations, rel_residual, converged); ``last_info`` keeps the PCGInfo
@@ -754,6 +800,11 @@ class DistributedCondensedPoisson(object):
             self.last_info = info
             self.last_inner_iterations = info.inner_iterations
             return xs, info.iterations, info.rel_residual, info.converged
+        if self.halo is not None and native:
+            it, rel, ok = _native_jacobi_pcg(self, None, self.sc._op, self.halo, self.view.n_owned,
+                                             b, x, self._dinv, self.sc.vec_partials, rtol, maxiter,
+                                             check_every)
+            return x, it, rel, ok
         it, rel, ok = distributed_pcg(self.dop, b, x, self._dinv, self.kernels, rtol=rtol,
                                       maxiter=maxiter, check_every=check_every)
         return x, it, rel, ok
@@ -816,6 +867,9 @@ class DistributedCondensedPoisson(object):
             if tl["comm"] is not None:
                 tl["comm"].close()
             self._ml = None
+        if getattr(self, "_comm", None) is not None:
+            self._comm.close()
+            self._comm = None
         if self.halo is not None:
             self.halo.close()
             self.halo = None

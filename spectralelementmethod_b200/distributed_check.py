@@ -55,7 +55,7 @@ def run(rank, world, dev, nxl=24, ny=20, p=8, kind="C"):
         results[exchange] = check_one(dp, gop, gid, ug, want, dot_ref, bg, xg, dev)
         if dp.halo is not None:
             dp.halo.check()
-            dp.halo.close()
+        dp.close()
     # the two exchange paths add the same two numbers: bit-identical results
     assert torch.equal(results["peer"][0], results["nccl"][0])
     # the peer-memory all-reduce against NCCL: same sums, bit-identical on every rank
@@ -137,5 +137,11 @@ def check_one(dp, gop, gid, ug, want, dot_ref, bg, xg, dev):
     x, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, check_every=10)
     serr = float((x - xg[gid]).norm() / xg.norm())
     assert ok and serr < 1e-9, (ok, serr)
+    if dp.halo is not None:
+        # the native driver (peer all-reduces) took the solve above; the host-driven loop
+        # with NCCL all-reduces must agree (same recurrence, reductions in another order)
+        xh, ith, relh, okh = dp.solve_pcg(b, rtol=1e-12, check_every=10, native=False)
+        assert okh and abs(ith - it) <= 3, (ith, it)
+        assert float((xh - x).norm() / x.norm()) < 1e-9
     return y, err, it, serr
 

@@ -217,3 +217,29 @@ def test_device_built_integer_tables_equal_the_host_builders(name):
     assert np.array_equal(host(t["pw"]), ct["pw"]) and np.array_equal(host(t["rw"]), ct["rw"])
     assert np.array_equal(host(t["phi"]), ct["phi"])
     assert np.array_equal(t["dirichlet_c_host"], ct["dirichlet_c"])
+
+
+@pytest.mark.parametrize("name", SC_CASES[:3])
+def test_stored_interior_operator_backsolve_equals_the_refactorising_one(name):
+    """W_e = A_ii^-1 A_ie kept by the Schur pass + the interior solution of the load kept by
+    rhs(): the streaming back-substitution gives the refactorising kernel's result, for a
+    scalar and for a nodal load, and falls back when the load differs."""
+    g = load_case(name)
+    mesh, mngr = build_package_case(g["kind"], g["nx"], g["ny"], g["p"], g["sc"], g["rcm"])
+    stored = mngr.condensed_poisson_operator(dirichlet=g["on_ebc"], store_interior=True)
+    plain = mngr.condensed_poisson_operator(dirichlet=g["on_ebc"], store_interior=False)
+    assert stored._W is not None and plain._W is None
+    rng = np.random.default_rng(2)
+    fn = dev(rng.standard_normal(stored.n_nodes))
+    for f in (1.0, fn):
+        b = stored.lift(stored.rhs(f), g["ebc_vals"])
+        assert stored._c is not None
+        x, info = stored.solve_pcg(b, rtol=1e-13)
+        fast = stored.backsolve(x, f)
+        slow = plain.backsolve(x, f)
+        assert rel_l2(host(fast), host(slow)) < 1e-12
+    # a different load than the cached one: the refactorising path is taken, same answer
+    other = stored.backsolve(x, 2.0)
+    assert rel_l2(host(other), host(plain.backsolve(x, 2.0))) < 1e-13
+    u, info = stored.solve(1.0, g["ebc_vals"], rtol=1e-13)
+    assert rel_l2(host(u), g["solution"]) < TOL
