@@ -65,7 +65,11 @@ enum {
   OP_RR2_FIRST = 7,
   OP_BETA_TOP = 8,       // inner level: r.z = r.(dinv r) + y3.r3, then beta
   OP_BETA_TOP_FIRST = 9,
-  OP_RR2_KEEP = 10       // as OP_RR2 for an initial residual: b.b and the count are kept
+  OP_RR2_KEEP = 10,      // as OP_RR2 for an initial residual: b.b and the count are kept
+  // no aggregation level between the two: OP_RR2* immediately followed by OP_BETA_TOP*
+  OP_RR2_BETA = 11,
+  OP_RR2_BETA_FIRST = 12,
+  OP_RR2_BETA_KEEP = 13
 };
 
 struct CommDev {
@@ -162,6 +166,9 @@ __global__ void __launch_bounds__(kStepThreads)
     s[S_BREAK] = 2.0;
     return;
   }
+  // converged in the previous iteration: its direction kernel has applied the last x
+  // update, from now on everything is frozen (inner / partitioned Jacobi loops)
+  if (op == OP_ALPHA && s[S_CONV] == 1.0) s[S_CONV] = 2.0;
   if (s[S_CONV] != 0.0 || s[S_BREAK] != 0.0) return;   // frozen
   switch (op) {
     case OP_ALPHA: {
@@ -187,15 +194,25 @@ __global__ void __launch_bounds__(kStepThreads)
     }
     case OP_RR2:
     case OP_RR2_FIRST:
-    case OP_RR2_KEEP: {
+    case OP_RR2_KEEP:
+    case OP_RR2_BETA:
+    case OP_RR2_BETA_FIRST:
+    case OP_RR2_BETA_KEEP: {
       const double rr = buf[n - 2];
+      const double rzn = buf[n - 1];
       s[S_RR] = rr;
-      s[S_RZN] = buf[n - 1];
-      if (op == OP_RR2_FIRST)
+      s[S_RZN] = rzn;
+      if (op == OP_RR2_FIRST || op == OP_RR2_BETA_FIRST)
         s[S_BB] = rr;
-      else if (op == OP_RR2)
+      else if (op == OP_RR2 || op == OP_RR2_BETA)
         s[S_ITER] += 1.0;
-      if (rr <= s[S_TOL2] * s[S_BB]) s[S_CONV] = 1.0;
+      if (rr <= s[S_TOL2] * s[S_BB]) {
+        s[S_CONV] = 1.0;
+      } else if (op >= OP_RR2_BETA) {
+        const double rz = s[S_RZ];
+        s[S_BETA] = (op != OP_RR2_BETA || rz == 0.0) ? 0.0 : rzn / rz;
+        s[S_RZ] = rzn;
+      }
       break;
     }
     case OP_BETA_TOP:
@@ -297,21 +314,24 @@ __global__ void __launch_bounds__(kT)
 }
 
 // ---- inner (vertex) level: the preconditioned residual z = dinv r + P2 y3 is never stored ----
-// x += alpha p ; r -= alpha Ap (unless first / frozen) ; out2 = { r.r, r.(dinv r) } (owned)
+// r -= alpha Ap (unless first / frozen) ; out2 = { r.r, r.(dinv r) } (owned).  x += alpha p
+// rides with the direction update below (that kernel reads p anyway): 4 + 6 vector passes.
+// VEC: every pointer is 16-byte aligned -> 128-bit accesses, two pairs in flight per thread
+// (these are pure HBM streams on the fine level of the partitioned Jacobi-PCG).
+template <bool VEC>
 __global__ void __launch_bounds__(kT)
-    ml_inner_update_kernel(int64_t n, int64_t n_dot, int first, const double *__restrict__ p,
-                           const double *__restrict__ Ap, const double *__restrict__ dinv,
-                           double *__restrict__ x, double *__restrict__ r,
+    ml_inner_update_kernel(int64_t n, int64_t n_dot, int first, const double *__restrict__ Ap,
+                           const double *__restrict__ dinv, double *__restrict__ r,
                            const double *__restrict__ s, double *__restrict__ out2,
                            double *__restrict__ partials) {
   const bool move = !first && s[S_CONV] == 0.0 && s[S_BREAK] == 0.0;
   const double alpha = s[S_ALPHA];
   double acc[2] = {0.0, 0.0};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  auto one = [&](int64_t i) {
     double ri = r[i];
     if (move) {
-      x[i] = fma(alpha, p[i], x[i]);
       ri = fma(-alpha, Ap[i], ri);
       r[i] = ri;
     }
@@ -319,6 +339,45 @@ __global__ void __launch_bounds__(kT)
       acc[0] = fma(ri, ri, acc[0]);
       acc[1] = fma(ri * dinv[i], ri, acc[1]);
     }
+  };
+  if (VEC) {
+    const int64_t npair = n >> 1;
+    const double2 *Ap2 = reinterpret_cast<const double2 *>(Ap);
+    const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int64_t j0 = tid; j0 < npair; j0 += 2 * nthreads) {
+      const int64_t jj[2] = {j0, j0 + nthreads};
+      const bool on[2] = {true, jj[1] < npair};
+      double2 av[2], rv[2], dv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        rv[q] = on[q] ? r2[jj[q]] : zero2;
+        dv[q] = on[q] ? d2[jj[q]] : zero2;
+        av[q] = (on[q] && move) ? Ap2[jj[q]] : zero2;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!on[q]) continue;
+        double2 ro = rv[q];
+        if (move) {
+          ro.x = fma(-alpha, av[q].x, rv[q].x);
+          ro.y = fma(-alpha, av[q].y, rv[q].y);
+          r2[jj[q]] = ro;
+        }
+        if (2 * jj[q] < n_dot) {
+          acc[0] = fma(ro.x, ro.x, acc[0]);
+          acc[1] = fma(ro.x * dv[q].x, ro.x, acc[1]);
+        }
+        if (2 * jj[q] + 1 < n_dot) {
+          acc[0] = fma(ro.y, ro.y, acc[0]);
+          acc[1] = fma(ro.y * dv[q].y, ro.y, acc[1]);
+        }
+      }
+    }
+    if ((n & 1) && tid == 0) one(n - 1);
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) one(i);
   }
   double tot[2];
   if (semk_finish_reduction<2>(acc, partials, tot) && threadIdx.x == 0) {
@@ -327,23 +386,80 @@ __global__ void __launch_bounds__(kT)
   }
 }
 
-// p = dinv r + y3[agg] + beta p  (frozen: nothing; agg == NULL: no aggregation level)
+// x += alpha p_old (unless first) ; p = dinv r + y3[agg] + beta p  (agg == NULL: no
+// aggregation level).  On the iteration that converged (S_CONV == 1, set by the step kernel
+// in between) only the x update is done -- x then is the converged iterate; the next ALPHA
+// step moves the state on to 2 = frozen, and this kernel does nothing any more.
+template <bool VEC>
 __global__ void __launch_bounds__(kT)
-    ml_inner_direction_kernel(int64_t n, const double *__restrict__ dinv,
+    ml_inner_direction_kernel(int64_t n, int first, const double *__restrict__ dinv,
                               const double *__restrict__ r, const uint32_t *__restrict__ agg,
                               const double *__restrict__ y3, double *__restrict__ p,
-                              const double *__restrict__ s) {
-  if (s[S_CONV] != 0.0 || s[S_BREAK] != 0.0) return;
-  const double beta = s[S_BETA];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    double z = dinv[i] * r[i];
-    if (agg) {
-      const uint32_t a = agg[i];
-      if (a != 0xffffffffu) z += y3[a];
+                              double *__restrict__ x, const double *__restrict__ s) {
+  const double state = s[S_CONV];
+  if (s[S_BREAK] != 0.0 || state == 2.0) return;
+  const bool move_p = state == 0.0;
+  const bool move_x = !first;
+  const double beta = s[S_BETA], alpha = s[S_ALPHA];
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  auto top = [&](int64_t i) -> double {
+    if (!agg) return 0.0;
+    const uint32_t a = agg[i];
+    return a != 0xffffffffu ? y3[a] : 0.0;
+  };
+  auto one = [&](int64_t i) {
+    const double pi = p[i];
+    if (move_x) x[i] = fma(alpha, pi, x[i]);
+    if (move_p) p[i] = fma(beta, pi, fma(dinv[i], r[i], top(i)));
+  };
+  if (VEC) {
+    const int64_t npair = n >> 1;
+    const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
+    const double2 *r2 = reinterpret_cast<const double2 *>(r);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    double2 *x2 = reinterpret_cast<double2 *>(x);
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int64_t j0 = tid; j0 < npair; j0 += 2 * nthreads) {
+      const int64_t jj[2] = {j0, j0 + nthreads};
+      const bool on[2] = {true, jj[1] < npair};
+      double2 dv[2], rv[2], pv[2], xv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        pv[q] = on[q] ? p2[jj[q]] : zero2;
+        dv[q] = (on[q] && move_p) ? d2[jj[q]] : zero2;
+        rv[q] = (on[q] && move_p) ? r2[jj[q]] : zero2;
+        xv[q] = (on[q] && move_x) ? x2[jj[q]] : zero2;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!on[q]) continue;
+        if (move_x) {
+          double2 xo;
+          xo.x = fma(alpha, pv[q].x, xv[q].x);
+          xo.y = fma(alpha, pv[q].y, xv[q].y);
+          x2[jj[q]] = xo;
+        }
+        if (move_p) {
+          double2 o;
+          o.x = fma(beta, pv[q].x, fma(dv[q].x, rv[q].x, top(2 * jj[q])));
+          o.y = fma(beta, pv[q].y, fma(dv[q].y, rv[q].y, top(2 * jj[q] + 1)));
+          p2[jj[q]] = o;
+        }
+      }
     }
-    p[i] = fma(beta, p[i], z);
+    if ((n & 1) && tid == 0) one(n - 1);
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) one(i);
   }
+}
+
+inline bool ml_aligned16(const void *a, const void *b, const void *c, const void *d,
+                         const void *e) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+           reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(d) |
+           reinterpret_cast<uintptr_t>(e)) &
+          15u) == 0;
 }
 
 // y = Ac x with Ac in ELL format (column major: entry k of row v at [k * n + v]) ;
@@ -758,27 +874,37 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
       if ((e = coarse_apply(pi, Api, si + S_PAP)) != SEMK_OK) return e;
       if ((e = step(si + S_PAP, 1, OP_ALPHA, si)) != SEMK_OK) return e;
     }
-    ml_inner_update_kernel<<<gc, blk, 0, st>>>(nv, nv_dot, first ? 1 : 0, pi, Api, dinv_c, xc, rc,
-                                               si, r3 + na, vec_partials);
+    if (ml_aligned16(pi, Api, dinv_c, xc, rc))
+      ml_inner_update_kernel<true><<<gc, blk, 0, st>>>(nv, nv_dot, first ? 1 : 0, Api, dinv_c, rc,
+                                                       si, r3 + na, vec_partials);
+    else
+      ml_inner_update_kernel<false><<<gc, blk, 0, st>>>(nv, nv_dot, first ? 1 : 0, Api, dinv_c, rc,
+                                                        si, r3 + na, vec_partials);
     SEMK_LAUNCH_CHECK("ml_inner_update_kernel");
     if (three) {
       ml_agg_restrict_kernel<<<ga, blk, 0, st>>>(na, top->aptr, top->aidx, rc, r3);
       SEMK_LAUNCH_CHECK("ml_agg_restrict_kernel");
     }
-    if ((e = step(r3, (int)na + 2, first ? OP_RR2_FIRST : OP_RR2, si)) != SEMK_OK) return e;
     if (three) {
+      if ((e = step(r3, (int)na + 2, first ? OP_RR2_FIRST : OP_RR2, si)) != SEMK_OK) return e;
       if (top->A3inv_f32)
         ml_dense_matvec_f32_kernel<<<ga, blk, 0, st>>>(na, top->A3inv_f32, r3, y3);
       else
         ml_dense_matvec_kernel<<<ga, blk, 0, st>>>(na, top->A3inv, r3, y3);
       SEMK_LAUNCH_CHECK("ml_dense_matvec_kernel");
+      ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, nullptr, 0,
+                                                 first ? OP_BETA_TOP_FIRST : OP_BETA_TOP, 0, si,
+                                                 y3, r3, (int)na);
+      SEMK_LAUNCH_CHECK("ml_step_kernel");
+    } else {
+      if ((e = step(r3, 2, first ? OP_RR2_BETA_FIRST : OP_RR2_BETA, si)) != SEMK_OK) return e;
     }
-    ml_step_kernel<<<1, kStepThreads, 0, st>>>(cd, nullptr, 0,
-                                               first ? OP_BETA_TOP_FIRST : OP_BETA_TOP, 0, si, y3,
-                                               r3, (int)na);
-    SEMK_LAUNCH_CHECK("ml_step_kernel");
-    ml_inner_direction_kernel<<<gc, blk, 0, st>>>(nv, dinv_c, rc, three ? top->agg : nullptr, y3,
-                                                  pi, si);
+    if (ml_aligned16(dinv_c, rc, pi, xc, pi))
+      ml_inner_direction_kernel<true><<<gc, blk, 0, st>>>(
+          nv, first ? 1 : 0, dinv_c, rc, three ? top->agg : nullptr, y3, pi, xc, si);
+    else
+      ml_inner_direction_kernel<false><<<gc, blk, 0, st>>>(
+          nv, first ? 1 : 0, dinv_c, rc, three ? top->agg : nullptr, y3, pi, xc, si);
     SEMK_LAUNCH_CHECK("ml_inner_direction_kernel");
     return SEMK_OK;
   };
@@ -959,13 +1085,22 @@ extern "C" int semk_pcg_dist_solve_f64(const semk_op *op, const semk_sc_op *sc_o
                                   halo->right, halo->epoch, dot, halo->status, st);
   };
   auto update = [&](int first) -> int {
-    ml_inner_update_kernel<<<g, blk, 0, st>>>(n, n_dot, first, p, Ap, dinv, x, r, s0, pair,
-                                              vec_partials);
+    if (ml_aligned16(p, Ap, dinv, x, r))
+      ml_inner_update_kernel<true><<<g, blk, 0, st>>>(n, n_dot, first, Ap, dinv, r, s0, pair,
+                                                      vec_partials);
+    else
+      ml_inner_update_kernel<false><<<g, blk, 0, st>>>(n, n_dot, first, Ap, dinv, r, s0, pair,
+                                                       vec_partials);
     SEMK_LAUNCH_CHECK("ml_inner_update_kernel");
     return SEMK_OK;
   };
-  auto direction = [&]() -> int {
-    ml_inner_direction_kernel<<<g, blk, 0, st>>>(n, dinv, r, nullptr, nullptr, p, s0);
+  auto direction = [&](int first) -> int {
+    if (ml_aligned16(dinv, r, p, x, p))
+      ml_inner_direction_kernel<true><<<g, blk, 0, st>>>(n, first, dinv, r, nullptr, nullptr, p, x,
+                                                         s0);
+    else
+      ml_inner_direction_kernel<false><<<g, blk, 0, st>>>(n, first, dinv, r, nullptr, nullptr, p,
+                                                          x, s0);
     SEMK_LAUNCH_CHECK("ml_inner_direction_kernel");
     return SEMK_OK;
   };
@@ -988,9 +1123,8 @@ extern "C" int semk_pcg_dist_solve_f64(const semk_op *op, const semk_sc_op *sc_o
   SEMK_CUDA_CHECK(cudaMemcpyAsync(s0 + S_BB, h, sizeof(double), cudaMemcpyHostToDevice, st));
   SEMK_CUDA_CHECK(cudaMemcpyAsync(s0 + S_TOL2, h + 1, sizeof(double), cudaMemcpyHostToDevice, st));
   if ((rcode = update(1)) != SEMK_OK) return rcode;
-  if ((rcode = step(pair, 2, OP_RR2_KEEP)) != SEMK_OK) return rcode;
-  if ((rcode = step(nullptr, 0, OP_BETA_TOP_FIRST)) != SEMK_OK) return rcode;
-  if ((rcode = direction()) != SEMK_OK) return rcode;
+  if ((rcode = step(pair, 2, OP_RR2_BETA_KEEP)) != SEMK_OK) return rcode;
+  if ((rcode = direction(1)) != SEMK_OK) return rcode;
   int status = 1, launched = 0;
   while (launched < maxiter) {
     const int chunk = check_every < maxiter - launched ? check_every : maxiter - launched;
@@ -998,9 +1132,8 @@ extern "C" int semk_pcg_dist_solve_f64(const semk_op *op, const semk_sc_op *sc_o
       if ((rcode = apply(p, Ap, s0 + S_PAP)) != SEMK_OK) return rcode;
       if ((rcode = step(s0 + S_PAP, 1, OP_ALPHA)) != SEMK_OK) return rcode;
       if ((rcode = update(0)) != SEMK_OK) return rcode;
-      if ((rcode = step(pair, 2, OP_RR2)) != SEMK_OK) return rcode;
-      if ((rcode = step(nullptr, 0, OP_BETA_TOP)) != SEMK_OK) return rcode;
-      if ((rcode = direction()) != SEMK_OK) return rcode;
+      if ((rcode = step(pair, 2, OP_RR2_BETA)) != SEMK_OK) return rcode;
+      if ((rcode = direction(0)) != SEMK_OK) return rcode;
     }
     launched += chunk;
     if ((rcode = fetch()) != SEMK_OK) return rcode;

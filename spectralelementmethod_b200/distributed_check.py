@@ -85,10 +85,17 @@ def run(rank, world, dev, nxl=24, ny=20, p=8, kind="C"):
     for exchange in ("peer", "nccl"):
         dc = DistributedCondensedPoisson(part, p, kind, exchange=exchange)
         cg = torch.from_numpy(dc.global_ids()).to(dev)
-        xs, it_sc, rel_sc, ok_sc = dc.solve(1.0, None, rtol=1e-12, check_every=10)
+        # host-driven loop on both exchanges: the two exchanges add the same two numbers, so
+        # the iterates are bit-identical
+        xs, it_sc, rel_sc, ok_sc = dc.solve(1.0, None, rtol=1e-12, check_every=10, native=False)
         serr_sc = float((xs - xg[cg]).norm() / xg.norm())
         assert ok_sc and serr_sc < 1e-9, (ok_sc, serr_sc)
         sc_res[exchange] = (xs, it_sc, serr_sc)
+        if exchange == "peer":
+            # the native driver (peer all-reduces): same recurrence, same solution
+            xn, it_n, rel_n, ok_n = dc.solve(1.0, None, rtol=1e-12, check_every=10)
+            assert ok_n and it_sc - 10 <= it_n <= it_sc + 3, (it_n, it_sc)   # (the host loop counts to its next poll)
+            assert float((xn - xs).norm() / xs.norm()) < 1e-9
         if exchange == "peer":
             # native multilevel driver on the partition (semk_sc_mlpcg_solve_f64): halo
             # exchanges and all-reduces are peer-memory kernels issued by the driver
@@ -141,7 +148,7 @@ def check_one(dp, gop, gid, ug, want, dot_ref, bg, xg, dev):
         # the native driver (peer all-reduces) took the solve above; the host-driven loop
         # with NCCL all-reduces must agree (same recurrence, reductions in another order)
         xh, ith, relh, okh = dp.solve_pcg(b, rtol=1e-12, check_every=10, native=False)
-        assert okh and abs(ith - it) <= 3, (ith, it)
+        assert okh and ith - 10 <= it <= ith + 3, (ith, it)   # (the host loop counts to its next poll)
         assert float((xh - x).norm() / x.norm()) < 1e-9
     return y, err, it, serr
 
