@@ -523,3 +523,173 @@ def c_set_threads(n=None):
         return 1
     lib.sem_oracle_c_set_threads(int(n or os.cpu_count() or 1))
     return c_threads()
+
+
+# --------------------------------------------------------------------------
+# Axisymmetric Stokes / Navier-Stokes in stream function - vorticity form
+# (examples/squirmer-axisymmetric.py).  Two DOFs per node,
+# DOF id = 2*node + comp (sem/discrete.py:561-576): comp 0 = stream function,
+# comp 1 = vorticity.  Pinned by tests/golden/stokes_*.npz, which hold what the
+# example's OWN class computes when run live (oracle/live_squirmer.py,
+# oracle/make_golden_stokes.py).
+# --------------------------------------------------------------------------
+def annulus_nodes(nr, nt, p, r_out):
+    """Synthetic stand-in for examples/meshes/donut.geo (no .msh ships): meridional
+    half plane (rho, z), r = r_out**s in [1, r_out], theta from pi down to 0 so that
+    detJ > 0; equispaced in the parametric coordinates of every element."""
+    NR, NT = nr * p + 1, nt * p + 1
+    r = r_out ** np.linspace(0.0, 1.0, NR)
+    th = np.linspace(np.pi, 0.0, NT)
+    sin = np.sin(th)
+    sin[0] = 0.0
+    sin[-1] = 0.0
+    return np.vstack([np.outer(r, sin).ravel(), np.outer(r, np.cos(th)).ravel()])
+
+
+def annulus_boundary_faces(nr, nt):
+    """{name: [(cell, face)]} in the registration order of the mesh builder."""
+    out = {"sphere": [], "shell": [], "symaxis": []}
+    c = 0
+    for ex in range(nr):
+        for ey in range(nt):
+            if ex == 0:
+                out["sphere"].append((c, 0))
+            if ex == nr - 1:
+                out["shell"].append((c, 1))
+            if ey == 0:
+                out["symaxis"].append((c, 2))
+            if ey == nt - 1:
+                out["symaxis"].append((c, 3))
+            c += 1
+    return out
+
+
+def stokes_local_operators(basis, x_phys, invJ, JxW):
+    """Dense local operators of examples/squirmer-axisymmetric.py:177-254, batched over
+    elements: E2e, Lve [E,p,q,r,s], the mass diagonal Me [E,m,n] and the four diagonals
+    of the advection operator Ae WITHOUT the Reynolds-number factor (:228-249)."""
+    D, N = basis.D, basis.N
+    rho = x_phys[:, 0]
+    g0 = np.einsum("mp,eimn->eimnp", D, invJ[:, 0])     # gradh_xi0 (:188)
+    g1 = np.einsum("nq,eimn->eimnq", D, invJ[:, 1])     # gradh_xi1 (:190)
+    E = invJ.shape[0]
+    rJ = rho * JxW                                      # rho_JxW (:194)
+    E2 = np.zeros((E, N, N, N, N))
+    p, q, r = np.ogrid[0:N, 0:N, 0:N]
+    E2[:, p, q, r, q] += np.einsum("emn,eimnp,eimnr->epnr", rJ, g0, g0)      # :198-199
+    E2 += np.einsum("emn,eimnp,eimns->epnms", rJ, g0, g1)                    # :200-201
+    E2 += np.einsum("emn,eimnq,eimnr->emqrn", rJ, g1, g0)                    # :204-205
+    E2[:, p, q, p, r] += np.einsum("emn,eimnq,eimns->emqs", rJ, g1, g1)      # :206-207
+    Lv = E2.copy()                                                           # :210
+    pp, qq = np.ogrid[0:N, 0:N]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        jr = JxW / rho                                                       # :211 (inf on the axis)
+    Lv[:, pp, qq, pp, qq] += jr
+    E2[:, p, q, r, q] += 2 * np.einsum("emn,emnr->emnr", JxW, g0[:, 0])     # :221
+    E2[:, p, q, p, r] += 2 * np.einsum("emn,emns->emns", JxW, g1[:, 0])     # :222
+    adv = dict(
+        a1=(np.einsum("emn,emnr,emnu->emnru", JxW, g0[:, 0], g1[:, 1]) -
+            np.einsum("emn,emnr,emnu->emnru", JxW, g0[:, 1], g1[:, 0])),    # :227-231, axes [0,1,2,1,0,3]
+        a2=(np.einsum("emn,emns,emnt->emnst", JxW, g1[:, 0], g0[:, 1]) -
+            np.einsum("emn,emns,emnt->emnst", JxW, g1[:, 1], g0[:, 0])),    # :233-238, axes [0,1,0,2,3,1]
+        a3=np.einsum("emn,emnr->emnr", jr, g0[:, 1]),                       # :240-242, axes [0,1,2,1,0,1]
+        a4=np.einsum("emn,emns->emns", jr, g1[:, 1]))                       # :244-247, axes [0,1,0,2,0,1]
+    Me = rJ * rho                                                           # :252
+    return dict(E2e=E2, Lve=Lv, Me=Me, adv=adv)
+
+
+def stokes_local_system(ops, n_rey, sfn, vort):
+    """(jac_l [E,2nn,2nn], -res_l [E,2nn]) of compute_local_system
+    (examples/squirmer-axisymmetric.py:259-297); sfn, vort [E,N,N] local values."""
+    E2, Lv, Me, adv = ops["E2e"], ops["Lve"], ops["Me"], ops["adv"]
+    E, N = Me.shape[0], Me.shape[1]
+    nn = N * N
+    old_err = np.seterr(invalid="ignore")      # 0 * inf on the axis of symmetry, as in the reference
+    a1, a2, a3, a4 = (n_rey * adv[k] for k in ("a1", "a2", "a3", "a4"))
+    m, n, k = np.ogrid[0:N, 0:N, 0:N]
+    # Ae.dot_dense(vort, [4, 5]) -> [m,n,r,s] (:276).  Entries are PLACED on their
+    # Kronecker diagonals like KroneckerArray.to_array (sem/sp_array.py:104-113), never
+    # multiplied by a zero: JxW/rho is infinite on the axis of symmetry.
+    Aw = np.zeros((E, N, N, N, N))
+    Aw[:, m, n, k, n] += np.einsum("emnru,emu->emnr", a1, vort)
+    Aw[:, m, n, m, k] += np.einsum("emnst,etn->emns", a2, vort)
+    Aw[:, m, n, k, n] += a3 * vort[:, :, :, None]
+    Aw[:, m, n, m, k] += a4 * vort[:, :, :, None]
+    # Ae.dot_dense(sfn, [2, 3]) -> [m,n,t,u] (:281)
+    As = np.zeros((E, N, N, N, N))
+    As[:, m, n, m, k] += np.einsum("emnru,ern->emnu", a1, sfn)
+    As[:, m, n, k, n] += np.einsum("emnst,ems->emnt", a2, sfn)
+    mm, nn2 = np.ogrid[0:N, 0:N]
+    As[:, mm, nn2, mm, nn2] += (np.einsum("emnr,ern->emn", a3, sfn) +
+                                np.einsum("emns,ems->emn", a4, sfn))
+    jac = np.zeros((E, 2 * nn, 2 * nn))
+    res = np.zeros((E, 2 * nn))
+    Md = np.zeros((E, N, N, N, N))
+    pp, qq = np.ogrid[0:N, 0:N]
+    Md[:, pp, qq, pp, qq] = Me
+    jac[:, 0::2, 0::2] = Aw.reshape(E, nn, nn)
+    jac[:, 0::2, 1::2] = (As + Lv).reshape(E, nn, nn)
+    with np.errstate(invalid="ignore"):
+        res[:, 0::2] = (np.einsum("emnrs,ers->emn", Aw, sfn) +
+                        np.einsum("epqrs,ers->epq", Lv, vort)).reshape(E, nn)
+    jac[:, 1::2, 0::2] = E2.reshape(E, nn, nn)
+    jac[:, 1::2, 1::2] = -Md.reshape(E, nn, nn)
+    res[:, 1::2] = (np.einsum("epqrs,ers->epq", E2, sfn) - Me * vort).reshape(E, nn)
+    np.seterr(**old_err)
+    return jac, -res
+
+
+def hier_dof_order(N, dpn):
+    """Local DOF order with the element-exterior DOFs first (sem/discrete.py:611-625):
+    node order of hier_order, DOFs of a node adjacent."""
+    h = hier_order(N).astype(np.int64)
+    return (h[:, None] * dpn + np.arange(dpn)[None, :]).ravel()
+
+
+def stokes_newton_step(jac, rhs, l2g, n_ext_nodes, dof_mask, cint):
+    """One pass of the example's solve loop (:420-431): hierarchical reorder (:300-306),
+    local Schur complements by a transposed dense solve (:318-321), COO assembly over the
+    exterior DOFs with the natural-BC contour integrals as the initial RHS (:336-358),
+    elimination of essential rows / columns against a ZERO increment (:362-370), spsolve,
+    interior back-substitution (:372-386).  Returns the increment dsoln [2 n_nodes]."""
+    E, N = l2g.shape[0], l2g.shape[1]
+    nn = N * N
+    hd = hier_dof_order(N, 2)
+    ne = 2 * (nn - (N - 2) ** 2)
+    n_ext = 2 * n_ext_nodes
+    A = jac[:, hd][:, :, hd]
+    b = rhs[:, hd]
+    gid = (2 * l2g.reshape(E, nn).astype(np.int64)[:, :, None] + np.arange(2)).reshape(E, 2 * nn)[:, hd]
+    Aee, Aei, Aie, Aii = A[:, :ne, :ne], A[:, :ne, ne:], A[:, ne:, :ne], A[:, ne:, ne:]
+    with np.errstate(invalid="ignore"):
+        X = np.swapaxes(np.linalg.solve(np.swapaxes(Aii, 1, 2), np.swapaxes(Aei, 1, 2)), 1, 2)
+        S = Aee - X @ Aie
+        g = b[:, :ne] - np.einsum("eij,ej->ei", X, b[:, ne:])
+    ids = gid[:, :ne]
+    rows = np.repeat(ids, ne, axis=1).ravel()
+    cols = np.tile(ids, (1, ne)).ravel()
+    Sg = sparse.coo_matrix((S.reshape(-1), (rows, cols)), shape=(n_ext, n_ext)).tocsr()
+    grhs = cint.copy()
+    np.add.at(grhs, ids.ravel(), g.ravel())
+    n_tot = 2 * (int(l2g.max()) + 1)
+    d = np.zeros(n_tot)
+    unk = dof_mask
+    A1 = Sg[unk]
+    r1 = grhs[unk] - A1[:, ~unk] @ d[:n_ext][~unk]
+    d[:n_ext][unk] = spsolve(A1[:, unk].tocsc(), r1)
+    inner = np.linalg.solve(Aii, (b[:, ne:] - np.einsum("eij,ej->ei", Aie, d[ids]))[..., None])
+    d[gid[:, ne:]] = inner[..., 0]
+    return d
+
+
+def stokes_global_jacobian(jac, l2g):
+    """Assembled (uncondensed, no BCs) Jacobian over all 2*n_nodes DOFs: what the
+    matrix-free device apply is compared with."""
+    E, N = l2g.shape[0], l2g.shape[1]
+    nn = N * N
+    gid = (2 * l2g.reshape(E, nn).astype(np.int64)[:, :, None] + np.arange(2)).reshape(E, 2 * nn)
+    rows = np.repeat(gid, 2 * nn, axis=1).ravel()
+    cols = np.tile(gid, (1, 2 * nn)).ravel()
+    J = np.where(np.isfinite(jac), jac, 0.0)   # JxW/rho on the axis: rows / columns eliminated by the BCs
+    n = 2 * (int(l2g.max()) + 1)
+    return sparse.coo_matrix((J.reshape(-1), (rows, cols)), shape=(n, n)).tocsr()
