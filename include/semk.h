@@ -773,6 +773,83 @@ int semk_halo_exchange_f64(int64_t n_col, int64_t n_local, double *y, const doub
                            void *right_region, uint64_t epoch, double *dot_inout, int *status,
                            void *stream);
 
+/* ------------------------------------------------------------------------
+ * Axisymmetric Stokes / linearised Navier-Stokes in stream function - vorticity
+ * form (BASELINE config 4).  Two DOFs per node, DOF id =
+ * 2*node + comp (comp 0: stream function, 1: vorticity; sem/discrete.py:561-576),
+ * so nodal vectors are device [n_nodes][2] = 16-byte (psi, omega) pairs.
+ *
+ * Replaces, matrix-free, the dense local operators of the reference's example:
+ *   pre_assembly          examples/squirmer-axisymmetric.py:163-257  (E2e, Lve, Ae, Me)
+ *   compute_local_system  examples/squirmer-axisymmetric.py:259-297  (Jacobian blocks
+ *                         jac[0::2,0::2] = Ae.vort, jac[0::2,1::2] = Ae.sfn + Lve,
+ *                         jac[1::2,0::2] = E2e, jac[1::2,1::2] = -Me, and the residual)
+ *   the scatter-add       examples/squirmer-axisymmetric.py:336-358 / sem/discrete.py:499
+ *
+ * The operator reuses the plan tables of a semk_op built for the same mesh
+ * (semk_hostplan_build); its G / g_patch_stride name the FACTOR block
+ * [n_patch][n_fac][n1][PE][n1] (same thread-major layout as G) holding
+ *   0..2  rho*JxW*(invJ invJ^T)   (:194-207)      3, 4  2*JxW*invJ[0][0], 2*JxW*invJ[1][0] (:221-222)
+ *   5     JxW/rho, 0 where rho = 0 (:211)         6     rho^2*JxW (:252)
+ *   7..11 advection coefficients of the linearisation about a state (:227-249; n_fac = 12)
+ * and its slot_buf holds 2*n_slots doubles.
+ * ------------------------------------------------------------------------ */
+typedef struct semk_stokes_op {
+  semk_op plan;
+  int32_t n_fac;          /* 7: Stokes (Re = 0); 12: with the advection coefficients */
+  int32_t reserved;
+  int64_t n_ess;          /* essential (Dirichlet) DOFs */
+  const int64_t *ess_dof; /* device [n_ess] DOF ids 2*node + comp */
+} semk_stokes_op;
+
+int64_t semk_stokes_smem_bytes(int n1, int elems_per_patch, int64_t f_patch_stride,
+                               int64_t pn_patch_stride, int64_t eloc_patch_stride,
+                               int64_t inv_patch_stride);
+/* factors 0..6 from the geometry in the reference's layouts: invJ [n_elem][2][2][NN]
+ * (fe.invJ), JxW [n_elem][NN] (fe.detJxW), x_phys [n_elem][2][NN] (fe.x_phys; [0] = rho) */
+int semk_stokes_factors_f64(int n1, int64_t n_slot_elems, const double *invJ, const double *JxW,
+                            const double *x_phys, const int64_t *elem_of_slot, double *F,
+                            int64_t f_patch_stride, int elems_per_patch, void *stream);
+/* factors 7..11: linearise the advection operator Ae about `state` (device [n_nodes][2]);
+ * D: device [NN]; l2g: device uint32 [n_elem][NN] */
+int semk_stokes_linearize_f64(int n1, int64_t n_slot_elems, const double *D, const double *invJ,
+                              const double *JxW, const double *x_phys, const uint32_t *l2g,
+                              const int64_t *elem_of_slot, const double *state, double n_rey,
+                              double *F, int64_t f_patch_stride, int elems_per_patch,
+                              void *stream);
+/* y = J u (assembled local Jacobians, no boundary conditions); with
+ * zero_essential_rows != 0 the rows listed in ess_dof are zeroed afterwards (the
+ * caller keeps the essential entries of u at zero: J restricted to the unknowns,
+ * examples/squirmer-axisymmetric.py:362-370).  adv_scale multiplies the advection
+ * terms: 1 = Jacobian, 0.5 with u = state = the nonlinear residual (the term is
+ * bilinear).  u, y: distinct, 16-byte aligned.  Deterministic (no atomics). */
+int semk_stokes_apply_f64(const semk_stokes_op *op, const double *u, double *y,
+                          int zero_essential_rows, double adv_scale, void *stream);
+/* element-local diagonals (engine slot order, [n_slot_elems][NN]) of Lve, E2e, Me and of
+ * the advection block d row0 / d psi (locA may be NULL): inputs of the nodal 2x2
+ * block-Jacobi preconditioner after semk_assemble_f64 */
+int semk_stokes_local_diag_f64(const semk_stokes_op *op, const double *D_dev,
+                               int64_t n_slot_elems, double *locL, double *locE, double *locM,
+                               double *locA, void *stream);
+/* y[idx[i]] = src ? src[idx[i]] : 0 */
+int semk_scatter_fix_f64(int64_t n, const int64_t *idx, const double *src, double *y,
+                         void *stream);
+
+/* Building blocks of the restarted GMRES that replaces the reference's sparse direct
+ * solve of the non-symmetric system (examples/squirmer-axisymmetric.py:360-370):
+ * out[j] = V_j . w for j < k with V_j = V + j*ldv (one pass, fixed-order reduction);
+ * w += sign * sum_j h[j] V_j (h on the device); out = alpha a (+ b);
+ * z_n = B_n r_n with nodal 2x2 blocks binv [n_nodes][4]. */
+int64_t semk_multi_dot_partials_len(int k);
+int semk_multi_dot_f64(int64_t n, int k, const double *V, int64_t ldv, const double *w,
+                       double *out, double *partials, void *stream);
+int semk_multi_axpy_f64(int64_t n, int k, const double *V, int64_t ldv, const double *h,
+                        double sign, double *w, void *stream);
+int semk_vec_scale_add_f64(int64_t n, double alpha, const double *a, const double *b,
+                           double *out, void *stream);
+int semk_block2_apply_f64(int64_t n_nodes, const double *binv, const double *r, double *z,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,11 @@ class semk_ml_info(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class semk_stokes_op(C.Structure):
+    _fields_ = [("plan", semk_op), ("n_fac", C.c_int32), ("reserved", C.c_int32),
+                ("n_ess", C.c_int64), ("ess_dof", C.c_void_p)]
+
+
 class semk_stage(C.Structure):
     _fields_ = [("patch_end", C.c_int64), ("chunk_end", C.c_int64), ("rec_end", C.c_int64),
                 ("u_need", C.c_int64), ("y_final", C.c_int64)]
@@ -212,6 +217,17 @@ SIGNATURES = {
     "semk_peer_close": (_I, [_P]),
     "semk_peer_free": (_I, [_P]),
     "semk_halo_exchange_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "semk_stokes_smem_bytes": (_L, [_I, _I, _L, _L, _L, _L]),
+    "semk_stokes_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _L, _I, _P]),
+    "semk_stokes_linearize_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _D, _P, _L, _I, _P]),
+    "semk_stokes_apply_f64": (_I, [C.POINTER(semk_stokes_op), _P, _P, _I, _D, _P]),
+    "semk_stokes_local_diag_f64": (_I, [C.POINTER(semk_stokes_op), _P, _L, _P, _P, _P, _P, _P]),
+    "semk_scatter_fix_f64": (_I, [_L, _P, _P, _P, _P]),
+    "semk_multi_dot_partials_len": (_L, [_I]),
+    "semk_multi_dot_f64": (_I, [_L, _I, _P, _L, _P, _P, _P, _P]),
+    "semk_multi_axpy_f64": (_I, [_L, _I, _P, _L, _P, _D, _P, _P]),
+    "semk_vec_scale_add_f64": (_I, [_L, _D, _P, _P, _P, _P]),
+    "semk_block2_apply_f64": (_I, [_L, _P, _P, _P, _P]),
 }
 
 _lib = None

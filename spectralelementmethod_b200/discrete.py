@@ -401,6 +401,17 @@ class DOFManager(object):
         return PoissonOperator(self, dirichlet=dirichlet,
                                geometric_factors=geometric_factors, **kwargs)
 
+    def axisymmetric_stokes_operator(self, n_rey=0.0, essential=None, **kwargs):
+        """Matrix-free Jacobian / residual of the axisymmetric stream function - vorticity
+        system of examples/squirmer-axisymmetric.py:163-297 on the GPU (two DOFs per node;
+        additive API, see stokes.AxisymmetricStokesOperator).
+
+        essential : bool[2*n_nodes] (or bool[ndof_exterior]), optional -- True on
+            essential-BC DOFs (the complement of the example's ``dof_mask``).
+        """
+        from .stokes import AxisymmetricStokesOperator
+        return AxisymmetricStokesOperator(self, n_rey=n_rey, essential=essential, **kwargs)
+
 
 class DOFManagerSC(DOFManager):
     """DOF manager that numbers cell-exterior nodes first so that cell

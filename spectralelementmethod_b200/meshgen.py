@@ -16,7 +16,8 @@ import numpy as np
 from .discrete import Mesh
 from .geometry import Quadrilateral
 
-__all__ = ["lattice_coordinates", "structured_node_maps", "structured_quad_mesh"]
+__all__ = ["lattice_coordinates", "structured_node_maps", "structured_quad_mesh",
+           "annulus_coordinates", "annulus_sector_mesh"]
 
 
 def lattice_coordinates(kind, nx, ny, p, bounds=(-1.0, 1.0, -1.0, 1.0)):
@@ -74,6 +75,54 @@ def structured_quad_mesh(nx, ny, p, kind="S", bounds=(-1.0, 1.0, -1.0, 1.0), nod
         mesh.add_boundary_cells(cell[-1, :], nbc, 1, 1)
         mesh.add_boundary_cells(cell[:, -1], nbc, 1, 3)
     mesh._structured_shape = (nx, ny)
+    return mesh
+
+
+def annulus_coordinates(nr, nt, p, r_out=100.0):
+    """``float64[2, NR*NT]`` meridional coordinates (rho, z) of a spherical-annulus
+    sector: r = r_out**s in [1, r_out] (geometric grading, as the ``Progression`` of
+    examples/meshes/donut.geo), polar angle from pi (the -z axis) down to 0 (the +z axis)
+    so that detJ = r > 0 with xi0 radial and xi1 along the angle; equispaced in the
+    parametric coordinates of every cell; rho is exactly 0 on the axis of symmetry."""
+    r = float(r_out) ** np.linspace(0.0, 1.0, nr * p + 1)
+    th = np.linspace(np.pi, 0.0, nt * p + 1)
+    sin = np.sin(th)
+    sin[0] = 0.0
+    sin[-1] = 0.0
+    return np.vstack([np.outer(r, sin).ravel(), np.outer(r, np.cos(th)).ravel()])
+
+
+def annulus_sector_mesh(nr, nt, p, r_out=100.0):
+    """nr x nt quadrilaterals of order p between the unit sphere and the shell r = r_out
+    in the meridional half plane: the synthetic stand-in for examples/meshes/donut.geo
+    (physical names "sphere", "shell", "symaxis", region "interior"; BASELINE config 4)."""
+    mesh = Mesh(2)
+    mesh.set_nodes(annulus_coordinates(nr, nt, p, r_out))
+    g = mesh.add_geometry(Quadrilateral(p + 1, p + 1))
+    reg = mesh.new_region("interior")
+    sphere = mesh.new_boundary("sphere")
+    shell = mesh.new_boundary("shell")
+    axis = mesh.new_boundary("symaxis")
+    mesh.add_cells(structured_node_maps(nr, nt, p), g, reg)
+    cell = np.arange(nr * nt).reshape(nr, nt)
+    if nr * nt <= 4096:
+        # per-cell registration order of a hand-built mesh: faces 0, 1, 2, 3
+        for c in range(nr * nt):
+            ex, ey = divmod(c, nt)
+            if ex == 0:
+                mesh.add_boundary_cell(c, sphere, 1, 0)
+            if ex == nr - 1:
+                mesh.add_boundary_cell(c, shell, 1, 1)
+            if ey == 0:
+                mesh.add_boundary_cell(c, axis, 1, 2)
+            if ey == nt - 1:
+                mesh.add_boundary_cell(c, axis, 1, 3)
+    else:
+        mesh.add_boundary_cells(cell[0, :], sphere, 1, 0)
+        mesh.add_boundary_cells(cell[-1, :], shell, 1, 1)
+        mesh.add_boundary_cells(cell[:, 0], axis, 1, 2)
+        mesh.add_boundary_cells(cell[:, -1], axis, 1, 3)
+    mesh._structured_shape = (nr, nt)
     return mesh
 
 
