@@ -443,6 +443,54 @@ SWEEP_NX = {2: 2048, 3: 1536, 4: 1024, 5: 1024, 6: 1024, 7: 1024, 8: 1024, 9: 89
             11: 704, 12: 640, 13: 576, 14: 576, 15: 512, 16: 512}
 
 
+def run_stokes(args, peak):
+    """BASELINE configs[3]: the axisymmetric Stokes system of examples/squirmer-axisymmetric.py
+    (2 DOF per node, Jacobian [[0, Lve], [E2e, -Me]] at Re = 0 and with the advection blocks
+    at Re = 1) on a graded annulus-sector mesh scaled to ~1e7 DOF: matrix-free apply
+    throughput and its HBM roofline.  (The non-symmetric solve is GMRES with a nodal
+    block-Jacobi preconditioner: parity-tested on small meshes, not mesh-independent.)"""
+    import numpy as np
+    import torch
+    from spectralelementmethod_b200 import discrete, meshgen
+    from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+    nr, nt, p = 224, 352, 8
+    t0 = time.perf_counter()
+    mesh = meshgen.annulus_sector_mesh(nr, nt, p, 100.0)
+    b1 = LagrangeGaussLobatto(p)
+    dm = discrete.DOFManager(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
+    out = {"workload": "annulus sector r in [1, 100], %dx%d elements p=%d, stream function + "
+                       "vorticity (BASELINE configs[3])" % (nr, nt, p)}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for n_rey in (0.0, 1.0):
+        op = dm.axisymmetric_stokes_operator(n_rey=n_rey)
+        torch.cuda.synchronize()
+        setup = time.perf_counter() - t0
+        x = torch.from_numpy(np.sin(np.arange(op.n_dof) * 1e-3)).cuda()
+        if op.advection:
+            op.linearize(x)
+        y = op.new_vector()
+        for _ in range(5):
+            op.apply_unmasked(x, out=y)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            op.apply_unmasked(x, out=y)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / args.steps
+        alg = op.algorithmic_bytes_per_apply
+        out["re_%g" % n_rey] = {
+            "dof": op.n_dof, "n_factors": op.n_fac, "elems_per_patch": op.elems_per_patch,
+            "smem_bytes_per_cta": op.smem_bytes, "setup_seconds": setup, "ms_per_apply": ms,
+            "gdof_per_s": op.n_dof / ms / 1e6, "algorithmic_bytes": alg,
+            "achieved_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak,
+            "kernel": "stokes_patch_kernel<9,%d,%s> + stokes_shared_nodes_kernel"
+                      % (op.elems_per_patch, "ADV" if op.advection else "STOKES")}
+        del op, x, y
+        t0 = time.perf_counter()
+    return out
+
+
 def sweep_bytes_per_dof(p):
     """B(p) = 16 + 28 ((p+1)/p)^2 algorithmic bytes per global DOF per apply."""
     return 16.0 + 28.0 * ((p + 1.0) / p) ** 2
@@ -729,6 +777,13 @@ def run_engine(args):
         if dc.halo is not None:
             dc.halo.check()
 
+    stokes_blk = None
+    if not multi and not args.no_condensed:
+        try:
+            stokes_blk = run_stokes(args, peak)
+        except Exception as exc:       # reported, never fatal for the headline line
+            stokes_blk = {"error": repr(exc)}
+
     # the metric's second half, PCG time to solution (rtol 1e-12), by the fastest device path:
     # static condensation + multilevel-preconditioned flexible CG + interior back-solve
     tts = None
@@ -825,6 +880,7 @@ def run_engine(args):
             "clocks": clocks.summary(),
             "pcg": pcg,
             "condensed": condensed,
+            "stokes": stokes_blk,
             "time_to_solution": tts,
             "parity": parity,
         }
