@@ -203,6 +203,11 @@ typedef struct semk_op {
   double *partials;         /* [semk_partials_len()] dot-product scratch    */
   const double *D_host;     /* HOST pointer, [NN] differentiation matrix    */
   const uint8_t *dirichlet; /* [n_nodes] 1 = essential-BC node, or NULL (PCG: not an unknown) */
+  int64_t kernel_variant;   /* thread mapping of the apply kernel: 0 = one thread per element
+                               column (patch_kernel, csrc/semk_apply.cu); 1 = a column lane +
+                               a row lane per element column (ho_patch_kernel, csrc/semk_ho.cu;
+                               n1 >= 9): twice the warps at half the registers, for the high
+                               orders where the column mapping is latency-bound */
 } semk_op;
 
 /* number of doubles the `partials` scratch of an operator must hold
@@ -213,6 +218,10 @@ int64_t semk_partials_len(int64_t n_patch, int64_t n_shared);
 int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_patch_stride,
                            int64_t pn_patch_stride, int64_t eloc_patch_stride,
                            int64_t inv_patch_stride);
+/* the same for a given semk_op.kernel_variant */
+int64_t semk_resident_ctas_variant(int kernel_variant, int n1, int elems_per_patch,
+                                   int64_t g_patch_stride, int64_t pn_patch_stride,
+                                   int64_t eloc_patch_stride, int64_t inv_patch_stride);
 /* dynamic shared memory (bytes) one CTA of the apply kernel needs */
 int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,
                               int64_t pn_patch_stride, int64_t eloc_patch_stride,

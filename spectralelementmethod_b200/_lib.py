@@ -64,6 +64,7 @@ class semk_op(C.Structure):
         ("n_shared", C.c_int64), ("shared_rec", C.c_void_p), ("shared_ext", C.c_void_p),
         ("n_shared_chunk", C.c_int64), ("shared_chunk", C.c_void_p),
         ("partials", C.c_void_p), ("D_host", C.c_void_p), ("dirichlet", C.c_void_p),
+        ("kernel_variant", C.c_int64),
     ]
 
 
@@ -156,6 +157,7 @@ SIGNATURES = {
     "semk_partials_len": (_L, [_L, _L]),
     "semk_patch_smem_bytes": (_L, [_I, _I, _L, _L, _L, _L]),
     "semk_resident_ctas": (_L, [_I, _I, _L, _L, _L, _L]),
+    "semk_resident_ctas_variant": (_L, [_I, _I, _I, _L, _L, _L, _L]),
     "semk_geom_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P,
                                    _P, _P, _P, _P]),
     "semk_gfactors_from_invj_f64": (_I, [_I, _L, _P, _P, _P, _P, _L, _I, _P]),

@@ -111,54 +111,10 @@ struct PatchCfg {
   static constexpr int kRS = scratch_row_stride(N, PE);
 };
 
-enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
-
-
-// Shared-memory carve-up of the persistent patch kernel (offsets multiples of
-// 16 B): one G buffer, two stages of {node block, index block}, one copy of
-// the working arrays.
-struct PatchSmem {
-  size_t hdr, gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
-  size_t inv, ua, bs, red, total;
-};
-__host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
-                                                       int64_t g_patch_stride,
-                                                       int64_t pn_patch_stride,
-                                                       int64_t eloc_patch_stride,
-                                                       int64_t inv_patch_stride) {
-  PatchSmem L;
-  const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
-  size_t o = 32;  // four mbarriers: tables[2], G, inverse table
-  L.hdr = o;      // two 32-byte patch headers (ring)
-  o += 64;
-  L.gs = o;
-  o += (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
-  L.stage0 = o;
-  L.pn_off = 0;
-  size_t st = 4 * (size_t)pn_patch_stride;
-  L.el_off = st;
-  st += 2 * (size_t)eloc_patch_stride;
-  st = (st + 15) & ~(size_t)15;
-  L.stage_bytes = st;
-  o += 2 * st;
-  L.inv = o;  // inverse table of the patch being written out (single buffer)
-  o += 2 * (size_t)inv_patch_stride;
-  o = (o + 15) & ~(size_t)15;
-  L.ua = o;  // scratch A
-  o += (mode == MODE_APPLY) ? 8 * scratch : 0;
-  o = (o + 15) & ~(size_t)15;
-  L.bs = o;  // scratch B: the element results the write-out gathers from; its head doubles
-             // as the block-reduction scratch at the very end
-  o += 8 * scratch > 256 ? 8 * scratch : 256;
-  L.red = L.bs;
-  L.total = o;
-  return L;
-}
-
 // Resident CTAs per SM the kernel is compiled for (register budget): what the
 // shared-memory footprint of the standard tiles (2x8, 1x8, 1x4 elements) allows.
 __host__ __device__ constexpr int patch_min_blocks(int N, int PE) {
-  const int bx = PE == 16 ? 2 : 1, by = PE == 4 ? 4 : 8, p = N - 1;
+  const int bx = PE == 32 ? 4 : (PE == 16 ? 2 : 1), by = PE == 4 ? 4 : 8, p = N - 1;
   const long long mpn = (long long)(bx * p + 1) * (by * p + 1);
   const long long mpn4 = (mpn + 3) & ~3LL;
   const long long nn = (long long)N * N;
@@ -768,17 +724,50 @@ struct PatchLaunch {
 };
 
 // elements per patch supported by the compiled kernels
-inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16; }
+inline bool pe_supported(int pe) { return pe == 4 || pe == 8 || pe == 16 || pe == 32; }
+
+// 32-element patches (4 x 8 tiles) exist for the low orders only (n1 <= kBigPatchMaxN1):
+// small elements amortise the per-patch barriers and tables better over a larger patch and
+// have a smaller share of interface nodes.
+constexpr int kBigPatchMaxN1 = 7;
+template <int NV, int MODE, bool OK = (NV <= kBigPatchMaxN1)>
+struct BigPatch {
+  static int run(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
+                 double *y, int flags, double fill, double *partials, cudaStream_t st,
+                 int *grid_out, int64_t pb, int64_t pe) {
+    return PatchLaunch<32, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st,
+                                                   grid_out, pb, pe);
+  }
+  static int occupancy(size_t smem, int *per_sm, int *sms) {
+    return PatchLaunch<32, MODE>::template occupancy<NV>(smem, per_sm, sms);
+  }
+};
+template <int NV, int MODE>
+struct BigPatch<NV, MODE, false> {
+  static int run(const semk_op &, const DMatEO &, const double *, const double *, double *, int,
+                 double, double *, cudaStream_t, int *, int64_t, int64_t) {
+    semk_set_error("32-element patches are compiled for n1 <= 7 only");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  static int occupancy(size_t, int *, int *) {
+    semk_set_error("32-element patches are compiled for n1 <= 7 only");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+};
 
 template <int MODE>
 int launch_patch(const semk_op &op, const DMatEO &dm, const double *u, const double *loc,
                  double *y, int flags, double fill, double *partials, cudaStream_t st,
                  int *grid_out, int64_t pb = 0, int64_t pe = -1) {
   if (pe < 0) pe = op.n_patch;
+  if (MODE == MODE_APPLY && op.kernel_variant == 1)
+    return semk_ho_launch(op, u, y, flags, partials, st, grid_out, pb, pe);
 #define SEMK_CALL(NV)                                                                     \
   do {                                                                                    \
     int rc;                                                                               \
-    if (op.elems_per_patch == 16)                                                         \
+    if (op.elems_per_patch == 32)                                                         \
+      rc = BigPatch<NV, MODE>::run(op, dm, u, loc, y, flags, fill, partials, st, grid_out, pb, pe); \
+    else if (op.elems_per_patch == 16)                                                    \
       rc = PatchLaunch<16, MODE>::template run<NV>(op, dm, u, loc, y, flags, fill, partials, st, \
                                                    grid_out, pb, pe); \
     else if (op.elems_per_patch == 8)                                                     \
@@ -804,7 +793,7 @@ int check_op(const semk_op *op, const char *who) {
     return SEMK_ERR_UNSUPPORTED;
   }
   if (!pe_supported(op->elems_per_patch)) {
-    semk_set_error(std::string(who) + ": elems_per_patch must be 4, 8 or 16");
+    semk_set_error(std::string(who) + ": elems_per_patch must be 4, 8, 16 or 32");
     return SEMK_ERR_UNSUPPORTED;
   }
   const int64_t nnp = (int64_t)op->n1 * op->n1 * op->elems_per_patch;
@@ -849,7 +838,9 @@ extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_pat
 #define SEMK_CALL(NV)                                                                  \
   do {                                                                                 \
     int rc;                                                                            \
-    if (elems_per_patch == 16)                                                         \
+    if (elems_per_patch == 32)                                                         \
+      rc = BigPatch<NV, MODE_APPLY>::occupancy(smem, &per_sm, &sms);                   \
+    else if (elems_per_patch == 16)                                                    \
       rc = PatchLaunch<16, MODE_APPLY>::template occupancy<NV>(smem, &per_sm, &sms);   \
     else if (elems_per_patch == 8)                                                     \
       rc = PatchLaunch<8, MODE_APPLY>::template occupancy<NV>(smem, &per_sm, &sms);    \
@@ -863,6 +854,21 @@ extern "C" int64_t semk_resident_ctas(int n1, int elems_per_patch, int64_t g_pat
   };
   if (run() != SEMK_OK) return -1;
   return (int64_t)per_sm * sms;
+}
+
+extern "C" int64_t semk_resident_ctas_variant(int kernel_variant, int n1, int elems_per_patch,
+                                              int64_t g_patch_stride, int64_t pn_patch_stride,
+                                              int64_t eloc_patch_stride,
+                                              int64_t inv_patch_stride) {
+  if (kernel_variant == 0)
+    return semk_resident_ctas(n1, elems_per_patch, g_patch_stride, pn_patch_stride,
+                              eloc_patch_stride, inv_patch_stride);
+  if (kernel_variant != 1 || !pe_supported(elems_per_patch) || elems_per_patch == 32) return -1;
+  const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
+                                        pn_patch_stride, eloc_patch_stride, inv_patch_stride)
+                          .total;
+  if (smem > 227 * 1024) return -1;
+  return semk_ho_resident(n1, elems_per_patch, smem);
 }
 
 extern "C" int64_t semk_patch_smem_bytes(int n1, int elems_per_patch, int64_t g_patch_stride,

@@ -155,4 +155,54 @@ __host__ __device__ constexpr int scratch_row_stride(int N, int PE) {
   return ((N * PE - 1 + 15) & ~15) + 1;  // == semk_scratch_row_stride (include/semk.h)
 }
 
+enum { MODE_APPLY = 0, MODE_ASSEMBLE = 1 };
+
+
+// Shared-memory carve-up of the persistent patch kernel (offsets multiples of
+// 16 B): one G buffer, two stages of {node block, index block}, one copy of
+// the working arrays.
+struct PatchSmem {
+  size_t hdr, gs, stage0, stage_bytes, pn_off, el_off;  // per stage: node block | index block
+  size_t inv, ua, bs, red, total;
+};
+__host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
+                                                       int64_t g_patch_stride,
+                                                       int64_t pn_patch_stride,
+                                                       int64_t eloc_patch_stride,
+                                                       int64_t inv_patch_stride) {
+  PatchSmem L;
+  const size_t scratch = (size_t)N * scratch_row_stride(N, PE);
+  size_t o = 32;  // four mbarriers: tables[2], G, inverse table
+  L.hdr = o;      // two 32-byte patch headers (ring)
+  o += 64;
+  L.gs = o;
+  o += (mode == MODE_APPLY) ? sizeof(double) * (size_t)g_patch_stride : 0;
+  L.stage0 = o;
+  L.pn_off = 0;
+  size_t st = 4 * (size_t)pn_patch_stride;
+  L.el_off = st;
+  st += 2 * (size_t)eloc_patch_stride;
+  st = (st + 15) & ~(size_t)15;
+  L.stage_bytes = st;
+  o += 2 * st;
+  L.inv = o;  // inverse table of the patch being written out (single buffer)
+  o += 2 * (size_t)inv_patch_stride;
+  o = (o + 15) & ~(size_t)15;
+  L.ua = o;  // scratch A
+  o += (mode == MODE_APPLY) ? 8 * scratch : 0;
+  o = (o + 15) & ~(size_t)15;
+  L.bs = o;  // scratch B: the element results the write-out gathers from; its head doubles
+             // as the block-reduction scratch at the very end
+  o += 8 * scratch > 256 ? 8 * scratch : 256;
+  L.red = L.bs;
+  L.total = o;
+  return L;
+}
+
+
 }  // namespace
+
+// semk_ho.cu: the column / row thread-pair variant of the apply kernel (high orders)
+int semk_ho_launch(const semk_op &op, const double *u, double *y, int flags, double *partials,
+                   cudaStream_t st, int *grid_out, int64_t pb, int64_t pe);
+int64_t semk_ho_resident(int n1, int elems_per_patch, size_t smem);

@@ -29,7 +29,7 @@ __all__ = ["PoissonOperator", "PCGInfo", "default_element_order", "choose_elems_
 # tiles are elongated along the second element axis, along which node ids are
 # contiguous in the lexicographic numbering: long coalesced runs, few strided
 # interface nodes (measured: 2x8 is 7 % faster than 4x4 at p = 8)
-_TILES = {16: (2, 8), 8: (1, 8), 4: (1, 4)}
+_TILES = {32: (4, 8), 16: (2, 8), 8: (1, 8), 4: (1, 4)}
 _SMEM_TARGET = 113 * 1024    # <= this keeps >= 2 persistent CTAs per SM
 _SMEM_LIMIT = 227 * 1024
 
@@ -68,6 +68,12 @@ def choose_elems_per_patch(n1):
     def est(pe):
         bx, by = _TILES[pe]
         return patch_smem_bytes(n1, pe, (bx * p + 1) * (by * p + 1))
+    if n1 <= 5:
+        # low orders: 4 x 8 tiles -- small elements amortise the per-patch barriers and tables
+        # better and have fewer interface nodes (measured on the curved mesh: p = 4 74.2 %
+        # of the HBM peak against 68.2 % with 16-element patches, p = 2 58 % against 41 %;
+        # at p = 6 the 16-element patch is ahead again, profiles/r02_sweep_pe32.json)
+        return 32
     for pe in (16, 8, 4):
         if est(pe) <= _SMEM_TARGET:
             return pe
@@ -149,7 +155,7 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, tile=None, weight=None):
+                 elem_order=None, keep_l2g=True, tile=None, weight=None, mode="auto"):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -176,8 +182,18 @@ class PoissonOperator(object):
         sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
         # engine slots = elements + empty padding slots (-1 entries of the order)
         self.n_order = int(ar[_lib.PA_ELEM_OF_SLOT].size)
-        actual = int(self._lib.semk_resident_ctas(
-            n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
+        # thread mapping of the apply kernel: "column" (one thread per element column) or
+        # "pair" (a column lane + a row lane per element column; high orders, n1 >= 9)
+        if mode == "auto":
+            # measured (profiles/r02_sweep_pair.json): the pair mapping only wins at p = 16
+            mode = "pair" if n1 == 17 else "column"
+        if mode not in ("column", "pair"):
+            raise ValueError("mode must be 'auto', 'column' or 'pair'")
+        self.kernel_variant = 1 if mode == "pair" else 0
+        self.kernel_name = ("ho_patch_kernel<%d,%d>" if self.kernel_variant else
+                            "patch_kernel<%d,%d,APPLY>") % (n1, pe)
+        actual = int(self._lib.semk_resident_ctas_variant(
+            self.kernel_variant, n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
             int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_INV_STRIDE])))
         if actual <= 0:
             raise NotImplementedError(
@@ -301,6 +317,7 @@ class PoissonOperator(object):
         op.partials = self.partials.data_ptr()
         op.D_host = self.tab.D_host.ctypes.data
         op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None
+        op.kernel_variant = self.kernel_variant
         self._op = op
         self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
         self._dinv = None

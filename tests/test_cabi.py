@@ -56,6 +56,9 @@ def test_struct_layout_matches_header(tmp_path):
     top_fields = [f[0] for f in _lib.semk_sc_top._fields_]
     src += ['  printf("%zu\\n", sizeof(struct semk_sc_top));']
     src += ['  printf("%%zu\\n", offsetof(struct semk_sc_top, %s));' % f for f in top_fields]
+    st_fields = [f[0] for f in _lib.semk_stokes_op._fields_]
+    src += ['  printf("%zu\\n", sizeof(struct semk_stokes_op));']
+    src += ['  printf("%%zu\\n", offsetof(struct semk_stokes_op, %s));' % f for f in st_fields]
     src += ['  return 0; }']
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -79,6 +82,10 @@ def test_struct_layout_matches_header(tmp_path):
     assert int(rest[0]) == ctypes.sizeof(_lib.semk_sc_top)
     for f, off in zip(top_fields, rest[1:]):
         assert getattr(_lib.semk_sc_top, f).offset == int(off), f
+    rest = rest[1 + len(top_fields):]
+    assert int(rest[0]) == ctypes.sizeof(_lib.semk_stokes_op)
+    for f, off in zip(st_fields, rest[1:]):
+        assert getattr(_lib.semk_stokes_op, f).offset == int(off), f
 
 
 def _plan(nx, ny, p, pe, order=None, dirichlet=None):

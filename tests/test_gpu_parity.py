@@ -239,6 +239,71 @@ def test_apply_vs_oracle_random(kind, nx, ny, p, sc, rcm, pe):
     assert rel_l2(host(opT1.rhs(f)), bref) < 1e-12
 
 
+@pytest.mark.parametrize("kind,nx,ny,p,sc,rcm,pe", [
+    ("C", 5, 9, 8, False, False, 8),
+    ("C", 4, 8, 8, True, True, 16),
+    ("C", 3, 8, 9, False, False, None),
+    ("C", 4, 5, 10, False, True, 8),
+    ("S", 5, 4, 12, False, False, None),
+    ("C", 3, 4, 12, False, False, 4),
+    ("C", 3, 5, 15, False, False, None),
+    ("C", 3, 3, 16, False, False, None),
+])
+def test_pair_kernel_vs_oracle_and_column_kernel(kind, nx, ny, p, sc, rcm, pe):
+    """The column / row thread-pair mapping (csrc/semk_ho.cu): T1 apply against the oracle
+    <= 1e-12, masked apply + fused dot against the column kernel, determinism."""
+    mesh, mngr = build_package_case(kind, nx, ny, p, sc, rcm)
+    r = so.run_case(kind, nx, ny, p, sc, rcm, solve=False)
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(mngr.ndof)
+    ref = so.apply_dense_batched(r["L"], r["l2g"], u)
+    kw = {} if pe is None else {"elems_per_patch": pe}
+    on = np.zeros(mngr.ndof, dtype=bool)
+    on[rng.choice(mngr.ndof, size=mngr.ndof // 7, replace=False)] = True
+    op = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), mode="pair",
+                               dirichlet=on, **kw)
+    col = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), dirichlet=on, **kw)
+    assert op.kernel_variant == 1 and col.kernel_variant == 0
+    y = op.apply_unmasked(dev(u))
+    assert rel_l2(host(y), ref) < 1e-12
+    assert torch.equal(op.apply_unmasked(dev(u)), y)
+    d0 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ym = op.apply(dev(u), dot_out=d0)
+    yc = col.apply(dev(u), dot_out=d1)
+    assert rel_l2(host(ym), host(yc)) < 1e-13
+    assert abs(float(d0) - float(d1)) <= 1e-12 * abs(float(d1))
+    assert abs(float(d0) - float(torch.dot(dev(u), ym))) <= 1e-11 * abs(float(d1))
+    # PCG through the native driver uses the same dispatch
+    b = op.lift(op.rhs(1.0), None)
+    x0, i0 = op.solve_pcg(b, rtol=1e-10, maxiter=5000)
+    x1, i1 = col.solve_pcg(b, rtol=1e-10, maxiter=5000)
+    assert i0.converged and i1.converged
+    assert rel_l2(host(x0), host(x1)) < 1e-8
+
+
+@pytest.mark.parametrize("kind,nx,ny,p,sc,rcm", [
+    ("C", 8, 16, 4, False, False),
+    ("C", 5, 9, 2, False, True),
+    ("S", 7, 10, 6, True, False),
+    ("C", 4, 8, 3, False, False),
+])
+def test_32_element_patches_vs_oracle(kind, nx, ny, p, sc, rcm):
+    """4 x 8 element tiles for the low orders (elems_per_patch = 32, n1 <= 7)."""
+    mesh, mngr = build_package_case(kind, nx, ny, p, sc, rcm)
+    r = so.run_case(kind, nx, ny, p, sc, rcm, solve=False)
+    rng = np.random.default_rng(6)
+    u = rng.standard_normal(mngr.ndof)
+    ref = so.apply_dense_batched(r["L"], r["l2g"], u)
+    op = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), elems_per_patch=32)
+    assert op.elems_per_patch == 32
+    assert rel_l2(host(op.apply_unmasked(dev(u))), ref) < 1e-12
+    assert rel_l2(host(op.diagonal(masked=False)), r["diag"]) < 1e-12
+    with pytest.raises(NotImplementedError):
+        big = build_package_case("S", 4, 8, 8, False, False)[1]
+        big.poisson_operator(elems_per_patch=32)
+
+
 def test_unstructured_element_order_and_ragged_last_patch():
     """Random element order (no locality), E not a multiple of the patch size."""
     mesh, mngr = build_package_case("C", 5, 5, 4, False, False)
