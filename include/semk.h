@@ -859,6 +859,23 @@ int semk_vec_scale_add_f64(int64_t n, double alpha, const double *a, const doubl
 int semk_block2_apply_f64(int64_t n_nodes, const double *binv, const double *r, double *z,
                           void *stream);
 
+/* ------------------------------------------------------------------------
+ * Host-side (no GPU) multi-threaded integer tables.
+ * semk_host_sc_numbering: DOFManagerSC._do_static_condensation (sem/discrete.py:314-359) +
+ * Mesh._permute_nodes (sem/discrete.py:1115-1127) for a homogeneous mesh, in place, bit-exact
+ * with the reference's np.unique / np.sort numbering; SEMK_ERR_UNSUPPORTED = a mesh the fast
+ * path does not cover (the caller falls back to the whole-array NumPy expressions).
+ * semk_host_structured_maps: the node maps of the hand-built structured mesh of
+ * tests/test_discrete.py:22-38 (node id = i*NY + j).  n_threads: 0 = all processors.
+ * ------------------------------------------------------------------------ */
+int semk_host_structured_maps(int64_t nx, int64_t ny, int32_t p, int64_t node_offset,
+                              uint32_t *out, int32_t n_threads);
+int semk_host_sc_numbering(int64_t n_nodes, int64_t n_cells, int32_t nn, uint32_t *maps,
+                           const int32_t *ext_idx, int32_t n_ext_idx, const int32_t *int_idx,
+                           int32_t n_int_idx, double *nodes, int32_t ndim, int64_t node_stride,
+                           int64_t *n_ext_out, int64_t *n_int_out, uint32_t *order_out,
+                           int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

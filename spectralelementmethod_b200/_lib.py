@@ -219,6 +219,9 @@ SIGNATURES = {
     "semk_peer_close": (_I, [_P]),
     "semk_peer_free": (_I, [_P]),
     "semk_halo_exchange_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "semk_host_structured_maps": (_I, [_L, _L, C.c_int32, _L, _P, C.c_int32]),
+    "semk_host_sc_numbering": (_I, [_L, _L, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P,
+                                    C.c_int32, _L, C.POINTER(_L), C.POINTER(_L), _P, C.c_int32]),
     "semk_stokes_smem_bytes": (_L, [_I, _I, _L, _L, _L, _L]),
     "semk_stokes_factors_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _L, _I, _P]),
     "semk_stokes_linearize_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _P, _D, _P, _L, _I, _P]),
@@ -251,6 +254,14 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def host_threads():
+    """Threads for the host-side table helpers: all processors, shared between the ranks of
+    one box (torchrun exports OMP_NUM_THREADS=1, which is not what set-up code wants)."""
+    n = os.cpu_count() or 1
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(64, n // max(local, 1)))
 
 
 def last_error():

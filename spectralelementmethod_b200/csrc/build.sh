@@ -22,8 +22,14 @@ if [ ! -f "$o" ] || [ semk_hostplan.cpp -nt "$o" ] || [ ../../include/semk.h -nt
   g++ -O3 -std=c++17 -fPIC -c semk_hostplan.cpp -o "$o" &
   PIDS="$PIDS $!"
 fi
+o=semk_hostnum.o
+if [ ! -f "$o" ] || [ semk_hostnum.cpp -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
+  rm -f "$o"
+  g++ -O3 -std=c++17 -fPIC -fopenmp -c semk_hostnum.cpp -o "$o" &
+  PIDS="$PIDS $!"
+fi
 for pid in $PIDS; do
   wait "$pid" || { echo "build.sh: a compile job failed" >&2; exit 1; }
 done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libsemk.so $OBJS semk_hostplan.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fopenmp -o libsemk.so $OBJS semk_hostplan.o semk_hostnum.o
 echo "built $(pwd)/libsemk.so"

@@ -436,6 +436,8 @@ class DOFManagerSC(DOFManager):
         """Renumber: distinct exterior nodes in ascending old id, then the
         interior nodes in ascending old id (sem/discrete.py:314-359)."""
         mesh = self._mesh
+        if self._fast_static_condensation():
+            return
         ext, itr = [], []
         for blk in mesh._blocks_flushed():
             flat = blk.node_maps.reshape(blk.n_cells, -1)
@@ -460,6 +462,47 @@ class DOFManagerSC(DOFManager):
         mesh.n_nodes_cell_exterior = ext_ids.size
         mesh.n_nodes_cell_interior = int_ids.size
         mesh.condensed = True
+
+    def _fast_static_condensation(self):
+        """The same renumbering by the multi-threaded host helper (csrc/semk_hostnum.cpp) for
+        the common case -- one block of cells, contiguous arrays, every node exterior in all
+        its cells or interior to exactly one.  Returns False (nothing touched) when the case
+        is not covered or the library is not built; the NumPy expressions below then run."""
+        mesh = self._mesh
+        blocks = mesh._blocks_flushed()
+        if len(blocks) != 1 or mesh.n_nodes < (1 << 16):
+            return False
+        blk = blocks[0]
+        maps, nodes = blk.node_maps, mesh.nodes
+        if not (isinstance(maps, np.ndarray) and maps.dtype == np.uint32 and maps.flags.c_contiguous
+                and maps.flags.writeable and isinstance(nodes, np.ndarray)
+                and nodes.dtype == np.float64 and nodes.ndim == 2 and nodes.flags.writeable
+                and nodes.strides[1] == 8 and nodes.strides[0] % 8 == 0
+                and nodes.shape[1] >= mesh.n_nodes):
+            return False
+        try:
+            from . import _lib
+            lib = _lib.load()
+        except (ImportError, OSError):
+            return False
+        import ctypes as C
+        geo = mesh._geometries[blk.geometry_id]
+        ext_idx = np.ascontiguousarray(geo.exterior_node_ind, dtype=np.int32).ravel()
+        int_idx = np.ascontiguousarray(geo.interior_node_ind, dtype=np.int32).ravel()
+        nn = int(np.prod(maps.shape[1:]))
+        order = np.empty(mesh.n_nodes, dtype=np.uint32)
+        n_ext, n_int = C.c_int64(0), C.c_int64(0)
+        rc = lib.semk_host_sc_numbering(
+            int(mesh.n_nodes), int(blk.n_cells), nn, maps.ctypes.data, ext_idx.ctypes.data,
+            int(ext_idx.size), int_idx.ctypes.data, int(int_idx.size), nodes.ctypes.data,
+            int(nodes.shape[0]), int(nodes.strides[0] // 8), C.byref(n_ext), C.byref(n_int),
+            order.ctypes.data, _lib.host_threads())
+        if rc != 0:
+            return False        # (the helper leaves everything untouched unless it succeeds)
+        mesh.n_nodes_cell_exterior = int(n_ext.value)
+        mesh.n_nodes_cell_interior = int(n_int.value)
+        mesh.condensed = True
+        return True
 
     def _graph_node_sets(self):
         out = []

@@ -39,6 +39,16 @@ def lattice_coordinates(kind, nx, ny, p, bounds=(-1.0, 1.0, -1.0, 1.0)):
 def structured_node_maps(nx, ny, p, node_offset=0):
     """``uint32[nx*ny, p+1, p+1]`` lexicographic node ids of every cell."""
     NY = ny * p + 1
+    if nx * ny >= 4096:
+        # large meshes: the multi-threaded host helper (csrc/semk_hostnum.cpp), same integers
+        try:
+            from . import _lib
+            out = np.empty((nx * ny, p + 1, p + 1), dtype=np.uint32)
+            if _lib.load().semk_host_structured_maps(nx, ny, p, int(node_offset), out.ctypes.data,
+                                                     _lib.host_threads()) == 0:
+                return out
+        except (ImportError, OSError):
+            pass
     ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
     base = ex * p * NY + ey * p
     m = np.arange(p + 1, dtype=np.int64)

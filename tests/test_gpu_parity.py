@@ -262,7 +262,8 @@ def test_pair_kernel_vs_oracle_and_column_kernel(kind, nx, ny, p, sc, rcm, pe):
     on[rng.choice(mngr.ndof, size=mngr.ndof // 7, replace=False)] = True
     op = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), mode="pair",
                                dirichlet=on, **kw)
-    col = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), dirichlet=on, **kw)
+    col = mngr.poisson_operator(geometric_factors=(r["invJ"], r["JxW"]), dirichlet=on,
+                                mode="column", **kw)
     assert op.kernel_variant == 1 and col.kernel_variant == 0
     y = op.apply_unmasked(dev(u))
     assert rel_l2(host(y), ref) < 1e-12
