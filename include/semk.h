@@ -859,6 +859,25 @@ int semk_vec_scale_add_f64(int64_t n, double alpha, const double *a, const doubl
 int semk_block2_apply_f64(int64_t n_nodes, const double *binv, const double *r, double *z,
                           void *stream);
 
+/* A sub-range of semk_poisson_apply_f64: patches [patch_begin, patch_end) and the interface
+ * entries [chunk_begin, chunk_end) / [rec_begin, rec_end).  Both interface tables are sorted
+ * by the highest patch involved, so what patches [0, P) complete is a prefix of each
+ * (SEMK_PA_CHUNK_MAXPATCH / SEMK_PA_REC_MAXPATCH).  No fused dot. */
+int semk_poisson_apply_range_f64(const semk_op *op, const double *u, double *y, int flags,
+                                 int64_t patch_begin, int64_t patch_end, int64_t chunk_begin,
+                                 int64_t chunk_end, int64_t rec_begin, int64_t rec_end,
+                                 void *stream);
+/* y = A u on a strip partition with the interface exchange overlapped with the local apply
+ * ("overlap with interior-element compute by processing interface elements
+ * first"): the plan's patch sequence must start with the boundary tile columns, patches
+ * [0, bnd_patch_end) with interface prefixes bnd_chunk_end / bnd_rec_end; they run first,
+ * the exchange (semk_halo_exchange_f64, a 128-thread variant) runs on a high-priority side
+ * stream while `stream` works through the remaining patches, then the streams join.
+ * Advances halo->epoch.  dirichlet: device uint8 [n_nodes] or NULL. */
+int semk_poisson_apply_halo_f64(const semk_op *op, const double *u, double *y, int flags,
+                                int64_t bnd_patch_end, int64_t bnd_chunk_end, int64_t bnd_rec_end,
+                                semk_halo *halo, const uint8_t *dirichlet, void *stream);
+
 /* ------------------------------------------------------------------------
  * Host-side (no GPU) multi-threaded integer tables.
  * semk_host_sc_numbering: DOFManagerSC._do_static_condensation (sem/discrete.py:314-359) +

@@ -219,6 +219,9 @@ SIGNATURES = {
     "semk_peer_close": (_I, [_P]),
     "semk_peer_free": (_I, [_P]),
     "semk_halo_exchange_f64": (_I, [_L, _L, _P, _P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P]),
+    "semk_poisson_apply_range_f64": (_I, [C.POINTER(semk_op), _P, _P, _I, _L, _L, _L, _L, _L, _L, _P]),
+    "semk_poisson_apply_halo_f64": (_I, [C.POINTER(semk_op), _P, _P, _I, _L, _L, _L,
+                                         C.POINTER(semk_halo), _P, _P]),
     "semk_host_structured_maps": (_I, [_L, _L, C.c_int32, _L, _P, C.c_int32]),
     "semk_host_sc_numbering": (_I, [_L, _L, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P,
                                     C.c_int32, _L, C.POINTER(_L), C.POINTER(_L), _P, C.c_int32]),

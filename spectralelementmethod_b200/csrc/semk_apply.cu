@@ -908,6 +908,37 @@ extern "C" int semk_poisson_apply_f64(const semk_op *op, const double *u, double
   return SEMK_OK;
 }
 
+// A sub-range of the apply: patches [patch_begin, patch_end) and the interface entries
+// [chunk_begin, chunk_end) / [rec_begin, rec_end) (both tables are sorted by the highest
+// patch involved, so "everything patches [0, P) complete" is a prefix of each).
+extern "C" int semk_poisson_apply_range_f64(const semk_op *op, const double *u, double *y,
+                                            int flags, int64_t patch_begin, int64_t patch_end,
+                                            int64_t chunk_begin, int64_t chunk_end,
+                                            int64_t rec_begin, int64_t rec_end, void *stream) {
+  int rc = check_op(op, "semk_poisson_apply_range_f64");
+  if (rc != SEMK_OK) return rc;
+  SEMK_REQUIRE(u && y && u != y && op->G && op->D_host,
+               "semk_poisson_apply_range_f64: bad arguments");
+  SEMK_REQUIRE(0 <= patch_begin && patch_begin <= patch_end && patch_end <= op->n_patch &&
+                   0 <= chunk_begin && chunk_begin <= chunk_end &&
+                   chunk_end <= op->n_shared_chunk && 0 <= rec_begin && rec_begin <= rec_end &&
+                   rec_end <= op->n_shared,
+               "semk_poisson_apply_range_f64: range outside the operator");
+  cudaStream_t st = semk_stream(stream);
+  DMatEO dm;
+  if (!make_dmat_eo(op->n1, op->D_host, &dm)) {
+    semk_set_error("semk_poisson_apply_range_f64: D is not centro-antisymmetric");
+    return SEMK_ERR_UNSUPPORTED;
+  }
+  if (patch_end > patch_begin) {
+    rc = launch_patch<MODE_APPLY>(*op, dm, u, nullptr, y, flags, 0.0, nullptr, st, nullptr,
+                                  patch_begin, patch_end);
+    if (rc != SEMK_OK) return rc;
+  }
+  const InterfaceRange r{chunk_begin, chunk_end, rec_begin, rec_end};
+  return launch_interface<MODE_APPLY>(*op, u, y, flags, 0.0, nullptr, 0, st, nullptr, &r);
+}
+
 extern "C" int semk_assemble_f64(const semk_op *op, const double *loc, double *out, int flags,
                                  double fill_dirichlet, void *stream) {
   int rc = check_op(op, "semk_assemble_f64");

@@ -34,6 +34,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 }
 
 constexpr int kHaloThreads = 1024;
+thread_local bool g_light_exchange = false;   // set around the call by semk_poisson_apply_halo_f64
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s of SM clock
 
 struct HaloSide {
@@ -48,7 +49,14 @@ struct HaloSide {
   int subtract_dup;                // 1: this rank does not own the column (take u^2 out of dot)
 };
 
-__global__ void __launch_bounds__(kHaloThreads)
+// LIGHT = the variant that runs on a side stream NEXT TO the persistent apply kernel: 128
+// threads and <= 32 registers, so that it fits into what three resident apply CTAs leave
+// free on an SM (4096 registers, ~5 KB of shared memory) and does not have to wait for one
+// of them to retire.
+constexpr int kHaloLightThreads = 128;
+
+template <bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? kHaloLightThreads : kHaloThreads, LIGHT ? 16 : 1)
     halo_exchange_kernel(HaloSide left, HaloSide right, int64_t n, unsigned long long epoch,
                          double *__restrict__ dot_inout, int *__restrict__ status) {
   const HaloSide &S = blockIdx.x == 0 ? left : right;
@@ -174,9 +182,66 @@ extern "C" int semk_halo_exchange_f64(int64_t n_col, int64_t n_local, double *y,
     R.subtract_dup = 1;
   }
   if (!L.active && !R.active) return SEMK_OK;
-  halo_exchange_kernel<<<2, kHaloThreads, 0, semk_stream(stream)>>>(
-      L, R, n_col, (unsigned long long)epoch, dot_inout, status);
+  if (g_light_exchange)
+    halo_exchange_kernel<true><<<2, kHaloLightThreads, 0, semk_stream(stream)>>>(
+        L, R, n_col, (unsigned long long)epoch, dot_inout, status);
+  else
+    halo_exchange_kernel<false><<<2, kHaloThreads, 0, semk_stream(stream)>>>(
+        L, R, n_col, (unsigned long long)epoch, dot_inout, status);
   SEMK_LAUNCH_CHECK("halo_exchange_kernel");
+  return SEMK_OK;
+}
+
+// y = A u on a strip partition with the interface exchange OVERLAPPED with the bulk of the
+// local apply.  The plan's patch sequence starts with the two boundary tile columns
+// (patches [0, bnd_patch_end); their interface entries are the prefixes [0, bnd_chunk_end)
+// / [0, bnd_rec_end) of the interface tables): they run on a high-priority side stream,
+// followed there by the exchange kernel -- push, publish, wait for the neighbour, add --
+// while the caller's stream works through the remaining patches, and the two streams join.
+// A neighbour may now be late by almost a whole apply before anybody waits for it.
+// halo->epoch is advanced.  No fused dot (use semk_poisson_apply_f64 +
+// semk_halo_exchange_f64 when u.y is needed).
+extern "C" int semk_poisson_apply_halo_f64(const semk_op *op, const double *u, double *y,
+                                           int flags, int64_t bnd_patch_end,
+                                           int64_t bnd_chunk_end, int64_t bnd_rec_end,
+                                           semk_halo *halo, const uint8_t *dirichlet,
+                                           void *stream) {
+  SEMK_REQUIRE(op && halo && u && y, "semk_poisson_apply_halo_f64: null pointer");
+  struct Side {
+    cudaStream_t s = nullptr;
+    cudaEvent_t a = nullptr, x = nullptr;
+  };
+  thread_local Side side;
+  if (!side.s) {
+    int lo = 0, hi = 0;
+    SEMK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SEMK_CUDA_CHECK(cudaStreamCreateWithPriority(&side.s, cudaStreamNonBlocking, hi));
+    SEMK_CUDA_CHECK(cudaEventCreateWithFlags(&side.a, cudaEventDisableTiming));
+    SEMK_CUDA_CHECK(cudaEventCreateWithFlags(&side.x, cudaEventDisableTiming));
+  }
+  cudaStream_t st = semk_stream(stream);
+  // the side stream starts after whatever the caller queued on `stream` (u ready, y free)
+  SEMK_CUDA_CHECK(cudaEventRecord(side.a, st));
+  SEMK_CUDA_CHECK(cudaStreamWaitEvent(side.s, side.a, 0));
+  // boundary tile columns + the interface entries they complete, then the exchange, all on
+  // the high-priority side stream; submitted FIRST so that their CTAs are placed before the
+  // persistent kernel of the interior patches fills the remaining slots
+  int rc = semk_poisson_apply_range_f64(op, u, y, flags, 0, bnd_patch_end, 0, bnd_chunk_end, 0,
+                                        bnd_rec_end, side.s);
+  if (rc != SEMK_OK) return rc;
+  halo->epoch += 1;
+  g_light_exchange = true;
+  rc = semk_halo_exchange_f64(halo->n_col, op->n_nodes, y, u, dirichlet, halo->mine, halo->left,
+                              halo->right, halo->epoch, nullptr, halo->status, side.s);
+  g_light_exchange = false;
+  if (rc != SEMK_OK) return rc;
+  SEMK_CUDA_CHECK(cudaEventRecord(side.x, side.s));
+  // interior patches on the caller's stream, concurrently (disjoint patches, slots and
+  // result nodes)
+  rc = semk_poisson_apply_range_f64(op, u, y, flags, bnd_patch_end, op->n_patch, bnd_chunk_end,
+                                    op->n_shared_chunk, bnd_rec_end, op->n_shared, stream);
+  if (rc != SEMK_OK) return rc;
+  SEMK_CUDA_CHECK(cudaStreamWaitEvent(st, side.x, 0));
   return SEMK_OK;
 }
 

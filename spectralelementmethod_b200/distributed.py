@@ -307,9 +307,13 @@ class DistributedOperator(object):
     """
 
     def __init__(self, part, local_apply, dirichlet=None, group=None, device=None, halo=None,
-                 dot=None):
+                 dot=None, overlap=None):
         self.part = part
         self.local_apply = local_apply
+        # overlap(u, out) -> out: local apply + peer exchange in one native call with the
+        # exchange hidden behind the interior patches (semk_poisson_apply_halo_f64); used
+        # whenever no fused dot is requested
+        self.overlap = overlap
         self._dot = dot               # dot(a, b, out): the C-ABI reduction (PCGKernels.dot)
         self.group = group
         self.device = device
@@ -364,6 +368,8 @@ class DistributedOperator(object):
         """y = A_global u on this rank's nodes.  ``dot_out`` (1-element
         tensor) receives this rank's share of u.y; all-reduce it for the
         global value."""
+        if self.overlap is not None and dot_out is None and self.halo is not None:
+            return self.overlap(u, out, self._dir_u8)
         y = self.local_apply(u, out, dot_out)
         if self.halo is not None:
             return self.halo.exchange(y, u, self._dir_u8, dot_out)
@@ -597,7 +603,8 @@ class DistributedPoisson(object):
     configurations (BASELINE.json configs[4]): local mesh + DOF manager +
     device operator on each rank, interface exchange, global Jacobi-PCG."""
 
-    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None, exchange="auto"):
+    def __init__(self, part, order, kind="S", group=None, elems_per_patch=None, exchange="auto",
+                 overlap=True):
         from . import discrete
         from .basis_functions import LagrangeGaussLobatto, TensorProductQS
         from .operators import PCGKernels
@@ -607,7 +614,8 @@ class DistributedPoisson(object):
         b1 = LagrangeGaussLobatto(order)
         self.mngr = discrete.DOFManager(self.mesh, 1, TensorProductQS(b1, b1), rcm_order=False)
         self.on_ebc = self.mngr.boundary_node_mask("ebc")
-        self.op = self.mngr.poisson_operator(dirichlet=self.on_ebc, elems_per_patch=elems_per_patch)
+        self.op = self.mngr.poisson_operator(dirichlet=self.on_ebc, elems_per_patch=elems_per_patch,
+                                             boundary_columns_first=overlap)
         self.kernels = PCGKernels(self.op)
         op = self.op
         if exchange not in ("auto", "peer", "nccl"):
@@ -623,10 +631,24 @@ class DistributedPoisson(object):
                     raise
                 self.halo = None
         self.exchange = "peer" if self.halo is not None else "nccl"
+        split = op.boundary_split() if (overlap and self.halo is not None) else None
+        self.overlapped = split is not None
+        fn = None
+        if split is not None:
+            import ctypes as C
+            from . import _lib, device as _dev
+            lib, halo = _lib.load(), self.halo
+
+            def fn(u, out, dir_u8):
+                y = op.new_vector() if out is None else out
+                _lib.check(lib.semk_poisson_apply_halo_f64(
+                    C.byref(op._op), _dev.ptr(u), _dev.ptr(y), int(op._masked_flags), split[0],
+                    split[1], split[2], C.byref(halo.c), _dev.ptr(dir_u8), _dev.stream_ptr()))
+                return y
         self.dop = DistributedOperator(
             part, lambda u, out, dot: op.apply(u, out=out, dot_out=dot),
             dirichlet=self.on_ebc if op.has_dirichlet else None, group=group, device=op.dev,
-            halo=self.halo, dot=self.kernels.dot)
+            halo=self.halo, dot=self.kernels.dot, overlap=fn)
         self._mask = op.dirichlet_dev.bool() if op.has_dirichlet else None
         self._dinv = None
 

@@ -101,11 +101,14 @@ def _morton_order(cx, cy):
     return np.argsort(key, kind="stable").astype(np.int64)
 
 
-def default_element_order(mesh, elems_per_patch, tile=None):
+def default_element_order(mesh, elems_per_patch, tile=None, boundary_columns_first=False):
     """Engine slot order (slot -> element) that makes consecutive runs of
     ``elems_per_patch`` elements compact patches: tiles of a structured grid
     when the mesh builder recorded one, else a Morton curve through the cell
-    centroids."""
+    centroids.  ``boundary_columns_first`` (structured meshes): the first and the last tile
+    column come first in the patch sequence -- the columns a strip partition shares with its
+    neighbours are then final after the first 2 * (tiles per column) patches, and their
+    exchange overlaps the rest of the apply (semk_poisson_apply_halo_f64)."""
     shape = getattr(mesh, "_structured_shape", None)
     if shape is not None and shape[0] * shape[1] == mesh.n_cells:
         nx, ny = shape
@@ -116,7 +119,13 @@ def default_element_order(mesh, elems_per_patch, tile=None):
         # tiles enumerated along the contiguous node direction: the resident CTAs work
         # on a compact window of the mesh at any time (best DRAM / L2 locality)
         ntx, nty = (nx + bx - 1) // bx, (ny + by - 1) // by
-        tile_id = (ex // bx) * nty + ey // by
+        col = ex // bx
+        if boundary_columns_first and ntx > 2:
+            rank = np.empty(ntx, dtype=np.int64)
+            rank[0], rank[ntx - 1] = 0, 1
+            rank[1:ntx - 1] = np.arange(2, ntx)
+            col = rank[col]
+        tile_id = col * nty + ey // by
         key = tile_id * (bx * by) + (ex % bx) * by + ey % by
         if nx % bx == 0 and ny % by == 0:
             return np.argsort(key, kind="stable").astype(np.int64)
@@ -155,7 +164,8 @@ class PCGInfo(object):
 
 class PoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, elems_per_patch=None,
-                 elem_order=None, keep_l2g=True, tile=None, weight=None, mode="auto"):
+                 elem_order=None, keep_l2g=True, tile=None, weight=None, mode="auto",
+                 boundary_columns_first=False):
         _lib.require_device()
         self._lib = _lib.load()
         mesh = dof_mngr.mesh
@@ -178,7 +188,10 @@ class PoissonOperator(object):
         pe = self.elems_per_patch = int(elems_per_patch or choose_elems_per_patch(n1))
         user_order = elem_order is not None
         if elem_order is None:
-            elem_order = default_element_order(mesh, pe, tile)
+            elem_order = default_element_order(mesh, pe, tile, boundary_columns_first)
+        self._tile = tuple(tile) if tile is not None else _TILES[pe]
+        self._boundary_first = bool(boundary_columns_first and not user_order and getattr(
+            mesh, "_structured_shape", None) is not None)
         sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
         # engine slots = elements + empty padding slots (-1 entries of the order)
         self.n_order = int(ar[_lib.PA_ELEM_OF_SLOT].size)
@@ -401,6 +414,32 @@ class PoissonOperator(object):
             arr[i].y_final = self.n_nodes if last else int(open_from[pe])
         self._stage_cache[n_stages] = (arr, n_stages)
         return self._stage_cache[n_stages]
+
+    def boundary_split(self):
+        """(patch_end, chunk_end, rec_end) of the two boundary tile columns of a structured
+        mesh whose plan was built with ``boundary_columns_first``: the patches that touch the
+        first / last node column and the prefixes of the interface tables they complete.
+        None when the plan has no such prefix."""
+        if not getattr(self, "_boundary_first", False):
+            return None
+        shape = getattr(self.dof_mngr.mesh, "_structured_shape", None)
+        bx, by = self._tile
+        ntx, nty = -(-shape[0] // bx), -(-shape[1] // by)
+        if ntx <= 2:
+            return None
+        pe = 2 * nty
+        _pmin, _pmax, cmax, rmax = self._stage_info
+        return (int(pe), int(np.searchsorted(cmax, pe, side="left")),
+                int(np.searchsorted(rmax, pe, side="left")))
+
+    def apply_range(self, u, y, pb, pe, cb, ce, rb, re, flags=None):
+        """Patches [pb, pe) and interface entries [cb, ce) / [rb, re) of the apply."""
+        if flags is None:
+            flags = self._masked_flags
+        _lib.check(self._lib.semk_poisson_apply_range_f64(
+            C.byref(self._op), device.ptr(u), device.ptr(y), int(flags), int(pb), int(pe), int(cb),
+            int(ce), int(rb), int(re), device.stream_ptr()))
+        return y
 
     def apply_host(self, u_host, y_host, scratch=None, stages=16):
         """End-to-end call on HOST buffers (numpy float64 or pinned torch CPU

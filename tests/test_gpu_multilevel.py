@@ -22,6 +22,10 @@ pytestmark = pytest.mark.gpu
 SC_CASES = [n for n in golden_case_names() if "_sc" in n]
 
 
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
 def host(t):
     return t.detach().cpu().numpy()
 
@@ -248,6 +252,59 @@ def test_halo_exchange_kernel_self_exchange(with_dirichlet):
             assert int(status.item()) == 0
             assert np.array_equal(host(y), want)         # one add per node: exact
             assert abs(float(dot.item()) - (5.0 - dup)) <= 1e-12 * max(1.0, dup)
+    finally:
+        torch.cuda.synchronize()
+        _lib.check(lib.semk_peer_free(region))
+
+
+@pytest.mark.parametrize("nx,ny,p", [(12, 24, 8), (13, 9, 4), (6, 16, 5)])
+def test_overlapped_apply_and_exchange_on_one_gpu(nx, ny, p):
+    """semk_poisson_apply_halo_f64 on ONE GPU: boundary tile columns first, the light exchange
+    kernel on the side stream with the rank as its own left and right neighbour (a periodic
+    strip), interior patches meanwhile.  Must equal the serial sequence apply -> exchange
+    bit for bit, and the range-split apply must equal the one-launch apply."""
+    lib = _lib.load()
+    mesh, mngr = build_package_case("C", nx, ny, p, False, False)
+    on = mngr.boundary_node_mask("ebc")
+    op = mngr.poisson_operator(dirichlet=on, boundary_columns_first=True)
+    ref = mngr.poisson_operator(dirichlet=on)
+    split = op.boundary_split()
+    assert split is not None and 0 < split[0] < op.n_patch
+    rng = np.random.default_rng(11)
+    u = dev(rng.standard_normal(op.n_nodes))
+    y_one = op.apply(u)
+    # another element order only reorders the 3- and 4-term sums at tile corners
+    assert rel_l2(host(y_one), host(ref.apply(u))) < 1e-14
+    y_two = op.new_vector(0.0)
+    op.apply_range(u, y_two, 0, split[0], 0, split[1], 0, split[2])
+    op.apply_range(u, y_two, split[0], op.n_patch, split[1], op._op.n_shared_chunk, split[2],
+                   op._op.n_shared)
+    assert torch.equal(y_two, y_one)
+    n_col = ny * p + 1
+    region = C.c_void_p()
+    handle = (C.c_ubyte * 64)()
+    _lib.check(lib.semk_peer_alloc(int(lib.semk_halo_region_bytes(n_col)), C.byref(region), handle))
+    try:
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        halo = _lib.semk_halo()
+        halo.n_col, halo.mine, halo.left, halo.right = n_col, region, region, region
+        halo.epoch, halo.status = 0, status.data_ptr()
+        m = torch.from_numpy(on.astype(np.uint8)).cuda()
+        stream = torch.cuda.current_stream().cuda_stream
+        for rep in range(3):
+            y = op.new_vector()
+            _lib.check(lib.semk_poisson_apply_halo_f64(
+                C.byref(op._op), u.data_ptr(), y.data_ptr(), int(op._masked_flags), split[0],
+                split[1], split[2], C.byref(halo), m.data_ptr(), stream))
+            torch.cuda.synchronize()
+            assert int(status.item()) == 0 and halo.epoch == 2 * rep + 1
+            want = y_one.clone()
+            halo.epoch += 1
+            _lib.check(lib.semk_halo_exchange_f64(
+                n_col, op.n_nodes, want.data_ptr(), u.data_ptr(), m.data_ptr(), region, region,
+                region, halo.epoch, None, status.data_ptr(), stream))
+            torch.cuda.synchronize()
+            assert torch.equal(y, want)
     finally:
         torch.cuda.synchronize()
         _lib.check(lib.semk_peer_free(region))
