@@ -662,7 +662,7 @@ def run_engine(args):
     traffic, traffic_src = None, None
     if (not multi and op.n_elem == 1024 * 1024 and op.elems_per_patch == 16 and not args.tile
             and args.kind == "S"):
-        traffic, traffic_src = committed_traffic("traffic.json", ["semk_apply.cu"])
+        traffic, traffic_src = committed_traffic("traffic.json", ["semk_apply.cu", "semk_elem.cuh"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_kind,
