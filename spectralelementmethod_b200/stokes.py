@@ -30,7 +30,8 @@ import torch
 from . import _lib, device
 from .operators import PoissonOperator, _TILES
 
-__all__ = ["AxisymmetricStokesOperator", "GMRESInfo", "squirmer_boundary_data",
+__all__ = ["AxisymmetricStokesOperator", "GMRESInfo", "PoissonBlockPreconditioner",
+           "squirmer_boundary_data",
            "sfn_potential", "sfn_free_stream", "squirmer_vslip_profile", "zero_slip_vel"]
 
 N_FAC_STOKES, N_FAC_ADV = 7, 12
@@ -265,6 +266,7 @@ class AxisymmetricStokesOperator(object):
             device.ptr(loc[0]), device.ptr(loc[1]), device.ptr(loc[2]), device.ptr(loc[3]),
             device.stream_ptr()))
         dL, dE, dM, dA = (po.assemble(l) for l in loc)
+        self._diagonals = (dL, dE, dM, dA)
         ess = torch.zeros(self.n_dof, dtype=torch.bool, device=self.dev)
         if self._sop.n_ess:
             ess[self._ess_dev] = True
@@ -283,10 +285,20 @@ class AxisymmetricStokesOperator(object):
         self._binv = binv.contiguous()
         return self._binv
 
+    def block_jacobi_diagonals(self):
+        """Assembled nodal diagonals (Lve, E2e, Me, advection) behind ``block_jacobi``."""
+        self.block_jacobi()
+        if getattr(self, "_diagonals", None) is None:
+            self._binv = None
+            self.block_jacobi()
+        return self._diagonals
+
     # -- restarted GMRES (right preconditioned, CGS2 orthogonalisation) -------------------
     def solve_gmres(self, b, x0=None, rtol=1e-10, restart=60, maxiter=2000, precondition=True):
         """Solve Jhat x = b for the unknown DOFs (essential entries of x stay at x0's, b's
-        essential entries are ignored).  Replaces the sparse direct solve of the Schur
+        essential entries are ignored).  precondition: True = nodal 2x2 block-Jacobi, False =
+        none, "poisson" = PoissonBlockPreconditioner (Re = 0, DOFManagerSC), or a callable
+        ``(src, dst)``.  Replaces the sparse direct solve of the Schur
         system (examples/squirmer-axisymmetric.py:360-370).  Returns (x, GMRESInfo)."""
         self._vec(b, "b")
         lib, n = self._lib, self.n_dof
@@ -295,11 +307,20 @@ class AxisymmetricStokesOperator(object):
         f64 = dict(dtype=torch.float64, device=self.dev)
         V = torch.empty((m + 1, n), **f64)
         w, z = self.new_vector(), self.new_vector()
+        # a preconditioner that contains iterative solves is not one fixed linear operator:
+        # FLEXIBLE GMRES keeps z_j = P^-1 v_j, so that x = sum_j y_j z_j satisfies the Arnoldi
+        # relation A z_j = V h_j exactly and the recurrence residual is the true one
+        flexible = callable(precondition) or precondition == "poisson"
+        Z = torch.empty((m, n), **f64) if flexible else None
         x = torch.zeros(n, **f64) if x0 is None else self._vec(x0, "x0").clone()
         bb = self._fix(b.clone())
         hdev = torch.empty(m + 2, **f64)
         partials = torch.empty(int(lib.semk_multi_dot_partials_len(m + 2)), **f64)
-        binv = self.block_jacobi() if precondition else None
+        custom = precondition if callable(precondition) else None
+        if precondition == "poisson":
+            custom = self._poisson_prec = (getattr(self, "_poisson_prec", None)
+                                           or PoissonBlockPreconditioner(self))
+        binv = self.block_jacobi() if (precondition and custom is None) else None
 
         def dots(k, vec):
             _lib.check(lib.semk_multi_dot_f64(n, k, device.ptr(V), n, device.ptr(vec),
@@ -312,7 +333,9 @@ class AxisymmetricStokesOperator(object):
             return math.sqrt(max(float(hdev[0].item()), 0.0))
 
         def precond(src, dst):
-            if binv is None:
+            if custom is not None:
+                custom(src, dst)
+            elif binv is None:
                 dst.copy_(src)
             else:
                 _lib.check(lib.semk_block2_apply_f64(self.n_nodes, device.ptr(binv),
@@ -324,8 +347,13 @@ class AxisymmetricStokesOperator(object):
             return x, GMRESInfo(0, 0, True, 0.0, 0.0)
         total, restarts, rel = 0, 0, 1.0
         converged = False
-        while total < maxiter and not converged:
-            # r = b - Jhat x on the unknowns (x's essential entries do not enter: masked)
+        last_true = float("inf")
+        while total < maxiter:
+            # TRUE residual r = b - Jhat x on the unknowns at the start of every cycle (x's
+            # essential entries do not enter: masked).  A cycle that ended on the recurrence
+            # residual is only accepted when the true residual agrees (iterative refinement:
+            # the next cycle solves for the correction); if a cycle no longer halves the true
+            # residual the attainable accuracy of the system has been reached
             xm = self._fix(x.clone())
             self._apply_raw(xm, w, True)
             _lib.check(lib.semk_vec_scale_add_f64(n, -1.0, device.ptr(w), device.ptr(bb),
@@ -335,6 +363,9 @@ class AxisymmetricStokesOperator(object):
             if rel <= rtol:
                 converged = True
                 break
+            if rel > 0.5 * last_true:
+                break
+            last_true = rel
             _lib.check(lib.semk_vec_scale_add_f64(n, 1.0 / beta, device.ptr(V[0]), None,
                                                   device.ptr(V[0]), st()))
             H = np.zeros((m + 1, m))
@@ -343,8 +374,9 @@ class AxisymmetricStokesOperator(object):
             g[0] = beta
             k_used = 0
             for j in range(m):
-                precond(V[j], z)
-                self._apply_raw(z, V[j + 1], True)
+                zj = Z[j] if flexible else z
+                precond(V[j], zj)
+                self._apply_raw(zj, V[j + 1], True)
                 h = dots(j + 1, V[j + 1]).copy()
                 _lib.check(lib.semk_multi_axpy_f64(n, j + 1, device.ptr(V), n, device.ptr(hdev),
                                                    -1.0, device.ptr(V[j + 1]), st()))
@@ -376,15 +408,17 @@ class AxisymmetricStokesOperator(object):
                                                       device.ptr(V[j + 1]), st()))
             yk = np.linalg.solve(np.triu(H[:k_used, :k_used]), g[:k_used])
             hdev[:k_used] = torch.from_numpy(yk).to(self.dev)
-            w.zero_()
-            _lib.check(lib.semk_multi_axpy_f64(n, k_used, device.ptr(V), n, device.ptr(hdev), 1.0,
-                                               device.ptr(w), st()))
-            precond(w, z)
-            _lib.check(lib.semk_vec_scale_add_f64(n, 1.0, device.ptr(z), device.ptr(x),
-                                                  device.ptr(x), st()))
+            if flexible:
+                _lib.check(lib.semk_multi_axpy_f64(n, k_used, device.ptr(Z), n, device.ptr(hdev),
+                                                   1.0, device.ptr(x), st()))
+            else:
+                w.zero_()
+                _lib.check(lib.semk_multi_axpy_f64(n, k_used, device.ptr(V), n, device.ptr(hdev),
+                                                   1.0, device.ptr(w), st()))
+                precond(w, z)
+                _lib.check(lib.semk_vec_scale_add_f64(n, 1.0, device.ptr(z), device.ptr(x),
+                                                      device.ptr(x), st()))
             restarts += 1
-            if rel <= rtol:
-                converged = True
         # true residual of the returned iterate
         xm = self._fix(x.clone())
         self._apply_raw(xm, w, True)
@@ -395,7 +429,8 @@ class AxisymmetricStokesOperator(object):
 
     # -- Newton driver -----------------------------------------------------------------
     def newton_solve(self, state0, cint=None, it_max=10, tol=1e-6, max_n_diverge=3,
-                     gmres_rtol=1e-10, restart=60, gmres_maxiter=4000, verbose=False):
+                     gmres_rtol=1e-10, restart=60, gmres_maxiter=4000, verbose=False,
+                     precondition=True):
         """Newton-Raphson of examples/squirmer-axisymmetric.py:389-457 with the Schur /
         SuperLU step replaced by GMRES on the matrix-free Jacobian.  state0 holds the
         initial guess with the essential values in place; cint: natural-BC contour
@@ -414,7 +449,7 @@ class AxisymmetricStokesOperator(object):
             res = self.residual(state)
             rhs = c - res
             d, info = self.solve_gmres(rhs, rtol=gmres_rtol, restart=restart,
-                                       maxiter=gmres_maxiter)
+                                       maxiter=gmres_maxiter, precondition=precondition)
             self._fix(d)
             state += d
             du = float(torch.linalg.vector_norm(d[1::2]).item())
@@ -447,6 +482,100 @@ class AxisymmetricStokesOperator(object):
             e[j] = 0.0
             cols.append(sparse.csc_matrix(y.cpu().numpy().reshape(-1, 1)))
         return sparse.hstack(cols).tocsr()
+
+
+class PoissonBlockPreconditioner(object):
+    """Block-triangular preconditioner of the Stokes (Re = 0) system from ONE weighted Poisson
+    operator, for right-preconditioned GMRES (mesh-independent iteration counts in the CPU
+    study oracle/precond_study_stokes.py: 72-121 iterations from 345 to 24 257 DOF).
+
+    With I = nodes where the stream function is unknown, G = nodes where it is essential but
+    the vorticity is not (the sphere), rows wte (L om = a) paired with om_I and rows wdef
+    (E psi - M om = b) paired with psi_I / om_G:
+        om_G = -b_G / M_G
+        om_I = Khat^-1 (a - L_IG om_G)
+        psi  = Khat^-1 (b_I + M_I om_I)
+    Khat = the rho-weighted stiffness with Dirichlet rows on every psi-essential node: the
+    statically condensed operator of section 7 row 1 (``condensed_poisson_operator(weight=
+    rho)``) solved by the native multilevel PCG driver to ``rtol`` (the composition amplifies
+    inner errors, so the inner solves are accurate and the outer method is plain GMRES).
+    Needs a ``DOFManagerSC`` (exterior-first numbering) built with ``rcm_order=False``.
+    The glue between the solves (strided copies, masks, scalings) is torch elementwise code;
+    the applies, element passes and PCG loops are the C-ABI kernels."""
+
+    def __init__(self, op, rtol=1e-10, preconditioner="three-level"):
+        from . import discrete
+        if op.advection:
+            raise NotImplementedError("the Poisson block preconditioner is built for Re = 0")
+        dm = op.dof_mngr
+        mesh = dm.mesh
+        if not getattr(mesh, "condensed", False):
+            raise ValueError("needs the exterior-first numbering of DOFManagerSC")
+        if op.essential_host is None:
+            raise ValueError("set the essential DOFs first (set_essential)")
+        ess_s, ess_w = op.essential_host[0::2], op.essential_host[1::2]
+        if (ess_w & ~ess_s).any():
+            raise NotImplementedError("vorticity essential where the stream function is free")
+        self.op, self.rtol, self.kind = op, float(rtol), preconditioner
+        before = mesh.node_map_array().copy()
+        sdm = discrete.DOFManagerSC(mesh, 1, dm._basis, rcm_order=False)
+        if not np.array_equal(before, mesh.node_map_array()):
+            raise AssertionError("the scalar manager renumbered the mesh: build the Stokes "
+                                 "manager as DOFManagerSC(mesh, 2, basis, rcm_order=False)")
+        self.sc = sdm.condensed_poisson_operator(dirichlet=ess_s, weight=lambda x, y: x)
+        dev = op.dev
+        self.free_s = torch.from_numpy(~ess_s).to(dev)                 # I
+        self.gamma = torch.from_numpy(ess_s & ~ess_w).to(dev)          # G
+        self.n_ext = self.sc.n_ext
+        # lumped element-interior weights: f_nodal = r / JxW reproduces the interior load r
+        # (interior nodes are private to their element), 0 on exterior nodes
+        mass = op._po.assemble(self._local_jxw(op))
+        inv = torch.zeros_like(mass)
+        inv[self.n_ext:] = 1.0 / mass[self.n_ext:]
+        self.inv_mass_int = inv
+        dM = op.block_jacobi_diagonals()[2]
+        self.M = dM
+        self.neg_inv_M_gamma = torch.where(self.gamma, -1.0 / dM, torch.zeros_like(dM))
+        self.solves = 0
+        self.inner_outer_iterations = 0
+
+    @staticmethod
+    def _local_jxw(op):
+        """JxW in engine slot order (zeros in the empty padding slots)."""
+        po = op._po
+        NN = op.n1 * op.n1
+        loc = torch.zeros((po.n_slot_elems, NN), dtype=torch.float64, device=op.dev)
+        eos = po._tables[_lib.PA_ELEM_OF_SLOT]
+        ok = eos >= 0
+        loc[:eos.numel()][ok] = po.JxW[eos[ok]]
+        return loc
+
+    def poisson_solve(self, r):
+        """u = Khat^-1 r for a nodal residual r (zero on the Dirichlet nodes)."""
+        sc = self.sc
+        f = r * self.inv_mass_int
+        g = sc.rhs(f)
+        g += r[:self.n_ext]
+        b = sc.lift(g, None)
+        x, info = sc.solve_pcg(b, rtol=self.rtol, preconditioner=self.kind)
+        self.solves += 1
+        self.inner_outer_iterations += info.iterations
+        return sc.backsolve(x, f)
+
+    def __call__(self, src, dst):
+        op = self.op
+        a, b = src[0::2], src[1::2]
+        om = b * self.neg_inv_M_gamma                       # om_G (zero elsewhere)
+        t = op.new_vector(0.0)
+        t[1::2] = om
+        y = op.apply_unmasked(t)                            # row 0 = L om_G
+        r1 = torch.where(self.free_s, a - y[0::2], torch.zeros_like(a)).contiguous()
+        om_i = self.poisson_solve(r1)
+        r2 = torch.where(self.free_s, b + self.M * om_i, torch.zeros_like(b)).contiguous()
+        psi = self.poisson_solve(r2)
+        dst[0::2] = torch.where(self.free_s, psi, torch.zeros_like(psi))
+        dst[1::2] = torch.where(self.free_s, om_i, om)
+        return dst
 
 
 # --------------------------------------------------------------------------------------

@@ -23,7 +23,9 @@ def main():
     t0 = time.perf_counter()
     mesh = meshgen.annulus_sector_mesh(nr, nt, p, 100.0)
     b1 = LagrangeGaussLobatto(p)
-    dm = discrete.DOFManager(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
+    prec = a[7] if len(a) > 7 else "block-jacobi"
+    mgr = discrete.DOFManagerSC if prec == "poisson" else discrete.DOFManager
+    dm = mgr(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
     op = dm.axisymmetric_stokes_operator(n_rey=n_rey, elems_per_patch=pe)
     torch.cuda.synchronize()
     setup = time.perf_counter() - t0
@@ -61,12 +63,19 @@ def main():
         rhs = op.from_host(bc.cint) - op.residual(s0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        d, info = op.solve_gmres(rhs, rtol=1e-8, restart=min(gm, 100), maxiter=gm)
+        if prec == "poisson" and len(a) > 8:
+            op._poisson_prec = stokes.PoissonBlockPreconditioner(op, rtol=float(a[8]))
+        d, info = op.solve_gmres(rhs, rtol=1e-8, restart=min(gm, 300), maxiter=gm,
+                                 precondition="poisson" if prec == "poisson" else True)
         torch.cuda.synchronize()
         out["gmres"] = {"seconds": time.perf_counter() - t0, "iterations": info.iterations,
                         "restarts": info.restarts, "converged": info.converged,
                         "rel_residual": info.rel_residual,
-                        "true_rel_residual": info.true_rel_residual}
+                        "true_rel_residual": info.true_rel_residual, "preconditioner": prec}
+        pp = getattr(op, "_poisson_prec", None)
+        if pp is not None:
+            out["gmres"]["poisson_solves"] = pp.solves
+            out["gmres"]["poisson_outer_iterations"] = pp.inner_outer_iterations
     print(json.dumps(out))
 
 
