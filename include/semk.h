@@ -466,6 +466,17 @@ int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem, con
                         const double *f_nodal, double f_scale, int mode, double *S_out,
                         int64_t s_stride, double *sdiag_loc, double *g_loc, double *u,
                         double *W_out, double *c_out, int32_t *bad_flag, void *stream);
+/* The same with a nodal reaction term: the local matrix is the stiffness of the recipe plus
+ * diag(react[e][k]) (react: device [n_elem][NN], reference element order, or NULL).  Used for
+ * the vector-Laplacian block Lve = rho-weighted stiffness + JxW/rho of
+ * examples/squirmer-axisymmetric.py:210-211 inside the Stokes preconditioner. */
+int semk_sc_element_react_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem, const double *G,
+                              int64_t g_patch_stride, int elems_per_patch, const double *D,
+                              const int32_t *ext_loc, const uint32_t *l2g, const double *JxW,
+                              const double *f_nodal, double f_scale, int mode, double *S_out,
+                              int64_t s_stride, double *sdiag_loc, double *g_loc, double *u,
+                              double *W_out, double *c_out, const double *react,
+                              int32_t *bad_flag, void *stream);
 /* u_i = c - W u_e for every element (c NULL: zero load): exterior entries of u read,
  * interior entries written; W, c from semk_sc_element_f64. */
 int semk_sc_backsolve_stored_f64(int n1, int64_t n_elem, const double *W, const double *c,

@@ -182,6 +182,8 @@ SIGNATURES = {
     "semk_scale_gfactors_f64": (_I, [_I, _L, _P, _P, _P, _L, _I, _P]),
     "semk_sc_element_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L, _P,
                                  _P, _P, _P, _P, _P, _P]),
+    "semk_sc_element_react_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L,
+                                       _P, _P, _P, _P, _P, _P, _P, _P]),
     "semk_sc_backsolve_stored_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
     "semk_sc_element_dense_f64": (_I, [_I, _L, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P, _P]),
     "semk_sc_apply_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _P, _P]),

@@ -162,7 +162,7 @@ def _load_key(f):
 
 class CondensedPoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, weight=None,
-                 store_interior="auto"):
+                 store_interior="auto", reaction=None):
         """store_interior : keep W_e = A_ii^-1 A_ie of every element (12.5 KB per element at
         p = 8) so that the interior back-substitution is one streaming pass instead of a
         refactorisation per element; "auto" = when it takes less than a third of the free
@@ -170,6 +170,14 @@ class CondensedPoissonOperator(object):
         self._store_interior = store_interior
         self._init_common(dof_mngr, dirichlet)
         self._init_geometry(geometric_factors, weight)
+        # reaction : float[E, N, N] element-local nodal values c >= 0 (array or CUDA tensor):
+        # the operator becomes stiffness + diag(c), e.g. the JxW/rho term of the vector
+        # Laplacian of examples/squirmer-axisymmetric.py:210-211
+        self._react = None
+        if reaction is not None:
+            self._react = device._f64(reaction, self.dev).reshape(self.n_elem, -1).contiguous()
+            if self._react.shape[1] != self.n1 * self.n1:
+                raise ValueError("reaction must have one value per element-local node")
         self._schur_pass()
 
     def _init_common(self, dof_mngr, dirichlet):
@@ -345,13 +353,13 @@ class CondensedPoissonOperator(object):
         else:
             f_nodal = self._full_vec(self.from_host(f), "f")
         self._bad.zero_()
-        _lib.check(self._lib.semk_sc_element_f64(
+        _lib.check(self._lib.semk_sc_element_react_f64(
             self.n1, self.n_elem, None, device.ptr(self.G), self.g_stride, 1,
             device.ptr(self.tab.dev()[0]), device.ptr(self._t["ext_loc"]),
             device.ptr(self.l2g_dev), device.ptr(self.JxW), device.ptr(f_nodal), f_scale,
             int(mode), device.ptr(S), self.s_stride, device.ptr(sdiag_loc), device.ptr(g_loc),
-            device.ptr(u), device.ptr(W), device.ptr(c), device.ptr(self._bad),
-            device.stream_ptr()))
+            device.ptr(u), device.ptr(W), device.ptr(c), device.ptr(getattr(self, "_react", None)),
+            device.ptr(self._bad), device.stream_ptr()))
         if int(self._bad.item()) != 0:
             raise AssertionError("an element-interior stiffness block is not positive definite")
 

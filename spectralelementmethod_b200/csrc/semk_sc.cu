@@ -47,7 +47,7 @@ struct ScCfg {
   static constexpr int LDI = NI | 1;             // odd row strides: conflict-free columns
   static constexpr int LDZ = NE + 1;             // NE columns of A_ie + the load column
   static constexpr int kDoubles =
-      3 * NN + NN + NI * LDI + NI * LDZ + NE * NE + NI + NE + NE + NI;
+      3 * NN + NN + NN + NI * LDI + NI * LDZ + NE * NE + NI + NE + NE + NI;
   static constexpr size_t kSmem = sizeof(double) * kDoubles + sizeof(int) * (NE + 4);
   static constexpr int EPB = kScThreads / NE;    // elements per CTA step of the matvec
 };
@@ -78,6 +78,7 @@ struct ScElemArgs {
   const double *A_dense;       // [n_elem][NN][NN] or nullptr
   const double *f_dense;       // [n_elem][NN]
   const uint32_t *l2g_hier;    // [n_elem][NN] global ids in hierarchical local order
+  const double *react;         // [n_elem][NN] nodal reaction term added to the local diagonal, or nullptr
 };
 
 template <int N>
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
   extern __shared__ __align__(128) double sc_smem[];
   double *sG = sc_smem;            // [3][N][N] geometric factors G00, G01, G11
   double *sD = sG + 3 * NN;        // [N][N]
-  double *sA = sD + NN;            // [NI][LDI] interior block -> Cholesky factor (lower)
+  double *sR = sD + NN;            // [N][N] reaction (nodal diagonal) term, zeros without one
+  double *sA = sR + NN;            // [NI][LDI] interior block -> Cholesky factor (lower)
   double *sZ = sA + NI * LDI;      // [NI][LDZ] A_ie | f_i  ->  L^{-1} of both
   double *sE = sZ + NI * LDZ;      // [NE][NE] A_ee (lower part used)
   double *sInv = sE + NE * NE;     // [NI] 1 / L[i][i]
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
 #pragma unroll
       for (int n = 0; n < N; ++n)
         v = fma(sD[n * N + s] * sD[n * N + q], sG[2 * NN + p * N + n], v);
+      if (q == s) v += sR[p * N + q];
     }
     return v;
   };
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
         sG[i] = g[(c * N + m) * NP + n];
       }
       for (int i = tid; i < NN; i += kScThreads) sD[i] = a.D[i];
+      for (int i = tid; i < NN; i += kScThreads) sR[i] = a.react ? a.react[e * NN + i] : 0.0;
       for (int i = tid; i < NE; i += kScThreads) sExt[i] = a.ext_loc[i];
     }
     if (tid == 0) *sBad = 0;
@@ -594,6 +598,20 @@ extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_o
                                    int mode, double *S_out, int64_t s_stride, double *sdiag_loc,
                                    double *g_loc, double *u, double *W_out, double *c_out,
                                    int32_t *bad_flag, void *stream) {
+  return semk_sc_element_react_f64(n1, n_elem, slot_of_elem, G, g_patch_stride, elems_per_patch,
+                                   D, ext_loc, l2g, JxW, f_nodal, f_scale, mode, S_out, s_stride,
+                                   sdiag_loc, g_loc, u, W_out, c_out, nullptr, bad_flag, stream);
+}
+
+extern "C" int semk_sc_element_react_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem,
+                                         const double *G, int64_t g_patch_stride,
+                                         int elems_per_patch, const double *D,
+                                         const int32_t *ext_loc, const uint32_t *l2g,
+                                         const double *JxW, const double *f_nodal,
+                                         double f_scale, int mode, double *S_out,
+                                         int64_t s_stride, double *sdiag_loc, double *g_loc,
+                                         double *u, double *W_out, double *c_out,
+                                         const double *react, int32_t *bad_flag, void *stream) {
   SEMK_REQUIRE(n_elem > 0 && G && D && ext_loc && bad_flag &&
                    elems_per_patch > 0 && g_patch_stride > 0,
                "semk_sc_element_f64: bad argument");
@@ -637,6 +655,7 @@ extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_o
   a.A_dense = nullptr;
   a.f_dense = nullptr;
   a.l2g_hier = nullptr;
+  a.react = react;
   return launch_sc_element(n1, a, stream);
 }
 
@@ -684,6 +703,7 @@ extern "C" int semk_sc_element_dense_f64(int n1, int64_t n_elem, const double *A
   a.A_dense = A_hier;
   a.f_dense = f_hier;
   a.l2g_hier = l2g_hier;
+  a.react = nullptr;
   return launch_sc_element(n1, a, stream);
 }
 

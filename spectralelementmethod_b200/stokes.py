@@ -495,15 +495,16 @@ class PoissonBlockPreconditioner(object):
         om_G = -b_G / M_G
         om_I = Khat^-1 (a - L_IG om_G)
         psi  = Khat^-1 (b_I + M_I om_I)
-    Khat = the rho-weighted stiffness with Dirichlet rows on every psi-essential node: the
-    statically condensed operator of section 7 row 1 (``condensed_poisson_operator(weight=
-    rho)``) solved by the native multilevel PCG driver to ``rtol`` (the composition amplifies
-    inner errors, so the inner solves are accurate and the outer method is plain GMRES).
+    Khat = Lve on I (rho-weighted stiffness + the JxW/rho reaction term) with Dirichlet rows on
+    every psi-essential node: the statically condensed operator of section 7 row 1
+    (``condensed_poisson_operator(weight=rho, reaction=JxW/rho)``) solved by the native
+    multilevel PCG driver to ``rtol``; the inner solves are iterative, so the outer method is
+    FLEXIBLE GMRES and convergence is accepted on the true residual.
     Needs a ``DOFManagerSC`` (exterior-first numbering) built with ``rcm_order=False``.
     The glue between the solves (strided copies, masks, scalings) is torch elementwise code;
     the applies, element passes and PCG loops are the C-ABI kernels."""
 
-    def __init__(self, op, rtol=1e-10, preconditioner="three-level"):
+    def __init__(self, op, rtol=1e-8, preconditioner="three-level", reaction_term=True):
         from . import discrete
         if op.advection:
             raise NotImplementedError("the Poisson block preconditioner is built for Re = 0")
@@ -522,7 +523,14 @@ class PoissonBlockPreconditioner(object):
         if not np.array_equal(before, mesh.node_map_array()):
             raise AssertionError("the scalar manager renumbered the mesh: build the Stokes "
                                  "manager as DOFManagerSC(mesh, 2, basis, rcm_order=False)")
-        self.sc = sdm.condensed_poisson_operator(dirichlet=ess_s, weight=lambda x, y: x)
+        # Khat = Lve restricted to I: rho-weighted stiffness + the JxW/rho reaction term (the
+        # CPU study needs a third fewer outer iterations with it than with the bare stiffness)
+        reaction = None
+        if reaction_term:
+            rho = op.x_phys[:, 0, :]
+            reaction = torch.where(rho > 0, op.JxW / rho.clamp_min(1e-300), torch.zeros_like(rho))
+        self.sc = sdm.condensed_poisson_operator(dirichlet=ess_s, weight=lambda x, y: x,
+                                                 reaction=reaction)
         dev = op.dev
         self.free_s = torch.from_numpy(~ess_s).to(dev)                 # I
         self.gamma = torch.from_numpy(ess_s & ~ess_w).to(dev)          # G

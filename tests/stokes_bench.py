@@ -64,7 +64,8 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if prec == "poisson" and len(a) > 8:
-            op._poisson_prec = stokes.PoissonBlockPreconditioner(op, rtol=float(a[8]))
+            op._poisson_prec = stokes.PoissonBlockPreconditioner(
+                op, rtol=float(a[8]), reaction_term=(len(a) <= 9 or a[9] != "K"))
         d, info = op.solve_gmres(rhs, rtol=1e-8, restart=min(gm, 300), maxiter=gm,
                                  precondition="poisson" if prec == "poisson" else True)
         torch.cuda.synchronize()
