@@ -506,8 +506,9 @@ class PoissonBlockPreconditioner(object):
 
     def __init__(self, op, rtol=1e-8, preconditioner="three-level", reaction_term=True):
         from . import discrete
-        if op.advection:
-            raise NotImplementedError("the Poisson block preconditioner is built for Re = 0")
+        # (with advection, n_rey != 0, the same Stokes blocks precondition the linearised
+        # Navier-Stokes Jacobian: the advection terms are first order; flexible GMRES absorbs
+        # the difference at moderate Reynolds numbers)
         dm = op.dof_mngr
         mesh = dm.mesh
         if not getattr(mesh, "condensed", False):

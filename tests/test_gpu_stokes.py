@@ -222,7 +222,8 @@ def test_gmres_true_residual_and_restarts():
     assert rel_l2(host(x), xd) < 1e-7
 
 
-@pytest.mark.parametrize("name", ["fixed_344_re0", "squirmer_238_re0"])
+@pytest.mark.parametrize("name", ["fixed_344_re0", "squirmer_238_re0", "fixed_225_re1",
+                                  "squirmer_334_re05"])
 def test_poisson_block_preconditioner_reproduces_reference_solution(name):
     """GMRES with the block-triangular preconditioner built from the weighted, statically
     condensed Poisson operator (multilevel PCG inside): same solution as the reference's
@@ -234,8 +235,8 @@ def test_poisson_block_preconditioner_reproduces_reference_solution(name):
     dm = discrete.DOFManagerSC(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
     speed, slip = slip_of(g)
     bc = stokes.squirmer_boundary_data(dm, speed, slip)
-    op = dm.axisymmetric_stokes_operator(essential=bc.essential)
-    state, hist = op.newton_solve(dev(bc.state0), bc.cint, it_max=6, tol=1e-9, gmres_rtol=1e-12,
+    op = dm.axisymmetric_stokes_operator(n_rey=float(g["n_rey"]), essential=bc.essential)
+    state, hist = op.newton_solve(dev(bc.state0), bc.cint, it_max=10, tol=1e-9, gmres_rtol=1e-12,
                                   restart=300, gmres_maxiter=300, precondition="poisson")
     assert all(info.true_rel_residual < 1e-8 for _, info in hist)
     assert hist[0][1].iterations <= 200, hist[0][1]
