@@ -420,6 +420,18 @@ def run_condensed(args, nx, dev, peak):
             x2, info2 = sc.solve_pcg(b2, rtol=1e-12, preconditioner=pre)
             torch.cuda.synchronize()
             t_solve = time.perf_counter() - t0
+            refined = None
+            if pre == "three-level":
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                x3, info3, cycles = sc.solve_pcg_refined(b2, rtol=1e-12)
+                torch.cuda.synchronize()
+                refined = {"seconds": time.perf_counter() - t0,
+                           "true_rel_residual_per_cycle": [c[0] for c in cycles],
+                           "outer_iterations_per_cycle": [c[1] for c in cycles],
+                           "note": "the same solve followed by refinement cycles on the true "
+                                   "residual until it meets rtol or stops halving"}
+                del x3
             t0 = time.perf_counter()
             sc.backsolve(x2, 1.0)
             torch.cuda.synchronize()
@@ -433,6 +445,7 @@ def run_condensed(args, nx, dev, peak):
                 "backsolve_seconds": time.perf_counter() - t0, "converged": info2.converged,
                 "rel_residual": info2.rel_residual,
                 "true_rel_residual": info2.true_rel_residual,
+                "refined": refined,
                 "note": "homogeneous Dirichlet on ebc, f=1, rtol 1e-12 (time to solution); "
                         "rel_residual is the recursive one, true_rel_residual = ||b - S x|| / ||b|| "
                         "recomputed from the returned iterate"}

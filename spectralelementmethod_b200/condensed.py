@@ -609,6 +609,37 @@ class CondensedPoissonOperator(object):
             device.stream_ptr()))
         return y
 
+    def solve_pcg_refined(self, b, rtol=1e-12, max_cycles=3, **kw):
+        """Multilevel PCG followed by iterative refinement on the TRUE residual: CG stops on
+        its recursive residual, which at large condition numbers runs ahead of
+        ``||b - Shat x|| / ||b||`` (2e-9 against 7e-13 at config 2); every cycle recomputes
+        the true residual and solves for the correction until it meets ``rtol`` or stops
+        halving (the attainable accuracy in FP64).  Returns (x, PCGInfo of the first solve
+        with ``true_rel_residual`` of the final iterate, list of (true residual, outer
+        iterations) per cycle)."""
+        kw.setdefault("preconditioner", "three-level")
+        x, info = self.solve_pcg(b, rtol=rtol, **kw)
+        lib = self._lib
+        mask = device.ptr(self.dirichlet_dev) if self.has_dirichlet else None
+        r, bm, Ax = torch.empty_like(b), torch.empty_like(b), torch.empty_like(b)
+        hist = []
+        last = float("inf")
+        for _ in range(max_cycles):
+            self.apply(x, out=Ax)
+            _lib.check(lib.semk_vec_resid_f64(self.n_ext, device.ptr(b), device.ptr(Ax), mask,
+                                              device.ptr(r), device.ptr(bm), device.stream_ptr()))
+            true = float(torch.linalg.vector_norm(r) / torch.linalg.vector_norm(bm))
+            hist.append((true, info.iterations if not hist else it2))
+            if true <= rtol or true > 0.5 * last:
+                break
+            last = true
+            d, i2 = self.solve_pcg(r, rtol=min(0.1, max(rtol / true, 1e-14)), **kw)
+            it2 = i2.iterations
+            _lib.check(lib.semk_vec_scale_add_f64(self.n_ext, 1.0, device.ptr(d), device.ptr(x),
+                                                  device.ptr(x), device.stream_ptr()))
+        info.true_rel_residual = hist[-1][0]
+        return x, info, hist
+
     def solve_pcg(self, b, x0=None, rtol=1e-12, maxiter=200000, check_every=25,
                   preconditioner="jacobi", inner_rtol=1e-2, inner_maxiter=20000, flexible=True,
                   inner_chunk=4, max_tiles=4096, dist=None):

@@ -294,7 +294,8 @@ class AxisymmetricStokesOperator(object):
         return self._diagonals
 
     # -- restarted GMRES (right preconditioned, CGS2 orthogonalisation) -------------------
-    def solve_gmres(self, b, x0=None, rtol=1e-10, restart=60, maxiter=2000, precondition=True):
+    def solve_gmres(self, b, x0=None, rtol=1e-10, restart=60, maxiter=2000, precondition=True,
+                    scale_rows=None):
         """Solve Jhat x = b for the unknown DOFs (essential entries of x stay at x0's, b's
         essential entries are ignored).  precondition: True = nodal 2x2 block-Jacobi, False =
         none, "poisson" = PoissonBlockPreconditioner (Re = 0, DOFManagerSC), or a callable
@@ -321,6 +322,30 @@ class AxisymmetricStokesOperator(object):
             custom = self._poisson_prec = (getattr(self, "_poisson_prec", None)
                                            or PoissonBlockPreconditioner(self))
         binv = self.block_jacobi() if (precondition and custom is None) else None
+        # Row equilibration (default with the Poisson preconditioner): the rows of the system
+        # differ by eight orders of magnitude on the graded annulus (rho^2 JxW against rho),
+        # so a tolerance on ||b - A x||_2 says little about the small rows.  Solve
+        # (D A) x = D b, D = 1 / diag(Lve) on the wte rows and 1 / diag(E2e) on the wdef rows;
+        # the preconditioner of D A is P^-1 D^-1 (a similarity transform of A P^-1).  All
+        # residuals reported are those of the scaled system.
+        if scale_rows is None:
+            scale_rows = precondition == "poisson"
+        D = Dinv = None
+        if scale_rows:
+            dL, dE = self.block_jacobi_diagonals()[:2]
+            D = torch.ones(n, **f64)
+            D[0::2] = torch.where(dL != 0, 1.0 / dL, torch.ones_like(dL))
+            D[1::2] = torch.where(dE != 0, 1.0 / dE, torch.ones_like(dE))
+            self._fix(D, torch.ones(n, **f64))
+            Dinv = 1.0 / D
+            tmp = self.new_vector()
+
+        def scale(d, vec, out):
+            _lib.check(lib.semk_vec_scale_f64(n, device.ptr(d), device.ptr(vec), device.ptr(out),
+                                              st()))
+            return out
+        if D is not None:
+            scale(D, bb, bb)
 
         def dots(k, vec):
             _lib.check(lib.semk_multi_dot_f64(n, k, device.ptr(V), n, device.ptr(vec),
@@ -333,6 +358,8 @@ class AxisymmetricStokesOperator(object):
             return math.sqrt(max(float(hdev[0].item()), 0.0))
 
         def precond(src, dst):
+            if Dinv is not None:
+                src = scale(Dinv, src, tmp)
             if custom is not None:
                 custom(src, dst)
             elif binv is None:
@@ -356,6 +383,8 @@ class AxisymmetricStokesOperator(object):
             # residual the attainable accuracy of the system has been reached
             xm = self._fix(x.clone())
             self._apply_raw(xm, w, True)
+            if D is not None:
+                scale(D, w, w)
             _lib.check(lib.semk_vec_scale_add_f64(n, -1.0, device.ptr(w), device.ptr(bb),
                                                   device.ptr(V[0]), st()))
             beta = norm(V[0])
@@ -377,6 +406,8 @@ class AxisymmetricStokesOperator(object):
                 zj = Z[j] if flexible else z
                 precond(V[j], zj)
                 self._apply_raw(zj, V[j + 1], True)
+                if D is not None:
+                    scale(D, V[j + 1], V[j + 1])
                 h = dots(j + 1, V[j + 1]).copy()
                 _lib.check(lib.semk_multi_axpy_f64(n, j + 1, device.ptr(V), n, device.ptr(hdev),
                                                    -1.0, device.ptr(V[j + 1]), st()))
@@ -422,6 +453,8 @@ class AxisymmetricStokesOperator(object):
         # true residual of the returned iterate
         xm = self._fix(x.clone())
         self._apply_raw(xm, w, True)
+        if D is not None:
+            scale(D, w, w)
         _lib.check(lib.semk_vec_scale_add_f64(n, -1.0, device.ptr(w), device.ptr(bb),
                                               device.ptr(w), st()))
         true_rel = norm(w) / bnorm

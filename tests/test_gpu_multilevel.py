@@ -330,3 +330,17 @@ def test_comm_allreduce_single_rank_is_a_noop():
     finally:
         torch.cuda.synchronize()
         _lib.check(lib.semk_peer_free(region))
+
+
+def test_refinement_on_the_true_residual():
+    """solve_pcg_refined: the recursive residual of CG runs ahead of the true one; refinement
+    cycles bring ||b - S x|| / ||b|| down to the tolerance (or to the attainable accuracy)."""
+    mesh, mngr = build_package_case("C", 96, 96, 8, True, False)
+    sc = mngr.condensed_poisson_operator(dirichlet=mngr.boundary_node_mask("ebc"))
+    b = sc.lift(sc.rhs(1.0), None)
+    x0, i0 = sc.solve_pcg(b, rtol=1e-12, preconditioner="three-level")
+    x1, i1, cycles = sc.solve_pcg_refined(b, rtol=1e-12)
+    assert abs(cycles[0][0] - i0.true_rel_residual) <= 0.5 * i0.true_rel_residual + 1e-15
+    assert cycles[-1][0] <= max(1e-12, 0.5 * cycles[0][0]) or len(cycles) == 1
+    assert sc.true_residual(b, x1) <= sc.true_residual(b, x0) * 1.0000001
+    assert rel_l2(host(x1), host(x0)) < 1e-8
