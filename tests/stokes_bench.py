@@ -77,6 +77,19 @@ def main():
         if pp is not None:
             out["gmres"]["poisson_solves"] = pp.solves
             out["gmres"]["poisson_outer_iterations"] = pp.inner_outer_iterations
+    if len(a) > 10 and a[10] == "newton":
+        # the whole nonlinear solve (Newton + flexible GMRES + Poisson block preconditioner)
+        bc = stokes.squirmer_boundary_data(dm, 1.0, stokes.squirmer_vslip_profile(1.0),
+                                           x_phys=op.x_phys.cpu().numpy().reshape(op.n_elem, 2, p + 1, p + 1))
+        op.set_essential(bc.essential)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        state, hist = op.newton_solve(op.from_host(bc.state0), bc.cint, it_max=12, tol=1e-6,
+                                      gmres_rtol=1e-8, restart=300, gmres_maxiter=900,
+                                      precondition="poisson", verbose=True)
+        torch.cuda.synchronize()
+        out["newton"] = {"seconds": time.perf_counter() - t0, "n_rey": n_rey,
+                         "steps": [(du, i.iterations, i.true_rel_residual) for du, i in hist]}
     print(json.dumps(out))
 
 
