@@ -10,6 +10,12 @@ SuperLU step (:299-387) are replaced by the matrix-free device Jacobian
 
     python examples/squirmer_axisymmetric.py [--nr 4] [--nt 6] [--order 8] [--r-out 100]
                                              [--re 0.0] [--beta 1.0] [--speed 1.0] [--fixed]
+                                             [--preconditioner poisson|block-jacobi]
+
+``--preconditioner poisson`` (default): flexible GMRES with the block-triangular
+preconditioner built from the weighted, statically condensed Poisson operator (mesh-
+independent: 10 M DOF in ~15 s per linear solve); ``block-jacobi``: the nodal 2 x 2 blocks
+(small meshes only).
 
 No .msh ships with the reference and gmsh is not available, so the mesh is the structured
 annulus sector of meshgen.annulus_sector_mesh (the transfinite mesh of
@@ -29,17 +35,20 @@ from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, Ten
 
 
 def run(nr=4, nt=6, order=8, r_out=100.0, n_rey=0.0, beta=1.0, speed=1.0, fixed=False,
-        quiet=False, tol=1e-6, restart=400):
+        quiet=False, tol=1e-6, restart=400, preconditioner="poisson"):
     mesh = meshgen.annulus_sector_mesh(nr, nt, order, r_out)
     b1 = LagrangeGaussLobatto(order)
-    dm = discrete.DOFManagerSC(mesh, 2, TensorProductQS(b1, b1))
+    # (rcm_order=False: the scalar manager of the Poisson preconditioner shares the numbering)
+    dm = discrete.DOFManagerSC(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
     slip = stokes.zero_slip_vel if fixed else stokes.squirmer_vslip_profile(beta)
     bc = stokes.squirmer_boundary_data(dm, 1.0 if fixed else speed, slip)
     op = dm.axisymmetric_stokes_operator(n_rey=n_rey, essential=bc.essential)
     t0 = time.perf_counter()
+    poisson = preconditioner == "poisson"
     state, hist = op.newton_solve(op.from_host(bc.state0), bc.cint, tol=tol, restart=restart,
-                                  gmres_rtol=1e-12, gmres_maxiter=20 * restart,
-                                  verbose=not quiet)
+                                  gmres_rtol=1e-10 if poisson else 1e-12,
+                                  gmres_maxiter=(3 if poisson else 20) * restart,
+                                  verbose=not quiet, precondition="poisson" if poisson else True)
     el = time.perf_counter() - t0
     soln = state.cpu().numpy()
     if not quiet:
@@ -60,8 +69,10 @@ def main():
     ap.add_argument("--beta", type=float, default=1.0)
     ap.add_argument("--speed", type=float, default=1.0)
     ap.add_argument("--fixed", action="store_true", help="fixed sphere in uniform flow (no slip)")
+    ap.add_argument("--preconditioner", default="poisson", choices=["poisson", "block-jacobi"])
     a = ap.parse_args()
-    run(a.nr, a.nt, a.order, a.r_out, a.re, a.beta, a.speed, a.fixed)
+    run(a.nr, a.nt, a.order, a.r_out, a.re, a.beta, a.speed, a.fixed,
+        preconditioner=a.preconditioner)
 
 
 if __name__ == "__main__":
