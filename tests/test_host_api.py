@@ -323,3 +323,49 @@ def test_condensed_tables_reject_a_numbering_that_is_not_exterior_first():
     n_ext_true = mesh.n_nodes - 6 * 9
     with pytest.raises(AssertionError):
         condensed_tables(l2g, np.asarray(geo.exterior_node_ind), n_ext_true)
+
+
+def test_multithreaded_host_helpers_are_bit_exact():
+    """csrc/semk_hostnum.cpp (the path large meshes take) against the whole-array NumPy
+    expressions (the path the golden cases take): same node maps, same permuted coordinates,
+    same exterior / interior counts; structured node maps against the closed form."""
+    import numpy as np
+    from spectralelementmethod_b200 import discrete, meshgen
+    from spectralelementmethod_b200.basis_functions import LagrangeGaussLobatto, TensorProductQS
+    for kind, nx, ny, p in (("C", 90, 70, 4), ("S", 40, 44, 8)):
+        ex, ey = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
+        m = np.arange(p + 1, dtype=np.int64)
+        closed = ((ex * p * (ny * p + 1) + ey * p)[:, None, None] + m[None, :, None] * (ny * p + 1)
+                  + m[None, None, :]).astype(np.uint32)
+        assert np.array_equal(meshgen.structured_node_maps(nx, ny, p), closed)
+        b1 = LagrangeGaussLobatto(p)
+        basis = TensorProductQS(b1, b1)
+        fast_mesh = meshgen.structured_quad_mesh(nx, ny, p, kind)
+        assert fast_mesh.n_nodes >= (1 << 16)
+        calls = []
+        orig = discrete.DOFManagerSC._fast_static_condensation
+
+        def spy(self):
+            ok = orig(self)
+            calls.append(ok)
+            return ok
+        discrete.DOFManagerSC._fast_static_condensation = spy
+        try:
+            fast = discrete.DOFManagerSC(fast_mesh, 1, basis, rcm_order=False)
+            discrete.DOFManagerSC._fast_static_condensation = lambda self: False
+            slow_mesh = meshgen.structured_quad_mesh(nx, ny, p, kind)
+            slow = discrete.DOFManagerSC(slow_mesh, 1, basis, rcm_order=False)
+        finally:
+            discrete.DOFManagerSC._fast_static_condensation = orig
+        assert calls == [True]                      # the helper really ran
+        assert np.array_equal(fast_mesh.node_map_array(), slow_mesh.node_map_array())
+        assert np.array_equal(fast_mesh.nodes, slow_mesh.nodes)
+        assert fast.ndof_exterior == slow.ndof_exterior and fast.ndof_interior == slow.ndof_interior
+        # with RCM on top (exterior nodes only) the two paths still agree
+        f2 = discrete.DOFManagerSC(meshgen.structured_quad_mesh(nx, ny, p, kind), 1, basis)
+        discrete.DOFManagerSC._fast_static_condensation = lambda self: False
+        try:
+            s2 = discrete.DOFManagerSC(meshgen.structured_quad_mesh(nx, ny, p, kind), 1, basis)
+        finally:
+            discrete.DOFManagerSC._fast_static_condensation = orig
+        assert np.array_equal(f2.mesh.node_map_array(), s2.mesh.node_map_array())
