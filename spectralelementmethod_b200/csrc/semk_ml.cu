@@ -16,6 +16,8 @@
 // read/update race on the scalar block and the host only polls it every few iterations.
 #include "semk_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kT = 256;                 // vector kernels
@@ -799,6 +801,47 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
   semk_halo *halo_c = multi ? dist->halo_c : nullptr;
   if (multi) SEMK_REQUIRE(halo_f && halo_c, "semk_sc_mlpcg_solve_f64: partition without halos");
   cudaStream_t st = semk_stream(stream);
+  // On one GPU the inner iterations are replayed from a CUDA graph (eight small kernels per
+  // iteration, a few microseconds each: launch gaps are a third of an inner solve on small
+  // coarse levels).  Stream capture needs a non-default stream, so the whole solve moves to a
+  // private one that is ordered after the caller's stream and joined with it at the end.
+  // (Multi-GPU: the halo epochs are kernel arguments that change per launch -- no graph.)
+  struct Private {
+    cudaStream_t s = nullptr;
+    cudaEvent_t in = nullptr, out = nullptr;
+  };
+  thread_local Private priv;
+  const bool use_graph = !multi && opts->inner_chunk >= 1 && !getenv("SEMK_NO_GRAPH");
+  cudaStream_t caller_stream = st;
+  if (use_graph) {
+    if (!priv.s) {
+      SEMK_CUDA_CHECK(cudaStreamCreateWithFlags(&priv.s, cudaStreamNonBlocking));
+      SEMK_CUDA_CHECK(cudaEventCreateWithFlags(&priv.in, cudaEventDisableTiming));
+      SEMK_CUDA_CHECK(cudaEventCreateWithFlags(&priv.out, cudaEventDisableTiming));
+    }
+    SEMK_CUDA_CHECK(cudaEventRecord(priv.in, caller_stream));
+    SEMK_CUDA_CHECK(cudaStreamWaitEvent(priv.s, priv.in, 0));
+    st = priv.s;
+  }
+  struct Join {     // whatever way the function returns, the caller's stream waits for the solve
+    bool on;
+    cudaStream_t from, to;
+    cudaEvent_t ev;
+    ~Join() {
+      if (on) {
+        cudaEventRecord(ev, from);
+        cudaStreamWaitEvent(to, ev, 0);
+      }
+    }
+  } join{use_graph, st, caller_stream, priv.out};
+  struct GraphHolder {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t x = nullptr;
+    ~GraphHolder() {
+      if (x) cudaGraphExecDestroy(x);
+      if (g) cudaGraphDestroy(g);
+    }
+  } inner_graph;
   const int64_t n = op->n_ext, nv = cs->n_v, n_elem = op->n_elem;
   const int64_t na = three ? top->n_agg : 0;
   const int64_t n_dot = multi ? dist->n_owned_f : n, nv_dot = multi ? dist->n_owned_c : nv;
@@ -922,8 +965,26 @@ extern "C" int semk_sc_mlpcg_solve_f64(const semk_sc_op *op, const semk_sc_coars
     int chunk = predicted > 2 ? predicted - 1 : 1;
     while (launched < opts->inner_maxiter) {
       if (chunk > opts->inner_maxiter - launched) chunk = opts->inner_maxiter - launched;
-      for (int k = 0; k < chunk; ++k)
-        if ((e = inner_iteration()) != SEMK_OK) return e;
+      if (use_graph) {
+        // one graph = inner_chunk iterations; iterations past convergence are no-ops (the
+        // kernels read S_CONV), so rounding the chunk up to whole graphs is harmless
+        const int per = opts->inner_chunk;
+        if (!inner_graph.x) {
+          SEMK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+          int ce = SEMK_OK;
+          for (int k = 0; k < per && ce == SEMK_OK; ++k) ce = inner_iteration();
+          cudaError_t ee = cudaStreamEndCapture(st, &inner_graph.g);
+          if (ce != SEMK_OK) return ce;
+          SEMK_CUDA_CHECK(ee);
+          SEMK_CUDA_CHECK(cudaGraphInstantiate(&inner_graph.x, inner_graph.g, 0));
+        }
+        const int reps = (chunk + per - 1) / per;
+        for (int k = 0; k < reps; ++k) SEMK_CUDA_CHECK(cudaGraphLaunch(inner_graph.x, st));
+        chunk = reps * per;
+      } else {
+        for (int k = 0; k < chunk; ++k)
+          if ((e = inner_iteration()) != SEMK_OK) return e;
+      }
       launched += chunk;
       if ((e = fetch()) != SEMK_OK) return e;
       const double *hi = h + S_LEN;
