@@ -855,6 +855,24 @@ int semk_stokes_local_diag_f64(const semk_stokes_op *op, const double *D_dev,
 int semk_scatter_fix_f64(int64_t n, const int64_t *idx, const double *src, double *y,
                          void *stream);
 
+/* Glue of the Poisson block preconditioner of the Stokes system (stokes.py,
+ * PoissonBlockPreconditioner): vectors src / t / y / dst are (psi, omega) pairs [n_nodes][2],
+ * the others nodal [n_nodes].
+ *   gamma : t = (0, nimg * src_omega)                      (om_G = -b_G / M_G)
+ *   rhs   : which 0: r = src_psi - y_psi;  which 1: r = src_omega + coef * om;
+ *           r = 0 outside free_mask;  f = r * inv_mass_int  (nodal load for semk_sc_element_*)
+ *   out   : dst = (free ? psi : 0, free ? om_i : t_omega)
+ *   semk_sc_rhs_finish_f64: b = dirichlet ? 0 : g + r over the element-exterior DOFs */
+int semk_stokes_prec_gamma_f64(int64_t n_nodes, const double *src, const double *nimg, double *t,
+                               void *stream);
+int semk_stokes_prec_rhs_f64(int64_t n_nodes, int which, const double *src, const double *y,
+                             const double *coef, const double *om, const uint8_t *free_mask,
+                             const double *inv_mass_int, double *r, double *f, void *stream);
+int semk_stokes_prec_out_f64(int64_t n_nodes, const uint8_t *free_mask, const double *psi,
+                             const double *om_i, const double *t, double *dst, void *stream);
+int semk_sc_rhs_finish_f64(int64_t n, const double *g, const double *r, const uint8_t *dirichlet,
+                           double *b, void *stream);
+
 /* Building blocks of the restarted GMRES that replaces the reference's sparse direct
  * solve of the non-symmetric system (examples/squirmer-axisymmetric.py:360-370):
  * out[j] = V_j . w for j < k with V_j = V + j*ldv (one pass, fixed-order reduction);

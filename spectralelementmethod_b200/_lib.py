@@ -233,6 +233,10 @@ SIGNATURES = {
     "semk_stokes_apply_f64": (_I, [C.POINTER(semk_stokes_op), _P, _P, _I, _D, _P]),
     "semk_stokes_local_diag_f64": (_I, [C.POINTER(semk_stokes_op), _P, _L, _P, _P, _P, _P, _P]),
     "semk_scatter_fix_f64": (_I, [_L, _P, _P, _P, _P]),
+    "semk_stokes_prec_gamma_f64": (_I, [_L, _P, _P, _P, _P]),
+    "semk_stokes_prec_rhs_f64": (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "semk_stokes_prec_out_f64": (_I, [_L, _P, _P, _P, _P, _P, _P]),
+    "semk_sc_rhs_finish_f64": (_I, [_L, _P, _P, _P, _P, _P]),
     "semk_multi_dot_partials_len": (_L, [_I]),
     "semk_multi_dot_f64": (_I, [_L, _I, _P, _L, _P, _P, _P, _P]),
     "semk_multi_axpy_f64": (_I, [_L, _I, _P, _L, _P, _D, _P, _P]),

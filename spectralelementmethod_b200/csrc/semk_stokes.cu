@@ -612,6 +612,53 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- glue of the Poisson block preconditioner (stokes.PoissonBlockPreconditioner) ---------
+// t = (0, nimg * src_omega): the boundary vorticities om_G = -b_G / M_G as a (psi, omega) vector
+__global__ void __launch_bounds__(256)
+    prec_gamma_kernel(int64_t n_nodes, const double2 *__restrict__ src,
+                      const double *__restrict__ nimg, double2 *__restrict__ t) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes;
+       i += (int64_t)gridDim.x * blockDim.x)
+    t[i] = make_double2(0.0, src[i].y * nimg[i]);
+}
+// which = 0: r = src_psi - y_psi           (rows wte minus L om_G)
+// which = 1: r = src_omega + coef * om     (rows wdef plus M om_I)
+// r is zeroed outside the free nodes; f = r * inv_mass_int is the nodal load whose element
+// load JxW f reproduces r on the element interiors (zero on exterior nodes)
+__global__ void __launch_bounds__(256)
+    prec_rhs_kernel(int64_t n_nodes, int which, const double2 *__restrict__ src,
+                    const double2 *__restrict__ y, const double *__restrict__ coef,
+                    const double *__restrict__ om, const uint8_t *__restrict__ free_mask,
+                    const double *__restrict__ inv_mass_int, double *__restrict__ r,
+                    double *__restrict__ f) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v = which == 0 ? src[i].x - y[i].x : fma(coef[i], om[i], src[i].y);
+    if (!free_mask[i]) v = 0.0;
+    r[i] = v;
+    f[i] = v * inv_mass_int[i];
+  }
+}
+// dst = (free ? psi : 0, free ? om_I : om_G)
+__global__ void __launch_bounds__(256)
+    prec_out_kernel(int64_t n_nodes, const uint8_t *__restrict__ free_mask,
+                    const double *__restrict__ psi, const double *__restrict__ om_i,
+                    const double2 *__restrict__ t, double2 *__restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nodes;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool fr = free_mask[i] != 0;
+    dst[i] = make_double2(fr ? psi[i] : 0.0, fr ? om_i[i] : t[i].y);
+  }
+}
+// b = Dirichlet ? 0 : g + r  (condensed right-hand side of a residual with zero boundary data)
+__global__ void __launch_bounds__(256)
+    cond_rhs_finish_kernel(int64_t n, const double *__restrict__ g, const double *__restrict__ r,
+                           const uint8_t *__restrict__ dirichlet, double *__restrict__ b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = (dirichlet && dirichlet[i]) ? 0.0 : g[i] + r[i];
+}
+
 inline int grid_for(int64_t n, int threads, int cap) {
   const int64_t want = (n + threads - 1) / threads;
   return (int)(want < 1 ? 1 : (want < cap ? want : cap));
@@ -828,5 +875,49 @@ extern "C" int semk_block2_apply_f64(int64_t n_nodes, const double *binv, const 
   block2_apply_kernel<<<grid_for(n_nodes, 256, 148 * 8), 256, 0, semk_stream(stream)>>>(
       n_nodes, binv, reinterpret_cast<const double2 *>(r), reinterpret_cast<double2 *>(z));
   SEMK_LAUNCH_CHECK("block2_apply_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_stokes_prec_gamma_f64(int64_t n_nodes, const double *src, const double *nimg,
+                                          double *t, void *stream) {
+  SEMK_REQUIRE(n_nodes > 0 && src && nimg && t, "semk_stokes_prec_gamma_f64: bad arguments");
+  prec_gamma_kernel<<<grid_for(n_nodes, 256, 148 * 8), 256, 0, semk_stream(stream)>>>(
+      n_nodes, reinterpret_cast<const double2 *>(src), nimg, reinterpret_cast<double2 *>(t));
+  SEMK_LAUNCH_CHECK("prec_gamma_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_stokes_prec_rhs_f64(int64_t n_nodes, int which, const double *src,
+                                        const double *y, const double *coef, const double *om,
+                                        const uint8_t *free_mask, const double *inv_mass_int,
+                                        double *r, double *f, void *stream) {
+  SEMK_REQUIRE(n_nodes > 0 && src && free_mask && inv_mass_int && r && f &&
+                   (which == 0 ? y != nullptr : (which == 1 && coef && om)),
+               "semk_stokes_prec_rhs_f64: bad arguments");
+  prec_rhs_kernel<<<grid_for(n_nodes, 256, 148 * 8), 256, 0, semk_stream(stream)>>>(
+      n_nodes, which, reinterpret_cast<const double2 *>(src),
+      reinterpret_cast<const double2 *>(y), coef, om, free_mask, inv_mass_int, r, f);
+  SEMK_LAUNCH_CHECK("prec_rhs_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_stokes_prec_out_f64(int64_t n_nodes, const uint8_t *free_mask,
+                                        const double *psi, const double *om_i, const double *t,
+                                        double *dst, void *stream) {
+  SEMK_REQUIRE(n_nodes > 0 && free_mask && psi && om_i && t && dst,
+               "semk_stokes_prec_out_f64: bad arguments");
+  prec_out_kernel<<<grid_for(n_nodes, 256, 148 * 8), 256, 0, semk_stream(stream)>>>(
+      n_nodes, free_mask, psi, om_i, reinterpret_cast<const double2 *>(t),
+      reinterpret_cast<double2 *>(dst));
+  SEMK_LAUNCH_CHECK("prec_out_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_rhs_finish_f64(int64_t n, const double *g, const double *r,
+                                      const uint8_t *dirichlet, double *b, void *stream) {
+  SEMK_REQUIRE(n > 0 && g && r && b, "semk_sc_rhs_finish_f64: bad arguments");
+  cond_rhs_finish_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, semk_stream(stream)>>>(n, g, r,
+                                                                                    dirichlet, b);
+  SEMK_LAUNCH_CHECK("cond_rhs_finish_kernel");
   return SEMK_OK;
 }

@@ -534,8 +534,7 @@ class PoissonBlockPreconditioner(object):
     multilevel PCG driver to ``rtol``; the inner solves are iterative, so the outer method is
     FLEXIBLE GMRES and convergence is accepted on the true residual.
     Needs a ``DOFManagerSC`` (exterior-first numbering) built with ``rcm_order=False``.
-    The glue between the solves (strided copies, masks, scalings) is torch elementwise code;
-    the applies, element passes and PCG loops are the C-ABI kernels."""
+    The glue between the solves is three small C-ABI kernels (semk_stokes_prec_*_f64)."""
 
     def __init__(self, op, rtol=1e-8, preconditioner="three-level", reaction_term=True):
         from . import discrete
@@ -578,6 +577,10 @@ class PoissonBlockPreconditioner(object):
         dM = op.block_jacobi_diagonals()[2]
         self.M = dM
         self.neg_inv_M_gamma = torch.where(self.gamma, -1.0 / dM, torch.zeros_like(dM))
+        self.free_u8 = self.free_s.to(torch.uint8).contiguous()
+        f64 = dict(dtype=torch.float64, device=dev)
+        self._t, self._y = torch.empty(op.n_dof, **f64), torch.empty(op.n_dof, **f64)
+        self._r, self._f = torch.empty(op.n_nodes, **f64), torch.empty(op.n_nodes, **f64)
         self.solves = 0
         self.inner_outer_iterations = 0
 
@@ -592,31 +595,41 @@ class PoissonBlockPreconditioner(object):
         loc[:eos.numel()][ok] = po.JxW[eos[ok]]
         return loc
 
-    def poisson_solve(self, r):
-        """u = Khat^-1 r for a nodal residual r (zero on the Dirichlet nodes)."""
-        sc = self.sc
-        f = r * self.inv_mass_int
+    def poisson_solve(self, r, f=None):
+        """u = Khat^-1 r for a nodal residual r (zero on the Dirichlet nodes); f = r *
+        inv_mass_int if the caller has it already."""
+        sc, lib = self.sc, self.op._lib
+        if f is None:
+            f = r * self.inv_mass_int
         g = sc.rhs(f)
-        g += r[:self.n_ext]
-        b = sc.lift(g, None)
+        b = torch.empty_like(g)
+        _lib.check(lib.semk_sc_rhs_finish_f64(
+            self.n_ext, device.ptr(g), device.ptr(r), device.ptr(sc.dirichlet_dev)
+            if sc.has_dirichlet else None, device.ptr(b), device.stream_ptr()))
         x, info = sc.solve_pcg(b, rtol=self.rtol, preconditioner=self.kind)
         self.solves += 1
         self.inner_outer_iterations += info.iterations
         return sc.backsolve(x, f)
 
     def __call__(self, src, dst):
-        op = self.op
-        a, b = src[0::2], src[1::2]
-        om = b * self.neg_inv_M_gamma                       # om_G (zero elsewhere)
-        t = op.new_vector(0.0)
-        t[1::2] = om
-        y = op.apply_unmasked(t)                            # row 0 = L om_G
-        r1 = torch.where(self.free_s, a - y[0::2], torch.zeros_like(a)).contiguous()
-        om_i = self.poisson_solve(r1)
-        r2 = torch.where(self.free_s, b + self.M * om_i, torch.zeros_like(b)).contiguous()
-        psi = self.poisson_solve(r2)
-        dst[0::2] = torch.where(self.free_s, psi, torch.zeros_like(psi))
-        dst[1::2] = torch.where(self.free_s, om_i, om)
+        op, lib, n = self.op, self.op._lib, self.op.n_nodes
+        st = device.stream_ptr
+        t, r, f = self._t, self._r, self._f
+        _lib.check(lib.semk_stokes_prec_gamma_f64(n, device.ptr(src), device.ptr(
+            self.neg_inv_M_gamma), device.ptr(t), st()))                    # om_G
+        y = op.apply_unmasked(t, out=self._y)                               # row 0 = L om_G
+        _lib.check(lib.semk_stokes_prec_rhs_f64(
+            n, 0, device.ptr(src), device.ptr(y), None, None, device.ptr(self.free_u8),
+            device.ptr(self.inv_mass_int), device.ptr(r), device.ptr(f), st()))
+        om_i = self.poisson_solve(r, f)
+        _lib.check(lib.semk_stokes_prec_rhs_f64(
+            n, 1, device.ptr(src), None, device.ptr(self.M), device.ptr(om_i),
+            device.ptr(self.free_u8), device.ptr(self.inv_mass_int), device.ptr(r), device.ptr(f),
+            st()))
+        psi = self.poisson_solve(r, f)
+        _lib.check(lib.semk_stokes_prec_out_f64(n, device.ptr(self.free_u8), device.ptr(psi),
+                                                device.ptr(om_i), device.ptr(t), device.ptr(dst),
+                                                st()))
         return dst
 
 
