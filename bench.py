@@ -503,6 +503,43 @@ def run_stokes(args, peak):
                       % (op.elems_per_patch, "ADV" if op.advection else "STOKES")}
         del op, x, y
         t0 = time.perf_counter()
+    # CPU baseline of this row (reported beside, not the target): the reference's own dense
+    # local apply of the Stokes blocks -- np.einsum('pqrs,rs', Lve, vort), np.einsum('pqrs,rs',
+    # E2e, sfn) and the diagonal mass term, examples/squirmer-axisymmetric.py:284-295 -- over
+    # precomputed dense operators (oracle restatement, vectorised over elements, one thread)
+    if args.cpu_sample > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import sem_oracle as so
+            snr, snt = 12, 16
+            nodes = so.annulus_nodes(snr, snt, p, 100.0)
+            l2g = so.mesh_l2g(snr, snt, p)
+            basis = so.Basis(p)
+            geo = so.geometry(basis, nodes, l2g)
+            ops = so.stokes_local_operators(basis, geo["x_phys"], geo["invJ"], geo["JxW"])
+            Lv = np.where(np.isfinite(ops["Lve"]), ops["Lve"], 0.0)
+            E2, Me = ops["E2e"], ops["Me"]
+            rng = np.random.default_rng(0)
+            sf, vo = rng.standard_normal((2, nodes.shape[1]))
+            n_dof_s = 2 * nodes.shape[1]
+            reps, t0c = 0, time.perf_counter()
+            while time.perf_counter() - t0c < 5.0:
+                r0 = np.einsum("epqrs,ers->epq", Lv, vo[l2g])
+                r1 = np.einsum("epqrs,ers->epq", E2, sf[l2g]) - Me * vo[l2g]
+                y = np.zeros(n_dof_s)
+                np.add.at(y[0::2], l2g.ravel(), r0.ravel())
+                np.add.at(y[1::2], l2g.ravel(), r1.ravel())
+                reps += 1
+            el = time.perf_counter() - t0c
+            out["cpu_baseline"] = {
+                "value": n_dof_s * reps / el / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "port",
+                "sample": "%dx%d elements p=%d (%d DOF), %d applies in %.1f s; dense local "
+                          "einsum apply of Lve / E2e / Me (oracle restatement of "
+                          "examples/squirmer-axisymmetric.py:284-295), NumPy, one thread"
+                          % (snr, snt, p, n_dof_s, reps, el)}
+        except Exception as exc:       # a reported baseline, never fatal
+            out["cpu_baseline"] = {"error": repr(exc)}
+
     # time to solution of the Stokes problem (Re = 0, squirmer boundary data) at the same
     # size: flexible GMRES, block-triangular preconditioner from the weighted condensed
     # Poisson operator (multilevel PCG inside), accepted on the TRUE residual
