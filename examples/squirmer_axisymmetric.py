@@ -70,7 +70,21 @@ def main():
     ap.add_argument("--speed", type=float, default=1.0)
     ap.add_argument("--fixed", action="store_true", help="fixed sphere in uniform flow (no slip)")
     ap.add_argument("--preconditioner", default="poisson", choices=["poisson", "block-jacobi"])
+    ap.add_argument("--swim", action="store_true",
+                    help="find the swimming speed (zero net force) by the secant iteration of "
+                         "the reference's calc_speed; its docstring quotes 0.92571156681483957 "
+                         "for Re = 1, beta = 1 on meshes/donut.msh (15 x 9 elements, r_out = 100)")
     a = ap.parse_args()
+    if a.swim:
+        mesh = meshgen.annulus_sector_mesh(a.nr, a.nt, a.order, a.r_out)
+        b1 = LagrangeGaussLobatto(a.order)
+        dm = discrete.DOFManagerSC(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
+        t0 = time.perf_counter()
+        speed, _, hist = stokes.squirmer_speed(dm, a.re, a.beta, verbose=True, restart=400,
+                                               gmres_rtol=1e-10, gmres_maxiter=1200)
+        print(" => swimming speed %.12g at Re = %g, beta = %g (%d flow solves, %.1f s)"
+              % (speed, a.re, a.beta, len(hist), time.perf_counter() - t0))
+        return
     run(a.nr, a.nt, a.order, a.r_out, a.re, a.beta, a.speed, a.fixed,
         preconditioner=a.preconditioner)
 

@@ -14,9 +14,13 @@ runs is the example's own `pre_assembly`, `compute_local_system`, `compute_loc_s
      the order from ORDER below so that small golden cases are possible)
   b. basis_funcs.TensorProductSupported  -> sem.basis_functions.TensorProductQS
   c. basis.get_diff_matrices()           -> get_D1_matrices()      (:185)
-  d. bnd_fe.normal()                     -> SubFiniteElement.n_dS  (:135, "non-normalized
-     unit vector": the normal times the arc-length factor; only enters the natural-BC
-     contour integral `cint`, which the golden files store as data)
+  d. bnd_fe.normal()                     -> -SubFiniteElement.n_dS (:135, "non-normalized
+     unit vector": the normal times the arc-length factor, pointing from the body INTO the
+     fluid.  The method no longer exists; the orientation is fixed by the example's own
+     numbers: with this sign the force-free speed of a Stokes squirmer comes out as +1 (the
+     secant guesses of calc_speed are 0.99 / 1.01, :630-744) and Re = 1, beta = 1 gives the
+     0.9257 quoted in its docstring (:667); with +n_dS both come out mirrored (-1, and the
+     pusher's 1.088).  Only enters the natural-BC contour integral `cint`.)
   e. python 2 names: itertools.izip -> zip, xrange -> range       (:345,:366,:427-431)
   f. np.ogrid[[slice, ...]] list index -> tuple index (numpy 2)   (:201,:216,:224 and
      sem/sp_array.py:107)
@@ -68,7 +72,7 @@ def load_example():
         bf.LagrangeAtGaussLobatto = lambda order: bf.LagrangeGaussLobatto(ORDER)
         bf.TensorProductSupported = bf.TensorProductQS
         bf.TensorProduct.get_diff_matrices = bf.TensorProduct.get_D1_matrices
-        sd.SubFiniteElement.normal = lambda self: self.n_dS
+        sd.SubFiniteElement.normal = lambda self: -self.n_dS
         itertools.izip = zip
         sd.Static_COO_Matrix.tocsr = lambda self: self.tocoo().tocsr()
         spa.np = _NumpyProxy()

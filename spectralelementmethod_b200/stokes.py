@@ -31,7 +31,7 @@ from . import _lib, device
 from .operators import PoissonOperator, _TILES
 
 __all__ = ["AxisymmetricStokesOperator", "GMRESInfo", "PoissonBlockPreconditioner",
-           "squirmer_boundary_data",
+           "squirmer_boundary_data", "squirmer_force", "squirmer_speed",
            "sfn_potential", "sfn_free_stream", "squirmer_vslip_profile", "zero_slip_vel"]
 
 N_FAC_STOKES, N_FAC_ADV = 7, 12
@@ -672,7 +672,8 @@ def squirmer_boundary_data(dof_mngr, speed=1.0, slip_vel=zero_slip_vel, x_phys=N
     """Initial guess and boundary conditions of the example, through the drop-in API:
     `set_initial_guess` (:109-117: potential flow) and `_apply_bcs_to_fe` (:119-161):
       "sphere":  sfn = 0 essential; natural BC on the vorticity-definition row
-                 cint -= xweight(rho * rho (n_rho v_z - n_z v_rho)), n = n_dS;
+                 cint -= xweight(rho * rho (n_rho v_z - n_z v_rho)), n = -n_dS (from the body
+                 into the fluid);
       "symaxis": sfn = vort = 0 essential;
       "shell":   sfn = -speed * free stream, vort = 0 essential.
     x_phys: optional host [E, 2, N, N] GLL-point coordinates (saves one geometry pass)."""
@@ -695,7 +696,8 @@ def squirmer_boundary_data(dof_mngr, speed=1.0, slip_vel=zero_slip_vel, x_phys=N
                 sfn[loc] = 0
                 ess_s[loc] = True
                 rho, z = bnd.x_phys
-                n_rho, n_z = bnd.n_dS
+                # the example's `bnd_fe.normal()`: non-normalised, from the body into the fluid
+                n_rho, n_z = -bnd.n_dS
                 r = np.sqrt(rho ** 2 + z ** 2)
                 sin_th, cos_th = rho / r, z / r
                 v = slip_vel(sin_th, cos_th)
@@ -720,3 +722,74 @@ def squirmer_boundary_data(dof_mngr, speed=1.0, slip_vel=zero_slip_vel, x_phys=N
     cint = np.zeros(2 * n)
     cint[1::2] = cint_w
     return SquirmerBoundaryData(state0, essential, cint)
+
+
+def squirmer_force(dof_mngr, soln_vec, slip_vel, n_rey):
+    """Total hydrodynamic force on the unit sphere in the swimming direction
+    (`calc_force`, examples/squirmer-axisymmetric.py:458-513, through the current API: the
+    example's version still uses the package's older element interface).  On r = 1, with
+    the polar angle from the +z axis,
+        stress = pi Re v_s^2 sin cos + pi (d omega / d r + omega) sin^2 - 2 pi omega sin^2,
+    integrated along the arc.  soln_vec: host array [2 n_nodes] (interleaved)."""
+    vort = np.asarray(soln_vec, dtype=np.float64)[1::2]
+    total = 0.0
+    for parent, bnd in dof_mngr.boundary_elements("sphere", x_phys=True, Jacobian=True):
+        rho, z = bnd.x_phys                           # r = 1: (sin, cos) of the polar angle
+        sin_th, cos_th = rho, z
+        vslip = slip_vel(sin_th, cos_th)
+        w_loc = vort[parent.node_ind]
+        grad = bnd.gradient(w_loc)                    # d omega / d(rho, z) on the face
+        dw_dr = grad[0] * rho + grad[1] * z
+        w_s = vort[bnd.node_ind]
+        sin2 = sin_th ** 2
+        bernoulli = np.pi * n_rey * vslip ** 2 * sin_th * cos_th
+        w_asym = np.pi * (dw_dr + w_s) * sin2
+        viscous = -2 * np.pi * w_s * sin2
+        total += float(((bernoulli + w_asym + viscous) * bnd.dSxW).sum())
+    return total
+
+
+def squirmer_speed(dof_mngr, n_rey, beta, speed_guess=(0.99, 1.01), it_max=10, tol=1e-5,
+                   newton_tol=1e-6, precondition="poisson", verbose=False, **newton_kw):
+    """Swimming speed of a squirmer: secant iteration on the speed at which the force on the
+    body vanishes (`calc_speed`, examples/squirmer-axisymmetric.py:630-744), every force
+    evaluation a full Newton solve of the flow on the device.  Returns (speed, state,
+    list of (speed, force))."""
+    from ._lib import SolverFailure
+    slip = squirmer_vslip_profile(beta)
+    op = None
+    x_phys = None
+    history = []
+
+    def force_at(speed, guess):
+        nonlocal op, x_phys
+        if op is None:
+            op = dof_mngr.axisymmetric_stokes_operator(n_rey=n_rey)
+            N = op.n1
+            x_phys = op.x_phys.cpu().numpy().reshape(op.n_elem, 2, N, N)
+        bc = squirmer_boundary_data(dof_mngr, speed, slip, x_phys=x_phys)
+        op.set_essential(bc.essential)
+        op._poisson_prec = None
+        s0 = bc.state0 if guess is None else np.where(bc.essential, bc.state0, guess)
+        state, _ = op.newton_solve(op.from_host(s0), bc.cint, tol=newton_tol,
+                                   precondition=precondition, **newton_kw)
+        sol = state.cpu().numpy()
+        f = squirmer_force(dof_mngr, sol, slip, n_rey)
+        history.append((float(speed), f))
+        if verbose:
+            print("speed = %.10g  =>  force = %.6e" % (speed, f))
+        return f, sol
+
+    speed0, speed1 = (float(v) for v in speed_guess)
+    if speed0 == speed1:
+        raise ValueError("Two distinct guesses for the speed must be supplied.")
+    force0, sol = force_at(speed0, None)
+    force1, sol = force_at(speed1, sol)
+    for _ in range(it_max):
+        speed2 = (speed1 * force0 - speed0 * force1) / (force0 - force1)
+        force2, sol = force_at(speed2, sol)
+        if abs(speed2 - speed1) < tol:
+            return speed2, sol, history
+        speed0, speed1, force0, force1 = speed1, speed2, force1, force2
+    raise SolverFailure("Swimming speed could not be found within the desired tolerance in "
+                        "the max number of iterations (%d)." % it_max)

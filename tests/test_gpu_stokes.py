@@ -274,3 +274,23 @@ def test_preconditioned_solve_vs_oracle_direct_solve_medium_mesh():
         # (without the row equilibration of solve_gmres the same residual tolerance leaves
         # 1e-3 here: the rows of the system span eight orders of magnitude)
         assert rel_l2(got[comp::2], dref[comp::2]) < 1e-5
+
+
+def test_swimming_speed_matches_the_number_in_the_reference_docstring():
+    """End-to-end known answer: the docstring of the example's `calc_speed`
+    (examples/squirmer-axisymmetric.py:661-668) quotes a swimming speed of
+    0.92571156681483957 for Re = 1, beta = 1 on meshes/donut.msh -- 15 x 9 transfinite
+    elements of order 8 between r = 1 and r = 100 with progression 1.35
+    (examples/meshes/donut.geo).  The same problem on the structured stand-in mesh (geometric
+    grading 100^(1/15) = 1.359) through the device operators, the Newton / flexible-GMRES
+    solver and the force functional reproduces it to 1e-7; the Stokes limit gives 1."""
+    mesh = meshgen.annulus_sector_mesh(15, 9, 8, 100.0)
+    b1 = LagrangeGaussLobatto(8)
+    dm = discrete.DOFManagerSC(mesh, 2, TensorProductQS(b1, b1), rcm_order=False)
+    speed, sol, hist = stokes.squirmer_speed(dm, 1.0, 1.0, restart=400, gmres_rtol=1e-10,
+                                             gmres_maxiter=1200)
+    assert abs(speed - 0.92571156681483957) < 1e-6, (speed, hist)
+    assert abs(hist[-1][1]) < 1e-5           # force-free
+    speed0, _, _ = stokes.squirmer_speed(dm, 0.0, 1.0, restart=400, gmres_rtol=1e-10,
+                                         gmres_maxiter=1200)
+    assert abs(speed0 - 1.0) < 1e-5, speed0  # U = 2/3 B1 = 1 for a Stokes squirmer
