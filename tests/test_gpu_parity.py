@@ -771,3 +771,46 @@ def test_batched_point_location_at_size():
     vals = mngr.interpolate_points(coeffs, pts)
     want = f(torch.from_numpy(pts[0]).cuda(), torch.from_numpy(pts[1]).cuda())
     assert float((vals - want).abs().max()) < 1e-7
+
+
+# known answers of the live reference through the DEVICE path
+from test_oracle_golden import APPENDIX_B_OPERATOR, APPENDIX_B_SOLVE  # noqa: E402
+
+
+@pytest.mark.parametrize("row", APPENDIX_B_OPERATOR)
+def test_survey_known_answers_operator_on_device(row):
+    kind, nx, ny, p, sc, rcm, nAu, mAu, sb, sd, md, nu = row
+    mesh, mngr = build_package_case(kind, nx, ny, p, sc, rcm)
+    op = mngr.poisson_operator()
+    x, y = mesh.nodes
+    u = np.sin(3 * x) * np.cos(2 * y)
+    Au = host(op.apply_unmasked(dev(u)))
+    rel = lambda a, b: abs(a - b) / abs(b)          # noqa: E731
+    assert rel(np.linalg.norm(Au), nAu) < 1e-12
+    assert rel(np.abs(Au).max(), mAu) < 1e-11
+    assert rel(host(op.rhs(1.0)).sum(), sb) < 1e-13
+    d = host(op.diagonal(masked=False))
+    assert rel(d.sum(), sd) < 1e-12 and rel(d.min(), md) < 1e-11
+    assert rel(np.linalg.norm(u), nu) < 1e-13
+
+
+@pytest.mark.parametrize("row", APPENDIX_B_SOLVE)
+def test_survey_known_answers_solve_on_device(row):
+    kind, nx, ny, p, rcm, n_ebc, nu, su, mu = row
+    mesh, mngr = build_package_case(kind, nx, ny, p, True, rcm)
+    on = mngr.boundary_node_mask("ebc")
+    assert int(on.sum()) == n_ebc
+    x, y = mesh.nodes
+    vals = np.where(on, 0.2 * ((x + 1) + (y + 1)), 0.0)
+    for solver in ("matrix-free", "condensed", "three-level"):
+        if solver == "matrix-free":
+            u, info = mngr.poisson_operator(dirichlet=on).solve(1.0, vals, rtol=1e-13)
+        else:
+            sc = mngr.condensed_poisson_operator(dirichlet=on)
+            kw = {} if solver == "condensed" else {"preconditioner": "three-level"}
+            u, info = sc.solve(1.0, vals, rtol=1e-13, **kw)
+        u = host(u)
+        assert info.converged
+        assert abs(np.linalg.norm(u) - nu) / nu < 1e-12, solver
+        assert abs(u.sum() - su) / su < 1e-12, solver
+        assert abs(u.max() - mu) / mu < 1e-11, solver

@@ -111,3 +111,51 @@ def test_c_openmp_restatement_matches_python_loop():
         assert rel_l2(y, g["Au"]) < TOL
         assert rel_l2(y, so.apply_dense_batched(L, g["l2g"], g["u"])) < 1e-13
     assert so.c_threads() >= 1
+
+
+# permutation-invariant known answers taken from the live reference
+# (unmasked operator on u = sin(3x)cos(2y); Poisson solve with the BCs of config 1)
+APPENDIX_B_OPERATOR = [
+    # kind, nx, ny, p, sc, rcm, |A u|_2, max|A u|, sum b, sum diag, min diag, |u|_2
+    ("S", 4, 4, 8, True, True, 4.871362215690856, 0.6613923998438448, 4.0, 7581.257142858502,
+     0.6759259259257385, 14.8506520866344),
+    ("S", 4, 4, 8, False, False, 4.871362215690856, 0.6613923998438448, 4.0, 7581.257142858502,
+     0.6759259259257385, 14.8506520866344),
+    ("C", 4, 4, 8, True, False, 4.951536253550776, 0.6754227080246211, 4.0, 7831.9289921098,
+     0.6711123657391915, 14.81396698424245),
+    ("C", 5, 3, 4, False, False, 4.273803547745486, 1.0875759595339827, 4.0, 1716.7979340362976,
+     0.7770480519335237, 7.276314819816275),
+    ("C", 3, 3, 10, False, False, 5.863015326611709, 0.9877851353604654, 4.0, 7305.133785417742,
+     0.6685660077924067, 13.89541775044856),
+]
+APPENDIX_B_SOLVE = [
+    # kind, nx, ny, p, rcm, n EBC nodes, |u|_2, sum u, max u
+    ("S", 4, 4, 8, False, 65, 28.98108681850342, 857.0220183132233, 1.4384900658533568),
+    ("S", 4, 4, 8, True, 65, 28.98108681850335, 857.0220183132216, 1.4384900658533508),
+    ("C", 4, 4, 8, False, 65, 28.874703751175932, 853.1756357787481, 1.4384900658551993),
+    ("C", 5, 3, 4, False, 33, 14.395512215342288, 211.2447623761652, 1.438491628298089),
+]
+
+
+@pytest.mark.parametrize("row", APPENDIX_B_OPERATOR)
+def test_survey_known_answers_operator(row):
+    kind, nx, ny, p, sc, rcm, nAu, mAu, sb, sd, md, nu = row
+    r = so.run_case(kind, nx, ny, p, sc, rcm, solve=False)
+    rel = lambda a, b: abs(a - b) / abs(b)          # noqa: E731
+    assert rel(np.linalg.norm(r["Au"]), nAu) < 1e-12
+    assert rel(np.abs(r["Au"]).max(), mAu) < 1e-11
+    assert rel(r["b"].sum(), sb) < 1e-13
+    assert rel(r["diag"].sum(), sd) < 1e-12
+    assert rel(r["diag"].min(), md) < 1e-11
+    assert rel(np.linalg.norm(r["u"]), nu) < 1e-13
+
+
+@pytest.mark.parametrize("row", APPENDIX_B_SOLVE)
+def test_survey_known_answers_solve(row):
+    kind, nx, ny, p, rcm, n_ebc, nu, su, mu = row
+    r = so.run_case(kind, nx, ny, p, True, rcm)
+    assert int(r["on_ebc"].sum()) == n_ebc
+    u = r["solution"]
+    assert abs(np.linalg.norm(u) - nu) / nu < 1e-12
+    assert abs(u.sum() - su) / su < 1e-12
+    assert abs(u.max() - mu) / mu < 1e-11
