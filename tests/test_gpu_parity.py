@@ -800,8 +800,11 @@ def test_survey_known_answers_solve_on_device(row):
     mesh, mngr = build_package_case(kind, nx, ny, p, True, rcm)
     on = mngr.boundary_node_mask("ebc")
     assert int(on.sum()) == n_ebc
-    x, y = mesh.nodes
-    vals = np.where(on, 0.2 * ((x + 1) + (y + 1)), 0.0)
+    # essential values u = 0.2((x+1)+(y+1)) at the GLL points of the boundary faces
+    # (examples/poisson.py:137-140), from the oracle's restatement of that recipe
+    ref = so.run_case(kind, nx, ny, p, True, rcm, solve=False)
+    assert np.array_equal(ref["on_ebc"], on)
+    vals = ref["ebc_vals"]
     for solver in ("matrix-free", "condensed", "three-level"):
         if solver == "matrix-free":
             u, info = mngr.poisson_operator(dirichlet=on).solve(1.0, vals, rtol=1e-13)
