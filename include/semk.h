@@ -441,6 +441,8 @@ typedef struct semk_sc_op {
 #define SEMK_SC_SCHUR 1       /* S (packed) and, if sdiag_loc != NULL, its diagonal          */
 #define SEMK_SC_RHS 2         /* g_loc = f_e - A_ei A_ii^{-1} f_i                            */
 #define SEMK_SC_BACKSOLVE 4   /* u_i = A_ii^{-1} (f_i - A_ie u_e) written into u             */
+#define SEMK_SC_STORE_INV 16  /* also keep A_ii^{-1} (Ainv_out, semk_sc_element_react_f64): with W it
+                                 makes the condensed load of any later right-hand side a stream */
 #define SEMK_SC_STORE 8       /* also keep W = A_ii^{-1} A_ie (W_out), so that later back-
                                  substitutions are one streaming pass                       */
 
@@ -476,7 +478,15 @@ int semk_sc_element_react_f64(int n1, int64_t n_elem, const int64_t *slot_of_ele
                               const double *f_nodal, double f_scale, int mode, double *S_out,
                               int64_t s_stride, double *sdiag_loc, double *g_loc, double *u,
                               double *W_out, double *c_out, const double *react,
-                              int32_t *bad_flag, void *stream);
+                              double *Ainv_out, int32_t *bad_flag, void *stream);
+/* Condensed load from the stored interior operators (W: SEMK_SC_STORE, Ainv: SEMK_SC_STORE_INV):
+ * c = A_ii^{-1} f_i and g_loc = f_e - W^T f_i with f = f_scale * JxW * f_nodal[l2g] -- the RHS
+ * mode of the element kernel (compute_local_sc_system, sem/discrete.py:438-476) without
+ * refactorising the interior block. */
+int semk_sc_load_stored_f64(int n1, int64_t n_elem, const double *W, const double *Ainv,
+                            const uint32_t *l2g, const int32_t *ext_loc, const double *JxW,
+                            const double *f_nodal, double f_scale, double *g_loc, double *c_out,
+                            void *stream);
 /* u_i = c - W u_e for every element (c NULL: zero load): exterior entries of u read,
  * interior entries written; W, c from semk_sc_element_f64. */
 int semk_sc_backsolve_stored_f64(int n1, int64_t n_elem, const double *W, const double *c,

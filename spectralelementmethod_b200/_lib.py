@@ -78,7 +78,7 @@ class semk_sc_op(C.Structure):
     ]
 
 
-SC_SCHUR, SC_RHS, SC_BACKSOLVE, SC_STORE = 1, 2, 4, 8
+SC_SCHUR, SC_RHS, SC_BACKSOLVE, SC_STORE, SC_STORE_INV = 1, 2, 4, 8, 16
 
 
 class semk_sc_top(C.Structure):
@@ -183,7 +183,8 @@ SIGNATURES = {
     "semk_sc_element_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L, _P,
                                  _P, _P, _P, _P, _P, _P]),
     "semk_sc_element_react_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L,
-                                       _P, _P, _P, _P, _P, _P, _P, _P]),
+                                       _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "semk_sc_load_stored_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P, _D, _P, _P, _P]),
     "semk_sc_backsolve_stored_f64": (_I, [_I, _L, _P, _P, _P, _P, _P, _P]),
     "semk_sc_element_dense_f64": (_I, [_I, _L, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P, _P]),
     "semk_sc_apply_f64": (_I, [C.POINTER(semk_sc_op), _P, _P, _I, _P, _P]),

@@ -162,12 +162,16 @@ def _load_key(f):
 
 class CondensedPoissonOperator(object):
     def __init__(self, dof_mngr, dirichlet=None, geometric_factors=None, weight=None,
-                 store_interior="auto", reaction=None):
+                 store_interior="auto", reaction=None, store_interior_inverse=False):
         """store_interior : keep W_e = A_ii^-1 A_ie of every element (12.5 KB per element at
         p = 8) so that the interior back-substitution is one streaming pass instead of a
         refactorisation per element; "auto" = when it takes less than a third of the free
         device memory."""
         self._store_interior = store_interior
+        # store_interior_inverse: also keep A_ii^-1 of every element (19 KB at p = 8): the
+        # condensed load of ANY right-hand side then is a streaming pass (semk_sc_load_stored_f64)
+        # instead of a refactorisation per element -- for solvers that call rhs() many times
+        self._store_inverse = bool(store_interior_inverse)
         self._init_common(dof_mngr, dirichlet)
         self._init_geometry(geometric_factors, weight)
         # reaction : float[E, N, N] element-local nodal values c >= 0 (array or CUDA tensor):
@@ -326,11 +330,16 @@ class CondensedPoissonOperator(object):
         nbytes = 8 * self.n_elem * self.n_ext_loc * self.n_int_loc
         if want == "auto":
             want = 3 * nbytes < torch.cuda.mem_get_info(self.dev)[0]
+        self._Ainv = None
         if want and not isinstance(self, CondensedLocalSystems):
             self._W = torch.empty((self.n_elem, self.n_ext_loc, self.n_int_loc),
                                   dtype=torch.float64, device=self.dev)
             mode |= _lib.SC_STORE
-        self._element_pass(mode, S=self.S, sdiag_loc=sdiag, W=self._W)
+            if getattr(self, "_store_inverse", False):
+                self._Ainv = torch.empty((self.n_elem, self.n_int_loc, self.n_int_loc),
+                                         dtype=torch.float64, device=self.dev)
+                mode |= _lib.SC_STORE_INV
+        self._element_pass(mode, S=self.S, sdiag_loc=sdiag, W=self._W, Ainv=self._Ainv)
         self._diag_unmasked = self.assemble(sdiag)
         del sdiag
         self._dinv = None
@@ -343,7 +352,7 @@ class CondensedPoissonOperator(object):
         return v
 
     def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=1.0, W=None,
-                      c=None):
+                      c=None, Ainv=None):
         """One launch of sc_element_kernel (csrc/semk_sc.cu)."""
         f_nodal, f_scale = None, 1.0
         if isinstance(f, torch.Tensor):
@@ -359,7 +368,7 @@ class CondensedPoissonOperator(object):
             device.ptr(self.l2g_dev), device.ptr(self.JxW), device.ptr(f_nodal), f_scale,
             int(mode), device.ptr(S), self.s_stride, device.ptr(sdiag_loc), device.ptr(g_loc),
             device.ptr(u), device.ptr(W), device.ptr(c), device.ptr(getattr(self, "_react", None)),
-            device.ptr(self._bad), device.stream_ptr()))
+            device.ptr(Ainv), device.ptr(self._bad), device.stream_ptr()))
         if int(self._bad.item()) != 0:
             raise AssertionError("an element-interior stiffness block is not positive definite")
 
@@ -431,6 +440,19 @@ class CondensedPoissonOperator(object):
         element load ``JxW . f`` (examples/poisson.py:200; scalar or nodal f)."""
         g_loc = torch.empty((self.n_elem, self.n_ext_loc), dtype=torch.float64, device=self.dev)
         c, key = None, _load_key(f)
+        if (getattr(self, "_Ainv", None) is not None and self._W is not None and key is not None
+                and type(self) is CondensedPoissonOperator):
+            # stored interior operators: the load is a stream over W and A_ii^-1
+            f_nodal, f_scale = (self._full_vec(f, "f"), 1.0) if isinstance(f, torch.Tensor) \
+                else (None, float(f))
+            c = torch.empty((self.n_elem, self.n_int_loc), dtype=torch.float64, device=self.dev)
+            _lib.check(self._lib.semk_sc_load_stored_f64(
+                self.n1, self.n_elem, device.ptr(self._W), device.ptr(self._Ainv),
+                device.ptr(self.l2g_dev), device.ptr(self._t["ext_loc"]), device.ptr(self.JxW),
+                device.ptr(f_nodal), f_scale, device.ptr(g_loc), device.ptr(c),
+                device.stream_ptr()))
+            self._c, self._c_key = c, key
+            return self.assemble(g_loc)
         if getattr(self, "_W", None) is not None and key is not None:
             # the interior solution of this load rides along: back-substitution of the same
             # load later is a stream over W (backsolve)
@@ -771,7 +793,7 @@ class CondensedLocalSystems(CondensedPoissonOperator):
         self._schur_pass()
 
     def _element_pass(self, mode, S=None, sdiag_loc=None, g_loc=None, u=None, f=None, W=None,
-                      c=None):
+                      c=None, Ainv=None):
         self._bad.zero_()
         _lib.check(self._lib.semk_sc_element_dense_f64(
             self.n1, self.n_elem, device.ptr(self._A), device.ptr(self._f),

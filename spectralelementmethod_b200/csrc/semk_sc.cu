@@ -47,7 +47,7 @@ struct ScCfg {
   static constexpr int LDI = NI | 1;             // odd row strides: conflict-free columns
   static constexpr int LDZ = NE + 1;             // NE columns of A_ie + the load column
   static constexpr int kDoubles =
-      3 * NN + NN + NN + NI * LDI + NI * LDZ + NE * NE + NI + NE + NE + NI;
+      3 * NN + NN + NN + NI * LDI + NI * LDZ + NE * NE + NI + NE + NE + NI + NI * LDI;
   static constexpr size_t kSmem = sizeof(double) * kDoubles + sizeof(int) * (NE + 4);
   static constexpr int EPB = kScThreads / NE;    // elements per CTA step of the matvec
 };
@@ -79,6 +79,7 @@ struct ScElemArgs {
   const double *f_dense;       // [n_elem][NN]
   const uint32_t *l2g_hier;    // [n_elem][NN] global ids in hierarchical local order
   const double *react;         // [n_elem][NN] nodal reaction term added to the local diagonal, or nullptr
+  double *Ainv_out;            // [n_elem][NI][NI] A_ii^{-1} (mode STORE_INV), or nullptr
 };
 
 template <int N>
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
   double *sFe = sInv + NI;         // [NE] exterior part of the load
   double *sUe = sFe + NE;          // [NE] exterior values (back-substitution)
   double *sT = sUe + NE;           // [NI] back-substitution vector
-  int *sExt = reinterpret_cast<int *>(sT + NI);  // [NE] lexicographic index of exterior k
+  double *sX = sT + NI;            // [NI][LDI] L^{-1} (mode STORE_INV only)
+  int *sExt = reinterpret_cast<int *>(sX + NI * LDI);  // [NE] lexicographic index of exterior k
   int *sBad = sExt + NE;
   const int tid = threadIdx.x;
   const int tx = tid % kScTX, ty = tid / kScTX;
@@ -273,6 +275,29 @@ __global__ void __launch_bounds__(kScThreads) sc_element_kernel(ScElemArgs a) {
         for (int i = tid; i < NI; i += kScThreads) a.u[row[(1 + i / M) * N + 1 + i % M]] = sT[i];
       }
     }
+    // ---- keep A_ii^{-1} = L^{-T} L^{-1} (symmetric, dense): with W it turns the condensed
+    // load of ANY later right-hand side into a streaming pass (sc_load_stored_kernel) --------
+    if ((a.mode & SEMK_SC_STORE_INV) && a.Ainv_out) {
+      __syncthreads();
+      if (tid < NI) {   // column tid of L^{-1}: forward substitution of the unit vector
+        for (int i = 0; i < tid; ++i) sX[i * LDI + tid] = 0.0;
+        sX[tid * LDI + tid] = sInv[tid];
+        for (int i = tid + 1; i < NI; ++i) {
+          double acc = 0.0;
+          for (int j = tid; j < i; ++j) acc = fma(-sA[i * LDI + j], sX[j * LDI + tid], acc);
+          sX[i * LDI + tid] = acc * sInv[i];
+        }
+      }
+      __syncthreads();
+      double *Ao = a.Ainv_out + e * (int64_t)NI * NI;
+      for (int idx = tid; idx < NI * NI; idx += kScThreads) {
+        const int i = idx / NI, j = idx - i * NI;
+        const int k0 = i > j ? i : j;
+        double acc = 0.0;
+        for (int k = k0; k < NI; ++k) acc = fma(sX[k * LDI + i], sX[k * LDI + j], acc);
+        Ao[idx] = acc;
+      }
+    }
     // ---- keep the interior solution operator: W = A_ii^{-1} A_ie = L^{-T} Z and
     // c = A_ii^{-1} f_i = L^{-T} (L^{-1} f_i), one thread per column, backward substitution
     // in place; the back-substitution u_i = c - W u_e then is one streaming pass
@@ -336,6 +361,55 @@ __global__ void __launch_bounds__(256)
 #pragma unroll 8
       for (int k = 0; k < NE; ++k) acc = fma(-__ldcs(Wt + (int64_t)k * NI), sUe[grp][k], acc);
       u[l2g[e * NN + (1 + i / M) * N + 1 + i % M]] = acc;
+    }
+  }
+}
+
+// Condensed load from the stored interior operators: for every element
+//   c = A_ii^{-1} f_i,   g = f_e - W^T f_i   (A_ei A_ii^{-1} = W^T by symmetry),
+// f = f_scale * JxW * f_nodal[l2g] as in sc_element_kernel.  A pure stream over A_ii^{-1}
+// (19 KB) and W (12.5 KB per element at p = 8) instead of a refactorisation per element.
+template <int N>
+__global__ void __launch_bounds__(256)
+    sc_load_stored_kernel(int64_t n_elem, const double *__restrict__ W,
+                          const double *__restrict__ Ainv, const uint32_t *__restrict__ l2g,
+                          const int32_t *__restrict__ ext_loc, const double *__restrict__ JxW,
+                          const double *__restrict__ f_nodal, double f_scale,
+                          double *__restrict__ g_loc, double *__restrict__ c_out) {
+  using C = ScCfg<N>;
+  constexpr int NN = C::NN, NE = C::NE, NI = C::NI, M = N - 2;
+  constexpr int GT = ((NI + 31) / 32) * 32;
+  constexpr int GPB = 256 / GT;
+  __shared__ double sF[GPB][NN];
+  const int tid = threadIdx.x;
+  const int grp = tid / GT, i = tid - grp * GT;
+  const int64_t n_steps = (n_elem + GPB - 1) / GPB;
+  for (int64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
+    const int64_t e = step * GPB + grp;
+    const bool on = grp < GPB && e < n_elem;
+    __syncthreads();
+    if (on) {
+      const uint32_t *row = l2g + e * NN;
+      const double *jw = JxW + e * NN;
+      for (int k = i; k < NN; k += GT)
+        sF[grp][k] = f_scale * jw[k] * (f_nodal ? f_nodal[row[k]] : 1.0);
+    }
+    __syncthreads();
+    if (on && i < NI) {
+      // A_ii^{-1} is symmetric: row i read as column i, consecutive across the threads
+      const double *Ac = Ainv + e * (int64_t)NI * NI + i;
+      double acc = 0.0;
+#pragma unroll 7
+      for (int j = 0; j < NI; ++j)
+        acc = fma(__ldcs(Ac + (int64_t)j * NI), sF[grp][(1 + j / M) * N + 1 + j % M], acc);
+      c_out[e * (int64_t)NI + i] = acc;
+    }
+    if (on && i < NE) {
+      const double *Wr = W + e * (int64_t)NE * NI + (int64_t)i * NI;
+      double acc = sF[grp][ext_loc[i]];
+      for (int j = 0; j < NI; ++j)
+        acc = fma(-Wr[j], sF[grp][(1 + j / M) * N + 1 + j % M], acc);
+      g_loc[e * (int64_t)NE + i] = acc;
     }
   }
 }
@@ -600,7 +674,8 @@ extern "C" int semk_sc_element_f64(int n1, int64_t n_elem, const int64_t *slot_o
                                    int32_t *bad_flag, void *stream) {
   return semk_sc_element_react_f64(n1, n_elem, slot_of_elem, G, g_patch_stride, elems_per_patch,
                                    D, ext_loc, l2g, JxW, f_nodal, f_scale, mode, S_out, s_stride,
-                                   sdiag_loc, g_loc, u, W_out, c_out, nullptr, bad_flag, stream);
+                                   sdiag_loc, g_loc, u, W_out, c_out, nullptr, nullptr, bad_flag,
+                                   stream);
 }
 
 extern "C" int semk_sc_element_react_f64(int n1, int64_t n_elem, const int64_t *slot_of_elem,
@@ -611,11 +686,14 @@ extern "C" int semk_sc_element_react_f64(int n1, int64_t n_elem, const int64_t *
                                          double f_scale, int mode, double *S_out,
                                          int64_t s_stride, double *sdiag_loc, double *g_loc,
                                          double *u, double *W_out, double *c_out,
-                                         const double *react, int32_t *bad_flag, void *stream) {
+                                         const double *react, double *Ainv_out,
+                                         int32_t *bad_flag, void *stream) {
   SEMK_REQUIRE(n_elem > 0 && G && D && ext_loc && bad_flag &&
                    elems_per_patch > 0 && g_patch_stride > 0,
                "semk_sc_element_f64: bad argument");
-  SEMK_REQUIRE(mode != 0 && (mode & ~15) == 0, "semk_sc_element_f64: bad mode");
+  SEMK_REQUIRE(mode != 0 && (mode & ~31) == 0, "semk_sc_element_f64: bad mode");
+  SEMK_REQUIRE(!(mode & SEMK_SC_STORE_INV) || Ainv_out,
+               "semk_sc_element_f64: STORE_INV needs Ainv_out");
   SEMK_REQUIRE(!(mode & SEMK_SC_STORE) || W_out, "semk_sc_element_f64: STORE needs W_out");
   SEMK_REQUIRE(!c_out || (mode & (SEMK_SC_RHS | SEMK_SC_BACKSOLVE)),
                "semk_sc_element_f64: c_out needs a load (RHS or BACKSOLVE mode)");
@@ -656,6 +734,7 @@ extern "C" int semk_sc_element_react_f64(int n1, int64_t n_elem, const int64_t *
   a.f_dense = nullptr;
   a.l2g_hier = nullptr;
   a.react = react;
+  a.Ainv_out = Ainv_out;
   return launch_sc_element(n1, a, stream);
 }
 
@@ -704,6 +783,7 @@ extern "C" int semk_sc_element_dense_f64(int n1, int64_t n_elem, const double *A
   a.f_dense = f_hier;
   a.l2g_hier = l2g_hier;
   a.react = nullptr;
+  a.Ainv_out = nullptr;
   return launch_sc_element(n1, a, stream);
 }
 
@@ -739,6 +819,27 @@ extern "C" int semk_sc_backsolve_stored_f64(int n1, int64_t n_elem, const double
   SEMK_DISPATCH_SC(n1, SEMK_CALL)
 #undef SEMK_CALL
   SEMK_LAUNCH_CHECK("sc_backsolve_stored_kernel");
+  return SEMK_OK;
+}
+
+extern "C" int semk_sc_load_stored_f64(int n1, int64_t n_elem, const double *W, const double *Ainv,
+                                       const uint32_t *l2g, const int32_t *ext_loc,
+                                       const double *JxW, const double *f_nodal, double f_scale,
+                                       double *g_loc, double *c_out, void *stream) {
+  SEMK_REQUIRE(n_elem > 0 && W && Ainv && l2g && ext_loc && JxW && g_loc && c_out,
+               "semk_sc_load_stored_f64: bad argument");
+  cudaStream_t st = semk_stream(stream);
+#define SEMK_CALL(NV)                                                                      \
+  do {                                                                                     \
+    constexpr int GT = ((ScCfg<NV>::NI + 31) / 32) * 32, GPB = 256 / GT;                   \
+    const int64_t steps = (n_elem + GPB - 1) / GPB;                                        \
+    const unsigned grid = (unsigned)(steps < 148 * 16 ? steps : 148 * 16);                 \
+    sc_load_stored_kernel<NV><<<grid, 256, 0, st>>>(n_elem, W, Ainv, l2g, ext_loc, JxW,    \
+                                                    f_nodal, f_scale, g_loc, c_out);       \
+  } while (0)
+  SEMK_DISPATCH_SC(n1, SEMK_CALL)
+#undef SEMK_CALL
+  SEMK_LAUNCH_CHECK("sc_load_stored_kernel");
   return SEMK_OK;
 }
 

@@ -563,7 +563,8 @@ class PoissonBlockPreconditioner(object):
             rho = op.x_phys[:, 0, :]
             reaction = torch.where(rho > 0, op.JxW / rho.clamp_min(1e-300), torch.zeros_like(rho))
         self.sc = sdm.condensed_poisson_operator(dirichlet=ess_s, weight=lambda x, y: x,
-                                                 reaction=reaction)
+                                                 reaction=reaction, store_interior=True,
+                                                 store_interior_inverse=True)
         dev = op.dev
         self.free_s = torch.from_numpy(~ess_s).to(dev)                 # I
         self.gamma = torch.from_numpy(ess_s & ~ess_w).to(dev)          # G
