@@ -207,7 +207,15 @@ typedef struct semk_op {
                                column (patch_kernel, csrc/semk_apply.cu); 1 = a column lane +
                                a row lane per element column (ho_patch_kernel, csrc/semk_ho.cu;
                                n1 >= 9): twice the warps at half the registers, for the high
-                               orders where the column mapping is latency-bound */
+                               orders where the column mapping is latency-bound; 2 = the column
+                               mapping with an arithmetic gather / write-out for regularly
+                               numbered structured meshes (csrc/semk_box.cu; needs box_ld) */
+  int64_t box_ld;           /* kernel_variant 2: node-id stride between consecutive node rows of the
+                               lattice.  A patch whose PATCH_HDR word 3 is non-zero is a tile box:
+                               node (m, t) of its slot le = lx*by + ly has the id
+                               base + (lx*p + m)*box_ld + ly*p + t (base = PATCH_HDR word 4) and
+                               carries no Dirichlet node; word 3 = mask of its non-empty slots.
+                               Patches with word 3 == 0 use the tables.  0 = not a lattice */
 } semk_op;
 
 /* number of doubles the `partials` scratch of an operator must hold
@@ -315,6 +323,20 @@ typedef struct semk_stage {
 int semk_poisson_apply_host_staged_f64(const semk_op *op, const semk_stage *stages, int n_stages,
                                        const double *u_host, double *y_host, double *d_u,
                                        double *d_y, int flags, void *stream);
+
+/* A batch of n_applies independent applies y_k = A u_k on host buffers (u_hosts[k],
+ * y_hosts[k]: pinned host memory, [n_nodes] each), every one cut into the same stages as
+ * above, with TWO device scratch sets (d_u0, d_y0), (d_u1, d_y1) used alternately: besides
+ * the overlap inside one apply, the upload of apply k+1 overlaps the download of apply k,
+ * so the full-duplex link is busy in both directions for the whole call (one apply alone
+ * leaves the first upload and the last download uncovered).  The many-right-hand-sides form
+ * of the reference's per-solve loop `for f in rhs: A @ f` over the assembled operator
+ * (sem/discrete.py:491-510 + examples/squirmer-axisymmetric.py:284-295).  Blocks until every
+ * y_hosts[k] is complete.  Results are bit-identical to semk_poisson_apply_f64. */
+int semk_poisson_apply_host_batch_f64(const semk_op *op, const semk_stage *stages, int n_stages,
+                                      int n_applies, const double *const *u_hosts,
+                                      double *const *y_hosts, double *d_u0, double *d_y0,
+                                      double *d_u1, double *d_y1, int flags, void *stream);
 
 /* ------------------------------------------------------------------------
  * K3: generic assembly  out[g] = sum over element-local entries mapped to g

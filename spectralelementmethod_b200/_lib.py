@@ -65,6 +65,7 @@ class semk_op(C.Structure):
         ("n_shared_chunk", C.c_int64), ("shared_chunk", C.c_void_p),
         ("partials", C.c_void_p), ("D_host", C.c_void_p), ("dirichlet", C.c_void_p),
         ("kernel_variant", C.c_int64),
+        ("box_ld", C.c_int64),
     ]
 
 
@@ -178,6 +179,9 @@ SIGNATURES = {
                                 C.POINTER(semk_pcg_info), _P]),
     "semk_poisson_apply_host_staged_f64": (_I, [C.POINTER(semk_op), C.POINTER(semk_stage), _I, _P, _P,
                                                 _P, _P, _I, _P]),
+    "semk_poisson_apply_host_batch_f64": (_I, [C.POINTER(semk_op), C.POINTER(semk_stage), _I, _I,
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                               _P, _P, _P, _P, _I, _P]),
     "semk_scratch_row_stride": (_I, [_I, _I]),
     "semk_scale_gfactors_f64": (_I, [_I, _L, _P, _P, _P, _L, _I, _P]),
     "semk_sc_element_f64": (_I, [_I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _P, _D, _I, _P, _L, _P,

@@ -206,3 +206,8 @@ __host__ __device__ inline PatchSmem patch_smem_layout(int N, int PE, int mode,
 int semk_ho_launch(const semk_op &op, const double *u, double *y, int flags, double *partials,
                    cudaStream_t st, int *grid_out, int64_t pb, int64_t pe);
 int64_t semk_ho_resident(int n1, int elems_per_patch, size_t smem);
+// semk_box.cu: the BOX instantiations of the patch kernel (regular structured numberings);
+// dm_eo points at the caller's DMatEO
+int semk_box_launch(const semk_op &op, const void *dm_eo, const double *u, double *y, int flags,
+                    double *partials, cudaStream_t st, int *grid_out, int64_t pb, int64_t pe);
+int64_t semk_box_resident(int n1, int elems_per_patch, size_t smem);

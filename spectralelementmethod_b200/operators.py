@@ -18,6 +18,8 @@ kernels behind the C ABI (include/semk.h); nothing here falls back to NumPy.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -198,13 +200,24 @@ class PoissonOperator(object):
         # thread mapping of the apply kernel: "column" (one thread per element column) or
         # "pair" (a column lane + a row lane per element column; high orders, n1 >= 9)
         if mode == "auto":
-            # measured (profiles/r02_sweep_pair.json): the pair mapping only wins at p = 16
-            mode = "pair" if n1 == 17 else "column"
-        if mode not in ("column", "pair"):
-            raise ValueError("mode must be 'auto', 'column' or 'pair'")
-        self.kernel_variant = 1 if mode == "pair" else 0
-        self.kernel_name = ("ho_patch_kernel<%d,%d>" if self.kernel_variant else
-                            "patch_kernel<%d,%d,APPLY>") % (n1, pe)
+            mode = os.environ.get("SEMK_APPLY_MODE", "auto")      # A/B runs
+        # "box": the column mapping with an arithmetic gather (csrc/semk_box.cu) -- tiled
+        # structured meshes whose numbering is a regular lattice; verified patch by patch
+        # on the device below (_mark_box_patches), anything else falls back to "column"
+        box_ok = (not user_order and self._tile == _TILES[pe] and pe in (8, 16)
+                  and 3 <= n1 <= 17 and getattr(mesh, "_structured_shape", None) is not None)
+        if mode == "auto":
+            # measured: the pair mapping only wins at p = 16 (profiles/r02_sweep_pair.json);
+            # the box gather is 1.5 - 2.5 % ahead of the table-driven one wherever it applies
+            # (profiles/r02_box_ab.txt)
+            mode = "pair" if n1 == 17 else ("box" if box_ok else "column")
+        if mode not in ("column", "pair", "box"):
+            raise ValueError("mode must be 'auto', 'column', 'pair' or 'box'")
+        if mode == "box" and not box_ok:
+            mode = "column"          # not a tiled structured mesh: the table-driven kernel
+        self.kernel_variant = {"column": 0, "pair": 1, "box": 2}[mode]
+        self.kernel_name = {0: "patch_kernel<%d,%d,APPLY>", 1: "ho_patch_kernel<%d,%d>",
+                            2: "patch_kernel<%d,%d,APPLY,BOX>"}[self.kernel_variant] % (n1, pe)
         actual = int(self._lib.semk_resident_ctas_variant(
             self.kernel_variant, n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
             int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_INV_STRIDE])))
@@ -295,6 +308,15 @@ class PoissonOperator(object):
             torch.cuda.current_stream().synchronize()
             del w
         del x_phys
+        self.box_ld = 0
+        if self.kernel_variant == 2:
+            self.box_ld = self._mark_box_patches(l2g, t)
+            if self.box_ld == 0:             # the numbering is not a regular lattice
+                self.kernel_variant = 0
+                self.kernel_name = "patch_kernel<%d,%d,APPLY>" % (n1, pe)
+                self.resident_ctas = int(self._lib.semk_resident_ctas_variant(
+                    0, n1, pe, g_patch_stride_of(n1, pe), int(sc[_lib.PS_PN_STRIDE]),
+                    int(sc[_lib.PS_EL_STRIDE]), int(sc[_lib.PS_INV_STRIDE])))
         if not keep_l2g:
             self.l2g_dev = None
 
@@ -331,11 +353,52 @@ class PoissonOperator(object):
         op.D_host = self.tab.D_host.ctypes.data
         op.dirichlet = self.dirichlet_dev.data_ptr() if self.has_dirichlet else None
         op.kernel_variant = self.kernel_variant
+        op.box_ld = self.box_ld
         self._op = op
         self._masked_flags = (MASK_IN | MASK_OUT | DIRICHLET_IDENTITY) if self.has_dirichlet else 0
         self._dinv = None
 
     # -- helpers ---------------------------------------------------------------------
+    def _mark_box_patches(self, l2g, t):
+        """kernel_variant 2 (csrc/semk_box.cu): find the patches that are regular tile boxes
+        -- node (m, t) of slot le = lx*by + ly has the id base + (lx*p + m)*ld + ly*p + t --
+        and carry no Dirichlet node, and write the mask of their non-empty slots into word 3
+        of their device header (0 = table-driven path).  Runs on the device.  Returns the row
+        stride ``ld`` of the lattice, 0 if no patch qualifies."""
+        n1, pe, p = self.n1, self.elems_per_patch, self.n1 - 1
+        bx, by = self._tile
+        if l2g.shape[0] == 0 or p < 1:
+            return 0
+        ld = int(l2g[0, n1]) - int(l2g[0, 0])
+        if ld < by * p + 1 or self.n_nodes >= 2 ** 31:
+            return 0
+        L = self.l2g_dev.view(self.n_elem, n1 * n1)
+        base = L[:, 0].clone()
+        k = torch.arange(n1, device=self.dev, dtype=torch.int32)
+        pattern = (k[:, None] * ld + k[None, :]).reshape(-1)
+        ok_elem = ((L - base[:, None]) == pattern[None, :]).all(dim=1)
+        if self.dirichlet_host is not None and self.has_dirichlet:
+            dmask = torch.from_numpy(self.dirichlet_host).to(self.dev)
+            ok_elem &= ~dmask[L.long()].any(dim=1)
+            del dmask
+        slots = t[_lib.PA_ELEM_OF_SLOT]
+        n_patch = int(self.n_patch)
+        if slots.numel() < n_patch * pe:
+            slots = torch.cat([slots, slots.new_full((n_patch * pe - slots.numel(),), -1)])
+        slots = slots.view(n_patch, pe)
+        present = slots >= 0
+        idx = slots.clamp(min=0)
+        le = torch.arange(pe, device=self.dev, dtype=torch.int64)
+        off = ((le // by) * p * ld + (le % by) * p).to(torch.int32)
+        hdr = t[_lib.PA_PATCH_HDR].view(n_patch, 8)
+        base_p = hdr[:, 4]
+        good = ok_elem[idx] & (base[idx] == base_p[:, None] + off[None, :])
+        ok_patch = (good | ~present).all(dim=1) & present[:, 0]
+        mask = (present.to(torch.int64) << le[None, :]).sum(dim=1)
+        hdr[:, 3] = torch.where(ok_patch, mask, torch.zeros_like(mask)).to(torch.int32)
+        self.n_box_patches = int(ok_patch.sum().item())
+        return ld if self.n_box_patches > 0 else 0
+
     def _vec(self, v, name="vector"):
         if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float64
                 and v.is_contiguous() and v.numel() == self.n_nodes):
@@ -460,6 +523,31 @@ class PoissonOperator(object):
             C.byref(self._op), device.ptr(u_host), device.ptr(y_host), device.ptr(scratch[0]),
             device.ptr(scratch[1]), int(self._masked_flags), device.stream_ptr()))
         return y_host
+
+    def apply_host_many(self, u_hosts, y_hosts, scratch=None, stages=16):
+        """A batch of independent applies on HOST buffers (lists of pinned torch CPU tensors
+        or numpy arrays, float64[n_nodes] each): like ``apply_host`` per pair, but with two
+        device scratch sets, so that the upload of apply k+1 overlaps the download of apply
+        k (semk_poisson_apply_host_batch_f64).  ``scratch``: four device vectors
+        (d_u0, d_y0, d_u1, d_y1) or None.  Synchronised on return."""
+        if len(u_hosts) != len(y_hosts):
+            raise ValueError("u_hosts and y_hosts must have the same length")
+        n = len(u_hosts)
+        if scratch is None:
+            scratch = tuple(self.new_vector() for _ in range(4))
+        if len(scratch) != 4:
+            raise ValueError("scratch must hold four device vectors")
+        for a in list(u_hosts) + list(y_hosts):
+            if int(a.numel() if isinstance(a, torch.Tensor) else a.size) != self.n_nodes:
+                raise ValueError("host buffers must hold n_nodes float64 values")
+        arr, n_st = self.stage_table(stages)
+        ups = (C.c_void_p * max(n, 1))(*[device.ptr(a) for a in u_hosts])
+        downs = (C.c_void_p * max(n, 1))(*[device.ptr(a) for a in y_hosts])
+        _lib.check(self._lib.semk_poisson_apply_host_batch_f64(
+            C.byref(self._op), arr, n_st, n, ups, downs, device.ptr(scratch[0]),
+            device.ptr(scratch[1]), device.ptr(scratch[2]), device.ptr(scratch[3]),
+            int(self._masked_flags), device.stream_ptr()))
+        return y_hosts
 
     def assemble(self, loc, out=None, mask=False, fill_dirichlet=0.0):
         """Assemble an element-local field ``loc[n_slot_elems, NN]`` (engine
