@@ -423,7 +423,7 @@ extern "C" int64_t semk_resident_ctas_variant(int kernel_variant, int n1, int el
     return semk_resident_ctas(n1, elems_per_patch, g_patch_stride, pn_patch_stride,
                               eloc_patch_stride, inv_patch_stride);
   if ((kernel_variant != 1 && kernel_variant != 2) || !pe_supported(elems_per_patch) ||
-      elems_per_patch == 32)
+      (kernel_variant == 1 && elems_per_patch == 32))
     return -1;
   const size_t smem = patch_smem_layout(n1, elems_per_patch, MODE_APPLY, g_patch_stride,
                                         pn_patch_stride, eloc_patch_stride, inv_patch_stride)

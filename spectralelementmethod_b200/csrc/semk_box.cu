@@ -17,30 +17,33 @@ namespace {
 #define SEMK_BOX_MAX_N1 17
 #endif
 
-template <int NV, bool OK = (NV >= SEMK_BOX_MIN_N1 && NV <= SEMK_BOX_MAX_N1)>
+// 32-element patches (4 x 8 tiles) exist for the low orders only, as in semk_apply.cu
+constexpr int kBoxBigPatchMaxN1 = 7;
+template <int NV, int PE>
+constexpr bool box_ok() {
+  return NV >= SEMK_BOX_MIN_N1 && NV <= SEMK_BOX_MAX_N1 && (PE != 32 || NV <= kBoxBigPatchMaxN1);
+}
+
+template <int NV, int PE, bool OK = box_ok<NV, PE>()>
 struct BoxN {
-  template <int PE>
   static int run(const semk_op &op, const DMatEO &dm, const double *u, double *y, int flags,
                  double *partials, cudaStream_t st, int *grid_out, int64_t pb, int64_t pe) {
     return PatchLaunch<PE, MODE_APPLY, true>::template run<NV>(op, dm, u, nullptr, y, flags, 0.0,
                                                                partials, st, grid_out, pb, pe);
   }
-  template <int PE>
   static int occupancy(size_t smem, int *per_sm, int *sms) {
     return PatchLaunch<PE, MODE_APPLY, true>::template occupancy<NV>(smem, per_sm, sms);
   }
 };
-template <int NV>
-struct BoxN<NV, false> {
-  template <int PE>
+template <int NV, int PE>
+struct BoxN<NV, PE, false> {
   static int run(const semk_op &, const DMatEO &, const double *, double *, int, double *,
                  cudaStream_t, int *, int64_t, int64_t) {
-    semk_set_error("box kernel: compiled for 3 <= n1 <= 17 only");
+    semk_set_error("box kernel: compiled for 3 <= n1 <= 17 (32-element patches: n1 <= 7) only");
     return SEMK_ERR_UNSUPPORTED;
   }
-  template <int PE>
   static int occupancy(size_t, int *, int *) {
-    semk_set_error("box kernel: compiled for 3 <= n1 <= 17 only");
+    semk_set_error("box kernel: compiled for 3 <= n1 <= 17 (32-element patches: n1 <= 7) only");
     return SEMK_ERR_UNSUPPORTED;
   }
 };
@@ -57,12 +60,14 @@ int semk_box_launch(const semk_op &op, const void *dm_eo, const double *u, doubl
 #define SEMK_CALL(NV)                                                                          \
   do {                                                                                         \
     int rc;                                                                                    \
-    if (op.elems_per_patch == 16) {                                                            \
-      rc = BoxN<NV>::template run<16>(op, dm, u, y, flags, partials, st, grid_out, pb, pe);    \
+    if (op.elems_per_patch == 32) {                                                            \
+      rc = BoxN<NV, 32>::run(op, dm, u, y, flags, partials, st, grid_out, pb, pe);             \
+    } else if (op.elems_per_patch == 16) {                                                     \
+      rc = BoxN<NV, 16>::run(op, dm, u, y, flags, partials, st, grid_out, pb, pe);             \
     } else if (op.elems_per_patch == 8) {                                                      \
-      rc = BoxN<NV>::template run<8>(op, dm, u, y, flags, partials, st, grid_out, pb, pe);     \
+      rc = BoxN<NV, 8>::run(op, dm, u, y, flags, partials, st, grid_out, pb, pe);              \
     } else {                                                                                   \
-      semk_set_error("box kernel: elems_per_patch must be 8 or 16");                           \
+      semk_set_error("box kernel: elems_per_patch must be 8, 16 or 32");                       \
       rc = SEMK_ERR_UNSUPPORTED;                                                               \
     }                                                                                          \
     if (rc != SEMK_OK) return rc;                                                              \
@@ -78,10 +83,12 @@ int64_t semk_box_resident(int n1, int elems_per_patch, size_t smem) {
 #define SEMK_CALL(NV)                                                         \
   do {                                                                        \
     int rc;                                                                   \
-    if (elems_per_patch == 16) {                                              \
-      rc = BoxN<NV>::template occupancy<16>(smem, &per_sm, &sms);             \
+    if (elems_per_patch == 32) {                                              \
+      rc = BoxN<NV, 32>::occupancy(smem, &per_sm, &sms);                      \
+    } else if (elems_per_patch == 16) {                                       \
+      rc = BoxN<NV, 16>::occupancy(smem, &per_sm, &sms);                      \
     } else if (elems_per_patch == 8) {                                        \
-      rc = BoxN<NV>::template occupancy<8>(smem, &per_sm, &sms);              \
+      rc = BoxN<NV, 8>::occupancy(smem, &per_sm, &sms);                       \
     } else                                                                    \
       rc = SEMK_ERR_UNSUPPORTED;                                              \
     if (rc != SEMK_OK) return rc;                                             \

@@ -204,8 +204,9 @@ class PoissonOperator(object):
         # "box": the column mapping with an arithmetic gather (csrc/semk_box.cu) -- tiled
         # structured meshes whose numbering is a regular lattice; verified patch by patch
         # on the device below (_mark_box_patches), anything else falls back to "column"
-        box_ok = (not user_order and self._tile == _TILES[pe] and pe in (8, 16)
-                  and 3 <= n1 <= 17 and getattr(mesh, "_structured_shape", None) is not None)
+        box_ok = (not user_order and self._tile == _TILES[pe] and 3 <= n1 <= 17
+                  and (pe in (8, 16) or (pe == 32 and n1 <= 7))
+                  and getattr(mesh, "_structured_shape", None) is not None)
         if mode == "auto":
             # measured: the pair mapping only wins at p = 16 (profiles/r02_sweep_pair.json);
             # the box gather is 1.5 - 2.5 % ahead of the table-driven one wherever it applies
@@ -395,6 +396,7 @@ class PoissonOperator(object):
         good = ok_elem[idx] & (base[idx] == base_p[:, None] + off[None, :])
         ok_patch = (good | ~present).all(dim=1) & present[:, 0]
         mask = (present.to(torch.int64) << le[None, :]).sum(dim=1)
+        mask = torch.where(mask >= 2 ** 31, mask - 2 ** 32, mask)      # uint32 bits in an int32
         hdr[:, 3] = torch.where(ok_patch, mask, torch.zeros_like(mask)).to(torch.int32)
         self.n_box_patches = int(ok_patch.sum().item())
         return ld if self.n_box_patches > 0 else 0

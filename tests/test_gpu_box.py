@@ -32,6 +32,8 @@ CASES = [
     ("C", 5, 17, 3, 8),
     ("C", 8, 32, 2, 16),                      # n1 = 3: one interior node row per tile
     ("C", 6, 24, 5, 16),                      # odd order: node rows of a tile start at odd ids
+    ("C", 12, 24, 4, 32),                     # 4 x 8 tiles (the automatic patch size for p <= 4)
+    ("C", 9, 19, 3, 32),                      # ... ragged
 ]
 
 
@@ -111,7 +113,7 @@ def test_box_mode_falls_back_when_the_numbering_is_not_a_lattice():
     mesh, mngr = build_package_case("C", 4, 16, 4, False, False)
     op = mngr.poisson_operator(mode="box", elems_per_patch=16, elem_order=np.arange(64)[::-1].copy())
     assert op.kernel_variant == 0
-    # 32- and 4-element patches have no box instantiation
+    # 4-element patches have no box instantiation
     op = mngr.poisson_operator(mode="box", elems_per_patch=4)
     assert op.kernel_variant == 0
     # the automatic choice on a lattice is the box kernel
