@@ -382,6 +382,17 @@ class DistributedOperator(object):
             dot_out -= (dup * dup).sum()
         return y
 
+    def finish(self, y, u):
+        """Second half of ``apply`` for a local result ``y`` computed elsewhere (the staged
+        host apply): sum the interface columns across neighbours and re-impose the Dirichlet
+        identity rows on them, in place."""
+        if self.halo is not None:
+            return self.halo.exchange(y, u, self._dir_u8, None)
+        self.exchange_add(y)
+        if self._fix_ids is not None:
+            y[self._fix_ids] = u[self._fix_ids]
+        return y
+
     def owned_dot(self, a, b):
         """a . b over the owned prefix, summed over the ranks (1-element tensor)."""
         n = self.part.n_owned
@@ -654,6 +665,38 @@ class DistributedPoisson(object):
 
     def apply(self, u, out=None, dot_out=None):
         return self.dop.apply(u, out=out, dot_out=dot_out)
+
+    def host_operator(self):
+        """The local operator of the staged host apply: the same elements in the plain tile
+        order (the boundary-columns-first order of ``self.op`` would make the very first stage
+        need both ends of u, i.e. all of it, before anything can be computed).  Built on first
+        use."""
+        if getattr(self, "_op_host", None) is None:
+            self._op_host = (self.mngr.poisson_operator(dirichlet=self.on_ebc,
+                                                        elems_per_patch=self.op.elems_per_patch)
+                             if self.op._boundary_first else self.op)
+        return self._op_host
+
+    def apply_host(self, u_host, y_host, scratch=None, stages=16):
+        """y = A_global u on HOST buffers (pinned float64[n_local] in this rank's node order):
+        the rank-local apply runs as the staged pipeline of ``PoissonOperator.apply_host``
+        (upload of stage i+1, compute of stage i and download of stage i-1 overlap), then the
+        interface columns are exchanged on the device and those two columns are downloaded
+        again.  Collective: every rank calls it.  ``scratch``: (d_u, d_y) device vectors."""
+        op = self.host_operator()
+        if scratch is None:
+            scratch = (op.new_vector(), op.new_vector())
+        op.apply_host(u_host, y_host, scratch, stages=stages)
+        d_u, d_y = scratch[0], scratch[1]
+        self.dop.finish(d_y, d_u)
+        part, NY, n = self.part, self.part.NY, self.part.n_local
+        yh = y_host if isinstance(y_host, torch.Tensor) else torch.from_numpy(y_host)
+        if part.left is not None:
+            yh[:NY].copy_(d_y[:NY], non_blocking=True)
+        if part.right is not None:
+            yh[n - NY:].copy_(d_y[n - NY:], non_blocking=True)
+        torch.cuda.current_stream(op.dev).synchronize()
+        return y_host
 
     def diagonal(self):
         d = self.op.diagonal(masked=False)

@@ -139,6 +139,16 @@ def check_one(dp, gop, gid, ug, want, dot_ref, bg, xg, dev):
     assert float((dp.diagonal() - gop.diagonal()[gid]).abs().max()) < 1e-11
     assert float((dp.rhs(1.0) - gop.rhs(1.0)[gid]).abs().max()) < 1e-14
 
+    # the host-buffer path: staged local apply + device-side exchange + second download of the
+    # exchanged columns; bitwise equal to the same two steps on device-resident vectors
+    uh = torch.empty(u.numel(), dtype=torch.float64).pin_memory()
+    yh = torch.empty(u.numel(), dtype=torch.float64).pin_memory()
+    uh.copy_(u)
+    dp.apply_host(uh, yh, stages=3)
+    y_dev = dp.dop.finish(dp.host_operator().apply(u), u)
+    assert torch.equal(yh.to(dev), y_dev)
+    assert float((y_dev - want[gid]).norm() / want.norm()) < 1e-13
+
     b = dp.lift(dp.rhs(1.0), None)
     assert float((b - bg[gid]).abs().max()) < 1e-13
     x, it, rel, ok = dp.solve_pcg(b, rtol=1e-12, check_every=10)

@@ -105,6 +105,8 @@ def _worker(rank, world, port, out):
         ug = rng.standard_normal(part.n_global)
         u = torch.from_numpy(ug[gid].copy())
         y = dop.apply(u)
+        # the two halves separately (the staged host apply computes the local part elsewhere)
+        y2 = dop.finish(local_apply(u, None, None), u)
         dotv = dop.owned_dot(u, u)
 
         # RHS / diagonal / lifted system, assembled across ranks
@@ -124,7 +126,7 @@ def _worker(rank, world, port, out):
         x0 = torch.where(torch.from_numpy(on), bh, torch.zeros_like(bh))
         it, rel, ok = distributed_pcg(dop, bh, x0, 1.0 / dl, CpuKernels(on), rtol=1e-13,
                                       maxiter=3000, check_every=7)
-        res = dict(gid=gid, y=y.numpy(), dot=float(dotv), x=x0.numpy(), it=it, ok=ok, rel=rel,
+        res = dict(gid=gid, y=y.numpy(), y2=y2.numpy(), dot=float(dotv), x=x0.numpy(), it=it, ok=ok, rel=rel,
                    n_owned=part.n_owned, on=on, b=bl.numpy(), d=dl.numpy())
         torch.save(res, os.path.join(out, "rank%d.pt" % rank))
     finally:
@@ -188,6 +190,7 @@ def test_two_rank_apply_matches_global_operator(two_rank_results):
     want = M * (ref["A"] @ (M * ug)) + (1 - M) * ug
     for r in two_rank_results:
         assert rel_l2(r["y"], want[r["gid"]]) < 1e-12
+        assert np.array_equal(r["y2"], r["y"])          # finish(local_apply(u), u) == apply(u)
         assert np.array_equal(r["on"], ref["on"][r["gid"]])
         assert rel_l2(r["b"], ref["b"][r["gid"]]) < 1e-13
         assert rel_l2(r["d"], (M * ref["A"].diagonal() + (1 - M))[r["gid"]]) < 1e-13
