@@ -106,7 +106,11 @@ enum semk_plan_array {
                                  {node0, dn, a0, da, b0, db, len, Dirichlet mask};
                                  node_k = node0 + k dn, slots a0 + k da (lower patch), b0 + k db */
   SEMK_PA_PATCH_HDR = 15,     /* uint32 [n_patch][8]  {n nodes, n private, first interface slot, 0,
-                                 base node id, PNBLK block, ELBLK block, INVBLK block}        */
+                                 base node id, PNBLK block, ELBLK block, INVBLK block}; word 3
+                                 is left 0 by the plan builder: a caller that selects
+                                 semk_op.kernel_variant 2 writes the non-empty-slot mask of every
+                                 patch it has verified to be a regular tile box there (see
+                                 semk_op.box_ld)                                              */
   SEMK_PA_PATCH_MAXNODE = 16, /* uint32 [n_patch]     largest node id of the patch (the smallest is
                                  PATCH_HDR word 4)                                            */
   SEMK_PA_CHUNK_MAXPATCH = 17,/* int32  [n_shared_chunk] higher of the two patches of a chunk; the
