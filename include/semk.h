@@ -162,6 +162,12 @@ enum semk_plan_scalar {
 int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
                          const int64_t *elem_order, int64_t n_order, int elems_per_patch,
                          const uint8_t *dirichlet, semk_hostplan **out);
+/* The same with an explicit thread count for the per-patch passes (0 = what OpenMP would use;
+ * under torchrun OMP_NUM_THREADS is 1, so set-up code passes its own share of the box).  The
+ * tables are byte-identical for every thread count. */
+int semk_hostplan_create_mt(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
+                            const int64_t *elem_order, int64_t n_order, int elems_per_patch,
+                            const uint8_t *dirichlet, int n_threads, semk_hostplan **out);
 int64_t semk_hostplan_scalar(const semk_hostplan *plan, int which);
 const void *semk_hostplan_array(const semk_hostplan *plan, int which, int64_t *n_bytes);
 void semk_hostplan_destroy(semk_hostplan *plan);

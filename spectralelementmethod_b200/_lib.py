@@ -152,6 +152,7 @@ SIGNATURES = {
     "semk_last_error": (C.c_char_p, []),
     "semk_device_available": (_I, []),
     "semk_hostplan_create": (_I, [_I, _L, _L, _P, _P, _L, _I, _P, C.POINTER(_P)]),
+    "semk_hostplan_create_mt": (_I, [_I, _L, _L, _P, _P, _L, _I, _P, _I, C.POINTER(_P)]),
     "semk_hostplan_scalar": (_L, [_P, _I]),
     "semk_hostplan_array": (_P, [_P, _I, C.POINTER(_L)]),
     "semk_hostplan_destroy": (None, [_P]),
@@ -306,8 +307,10 @@ def require_device():
                            "the operator engine has no CPU fallback")
 
 
-def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None):
-    """Run the host plan builder; returns (scalars dict, arrays dict of numpy copies)."""
+def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None, threads=None):
+    """Run the host plan builder (``threads``: for its per-patch passes; default
+    ``host_threads()``; same tables for any count); returns (scalars dict, arrays dict of
+    numpy copies)."""
     lib = load()
     l2g = np.ascontiguousarray(l2g, dtype=np.uint32).reshape(-1, n1 * n1)
     n_elem = l2g.shape[0]
@@ -325,8 +328,10 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
         dir_p = dirichlet.ctypes.data
     handle = _P()
     n_order = 0 if elem_order is None else int(elem_order.size)
-    check(lib.semk_hostplan_create(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p, n_order,
-                                   int(elems_per_patch), dir_p, C.byref(handle)))
+    check(lib.semk_hostplan_create_mt(int(n1), n_elem, int(n_nodes), l2g.ctypes.data, order_p, n_order,
+                                      int(elems_per_patch), dir_p,
+                                      int(host_threads() if threads is None else threads),
+                                      C.byref(handle)))
     try:
         scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(PS_COUNT)}
         arrays = {}

@@ -19,7 +19,7 @@ done
 o=semk_hostplan.o
 if [ ! -f "$o" ] || [ semk_hostplan.cpp -nt "$o" ] || [ ../../include/semk.h -nt "$o" ]; then
   rm -f "$o"
-  g++ -O3 -std=c++17 -fPIC -c semk_hostplan.cpp -o "$o" &
+  g++ -O3 -std=c++17 -fPIC -fopenmp -c semk_hostplan.cpp -o "$o" &
   PIDS="$PIDS $!"
 fi
 o=semk_hostnum.o

@@ -21,6 +21,11 @@
 #include <unordered_map>
 #include <vector>
 
+#ifdef _OPENMP
+#include <omp.h>
+#include <parallel/algorithm>
+#endif
+
 #include "../../include/semk.h"
 
 extern void semk_set_error(const std::string &msg);  // semk_api.cu
@@ -44,11 +49,53 @@ extern "C" int semk_scratch_row_stride(int n1, int elems_per_patch) {
   return ((n1 * elems_per_patch - 1 + 15) & ~15) + 1;  // == scratch_row_stride (semk_apply.cu)
 }
 
+namespace {
+template <class It, class Cmp>
+void semk_plan_sort(It first, It last, int threads, Cmp cmp) {
+#if defined(_OPENMP) && defined(_PARALLEL_ALGORITHM)
+  if (threads > 1 && last - first > (1 << 16)) {
+    const int before = omp_get_max_threads();
+    omp_set_num_threads(threads);
+    __gnu_parallel::sort(first, last, cmp);
+    omp_set_num_threads(before);
+    return;
+  }
+#endif
+  (void)threads;
+  std::sort(first, last, cmp);
+}
+
+// threads of the per-patch passes: the caller's request, else what OpenMP would use
+int plan_threads(int requested) {
+#ifdef _OPENMP
+  int t = requested > 0 ? requested : omp_get_max_threads();
+  return t < 1 ? 1 : (t > 256 ? 256 : t);
+#else
+  (void)requested;
+  return 1;
+#endif
+}
+}  // namespace
+
 extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, const uint32_t *l2g,
                                     const int64_t *elem_order, int64_t n_order,
                                     int elems_per_patch, const uint8_t *dirichlet,
                                     semk_hostplan **out) {
+  return semk_hostplan_create_mt(n1, n_elem, n_nodes, l2g, elem_order, n_order, elems_per_patch,
+                                 dirichlet, 0, out);
+}
+
+// The per-patch passes (node lists, index tables, device blocks, inverse tables) run on
+// `n_threads` threads; every table is byte-identical to the single-threaded build (patches
+// are independent once the private / shared split is known; offsets come from prefix sums).
+extern "C" int semk_hostplan_create_mt(int n1, int64_t n_elem, int64_t n_nodes,
+                                       const uint32_t *l2g, const int64_t *elem_order,
+                                       int64_t n_order, int elems_per_patch,
+                                       const uint8_t *dirichlet, int n_threads,
+                                       semk_hostplan **out) {
   if (!out) return SEMK_ERR_INVALID;
+  const int T = plan_threads(n_threads);
+  (void)T;
   *out = nullptr;
   if (n1 < 2 || n1 > SEMK_MAX_N1) {
     semk_set_error("semk_hostplan_create: n1 must be in [2, 17]");
@@ -132,7 +179,9 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       }
     }
 
-    // pass 1: which nodes are touched by more than one patch
+    // pass 1: which nodes are touched by more than one patch (serial: the sweep is bound by
+    // first-touching its two n_nodes-sized arrays; a compare-and-swap version on 8 threads
+    // was no faster)
     std::vector<int32_t> first_patch(n_nodes, -1);
     std::vector<uint8_t> multi(n_nodes, 0);  // 0 private, 1 shared (interface slots)
     for (int64_t p = 0; p < n_patch; ++p) {
@@ -149,111 +198,204 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         }
       }
     }
+    std::vector<int32_t>().swap(first_patch);
 
-    // shared node list (ascending id) and slot counts
+    // shared node list (ascending id) and slot counts: count per block of nodes, prefix,
+    // fill
     std::vector<int32_t> shared_index(n_nodes, -1);
-    for (int64_t g = 0; g < n_nodes; ++g)
-      if (multi[g] == 1) {
-        shared_index[g] = (int32_t)P->shared_node.size();
-        uint32_t v = (uint32_t)g | SEMK_NODE_SHARED;
-        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
-        P->shared_node.push_back(v);
+    {
+      const int64_t kBlk = 1 << 16;
+      const int64_t n_blk = (n_nodes + kBlk - 1) / kBlk;
+      std::vector<int64_t> first_of(n_blk + 1, 0);
+#pragma omp parallel for num_threads(T) schedule(static)
+      for (int64_t b = 0; b < n_blk; ++b) {
+        int64_t c = 0;
+        const int64_t g1 = std::min<int64_t>((b + 1) * kBlk, n_nodes);
+        for (int64_t g = b * kBlk; g < g1; ++g) c += multi[g];
+        first_of[b + 1] = c;
       }
+      for (int64_t b = 0; b < n_blk; ++b) first_of[b + 1] += first_of[b];
+      if (first_of[n_blk] > INT32_MAX) {
+        delete P;
+        semk_set_error("semk_hostplan_create: shared node count overflows int32");
+        return SEMK_ERR_UNSUPPORTED;
+      }
+      P->shared_node.resize((size_t)first_of[n_blk]);
+#pragma omp parallel for num_threads(T) schedule(static)
+      for (int64_t b = 0; b < n_blk; ++b) {
+        int64_t i = first_of[b];
+        const int64_t g1 = std::min<int64_t>((b + 1) * kBlk, n_nodes);
+        for (int64_t g = b * kBlk; g < g1; ++g)
+          if (multi[g] == 1) {
+            shared_index[g] = (int32_t)i;
+            uint32_t v = (uint32_t)g | SEMK_NODE_SHARED;
+            if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
+            P->shared_node[(size_t)i++] = v;
+          }
+      }
+    }
     const int64_t n_shared = (int64_t)P->shared_node.size();
     P->shared_ptr.assign(n_shared + 1, 0);
 
-    // pass 2: per-patch tables
+    // pass 2: per-patch tables, one sweep.  Every thread takes a CONTIGUOUS range of patches
+    // and appends their node lists / interface-slot owners to its own buffers; the index
+    // tables have a fixed stride and are written in place.  Offsets then come from prefix
+    // sums over the patches and every thread's buffer is copied to its final position (it is
+    // exactly the final sub-array of its patch range).
     P->patch_node_ptr.assign(n_patch + 1, 0);
     P->patch_npriv.assign(n_patch, 0);
     P->patch_nnodes.assign(n_patch, 0);
     P->patch_slot_base.assign(n_patch, 0);
     P->eloc.assign((size_t)n_patch * ES, 0);
-    std::vector<int32_t> local_of(n_nodes, -1);   // scratch: global -> patch-local
-    std::vector<uint32_t> priv, shar;
-    std::vector<std::pair<int32_t, int32_t>> slot_pairs;  // (shared index, slot)
-    int64_t max_patch_nodes = 0, n_slots = 0;
-    for (int64_t p = 0; p < n_patch; ++p) {
-      const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_order);
-      priv.clear();
-      shar.clear();
-      for (int64_t s = s0; s < s1; ++s) {
-        if (P->elem_of_slot[s] < 0) continue;
-        const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
-        for (int k = 0; k < NN; ++k) {
-          const uint32_t g = row[k];
-          if (local_of[g] == -1) {
-            local_of[g] = -2;  // mark as collected
-            if (multi[g] == 0)
-              priv.push_back(g);
-            else
-              shar.push_back(g);
+    // global node id -> patch-local index, for one patch at a time (open addressing; the
+    // single-threaded build used an n_nodes-sized scratch array instead)
+    struct NodeMap {
+      std::vector<uint32_t> key;
+      std::vector<int32_t> val;
+      std::vector<uint32_t> used;
+      uint32_t mask = 0;
+      int shift = 0;
+      explicit NodeMap(size_t n_max) {
+        size_t cap = 16;
+        int bits = 4;
+        while (cap < 2 * n_max) cap <<= 1, ++bits;
+        key.assign(cap, 0xffffffffu);
+        val.assign(cap, -1);
+        mask = (uint32_t)(cap - 1);
+        shift = 32 - bits;
+      }
+      // slot of g, inserted (val = -1) if absent; *fresh tells which
+      uint32_t slot(uint32_t g, bool *fresh) {
+        uint32_t i = (g * 2654435761u) >> shift;
+        for (;; i = (i + 1) & mask) {
+          if (key[i] == g) return *fresh = false, i;
+          if (key[i] == 0xffffffffu) {
+            key[i] = g;
+            used.push_back(i);
+            return *fresh = true, i;
           }
         }
       }
-      std::sort(priv.begin(), priv.end());
-      std::sort(shar.begin(), shar.end());
-      // node list order: [private | shared]; the patch writes the private entries to the
-      // result vector itself
-      const int32_t np = (int32_t)priv.size(), ns = (int32_t)shar.size();
-      P->patch_npriv[p] = np;
-      P->patch_slot_base[p] = (int32_t)n_slots;
-      for (int32_t k = 0; k < np; ++k) {
-        const uint32_t g = priv[k];
-        local_of[g] = k;
-        uint32_t v = g;
-        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
-        P->pnode.push_back(v);
+      void clear() {
+        for (uint32_t i : used) key[i] = 0xffffffffu, val[i] = -1;
+        used.clear();
       }
-      for (int32_t k = 0; k < ns; ++k) {
-        const uint32_t g = shar[k];
-        local_of[g] = np + k;
-        uint32_t v = g | SEMK_NODE_SHARED;
-        if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
-        P->pnode.push_back(v);
-        slot_pairs.emplace_back(shared_index[g], (int32_t)(n_slots + k));
-        P->shared_ptr[shared_index[g] + 1] += 1;
-      }
-      n_slots += ns;
-      if (n_slots > INT32_MAX) {
-        delete P;
-        semk_set_error("semk_hostplan_create: interface slot count overflows int32");
-        return SEMK_ERR_UNSUPPORTED;
-      }
-      // pad to a multiple of 4 entries: every patch's list starts 16-byte aligned (TMA)
-      while (P->pnode.size() & 3u) P->pnode.push_back(0xffffffffu);
-      P->patch_node_ptr[p + 1] = (int32_t)P->pnode.size();
-      P->patch_nnodes[p] = np + ns;
-      max_patch_nodes = std::max<int64_t>(max_patch_nodes, np + ns);
-
-      // element-local index table (empty slots keep index 0: a valid node of the patch;
-      // their geometric factors are zero, so they contribute exact zeros)
-      for (int64_t s = s0; s < s1; ++s) {
-        if (P->elem_of_slot[s] < 0) continue;
-        const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
-        uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
-        const int le = (int)(s - s0);
-        for (int k = 0; k < NN; ++k) {
-          const int m = k / n1, t = k - m * n1;
-          eb[((size_t)m * PE + le) * n1 + t] = (uint16_t)local_of[row[k]];
+    };
+    std::vector<std::vector<uint32_t>> pnode_of(T);       // per thread: node lists, padded
+    std::vector<std::vector<int32_t>> shared_of(T);       // per thread: shared index per slot
+    std::vector<int64_t> range_of(T + 1, n_patch);
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+      const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+      const int tid = 0, nt = 1;
+#endif
+      const int64_t p0 = n_patch * tid / nt, p1 = n_patch * (tid + 1) / nt;
+      range_of[tid] = p0;
+      std::vector<uint32_t> &pn = pnode_of[tid];
+      std::vector<int32_t> &so = shared_of[tid];
+      NodeMap map((size_t)PE * NN);
+      std::vector<uint32_t> priv, shar;
+      bool fresh = false;
+      for (int64_t p = p0; p < p1; ++p) {
+        const int64_t s0 = p * PE, s1 = std::min<int64_t>(s0 + PE, n_order);
+        priv.clear();
+        shar.clear();
+        for (int64_t s = s0; s < s1; ++s) {
+          if (P->elem_of_slot[s] < 0) continue;
+          const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
+          for (int k = 0; k < NN; ++k) {
+            const uint32_t g = row[k];
+            map.slot(g, &fresh);
+            if (fresh) (multi[g] == 0 ? priv : shar).push_back(g);
+          }
         }
+        std::sort(priv.begin(), priv.end());
+        std::sort(shar.begin(), shar.end());
+        // node list order: [private | shared], each ascending; the patch writes the private
+        // entries to the result vector itself
+        const int32_t np = (int32_t)priv.size(), ns = (int32_t)shar.size();
+        P->patch_npriv[p] = np;
+        P->patch_nnodes[p] = np + ns;
+        for (int32_t k = 0; k < np; ++k) {
+          const uint32_t g = priv[k];
+          map.val[map.slot(g, &fresh)] = k;
+          pn.push_back((dirichlet && dirichlet[g]) ? (g | SEMK_NODE_DIRICHLET) : g);
+        }
+        for (int32_t k = 0; k < ns; ++k) {
+          const uint32_t g = shar[k];
+          map.val[map.slot(g, &fresh)] = np + k;
+          uint32_t v = g | SEMK_NODE_SHARED;
+          if (dirichlet && dirichlet[g]) v |= SEMK_NODE_DIRICHLET;
+          pn.push_back(v);
+          so.push_back(shared_index[g]);
+        }
+        // pad to a multiple of 4 entries: every patch's list starts 16-byte aligned (TMA)
+        while (pn.size() & 3u) pn.push_back(0xffffffffu);
+        // element-local index table (empty slots keep index 0: a valid node of the patch;
+        // their geometric factors are zero, so they contribute exact zeros)
+        uint16_t *eb = P->eloc.data() + (size_t)p * ES;  // this patch's [m][le][t] table
+        for (int64_t s = s0; s < s1; ++s) {
+          if (P->elem_of_slot[s] < 0) continue;
+          const uint32_t *row = l2g + P->elem_of_slot[s] * NN;
+          const int le = (int)(s - s0);
+          for (int k = 0; k < NN; ++k) {
+            const int m = k / n1, t = k - m * n1;
+            eb[((size_t)m * PE + le) * n1 + t] = (uint16_t)map.val[map.slot(row[k], &fresh)];
+          }
+        }
+        map.clear();
       }
-      // reset scratch
-      for (uint32_t g : priv) local_of[g] = -1;
-      for (uint32_t g : shar) local_of[g] = -1;
     }
-    if ((int64_t)P->pnode.size() > INT32_MAX) {
-      delete P;
-      semk_set_error("semk_hostplan_create: patch node table overflows int32");
-      return SEMK_ERR_UNSUPPORTED;
+    int64_t max_patch_nodes = 0, n_slots = 0;
+    {
+      int64_t ptr = 0;
+      for (int64_t p = 0; p < n_patch; ++p) {
+        const int64_t nn = P->patch_nnodes[p], ns = nn - P->patch_npriv[p];
+        P->patch_slot_base[p] = (int32_t)n_slots;
+        n_slots += ns;
+        if (n_slots > INT32_MAX) {
+          delete P;
+          semk_set_error("semk_hostplan_create: interface slot count overflows int32");
+          return SEMK_ERR_UNSUPPORTED;
+        }
+        ptr += (nn + 3) & ~(int64_t)3;
+        if (ptr > INT32_MAX) {
+          delete P;
+          semk_set_error("semk_hostplan_create: patch node table overflows int32");
+          return SEMK_ERR_UNSUPPORTED;
+        }
+        P->patch_node_ptr[p + 1] = (int32_t)ptr;
+        max_patch_nodes = std::max<int64_t>(max_patch_nodes, nn);
+      }
+      P->pnode.resize((size_t)ptr);
+    }
+    std::vector<int32_t> shared_of_slot(n_slots);  // shared index of the node behind every slot
+    for (int t = 0; t < T; ++t) {
+      if (range_of[t] >= n_patch) continue;
+      const int64_t p0 = range_of[t];
+      if (!pnode_of[t].empty())
+        std::memcpy(P->pnode.data() + P->patch_node_ptr[p0], pnode_of[t].data(),
+                    pnode_of[t].size() * sizeof(uint32_t));
+      if (!shared_of[t].empty())
+        std::memcpy(shared_of_slot.data() + P->patch_slot_base[p0], shared_of[t].data(),
+                    shared_of[t].size() * sizeof(int32_t));
+      std::vector<uint32_t>().swap(pnode_of[t]);
+      std::vector<int32_t>().swap(shared_of[t]);
     }
 
-    // CSR of interface slots per shared node (slots in ascending patch order)
+    // CSR of interface slots per shared node (slots in ascending patch order = ascending
+    // slot index)
+    for (int64_t sl = 0; sl < n_slots; ++sl) P->shared_ptr[shared_of_slot[sl] + 1] += 1;
     for (int64_t i = 0; i < n_shared; ++i) P->shared_ptr[i + 1] += P->shared_ptr[i];
     P->shared_slot.assign(n_slots, 0);
     {
       std::vector<int32_t> fill(P->shared_ptr.begin(), P->shared_ptr.end() - 1);
-      for (const auto &pr : slot_pairs) P->shared_slot[fill[pr.first]++] = pr.second;
+      for (int64_t sl = 0; sl < n_slots; ++sl)
+        P->shared_slot[fill[shared_of_slot[sl]]++] = (int32_t)sl;
     }
+    std::vector<int32_t>().swap(shared_of_slot);
 
     // Device slots are PATCH-ordered: patch p writes the partial sums of its shared nodes
     // to the contiguous run [patch_slot_base[p], +n shared) (coalesced stores).
@@ -290,7 +432,9 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
       }
       std::vector<int32_t> ord(pairs.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int32_t)i;
-      std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+      // (a strict total order -- slot numbers are unique -- so any correct sort, parallel or
+      // not, gives the same sequence)
+      semk_plan_sort(ord.begin(), ord.end(), T, [&](int32_t x, int32_t y) {
         // higher patch first: the chunks that are complete once patches [0, P) have run
         // form a prefix of the table (staged host apply)
         const Pair &a = pairs[x], &b = pairs[y];
@@ -424,11 +568,21 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
         for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
         return h;
       };
-      std::unordered_multimap<uint64_t, int32_t> pn_seen, el_seen, inv_seen;
-      std::vector<uint32_t> pblk(pn_stride);
-      std::vector<uint16_t> eblk(el_stride), iblk(inv_stride);
-      std::vector<int32_t> fill(max_patch_nodes, 0);
-      for (int64_t p = 0; p < n_patch; ++p) {
+      struct Scratch {
+        std::vector<uint32_t> pblk;
+        std::vector<uint16_t> eblk, iblk;
+        std::vector<int32_t> fill;
+      };
+      auto make_scratch = [&]() {
+        Scratch w;
+        w.pblk.resize(pn_stride);
+        w.eblk.resize(el_stride);
+        w.iblk.resize(inv_stride);
+        w.fill.resize(max_patch_nodes);
+        return w;
+      };
+      // the three device blocks of patch p (relative node list, index table, inverse table)
+      auto gen_blocks = [&](int64_t p, Scratch &w, uint32_t *base_out, uint32_t *top_out) {
         const int32_t nn = P->patch_nnodes[p];
         const uint32_t *src = P->pnode.data() + P->patch_node_ptr[p];
         uint32_t base = SEMK_NODE_ID_MASK, top = 0;
@@ -437,50 +591,114 @@ extern "C" int semk_hostplan_create(int n1, int64_t n_elem, int64_t n_nodes, con
           top = std::max(top, src[k] & SEMK_NODE_ID_MASK);
         }
         if (nn == 0) base = 0;
-        P->patch_maxnode.push_back(top);
-        std::fill(pblk.begin(), pblk.end(), 0xffffffffu);
+        std::fill(w.pblk.begin(), w.pblk.end(), 0xffffffffu);
         for (int32_t k = 0; k < nn; ++k)
-          pblk[k] = ((src[k] & SEMK_NODE_ID_MASK) - base) | (src[k] & ~SEMK_NODE_ID_MASK);
-        std::fill(eblk.begin(), eblk.end(), (uint16_t)0);
+          w.pblk[k] = ((src[k] & SEMK_NODE_ID_MASK) - base) | (src[k] & ~SEMK_NODE_ID_MASK);
+        std::fill(w.eblk.begin(), w.eblk.end(), (uint16_t)0);
         std::copy(P->eloc.begin() + (size_t)p * ES, P->eloc.begin() + (size_t)p * ES + (size_t)NN * PE,
-                  eblk.begin());
-
-        auto find_or_add = [&](auto &seen, auto &pool, const auto &blk, int64_t stride) {
-          const size_t bytes = (size_t)stride * sizeof(blk[0]);
-          const uint64_t h = hash_bytes(blk.data(), bytes);
-          auto range = seen.equal_range(h);
-          for (auto it = range.first; it != range.second; ++it)
-            if (std::memcmp(pool.data() + (size_t)it->second * stride, blk.data(), bytes) == 0)
-              return it->second;
-          const int32_t idx = (int32_t)(pool.size() / (size_t)stride);
-          pool.insert(pool.end(), blk.begin(), blk.end());
-          seen.emplace(h, idx);
-          return idx;
-        };
-        std::fill(iblk.begin(), iblk.end(), (uint16_t)0xffff);
-        std::fill(fill.begin(), fill.end(), 0);
-        {
-          const int64_t live = std::min<int64_t>(PE, n_order - p * PE);
-          for (int64_t le = 0; le < live; ++le) {    // ascending element slot: fixed sum order
-            if (P->elem_of_slot[p * PE + le] < 0) continue;
-            for (int m = 0; m < n1; ++m)
-              for (int t = 0; t < n1; ++t) {
-                const int32_t loc = eblk[((size_t)m * PE + le) * n1 + t];
-                iblk[(size_t)loc * inv_width + fill[loc]++] = (uint16_t)(m * RS + le * n1 + t);
-              }
-          }
+                  w.eblk.begin());
+        std::fill(w.iblk.begin(), w.iblk.end(), (uint16_t)0xffff);
+        std::fill(w.fill.begin(), w.fill.end(), 0);
+        const int64_t live = std::min<int64_t>(PE, n_order - p * PE);
+        for (int64_t le = 0; le < live; ++le) {    // ascending element slot: fixed sum order
+          if (P->elem_of_slot[p * PE + le] < 0) continue;
+          for (int m = 0; m < n1; ++m)
+            for (int t = 0; t < n1; ++t) {
+              const int32_t loc = w.eblk[((size_t)m * PE + le) * n1 + t];
+              w.iblk[(size_t)loc * inv_width + w.fill[loc]++] = (uint16_t)(m * RS + le * n1 + t);
+            }
         }
-        const int32_t pi = find_or_add(pn_seen, P->pnblk, pblk, pn_stride);
-        const int32_t ei = find_or_add(el_seen, P->elblk, eblk, el_stride);
-        const int32_t ii = find_or_add(inv_seen, P->invblk, iblk, inv_stride);
+        if (base_out) *base_out = base;
+        if (top_out) *top_out = top;
+      };
+      const size_t pn_bytes = (size_t)pn_stride * sizeof(uint32_t);
+      const size_t el_bytes = (size_t)el_stride * sizeof(uint16_t);
+      const size_t inv_bytes = (size_t)inv_stride * sizeof(uint16_t);
+      P->patch_maxnode.assign(n_patch, 0);
+      // Deduplication with exact comparison, in two levels.  Every thread takes a CONTIGUOUS
+      // range of patches and keeps its own pool of distinct blocks, numbered in order of first
+      // appearance (hash + memcmp against its candidates, as a single-threaded build would).
+      // The pools are then merged in thread order = patch order, which numbers the global
+      // blocks in order of first appearance over all patches -- the numbering of the
+      // single-threaded build -- and the headers are renumbered.
+      struct Pool {
+        std::vector<uint32_t> pn;
+        std::vector<uint16_t> el, inv;
+        std::unordered_multimap<uint64_t, int32_t> pn_seen, el_seen, inv_seen;
+        std::vector<uint64_t> pn_hash, el_hash, inv_hash;  // hash of every pooled block
+      };
+      auto find_or_add = [&](auto &seen_c, auto &pool, auto &pool_hash, const auto *blk,
+                             int64_t stride, uint64_t hv) {
+        const size_t bytes = (size_t)stride * sizeof(blk[0]);
+        auto range = seen_c.equal_range(hv);
+        for (auto it = range.first; it != range.second; ++it)
+          if (std::memcmp(pool.data() + (size_t)it->second * stride, blk, bytes) == 0)
+            return it->second;
+        const int32_t idx = (int32_t)(pool.size() / (size_t)stride);
+        pool.insert(pool.end(), blk, blk + stride);
+        pool_hash.push_back(hv);
+        seen_c.emplace(hv, idx);
+        return idx;
+      };
+      std::vector<Pool> pools(T);
+      std::vector<int64_t> range_begin(T + 1, n_patch);
+#pragma omp parallel num_threads(T)
+      {
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        const int tid = 0, nt = 1;
+#endif
+        const int64_t p0 = n_patch * tid / nt, p1 = n_patch * (tid + 1) / nt;
+        range_begin[tid] = p0;
+        Pool &Q = pools[tid];
+        Scratch w = make_scratch();
+        for (int64_t p = p0; p < p1; ++p) {
+          uint32_t base = 0, top = 0;
+          gen_blocks(p, w, &base, &top);
+          P->patch_maxnode[p] = top;
+          uint32_t *h = P->patch_hdr.data() + (size_t)p * 8;
+          h[0] = (uint32_t)P->patch_nnodes[p];
+          h[1] = (uint32_t)P->patch_npriv[p];
+          h[2] = (uint32_t)P->patch_slot_base[p];
+          h[4] = base;
+          // (thread-local block numbers for now)
+          h[5] = (uint32_t)find_or_add(Q.pn_seen, Q.pn, Q.pn_hash, w.pblk.data(), pn_stride,
+                                       hash_bytes(w.pblk.data(), pn_bytes));
+          h[6] = (uint32_t)find_or_add(Q.el_seen, Q.el, Q.el_hash, w.eblk.data(), el_stride,
+                                       hash_bytes(w.eblk.data(), el_bytes));
+          h[7] = (uint32_t)find_or_add(Q.inv_seen, Q.inv, Q.inv_hash, w.iblk.data(), inv_stride,
+                                       hash_bytes(w.iblk.data(), inv_bytes));
+        }
+      }
+      // merge: global number of every thread-local block
+      std::vector<std::vector<int32_t>> map_pn(T), map_el(T), map_inv(T);
+      {
+        Pool G;  // only the `seen` maps and hash lists are used; the blocks go to P->...
+        for (int t = 0; t < T; ++t) {
+          const Pool &Q = pools[t];
+          for (size_t i = 0; i < Q.pn_hash.size(); ++i)
+            map_pn[t].push_back(find_or_add(G.pn_seen, P->pnblk, G.pn_hash,
+                                            Q.pn.data() + i * (size_t)pn_stride, pn_stride,
+                                            Q.pn_hash[i]));
+          for (size_t i = 0; i < Q.el_hash.size(); ++i)
+            map_el[t].push_back(find_or_add(G.el_seen, P->elblk, G.el_hash,
+                                            Q.el.data() + i * (size_t)el_stride, el_stride,
+                                            Q.el_hash[i]));
+          for (size_t i = 0; i < Q.inv_hash.size(); ++i)
+            map_inv[t].push_back(find_or_add(G.inv_seen, P->invblk, G.inv_hash,
+                                             Q.inv.data() + i * (size_t)inv_stride, inv_stride,
+                                             Q.inv_hash[i]));
+        }
+      }
+#pragma omp parallel for num_threads(T) schedule(static)
+      for (int64_t p = 0; p < n_patch; ++p) {
+        int t = 0;
+        while (t + 1 < T && p >= range_begin[t + 1]) ++t;
         uint32_t *h = P->patch_hdr.data() + (size_t)p * 8;
-        h[0] = (uint32_t)nn;
-        h[1] = (uint32_t)P->patch_npriv[p];
-        h[2] = (uint32_t)P->patch_slot_base[p];
-        h[4] = base;
-        h[5] = (uint32_t)pi;
-        h[6] = (uint32_t)ei;
-        h[7] = (uint32_t)ii;
+        h[5] = (uint32_t)map_pn[t][h[5]];
+        h[6] = (uint32_t)map_el[t][h[6]];
+        h[7] = (uint32_t)map_inv[t][h[7]];
       }
     }
     P->scalars[SEMK_PS_N_PN_UNIQUE] = (int64_t)(P->pnblk.size() / (size_t)pn_stride);

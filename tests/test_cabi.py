@@ -284,6 +284,34 @@ def test_hostplan_deduplicates_table_blocks():
     check_plan(l2g, n_nodes, sc, ar, pe)
 
 
+def test_hostplan_tables_do_not_depend_on_the_thread_count():
+    """semk_hostplan_create_mt: the per-patch passes run on several threads (contiguous patch
+    ranges, thread-local block pools merged in patch order); every table must be byte-identical
+    to the single-threaded build -- structured with ragged tiles, scrambled numbering with a
+    random element order, irregular vertices, and more threads than patches."""
+    rng = np.random.default_rng(8)
+    cases = []
+    for nx, ny, p, pe in ((23, 41, 4, 16), (7, 19, 8, 16), (13, 26, 3, 32), (2, 3, 5, 16)):
+        mesh = meshgen.structured_quad_mesh(nx, ny, p)
+        l2g = mesh.node_map_array().reshape(nx * ny, -1)
+        d = (rng.uniform(size=mesh.n_nodes) < 0.1).astype(np.uint8)
+        cases.append((p + 1, l2g, mesh.n_nodes, operators.default_element_order(mesh, pe), pe, d))
+    nx, ny, p = 11, 9, 3
+    l2g = meshgen.structured_node_maps(nx, ny, p).reshape(nx * ny, -1)
+    n_nodes = (nx * p + 1) * (ny * p + 1)
+    perm = rng.permutation(n_nodes).astype(np.uint32)
+    cases.append((p + 1, perm[l2g], n_nodes, rng.permutation(nx * ny), 8, None))
+    mesh = meshgen.pinwheel_mesh(7, 4, rings=3)
+    cases.append((5, mesh.node_map_array().reshape(mesh.n_cells, -1), mesh.n_nodes, None, 8, None))
+    for n1, l2g, n_nodes, order, pe, d in cases:
+        sc1, ar1 = _lib.hostplan(n1, l2g, n_nodes, order, pe, d, threads=1)
+        for t in (2, 3, 8):
+            sc, ar = _lib.hostplan(n1, l2g, n_nodes, order, pe, d, threads=t)
+            assert sc == sc1
+            for k in ar1:
+                assert np.array_equal(ar[k], ar1[k]), (k, t)
+
+
 def test_hostplan_scrambled_numbering_and_order():
     """Arbitrary node numbering (as after RCM) and a random element order."""
     nx, ny, p, pe = 6, 5, 3, 8
