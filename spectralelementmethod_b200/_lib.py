@@ -274,6 +274,9 @@ def load():
 def host_threads():
     """Threads for the host-side table helpers: all processors, shared between the ranks of
     one box (torchrun exports OMP_NUM_THREADS=1, which is not what set-up code wants)."""
+    forced = os.environ.get("SEMK_HOST_THREADS")
+    if forced:
+        return max(1, int(forced))
     n = os.cpu_count() or 1
     local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
     return max(1, min(64, n // max(local, 1)))

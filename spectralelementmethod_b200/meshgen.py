@@ -25,15 +25,23 @@ def lattice_coordinates(kind, nx, ny, p, bounds=(-1.0, 1.0, -1.0, 1.0)):
     'C': the same lattice displaced by s = 0.08 sin(pi X) sin(pi Y) in both
     coordinates (curved elements, boundary fixed)."""
     x0, x1, y0, y1 = bounds
-    X, Y = np.meshgrid(np.linspace(x0, x1, nx * p + 1), np.linspace(y0, y1, ny * p + 1),
-                       indexing="ij")
-    if kind == "C":
-        s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
-        X = X + s
-        Y = Y + s
-    elif kind != "S":
+    x = np.linspace(x0, x1, nx * p + 1)
+    y = np.linspace(y0, y1, ny * p + 1)
+    if kind not in ("S", "C"):
         raise ValueError("kind must be 'S' (straight) or 'C' (curved)")
-    return np.vstack([X.ravel(), Y.ravel()])
+    # written straight into the result (no meshgrid / vstack temporaries: 1 GB each at
+    # 1024 x 1024 elements, p = 8); same values bit for bit
+    out = np.empty((2, x.size * y.size))
+    X = out[0].reshape(x.size, y.size)
+    Y = out[1].reshape(x.size, y.size)
+    X[:] = x[:, None]
+    Y[:] = y[None, :]
+    if kind == "C":
+        # s = (0.08 sin(pi X)) sin(pi Y) is separable: the sines are taken on the 1-D grids
+        s = (0.08 * np.sin(np.pi * x))[:, None] * np.sin(np.pi * y)[None, :]
+        X += s
+        Y += s
+    return out
 
 
 def structured_node_maps(nx, ny, p, node_offset=0):
