@@ -310,10 +310,13 @@ def require_device():
                            "the operator engine has no CPU fallback")
 
 
-def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None, threads=None):
+def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=None, threads=None,
+             arrays=None):
     """Run the host plan builder (``threads``: for its per-patch passes; default
     ``host_threads()``; same tables for any count); returns (scalars dict, arrays dict of
-    numpy copies)."""
+    numpy copies).  ``arrays``: the SEMK_PA_* tables to copy out (default: all; the full
+    per-patch node and index tables are several hundred MB at config 2 and the device only
+    needs their deduplicated blocks)."""
     lib = load()
     l2g = np.ascontiguousarray(l2g, dtype=np.uint32).reshape(-1, n1 * n1)
     n_elem = l2g.shape[0]
@@ -337,8 +340,11 @@ def hostplan(n1, l2g, n_nodes, elem_order=None, elems_per_patch=16, dirichlet=No
                                       C.byref(handle)))
     try:
         scalars = {k: int(lib.semk_hostplan_scalar(handle, k)) for k in range(PS_COUNT)}
+        want = None if arrays is None else set(arrays)
         arrays = {}
         for k, dt in PLAN_ARRAY_DTYPES.items():
+            if want is not None and k not in want:
+                continue
             nb = _L(0)
             ptr = lib.semk_hostplan_array(handle, k, C.byref(nb))
             if nb.value:

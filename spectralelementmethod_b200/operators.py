@@ -194,7 +194,10 @@ class PoissonOperator(object):
         self._tile = tuple(tile) if tile is not None else _TILES[pe]
         self._boundary_first = bool(boundary_columns_first and not user_order and getattr(
             mesh, "_structured_shape", None) is not None)
-        sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet)
+        sc, ar = _lib.hostplan(n1, l2g, self.n_nodes, elem_order, pe, dirichlet, arrays=(
+            _lib.PA_PNBLK, _lib.PA_PATCH_HDR, _lib.PA_SHARED_REC, _lib.PA_SHARED_EXT,
+            _lib.PA_SHARED_CHUNK, _lib.PA_ELBLK, _lib.PA_INVBLK, _lib.PA_ELEM_OF_SLOT,
+            _lib.PA_PATCH_MAXNODE, _lib.PA_CHUNK_MAXPATCH, _lib.PA_REC_MAXPATCH))
         # engine slots = elements + empty padding slots (-1 entries of the order)
         self.n_order = int(ar[_lib.PA_ELEM_OF_SLOT].size)
         # thread mapping of the apply kernel: "column" (one thread per element column) or
