@@ -372,6 +372,7 @@ extern "C" int semk_hostplan_create_mt(int n1, int64_t n_elem, int64_t n_nodes,
       P->pnode.resize((size_t)ptr);
     }
     std::vector<int32_t> shared_of_slot(n_slots);  // shared index of the node behind every slot
+#pragma omp parallel for num_threads(T) schedule(static, 1)
     for (int t = 0; t < T; ++t) {
       if (range_of[t] >= n_patch) continue;
       const int64_t p0 = range_of[t];
@@ -545,19 +546,25 @@ extern "C" int semk_hostplan_create_mt(int n1, int64_t n_elem, int64_t n_nodes,
     }
     int64_t inv_width = 4;
     {
-      std::vector<int32_t> cnt(max_patch_nodes, 0);
-      for (int64_t p = 0; p < n_patch; ++p) {
-        const uint16_t *eb = P->eloc.data() + (size_t)p * ES;
-        const int64_t live = std::min<int64_t>(PE, n_order - p * PE);
-        std::fill(cnt.begin(), cnt.end(), 0);
-        for (int m = 0; m < n1; ++m)
-          for (int64_t le = 0; le < live; ++le)
-            for (int t = 0; t < n1; ++t) {
-              if (P->elem_of_slot[p * PE + le] < 0) continue;
-              const int32_t c = ++cnt[eb[((size_t)m * PE + le) * n1 + t]];
-              if (c > inv_width) inv_width = (c + 3) & ~3;
-            }
+      int64_t max_count = 0;  // largest number of element-local entries meeting in one patch node
+#pragma omp parallel num_threads(T) reduction(max : max_count)
+      {
+        std::vector<int32_t> cnt(max_patch_nodes, 0);
+#pragma omp for schedule(static)
+        for (int64_t p = 0; p < n_patch; ++p) {
+          const uint16_t *eb = P->eloc.data() + (size_t)p * ES;
+          const int64_t live = std::min<int64_t>(PE, n_order - p * PE);
+          std::fill(cnt.begin(), cnt.end(), 0);
+          for (int m = 0; m < n1; ++m)
+            for (int64_t le = 0; le < live; ++le)
+              for (int t = 0; t < n1; ++t) {
+                if (P->elem_of_slot[p * PE + le] < 0) continue;
+                const int32_t c = ++cnt[eb[((size_t)m * PE + le) * n1 + t]];
+                if (c > max_count) max_count = c;
+              }
+        }
       }
+      if (max_count > inv_width) inv_width = (max_count + 3) & ~(int64_t)3;
     }
     const int64_t inv_stride = pn_stride * inv_width;  // uint16 entries per block
     P->patch_hdr.assign((size_t)n_patch * 8, 0u);
