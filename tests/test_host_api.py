@@ -369,3 +369,22 @@ def test_multithreaded_host_helpers_are_bit_exact():
         finally:
             discrete.DOFManagerSC._fast_static_condensation = orig
         assert np.array_equal(f2.mesh.node_map_array(), s2.mesh.node_map_array())
+
+
+def test_lattice_coordinates_equal_the_meshgrid_recipe_bit_for_bit():
+    """meshgen.lattice_coordinates writes the lattice in place (no meshgrid / vstack temporaries,
+    the curved displacement from 1-D sines); the values must be those of the plain recipe of
+    SURVEY appendix B: X, Y = meshgrid(...); s = 0.08 sin(pi X) sin(pi Y); X + s, Y + s."""
+    for kind in "SC":
+        for nx, ny, p, b in ((5, 7, 3, (-1.0, 1.0, -1.0, 1.0)), (16, 9, 8, (-1.0, 3.0, -1.0, 1.0)),
+                             (4, 6, 10, (0.0, 2.5, -0.3, 0.9))):
+            X, Y = np.meshgrid(np.linspace(b[0], b[1], nx * p + 1), np.linspace(b[2], b[3], ny * p + 1),
+                               indexing="ij")
+            if kind == "C":
+                s = 0.08 * np.sin(np.pi * X) * np.sin(np.pi * Y)
+                X, Y = X + s, Y + s
+            want = np.vstack([X.ravel(), Y.ravel()])
+            got = meshgen.lattice_coordinates(kind, nx, ny, p, b)
+            assert got.shape == want.shape and np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        meshgen.lattice_coordinates("X", 2, 2, 2)
